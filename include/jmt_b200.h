@@ -1,0 +1,221 @@
+/*
+ * jmt_b200.h -- C-ABI of the B200-native (sm_100a) engine for the Joint Multimodal Transformer
+ * data-parallel hot path: fusion forward/backward, TCN, CCC loss/metric.
+ *
+ * The reference (PoloWlg/Joint-Multimodal-Transformer-6th-ABAW) has no FFI: its boundary is the
+ * Python nn.Module API.  The drop-in modules in
+ * joint-multimodal-transformer-6th-abaw_b200/ keep that API and drive this library through
+ * ctypes; every entry point below states which reference computation (file:line) it replaces.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers on the current device unless
+ *     stated otherwise; `stream` is a cudaStream_t passed as void*.
+ *   - functions never allocate, never synchronise, never throw; they return JMT_OK (0) or a
+ *     negative jmt_status.  jmt_last_error() gives a thread-local message for the last failure.
+ *   - thread-safe / re-entrant: no global mutable state except an immutable per-process table of
+ *     driver entry points and per-function attribute flags.
+ *   - dtype codes: JMT_F32 = 0, JMT_BF16 = 1.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point returns
+ *     JMT_ERR_CUDA.
+ */
+#ifndef JMT_B200_H_
+#define JMT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JMT_ABI_VERSION 1
+
+typedef enum {
+  JMT_OK = 0,
+  JMT_ERR_INVALID = -1,   /* bad argument (shape, alignment, enum) */
+  JMT_ERR_CUDA = -2,      /* CUDA runtime / driver error (launch, tensor-map encode, no device) */
+  JMT_ERR_UNSUPPORTED = -3
+} jmt_status;
+
+enum { JMT_F32 = 0, JMT_BF16 = 1 };
+enum { JMT_ACT_NONE = 0, JMT_ACT_RELU = 1, JMT_ACT_LEAKY_RELU = 2 };
+enum { JMT_MAJOR_K = 0, JMT_MAJOR_MN = 1 };
+enum { JMT_STORE = 0, JMT_ACCUMULATE = 1, JMT_ATOMIC_ADD = 2 };
+/* CCC closed forms */
+enum {
+  JMT_CCC_METRIC = 0,      /* EvaluationMetrics/cccmetric.py:4-21  (population std)            */
+  JMT_CCC_LOSS_LIVE = 1,   /* losses/loss.py:18-32, digitize_num==1 (unbiased std, eps in rho)  */
+  JMT_CCC_LOSS_MASKED = 2, /* losses/CCCLoss.py:12-43 (y != ignore mask, pre-mask N divisor)    */
+  JMT_CCC_NUMPY = 3        /* cccmetric.py:41-56 (np.cov N-1 over np.var N, +1e-8)              */
+};
+
+int jmt_abi_version(void);
+const char* jmt_last_error(void);
+/* number of kernels launched by this library in the calling process since load (all threads) */
+int64_t jmt_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------ *
+ * GEMM family.  One descriptor drives both implementations:
+ *   jmt_gemm_bf16 : TMA-fed tcgen05.mma (kind::f16, bf16 operands, fp32 accumulate in TMEM),
+ *                   persistent warp-specialised kernel.  a/b are bf16.
+ *   jmt_gemm_f32  : fp32 FFMA tiled kernel (the high-precision parity mode).  a/b are fp32.
+ *
+ *   D[b](m, n) (op)= act( alpha * sum_{tap} sum_{k} A[b](m + ash(tap), k) * B[b](n, tap*K + k + ...) + bias[n] )
+ *
+ * Operand addressing (elements):  K-major operand X: X(r, k) = x[batch_off + r*ld + k]
+ *                                 MN-major operand X: X(r, k) = x[batch_off + k*ld + r]
+ *   batch b = b1*nb0 + b0, batch_off = b0*bs0 + b1*bs1 (B may use strides 0,0 = shared).
+ *   `*_rows` is the number of valid rows of the 2-D matrix (m/n extent for K-major, k extent for
+ *   MN-major); rows outside [0, rows) read as zero (TMA out-of-bounds fill) -- this is how the
+ *   causal left padding of the TCN (temporal_convolutional_model.py:12-18,24-27) and ragged tile
+ *   tails are realised without materialising padding.
+ *   Taps (implicit-GEMM dilated conv): for tap j the A row index is shifted by
+ *   a_shift0 + j*a_shift_step (K-major A: shifts m; MN-major A: shifts k), the B row index by
+ *   b_shift0 + j*b_shift_step when B is MN-major, and for K-major B the k offset advances by
+ *   j*K (weights laid out (n, tap*K + k)).
+ *   reduce_batch != 0: the batch index becomes an extra reduction dimension (D is not batched).
+ *   split_k > 1 requires store_mode == JMT_ATOMIC_ADD and d_dtype == JMT_F32.
+ *
+ * Replaces: every nn.Linear / in_proj / out_proj / bmm of the fusion path
+ * (mm_multi_transformers.py:52-56,120-124,142-167,203-209; two_transformers.py:104-128;
+ * torch F.multi_head_attention_forward's addmm/bmm) and nn.Conv1d of the TCN
+ * (temporal_convolutional_model.py:24-41), forward, dgrad and wgrad.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  const void* a; const void* b; void* d;
+  const float* bias;            /* length N, nullable */
+  int32_t a_major, b_major;     /* JMT_MAJOR_* */
+  int32_t M, N, K;              /* K = reduction extent per tap (per batch) */
+  int32_t a_rows, b_rows;       /* valid rows of each operand's 2-D matrix (see above) */
+  int64_t a_ld, a_bs0, a_bs1;
+  int64_t b_ld, b_bs0, b_bs1;
+  int64_t d_ld, d_bs0, d_bs1;   /* D(m, n) = d[batch_off + m*d_ld + n] */
+  int32_t nb0, nb1;             /* batch extents (>= 1) */
+  int32_t d_dtype;              /* JMT_F32 / JMT_BF16 */
+  int32_t act;                  /* JMT_ACT_* applied after bias */
+  float alpha, slope;
+  int32_t store_mode;           /* JMT_STORE / JMT_ACCUMULATE / JMT_ATOMIC_ADD */
+  int32_t ntaps;                /* >= 1 */
+  int32_t a_shift0, a_shift_step, b_shift0, b_shift_step;
+  int32_t reduce_batch;
+  int32_t split_k;              /* >= 1 */
+} jmt_gemm_desc;
+
+int jmt_gemm_bf16(const jmt_gemm_desc* g, void* stream);
+int jmt_gemm_f32(const jmt_gemm_desc* g, void* stream);
+
+/* ------------------------------------------------------------------------------------------ *
+ * Memory-bound fused row kernels (one warp per row, warp-shuffle reductions, 16-byte accesses).
+ * `dtype` is the activation dtype of x/out tensors; statistics and parameters are fp32.
+ * ------------------------------------------------------------------------------------------ */
+/* F.normalize(x, dim=-1): two_transformers.py:118-119.  in: (rows, D) in_dtype (row pitch in_ld);
+ * out: (rows, D) out_dtype; inv_norm (rows) fp32 saved for backward (nullable). */
+int jmt_l2norm_fwd(const void* x, int in_dtype, int64_t in_ld, void* out, int out_dtype, int64_t rows,
+                   int D, float eps, float* inv_norm, void* stream);
+/* dx = r*(dy - y*(y.dy)) (r = inv_norm; rows with ||x|| < eps: dx = r*dy).  y = saved output. */
+int jmt_l2norm_bwd(const void* dy, const void* y, int dtype, const float* inv_norm, float eps,
+                   float* dx, int64_t rows, int D, void* stream);
+
+/* y = LayerNorm(x + res) * gamma + beta  (post-LN residual: mm_multi_transformers.py:62-69).
+ * res nullable.  Saves mean/rstd (rows) fp32. */
+int jmt_add_layernorm_fwd(const void* x, const void* res, const float* gamma, const float* beta, float eps,
+                          void* y, float* mean, float* rstd, int64_t rows, int D, int dtype, void* stream);
+/* dz = d(x+res); dgamma/dbeta (D) fp32 are ACCUMULATED with atomics (caller zeroes).
+ * dz_accumulate != 0: dz += result. */
+int jmt_add_layernorm_bwd(const void* dy, const void* x, const void* res, const float* gamma,
+                          const float* mean, const float* rstd, void* dz, int dz_accumulate,
+                          float* dgamma, float* dbeta, int64_t rows, int D, int dtype, void* stream);
+
+/* P = softmax(S) over the last dim (torch MHA math path, keys axis).  S fp32 (rows, s_ld),
+ * P p_dtype (rows, p_ld); columns >= cols of P are written as zero up to p_ld. */
+int jmt_softmax_fwd(const float* s, int64_t s_ld, void* p, int p_dtype, int64_t p_ld, int64_t rows, int cols,
+                    void* stream);
+/* dS = P o (dP - rowsum(dP o P)); dP fp32 (rows, dp_ld); dS ds_dtype (rows, ds_ld), pad zeroed. */
+int jmt_softmax_bwd(const void* p, int p_dtype, int64_t p_ld, const float* dp, int64_t dp_ld, void* ds,
+                    int ds_dtype, int64_t ds_ld, int64_t rows, int cols, void* stream);
+
+/* Tiny-sequence attention (L = S <= 8): Intra_modal_transformer_fusion (L=2,
+ * intra_modal_transformer_fusion.py:93-108) and the SELF_ATTEN head (L=6,
+ * mm_multi_transformers.py:173-193).  qkv: (L, N, 3E) packed projections (dtype), out: (L, N, E);
+ * one warp per (n, head), everything in registers.  probs (N*h, L, L) fp32 saved for backward. */
+int jmt_attn_small_fwd(const void* qkv, void* out, float* probs, int L, int64_t N, int E, int heads,
+                       float scale, int dtype, void* stream);
+int jmt_attn_small_bwd(const void* qkv, const void* dout, const float* probs, void* dqkv, int L, int64_t N,
+                       int E, int heads, float scale, int dtype, void* stream);
+
+/* Regressor tail: out[g][b*sb + t*st] = h[g][m,:128] . w[g] + b[g], row m = b*T + t, G <= 4 groups
+ * (two_transformers.py:104-114: Linear(128,1) of vregressor/aregressor; :146-149: Linear(128,2)),
+ * fused with squeeze and the (B,T) / (T,B) output layout.  h: hidden after ReLU (and
+ * dropout), dtype `dtype`, row pitch h_ld.  Pointer arrays are HOST arrays of device pointers. */
+int jmt_regressor_tail_fwd(int G, const void* const* h, int64_t h_ld, int dtype, const float* const* w,
+                           const float* const* b, float* const* out, int64_t M, int64_t T, int64_t sb, int64_t st,
+                           void* stream);
+/* dh[g][m,j] (+)= (h>0) * dout[g][m] * w[g][j] * scale[g]; dw[g] += sum_m dout*h; db[g] += sum_m dout
+ * (fp32 atomics; caller zeroes dw/db).  accumulate[g] != 0: add into dh[g] (hidden shared by groups). */
+int jmt_regressor_tail_bwd(int G, const void* const* h, int64_t h_ld, int dtype, const float* const* w,
+                           const float* const* dout, void* const* dh, const int* accumulate, const float* scale,
+                           float* const* dw, float* const* db, int64_t M, int64_t T, int64_t sb, int64_t st,
+                           void* stream);
+
+/* ------------------------------------------------------------------------------------------ *
+ * Elementwise / column reductions
+ * ------------------------------------------------------------------------------------------ */
+/* dx = dy * (y > 0 ? 1 : slope)   (ReLU: slope 0; LeakyReLU 0.01), in place allowed. */
+int jmt_act_bwd(const void* dy, const void* y, void* dx, int64_t n, float slope, int dtype, void* stream);
+/* out[c] += sum_r x[r*ld + c]  (bias gradients), fp32 atomics; caller zeroes. */
+int jmt_colsum(const void* x, int dtype, int64_t ld, int64_t rows, int cols, float* out, void* stream);
+/* out = cast(in) */
+int jmt_cast(const void* in, int in_dtype, void* out, int out_dtype, int64_t n, void* stream);
+/* y += a*x (same dtype) */
+int jmt_axpy(const void* x, void* y, float a, int64_t n, int dtype, void* stream);
+/* strided 2-D copy with cast: out[r*out_ld + c] = in[r*in_ld + c] */
+int jmt_copy2d(const void* in, int in_dtype, int64_t in_ld, void* out, int out_dtype, int64_t out_ld,
+               int64_t rows, int cols, void* stream);
+/* batched transpose of the two inner dims with cast: in (nb, R, C) -> out (nb, C, R)
+ * ((N,C,L) <-> channels-last (N,L,C) at the TCN boundary, I3DWSDDA.py:44) */
+int jmt_transpose(const void* in, int in_dtype, void* out, int out_dtype, int64_t nb, int R, int C, void* stream);
+/* out = LeakyReLU(a + b)  (TemporalBlock.forward, temporal_convolutional_model.py:54-57) */
+int jmt_add_act(const void* a, const void* b, void* out, int64_t n, int act, float slope, int dtype, void* stream);
+/* channel dropout (nn.Dropout2d on (N,C,L)) / element dropout with an explicit
+ * keep-mask: x (nb, L, C) channels-last; mask (nb, C) or (nb*L*C) uint8; scale = 1/(1-p). */
+int jmt_apply_mask(const void* x, const uint8_t* mask, void* out, int64_t nb, int L, int C, int per_channel,
+                   float scale, int dtype, void* stream);
+/* Philox-4x32-10 keep-mask generator: mask[i] = uniform(seed, offset+i) >= p */
+int jmt_dropout_mask(uint8_t* mask, int64_t n, float p, uint64_t seed, uint64_t offset, void* stream);
+
+/* weight_norm (legacy, dim=0): w[co,:] = g[co] * v[co,:] / ||v[co,:]||  (Cout rows of `inner`
+ * = Cin*k elements; temporal_convolutional_model.py:24-33).  Writes w re-laid out for the
+ * implicit GEMM as (Cout, k*Cin) [tap-major] in out_dtype plus its transpose-per-tap for dgrad
+ * (k*... see DESIGN.md); norm (Cout) fp32 saved. */
+int jmt_weight_norm_fwd(const float* g, const float* v, void* w_fwd, void* w_dgrad, int out_dtype,
+                        float* norm, int cout, int cin, int k, void* stream);
+/* dv, dg from dw_fwd ((Cout, k*Cin) fp32, tap-major): dg = (dw.v)/||v||, dv = g/||v|| (dw - v (dw.v)/||v||^2) */
+int jmt_weight_norm_bwd(const float* dw_fwd, const float* g, const float* v, const float* norm, float* dg,
+                        float* dv, int cout, int cin, int k, void* stream);
+
+/* ------------------------------------------------------------------------------------------ *
+ * CCC statistics: single-pass six-sum reduction (N, Sx, Sy, Sxy, Sxx, Syy) in fp64.
+ * Replaces losses/loss.py:18-32, losses/CCCLoss.py:12-43, EvaluationMetrics/cccmetric.py:4-56.
+ * ------------------------------------------------------------------------------------------ */
+/* x, y: npairs rows of n fp32 values (row pitch `stride`); sums (npairs, 6) fp64, ACCUMULATED
+ * (caller zeroes) so partial shards / ranks can be combined; use_ignore: skip y == ignore. */
+int jmt_ccc_sums(const float* x, const float* y, int64_t n, int npairs, int64_t stride, int use_ignore,
+                 float ignore, double* sums, void* stream);
+/* device-side finaliser: value[p] (fp32) = the CCC variant `kind`; coef (npairs, 4) fp64 =
+ * (c0, cx, cy, valid) such that d value / d x_i = c0 + cx*x_i + cy*y_i on non-ignored elements.
+ * n_all = pre-mask length (JMT_CCC_LOSS_MASKED). */
+int jmt_ccc_finalize(const double* sums, int npairs, int kind, double n_all, double eps, float* value,
+                     double* coef, void* stream);
+/* dx[p][i] = gout[p or 0] * (c0 + cx*x + cy*y), zero where ignored. gout: device fp32. */
+int jmt_ccc_bwd(const float* x, const float* y, int64_t n, int npairs, int64_t stride, const double* coef,
+                const float* gout, int gout_per_pair, int use_ignore, float ignore, float* dx, void* stream);
+/* the reference's only padding mask: mask[i] = (y[i] != ignore)  (losses/CCCLoss.py:19) */
+int jmt_label_mask(const float* y, int64_t n, float ignore, uint8_t* mask, void* stream);
+/* zero-left-pad copy of the collate (padSequence.py:14-21): out (rows, out_w) zero-filled, then
+ * in (rows, in_w) copied right-aligned. fp32. */
+int jmt_pad_right_align(const float* in, int64_t rows, int in_w, float* out, int out_w, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JMT_B200_H_ */

@@ -1,0 +1,421 @@
+// Elementwise / small reduction kernels of the fusion + TCN path (all HBM-bound, vectorised).
+#include "common.cuh"
+
+namespace jmt {
+
+constexpr int kEwThreads = 256;
+
+template <typename T>
+__global__ void __launch_bounds__(kEwThreads)
+act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ y, T* __restrict__ dx, int64_t n8, int64_t n, float slope) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nt = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = tid; i < n8; i += nt) {
+    Vec8<T> a, b; a.load(dy + i * 8); b.load(y + i * 8);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a.v[k] = b.v[k] > 0.f ? a.v[k] : a.v[k] * slope;
+    a.store(dx + i * 8);
+  }
+  for (int64_t i = n8 * 8 + tid; i < n; i += nt) {
+    const float g = to_f32(dy[i]);
+    dx[i] = from_f32<T>(to_f32(y[i]) > 0.f ? g : g * slope);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kEwThreads)
+add_act_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out, int64_t n8, int64_t n, int act, float slope) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nt = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = tid; i < n8; i += nt) {
+    Vec8<T> x, y; x.load(a + i * 8); y.load(b + i * 8);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x.v[k] = apply_act(x.v[k] + y.v[k], act, slope);
+    x.store(out + i * 8);
+  }
+  for (int64_t i = n8 * 8 + tid; i < n; i += nt) out[i] = from_f32<T>(apply_act(to_f32(a[i]) + to_f32(b[i]), act, slope));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kEwThreads)
+axpy_kernel(const T* __restrict__ x, T* __restrict__ y, float a, int64_t n8, int64_t n) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nt = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = tid; i < n8; i += nt) {
+    Vec8<T> u, v; u.load(x + i * 8); v.load(y + i * 8);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v.v[k] = fmaf(a, u.v[k], v.v[k]);
+    v.store(y + i * 8);
+  }
+  for (int64_t i = n8 * 8 + tid; i < n; i += nt) y[i] = from_f32<T>(fmaf(a, to_f32(x[i]), to_f32(y[i])));
+}
+
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(kEwThreads)
+copy2d_kernel(const TI* __restrict__ in, int64_t in_ld, TO* __restrict__ out, int64_t out_ld, int64_t rows, int cols, int vec) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nt = (int64_t)gridDim.x * blockDim.x;
+  if (vec) {
+    const int c8 = cols / 8;
+    for (int64_t i = tid; i < rows * c8; i += nt) {
+      const int64_t r = i / c8; const int c = (int)(i - r * c8) * 8;
+      Vec8<TI> v; v.load(in + r * in_ld + c);
+      Vec8<TO> o;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o.v[k] = v.v[k];
+      o.store(out + r * out_ld + c);
+    }
+  } else {
+    for (int64_t i = tid; i < rows * cols; i += nt) {
+      const int64_t r = i / cols; const int c = (int)(i - r * cols);
+      out[r * out_ld + c] = from_f32<TO>(to_f32(in[r * in_ld + c]));
+    }
+  }
+}
+
+// (nb, R, C) -> (nb, C, R) through a padded 32x32 shared tile (coalesced both ways)
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256)
+transpose_kernel(const TI* __restrict__ in, TO* __restrict__ out, int R, int C) {
+  __shared__ float tile[32][33];
+  const int64_t b = blockIdx.z;
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const TI* ib = in + b * (int64_t)R * C;
+  TO* ob = out + b * (int64_t)R * C;
+  for (int i = ty; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + tx;
+    tile[i][tx] = (r < R && c < C) ? to_f32(ib[(int64_t)r * C + c]) : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, r = r0 + tx;
+    if (r < R && c < C) ob[(int64_t)c * R + r] = from_f32<TO>(tile[tx][i]);
+  }
+}
+
+// out[c] += sum_r x[r*ld + c]
+template <typename T>
+__global__ void __launch_bounds__(256)
+colsum_kernel(const T* __restrict__ x, int64_t ld, int64_t rows, int cols, float* __restrict__ out) {
+  // block = 32 column-lanes x 8 row-lanes; each block owns a 32-column strip and a row slab
+  __shared__ float sh[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  float s = 0.f;
+  if (c < cols)
+    for (int64_t r = (int64_t)blockIdx.y * 8 + ty; r < rows; r += (int64_t)gridDim.y * 8) s += to_f32(x[r * ld + c]);
+  sh[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && c < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += sh[i][tx];
+    atomicAdd(out + c, t);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kEwThreads)
+apply_mask_kernel(const T* __restrict__ x, const uint8_t* __restrict__ mask, T* __restrict__ out, int64_t total, int L,
+                  int C, int per_channel, float scale) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t mi = i;
+    if (per_channel) { const int64_t b = i / ((int64_t)L * C); const int c = (int)(i % C); mi = b * C + c; }
+    out[i] = from_f32<T>(mask[mi] ? to_f32(x[i]) * scale : 0.f);
+  }
+}
+
+// Philox-4x32-10 (Salmon et al. 2011) counter-based generator
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0; key.y += W1;
+  }
+  return ctr;
+}
+
+__global__ void __launch_bounds__(kEwThreads)
+dropout_mask_kernel(uint8_t* __restrict__ mask, int64_t n, float p, uint64_t seed, uint64_t offset) {
+  const int64_t n4 = (n + 3) / 4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint64_t c = offset + (uint64_t)i;
+    const uint4 r = philox4x32_10(make_uint4((uint32_t)c, (uint32_t)(c >> 32), 0u, 0u),
+                                  make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int64_t j = i * 4 + k;
+      if (j < n) mask[j] = ((float)rr[k] * 2.3283064365386963e-10f) >= p ? 1 : 0;
+    }
+  }
+}
+
+// weight_norm: one block per output channel
+template <typename TO>
+__global__ void __launch_bounds__(256)
+weight_norm_fwd_kernel(const float* __restrict__ g, const float* __restrict__ v, TO* __restrict__ w_fwd,
+                       TO* __restrict__ w_dgrad, float* __restrict__ norm, int cout, int cin, int k) {
+  const int co = blockIdx.x;
+  const int inner = cin * k;
+  const float* vr = v + (int64_t)co * inner;
+  float ss = 0.f;
+  for (int i = threadIdx.x; i < inner; i += blockDim.x) ss = fmaf(vr[i], vr[i], ss);
+  __shared__ float sh[8];
+  ss = warp_sum(ss);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) tot += sh[i];
+  const float nrm = sqrtf(tot);
+  if (threadIdx.x == 0 && norm) norm[co] = nrm;
+  const float sc = g[co] / nrm;
+  for (int i = threadIdx.x; i < inner; i += blockDim.x) {
+    const int ci = i / k, j = i - ci * k;
+    const TO w = from_f32<TO>(vr[i] * sc);
+    w_fwd[(int64_t)co * inner + (int64_t)j * cin + ci] = w;
+    if (w_dgrad) w_dgrad[(int64_t)ci * ((int64_t)k * cout) + (int64_t)j * cout + co] = w;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+weight_norm_bwd_kernel(const float* __restrict__ dw_fwd, const float* __restrict__ g, const float* __restrict__ v,
+                       const float* __restrict__ norm, float* __restrict__ dg, float* __restrict__ dv, int cout,
+                       int cin, int k) {
+  const int co = blockIdx.x;
+  const int inner = cin * k;
+  const float* vr = v + (int64_t)co * inner;
+  const float* dwr = dw_fwd + (int64_t)co * inner;
+  float dot = 0.f;
+  for (int i = threadIdx.x; i < inner; i += blockDim.x) {
+    const int ci = i / k, j = i - ci * k;
+    dot = fmaf(dwr[(int64_t)j * cin + ci], vr[i], dot);
+  }
+  __shared__ float sh[8];
+  dot = warp_sum(dot);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = dot;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) tot += sh[i];
+  const float nrm = norm[co];
+  if (threadIdx.x == 0) dg[co] = tot / nrm;
+  const float sc = g[co] / nrm, proj = tot / (nrm * nrm);
+  for (int i = threadIdx.x; i < inner; i += blockDim.x) {
+    const int ci = i / k, j = i - ci * k;
+    dv[(int64_t)co * inner + i] = sc * (dwr[(int64_t)j * cin + ci] - vr[i] * proj);
+  }
+}
+
+// ---------------------------------------------------------------- tiny-sequence attention
+constexpr int kMaxSmallL = 8;
+
+template <typename T, int L>
+__global__ void __launch_bounds__(256)
+attn_small_fwd_kernel(const T* __restrict__ qkv, T* __restrict__ out, float* __restrict__ probs, int64_t N,
+                      int E, int heads, float scale) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w0 = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int64_t total = N * heads;
+  const int dh = E / heads;
+  const int64_t row = 3 * (int64_t)E;          // elements per (l, n) row of qkv
+  for (int64_t w = w0; w < total; w += (int64_t)gridDim.x * 8) {
+    const int64_t n = w / heads; const int h = (int)(w - n * heads);
+    const T* base = qkv + n * row + (int64_t)h * dh;
+    float p[L][L];
+    for (int i = 0; i < L; ++i) {
+      float m = -INFINITY;
+      for (int j = 0; j < L; ++j) {
+        const T* q = base + (int64_t)i * N * row;
+        const T* k = base + (int64_t)j * N * row + E;
+        float s = 0.f;
+        for (int d = lane; d < dh; d += 32) s = fmaf(to_f32(q[d]), to_f32(k[d]), s);
+        s = warp_sum(s) * scale;
+        p[i][j] = s; m = fmaxf(m, s);
+      }
+      float sum = 0.f;
+      for (int j = 0; j < L; ++j) { p[i][j] = __expf(p[i][j] - m); sum += p[i][j]; }
+      const float inv = 1.f / sum;
+      for (int j = 0; j < L; ++j) {
+        p[i][j] *= inv;
+        if (lane == 0) probs[(w * L + i) * L + j] = p[i][j];
+      }
+    }
+    for (int i = 0; i < L; ++i) {
+      T* o = out + ((int64_t)i * N + n) * E + (int64_t)h * dh;
+      for (int d = lane; d < dh; d += 32) {
+        float acc = 0.f;
+        for (int j = 0; j < L; ++j) acc = fmaf(p[i][j], to_f32(base[(int64_t)j * N * row + 2 * E + d]), acc);
+        o[d] = from_f32<T>(acc);
+      }
+    }
+  }
+}
+
+template <typename T, int L>
+__global__ void __launch_bounds__(256)
+attn_small_bwd_kernel(const T* __restrict__ qkv, const T* __restrict__ dout, const float* __restrict__ probs,
+                      T* __restrict__ dqkv, int64_t N, int E, int heads, float scale) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w0 = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int64_t total = N * heads;
+  const int dh = E / heads;
+  const int64_t row = 3 * (int64_t)E;
+  for (int64_t w = w0; w < total; w += (int64_t)gridDim.x * 8) {
+    const int64_t n = w / heads; const int h = (int)(w - n * heads);
+    const T* base = qkv + n * row + (int64_t)h * dh;
+    T* dbase = dqkv + n * row + (int64_t)h * dh;
+    float p[L][L], ds[L][L];
+    for (int i = 0; i < L; ++i) {
+      const T* go = dout + ((int64_t)i * N + n) * E + (int64_t)h * dh;
+      float dot = 0.f;
+      for (int j = 0; j < L; ++j) {
+        p[i][j] = probs[(w * L + i) * L + j];
+        const T* v = base + (int64_t)j * N * row + 2 * E;
+        float s = 0.f;
+        for (int d = lane; d < dh; d += 32) s = fmaf(to_f32(go[d]), to_f32(v[d]), s);
+        s = warp_sum(s);
+        ds[i][j] = s; dot = fmaf(p[i][j], s, dot);
+      }
+      for (int j = 0; j < L; ++j) ds[i][j] = p[i][j] * (ds[i][j] - dot) * scale;
+    }
+    for (int d = lane; d < dh; d += 32) {
+      for (int i = 0; i < L; ++i) {
+        float dq = 0.f, dk = 0.f, dv = 0.f;
+        for (int j = 0; j < L; ++j) {
+          dq = fmaf(ds[i][j], to_f32(base[(int64_t)j * N * row + E + d]), dq);        // dQ_i = sum_j dS_ij K_j
+          dk = fmaf(ds[j][i], to_f32(base[(int64_t)j * N * row + d]), dk);            // dK_i = sum_j dS_ji Q_j
+          dv = fmaf(p[j][i], to_f32(dout[((int64_t)j * N + n) * E + (int64_t)h * dh + d]), dv);  // dV_i = sum_j P_ji dO_j
+        }
+        T* drow = dbase + (int64_t)i * N * row;
+        drow[d] = from_f32<T>(dq); drow[E + d] = from_f32<T>(dk); drow[2 * E + d] = from_f32<T>(dv);
+      }
+    }
+  }
+}
+
+}  // namespace jmt
+
+using namespace jmt;
+
+extern "C" int jmt_act_bwd(const void* dy, const void* y, void* dx, int64_t n, float slope, int dtype, void* stream) {
+  JMT_REQUIRE(dy && y && dx && n >= 0, "jmt_act_bwd: bad arguments");
+  if (n == 0) return JMT_OK;
+  const bool al = ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(dx)) & 31) == 0;
+  const int64_t n8 = al ? n / 8 : 0;
+  JMT_DISPATCH_DTYPE(dtype, T, (act_bwd_kernel<T><<<grid_for(n, kEwThreads * 16), kEwThreads, 0, (cudaStream_t)stream>>>((const T*)dy, (const T*)y, (T*)dx, n8, n, slope)));
+  return check_launch("act_bwd_kernel");
+}
+
+extern "C" int jmt_add_act(const void* a, const void* b, void* out, int64_t n, int act, float slope, int dtype, void* stream) {
+  JMT_REQUIRE(a && b && out && n >= 0, "jmt_add_act: bad arguments");
+  if (n == 0) return JMT_OK;
+  const bool al = ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(out)) & 31) == 0;
+  const int64_t n8 = al ? n / 8 : 0;
+  JMT_DISPATCH_DTYPE(dtype, T, (add_act_kernel<T><<<grid_for(n, kEwThreads * 16), kEwThreads, 0, (cudaStream_t)stream>>>((const T*)a, (const T*)b, (T*)out, n8, n, act, slope)));
+  return check_launch("add_act_kernel");
+}
+
+extern "C" int jmt_axpy(const void* x, void* y, float a, int64_t n, int dtype, void* stream) {
+  JMT_REQUIRE(x && y && n >= 0, "jmt_axpy: bad arguments");
+  if (n == 0) return JMT_OK;
+  const bool al = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 31) == 0;
+  const int64_t n8 = al ? n / 8 : 0;
+  JMT_DISPATCH_DTYPE(dtype, T, (axpy_kernel<T><<<grid_for(n, kEwThreads * 16), kEwThreads, 0, (cudaStream_t)stream>>>((const T*)x, (T*)y, a, n8, n)));
+  return check_launch("axpy_kernel");
+}
+
+extern "C" int jmt_copy2d(const void* in, int in_dtype, int64_t in_ld, void* out, int out_dtype, int64_t out_ld,
+                          int64_t rows, int cols, void* stream) {
+  JMT_REQUIRE(in && out && rows >= 0 && cols >= 0, "jmt_copy2d: bad arguments");
+  if (rows * cols == 0) return JMT_OK;
+  const int vec = (cols % 8 == 0 && in_ld % 8 == 0 && out_ld % 8 == 0 &&
+                   ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 31) == 0) ? 1 : 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int g = grid_for(rows * cols, kEwThreads * 16);
+  JMT_DISPATCH_DTYPE(in_dtype, TI, JMT_DISPATCH_DTYPE(out_dtype, TO,
+      (copy2d_kernel<TI, TO><<<g, kEwThreads, 0, st>>>((const TI*)in, in_ld, (TO*)out, out_ld, rows, cols, vec))));
+  return check_launch("copy2d_kernel");
+}
+
+extern "C" int jmt_cast(const void* in, int in_dtype, void* out, int out_dtype, int64_t n, void* stream) {
+  if (n == 0) return JMT_OK;
+  if (n % 8 == 0) return jmt_copy2d(in, in_dtype, 8, out, out_dtype, 8, n / 8, 8, stream);
+  JMT_REQUIRE(n < (int64_t)1 << 31, "jmt_cast: n too large for the unaligned path");
+  return jmt_copy2d(in, in_dtype, n, out, out_dtype, n, 1, (int)n, stream);
+}
+
+extern "C" int jmt_transpose(const void* in, int in_dtype, void* out, int out_dtype, int64_t nb, int R, int C, void* stream) {
+  JMT_REQUIRE(in && out && nb >= 0 && R >= 0 && C >= 0 && nb < 65536, "jmt_transpose: bad arguments");
+  if (nb * R * C == 0) return JMT_OK;
+  dim3 grid((C + 31) / 32, (R + 31) / 32, (unsigned)nb);
+  cudaStream_t st = (cudaStream_t)stream;
+  JMT_DISPATCH_DTYPE(in_dtype, TI, JMT_DISPATCH_DTYPE(out_dtype, TO,
+      (transpose_kernel<TI, TO><<<grid, 256, 0, st>>>((const TI*)in, (TO*)out, R, C))));
+  return check_launch("transpose_kernel");
+}
+
+extern "C" int jmt_colsum(const void* x, int dtype, int64_t ld, int64_t rows, int cols, float* out, void* stream) {
+  JMT_REQUIRE(x && out && rows >= 0 && cols > 0, "jmt_colsum: bad arguments");
+  if (rows == 0) return JMT_OK;
+  const int gx = (cols + 31) / 32;
+  int gy = (int)((rows + 255) / 256);
+  const int cap = (kNumSMs * 8 + gx - 1) / gx;
+  if (gy > cap) gy = cap;
+  if (gy < 1) gy = 1;
+  JMT_DISPATCH_DTYPE(dtype, T, (colsum_kernel<T><<<dim3(gx, gy), 256, 0, (cudaStream_t)stream>>>((const T*)x, ld, rows, cols, out)));
+  return check_launch("colsum_kernel");
+}
+
+extern "C" int jmt_apply_mask(const void* x, const uint8_t* mask, void* out, int64_t nb, int L, int C, int per_channel,
+                              float scale, int dtype, void* stream) {
+  JMT_REQUIRE(x && mask && out, "jmt_apply_mask: bad arguments");
+  const int64_t total = nb * L * C;
+  if (total == 0) return JMT_OK;
+  JMT_DISPATCH_DTYPE(dtype, T, (apply_mask_kernel<T><<<grid_for(total, kEwThreads * 4), kEwThreads, 0, (cudaStream_t)stream>>>((const T*)x, mask, (T*)out, total, L, C, per_channel, scale)));
+  return check_launch("apply_mask_kernel");
+}
+
+extern "C" int jmt_dropout_mask(uint8_t* mask, int64_t n, float p, uint64_t seed, uint64_t offset, void* stream) {
+  JMT_REQUIRE(mask && n >= 0 && p >= 0.f && p < 1.f, "jmt_dropout_mask: bad arguments");
+  if (n == 0) return JMT_OK;
+  dropout_mask_kernel<<<grid_for((n + 3) / 4, kEwThreads), kEwThreads, 0, (cudaStream_t)stream>>>(mask, n, p, seed, offset);
+  return check_launch("dropout_mask_kernel");
+}
+
+extern "C" int jmt_weight_norm_fwd(const float* g, const float* v, void* w_fwd, void* w_dgrad, int out_dtype, float* norm,
+                                   int cout, int cin, int k, void* stream) {
+  JMT_REQUIRE(g && v && w_fwd && cout > 0 && cin > 0 && k > 0, "jmt_weight_norm_fwd: bad arguments");
+  JMT_DISPATCH_DTYPE(out_dtype, TO, (weight_norm_fwd_kernel<TO><<<cout, 256, 0, (cudaStream_t)stream>>>(g, v, (TO*)w_fwd, (TO*)w_dgrad, norm, cout, cin, k)));
+  return check_launch("weight_norm_fwd_kernel");
+}
+
+extern "C" int jmt_weight_norm_bwd(const float* dw_fwd, const float* g, const float* v, const float* norm, float* dg,
+                                   float* dv, int cout, int cin, int k, void* stream) {
+  JMT_REQUIRE(dw_fwd && g && v && norm && dg && dv, "jmt_weight_norm_bwd: bad arguments");
+  weight_norm_bwd_kernel<<<cout, 256, 0, (cudaStream_t)stream>>>(dw_fwd, g, v, norm, dg, dv, cout, cin, k);
+  return check_launch("weight_norm_bwd_kernel");
+}
+
+extern "C" int jmt_attn_small_fwd(const void* qkv, void* out, float* probs, int L, int64_t N, int E, int heads,
+                                  float scale, int dtype, void* stream) {
+  JMT_REQUIRE(qkv && out && probs && L >= 1 && L <= kMaxSmallL && heads >= 1 && E % heads == 0, "jmt_attn_small_fwd: need 1 <= L <= 8");
+  if (N == 0) return JMT_OK;
+  const int g = grid_for(N * heads, 8, kNumSMs * 8);
+#define JMT_L_CASE(LL) case LL: attn_small_fwd_kernel<T, LL><<<g, 256, 0, (cudaStream_t)stream>>>((const T*)qkv, (T*)out, probs, N, E, heads, scale); break;
+  JMT_DISPATCH_DTYPE(dtype, T, switch (L) { JMT_L_CASE(1) JMT_L_CASE(2) JMT_L_CASE(3) JMT_L_CASE(4) JMT_L_CASE(5) JMT_L_CASE(6) JMT_L_CASE(7) JMT_L_CASE(8) });
+#undef JMT_L_CASE
+  return check_launch("attn_small_fwd_kernel");
+}
+
+extern "C" int jmt_attn_small_bwd(const void* qkv, const void* dout, const float* probs, void* dqkv, int L, int64_t N,
+                                  int E, int heads, float scale, int dtype, void* stream) {
+  JMT_REQUIRE(qkv && dout && probs && dqkv && L >= 1 && L <= kMaxSmallL && heads >= 1 && E % heads == 0, "jmt_attn_small_bwd: need 1 <= L <= 8");
+  if (N == 0) return JMT_OK;
+  const int g = grid_for(N * heads, 8, kNumSMs * 8);
+#define JMT_L_CASE(LL) case LL: attn_small_bwd_kernel<T, LL><<<g, 256, 0, (cudaStream_t)stream>>>((const T*)qkv, (const T*)dout, probs, (T*)dqkv, N, E, heads, scale); break;
+  JMT_DISPATCH_DTYPE(dtype, T, switch (L) { JMT_L_CASE(1) JMT_L_CASE(2) JMT_L_CASE(3) JMT_L_CASE(4) JMT_L_CASE(5) JMT_L_CASE(6) JMT_L_CASE(7) JMT_L_CASE(8) });
+#undef JMT_L_CASE
+  return check_launch("attn_small_bwd_kernel");
+}

@@ -1,0 +1,457 @@
+// jmt_gemm_bf16: persistent, warp-specialised tcgen05 GEMM for sm_100a.
+//
+//   warp 0 (1 elected thread) : TMA producer   -- cp.async.bulk.tensor.4d -> 128B-swizzled smem ring
+//   warp 1 (1 elected thread) : MMA issuer     -- tcgen05.mma.cta_group::1.kind::f16, fp32 accum in TMEM
+//   warps 2..5                : epilogue       -- tcgen05.ld 32x32b -> alpha/bias/activation -> global
+//
+// Two TMEM accumulator stages (2 x 256 columns) let the epilogue of tile i overlap the mainloop of
+// tile i+1.  One descriptor (jmt_gemm_desc) covers every dense contraction of the JMT path: Linear
+// fwd/dgrad/wgrad, QK^T / PV and their gradients (batched over (b, head) through 4-D tensor maps,
+// K- or MN-major operands selected in the UMMA instruction descriptor) and the dilated causal
+// Conv1d of the TCN as an implicit GEMM (taps = extra K blocks with a shifted TMA row coordinate;
+// causal zero padding = TMA out-of-bounds fill).
+#include <cuda.h>
+
+#include "common.cuh"
+
+int jmt_validate_gemm_desc(const jmt_gemm_desc* g, const char* who);
+
+namespace jmt {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;           // 64 bf16 = 128 bytes = one swizzle row
+constexpr int kUmmaK = 16;
+constexpr int kTcThreads = 192;
+constexpr int kAStageBytes = kBlockM * kBlockK * 2;   // 16 KiB
+constexpr int kMaxStages = 8;
+constexpr int kTmemCols = 512;
+constexpr int kAccStride = 256;       // TMEM columns per accumulator stage
+constexpr uint32_t kSpinLimit = 1u << 24;   // ~1 s of polling, far beyond any legitimate wait
+
+struct TcParams {
+  int M, N, K, block_n;
+  int m_tiles, n_tiles, batch_tiles, split_k, total_tiles;
+  int kblocks, rb_n, iters_total;
+  int nb0;
+  int a_major, b_major;
+  int a_shift0, a_shift_step, b_shift0, b_shift_step;
+  int b_has_b0, b_has_b1;
+  int reduce_batch;
+  uint32_t idesc;
+  int b_stage_bytes, b_tx_bytes, stages;
+  // epilogue
+  void* d;
+  const float* bias;
+  int64_t d_ld, d_bs0, d_bs1;
+  float alpha, slope;
+  int d_dtype, act, store_mode, vec_ok;
+};
+
+// ----------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+#pragma unroll 1
+  for (uint32_t spin = 0; spin < kSpinLimit; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (done) return;
+  }
+  __trap();   // a pipeline bug must fail loudly, never hang the GPU
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory matrix descriptor, 128-byte swizzle, Blackwell version bits.
+// K-major tile  [rows][64 elem]: 8-row groups 1024 B apart (SBO); LBO unused (encoded 1).
+// MN-major tile [chunk][k][64 elem]: 8-k groups 1024 B apart (SBO), 64-wide MN chunks 8192 B apart (LBO).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;      // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;      // SWIZZLE_128B
+  return d;
+}
+
+struct TileCoord { int m0, n0, batch, it0, it1; };
+
+__device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int t) {
+  TileCoord c;
+  const int nt = t % p.n_tiles; t /= p.n_tiles;
+  const int mt = t % p.m_tiles; t /= p.m_tiles;
+  c.batch = t % p.batch_tiles;
+  const int split = t / p.batch_tiles;
+  c.m0 = mt * kBlockM;
+  c.n0 = nt * p.block_n;
+  c.it0 = (int)(((int64_t)split * p.iters_total) / p.split_k);
+  c.it1 = (int)(((int64_t)(split + 1) * p.iters_total) / p.split_k);
+  return c;
+}
+
+template <typename T> struct Pack32;   // store 32 consecutive fp32 results of one row
+template <> struct Pack32<float> {
+  static __device__ __forceinline__ void store(float* dst, const float (&v)[32], int mode) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float4 o = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      float4* q = reinterpret_cast<float4*>(dst) + i;
+      if (mode == JMT_ACCUMULATE) { const float4 c = *q; o.x += c.x; o.y += c.y; o.z += c.z; o.w += c.w; }
+      *q = o;
+    }
+  }
+};
+template <> struct Pack32<__nv_bfloat16> {
+  static __device__ __forceinline__ void store(__nv_bfloat16* dst, const float (&v)[32], int mode) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint4* q = reinterpret_cast<uint4*>(dst) + i;
+      float w[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) w[j] = v[8 * i + j];
+      if (mode == JMT_ACCUMULATE) {
+        const uint4 c = *q;
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&c);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const float2 f = __bfloat1622float2(h[j]); w[2 * j] += f.x; w[2 * j + 1] += f.y; }
+      }
+      uint4 o;
+      __nv_bfloat162* ho = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) ho[j] = __floats2bfloat162_rn(w[2 * j], w[2 * j + 1]);
+      *q = o;
+    }
+  }
+};
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // 1024-byte aligned carve-up (SWIZZLE_128B atoms are 1024 B)
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sA = smem_base;
+  const uint32_t sB = sA + p.stages * kAStageBytes;
+  const uint32_t bars = sB + p.stages * p.b_stage_bytes;     // 8-byte aligned (multiples of 1024)
+  const uint32_t full_bar = bars, empty_bar = bars + 8 * kMaxStages;
+  const uint32_t tfull_bar = bars + 16 * kMaxStages, tempty_bar = tfull_bar + 16;
+  const uint32_t tmem_slot = tempty_bar + 16;
+  uint8_t* smem_aligned = smem_raw + (smem_base - smem_u32(smem_raw));
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_aligned + (tmem_slot - smem_base));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar + 8 * s, 1); mbar_init(tempty_bar + 8 * s, 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ================================ TMA producer ================================
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_a)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_b)) : "memory");
+      int stage = 0; uint32_t phase = 0;
+      const int b_chunks = (p.block_n + 63) / 64;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const TileCoord c = decode_tile(p, t);
+        for (int it = c.it0; it < c.it1; ++it) {
+          const int kb = it % p.kblocks;
+          const int rb = (it / p.kblocks) % p.rb_n;
+          const int tap = it / (p.kblocks * p.rb_n);
+          const int bidx = p.reduce_batch ? rb : c.batch;
+          const int b0 = bidx % p.nb0, b1 = bidx / p.nb0;
+          const int bb0 = p.b_has_b0 ? b0 : 0, bb1 = p.b_has_b1 ? b1 : 0;
+          const int ash = p.a_shift0 + tap * p.a_shift_step;
+          const int bsh = p.b_shift0 + tap * p.b_shift_step;
+          mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+          const uint32_t fb = full_bar + 8 * stage;
+          mbar_expect_tx(fb, kAStageBytes + p.b_tx_bytes);
+          const uint32_t a_dst = sA + stage * kAStageBytes;
+          const uint32_t b_dst = sB + stage * p.b_stage_bytes;
+          if (p.a_major == JMT_MAJOR_K) {
+            tma_load_4d(a_dst, &tma_a, fb, kb * kBlockK, c.m0 + ash, b0, b1);
+          } else {
+            tma_load_4d(a_dst, &tma_a, fb, c.m0, kb * kBlockK + ash, b0, b1);
+            tma_load_4d(a_dst + 8192, &tma_a, fb, c.m0 + 64, kb * kBlockK + ash, b0, b1);
+          }
+          if (p.b_major == JMT_MAJOR_K) {
+            tma_load_4d(b_dst, &tma_b, fb, tap * p.K + kb * kBlockK, c.n0, bb0, bb1);
+          } else {
+            for (int ch = 0; ch < b_chunks; ++ch)
+              tma_load_4d(b_dst + ch * 8192, &tma_b, fb, c.n0 + ch * 64, kb * kBlockK + bsh, bb0, bb1);
+          }
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ================================ MMA issuer ================================
+      int stage = 0; uint32_t phase = 0;
+      int tile_iter = 0;
+      const uint32_t a_lbo = p.a_major == JMT_MAJOR_K ? 16u : 8192u;
+      const uint32_t b_lbo = p.b_major == JMT_MAJOR_K ? 16u : 8192u;
+      const uint32_t a_kstep = p.a_major == JMT_MAJOR_K ? (kUmmaK * 2) >> 4 : (kUmmaK * 128) >> 4;   // desc.lo units (16 B)
+      const uint32_t b_kstep = p.b_major == JMT_MAJOR_K ? (kUmmaK * 2) >> 4 : (kUmmaK * 128) >> 4;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tile_iter) {
+        const TileCoord c = decode_tile(p, t);
+        const int acc = tile_iter & 1;
+        const uint32_t acc_phase = (tile_iter >> 1) & 1;
+        mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * kAccStride;
+        for (int it = c.it0; it < c.it1; ++it) {
+          mbar_wait(full_bar + 8 * stage, phase);
+          tc_fence_after();
+          const uint64_t a_desc = make_smem_desc(sA + stage * kAStageBytes, a_lbo, 1024);
+          const uint64_t b_desc = make_smem_desc(sB + stage * p.b_stage_bytes, b_lbo, 1024);
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k)
+            tc_mma(d_tmem, a_desc + (uint64_t)(k * a_kstep), b_desc + (uint64_t)(k * b_kstep), p.idesc,
+                   (it > c.it0 || k > 0) ? 1u : 0u);
+          tc_commit(empty_bar + 8 * stage);      // frees the smem slot once these MMAs retire
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(tfull_bar + 8 * acc);          // accumulator ready for the epilogue
+      }
+    }
+  } else {
+    // ================================ epilogue (warps 2..5) ================================
+    const int q = warp & 3;                       // TMEM lane quarter this warp may access
+    int tile_iter = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tile_iter) {
+      const TileCoord c = decode_tile(p, t);
+      const int split = (t / (p.n_tiles * p.m_tiles)) / p.batch_tiles;
+      const int acc = tile_iter & 1;
+      const uint32_t acc_phase = (tile_iter >> 1) & 1;
+      mbar_wait(tfull_bar + 8 * acc, acc_phase);
+      tc_fence_after();
+      const int m = c.m0 + q * 32 + lane;
+      const int b0 = c.batch % p.nb0, b1 = c.batch / p.nb0;
+      const int64_t row_off = (int64_t)b0 * p.d_bs0 + (int64_t)b1 * p.d_bs1 + (int64_t)m * p.d_ld;
+      const bool add_bias = p.bias != nullptr && split == 0;
+      for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+        const int n = c.n0 + c0;
+        if (n >= p.N) break;                      // warp-uniform
+        uint32_t r[32];
+        tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kAccStride + c0), r);
+        if (m >= p.M) continue;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float x = p.alpha * __uint_as_float(r[j]);
+          if (add_bias && n + j < p.N) x += __ldg(p.bias + n + j);
+          v[j] = apply_act(x, p.act, p.slope);
+        }
+        if (p.vec_ok && n + 32 <= p.N && p.store_mode != JMT_ATOMIC_ADD) {
+          if (p.d_dtype == JMT_F32) Pack32<float>::store((float*)p.d + row_off + n, v, p.store_mode);
+          else Pack32<__nv_bfloat16>::store((__nv_bfloat16*)p.d + row_off + n, v, p.store_mode);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (n + j >= p.N) break;
+            const int64_t idx = row_off + n + j;
+            if (p.d_dtype == JMT_F32) {
+              float* d = (float*)p.d;
+              if (p.store_mode == JMT_STORE) d[idx] = v[j];
+              else if (p.store_mode == JMT_ACCUMULATE) d[idx] += v[j];
+              else atomicAdd(d + idx, v[j]);
+            } else {
+              __nv_bfloat16* d = (__nv_bfloat16*)p.d;
+              d[idx] = __float2bfloat16_rn(p.store_mode == JMT_STORE ? v[j] : __bfloat162float(d[idx]) + v[j]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar + 8 * acc);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
+// ----------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess) { cudaGetLastError(); return nullptr; }
+    return (EncodeTiledFn)f;
+  }();
+  return fn;
+}
+
+// 4-D bf16 tensor map over (inner, rows, b0, b1) with a {64, box_rows, 1, 1} box, 128B swizzle, zero OOB fill
+static int make_map(CUtensorMap* map, const void* ptr, int64_t inner, int64_t rows, int64_t ld, int64_t nb0, int64_t bs0,
+                    int64_t nb1, int64_t bs1, int box_rows, const char* who) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { set_error("%s: cuTensorMapEncodeTiled unavailable (no CUDA driver?)", who); return JMT_ERR_CUDA; }
+  JMT_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "%s: operand pointer must be 16-byte aligned", who);
+  JMT_REQUIRE(ld % 8 == 0 && (nb0 == 1 || bs0 % 8 == 0) && (nb1 == 1 || bs1 % 8 == 0),
+              "%s: operand ld / batch strides must be multiples of 8 elements (ld=%lld bs0=%lld bs1=%lld)", who,
+              (long long)ld, (long long)bs0, (long long)bs1);
+  JMT_REQUIRE(box_rows >= 1 && box_rows <= 256, "%s: bad box rows %d", who, box_rows);
+  const cuuint64_t dims[4] = {(cuuint64_t)inner, (cuuint64_t)rows, (cuuint64_t)nb0, (cuuint64_t)nb1};
+  const cuuint64_t row_bytes = (cuuint64_t)ld * 2;
+  const cuuint64_t strides[3] = {row_bytes, nb0 > 1 ? (cuuint64_t)bs0 * 2 : row_bytes, nb1 > 1 ? (cuuint64_t)bs1 * 2 : row_bytes};
+  const cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)box_rows, 1, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("%s: cuTensorMapEncodeTiled failed (%d) inner=%lld rows=%lld ld=%lld nb0=%lld bs0=%lld nb1=%lld bs1=%lld box_rows=%d",
+              who, (int)r, (long long)inner, (long long)rows, (long long)ld, (long long)nb0, (long long)bs0,
+              (long long)nb1, (long long)bs1, box_rows);
+    return JMT_ERR_CUDA;
+  }
+  return JMT_OK;
+}
+
+static int pick_block_n(int N) {
+  int best = 32; long best_cost = -1;
+  for (int bn = 32; bn <= 256; bn += 32) {
+    const int tiles = (N + bn - 1) / bn;
+    // padded columns computed + a per-tile overhead of ~24 columns' worth of work
+    const long cost = (long)tiles * bn + 24L * tiles;
+    if (best_cost < 0 || cost <= best_cost) { best = bn; best_cost = cost; }
+  }
+  return best;
+}
+
+}  // namespace jmt
+
+using namespace jmt;
+
+extern "C" int jmt_gemm_bf16(const jmt_gemm_desc* g, void* stream) {
+  int rc = jmt_validate_gemm_desc(g, "jmt_gemm_bf16");
+  if (rc != JMT_OK) return rc;
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = g->M; p.N = g->N; p.K = g->K;
+  p.block_n = pick_block_n(g->N);
+  p.m_tiles = (g->M + kBlockM - 1) / kBlockM;
+  p.n_tiles = (g->N + p.block_n - 1) / p.block_n;
+  const int nb = g->nb0 * g->nb1;
+  p.reduce_batch = g->reduce_batch ? 1 : 0;
+  p.batch_tiles = p.reduce_batch ? 1 : nb;
+  p.kblocks = (g->K + kBlockK - 1) / kBlockK;
+  p.rb_n = p.reduce_batch ? nb : 1;
+  p.iters_total = g->ntaps * p.rb_n * p.kblocks;
+  p.split_k = g->split_k < p.iters_total ? g->split_k : p.iters_total;
+  const int64_t total = (int64_t)p.m_tiles * p.n_tiles * p.batch_tiles * p.split_k;
+  JMT_REQUIRE(total < (1ll << 31), "jmt_gemm_bf16: too many tiles");
+  p.total_tiles = (int)total;
+  p.nb0 = g->nb0;
+  p.a_major = g->a_major; p.b_major = g->b_major;
+  p.a_shift0 = g->a_shift0; p.a_shift_step = g->a_shift_step;
+  p.b_shift0 = g->b_shift0; p.b_shift_step = g->b_shift_step;
+  p.b_has_b0 = (g->nb0 > 1 && g->b_bs0 != 0) ? 1 : 0;
+  p.b_has_b1 = (g->nb1 > 1 && g->b_bs1 != 0) ? 1 : 0;
+  JMT_REQUIRE(!(g->ntaps > 1 && g->b_major == JMT_MAJOR_K && g->K % 8 != 0), "jmt_gemm_bf16: taps need K %% 8 == 0");
+  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)g->a_major << 15) | ((uint32_t)g->b_major << 16) |
+            ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+  const int b_chunks = (p.block_n + 63) / 64;
+  p.b_stage_bytes = g->b_major == JMT_MAJOR_K ? p.block_n * 128 : b_chunks * 8192;
+  p.b_tx_bytes = p.b_stage_bytes;
+  const int stage_bytes = kAStageBytes + p.b_stage_bytes;
+  const int budget = 227 * 1024 - 1024 /*align*/ - 512 /*barriers*/;
+  p.stages = budget / stage_bytes;
+  if (p.stages > kMaxStages) p.stages = kMaxStages;
+  JMT_REQUIRE(p.stages >= 2, "jmt_gemm_bf16: shared memory budget");
+  p.d = g->d; p.bias = g->bias; p.d_ld = g->d_ld; p.d_bs0 = g->d_bs0; p.d_bs1 = g->d_bs1;
+  p.alpha = g->alpha; p.slope = g->slope; p.d_dtype = g->d_dtype; p.act = g->act; p.store_mode = g->store_mode;
+  const int64_t es = g->d_dtype == JMT_F32 ? 4 : 2;
+  p.vec_ok = ((reinterpret_cast<uintptr_t>(g->d) & 15) == 0 && (g->d_ld * es) % 16 == 0 &&
+              (g->d_bs0 * es) % 16 == 0 && (g->d_bs1 * es) % 16 == 0) ? 1 : 0;
+
+  CUtensorMap map_a, map_b;
+  // A: K-major -> (K, a_rows) box {64,128}; MN-major -> (M, a_rows = k extent) box {64,64}
+  if (g->a_major == JMT_MAJOR_K)
+    rc = make_map(&map_a, g->a, g->K, g->a_rows, g->a_ld, g->nb0, g->a_bs0, g->nb1, g->a_bs1, kBlockM, "jmt_gemm_bf16(A)");
+  else
+    rc = make_map(&map_a, g->a, g->M, g->a_rows, g->a_ld, g->nb0, g->a_bs0, g->nb1, g->a_bs1, kBlockK, "jmt_gemm_bf16(A)");
+  if (rc != JMT_OK) return rc;
+  const int bnb0 = p.b_has_b0 ? g->nb0 : 1, bnb1 = p.b_has_b1 ? g->nb1 : 1;
+  if (g->b_major == JMT_MAJOR_K)
+    rc = make_map(&map_b, g->b, (int64_t)g->ntaps * g->K, g->b_rows, g->b_ld, bnb0, g->b_bs0, bnb1, g->b_bs1, p.block_n, "jmt_gemm_bf16(B)");
+  else
+    rc = make_map(&map_b, g->b, g->N, g->b_rows, g->b_ld, bnb0, g->b_bs0, bnb1, g->b_bs1, kBlockK, "jmt_gemm_bf16(B)");
+  if (rc != JMT_OK) return rc;
+
+  const int smem = 1024 + p.stages * stage_bytes + 512;
+  static std::atomic<int> attr_set[64];     // per device (immutable once set)
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); set_error("jmt_gemm_bf16: no CUDA device"); return JMT_ERR_CUDA; }
+  if (!attr_set[dev & 63].load(std::memory_order_acquire)) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) { set_error("jmt_gemm_bf16: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); cudaGetLastError(); return JMT_ERR_CUDA; }
+    attr_set[dev & 63].store(1, std::memory_order_release);
+  }
+  const int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
+  gemm_tc_kernel<<<grid, kTcThreads, smem, (cudaStream_t)stream>>>(map_a, map_b, p);
+  return check_launch("gemm_tc_kernel");
+}

@@ -1,0 +1,59 @@
+"""Data-parallel plumbing (one process per GPU, torch.distributed / NCCL over NVLink).
+
+The path shards along the batch of clip windows; the only collectives are
+  (1) training: one all-reduce(sum)/n over the flat fp32 live-gradient bucket at the end of backward,
+  (2) eval / global loss: one all-reduce(sum) of the (2, 6) fp64 CCC partial sums.
+`joint_modalities='NONE'` attends across the batch and is therefore per-shard
+("replicas only") exactly as the reference's DataParallel scatter would make it.
+"""
+from __future__ import annotations
+
+import os
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+
+def init_from_env(backend: Optional[str] = None) -> int:
+    """Initialise the default process group from torchrun's env (RANK/WORLD_SIZE/MASTER_*)."""
+    if dist.is_initialized():
+        return dist.get_rank()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world == 1:
+        return 0
+    if backend is None:
+        backend = "nccl" if torch.cuda.is_available() else "gloo"
+    if backend == "nccl":
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    dist.init_process_group(backend=backend)
+    return dist.get_rank()
+
+
+def shard_bounds(n_items: int, rank: int, world: int):
+    """Rank r takes windows [r*n/world, (r+1)*n/world) (contiguous, balanced to +-1)."""
+    return (rank * n_items) // world, ((rank + 1) * n_items) // world
+
+
+def make_grad_sync(group=None, average: bool = True):
+    """Hook for `module.set_grad_sync`: all-reduce the flat gradient bucket in place."""
+    def sync(bucket: torch.Tensor):
+        if not dist.is_initialized() or dist.get_world_size(group) == 1:
+            return
+        dist.all_reduce(bucket, op=dist.ReduceOp.SUM, group=group)
+        if average:
+            bucket.mul_(1.0 / dist.get_world_size(group))
+    return sync
+
+
+def allreduce_sums(sums: torch.Tensor, group=None) -> torch.Tensor:
+    """All-reduce CCC partial sums ((npairs, 6) fp64) across ranks; no-op without a process group."""
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+    return sums
+
+
+def broadcast_parameters(module: torch.nn.Module, src: int = 0, group=None):
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        for p in module.parameters():
+            dist.broadcast(p.data, src=src, group=group)

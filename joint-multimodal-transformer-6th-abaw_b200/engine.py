@@ -1,0 +1,856 @@
+"""Tape engine: forward/backward orchestration of the JMT hot path over the C-ABI kernels.
+
+PyTorch supplies device memory (caching allocator), the current stream and the outer autograd
+hook; every byte and FLOP of the path itself runs in libjmt_b200.so.  The engine keeps its own
+reverse-mode tape so that (a) no ATen kernel runs on the path, (b) gradient accumulation is
+fused into kernel epilogues (GEMM ``ACCUMULATE`` stores), (c) parameter gradients land in ONE
+flat fp32 bucket (the NCCL all-reduce unit) and (d) the step is CUDA-graph
+capturable (no host synchronisation anywhere).
+
+Precision modes (SURVEY.md 7 "hard parts" #4):
+  'bf16' : bf16 operands / activations, fp32 accumulate (tcgen05 path), fp32 LN/softmax statistics
+  'fp32' : fp32 operands / activations on the FFMA GEMM -- the parity mode for the 1e-3 gate
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib as L
+
+_DT = {torch.float32: L.F32, torch.bfloat16: L.BF16}
+LEAKY_SLOPE = 0.01
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("jmt_b200 runs on CUDA tensors only (there is no CPU fallback)")
+
+
+# --------------------------------------------------------------------------- CUDA runtime memset
+_cudart = None
+
+
+def cuda_memset0(t: torch.Tensor):
+    """Stream-ordered zero fill through cudaMemsetAsync (copy engine, not an ATen kernel)."""
+    global _cudart
+    if t.numel() == 0:
+        return
+    if _cudart is None:
+        import glob
+        import os
+        cands = sorted(glob.glob(os.path.join(os.path.dirname(torch.__file__), "lib", "libcudart*.so*"))) + \
+            sorted(glob.glob("/usr/local/cuda/lib64/libcudart.so*"))
+        lib = None
+        for c in cands:
+            try:
+                lib = C.CDLL(c)
+                break
+            except OSError:
+                continue
+        if lib is None:
+            raise RuntimeError("libcudart not found")
+        lib.cudaMemsetAsync.argtypes = [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p]
+        lib.cudaMemsetAsync.restype = C.c_int
+        _cudart = lib
+    assert t.is_contiguous()
+    rc = _cudart.cudaMemsetAsync(C.c_void_p(t.data_ptr()), 0, t.numel() * t.element_size(), _stream())
+    if rc != 0:
+        raise RuntimeError(f"cudaMemsetAsync failed ({rc})")
+
+
+class GradBuf:
+    __slots__ = ("t", "refs")
+
+    def __init__(self, t):
+        self.t = t
+        self.refs = 1
+
+
+class Var:
+    """An activation on the tape: ``data`` is a 2-D (rows, cols) view with unit inner stride."""
+    __slots__ = ("data", "gbuf", "needs_grad")
+
+    def __init__(self, data: torch.Tensor, needs_grad: bool = True):
+        self.data = data
+        self.gbuf: Optional[GradBuf] = None
+        self.needs_grad = needs_grad
+
+    @property
+    def grad(self) -> Optional[torch.Tensor]:
+        return None if self.gbuf is None else self.gbuf.t
+
+
+class Ctx:
+    """One forward(+backward) pass: precision, parameter access, tape, flat gradient bucket."""
+
+    def __init__(self, params: Dict[str, torch.Tensor], precision: str, record: bool, training: bool,
+                 wcache: Optional[dict] = None, seed: int = 0):
+        assert precision in ("bf16", "fp32"), precision
+        self.params = params
+        self.precision = precision
+        self.adt = torch.bfloat16 if precision == "bf16" else torch.float32
+        self.acode = _DT[self.adt]
+        self.record = record
+        self.training = training
+        self.tape: List[Callable[[], None]] = []
+        self.lib = L.lib()
+        self.wcache = wcache if wcache is not None else {}
+        self._w: Dict[str, torch.Tensor] = {}
+        self.pgrads: Dict[str, torch.Tensor] = {}
+        self.bucket: Optional[torch.Tensor] = None
+        self.seed = seed
+        self.rng_offset = 0
+        self.qcache: Dict[Tuple[str, int], Var] = {}
+        self.dev = next(iter(params.values())).device if params else torch.device("cuda", torch.cuda.current_device())
+        self.keep: List[object] = []          # host arrays that must outlive async launches
+
+    # ---------------------------------------------------------------- memory helpers
+    def empty(self, shape, dtype=None) -> torch.Tensor:
+        return torch.empty(shape, dtype=dtype or self.adt, device=self.dev)
+
+    def zeros(self, shape, dtype=None) -> torch.Tensor:
+        t = torch.empty(shape, dtype=dtype or self.adt, device=self.dev)
+        cuda_memset0(t)
+        return t
+
+    # ---------------------------------------------------------------- parameters
+    def p(self, name: str) -> torch.Tensor:
+        return self.params[name]
+
+    def w(self, name: str) -> torch.Tensor:
+        """Parameter as a GEMM operand in the activation dtype (cast once per parameter version)."""
+        par = self.params[name]
+        if self.adt == torch.float32:
+            return par
+        t = self._w.get(name)
+        if t is None:
+            key = (par.data_ptr(), par._version, tuple(par.shape))
+            ent = self.wcache.get(name)
+            if ent is None or ent[0] != key:
+                out = torch.empty(par.shape, dtype=self.adt, device=par.device)
+                L.check(self.lib.jmt_cast(_ptr(par), L.F32, _ptr(out), self.acode, par.numel(), _stream()), "jmt_cast")
+                ent = (key, out)
+                self.wcache[name] = ent
+            t = ent[1]
+            self._w[name] = t
+        return t
+
+    def prepare_param_grads(self, names: Sequence[str]):
+        """Allocate the flat fp32 gradient bucket (zeroed) with one 256-byte aligned view per parameter."""
+        total = 0
+        offs = []
+        for n in names:
+            k = self.params[n].numel()
+            offs.append((n, total, k))
+            total += (k + 63) // 64 * 64
+        self.bucket = self.zeros((max(total, 64),), torch.float32)
+        for n, o, k in offs:
+            self.pgrads[n] = self.bucket[o:o + k].view(self.params[n].shape)
+
+    def pgrad(self, name: str) -> torch.Tensor:
+        return self.pgrads[name]
+
+    # ---------------------------------------------------------------- gradient plumbing
+    def grad_target(self, v: Var) -> Tuple[torch.Tensor, int]:
+        """Tensor to write d(v) into and the store mode (STORE the first time, ACCUMULATE after)."""
+        if v.gbuf is None:
+            v.gbuf = GradBuf(self.empty(v.data.shape, v.data.dtype))
+            return v.gbuf.t, L.STORE
+        if v.gbuf.refs > 1:                       # buffer aliased by another Var: copy-on-write
+            old = v.gbuf
+            new = self.empty(old.t.shape, old.t.dtype)
+            copy2d(self, old.t, new)
+            old.refs -= 1
+            v.gbuf = GradBuf(new)
+        return v.gbuf.t, L.ACCUMULATE
+
+    def add_grad(self, v: Var, gb: GradBuf):
+        """d(v) += gb.  A Var without gradient aliases the buffer (ref-counted) instead of copying."""
+        if not v.needs_grad:
+            return
+        if v.gbuf is None:
+            gb.refs += 1
+            v.gbuf = gb
+            return
+        t, _ = self.grad_target(v)
+        g = gb.t
+        assert g.is_contiguous() and t.is_contiguous()
+        L.check(self.lib.jmt_axpy(_ptr(g), _ptr(t), 1.0, g.numel(), _DT[g.dtype], _stream()), "jmt_axpy")
+
+    def release(self, v: Var):
+        if v.gbuf is not None:
+            v.gbuf.refs -= 1
+            v.gbuf = None
+
+    def backward(self):
+        for fn in reversed(self.tape):
+            fn()
+        self.tape = []
+
+
+# --------------------------------------------------------------------------- raw op wrappers
+def gemm(ctx: Ctx, a: torch.Tensor, b: torch.Tensor, d: torch.Tensor, *, M: int, N: int, K: int,
+         a_major=L.MAJOR_K, b_major=L.MAJOR_K, a_rows=None, b_rows=None, a_ld=None, b_ld=None, d_ld=None,
+         nb0=1, nb1=1, a_bs=(0, 0), b_bs=(0, 0), d_bs=(0, 0), bias=None, act=L.ACT_NONE, slope=0.0, alpha=1.0,
+         store=L.STORE, ntaps=1, a_shift=(0, 0), b_shift=(0, 0), reduce_batch=False, split_k=1):
+    """One GEMM of the family in include/jmt_b200.h.  a/b/d supply base pointers and dtypes (views
+    allowed); strides are in elements."""
+    require_cuda(a, b, d)
+    g = L.GemmDesc()
+    g.a, g.b, g.d = a.data_ptr(), b.data_ptr(), d.data_ptr()
+    g.bias = bias.data_ptr() if bias is not None else None
+    g.a_major, g.b_major = a_major, b_major
+    g.M, g.N, g.K = M, N, K
+    g.a_rows = a_rows if a_rows is not None else (M if a_major == L.MAJOR_K else K)
+    g.b_rows = b_rows if b_rows is not None else (N if b_major == L.MAJOR_K else K)
+    g.a_ld = a_ld if a_ld is not None else a.stride(-2)
+    g.b_ld = b_ld if b_ld is not None else b.stride(-2)
+    g.d_ld = d_ld if d_ld is not None else d.stride(-2)
+    g.a_bs0, g.a_bs1 = a_bs
+    g.b_bs0, g.b_bs1 = b_bs
+    g.d_bs0, g.d_bs1 = d_bs
+    g.nb0, g.nb1 = nb0, nb1
+    g.d_dtype = _DT[d.dtype]
+    g.act, g.alpha, g.slope = act, alpha, slope
+    g.store_mode = store
+    g.ntaps = ntaps
+    g.a_shift0, g.a_shift_step = a_shift
+    g.b_shift0, g.b_shift_step = b_shift
+    g.reduce_batch = 1 if reduce_batch else 0
+    g.split_k = split_k
+    if a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16:
+        L.check(ctx.lib.jmt_gemm_bf16(C.byref(g), _stream()), "jmt_gemm_bf16")
+    elif a.dtype == torch.float32 and b.dtype == torch.float32:
+        L.check(ctx.lib.jmt_gemm_f32(C.byref(g), _stream()), "jmt_gemm_f32")
+    else:
+        raise RuntimeError(f"gemm operand dtypes {a.dtype}/{b.dtype}")
+
+
+def copy2d(ctx: Ctx, src: torch.Tensor, dst: torch.Tensor):
+    """dst[r, c] = cast(src[r, c]) for 2-D views with unit inner stride."""
+    src = src.reshape(-1, src.shape[-1]) if src.dim() != 2 else src
+    dst = dst.reshape(-1, dst.shape[-1]) if dst.dim() != 2 else dst
+    rows, cols = src.shape
+    assert src.stride(1) == 1 and dst.stride(1) == 1 and tuple(dst.shape) == (rows, cols)
+    L.check(ctx.lib.jmt_copy2d(_ptr(src), _DT[src.dtype], src.stride(0), _ptr(dst), _DT[dst.dtype], dst.stride(0),
+                               rows, cols, _stream()), "jmt_copy2d")
+
+
+def split_k_for(red: int, tiles: int) -> int:
+    """Split factor for weight-gradient GEMMs: `red` reduction rows, `tiles` output tiles."""
+    kblocks = max(1, (red + 63) // 64)
+    want = max(1, (148 * 2) // max(1, tiles))
+    return max(1, min(want, kblocks // 4)) if kblocks >= 8 else 1
+
+
+# --------------------------------------------------------------------------- differentiable ops
+def from_external(ctx: Ctx, x: torch.Tensor, needs_grad: bool):
+    """External (.., D) tensor -> activation-dtype Var (cast copy).  Returns (Var, grad getter)."""
+    require_cuda(x)
+    x2 = x.reshape(-1, x.shape[-1])
+    if x2.stride(-1) != 1 or x2.dtype not in _DT:
+        raise RuntimeError("inputs must be fp32/bf16 with a contiguous feature dimension")
+    out = ctx.empty(x2.shape)
+    copy2d(ctx, x2, out)
+    v = Var(out, needs_grad)
+    holder: dict = {}
+    if ctx.record and needs_grad:
+        def bwd():
+            dx = ctx.empty(x2.shape, torch.float32)
+            if v.grad is None:
+                cuda_memset0(dx)
+            else:
+                copy2d(ctx, v.grad, dx)
+            ctx.release(v)
+            holder["dx"] = dx
+        ctx.tape.append(bwd)
+        return v, (lambda: holder["dx"])
+    return v, None
+
+
+def l2norm(ctx: Ctx, x: torch.Tensor, needs_grad: bool):
+    """F.normalize over the last dim of an external (.., D) tensor -> activation-dtype Var.
+    Returns (Var, getter of d(input) in fp32 valid after backward, or None)."""
+    require_cuda(x)
+    x2 = x.reshape(-1, x.shape[-1])
+    if x2.stride(-1) != 1 or x2.dtype not in _DT:
+        raise RuntimeError("inputs must be fp32/bf16 with a contiguous feature dimension")
+    rows, D = x2.shape
+    out = ctx.empty((rows, D))
+    rec = ctx.record and needs_grad
+    inv = ctx.empty((rows,), torch.float32) if rec else None
+    L.check(ctx.lib.jmt_l2norm_fwd(_ptr(x2), _DT[x2.dtype], x2.stride(0), _ptr(out), ctx.acode, rows, D, 1e-12,
+                                   _ptr(inv), _stream()), "jmt_l2norm_fwd")
+    v = Var(out, needs_grad)
+    holder: dict = {}
+    if rec:
+        def bwd():
+            dx = ctx.empty((rows, D), torch.float32)
+            if v.grad is None:
+                cuda_memset0(dx)
+            else:
+                L.check(ctx.lib.jmt_l2norm_bwd(_ptr(v.grad), _ptr(out), ctx.acode, _ptr(inv), 1e-12, _ptr(dx), rows, D,
+                                               _stream()), "jmt_l2norm_bwd")
+            ctx.release(v)
+            holder["dx"] = dx
+        ctx.tape.append(bwd)
+        return v, (lambda: holder["dx"])
+    return v, None
+
+
+def linear(ctx: Ctx, x: Var, wname: str, bname: Optional[str], act=L.ACT_NONE, slope=0.0,
+           out: Optional[torch.Tensor] = None, w_rows: Optional[Tuple[int, int]] = None,
+           w_cols: Optional[Tuple[int, int]] = None, accumulate_into: Optional[Var] = None,
+           grad_from: Optional[Tuple[Var, int, int]] = None) -> Var:
+    """y = act(x W[r0:r1, c0:c1]^T + b[r0:r1])  (nn.Linear).  ``out`` may be a strided (rows, N) view
+    (concat-free epilogue: a GEMM writes straight into its slice of a wider buffer);
+    ``accumulate_into`` adds into an existing Var (Linear over a concatenation = sum of Linears over
+    column blocks of W, FeatureConcatFC / out_layer_pv without materialising the cat)."""
+    W = ctx.w(wname)
+    if W.dim() == 3:                       # 1x1 Conv1d weight (cout, cin, 1)
+        W = W.view(W.shape[0], W.shape[1])
+    r0, r1 = w_rows if w_rows else (0, W.shape[0])
+    c0, c1 = w_cols if w_cols else (0, W.shape[1])
+    Wv = W[r0:r1, c0:c1]
+    N, K = r1 - r0, c1 - c0
+    M = x.data.shape[0]
+    assert x.data.shape[1] == K, (tuple(x.data.shape), K, wname)
+    bias = ctx.p(bname)[r0:r1] if bname else None
+    if accumulate_into is not None:
+        assert act == L.ACT_NONE
+        y = accumulate_into
+        gemm(ctx, x.data, Wv, y.data, M=M, N=N, K=K, bias=bias, store=L.ACCUMULATE)
+    else:
+        if out is None:
+            out = ctx.empty((M, N))
+        y = Var(out)
+        gemm(ctx, x.data, Wv, out, M=M, N=N, K=K, bias=bias, act=act, slope=slope)
+    if ctx.record:
+        def bwd():
+            if grad_from is not None:          # `out` is a column slice of a wider buffer owned by grad_from[0]
+                pg = grad_from[0].grad
+                dy = None if pg is None else pg[:, grad_from[1]:grad_from[2]]
+            else:
+                dy = y.grad
+            if dy is None:
+                return
+            if act != L.ACT_NONE:
+                assert dy.is_contiguous() and y.data.is_contiguous()
+                L.check(ctx.lib.jmt_act_bwd(_ptr(dy), _ptr(y.data), _ptr(dy), dy.numel(), slope, _DT[dy.dtype],
+                                            _stream()), "jmt_act_bwd")
+            if bname:
+                L.check(ctx.lib.jmt_colsum(_ptr(dy), _DT[dy.dtype], dy.stride(0), M, N, _ptr(ctx.pgrad(bname)[r0:r1]),
+                                           _stream()), "jmt_colsum")
+            # dW[r0:r1, c0:c1] += dy^T x   (both operands MN-major, split-K over the M rows, fp32 atomics)
+            dWf = ctx.pgrad(wname)
+            if dWf.dim() == 3:
+                dWf = dWf.view(dWf.shape[0], dWf.shape[1])
+            dW = dWf[r0:r1, c0:c1]
+            tiles = ((N + 127) // 128) * ((K + 255) // 256)
+            gemm(ctx, dy, x.data, dW, M=N, N=K, K=M, a_major=L.MAJOR_MN, b_major=L.MAJOR_MN,
+                 store=L.ATOMIC_ADD, split_k=split_k_for(M, tiles))
+            if x.needs_grad:
+                dx, mode = ctx.grad_target(x)
+                gemm(ctx, dy, Wv, dx, M=M, N=K, K=N, b_major=L.MAJOR_MN, store=mode)
+            if accumulate_into is None:
+                ctx.release(y)
+        ctx.tape.append(bwd)
+    return y
+
+
+def add_layernorm(ctx: Ctx, x: Var, res: Optional[Var], gname: str, bname: str) -> Var:
+    """LayerNorm(x + res) with affine params (post-LN residual, mm_multi_transformers.py:62-69)."""
+    rows, D = x.data.shape
+    assert x.data.is_contiguous() and (res is None or res.data.is_contiguous())
+    y = ctx.empty((rows, D))
+    mean = ctx.empty((rows,), torch.float32)
+    rstd = ctx.empty((rows,), torch.float32)
+    L.check(ctx.lib.jmt_add_layernorm_fwd(_ptr(x.data), _ptr(res.data) if res else None, _ptr(ctx.p(gname)),
+                                          _ptr(ctx.p(bname)), 1e-5, _ptr(y), _ptr(mean), _ptr(rstd), rows, D, ctx.acode,
+                                          _stream()), "jmt_add_layernorm_fwd")
+    out = Var(y)
+    if ctx.record:
+        def bwd():
+            dy = out.grad
+            if dy is None:
+                return
+            assert dy.is_contiguous()
+            dz = GradBuf(ctx.empty((rows, D)))
+            L.check(ctx.lib.jmt_add_layernorm_bwd(_ptr(dy), _ptr(x.data), _ptr(res.data) if res else None,
+                                                  _ptr(ctx.p(gname)), _ptr(mean), _ptr(rstd), _ptr(dz.t), 0,
+                                                  _ptr(ctx.pgrad(gname)), _ptr(ctx.pgrad(bname)), rows, D, ctx.acode,
+                                                  _stream()), "jmt_add_layernorm_bwd")
+            ctx.add_grad(x, dz)
+            if res is not None:
+                ctx.add_grad(res, dz)
+            dz.refs -= 1            # drop the creator's reference
+            ctx.release(out)
+        ctx.tape.append(bwd)
+    return out
+
+
+class AttnGeom:
+    """How (seq, batch) index the rows of a (rows, E) activation matrix.
+    Standard (B, T, E): seq_stride=1, batch_stride=T.  Attention across the batch dimension
+    (MultimodalTransformer_wo_JR encoders): seq = b (stride T), batch = t (stride 1)."""
+
+    def __init__(self, seq: int, batch: int, seq_stride: int, batch_stride: int):
+        self.seq, self.batch, self.seq_stride, self.batch_stride = seq, batch, seq_stride, batch_stride
+
+
+def _proj_grad(ctx: Ctx, v: Var) -> torch.Tensor:
+    """Gradient buffer of a projection matrix whose column slices are written by attention backward
+    (zero-filled on first touch, then accumulated)."""
+    if v.gbuf is None:
+        v.gbuf = GradBuf(ctx.zeros(v.data.shape, v.data.dtype))
+    elif v.gbuf.refs > 1:
+        ctx.grad_target(v)
+    return v.gbuf.t
+
+
+def attention_core(ctx: Ctx, q: Var, qcol: int, k: Var, kcol: int, v: Var, vcol: int, E: int, heads: int,
+                   gq: AttnGeom, gk: AttnGeom) -> Var:
+    """softmax((Q/sqrt(dh)) K^T) V per (batch, head) -- torch's MHA math path minus the
+    head-averaged weights the reference discards.  q/k/v are column slices [col, col+E) of projection
+    matrices; the output (rows_q, E) is laid out like q's rows."""
+    dh = E // heads
+    Lq, S, NB = gq.seq, gk.seq, gq.batch
+    assert gk.batch == NB and E % heads == 0
+    s_ld = (S + 7) // 8 * 8
+    scale = 1.0 / math.sqrt(dh)
+    qd, kd, vd = q.data[:, qcol:qcol + E], k.data[:, kcol:kcol + E], v.data[:, vcol:vcol + E]
+    qld, kld, vld = q.data.stride(0), k.data.stride(0), v.data.stride(0)
+    sb = (Lq * s_ld, heads * Lq * s_ld)
+    scores = ctx.empty((NB, heads, Lq, s_ld), torch.float32)
+    gemm(ctx, qd, kd, scores, M=Lq, N=S, K=dh, a_rows=Lq, b_rows=S,
+         a_ld=gq.seq_stride * qld, b_ld=gk.seq_stride * kld, d_ld=s_ld,
+         nb0=heads, nb1=NB, a_bs=(dh, gq.batch_stride * qld), b_bs=(dh, gk.batch_stride * kld), d_bs=sb, alpha=scale)
+    probs = ctx.empty((NB, heads, Lq, s_ld))
+    rows = NB * heads * Lq
+    L.check(ctx.lib.jmt_softmax_fwd(_ptr(scores), s_ld, _ptr(probs), ctx.acode, s_ld, rows, S, _stream()), "jmt_softmax_fwd")
+    del scores
+    o = ctx.empty((q.data.shape[0], E))
+    gemm(ctx, probs, vd, o, M=Lq, N=dh, K=S, a_rows=Lq, b_major=L.MAJOR_MN, b_rows=S,
+         a_ld=s_ld, b_ld=gk.seq_stride * vld, d_ld=gq.seq_stride * E,
+         nb0=heads, nb1=NB, a_bs=sb, b_bs=(dh, gk.batch_stride * vld), d_bs=(dh, gq.batch_stride * E))
+    out = Var(o)
+    if ctx.record:
+        def bwd():
+            do = out.grad
+            if do is None:
+                return
+            assert do.is_contiguous()
+            dp = ctx.empty((NB, heads, Lq, s_ld), torch.float32)          # dP = dO V^T
+            gemm(ctx, do, vd, dp, M=Lq, N=S, K=dh, a_rows=Lq, b_rows=S,
+                 a_ld=gq.seq_stride * E, b_ld=gk.seq_stride * vld, d_ld=s_ld,
+                 nb0=heads, nb1=NB, a_bs=(dh, gq.batch_stride * E), b_bs=(dh, gk.batch_stride * vld), d_bs=sb)
+            ds = ctx.empty((NB, heads, Lq, s_ld))
+            L.check(ctx.lib.jmt_softmax_bwd(_ptr(probs), ctx.acode, s_ld, _ptr(dp), s_ld, _ptr(ds), ctx.acode, s_ld,
+                                            rows, S, _stream()), "jmt_softmax_bwd")
+            del dp
+            gv = _proj_grad(ctx, v)                                        # dV = P^T dO
+            gemm(ctx, probs, do, gv[:, vcol:vcol + E], M=S, N=dh, K=Lq, a_major=L.MAJOR_MN, b_major=L.MAJOR_MN,
+                 a_rows=Lq, b_rows=Lq, a_ld=s_ld, b_ld=gq.seq_stride * E, d_ld=gk.seq_stride * gv.stride(0),
+                 nb0=heads, nb1=NB, a_bs=sb, b_bs=(dh, gq.batch_stride * E), d_bs=(dh, gk.batch_stride * gv.stride(0)),
+                 store=L.ACCUMULATE)
+            gq_ = _proj_grad(ctx, q)                                       # dQ = scale * dS K
+            gemm(ctx, ds, kd, gq_[:, qcol:qcol + E], M=Lq, N=dh, K=S, a_rows=Lq, b_major=L.MAJOR_MN, b_rows=S,
+                 a_ld=s_ld, b_ld=gk.seq_stride * kld, d_ld=gq.seq_stride * gq_.stride(0),
+                 nb0=heads, nb1=NB, a_bs=sb, b_bs=(dh, gk.batch_stride * kld), d_bs=(dh, gq.batch_stride * gq_.stride(0)),
+                 alpha=scale, store=L.ACCUMULATE)
+            gk_ = _proj_grad(ctx, k)                                       # dK = scale * dS^T Q
+            gemm(ctx, ds, qd, gk_[:, kcol:kcol + E], M=S, N=dh, K=Lq, a_major=L.MAJOR_MN, b_major=L.MAJOR_MN,
+                 a_rows=Lq, b_rows=Lq, a_ld=s_ld, b_ld=gq.seq_stride * qld, d_ld=gk.seq_stride * gk_.stride(0),
+                 nb0=heads, nb1=NB, a_bs=sb, b_bs=(dh, gq.batch_stride * qld), d_bs=(dh, gk.batch_stride * gk_.stride(0)),
+                 alpha=scale, store=L.ACCUMULATE)
+            ctx.release(out)
+        ctx.tape.append(bwd)
+    return out
+
+
+def attention_small(ctx: Ctx, qkv: Var, Lseq: int, N: int, E: int, heads: int) -> Var:
+    """Self-attention over tiny sequences (L <= 8): qkv is (L*N, 3E) with row = l*N + n."""
+    scale = 1.0 / math.sqrt(E // heads)
+    assert qkv.data.is_contiguous()
+    o = ctx.empty((Lseq * N, E))
+    probs = ctx.empty((N * heads, Lseq, Lseq), torch.float32)
+    L.check(ctx.lib.jmt_attn_small_fwd(_ptr(qkv.data), _ptr(o), _ptr(probs), Lseq, N, E, heads, scale, ctx.acode,
+                                       _stream()), "jmt_attn_small_fwd")
+    out = Var(o)
+    if ctx.record:
+        def bwd():
+            do = out.grad
+            if do is None:
+                return
+            assert do.is_contiguous()
+            dq = GradBuf(ctx.empty(qkv.data.shape))
+            L.check(ctx.lib.jmt_attn_small_bwd(_ptr(qkv.data), _ptr(do), _ptr(probs), _ptr(dq.t), Lseq, N, E, heads,
+                                               scale, ctx.acode, _stream()), "jmt_attn_small_bwd")
+            ctx.add_grad(qkv, dq)
+            dq.refs -= 1
+            ctx.release(out)
+        ctx.tape.append(bwd)
+    return out
+
+
+def mha_self(ctx: Ctx, x: Var, prefix: str, heads: int, geom: Optional[AttnGeom], small: Optional[Tuple[int, int]] = None) -> Var:
+    """nn.MultiheadAttention(x, x, x): packed QKV projection (one N=3E GEMM), attention, out-proj."""
+    E = x.data.shape[1]
+    qkv = linear(ctx, x, prefix + "in_proj_weight", prefix + "in_proj_bias")
+    if small is not None:
+        o = attention_small(ctx, qkv, small[0], small[1], E, heads)
+    else:
+        o = attention_core(ctx, qkv, 0, qkv, E, qkv, 2 * E, E, heads, geom, geom)
+    return linear(ctx, o, prefix + "out_proj.weight", prefix + "out_proj.bias")
+
+
+def mha_cross(ctx: Ctx, xq: Var, xkv: Var, prefix: str, heads: int, gq: AttnGeom, gk: AttnGeom,
+              out: Optional[torch.Tensor] = None, grad_from=None) -> Var:
+    """nn.MultiheadAttention(xq, xkv, xkv).  The Q projection of a module applied twice to the same
+    query (cross_attention_{v,p,pv} in MultimodalTransformer_w_JR) is computed once."""
+    E = xq.data.shape[1]
+    key = (prefix, id(xq))
+    q = ctx.qcache.get(key)
+    if q is None:
+        q = linear(ctx, xq, prefix + "in_proj_weight", prefix + "in_proj_bias", w_rows=(0, E))
+        ctx.qcache[key] = q
+    kv = linear(ctx, xkv, prefix + "in_proj_weight", prefix + "in_proj_bias", w_rows=(E, 3 * E))
+    o = attention_core(ctx, q, 0, kv, 0, kv, E, E, heads, gq, gk)
+    return linear(ctx, o, prefix + "out_proj.weight", prefix + "out_proj.bias", out=out, grad_from=grad_from)
+
+
+def encoder_layer(ctx: Ctx, x: Var, prefix: str, heads: int, geom: Optional[AttnGeom], small=None) -> Var:
+    """TransformerEncoderLayer.forward (mm_multi_transformers.py:60-70): post-LN MHA + ReLU FFN."""
+    a = mha_self(ctx, x, prefix + "attention.", heads, geom, small)
+    x1 = add_layernorm(ctx, x, a, prefix + "layer_norm1.weight", prefix + "layer_norm1.bias")
+    h = linear(ctx, x1, prefix + "feed_forward.0.weight", prefix + "feed_forward.0.bias", act=L.ACT_RELU)
+    f = linear(ctx, h, prefix + "feed_forward.2.weight", prefix + "feed_forward.2.bias")
+    return add_layernorm(ctx, x1, f, prefix + "layer_norm2.weight", prefix + "layer_norm2.bias")
+
+
+def encoder_block(ctx: Ctx, x: Var, prefix: str, heads: int, layers: int, geom, small=None) -> Var:
+    for i in range(layers):
+        x = encoder_layer(ctx, x, f"{prefix}layers.{i}.", heads, geom, small)
+    return x
+
+
+def dropout(ctx: Ctx, x: Var, p: float) -> Tuple[Var, float]:
+    """nn.Dropout(p) in training mode with a Philox keep-mask (replayed in backward).  Identity (and no
+    kernel) when p == 0 or in eval mode.  Returns (Var, scale)."""
+    if p <= 0.0 or not ctx.training:
+        return x, 1.0
+    n = x.data.numel()
+    assert x.data.is_contiguous()
+    mask = ctx.empty((n,), torch.uint8)
+    L.check(ctx.lib.jmt_dropout_mask(_ptr(mask), n, p, ctx.seed, ctx.rng_offset, _stream()), "jmt_dropout_mask")
+    ctx.rng_offset += (n + 3) // 4
+    scale = 1.0 / (1.0 - p)
+    y = ctx.empty(x.data.shape)
+    L.check(ctx.lib.jmt_apply_mask(_ptr(x.data), _ptr(mask), _ptr(y), 1, 1, n, 0, scale, ctx.acode, _stream()), "jmt_apply_mask")
+    out = Var(y)
+    if ctx.record:
+        def bwd():
+            dy = out.grad
+            if dy is None:
+                return
+            dx = GradBuf(ctx.empty(x.data.shape))
+            L.check(ctx.lib.jmt_apply_mask(_ptr(dy), _ptr(mask), _ptr(dx.t), 1, 1, n, 0, scale, ctx.acode, _stream()), "jmt_apply_mask")
+            ctx.add_grad(x, dx)
+            dx.refs -= 1
+            ctx.release(out)
+        ctx.tape.append(bwd)
+    return out, scale
+
+
+def _ptr_array(ctx: Ctx, tensors):
+    arr = (C.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+    ctx.keep.append(arr)
+    return arr
+
+
+def regressor_tail(ctx: Ctx, hidden: List[Var], wnames: List[str], bnames: List[str], w_row: List[int],
+                   B: int, T: int, time_major: bool):
+    """Final Linear(128, k) of the heads as one fused kernel over G groups (hidden[g] may repeat).
+    Returns (list of fp32 output tensors, list of output 'grad setters')."""
+    G = len(hidden)
+    M = B * T
+    shape = (T, B) if time_major else (B, T)
+    sb, st = (1, B) if time_major else (T, 1)
+    outs = [ctx.empty(shape, torch.float32) for _ in range(G)]
+    ws = [ctx.p(wnames[g])[w_row[g]] for g in range(G)]
+    bs = [ctx.p(bnames[g])[w_row[g]:w_row[g] + 1] for g in range(G)]
+    hl = [h.data for h in hidden]
+    h_ld = hl[0].stride(0)
+    assert all(h.stride(0) == h_ld and h.shape[1] == 128 for h in hl)
+    L.check(ctx.lib.jmt_regressor_tail_fwd(G, _ptr_array(ctx, hl), h_ld, ctx.acode, _ptr_array(ctx, ws), _ptr_array(ctx, bs),
+                                           _ptr_array(ctx, outs), M, T, sb, st, _stream()), "jmt_regressor_tail_fwd")
+    gouts: List[Optional[torch.Tensor]] = [None] * G
+    if ctx.record:
+        def bwd():
+            dhs, acc, seen = [], [], {}
+            for g in range(G):
+                hv = hidden[g]
+                if id(hv) in seen:
+                    dhs.append(seen[id(hv)].t)
+                    acc.append(1)
+                else:
+                    gb = GradBuf(ctx.empty(hv.data.shape))
+                    seen[id(hv)] = gb
+                    dhs.append(gb.t)
+                    acc.append(0)
+            douts = []
+            for g in range(G):
+                d = gouts[g]
+                if d is None:
+                    d = ctx.zeros(shape, torch.float32)
+                douts.append(d.contiguous().to(torch.float32) if (not d.is_contiguous() or d.dtype != torch.float32) else d)
+            dws = [ctx.pgrad(wnames[g])[w_row[g]] for g in range(G)]
+            dbs = [ctx.pgrad(bnames[g])[w_row[g]:w_row[g] + 1] for g in range(G)]
+            acc_arr = (C.c_int * G)(*acc)
+            sc_arr = (C.c_float * G)(*([1.0] * G))
+            ctx.keep += [acc_arr, sc_arr]
+            L.check(ctx.lib.jmt_regressor_tail_bwd(G, _ptr_array(ctx, hl), h_ld, ctx.acode, _ptr_array(ctx, ws),
+                                                   _ptr_array(ctx, douts), _ptr_array(ctx, dhs), acc_arr, sc_arr,
+                                                   _ptr_array(ctx, dws), _ptr_array(ctx, dbs), M, T, sb, st, _stream()),
+                    "jmt_regressor_tail_bwd")
+            done = set()
+            for g in range(G):
+                hv = hidden[g]
+                if id(hv) in done:
+                    continue
+                done.add(id(hv))
+                gb = seen[id(hv)]
+                ctx.add_grad(hv, gb)
+                gb.refs -= 1
+        ctx.tape.append(bwd)
+
+    def set_gout(g, t):
+        gouts[g] = t
+    return outs, set_gout
+
+
+# --------------------------------------------------------------------------- TCN ops
+def transpose_in(ctx: Ctx, x: torch.Tensor, needs_grad: bool):
+    """(N, C, L) external tensor -> channels-last activation Var of shape (N*L, C)."""
+    require_cuda(x)
+    xc = x.contiguous()
+    if xc.dtype not in _DT:
+        raise RuntimeError(f"unsupported input dtype {xc.dtype}")
+    N, Cc, Ls = xc.shape
+    out = ctx.empty((N * Ls, Cc))
+    L.check(ctx.lib.jmt_transpose(_ptr(xc), _DT[xc.dtype], _ptr(out), ctx.acode, N, Cc, Ls, _stream()), "jmt_transpose")
+    v = Var(out, needs_grad)
+    holder: dict = {}
+    if ctx.record and needs_grad:
+        def bwd():
+            dx = ctx.empty((N, Cc, Ls), torch.float32)
+            if v.grad is None:
+                cuda_memset0(dx)
+            else:
+                L.check(ctx.lib.jmt_transpose(_ptr(v.grad), ctx.acode, _ptr(dx), L.F32, N, Ls, Cc, _stream()), "jmt_transpose")
+            ctx.release(v)
+            holder["dx"] = dx
+        ctx.tape.append(bwd)
+        return v, (lambda: holder["dx"])
+    return v, None
+
+
+def weight_norm_conv_weights(ctx: Ctx, prefix: str, cout: int, cin: int, k: int):
+    """w = g * v / ||v|| (legacy weight_norm), emitted in the two implicit-GEMM layouts:
+    forward (Cout, k*Cin) tap-major and dgrad (Cin, k*Cout).  Records the weight_norm backward that turns
+    the fp32 tap-major dW into d(weight_g), d(weight_v)."""
+    g, v = ctx.p(prefix + "weight_g"), ctx.p(prefix + "weight_v")
+    w_fwd = ctx.empty((cout, k * cin))
+    w_dg = ctx.empty((cin, k * cout)) if ctx.record else None
+    norm = ctx.empty((cout,), torch.float32)
+    L.check(ctx.lib.jmt_weight_norm_fwd(_ptr(g), _ptr(v), _ptr(w_fwd), _ptr(w_dg), ctx.acode, _ptr(norm), cout, cin, k,
+                                        _stream()), "jmt_weight_norm_fwd")
+    dw = {"t": None}
+    if ctx.record:
+        def bwd():
+            if dw["t"] is None:
+                return
+            L.check(ctx.lib.jmt_weight_norm_bwd(_ptr(dw["t"]), _ptr(g), _ptr(v), _ptr(norm),
+                                                _ptr(ctx.pgrad(prefix + "weight_g")), _ptr(ctx.pgrad(prefix + "weight_v")),
+                                                cout, cin, k, _stream()), "jmt_weight_norm_bwd")
+        ctx.tape.append(bwd)
+    return w_fwd, w_dg, dw
+
+
+def causal_conv(ctx: Ctx, x: Var, prefix: str, N: int, Ls: int, cin: int, cout: int, k: int, dil: int, act: int) -> Var:
+    """weight-normed dilated causal Conv1d + Chomp1d + LeakyReLU (temporal_convolutional_model.py:24-28)
+    as an implicit GEMM on channels-last data: taps are K blocks whose A rows are shifted by
+    -(k-1-j)*dil inside each sequence; rows before t=0 come back as zeros (TMA OOB fill / predicate)."""
+    w_fwd, w_dg, dwh = weight_norm_conv_weights(ctx, prefix, cout, cin, k)   # recorded first => runs last in backward
+    y = ctx.empty((N * Ls, cout))
+    bias = ctx.p(prefix + "bias")
+    gemm(ctx, x.data, w_fwd, y, M=Ls, N=cout, K=cin, a_rows=Ls, b_rows=cout, a_ld=cin, b_ld=k * cin, d_ld=cout,
+         nb0=1, nb1=N, a_bs=(0, Ls * cin), d_bs=(0, Ls * cout), bias=bias, act=act, slope=LEAKY_SLOPE,
+         ntaps=k, a_shift=(-(k - 1) * dil, dil))
+    out = Var(y)
+    if ctx.record:
+        def bwd():
+            dy = out.grad
+            if dy is None:
+                return
+            assert dy.is_contiguous()
+            if act != L.ACT_NONE:
+                L.check(ctx.lib.jmt_act_bwd(_ptr(dy), _ptr(y), _ptr(dy), dy.numel(), LEAKY_SLOPE, _DT[dy.dtype], _stream()),
+                        "jmt_act_bwd")
+            L.check(ctx.lib.jmt_colsum(_ptr(dy), _DT[dy.dtype], cout, N * Ls, cout, _ptr(ctx.pgrad(prefix + "bias")), _stream()),
+                    "jmt_colsum")
+            # wgrad per tap: dW_j (Cout, Cin) = sum_n dy_n^T shift_j(x_n); reduction over (n, t)
+            dw = ctx.zeros((cout, k * cin), torch.float32)
+            tiles = ((cout + 127) // 128) * ((cin + 255) // 256)
+            sk = split_k_for(N * Ls, tiles * k)
+            for j in range(k):
+                gemm(ctx, dy, x.data, dw[:, j * cin:(j + 1) * cin], M=cout, N=cin, K=Ls,
+                     a_major=L.MAJOR_MN, b_major=L.MAJOR_MN, a_rows=Ls, b_rows=Ls, a_ld=cout, b_ld=cin, d_ld=k * cin,
+                     nb0=1, nb1=N, a_bs=(0, Ls * cout), b_bs=(0, Ls * cin), b_shift=(-(k - 1 - j) * dil, 0),
+                     reduce_batch=True, store=L.ATOMIC_ADD, split_k=sk)
+            dwh["t"] = dw
+            if x.needs_grad:
+                # dgrad: dx[t] = sum_j W_j^T dy[t + (k-1-j) dil]
+                dx, mode = ctx.grad_target(x)
+                gemm(ctx, dy, w_dg, dx, M=Ls, N=cin, K=cout, a_rows=Ls, b_rows=cin, a_ld=cout, b_ld=k * cout, d_ld=cin,
+                     nb0=1, nb1=N, a_bs=(0, Ls * cout), d_bs=(0, Ls * cin), ntaps=k, a_shift=((k - 1) * dil, -dil),
+                     store=mode)
+            ctx.release(out)
+        ctx.tape.append(bwd)
+    return out
+
+
+def channel_dropout(ctx: Ctx, x: Var, p: float, N: int, Ls: int, Cc: int) -> Var:
+    """nn.Dropout2d on (N, C, L) = drop whole channels per sample; training only."""
+    if p <= 0.0 or not ctx.training:
+        return x
+    mask = ctx.empty((N * Cc,), torch.uint8)
+    L.check(ctx.lib.jmt_dropout_mask(_ptr(mask), N * Cc, p, ctx.seed, ctx.rng_offset, _stream()), "jmt_dropout_mask")
+    ctx.rng_offset += (N * Cc + 3) // 4
+    scale = 1.0 / (1.0 - p)
+    y = ctx.empty(x.data.shape)
+    L.check(ctx.lib.jmt_apply_mask(_ptr(x.data), _ptr(mask), _ptr(y), N, Ls, Cc, 1, scale, ctx.acode, _stream()), "jmt_apply_mask")
+    out = Var(y)
+    if ctx.record:
+        def bwd():
+            dy = out.grad
+            if dy is None:
+                return
+            dx = GradBuf(ctx.empty(x.data.shape))
+            L.check(ctx.lib.jmt_apply_mask(_ptr(dy), _ptr(mask), _ptr(dx.t), N, Ls, Cc, 1, scale, ctx.acode, _stream()), "jmt_apply_mask")
+            ctx.add_grad(x, dx)
+            dx.refs -= 1
+            ctx.release(out)
+        ctx.tape.append(bwd)
+    return out
+
+
+def add_act(ctx: Ctx, a: Var, b: Var, act: int, slope: float) -> Var:
+    """act(a + b)  (TemporalBlock residual, temporal_convolutional_model.py:54-57)."""
+    assert a.data.is_contiguous() and b.data.is_contiguous()
+    y = ctx.empty(a.data.shape)
+    L.check(ctx.lib.jmt_add_act(_ptr(a.data), _ptr(b.data), _ptr(y), y.numel(), act, slope, ctx.acode, _stream()), "jmt_add_act")
+    out = Var(y)
+    if ctx.record:
+        def bwd():
+            dy = out.grad
+            if dy is None:
+                return
+            dz = GradBuf(ctx.empty(y.shape))
+            L.check(ctx.lib.jmt_act_bwd(_ptr(dy), _ptr(y), _ptr(dz.t), y.numel(), slope, ctx.acode, _stream()), "jmt_act_bwd")
+            ctx.add_grad(a, dz)
+            ctx.add_grad(b, dz)
+            dz.refs -= 1
+            ctx.release(out)
+        ctx.tape.append(bwd)
+    return out
+
+
+def transpose_out(ctx: Ctx, x: Var, N: int, Ls: int, Cc: int):
+    """channels-last (N*L, C) Var -> external fp32 (N, C, L) tensor; returns (tensor, grad setter)."""
+    out = ctx.empty((N, Cc, Ls), torch.float32)
+    L.check(ctx.lib.jmt_transpose(_ptr(x.data), ctx.acode, _ptr(out), L.F32, N, Ls, Cc, _stream()), "jmt_transpose")
+    g = {"t": None}
+    if ctx.record:
+        def bwd():
+            if g["t"] is None:
+                return
+            d = g["t"].contiguous()
+            gb = GradBuf(ctx.empty((N * Ls, Cc)))
+            L.check(ctx.lib.jmt_transpose(_ptr(d), _DT[d.dtype], _ptr(gb.t), ctx.acode, N, Cc, Ls, _stream()), "jmt_transpose")
+            ctx.add_grad(x, gb)
+            gb.refs -= 1
+        ctx.tape.append(bwd)
+    return out, (lambda t: g.__setitem__("t", t))
+
+
+def to_external(ctx: Ctx, x: Var, shape):
+    """Activation Var -> external fp32 tensor of `shape` (row-major compatible); returns (tensor, setter)."""
+    out = ctx.empty(shape, torch.float32)
+    copy2d(ctx, x.data, out.view(-1, shape[-1]))
+    g = {"t": None}
+    if ctx.record:
+        def bwd():
+            if g["t"] is None:
+                return
+            d = g["t"].contiguous()
+            gb = GradBuf(ctx.empty(x.data.shape))
+            copy2d(ctx, d.view(-1, shape[-1]), gb.t)
+            ctx.add_grad(x, gb)
+            gb.refs -= 1
+        ctx.tape.append(bwd)
+    return out, (lambda t: g.__setitem__("t", t))
+
+
+def stack_rows(ctx: Ctx, parts: List[Var]) -> Var:
+    """torch.stack(parts, dim=2).flatten(0,1).permute(1,0,2) of the reference (length-L 'sequences' per
+    (b, t); intra_modal_transformer_fusion.py:93-99, mm_multi_transformers.py:173-184): rows l*M + m."""
+    M, E = parts[0].data.shape
+    buf = ctx.empty((len(parts) * M, E))
+    for l, pv in enumerate(parts):
+        copy2d(ctx, pv.data, buf[l * M:(l + 1) * M])
+    out = Var(buf)
+    if ctx.record:
+        def bwd():
+            g = out.grad
+            if g is None:
+                return
+            for l, pv in enumerate(parts):
+                if not pv.needs_grad:
+                    continue
+                gb = GradBuf(ctx.empty((M, E)))
+                copy2d(ctx, g[l * M:(l + 1) * M], gb.t)
+                ctx.add_grad(pv, gb)
+                gb.refs -= 1
+            ctx.release(out)
+        ctx.tape.append(bwd)
+    return out
+
+
+def take_rows(ctx: Ctx, x: Var, r0: int, r1: int) -> Var:
+    """x[r0:r1] as a new Var (the reference's `[:, :, -1, :]` last-token select)."""
+    out = Var(x.data[r0:r1])
+    if ctx.record:
+        def bwd():
+            g = out.grad
+            if g is None:
+                return
+            full = _proj_grad(ctx, x)
+            t = full[r0:r1]
+            L.check(ctx.lib.jmt_axpy(_ptr(g), _ptr(t), 1.0, g.numel(), _DT[g.dtype], _stream()), "jmt_axpy")
+            ctx.release(out)
+        ctx.tape.append(bwd)
+    return out

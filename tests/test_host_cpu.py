@@ -1,0 +1,132 @@
+"""CPU-side checks (no GPU): the C-ABI library loads and exports every declared symbol, the drop-in
+modules reproduce the reference's state_dict inventory and seeded initialisation, error behaviour,
+and the data-parallel host logic on a 2-rank gloo group."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_builds_and_exports_header_symbols():
+    sys.path.insert(0, ROOT)
+    import build
+    lib_path = build.build()
+    assert os.path.exists(lib_path)
+    header = open(os.path.join(ROOT, "include", "jmt_b200.h")).read()
+    declared = set(re.findall(r"\b(jmt_[a-z0-9_]+)\s*\(", header)) - {"jmt_status"}
+    import jmt_b200
+    from jmt_b200 import _lib
+    h = _lib.lib()                      # raises if any bound symbol is missing
+    for name in declared:
+        assert hasattr(h, name), f"{name} declared in jmt_b200.h but not exported"
+        assert name in _lib.SIGNATURES, f"{name} has no ctypes signature"
+    assert set(_lib.SIGNATURES) == declared
+    assert h.jmt_abi_version() == 1
+    # argument validation works without a GPU and reports through jmt_last_error
+    assert h.jmt_ccc_sums(None, None, 0, 1, 0, 0, 0.0, None, None) == -1
+    assert b"jmt_ccc_sums" in h.jmt_last_error()
+    # sm_100a tensor-core / TMA instructions are present in the shipped SASS
+    sass = subprocess.run(["cuobjdump", "-sass", lib_path], capture_output=True, text=True).stdout
+    for mnem in ("UTCHMMA", "UTMALDG", "LDTM"):
+        assert mnem in sass, mnem
+
+
+def test_state_dict_inventory_matches_reference(golden_meta):
+    import jmt_b200
+    inv = golden_meta["inventory"]
+    for joint, fmt in [("TRANSFORMER", "FC"), ("TRANSFORMER", "SELF_ATTEN"), ("NONE", "FC"), ("FC", "FC")]:
+        m = jmt_b200.Two_transformers(0.0, 0.0, 1, 1, joint, fmt, 512)
+        ref = inv[f"Two_transformers/{joint}/{fmt}"]
+        assert [[k, list(v.shape)] for k, v in m.state_dict().items()] == ref["keys"]
+        assert sum(p.numel() for p in m.parameters()) == ref["n_params"]
+    for cls, key, args in [(jmt_b200.Intra_modal_transformer_fusion, "Intra_modal_transformer_fusion", (512, 1, 512, 1)),
+                           (jmt_b200.SingleBackbonePretrainer, "SingleBackbonePretrainer", (0.0, 0.0)),
+                           (jmt_b200.FcLayer, "FcLayer", (768, 512))]:
+        m = cls(*args)
+        assert [[k, list(v.shape)] for k, v in m.state_dict().items()] == inv[key]["keys"], key
+    t = jmt_b200.TemporalConvNet(1024, [512] * 4, kernel_size=5, attention=0, dropout=0.1)
+    assert [[k, list(v.shape)] for k, v in t.state_dict().items()] == inv["TemporalConvNet"]["keys"]
+    assert sum(p.numel() for p in t.parameters()) == inv["TemporalConvNet"]["n_params"]
+    # live parameters exclude the 40.9 M never-used final_encoder
+    m = jmt_b200.Two_transformers(0.0, 0.0, 1, 1, "TRANSFORMER", "FC", 512)
+    live = sum(p.numel() for p in m.live_parameters())
+    assert live == 52742658 - 40922624
+
+
+def test_seeded_init_matches_reference(golden_meta):
+    import jmt_b200
+    torch.manual_seed(0)
+    m = jmt_b200.Two_transformers(0.0, 0.0, 1, 1, "TRANSFORMER", "FC", 512)
+    ref = golden_meta["inventory"]["seed0_init_sums"]
+    sd = m.state_dict()
+    for k, s in ref.items():
+        assert abs(float(sd[k].double().sum()) - s) < 1e-6 * max(1.0, abs(s)), k
+
+
+def test_constructor_errors_like_reference():
+    import jmt_b200
+    with pytest.raises(AssertionError):
+        jmt_b200.Two_transformers(0, 0.0, 1, 1, "TRANSFORMER")            # v_dropout must be float
+    with pytest.raises(AssertionError):
+        jmt_b200.Two_transformers(0.0, 0.0, 1, 1, "BOGUS")
+    with pytest.raises(AssertionError):
+        jmt_b200.Two_transformers(0.0, 0.0, 1, 1, "NONE", "SELF_ATTEN")
+    with pytest.raises(NotImplementedError):
+        jmt_b200.TemporalConvNet(16, [8], attention=1)
+    with pytest.raises(NotImplementedError):
+        jmt_b200.CCCLoss(digitize_num=20)
+    m = jmt_b200.FcLayer(8, 8)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(torch.zeros(1, 2, 8))                                           # no CPU fallback
+
+
+def _dist_worker(rank, world, port, q):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import jmt_b200
+    from oracle import jmt_oracle as O
+    jmt_b200.dist.init_from_env("gloo")
+    rs = np.random.RandomState(0)
+    x = rs.randn(2, 1001)
+    y = 0.5 * x + 0.5 * rs.randn(2, 1001)
+    lo, hi = jmt_b200.dist.shard_bounds(1001, rank, world)
+    part = torch.tensor(np.stack([O.six_sums(x[i, lo:hi], y[i, lo:hi]) for i in range(2)]))
+    tot = jmt_b200.dist.allreduce_sums(part.clone())
+    full = np.stack([O.six_sums(x[i], y[i]) for i in range(2)])
+    ok = np.allclose(tot.numpy(), full, rtol=1e-12)
+    ccc_sharded = O.ccc_from_sums(tot[0].numpy(), "metric")
+    ok &= abs(ccc_sharded - O.ccc_metric(x[0], y[0])) < 1e-12
+    # gradient bucket sync: mean over ranks, identical on every rank afterwards
+    bucket = torch.full((257,), float(rank + 1))
+    jmt_b200.dist.make_grad_sync()(bucket)
+    ok &= bool(torch.allclose(bucket, torch.full((257,), (1 + world) / 2)))
+    p = torch.nn.Linear(3, 3)
+    jmt_b200.dist.broadcast_parameters(p)
+    flat = torch.cat([t.reshape(-1) for t in p.parameters()]).detach()
+    gathered = [torch.zeros_like(flat) for _ in range(world)]
+    dist.all_gather(gathered, flat)
+    ok &= all(torch.equal(gathered[0], t) for t in gathered)
+    q.put((rank, bool(ok), (lo, hi)))
+    dist.destroy_process_group()
+
+
+def test_data_parallel_host_logic_gloo_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 1000
+    procs = [ctx.Process(target=_dist_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in range(2))
+    for p in procs:
+        p.join(60)
+    assert [r[1] for r in res] == [True, True], res
+    assert res[0][2] == (0, 500) and res[1][2] == (500, 1001)

@@ -1,0 +1,386 @@
+"""Kernel-level parity tests (GPU): every C-ABI kernel against a plain PyTorch fp32/fp64 reference of the
+same op on the same seeded inputs.  GEMM cases cover K-/MN-major operands, batches, ragged tails, taps with
+zero-fill shifts, reduce_batch, split-K, every epilogue -- for both the tcgen05 (bf16) and the FFMA (fp32) path."""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import jmt_b200  # noqa: E402
+from jmt_b200 import _lib as L  # noqa: E402
+from jmt_b200 import engine as E  # noqa: E402
+
+
+def _ctx(precision="fp32"):
+    return E.Ctx({}, precision, False, False)
+
+
+def _ref_gemm(A, B, *, a_major, b_major, M, N, K, ntaps, a_shift, b_shift, nb, reduce_batch, alpha, bias, act, slope):
+    """fp64 reference of the jmt_gemm_desc semantics.  A: (nb, rows, cols) per-batch 2-D operand as stored."""
+    outs = []
+    for b in range(nb):
+        acc = torch.zeros(M, N, dtype=torch.float64)
+        for j in range(ntaps):
+            ash = a_shift[0] + j * a_shift[1]
+            bsh = b_shift[0] + j * b_shift[1]
+            a2 = A[b].double()
+            if a_major == L.MAJOR_K:        # stored (a_rows, K): row m+ash
+                Am = torch.zeros(M, K, dtype=torch.float64)
+                for m in range(M):
+                    r = m + ash
+                    if 0 <= r < a2.shape[0]:
+                        Am[m] = a2[r, :K]
+            else:                            # stored (k rows, M): row k+ash
+                Am = torch.zeros(M, K, dtype=torch.float64)
+                for k in range(K):
+                    r = k + ash
+                    if 0 <= r < a2.shape[0]:
+                        Am[:, k] = a2[r, :M]
+            b2 = B[b if B.shape[0] > 1 else 0].double()
+            if b_major == L.MAJOR_K:        # stored (N, ntaps*K)
+                Bm = b2[:N, j * K:(j + 1) * K]
+            else:                            # stored (k rows, N)
+                Bm = torch.zeros(N, K, dtype=torch.float64)
+                for k in range(K):
+                    r = k + bsh
+                    if 0 <= r < b2.shape[0]:
+                        Bm[:, k] = b2[r, :N]
+            acc += Am @ Bm.t()
+        outs.append(acc)
+    if reduce_batch:
+        outs = [sum(outs)]
+    res = []
+    for o in outs:
+        o = alpha * o
+        if bias is not None:
+            o = o + bias.double()
+        if act == L.ACT_RELU:
+            o = torch.relu(o)
+        elif act == L.ACT_LEAKY:
+            o = torch.where(o >= 0, o, o * slope)
+        res.append(o)
+    return torch.stack(res)
+
+
+GEMM_CASES = [
+    # name, M, N, K, a_major, b_major, nb, ntaps, a_shift, b_shift, reduce, split, act, bias, d_dtype, store
+    ("tn_basic", 256, 256, 128, 0, 0, 1, 1, (0, 0), (0, 0), False, 1, 0, False, "f32", 0),
+    ("tn_tails", 300, 300, 72, 0, 0, 3, 1, (0, 0), (0, 0), False, 1, 0, True, "f32", 0),
+    ("tn_bf16_relu", 200, 512, 512, 0, 0, 1, 1, (0, 0), (0, 0), False, 1, 1, True, "act", 0),
+    ("tn_n1536", 384, 1536, 512, 0, 0, 1, 1, (0, 0), (0, 0), False, 1, 0, True, "act", 0),
+    ("tn_accumulate", 130, 96, 64, 0, 0, 2, 1, (0, 0), (0, 0), False, 1, 0, False, "f32", 1),
+    ("nn_bmn", 300, 64, 300, 0, 1, 4, 1, (0, 0), (0, 0), False, 1, 0, False, "act", 0),       # P @ V
+    ("tt_amn", 200, 128, 136, 1, 0, 2, 1, (0, 0), (0, 0), False, 1, 0, False, "f32", 0),
+    ("wgrad_mnmn_split", 512, 512, 1000, 1, 1, 1, 1, (0, 0), (0, 0), False, 4, 0, False, "f32", 2),
+    ("dk_mnmn_batched", 300, 64, 300, 1, 1, 3, 1, (0, 0), (0, 0), False, 1, 0, False, "act", 1),
+    ("conv_fwd_taps", 40, 96, 64, 0, 0, 3, 5, (-8, 2), (0, 0), False, 1, 2, True, "act", 0),
+    ("conv_dgrad_taps", 40, 64, 96, 0, 0, 3, 5, (8, -2), (0, 0), False, 1, 0, False, "act", 0),
+    ("conv_wgrad_tap", 96, 64, 40, 1, 1, 3, 1, (0, 0), (-4, 0), True, 2, 0, False, "f32", 2),
+    ("n_small", 150, 8, 128, 0, 0, 1, 1, (0, 0), (0, 0), False, 1, 0, True, "f32", 0),
+    ("k_small", 150, 300, 16, 0, 0, 2, 1, (0, 0), (0, 0), False, 1, 0, False, "f32", 0),
+]
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("case", GEMM_CASES, ids=[c[0] for c in GEMM_CASES])
+def test_gemm(case, precision):
+    (name, M, N, K, a_major, b_major, nb, ntaps, a_shift, b_shift, reduce, split, act, use_bias, d_kind, store) = case
+    torch.manual_seed(hash(name) % 1000)
+    dev = torch.device("cuda")
+    dt = torch.float32 if precision == "fp32" else torch.bfloat16
+    pad = lambda v: (v + 7) // 8 * 8  # noqa: E731
+    # stored operand shapes (per batch), leading dims padded to 8 with garbage beyond the valid extent
+    if a_major == L.MAJOR_K:
+        a_rows, a_cols = M, K
+    else:
+        a_rows, a_cols = K, M
+    if b_major == L.MAJOR_K:
+        b_rows, b_cols = N, ntaps * K
+    else:
+        b_rows, b_cols = K, N
+    a_ld, b_ld = pad(a_cols) + 8, pad(b_cols)
+    A_store = torch.full((nb, a_rows, a_ld), float("nan"))
+    A_val = (torch.randn(nb, a_rows, a_cols) * 0.5).to(dt).float()
+    A_store[:, :, :a_cols] = A_val
+    share_b = name.startswith("conv_fwd") or name.startswith("conv_dgrad") or name == "tn_tails"
+    nbb = 1 if share_b else nb
+    B_store = torch.full((nbb, b_rows, b_ld), float("nan"))
+    B_val = (torch.randn(nbb, b_rows, b_cols) * 0.5).to(dt).float()
+    B_store[:, :, :b_cols] = B_val
+    bias = torch.randn(N) if use_bias else None
+    alpha, slope = 0.75, 0.01
+    ref = _ref_gemm(A_val, B_val, a_major=a_major, b_major=b_major, M=M, N=N, K=K, ntaps=ntaps, a_shift=a_shift,
+                    b_shift=b_shift, nb=nb, reduce_batch=reduce, alpha=alpha, bias=bias, act=act, slope=slope)
+    d_dt = torch.float32 if d_kind == "f32" else dt
+    nbd = 1 if reduce else nb
+    d_ld = pad(N) + 8
+    D0 = torch.randn(nbd, M, d_ld) * 0.1
+    if store == L.STORE:
+        expect = ref
+    else:
+        expect = ref + D0[:, :, :N].to(d_dt).double()
+    A_d, B_d, D_d = A_store.to(dev, dt), B_store.to(dev, dt), D0.to(dev, d_dt)
+    ctx = _ctx(precision)
+    E.gemm(ctx, A_d, B_d, D_d, M=M, N=N, K=K, a_major=a_major, b_major=b_major, a_rows=a_rows, b_rows=b_rows,
+           a_ld=a_ld, b_ld=b_ld, d_ld=d_ld, nb0=1, nb1=nb, a_bs=(0, a_rows * a_ld),
+           b_bs=(0, 0 if share_b else b_rows * b_ld), d_bs=(0, 0 if reduce else M * d_ld),
+           bias=bias.to(dev) if use_bias else None, act=act, slope=slope, alpha=alpha, store=store, ntaps=ntaps,
+           a_shift=a_shift, b_shift=b_shift, reduce_batch=reduce, split_k=split)
+    torch.cuda.synchronize()
+    got = D_d.float().cpu()[:, :, :N].double()
+    pad_after = D_d.float().cpu()[:, :, N:]
+    assert torch.equal(pad_after, D0[:, :, N:].to(d_dt).float()), "GEMM wrote outside its N columns"
+    tol = 2e-4 if d_dt == torch.float32 else 1.2e-2
+    err = (got - expect).abs()
+    scale = expect.abs().max().item() + 1e-6
+    bad = err > tol * scale
+    if bad.any():
+        idx = bad.nonzero()[:8].tolist()
+        raise AssertionError(f"{name}/{precision}: max err {err.max().item():.4g} (scale {scale:.3g}); first bad {idx}; "
+                             f"got {[got[tuple(i)].item() for i in idx[:4]]} want {[expect[tuple(i)].item() for i in idx[:4]]}; "
+                             f"bad rows {sorted(set(i[1] for i in bad.nonzero().tolist()))[:16]} "
+                             f"bad cols {sorted(set(i[2] for i in bad.nonzero().tolist()))[:16]} frac {bad.float().mean().item():.3f}")
+
+
+def test_gemm_heads_geometry():
+    """(b, head) batching through two batch dims with non-monotonic strides (Q of shape (B*T, 3E))."""
+    torch.manual_seed(3)
+    dev = torch.device("cuda")
+    B, T, E_, h = 3, 70, 128, 4
+    dh = E_ // h
+    for precision, dt, tol in [("fp32", torch.float32, 1e-4), ("bf16", torch.bfloat16, 2e-2)]:
+        qkv = (torch.randn(B * T, 3 * E_) * 0.5).to(dt)
+        q, k = qkv[:, :E_].float(), qkv[:, E_:2 * E_].float()
+        ref = torch.einsum("bthd,bshd->bhts", q.view(B, T, h, dh), k.view(B, T, h, dh)).double()
+        s_ld = (T + 7) // 8 * 8
+        S = torch.zeros(B, h, T, s_ld, device=dev)
+        qd = qkv.to(dev)
+        E.gemm(_ctx(precision), qd[:, :E_], qd[:, E_:2 * E_], S, M=T, N=T, K=dh, a_rows=T, b_rows=T, a_ld=3 * E_,
+               b_ld=3 * E_, d_ld=s_ld, nb0=h, nb1=B, a_bs=(dh, T * 3 * E_), b_bs=(dh, T * 3 * E_),
+               d_bs=(T * s_ld, h * T * s_ld))
+        torch.cuda.synchronize()
+        got = S.cpu()[..., :T].double()
+        assert (got - ref).abs().max() < tol * ref.abs().max(), precision
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_layernorm_l2norm_softmax(dt):
+    torch.manual_seed(0)
+    dev = torch.device("cuda")
+    lib = L.lib()
+    code = E._DT[dt]
+    rows, D = 333, 512
+    st = E._stream()
+    x = torch.randn(rows, D).to(dt)
+    r = torch.randn(rows, D).to(dt)
+    g, b = 1 + 0.1 * torch.randn(D), 0.1 * torch.randn(D)
+    xd, rd, gd, bd = x.to(dev), r.to(dev), g.to(dev), b.to(dev)
+    y = torch.empty(rows, D, device=dev, dtype=dt)
+    mean = torch.empty(rows, device=dev)
+    rstd = torch.empty(rows, device=dev)
+    L.check(lib.jmt_add_layernorm_fwd(E._ptr(xd), E._ptr(rd), E._ptr(gd), E._ptr(bd), 1e-5, E._ptr(y), E._ptr(mean), E._ptr(rstd), rows, D, code, st), "ln")
+    z = (x.float() + r.float()).double().requires_grad_(True)
+    ref = torch.nn.functional.layer_norm(z, (D,), g.double(), b.double(), 1e-5)
+    tol = 1e-5 if dt == torch.float32 else 2e-2
+    assert (y.float().cpu().double() - ref).abs().max() < tol * 4
+    dy = torch.randn(rows, D).to(dt)
+    gg = g.double().requires_grad_(True)
+    bb = b.double().requires_grad_(True)
+    ref2 = torch.nn.functional.layer_norm(z, (D,), gg, bb, 1e-5)
+    ref2.backward(dy.double())
+    dz = torch.empty(rows, D, device=dev, dtype=dt)
+    dgam = torch.zeros(D, device=dev)
+    dbet = torch.zeros(D, device=dev)
+    L.check(lib.jmt_add_layernorm_bwd(E._ptr(dy.to(dev)), E._ptr(xd), E._ptr(rd), E._ptr(gd), E._ptr(mean), E._ptr(rstd), E._ptr(dz), 0,
+                                      E._ptr(dgam), E._ptr(dbet), rows, D, code, st), "lnb")
+    assert (dz.float().cpu().double() - z.grad).abs().max() < tol * 8
+    assert (dgam.cpu().double() - gg.grad).abs().max() < tol * 40
+    assert (dbet.cpu().double() - bb.grad).abs().max() < tol * 40
+    # l2norm
+    x768 = torch.randn(rows, 768)
+    x768[5] = 0.0                     # zero row: clamp path
+    out = torch.empty(rows, 768, device=dev, dtype=dt)
+    inv = torch.empty(rows, device=dev)
+    L.check(lib.jmt_l2norm_fwd(E._ptr(x768.to(dev)), L.F32, 768, E._ptr(out), code, rows, 768, 1e-12, E._ptr(inv), st), "l2")
+    xr = x768.double().requires_grad_(True)
+    refn = torch.nn.functional.normalize(xr, dim=-1)
+    assert (out.float().cpu().double() - refn).abs().max() < tol
+    dyn = torch.randn(rows, 768).to(dt)
+    refn.backward(dyn.double())
+    dx = torch.empty(rows, 768, device=dev)
+    L.check(lib.jmt_l2norm_bwd(E._ptr(dyn.to(dev)), E._ptr(out), code, E._ptr(inv), 1e-12, E._ptr(dx), rows, 768, st), "l2b")
+    m = torch.ones(rows, dtype=torch.bool)
+    m[5] = False
+    assert (dx.cpu().double()[m] - xr.grad[m]).abs().max() < tol * 4
+    # softmax fwd / bwd
+    R, Ccols, ld = 257, 300, 304
+    s = torch.randn(R, ld) * 3
+    p = torch.full((R, ld), 7.0, device=dev, dtype=dt)
+    L.check(lib.jmt_softmax_fwd(E._ptr(s.to(dev)), ld, E._ptr(p), code, ld, R, Ccols, st), "sm")
+    refp = torch.softmax(s[:, :Ccols].double(), -1)
+    assert (p.float().cpu()[:, :Ccols].double() - refp).abs().max() < tol
+    assert (p.float().cpu()[:, Ccols:] == 0).all()
+    dp = torch.randn(R, ld)
+    ds = torch.empty(R, ld, device=dev, dtype=dt)
+    L.check(lib.jmt_softmax_bwd(E._ptr(p), code, ld, E._ptr(dp.to(dev)), ld, E._ptr(ds), code, ld, R, Ccols, st), "smb")
+    pp = p.float().cpu()[:, :Ccols].double()
+    refds = pp * (dp[:, :Ccols].double() - (pp * dp[:, :Ccols].double()).sum(-1, keepdim=True))
+    assert (ds.float().cpu()[:, :Ccols].double() - refds).abs().max() < tol * 2
+    torch.cuda.synchronize()
+
+
+def test_ccc_kernels_vs_closed_form():
+    from oracle import jmt_oracle as O
+    torch.manual_seed(1)
+    dev = torch.device("cuda")
+    n = 76800
+    x = torch.randn(2, n) * 0.3
+    y = (0.6 * x + 0.3 * torch.randn(2, n)).clamp(-1, 1)
+    y[0, ::17] = -5.0
+    xd, yd = x.to(dev), y.to(dev)
+    from jmt_b200.losses import six_sums
+    s_all = six_sums(xd, yd, None).cpu().numpy()
+    s_msk = six_sums(xd, yd, -5.0).cpu().numpy()
+    for i in range(2):
+        np.testing.assert_allclose(s_all[i], O.six_sums(x[i].numpy(), y[i].numpy()), rtol=1e-12)
+        np.testing.assert_allclose(s_msk[i], O.six_sums(x[i].numpy(), y[i].numpy(), ignore=-5.0), rtol=1e-12)
+    # the three formulas + gradients against the oracle (autograd)
+    crit = jmt_b200.CCCLoss(digitize_num=1)
+    xg = xd[0].clone().requires_grad_(True)
+    loss = crit(xg.view(1, -1), yd[0].view(1, -1))
+    loss.backward()
+    xo = x[0].clone().double().requires_grad_(True)
+    lo = O.ccc_loss_live(xo, y[0].double())
+    lo.backward()
+    assert abs(loss.item() - lo.item()) < 1e-6
+    np.testing.assert_allclose(xg.grad.cpu().numpy(), xo.grad.numpy(), rtol=1e-4, atol=1e-10)
+    critm = jmt_b200.CCCLossMasked()
+    xg2 = xd[0].clone().requires_grad_(True)
+    lm = critm(xg2, yd[0])
+    lm.backward()
+    xo2 = x[0].clone().double().requires_grad_(True)
+    lmo = O.ccc_loss_masked(xo2, y[0].double())
+    lmo.backward()
+    assert abs(lm.item() - lmo.item()) < 1e-6
+    np.testing.assert_allclose(xg2.grad.cpu().numpy(), xo2.grad.numpy(), rtol=1e-4, atol=1e-12)
+    assert abs(jmt_b200.cccmetric.ccc(xd[1], yd[1]) - O.ccc_metric(x[1].double().numpy(), y[1].double().numpy())) < 1e-6
+    assert abs(jmt_b200.cccmetric.ccc_numpy(yd[1], xd[1]) - O.ccc_numpy(y[1].numpy(), x[1].numpy())) < 1e-6
+    # masks bit-exact
+    from jmt_b200.losses import label_mask
+    assert torch.equal(label_mask(yd).cpu(), O.label_mask(y))
+    # <= 1 valid element -> loss 0, grad 0
+    yp = torch.tensor([0.1, 0.2, 0.3], device=dev, requires_grad=True)
+    l0 = critm(yp, torch.tensor([-5.0, 0.5, -5.0], device=dev))
+    l0.backward()
+    assert l0.item() == 0.0 and (yp.grad == 0).all()
+
+
+def test_ccc_golden(golden_meta, golden_dir):
+    import os
+    c = golden_meta["ccc"]
+    g = np.load(os.path.join(golden_dir, "ccc.npz"))
+    dev = torch.device("cuda")
+    x, y, ym = (torch.tensor(g[k], device=dev) for k in ("x", "y", "ym"))
+    assert abs(jmt_b200.cccmetric.ccc(x, y) - c["metric"]) < 1e-6
+    assert abs(jmt_b200.cccmetric.ccc_numpy(y, x) - c["ccc_numpy"]) < 1e-6
+    xg = x.clone().requires_grad_(True)
+    l = jmt_b200.CCCLoss(1)(xg[None], y[None])
+    l.backward()
+    assert abs(l.item() - c["loss_live"]) < 1e-6
+    np.testing.assert_allclose(xg.grad.cpu().numpy(), g["g_live"], rtol=2e-3, atol=1e-8)
+    xg2 = x.clone().requires_grad_(True)
+    l2 = jmt_b200.CCCLossMasked()(xg2, ym)
+    l2.backward()
+    assert abs(l2.item() - c["loss_masked"]) < 1e-6
+    np.testing.assert_allclose(xg2.grad.cpu().numpy(), g["g_masked"], rtol=2e-3, atol=1e-9)
+    cv, ca, cm = jmt_b200.cccmetric.cccva(torch.stack([y, ym], 1), torch.stack([x, x * 0.5], 1))
+    np.testing.assert_allclose([cv, ca, cm], c["cccva"], rtol=1e-5)
+    with pytest.raises(ValueError):
+        jmt_b200.cccmetric.ccc(x[:1], y[:1])
+    m = jmt_b200.cccmetric.CCCMetric()
+    m.update(x[:400], y[:400])
+    m.update(x[400:], y[400:])
+    assert abs(m.get() - c["metric"]) < 1e-6
+
+
+def test_padseq_golden(golden_meta, golden_dir):
+    import os
+    m = golden_meta["padseq"]
+    g = np.load(os.path.join(golden_dir, "padseq.npz"))
+    gen = torch.Generator().manual_seed(m["seed"])
+    specs = []
+    for w in m["widths"]:
+        torch.randn(16, 3, 2, 4, 4, generator=gen)
+        specs.append((torch.randn(16, 1, 64, w, generator=gen) + 3.0).cuda())
+        torch.randn(16, generator=gen), torch.randn(16, generator=gen)
+    out = jmt_b200.padseq.pad_spectrograms(specs).cpu()
+    assert np.array_equal((out == 0).numpy(), g["zero_mask"])
+    np.testing.assert_allclose(out.double().sum().numpy(), g["audio_sum"], rtol=1e-12)
+
+
+def test_small_kernels():
+    torch.manual_seed(5)
+    dev = torch.device("cuda")
+    lib = L.lib()
+    st = E._stream()
+    # transpose with cast
+    x = torch.randn(3, 37, 70)
+    o = torch.empty(3, 70, 37, device=dev, dtype=torch.bfloat16)
+    L.check(lib.jmt_transpose(E._ptr(x.to(dev)), L.F32, E._ptr(o), L.BF16, 3, 37, 70, st), "tr")
+    assert torch.equal(o.cpu(), x.transpose(1, 2).to(torch.bfloat16))
+    # colsum
+    a = torch.randn(1000, 130).to(torch.bfloat16)
+    out = torch.zeros(130, device=dev)
+    L.check(lib.jmt_colsum(E._ptr(a.to(dev)), L.BF16, 130, 1000, 130, E._ptr(out), st), "cs")
+    assert (out.cpu() - a.float().sum(0)).abs().max() < 1e-3
+    # weight norm fwd/bwd
+    cout, cin, k = 24, 40, 5
+    g = torch.rand(cout, 1, 1) + 0.5
+    v = torch.randn(cout, cin, k)
+    wf = torch.empty(cout, k * cin, device=dev)
+    wd = torch.empty(cin, k * cout, device=dev)
+    nrm = torch.empty(cout, device=dev)
+    L.check(lib.jmt_weight_norm_fwd(E._ptr(g.to(dev)), E._ptr(v.to(dev)), E._ptr(wf), E._ptr(wd), L.F32, E._ptr(nrm), cout, cin, k, st), "wn")
+    gg = g.double().requires_grad_(True)
+    vv = v.double().requires_grad_(True)
+    w = vv * (gg / vv.pow(2).sum((1, 2), keepdim=True).sqrt())
+    assert (wf.cpu().double() - w.permute(0, 2, 1).reshape(cout, -1)).abs().max() < 1e-5
+    assert (wd.cpu().double() - w.permute(1, 2, 0).reshape(cin, -1)).abs().max() < 1e-5
+    dw = torch.randn(cout, cin, k)
+    w.backward(dw.double())
+    dwf = dw.permute(0, 2, 1).reshape(cout, -1).contiguous().to(dev)
+    dg = torch.empty(cout, 1, 1, device=dev)
+    dv = torch.empty(cout, cin, k, device=dev)
+    L.check(lib.jmt_weight_norm_bwd(E._ptr(dwf), E._ptr(g.to(dev)), E._ptr(v.to(dev)), E._ptr(nrm), E._ptr(dg), E._ptr(dv), cout, cin, k, st), "wnb")
+    assert (dg.cpu().double() - gg.grad).abs().max() < 1e-4
+    assert (dv.cpu().double() - vv.grad).abs().max() < 1e-4
+    # dropout mask statistics + determinism
+    n = 1 << 20
+    m1 = torch.empty(n, dtype=torch.uint8, device=dev)
+    m2 = torch.empty(n, dtype=torch.uint8, device=dev)
+    L.check(lib.jmt_dropout_mask(E._ptr(m1), n, 0.3, 1234, 0, st), "dm")
+    L.check(lib.jmt_dropout_mask(E._ptr(m2), n, 0.3, 1234, 0, st), "dm")
+    assert torch.equal(m1, m2) and abs(m1.float().mean().item() - 0.7) < 3e-3
+    # tiny attention fwd/bwd vs torch
+    Ls, N, Em, h = 6, 50, 64, 2
+    qkv = torch.randn(Ls, N, 3 * Em, requires_grad=True, dtype=torch.float64)
+    q, kk, vv2 = qkv[..., :Em], qkv[..., Em:2 * Em], qkv[..., 2 * Em:]
+    dh = Em // h
+    sh = lambda t: t.reshape(Ls, N, h, dh).permute(1, 2, 0, 3)  # noqa: E731
+    att = torch.softmax(sh(q) @ sh(kk).transpose(-1, -2) / math.sqrt(dh), -1) @ sh(vv2)
+    ref = att.permute(2, 0, 1, 3).reshape(Ls, N, Em)
+    do = torch.randn(Ls, N, Em, dtype=torch.float64)
+    ref.backward(do)
+    qd = qkv.detach().float().to(dev)
+    out = torch.empty(Ls, N, Em, device=dev)
+    probs = torch.empty(N * h, Ls, Ls, device=dev)
+    L.check(lib.jmt_attn_small_fwd(E._ptr(qd), E._ptr(out), E._ptr(probs), Ls, N, Em, h, 1 / math.sqrt(dh), L.F32, st), "as")
+    assert (out.cpu().double() - ref.detach()).abs().max() < 1e-4
+    dq = torch.empty(Ls, N, 3 * Em, device=dev)
+    L.check(lib.jmt_attn_small_bwd(E._ptr(qd), E._ptr(do.float().to(dev)), E._ptr(probs), E._ptr(dq), Ls, N, Em, h, 1 / math.sqrt(dh), L.F32, st), "asb")
+    assert (dq.cpu().double() - qkv.grad).abs().max() < 1e-4
+    torch.cuda.synchronize()

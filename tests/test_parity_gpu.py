@@ -1,0 +1,213 @@
+"""Module-level parity (GPU): the drop-in modules, driven through the C-ABI kernels, against
+(a) golden vectors produced by the reference itself and (b) the CPU oracle on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): predictions within 1e-3 relative in the fp32-operand mode
+('fp32'); the bf16-operand mode is reported separately with a looser bound; CCC within 1e-4."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import jmt_b200  # noqa: E402
+from oracle import jmt_oracle as O  # noqa: E402
+
+TT_NAMES = ["tt_transformer_fc_h1_l1", "tt_transformer_fc_h4_l2", "tt_transformer_fc_h8_vin1024",
+            "tt_transformer_sa_h2_l1", "tt_none_fc_h2_l1", "tt_fc_fc"]
+DEV = "cuda"
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return np.abs(a - b).max() / (np.abs(b).max() + 1e-12)
+
+
+def _load(module, params):
+    sd = module.state_dict()
+    missing = [k for k in sd if k not in params]
+    assert not missing, missing
+    module.load_state_dict({k: params[k] for k in sd}, strict=True)
+    return module.to(DEV)
+
+
+def _grad_summary(module, names):
+    named = dict(module.named_parameters())
+    l2, head = [], []
+    for n in names:
+        g = named[n].grad
+        assert g is not None, n
+        g = g.detach().double().reshape(-1).cpu()
+        l2.append(float(g.norm()))
+        h = np.zeros(8)
+        h[: min(8, g.numel())] = g[:8].numpy()
+        head.append(h)
+    return np.array(l2), np.stack(head)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", TT_NAMES)
+def test_two_transformers(name, precision, golden_meta, golden_dir):
+    m = golden_meta[name]
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    params = O.synth_params(O.two_transformers_shapes(m["layers"], m["joint"], m["fmt"], m["vin"]), m["param_seed"])
+    model = _load(jmt_b200.Two_transformers(0.0, 0.0, m["heads"], m["layers"], m["joint"], m["fmt"], m["vin"],
+                                            precision=precision), params)
+    model.eval()
+    aud, vis = O.synth_features(m["B"], m["T"], [512, m["vin"]], m["feat_seed"])
+    lv, la = O.synth_labels(m["B"], m["T"], m["label_seed"])
+    aud_d = aud.to(DEV).requires_grad_(True)
+    vis_d = vis.to(DEV).requires_grad_(True)
+    v, a = model(aud_d, vis_d)
+    assert list(v.shape) == m["out_shape"] and v.is_contiguous() and v.dtype == torch.float32
+    tol = 1e-3 if precision == "fp32" else 4e-2
+    assert _rel(v.detach().cpu(), g["vout"]) < tol, ("vout", _rel(v.detach().cpu(), g["vout"]))
+    assert _rel(a.detach().cpu(), g["aout"]) < tol, ("aout", _rel(a.detach().cpu(), g["aout"]))
+    # live loss exactly as train.py:303-311 (independent flatten of preds and labels)
+    crit = jmt_b200.CCCLoss(digitize_num=1)
+    n = v.shape[0] * v.shape[1]
+    loss = crit(v.view(-1, n), lv.to(DEV).view(-1, n)) + crit(a.view(-1, n), la.to(DEV).view(-1, n))
+    ltol = 1e-4 if precision == "fp32" else 2e-2
+    assert abs(loss.item() - float(g["loss"])) < ltol, (loss.item(), float(g["loss"]))
+    loss.backward()
+    gtol = 2e-3 if precision == "fp32" else 8e-2
+    assert _rel(aud_d.grad.cpu(), g["d_aud"]) < gtol, ("d_aud", _rel(aud_d.grad.cpu(), g["d_aud"]))
+    assert _rel(vis_d.grad.cpu(), g["d_vis"]) < gtol, ("d_vis", _rel(vis_d.grad.cpu(), g["d_vis"]))
+    l2, head = _grad_summary(model, m["grad_names"])
+    rel_l2 = np.abs(l2 - g["grad_l2"]) / (g["grad_l2"] + 1e-12)
+    assert rel_l2.max() < gtol * 2, (m["grad_names"][int(rel_l2.argmax())], rel_l2.max())
+    if precision == "fp32":
+        for i, nme in enumerate(m["grad_names"]):
+            sc = np.abs(g["grad_head"][i]).max() + 1e-9
+            assert np.abs(head[i] - g["grad_head"][i]).max() < 5e-3 * max(sc, g["grad_l2"][i] / 50), nme
+    # dead parameters never get a gradient
+    for nme, p in model.named_parameters():
+        if "final_encoder" in nme or "gated_attention" in nme:
+            assert p.grad is None, nme
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_c1_config(precision, golden_meta, golden_dir):
+    """BASELINE.json configs[0]: FcLayer(768,512) + Two_transformers(TRANSFORMER, FC), B=8, T=300."""
+    m = golden_meta["c1_b8_t300"]
+    g = np.load(os.path.join(golden_dir, "c1_b8_t300.npz"))
+    params = O.synth_params(O.two_transformers_shapes(1, "TRANSFORMER", "FC", 512), m["param_seed"])
+    fcp = O.synth_params([("fc_layer.weight", (512, 768)), ("fc_layer.bias", (512,))], m["fc_seed"])
+    model = _load(jmt_b200.Two_transformers(0.0, 0.0, 1, 1, "TRANSFORMER", "FC", 512, precision=precision), params).eval()
+    fc = _load(jmt_b200.FcLayer(768, 512, precision=precision), fcp).eval()
+    vis, aud768 = O.synth_features(m["B"], m["T"], [512, 768], m["feat_seed"])
+    with torch.no_grad():
+        v, a = model(fc(aud768.to(DEV)), vis.to(DEV))
+    assert tuple(v.shape) == (300, 8)
+    tol = 1e-3 if precision == "fp32" else 4e-2
+    assert _rel(v.cpu(), g["vout"]) < tol and _rel(a.cpu(), g["aout"]) < tol, (_rel(v.cpu(), g["vout"]), _rel(a.cpu(), g["aout"]))
+    # CCC of the engine's predictions vs CCC of the reference's predictions on the same labels: within 1e-4 (fp32 mode)
+    lv, _ = O.synth_labels(m["B"], m["T"], 5)
+    c_ref = O.ccc_metric(g["vout"].reshape(-1).astype(np.float64), lv.numpy().reshape(-1).astype(np.float64))
+    c_new = jmt_b200.cccmetric.ccc(v.reshape(-1), lv.to(DEV).reshape(-1))
+    assert abs(c_ref - c_new) < (1e-4 if precision == "fp32" else 5e-3)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", ["intra_512_768_h2", "intra_512_512_h1_l2"])
+def test_intra_modal(name, precision, golden_meta, golden_dir):
+    m = golden_meta[name]
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    params = O.synth_params(O.intra_modal_shapes(m["layers"]), m["param_seed"])
+    model = _load(jmt_b200.Intra_modal_transformer_fusion(512, m["heads"], 512, m["layers"], precision=precision), params).eval()
+    fa, fb = O.synth_features(m["B"], m["T"], [m["da"], m["db"]], m["feat_seed"])
+    fa_d, fb_d = fa.to(DEV).requires_grad_(True), fb.to(DEV).requires_grad_(True)
+    out = model(fa_d, fb_d)
+    tol = 1e-3 if precision == "fp32" else 4e-2
+    assert _rel(out.detach().cpu(), g["out"]) < tol
+    w = torch.linspace(-1, 1, out.numel()).reshape(out.shape).to(DEV)
+    (out * w).sum().backward()
+    gtol = 2e-3 if precision == "fp32" else 8e-2
+    assert _rel(fa_d.grad.cpu(), g["d_a"]) < gtol and _rel(fb_d.grad.cpu(), g["d_b"]) < gtol
+    l2, _ = _grad_summary(model, m["grad_names"])
+    assert (np.abs(l2 - g["grad_l2"]) / (g["grad_l2"] + 1e-12)).max() < gtol * 2
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", ["tcn_1024_512x4_k5_L7", "tcn_1024_512x4_k5_L40", "tcn_16_8x2_k3_L19"])
+def test_tcn(name, precision, golden_meta, golden_dir):
+    m = golden_meta[name]
+    if precision == "bf16" and m["cin"] % 8 != 0:
+        pytest.skip("tcgen05 path needs channel counts that are multiples of 8")
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    params = O.synth_params(O.tcn_shapes(m["cin"], m["chans"], m["k"]), m["param_seed"])
+    model = jmt_b200.TemporalConvNet(m["cin"], m["chans"], kernel_size=m["k"], attention=0, dropout=0.1, precision=precision)
+    model.load_state_dict(O.tcn_state_dict(params), strict=True)
+    model = model.to(DEV).eval()
+    gen = torch.Generator().manual_seed(m["x_seed"])
+    x = torch.randn(m["N"], m["cin"], m["L"], generator=gen)
+    xd = x.to(DEV).requires_grad_(True)
+    out = model(xd)
+    assert tuple(out.shape) == g["out"].shape
+    tol = 1e-3 if precision == "fp32" else 4e-2
+    assert _rel(out.detach().cpu(), g["out"]) < tol, _rel(out.detach().cpu(), g["out"])
+    w = torch.linspace(-1, 1, out.numel()).reshape(out.shape).to(DEV)
+    (out * w).sum().backward()
+    gtol = 2e-3 if precision == "fp32" else 8e-2
+    assert _rel(xd.grad.cpu(), g["d_x"]) < gtol, _rel(xd.grad.cpu(), g["d_x"])
+    l2, _ = _grad_summary(model, m["grad_names"])
+    rel = np.abs(l2 - g["grad_l2"]) / (g["grad_l2"] + 1e-12)
+    assert rel.max() < gtol * 2, (m["grad_names"][int(rel.argmax())], rel.max())
+
+
+def test_single_backbone_and_fc(golden_meta, golden_dir):
+    m = golden_meta["single_backbone"]
+    g = np.load(os.path.join(golden_dir, "single_backbone.npz"))
+    params = O.synth_params(O._regressor_shapes("regressor.", 512, 2), m["param_seed"])
+    model = _load(jmt_b200.SingleBackbonePretrainer(0.0, 0.0, precision="fp32"), params).eval()
+    (x,) = O.synth_features(m["B"], m["T"], [512], m["feat_seed"])
+    xd = x.to(DEV).requires_grad_(True)
+    v, a = model(xd)
+    assert _rel(v.detach().cpu(), g["v"]) < 1e-3 and _rel(a.detach().cpu(), g["a"]) < 1e-3
+    (v.sum() + 2 * a.sum()).backward()
+    xo = x.clone().requires_grad_(True)
+    po = {k: t.clone().requires_grad_(True) for k, t in params.items()}
+    vo, ao = O.single_backbone_pretrainer_forward(xo, po)
+    (vo.sum() + 2 * ao.sum()).backward()
+    assert _rel(xd.grad.cpu(), xo.grad) < 2e-3
+    for k, p in model.named_parameters():
+        assert _rel(p.grad.cpu(), po[k].grad) < 2e-3, k
+
+
+def test_training_semantics_dropout_and_modes():
+    """train()/eval() toggle dropout only; p>0 training changes outputs, eval does not; deepcopy works."""
+    import copy
+    torch.manual_seed(0)
+    model = jmt_b200.Two_transformers(0.5, 0.5, 2, 1, "FC", "FC", 512, precision="fp32").to(DEV)
+    aud, vis = (t.to(DEV) for t in O.synth_features(2, 5, [512, 512], 1))
+    model.eval()
+    v0, _ = model(aud, vis)
+    v1, _ = model(aud, vis)
+    assert torch.equal(v0, v1)
+    model.train()
+    v2, _ = model(aud, vis)
+    assert not torch.equal(v0, v2)
+    m2 = copy.deepcopy(model).eval()
+    v3, _ = m2(aud, vis)
+    assert torch.equal(v0, v3)
+    # a step of SGD under autocast + GradScaler (train.py:89,101,314-316) runs and changes the live params only
+    opt = torch.optim.SGD(model.parameters(), lr=0.1)
+    scaler = torch.amp.GradScaler("cuda")
+    lv, la = (t.to(DEV) for t in O.synth_labels(2, 5, 2))
+    before = {k: p.detach().clone() for k, p in model.named_parameters()}
+    with torch.autocast("cuda", dtype=torch.float16):
+        v, a = model(aud, vis)
+        crit = jmt_b200.CCCLoss(1)
+        loss = crit(v.view(1, -1), lv.view(1, -1)) + crit(a.view(1, -1), la.view(1, -1))
+    scaler.scale(loss).backward()
+    scaler.step(opt)
+    scaler.update()
+    changed = [k for k, p in model.named_parameters() if not torch.equal(p, before[k])]
+    assert "vregressor.3.weight" in changed and "mm_transformer.fc.weight" in changed
+
+
+def test_cpu_tensor_is_refused():
+    model = jmt_b200.FcLayer(768, 512).to(DEV)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        model(torch.randn(2, 3, 768))
