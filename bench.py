@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""bench.py -- clip-windows/sec of the JMT hot path (BASELINE.json metric) on N B200s.
+
+    python bench.py --gpus 1 --steps 10 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \\
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...        # the reference algorithm's CPU port on the host cores
+
+Workload (BASELINE.json configs[1], SURVEY.md 8d "C2"): one training step of
+    TemporalConvNet(1024,[512]*4,k=5) on visual (B,1024,T)  +  FcLayer(768,512) on audio (B,T,768)
+    -> Two_transformers(TRANSFORMER, FC, heads=1, layers=1) -> live CCC loss (V + A) -> backward -> SGD step
+with B = 256 windows per GPU, T = 300, bf16 operands / fp32 accumulate, synthetic N(0,1) features,
+random-init weights (seed 0).  A "step" is one pass over one batch; throughput = windows / second.
+One process per GPU; the batch of windows is sharded across ranks (weak scaling: 256 per GPU), the flat
+live-gradient bucket is all-reduced over NCCL at the end of backward, and the six CCC sums are all-reduced
+inside the loss so every rank optimises the global-batch CCC.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FWD_GFLOP_PER_WINDOW = 0.236 + 10.15 + 7.23     # FcLayer + w_JR/FC + TCN useful taps, T=300
+METRIC = "clip-windows/sec fwd+bwd"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="jmt", choices=["jmt", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="windows per GPU")
+    ap.add_argument("--seq", type=int, default=300)
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--heads", type=int, default=1)
+    ap.add_argument("--cpu-sample", type=int, default=4, help="windows in the CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------------------- CPU port
+def cpu_port_step(B, T, heads, threads, seed=0):
+    """One fwd+bwd of the same pipeline through the CPU oracle (the reference algorithm restated with plain
+    torch CPU ops, fp32, all host threads).  Returns (seconds, windows)."""
+    from oracle import jmt_oracle as O
+    torch.set_num_threads(threads)
+    gen = torch.Generator().manual_seed(seed)
+    fus = {k: v.requires_grad_(True) for k, v in O.synth_params(O.two_transformers_shapes(1, "TRANSFORMER", "FC", 512, include_dead=False), 1).items()}
+    fc = {k: v.requires_grad_(True) for k, v in O.synth_params([("fc_layer.weight", (512, 768)), ("fc_layer.bias", (512,))], 2).items()}
+    tcn = {k: v.requires_grad_(True) for k, v in O.synth_params(O.tcn_shapes(1024, [512] * 4, 5), 3).items()}
+    vis = torch.randn(B, 1024, T, generator=gen)
+    aud = torch.randn(B, T, 768, generator=gen)
+    lv, la = O.synth_labels(B, T, 4)
+    t0 = time.perf_counter()
+    vfeat = O.tcn_forward(vis, tcn, 4).transpose(1, 2)
+    afeat = O.fc_layer_forward(aud, fc)
+    v, a = O.two_transformers_forward(afeat, vfeat, fus, heads, 1, "TRANSFORMER", "FC")
+    loss = O.ccc_loss_live(v, lv) + O.ccc_loss_live(a, la)
+    loss.backward()
+    return time.perf_counter() - t0, B
+
+
+def run_reference(args):
+    """Reference arm: the reference's own CPU path cannot travel to the GPU box (/root/reference is absent
+    there), so this times its restatement (oracle port, same torch CPU kernels underneath) on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    B = args.cpu_sample
+    for _ in range(min(args.warmup, 1)):
+        cpu_port_step(B, args.seq, args.heads, cores)
+    times = []
+    for _ in range(args.steps):
+        dt, _ = cpu_port_step(B, args.seq, args.heads, cores)
+        times.append(dt)
+        if sum(times) > 150:
+            break
+    med = float(np.median(times))
+    val = B / med
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "windows/s", "n_gpus": args.gpus,
+            "steps": len(times), "warmup": min(args.warmup, 1), "ms_per_step": med * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, sample=B),
+            "cpu_baseline": {"value": val, "unit": "windows/s", "cores": cores, "kind": "port",
+                             "sample": f"{B} windows x T={args.seq}, fwd+bwd, fp32, torch CPU ops via oracle/jmt_oracle.py"},
+            "e2e": {"value": val, "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_config(args, sample=None):
+    return {"workload": "C2: TCN(1024,[512]*4,k=5)+FcLayer(768,512)+Two_transformers(TRANSFORMER,FC,h=%d,L=1)+CCC train step" % args.heads,
+            "windows_per_gpu": sample if sample is not None else args.batch, "seq_len": args.seq,
+            "global_windows": (sample if sample is not None else args.batch * args.gpus),
+            "parallelism": f"dp{args.gpus} (batch of windows sharded, NCCL grad all-reduce + CCC-sum all-reduce)",
+            "optimizer": "SGD(lr=1e-3)", "l2": "inputs+activations per step (>1 GB) exceed the 126 MB L2; no explicit flush",
+            "host_feature_dtype": "bf16"}
+
+
+# --------------------------------------------------------------------------------------- clocks
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag = index, [], set(), False
+        self.max_mhz = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap", nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake"}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def result(self):
+        self.stop_flag = True
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons)}
+
+
+# --------------------------------------------------------------------------------------- GPU arm
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    import jmt_b200
+    from jmt_b200 import engine as E
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = jmt_b200.dist.init_from_env("nccl") if world > 1 else 0
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    B, T = args.batch, args.seq
+
+    torch.manual_seed(0)                                   # identical weights on every rank
+    fusion = jmt_b200.Two_transformers(0.0, 0.0, args.heads, 1, "TRANSFORMER", "FC", 512, precision=args.precision)
+    fc = jmt_b200.FcLayer(768, 512, precision=args.precision)
+    tcn = jmt_b200.TemporalConvNet(1024, [512] * 4, kernel_size=5, attention=0, dropout=0.1, precision=args.precision)
+    model = jmt_b200.JMTPipeline(fusion, fc, tcn).to(dev).train()
+    crit = jmt_b200.CCCLoss(digitize_num=1, global_stats=world > 1)
+    if world > 1:
+        jmt_b200.dist.broadcast_parameters(model)
+        model.set_grad_sync(jmt_b200.dist.make_grad_sync())
+    opt = torch.optim.SGD(model.live_parameters(), lr=1e-3)
+
+    # synthetic features, per-rank seed; host copies pinned (bf16 feature shards), device copies resident
+    gen = torch.Generator().manual_seed(100 + rank)
+    n_buf = 2
+    host = []
+    for i in range(n_buf):
+        vis = torch.randn(B, 1024, T, generator=gen).to(torch.bfloat16).pin_memory()
+        aud = torch.randn(B, T, 768, generator=gen).to(torch.bfloat16).pin_memory()
+        lv = (torch.rand(B, T, generator=gen) * 2 - 1)
+        la = (torch.rand(B, T, generator=gen) * 2 - 1)
+        drop = torch.rand(B, T, generator=gen) < 0.05
+        lv = torch.where(drop, torch.full_like(lv, -5.0), lv).pin_memory()
+        la = la.pin_memory()
+        host.append((aud, vis, lv, la))
+    resident = [tuple(t.to(dev) for t in h) for h in host]
+    n = B * T
+
+    def step(aud, vis, lv, la):
+        v, a = model(aud, vis)
+        loss = crit(v.view(-1, n), lv.view(-1, n)) + crit(a.view(-1, n), la.view(-1, n))   # train.py:303-311
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 3)):
+        step(*resident[i % n_buf])
+    barrier()
+
+    # ---- timed region: K steps, inputs resident in HBM, CUDA events on the launching stream
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = jmt_b200.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        loss = step(*resident[i % n_buf])
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = jmt_b200.launch_count() - l0
+    clocks = sampler.result()
+    final_loss = float(loss.item())
+    t_ms = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms = float(t_ms.item())
+    value = B * world * args.steps / (ms / 1e3)
+
+    # ---- e2e: same step through the public API with HOST (pinned) inputs; H2D of every step's inputs and
+    #      a D2H read of the loss inside the timed region (copies double-buffered on a side stream)
+    e2e = None
+    if not args.no_e2e:
+        copy_stream = torch.cuda.Stream()
+        dbuf = [tuple(torch.empty_like(t, device=dev) for t in host[0]) for _ in range(2)]
+        ready = [torch.cuda.Event(), torch.cuda.Event()]
+        consumed = [torch.cuda.Event(), torch.cuda.Event()]
+
+        def prefetch(i):
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(consumed[i % 2])
+                for d, h in zip(dbuf[i % 2], host[i % n_buf]):
+                    d.copy_(h, non_blocking=True)
+                ready[i % 2].record(copy_stream)
+
+        h2d = sum(t.numel() * t.element_size() for t in host[0])
+        for ev in consumed:
+            ev.record()
+        barrier()
+        t0 = time.perf_counter()
+        prefetch(0)
+        lsum = 0.0
+        for i in range(args.steps):
+            if i + 1 < args.steps:
+                prefetch(i + 1)
+            torch.cuda.current_stream().wait_event(ready[i % 2])
+            l = step(*dbuf[i % 2])
+            consumed[i % 2].record()
+            lsum += float(l.item())                          # D2H of the step's result (synchronises)
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": B * world * args.steps / float(tt.item()), "unit": "windows/s",
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4}
+
+    # ---- roofline of the dominant kernel (gemm_tc_kernel): per-launch CUDA events over timed steps
+    roof = None
+    if not args.no_roofline and rank == 0:
+        peaks = {}
+        pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(pk_path):
+            peaks = json.load(open(pk_path))
+        peak = peaks.get("bf16_tflops_sustained", 1400.0)
+        E.PROFILE = []
+        nprof = min(args.steps, 3)
+        for i in range(nprof):
+            step(*resident[i % n_buf])
+        torch.cuda.synchronize()
+        rec, E.PROFILE = E.PROFILE, None
+        kname = "gemm_tc_kernel" if args.precision == "bf16" else "gemm_simt_kernel"
+        sel = [r for r in rec if r[0] == kname]
+        tot_ms = sum(r[2].elapsed_time(r[3]) for r in sel)
+        tot_fl = sum(r[1] for r in sel)
+        ach = tot_fl / (tot_ms / 1e3) / 1e12 if tot_ms > 0 else 0.0
+        roof = {"bound": "tensor", "kernel": kname, "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                "frac": ach / peak, "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s sustained (of fallback)",
+                "launches_per_step": len(sel) // nprof, "gemm_ms_per_step": tot_ms / nprof,
+                "gemm_gflop_per_step": tot_fl / nprof / 1e9,
+                "avg_launch_us": 1e3 * tot_ms / max(1, len(sel)),
+                "step_model_gflop": 3 * FWD_GFLOP_PER_WINDOW * B}
+        if world > 1:
+            dist.barrier()
+    elif world > 1 and not args.no_roofline:
+        dist.barrier()
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        cpu_port_step(1, T, args.heads, cores)                 # warm-up (thread pools, allocator)
+        times = []
+        t_start = time.perf_counter()
+        while len(times) < 3 and time.perf_counter() - t_start < 40:
+            dt, _ = cpu_port_step(args.cpu_sample, T, args.heads, cores)
+            times.append(dt)
+        med = float(np.median(times))
+        cpu = {"value": args.cpu_sample / med, "unit": "windows/s", "cores": cores, "kind": "port",
+               "sample": f"{args.cpu_sample} windows x T={T}, fwd+bwd, fp32, median of {len(times)} runs of oracle/jmt_oracle.py (torch CPU ops)"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "windows/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": args.precision if args.precision == "bf16" else "f32", "data": "synthetic",
+                "config": workload_config(args), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+                "roofline": roof, "cpu_baseline": cpu, "final_loss": final_loss,
+                "model_tflops": 3 * FWD_GFLOP_PER_WINDOW * value / 1e3}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -5,7 +5,7 @@ reference modules named in SURVEY.md section 8b, backed by hand-written CUDA ker
 C-ABI in include/jmt_b200.h.  CUDA only; no CPU or ATen fallback.
 """
 from ._lib import LIB_PATH, launch_count, lib  # noqa: F401
-from .modules import (FcLayer, FeatureConcatFC, Intra_modal_transformer_fusion,  # noqa: F401
+from .modules import (FcLayer, JMTPipeline, FeatureConcatFC, Intra_modal_transformer_fusion,  # noqa: F401
                       MultimodalTransformer_w_JR, MultimodalTransformer_wo_JR, SingleBackbonePretrainer,
                       TemporalBlock, TemporalConvNet, TransformerEncoderBlock, TransformerEncoderLayer,
                       Two_transformers)

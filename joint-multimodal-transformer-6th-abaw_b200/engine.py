@@ -202,6 +202,30 @@ class Ctx:
 
 
 # --------------------------------------------------------------------------- raw op wrappers
+PROFILE: Optional[list] = None      # when a list: gemm() appends (kind, algorithmic flops, start event, end event)
+
+
+def gemm_flops(M, N, K, nb, ntaps, a_shift, b_shift, a_rows, b_rows, a_major, b_major) -> float:
+    """Algorithmic FLOPs (multiply-add = 2) of one launch; taps count only rows whose shifted index is in
+    range (useful taps)."""
+    if ntaps == 1 and a_shift == (0, 0) and b_shift == (0, 0):
+        return 2.0 * M * N * K * nb
+    total = 0.0
+    for j in range(ntaps):
+        ash = a_shift[0] + j * a_shift[1]
+        bsh = b_shift[0] + j * b_shift[1]
+        if a_major == L.MAJOR_K:      # shift moves the output row m
+            valid_m = max(0, min(M, a_rows - ash) - max(0, -ash))
+            valid_k = K
+        else:                         # shift moves the reduction index k
+            valid_m = M
+            valid_k = max(0, min(K, a_rows - ash) - max(0, -ash))
+        if b_major == L.MAJOR_MN and bsh != 0:
+            valid_k = min(valid_k, max(0, min(K, b_rows - bsh) - max(0, -bsh)))
+        total += 2.0 * valid_m * N * valid_k * nb
+    return total
+
+
 def gemm(ctx: Ctx, a: torch.Tensor, b: torch.Tensor, d: torch.Tensor, *, M: int, N: int, K: int,
          a_major=L.MAJOR_K, b_major=L.MAJOR_K, a_rows=None, b_rows=None, a_ld=None, b_ld=None, d_ld=None,
          nb0=1, nb1=1, a_bs=(0, 0), b_bs=(0, 0), d_bs=(0, 0), bias=None, act=L.ACT_NONE, slope=0.0, alpha=1.0,
@@ -231,12 +255,22 @@ def gemm(ctx: Ctx, a: torch.Tensor, b: torch.Tensor, d: torch.Tensor, *, M: int,
     g.b_shift0, g.b_shift_step = b_shift
     g.reduce_batch = 1 if reduce_batch else 0
     g.split_k = split_k
+    prof = PROFILE
+    if prof is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     if a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16:
         L.check(ctx.lib.jmt_gemm_bf16(C.byref(g), _stream()), "jmt_gemm_bf16")
+        kind = "gemm_tc_kernel"
     elif a.dtype == torch.float32 and b.dtype == torch.float32:
         L.check(ctx.lib.jmt_gemm_f32(C.byref(g), _stream()), "jmt_gemm_f32")
+        kind = "gemm_simt_kernel"
     else:
         raise RuntimeError(f"gemm operand dtypes {a.dtype}/{b.dtype}")
+    if prof is not None:
+        e1.record()
+        prof.append((kind, gemm_flops(M, N, K, nb0 * nb1, ntaps, tuple(a_shift), tuple(b_shift), g.a_rows, g.b_rows,
+                                      a_major, b_major), e0, e1, (M, N, K, nb0 * nb1, ntaps)))
 
 
 def copy2d(ctx: Ctx, src: torch.Tensor, dst: torch.Tensor):
@@ -348,9 +382,7 @@ def linear(ctx: Ctx, x: Var, wname: str, bname: Optional[str], act=L.ACT_NONE, s
             if dy is None:
                 return
             if act != L.ACT_NONE:
-                assert dy.is_contiguous() and y.data.is_contiguous()
-                L.check(ctx.lib.jmt_act_bwd(_ptr(dy), _ptr(y.data), _ptr(dy), dy.numel(), slope, _DT[dy.dtype],
-                                            _stream()), "jmt_act_bwd")
+                dy = _act_bwd(ctx, y, dy, slope)
             if bname:
                 L.check(ctx.lib.jmt_colsum(_ptr(dy), _DT[dy.dtype], dy.stride(0), M, N, _ptr(ctx.pgrad(bname)[r0:r1]),
                                            _stream()), "jmt_colsum")
@@ -369,6 +401,16 @@ def linear(ctx: Ctx, x: Var, wname: str, bname: Optional[str], act=L.ACT_NONE, s
                 ctx.release(y)
         ctx.tape.append(bwd)
     return y
+
+
+def _act_bwd(ctx: Ctx, y: Var, dy: torch.Tensor, slope: float) -> torch.Tensor:
+    """dy * act'(y).  In place when this Var is the only owner of its gradient buffer; otherwise (buffer
+    aliased by a sibling, e.g. the two branches of a residual add) into a fresh buffer."""
+    assert dy.is_contiguous() and y.data.is_contiguous()
+    dst = dy if (y.gbuf is not None and y.gbuf.refs == 1 and y.gbuf.t is dy) else ctx.empty(dy.shape, dy.dtype)
+    L.check(ctx.lib.jmt_act_bwd(_ptr(dy), _ptr(y.data), _ptr(dst), dy.numel(), slope, _DT[dy.dtype], _stream()),
+            "jmt_act_bwd")
+    return dst
 
 
 def add_layernorm(ctx: Ctx, x: Var, res: Optional[Var], gname: str, bname: str) -> Var:
@@ -708,8 +750,7 @@ def causal_conv(ctx: Ctx, x: Var, prefix: str, N: int, Ls: int, cin: int, cout: 
                 return
             assert dy.is_contiguous()
             if act != L.ACT_NONE:
-                L.check(ctx.lib.jmt_act_bwd(_ptr(dy), _ptr(y), _ptr(dy), dy.numel(), LEAKY_SLOPE, _DT[dy.dtype], _stream()),
-                        "jmt_act_bwd")
+                dy = _act_bwd(ctx, out, dy, LEAKY_SLOPE)
             L.check(ctx.lib.jmt_colsum(_ptr(dy), _DT[dy.dtype], cout, N * Ls, cout, _ptr(ctx.pgrad(prefix + "bias")), _stream()),
                     "jmt_colsum")
             # wgrad per tap: dW_j (Cout, Cin) = sum_n dy_n^T shift_j(x_n); reduction over (n, t)

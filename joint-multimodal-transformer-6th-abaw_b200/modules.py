@@ -16,7 +16,7 @@ from torch import nn
 from . import _lib as L
 from . import engine as E
 
-__all__ = ["Two_transformers", "SingleBackbonePretrainer", "MultimodalTransformer_w_JR",
+__all__ = ["JMTPipeline", "Two_transformers", "SingleBackbonePretrainer", "MultimodalTransformer_w_JR",
            "MultimodalTransformer_wo_JR", "FeatureConcatFC", "Intra_modal_transformer_fusion", "FcLayer",
            "TemporalConvNet", "TemporalBlock", "TransformerEncoderBlock", "TransformerEncoderLayer"]
 
@@ -100,6 +100,7 @@ class _TapeFn(torch.autograd.Function):
         outs, setters, getters = runner(ctx, *inputs)
         actx.jctx, actx.setters, actx.getters, actx.names, actx.owner = ctx, setters, getters, names, owner
         actx.n_in = n_in
+        actx.in_shapes = [tuple(i.shape) for i in inputs]
         return tuple(outs)
 
     @staticmethod
@@ -115,7 +116,7 @@ class _TapeFn(torch.autograd.Function):
         hook = getattr(actx.owner, "_grad_sync", None)
         if hook is not None:
             hook(ctx.bucket)                      # NCCL all-reduce of the flat live-gradient bucket
-        gin = [g() if g is not None else None for g in actx.getters]
+        gin = [g().view(sh) if g is not None else None for g, sh in zip(actx.getters, actx.in_shapes)]
         gp = [ctx.pgrads[n] for n in actx.names]
         actx.jctx = None
         return (None, None, None, None, *gin, *gp)
@@ -386,26 +387,31 @@ class Two_transformers(_JmtModule):
         def runner(ctx, f1, f2):
             video, gv = E.l2norm(ctx, f2, f2.requires_grad)          # :118
             audio, ga = E.l2norm(ctx, f1, f1.requires_grad)          # :119
-            if self.linear is not None:
-                video = E.linear(ctx, video, "linear.weight", "linear.bias")
-            time_major = False
-            m = "mm_transformer."
-            if self.joint_modalities == 'TRANSFORMER':
-                feats, time_major = _w_jr_graph(ctx, video, audio, m, self.num_heads, self.num_layers,
-                                                self.output_format, B, T)
-            elif self.joint_modalities == 'FC':
-                feats = _concat_fc_graph(ctx, video, audio, m)
-            else:
-                feats = _wo_jr_graph(ctx, video, audio, m, self.num_heads, self.num_layers, B, T)
-            hv = E.linear(ctx, feats, "vregressor.0.weight", "vregressor.0.bias", act=L.ACT_RELU)
-            ha = E.linear(ctx, feats, "aregressor.0.weight", "aregressor.0.bias", act=L.ACT_RELU)
-            hv, _ = E.dropout(ctx, hv, self.v_dropout)
-            ha, _ = E.dropout(ctx, ha, self.a_dropout)
-            outs, set_gout = E.regressor_tail(ctx, [hv, ha], ["vregressor.3.weight", "aregressor.3.weight"],
-                                              ["vregressor.3.bias", "aregressor.3.bias"], [0, 0], B, T, time_major)
-            return outs, [lambda t: set_gout(0, t), lambda t: set_gout(1, t)], [ga, gv]
+            outs, setters = _two_transformers_graph(ctx, self, "", video, audio, B, T)
+            return outs, setters, [ga, gv]
         v, a = self._run(runner, f1_norm, f2_norm)
         return v, a
+
+
+def _two_transformers_graph(ctx, mod, prefix, video, audio, B, T):
+    """Two_transformers.forward after the L2 normalisation (two_transformers.py:120-128)."""
+    if mod.linear is not None:
+        video = E.linear(ctx, video, prefix + "linear.weight", prefix + "linear.bias")
+    time_major = False
+    m = prefix + "mm_transformer."
+    if mod.joint_modalities == 'TRANSFORMER':
+        feats, time_major = _w_jr_graph(ctx, video, audio, m, mod.num_heads, mod.num_layers, mod.output_format, B, T)
+    elif mod.joint_modalities == 'FC':
+        feats = _concat_fc_graph(ctx, video, audio, m)
+    else:
+        feats = _wo_jr_graph(ctx, video, audio, m, mod.num_heads, mod.num_layers, B, T)
+    hv = E.linear(ctx, feats, prefix + "vregressor.0.weight", prefix + "vregressor.0.bias", act=L.ACT_RELU)
+    ha = E.linear(ctx, feats, prefix + "aregressor.0.weight", prefix + "aregressor.0.bias", act=L.ACT_RELU)
+    hv, _ = E.dropout(ctx, hv, mod.v_dropout)
+    ha, _ = E.dropout(ctx, ha, mod.a_dropout)
+    outs, set_gout = E.regressor_tail(ctx, [hv, ha], [prefix + "vregressor.3.weight", prefix + "aregressor.3.weight"],
+                                      [prefix + "vregressor.3.bias", prefix + "aregressor.3.bias"], [0, 0], B, T, time_major)
+    return outs, [lambda t: set_gout(0, t), lambda t: set_gout(1, t)]
 
 
 class SingleBackbonePretrainer(_JmtModule):
@@ -483,12 +489,8 @@ class FcLayer(_JmtModule):
             xv, gx = E.from_external(ctx, xin, xin.requires_grad)
             y = E.linear(ctx, xv, "fc_layer.weight", "fc_layer.bias")
             out, setter = E.to_external(ctx, y, shape)
-            return [out], [setter], [_reshape_getter(gx, tuple(x.shape))]
+            return [out], [setter], [gx]
         return self._run(runner, x)[0]
-
-
-def _reshape_getter(g, shape):
-    return None if g is None else (lambda: g().view(shape))
 
 
 # ----------------------------------------------------------------------------- TCN
@@ -556,30 +558,110 @@ class TemporalConvNet(_JmtModule):
         # `net.0/net.4` alias conv1/conv2: named_parameters() already de-duplicates them
         return [n for n, _ in self.named_parameters()]
 
+    def block_specs(self):
+        return [(b.n_inputs, b.n_outputs, b.kernel_size, b.dilation, b.p, b.downsample is not None) for b in self.network]
+
     def forward(self, x):
         """x: (N, C, L) -> (N, C_last, L)."""
         N, C0, Ls = x.shape
-        blocks = list(self.network)
+        specs = self.block_specs()
 
         def runner(ctx, xin):
             h, gx = E.transpose_in(ctx, xin, xin.requires_grad)            # channels-last (N*L, C)
-            for i, blk in enumerate(blocks):
-                pre = f"network.{i}."
-                cin, cout, k, d = blk.n_inputs, blk.n_outputs, blk.kernel_size, blk.dilation
-                y = E.causal_conv(ctx, h, pre + "conv1.", N, Ls, cin, cout, k, d, L.ACT_LEAKY)
-                y = E.channel_dropout(ctx, y, blk.p, N, Ls, cout)
-                y = E.causal_conv(ctx, y, pre + "conv2.", N, Ls, cout, cout, k, d, L.ACT_LEAKY)
-                y = E.channel_dropout(ctx, y, blk.p, N, Ls, cout)
-                if blk.downsample is not None:
-                    res = _conv1x1(ctx, h, pre + "downsample.")
-                else:
-                    res = h
-                h = E.add_act(ctx, y, res, L.ACT_LEAKY, E.LEAKY_SLOPE)
+            h = _tcn_graph(ctx, h, "", specs, N, Ls)
             out, setter = E.transpose_out(ctx, h, N, Ls, h.data.shape[1])
             return [out], [setter], [gx]
         return self._run(runner, x)[0]
 
 
+def _tcn_graph(ctx, h, prefix, specs, N, Ls):
+    """TemporalConvNet.forward on channels-last rows (row = n*L + t): per level two weight-normed dilated
+    causal convs (+LeakyReLU, channel dropout), residual (1x1 conv when Cin != Cout), LeakyReLU
+    (temporal_convolutional_model.py:54-57, 81-82)."""
+    for i, (cin, cout, k, d, p, has_ds) in enumerate(specs):
+        pre = f"{prefix}network.{i}."
+        y = E.causal_conv(ctx, h, pre + "conv1.", N, Ls, cin, cout, k, d, L.ACT_LEAKY)
+        y = E.channel_dropout(ctx, y, p, N, Ls, cout)
+        y = E.causal_conv(ctx, y, pre + "conv2.", N, Ls, cout, cout, k, d, L.ACT_LEAKY)
+        y = E.channel_dropout(ctx, y, p, N, Ls, cout)
+        res = _conv1x1(ctx, h, pre + "downsample.") if has_ds else h
+        h = E.add_act(ctx, y, res, L.ACT_LEAKY, E.LEAKY_SLOPE)
+    return h
+
+
 def _conv1x1(ctx, x, prefix):
     """nn.Conv1d(cin, cout, 1) on channels-last rows = a Linear whose (cout, cin, 1) weight is viewed 2-D."""
     return E.linear(ctx, x, prefix + "weight", prefix + "bias")
+
+
+class JMTPipeline(_JmtModule):
+    """The BASELINE.json C2 pipeline as ONE tape (no fp32 round trips between modules):
+
+        visual (B, 1024, T) --TemporalConvNet--> (B, T, 512)   [I3D_WSDDA.forward, I3DWSDDA.py:40-45]
+        audio  (B, T, 768)  --FcLayer(768,512)--> (B, T, 512)  [main.py:360, train.py:265]
+        Two_transformers(audio, visual) -> (vouts, aouts)      [train.py:287]
+
+    Sub-modules keep their reference names/state_dicts (`fusion`, `fc_audio`, `tcn`); either front-end may
+    be None (features are then fed directly).  Inputs may be fp32 or bf16."""
+
+    def __init__(self, fusion: "Two_transformers", fc_audio: Optional["FcLayer"] = None,
+                 tcn: Optional["TemporalConvNet"] = None):
+        super().__init__()
+        self.fusion, self.fc_audio, self.tcn = fusion, fc_audio, tcn
+        self.precision = fusion.precision
+
+    def _dead_prefixes(self):
+        return ("fusion.mm_transformer.final_encoder.", "fusion.mm_transformer.gated_attention.")
+
+    def forward(self, audio, visual):
+        B = audio.shape[0]
+        T = audio.shape[1]
+        fusion = self.fusion
+
+        def runner(ctx, aud, vis):
+            if self.fc_audio is not None:
+                a0, ga = E.from_external(ctx, aud, aud.requires_grad)
+                a1 = E.linear(ctx, a0, "fc_audio.fc_layer.weight", "fc_audio.fc_layer.bias")
+                # two_transformers.py:119 normalises the FcLayer output
+                audio_n = _l2norm_var(ctx, a1)
+            else:
+                audio_n, ga = E.l2norm(ctx, aud, aud.requires_grad)
+            if self.tcn is not None:
+                N, C0, Ls = vis.shape
+                assert N == B and Ls == T
+                h, gv = E.transpose_in(ctx, vis, vis.requires_grad)
+                h = _tcn_graph(ctx, h, "tcn.", self.tcn.block_specs(), N, Ls)     # (B*T, 512) == transpose(1,2)
+                video_n = _l2norm_var(ctx, h)
+            else:
+                video_n, gv = E.l2norm(ctx, vis, vis.requires_grad)
+            outs, setters = _two_transformers_graph(ctx, fusion, "fusion.", video_n, audio_n, B, T)
+            return outs, setters, [ga, gv]
+        v, a = self._run(runner, audio, visual)
+        return v, a
+
+
+def _l2norm_var(ctx, x):
+    """F.normalize on an activation Var (rows, D) staying in the activation dtype."""
+    rows, D = x.data.shape
+    out = ctx.empty((rows, D))
+    inv = ctx.empty((rows,), torch.float32) if ctx.record else None
+    L.check(ctx.lib.jmt_l2norm_fwd(E._ptr(x.data), ctx.acode, x.data.stride(0), E._ptr(out), ctx.acode, rows, D, 1e-12,
+                                   E._ptr(inv), E._stream()), "jmt_l2norm_fwd")
+    y = E.Var(out)
+    if ctx.record:
+        def bwd():
+            if y.grad is None:
+                return
+            dx32 = ctx.empty((rows, D), torch.float32)
+            L.check(ctx.lib.jmt_l2norm_bwd(E._ptr(y.grad), E._ptr(out), ctx.acode, E._ptr(inv), 1e-12, E._ptr(dx32), rows, D,
+                                           E._stream()), "jmt_l2norm_bwd")
+            if ctx.adt == torch.float32:
+                gb = E.GradBuf(dx32)
+            else:
+                gb = E.GradBuf(ctx.empty((rows, D)))
+                E.copy2d(ctx, dx32, gb.t)
+            ctx.add_grad(x, gb)
+            gb.refs -= 1
+            ctx.release(y)
+        ctx.tape.append(bwd)
+    return y

@@ -195,7 +195,8 @@ def test_layernorm_l2norm_softmax(dt):
     dz = torch.empty(rows, D, device=dev, dtype=dt)
     dgam = torch.zeros(D, device=dev)
     dbet = torch.zeros(D, device=dev)
-    L.check(lib.jmt_add_layernorm_bwd(E._ptr(dy.to(dev)), E._ptr(xd), E._ptr(rd), E._ptr(gd), E._ptr(mean), E._ptr(rstd), E._ptr(dz), 0,
+    dy_d = dy.to(dev)
+    L.check(lib.jmt_add_layernorm_bwd(E._ptr(dy_d), E._ptr(xd), E._ptr(rd), E._ptr(gd), E._ptr(mean), E._ptr(rstd), E._ptr(dz), 0,
                                       E._ptr(dgam), E._ptr(dbet), rows, D, code, st), "lnb")
     assert (dz.float().cpu().double() - z.grad).abs().max() < tol * 8
     assert (dgam.cpu().double() - gg.grad).abs().max() < tol * 40
@@ -205,14 +206,16 @@ def test_layernorm_l2norm_softmax(dt):
     x768[5] = 0.0                     # zero row: clamp path
     out = torch.empty(rows, 768, device=dev, dtype=dt)
     inv = torch.empty(rows, device=dev)
-    L.check(lib.jmt_l2norm_fwd(E._ptr(x768.to(dev)), L.F32, 768, E._ptr(out), code, rows, 768, 1e-12, E._ptr(inv), st), "l2")
+    x768_d = x768.to(dev)
+    L.check(lib.jmt_l2norm_fwd(E._ptr(x768_d), L.F32, 768, E._ptr(out), code, rows, 768, 1e-12, E._ptr(inv), st), "l2")
     xr = x768.double().requires_grad_(True)
     refn = torch.nn.functional.normalize(xr, dim=-1)
     assert (out.float().cpu().double() - refn).abs().max() < tol
     dyn = torch.randn(rows, 768).to(dt)
     refn.backward(dyn.double())
     dx = torch.empty(rows, 768, device=dev)
-    L.check(lib.jmt_l2norm_bwd(E._ptr(dyn.to(dev)), E._ptr(out), code, E._ptr(inv), 1e-12, E._ptr(dx), rows, 768, st), "l2b")
+    dyn_d = dyn.to(dev)
+    L.check(lib.jmt_l2norm_bwd(E._ptr(dyn_d), E._ptr(out), code, E._ptr(inv), 1e-12, E._ptr(dx), rows, 768, st), "l2b")
     m = torch.ones(rows, dtype=torch.bool)
     m[5] = False
     assert (dx.cpu().double()[m] - xr.grad[m]).abs().max() < tol * 4
@@ -220,13 +223,15 @@ def test_layernorm_l2norm_softmax(dt):
     R, Ccols, ld = 257, 300, 304
     s = torch.randn(R, ld) * 3
     p = torch.full((R, ld), 7.0, device=dev, dtype=dt)
-    L.check(lib.jmt_softmax_fwd(E._ptr(s.to(dev)), ld, E._ptr(p), code, ld, R, Ccols, st), "sm")
+    s_d = s.to(dev)
+    L.check(lib.jmt_softmax_fwd(E._ptr(s_d), ld, E._ptr(p), code, ld, R, Ccols, st), "sm")
     refp = torch.softmax(s[:, :Ccols].double(), -1)
     assert (p.float().cpu()[:, :Ccols].double() - refp).abs().max() < tol
     assert (p.float().cpu()[:, Ccols:] == 0).all()
     dp = torch.randn(R, ld)
     ds = torch.empty(R, ld, device=dev, dtype=dt)
-    L.check(lib.jmt_softmax_bwd(E._ptr(p), code, ld, E._ptr(dp.to(dev)), ld, E._ptr(ds), code, ld, R, Ccols, st), "smb")
+    dp_d = dp.to(dev)
+    L.check(lib.jmt_softmax_bwd(E._ptr(p), code, ld, E._ptr(dp_d), ld, E._ptr(ds), code, ld, R, Ccols, st), "smb")
     pp = p.float().cpu()[:, :Ccols].double()
     refds = pp * (dp[:, :Ccols].double() - (pp * dp[:, :Ccols].double()).sum(-1, keepdim=True))
     assert (ds.float().cpu()[:, :Ccols].double() - refds).abs().max() < tol * 2
@@ -330,12 +335,14 @@ def test_small_kernels():
     # transpose with cast
     x = torch.randn(3, 37, 70)
     o = torch.empty(3, 70, 37, device=dev, dtype=torch.bfloat16)
-    L.check(lib.jmt_transpose(E._ptr(x.to(dev)), L.F32, E._ptr(o), L.BF16, 3, 37, 70, st), "tr")
+    x_d = x.to(dev)
+    L.check(lib.jmt_transpose(E._ptr(x_d), L.F32, E._ptr(o), L.BF16, 3, 37, 70, st), "tr")
     assert torch.equal(o.cpu(), x.transpose(1, 2).to(torch.bfloat16))
     # colsum
     a = torch.randn(1000, 130).to(torch.bfloat16)
     out = torch.zeros(130, device=dev)
-    L.check(lib.jmt_colsum(E._ptr(a.to(dev)), L.BF16, 130, 1000, 130, E._ptr(out), st), "cs")
+    a_d = a.to(dev)
+    L.check(lib.jmt_colsum(E._ptr(a_d), L.BF16, 130, 1000, 130, E._ptr(out), st), "cs")
     assert (out.cpu() - a.float().sum(0)).abs().max() < 1e-3
     # weight norm fwd/bwd
     cout, cin, k = 24, 40, 5
@@ -344,7 +351,8 @@ def test_small_kernels():
     wf = torch.empty(cout, k * cin, device=dev)
     wd = torch.empty(cin, k * cout, device=dev)
     nrm = torch.empty(cout, device=dev)
-    L.check(lib.jmt_weight_norm_fwd(E._ptr(g.to(dev)), E._ptr(v.to(dev)), E._ptr(wf), E._ptr(wd), L.F32, E._ptr(nrm), cout, cin, k, st), "wn")
+    g_d, v_d = g.to(dev), v.to(dev)      # keep device operands alive across the async launches
+    L.check(lib.jmt_weight_norm_fwd(E._ptr(g_d), E._ptr(v_d), E._ptr(wf), E._ptr(wd), L.F32, E._ptr(nrm), cout, cin, k, st), "wn")
     gg = g.double().requires_grad_(True)
     vv = v.double().requires_grad_(True)
     w = vv * (gg / vv.pow(2).sum((1, 2), keepdim=True).sqrt())
@@ -355,7 +363,7 @@ def test_small_kernels():
     dwf = dw.permute(0, 2, 1).reshape(cout, -1).contiguous().to(dev)
     dg = torch.empty(cout, 1, 1, device=dev)
     dv = torch.empty(cout, cin, k, device=dev)
-    L.check(lib.jmt_weight_norm_bwd(E._ptr(dwf), E._ptr(g.to(dev)), E._ptr(v.to(dev)), E._ptr(nrm), E._ptr(dg), E._ptr(dv), cout, cin, k, st), "wnb")
+    L.check(lib.jmt_weight_norm_bwd(E._ptr(dwf), E._ptr(g_d), E._ptr(v_d), E._ptr(nrm), E._ptr(dg), E._ptr(dv), cout, cin, k, st), "wnb")
     assert (dg.cpu().double() - gg.grad).abs().max() < 1e-4
     assert (dv.cpu().double() - vv.grad).abs().max() < 1e-4
     # dropout mask statistics + determinism
@@ -381,6 +389,7 @@ def test_small_kernels():
     L.check(lib.jmt_attn_small_fwd(E._ptr(qd), E._ptr(out), E._ptr(probs), Ls, N, Em, h, 1 / math.sqrt(dh), L.F32, st), "as")
     assert (out.cpu().double() - ref.detach()).abs().max() < 1e-4
     dq = torch.empty(Ls, N, 3 * Em, device=dev)
-    L.check(lib.jmt_attn_small_bwd(E._ptr(qd), E._ptr(do.float().to(dev)), E._ptr(probs), E._ptr(dq), Ls, N, Em, h, 1 / math.sqrt(dh), L.F32, st), "asb")
+    do_d = do.float().to(dev)
+    L.check(lib.jmt_attn_small_bwd(E._ptr(qd), E._ptr(do_d), E._ptr(probs), E._ptr(dq), Ls, N, Em, h, 1 / math.sqrt(dh), L.F32, st), "asb")
     assert (dq.cpu().double() - qkv.grad).abs().max() < 1e-4
     torch.cuda.synchronize()
