@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--gemm-table", default=None, help="write the per-shape GEMM timing table (roofline pass) to this file")
     return ap.parse_args()
 
 
@@ -294,6 +295,19 @@ def main():
                 "gemm_gflop_per_step": tot_fl / nprof / 1e9,
                 "avg_launch_us": 1e3 * tot_ms / max(1, len(sel)),
                 "step_model_gflop": 3 * FWD_GFLOP_PER_WINDOW * B}
+        if args.gemm_table:
+            agg = {}
+            for r in rec:
+                key = (r[0],) + tuple(r[4])
+                a = agg.setdefault(key, [0, 0.0, 0.0])
+                a[0] += 1
+                a[1] += r[2].elapsed_time(r[3])
+                a[2] += r[1]
+            with open(args.gemm_table, "w") as f:
+                f.write("kernel M N K nb taps | launches/step ms/step GFLOP/step TFLOP/s\n")
+                for key, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+                    f.write(f"{key[0]} {key[1]} {key[2]} {key[3]} {key[4]} {key[5]} | {a[0] / nprof:.1f} {a[1] / nprof:.3f} "
+                            f"{a[2] / nprof / 1e9:.1f} {a[2] / (a[1] / 1e3) / 1e12 if a[1] > 0 else 0:.1f}\n")
         if world > 1:
             dist.barrier()
     elif world > 1 and not args.no_roofline:

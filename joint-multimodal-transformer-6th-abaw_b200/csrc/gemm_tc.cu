@@ -26,6 +26,8 @@ constexpr int kAStageBytes = kBlockM * kBlockK * 2;   // 16 KiB
 constexpr int kMaxStages = 8;
 constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;       // TMEM columns per accumulator stage
+constexpr int kEpiStageBytes = 4096;      // 32 rows x 128 B per epilogue warp
+constexpr int kEpiSmemBytes = 4 * kEpiStageBytes + 4 * 1024;
 constexpr uint32_t kSpinLimit = 1u << 24;   // ~1 s of polling, far beyond any legitimate wait
 
 struct TcParams {
@@ -45,6 +47,7 @@ struct TcParams {
   int64_t d_ld, d_bs0, d_bs1;
   float alpha, slope;
   int d_dtype, act, store_mode, vec_ok;
+  int tma_store;      // epilogue through swizzled smem + TMA store / reduce-add (needs 16-byte aligned D geometry)
 };
 
 // ----------------------------------------------------------------------------- PTX wrappers
@@ -76,6 +79,25 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
   asm volatile(
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -130,49 +152,17 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int t) {
   return c;
 }
 
-template <typename T> struct Pack32;   // store 32 consecutive fp32 results of one row
-template <> struct Pack32<float> {
-  static __device__ __forceinline__ void store(float* dst, const float (&v)[32], int mode) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float4 o = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-      float4* q = reinterpret_cast<float4*>(dst) + i;
-      if (mode == JMT_ACCUMULATE) { const float4 c = *q; o.x += c.x; o.y += c.y; o.z += c.z; o.w += c.w; }
-      *q = o;
-    }
-  }
-};
-template <> struct Pack32<__nv_bfloat16> {
-  static __device__ __forceinline__ void store(__nv_bfloat16* dst, const float (&v)[32], int mode) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      uint4* q = reinterpret_cast<uint4*>(dst) + i;
-      float w[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) w[j] = v[8 * i + j];
-      if (mode == JMT_ACCUMULATE) {
-        const uint4 c = *q;
-        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&c);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) { const float2 f = __bfloat1622float2(h[j]); w[2 * j] += f.x; w[2 * j + 1] += f.y; }
-      }
-      uint4 o;
-      __nv_bfloat162* ho = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) ho[j] = __floats2bfloat162_rn(w[2 * j], w[2 * j + 1]);
-      *q = o;
-    }
-  }
-};
-
 __global__ void __launch_bounds__(kTcThreads, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const TcParams p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+               const __grid_constant__ CUtensorMap tma_d, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte aligned carve-up (SWIZZLE_128B atoms are 1024 B)
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = smem_base;
   const uint32_t sB = sA + p.stages * kAStageBytes;
-  const uint32_t bars = sB + p.stages * p.b_stage_bytes;     // 8-byte aligned (multiples of 1024)
+  const uint32_t sD = sB + p.stages * p.b_stage_bytes;       // 4 epilogue warps x 4 KiB staging (1024-aligned)
+  const uint32_t sBias = sD + 4 * kEpiStageBytes;            // 4 x 256 floats (per-warp private copies)
+  const uint32_t bars = sBias + 4 * 1024;                    // 8-byte aligned
   const uint32_t full_bar = bars, empty_bar = bars + 8 * kMaxStages;
   const uint32_t tfull_bar = bars + 16 * kMaxStages, tempty_bar = tfull_bar + 16;
   const uint32_t tmem_slot = tempty_bar + 16;
@@ -269,47 +259,116 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   } else {
     // ================================ epilogue (warps 2..5) ================================
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
+    const uint32_t stage_smem = sD + q * kEpiStageBytes;
+    const uint32_t bias_smem = sBias + q * 1024;
+    float* bias_ptr = reinterpret_cast<float*>(smem_aligned + (bias_smem - smem_base));
+    const uint32_t row_smem = stage_smem + lane * 128;
+    const uint32_t sw = lane & 7;                 // 128B-swizzle phase of this thread's staging row
     int tile_iter = 0;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tile_iter) {
       const TileCoord c = decode_tile(p, t);
       const int split = (t / (p.n_tiles * p.m_tiles)) / p.batch_tiles;
       const int acc = tile_iter & 1;
       const uint32_t acc_phase = (tile_iter >> 1) & 1;
+      const bool add_bias = p.bias != nullptr && split == 0;
+      // stage this tile's bias slice in shared memory (one private copy per warp; overlaps the mainloop)
+      __syncwarp();
+      for (int i = lane; i < p.block_n; i += 32)
+        bias_ptr[i] = (add_bias && c.n0 + i < p.N) ? __ldg(p.bias + c.n0 + i) : 0.f;
+      __syncwarp();
       mbar_wait(tfull_bar + 8 * acc, acc_phase);
       tc_fence_after();
       const int m = c.m0 + q * 32 + lane;
       const int b0 = c.batch % p.nb0, b1 = c.batch / p.nb0;
-      const int64_t row_off = (int64_t)b0 * p.d_bs0 + (int64_t)b1 * p.d_bs1 + (int64_t)m * p.d_ld;
-      const bool add_bias = p.bias != nullptr && split == 0;
-      for (int c0 = 0; c0 < p.block_n; c0 += 32) {
-        const int n = c.n0 + c0;
-        if (n >= p.N) break;                      // warp-uniform
-        uint32_t r[32];
-        tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kAccStride + c0), r);
-        if (m >= p.M) continue;
-        float v[32];
+      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kAccStride);
+      if (p.tma_store) {
+        const bool warp_rows_valid = c.m0 + q * 32 < p.M;      // warp-uniform
+        if (p.d_dtype == JMT_BF16) {
+          for (int c0 = 0; c0 < p.block_n; c0 += 64) {
+            if (c.n0 + c0 >= p.N) break;
+            uint32_t pk[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float x = p.alpha * __uint_as_float(r[j]);
-          if (add_bias && n + j < p.N) x += __ldg(p.bias + n + j);
-          v[j] = apply_act(x, p.act, p.slope);
-        }
-        if (p.vec_ok && n + 32 <= p.N && p.store_mode != JMT_ATOMIC_ADD) {
-          if (p.d_dtype == JMT_F32) Pack32<float>::store((float*)p.d + row_off + n, v, p.store_mode);
-          else Pack32<__nv_bfloat16>::store((__nv_bfloat16*)p.d + row_off + n, v, p.store_mode);
+            for (int h = 0; h < 2; ++h) {
+              if (c0 + 32 * h < p.block_n) {
+                uint32_t r[32];
+                tc_ld32(tbase + c0 + 32 * h, r);
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  const float4 bv = *reinterpret_cast<const float4*>(bias_ptr + c0 + 32 * h + j);
+                  const float x0 = apply_act(fmaf(p.alpha, __uint_as_float(r[j]), bv.x), p.act, p.slope);
+                  const float x1 = apply_act(fmaf(p.alpha, __uint_as_float(r[j + 1]), bv.y), p.act, p.slope);
+                  const float x2 = apply_act(fmaf(p.alpha, __uint_as_float(r[j + 2]), bv.z), p.act, p.slope);
+                  const float x3 = apply_act(fmaf(p.alpha, __uint_as_float(r[j + 3]), bv.w), p.act, p.slope);
+                  pk[16 * h + j / 2] = pack_bf16(x0, x1);
+                  pk[16 * h + j / 2 + 1] = pack_bf16(x2, x3);
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) pk[16 * h + j] = 0u;
+              }
+            }
+            if (lane == 0) bulk_wait_read0();       // previous TMA store has finished reading the staging tile
+            __syncwarp();
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch)
+              st_shared_v4(row_smem + ((ch ^ sw) << 4), pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0 && warp_rows_valid) {
+              if (p.store_mode == JMT_STORE) tma_store_4d(&tma_d, stage_smem, c.n0 + c0, c.m0 + q * 32, b0, b1);
+              else tma_reduce_add_4d(&tma_d, stage_smem, c.n0 + c0, c.m0 + q * 32, b0, b1);
+              bulk_commit();
+            }
+          }
         } else {
+          for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+            if (c.n0 + c0 >= p.N) break;
+            uint32_t r[32];
+            tc_ld32(tbase + c0, r);
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 bv = *reinterpret_cast<const float4*>(bias_ptr + c0 + j);
+              r[j] = __float_as_uint(apply_act(fmaf(p.alpha, __uint_as_float(r[j]), bv.x), p.act, p.slope));
+              r[j + 1] = __float_as_uint(apply_act(fmaf(p.alpha, __uint_as_float(r[j + 1]), bv.y), p.act, p.slope));
+              r[j + 2] = __float_as_uint(apply_act(fmaf(p.alpha, __uint_as_float(r[j + 2]), bv.z), p.act, p.slope));
+              r[j + 3] = __float_as_uint(apply_act(fmaf(p.alpha, __uint_as_float(r[j + 3]), bv.w), p.act, p.slope));
+            }
+            if (lane == 0) bulk_wait_read0();
+            __syncwarp();
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch)
+              st_shared_v4(row_smem + ((ch ^ sw) << 4), r[4 * ch], r[4 * ch + 1], r[4 * ch + 2], r[4 * ch + 3]);
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0 && warp_rows_valid) {
+              if (p.store_mode == JMT_STORE) tma_store_4d(&tma_d, stage_smem, c.n0 + c0, c.m0 + q * 32, b0, b1);
+              else tma_reduce_add_4d(&tma_d, stage_smem, c.n0 + c0, c.m0 + q * 32, b0, b1);
+              bulk_commit();
+            }
+          }
+        }
+      } else {
+        // direct (unaligned D geometry): per-thread row stores / atomics
+        const int64_t row_off = (int64_t)b0 * p.d_bs0 + (int64_t)b1 * p.d_bs1 + (int64_t)m * p.d_ld;
+        for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+          const int n = c.n0 + c0;
+          if (n >= p.N) break;                      // warp-uniform
+          uint32_t r[32];
+          tc_ld32(tbase + c0, r);
+          if (m >= p.M) continue;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             if (n + j >= p.N) break;
+            const float v = apply_act(fmaf(p.alpha, __uint_as_float(r[j]), bias_ptr[c0 + j]), p.act, p.slope);
             const int64_t idx = row_off + n + j;
             if (p.d_dtype == JMT_F32) {
               float* d = (float*)p.d;
-              if (p.store_mode == JMT_STORE) d[idx] = v[j];
-              else if (p.store_mode == JMT_ACCUMULATE) d[idx] += v[j];
-              else atomicAdd(d + idx, v[j]);
+              if (p.store_mode == JMT_STORE) d[idx] = v;
+              else if (p.store_mode == JMT_ACCUMULATE) d[idx] += v;
+              else atomicAdd(d + idx, v);
             } else {
               __nv_bfloat16* d = (__nv_bfloat16*)p.d;
-              d[idx] = __float2bfloat16_rn(p.store_mode == JMT_STORE ? v[j] : __bfloat162float(d[idx]) + v[j]);
+              d[idx] = __float2bfloat16_rn(p.store_mode == JMT_STORE ? v : __bfloat162float(d[idx]) + v);
             }
           }
         }
@@ -318,6 +377,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar + 8 * acc);
     }
+    if (lane == 0) bulk_wait0();                   // all TMA stores of this warp have completed
   }
 
   tc_fence_before();
@@ -371,6 +431,29 @@ static int make_map(CUtensorMap* map, const void* ptr, int64_t inner, int64_t ro
   return JMT_OK;
 }
 
+// D tensor map: (N, M, b0, b1), box {128 bytes of columns, 32 rows}, 128B swizzle (matches the epilogue staging)
+static int make_map_d(CUtensorMap* map, const void* ptr, int dtype, int64_t inner, int64_t rows, int64_t ld, int64_t nb0,
+                      int64_t bs0, int64_t nb1, int64_t bs1, const char* who) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { set_error("%s: cuTensorMapEncodeTiled unavailable (no CUDA driver?)", who); return JMT_ERR_CUDA; }
+  const cuuint64_t es = dtype == JMT_F32 ? 4 : 2;
+  const cuuint64_t dims[4] = {(cuuint64_t)inner, (cuuint64_t)rows, (cuuint64_t)nb0, (cuuint64_t)nb1};
+  const cuuint64_t row_bytes = (cuuint64_t)ld * es;
+  const cuuint64_t strides[3] = {row_bytes, nb0 > 1 ? (cuuint64_t)bs0 * es : row_bytes, nb1 > 1 ? (cuuint64_t)bs1 * es : row_bytes};
+  const cuuint32_t box[4] = {(cuuint32_t)(128 / es), 32, 1, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, dtype == JMT_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
+                   const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("%s: cuTensorMapEncodeTiled failed (%d) inner=%lld rows=%lld ld=%lld nb0=%lld bs0=%lld nb1=%lld bs1=%lld", who,
+              (int)r, (long long)inner, (long long)rows, (long long)ld, (long long)nb0, (long long)bs0, (long long)nb1,
+              (long long)bs1);
+    return JMT_ERR_CUDA;
+  }
+  return JMT_OK;
+}
+
 static int pick_block_n(int N) {
   int best = 32; long best_cost = -1;
   for (int bn = 32; bn <= 256; bn += 32) {
@@ -418,7 +501,7 @@ extern "C" int jmt_gemm_bf16(const jmt_gemm_desc* g, void* stream) {
   p.b_stage_bytes = g->b_major == JMT_MAJOR_K ? p.block_n * 128 : b_chunks * 8192;
   p.b_tx_bytes = p.b_stage_bytes;
   const int stage_bytes = kAStageBytes + p.b_stage_bytes;
-  const int budget = 227 * 1024 - 1024 /*align*/ - 512 /*barriers*/;
+  const int budget = 227 * 1024 - 1024 /*align*/ - 512 /*barriers*/ - kEpiSmemBytes;
   p.stages = budget / stage_bytes;
   if (p.stages > kMaxStages) p.stages = kMaxStages;
   JMT_REQUIRE(p.stages >= 2, "jmt_gemm_bf16: shared memory budget");
@@ -442,7 +525,16 @@ extern "C" int jmt_gemm_bf16(const jmt_gemm_desc* g, void* stream) {
     rc = make_map(&map_b, g->b, g->N, g->b_rows, g->b_ld, bnb0, g->b_bs0, bnb1, g->b_bs1, kBlockK, "jmt_gemm_bf16(B)");
   if (rc != JMT_OK) return rc;
 
-  const int smem = 1024 + p.stages * stage_bytes + 512;
+  // D through TMA (store / reduce-add) when its geometry is 16-byte aligned; bf16 read-modify-write
+  // accumulation and fp32 atomics both become cp.reduce.async.bulk.tensor .add
+  CUtensorMap map_d = map_a;
+  p.tma_store = p.vec_ok;
+  if (p.tma_store) {
+    const int dnb0 = p.reduce_batch ? 1 : g->nb0, dnb1 = p.reduce_batch ? 1 : g->nb1;
+    rc = make_map_d(&map_d, g->d, g->d_dtype, g->N, g->M, g->d_ld, dnb0, g->d_bs0, dnb1, g->d_bs1, "jmt_gemm_bf16(D)");
+    if (rc != JMT_OK) return rc;
+  }
+  const int smem = 1024 + p.stages * stage_bytes + kEpiSmemBytes + 512;
   static std::atomic<int> attr_set[64];     // per device (immutable once set)
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); set_error("jmt_gemm_bf16: no CUDA device"); return JMT_ERR_CUDA; }
@@ -452,6 +544,6 @@ extern "C" int jmt_gemm_bf16(const jmt_gemm_desc* g, void* stream) {
     attr_set[dev & 63].store(1, std::memory_order_release);
   }
   const int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
-  gemm_tc_kernel<<<grid, kTcThreads, smem, (cudaStream_t)stream>>>(map_a, map_b, p);
+  gemm_tc_kernel<<<grid, kTcThreads, smem, (cudaStream_t)stream>>>(map_a, map_b, map_d, p);
   return check_launch("gemm_tc_kernel");
 }
