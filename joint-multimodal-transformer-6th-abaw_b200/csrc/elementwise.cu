@@ -90,23 +90,39 @@ transpose_kernel(const TI* __restrict__ in, TO* __restrict__ out, int R, int C) 
   }
 }
 
-// out[c] += sum_r x[r*ld + c]
+// out[c] += sum_r x[r*ld + c].  Block = 32 column-groups (8 columns each, one 16-byte load) x 8 row lanes;
+// grid.y slabs of rows; per-block shared reduction then one fp32 atomic per column.
 template <typename T>
 __global__ void __launch_bounds__(256)
-colsum_kernel(const T* __restrict__ x, int64_t ld, int64_t rows, int cols, float* __restrict__ out) {
-  // block = 32 column-lanes x 8 row-lanes; each block owns a 32-column strip and a row slab
-  __shared__ float sh[8][33];
+colsum_kernel(const T* __restrict__ x, int64_t ld, int64_t rows, int cols, float* __restrict__ out, int vec) {
+  __shared__ float sh[8][257];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + tx;
-  float s = 0.f;
-  if (c < cols)
-    for (int64_t r = (int64_t)blockIdx.y * 8 + ty; r < rows; r += (int64_t)gridDim.y * 8) s += to_f32(x[r * ld + c]);
-  sh[ty][tx] = s;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  const int c0 = blockIdx.x * 256 + tx * 8;
+  if (vec) {
+    if (c0 < cols) {
+      for (int64_t r = (int64_t)blockIdx.y * 8 + ty; r < rows; r += (int64_t)gridDim.y * 8) {
+        Vec8<T> v; v.load(x + r * ld + c0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] += v.v[i];
+      }
+    }
+  } else {
+    for (int64_t r = (int64_t)blockIdx.y * 8 + ty; r < rows; r += (int64_t)gridDim.y * 8)
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (c0 + i < cols) acc[i] += to_f32(x[r * ld + c0 + i]);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sh[ty][tx * 8 + i] = acc[i];
   __syncthreads();
-  if (ty == 0 && c < cols) {
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c < cols) {
     float t = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) t += sh[i][tx];
+    for (int i = 0; i < 8; ++i) t += sh[i][threadIdx.x];
     atomicAdd(out + c, t);
   }
 }
@@ -114,8 +130,25 @@ colsum_kernel(const T* __restrict__ x, int64_t ld, int64_t rows, int cols, float
 template <typename T>
 __global__ void __launch_bounds__(kEwThreads)
 apply_mask_kernel(const T* __restrict__ x, const uint8_t* __restrict__ mask, T* __restrict__ out, int64_t total, int L,
-                  int C, int per_channel, float scale) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+                  int C, int per_channel, float scale, int vec) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nt = (int64_t)gridDim.x * blockDim.x;
+  if (vec) {      // C % 8 == 0: one 16-byte (bf16) / 32-byte (fp32) access and one 8-byte mask load per thread-iteration
+    const int c8n = C / 8;
+    const int64_t rows = total / C;
+    for (int64_t i = tid; i < rows * c8n; i += nt) {
+      const int64_t r = i / c8n;
+      const int c = (int)(i - r * c8n) * 8;
+      const int64_t mi = per_channel ? (r / L) * C + c : r * C + c;
+      const uint2 mk = *reinterpret_cast<const uint2*>(mask + mi);
+      const uint8_t* mb = reinterpret_cast<const uint8_t*>(&mk);
+      Vec8<T> v; v.load(x + r * C + c);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v.v[k] = mb[k] ? v.v[k] * scale : 0.f;
+      v.store(out + r * C + c);
+    }
+    return;
+  }
+  for (int64_t i = tid; i < total; i += nt) {
     int64_t mi = i;
     if (per_channel) { const int64_t b = i / ((int64_t)L * C); const int c = (int)(i % C); mi = b * C + c; }
     out[i] = from_f32<T>(mask[mi] ? to_f32(x[i]) * scale : 0.f);
@@ -359,12 +392,13 @@ extern "C" int jmt_transpose(const void* in, int in_dtype, void* out, int out_dt
 extern "C" int jmt_colsum(const void* x, int dtype, int64_t ld, int64_t rows, int cols, float* out, void* stream) {
   JMT_REQUIRE(x && out && rows >= 0 && cols > 0, "jmt_colsum: bad arguments");
   if (rows == 0) return JMT_OK;
-  const int gx = (cols + 31) / 32;
-  int gy = (int)((rows + 255) / 256);
-  const int cap = (kNumSMs * 8 + gx - 1) / gx;
+  const int gx = (cols + 255) / 256;
+  int gy = (int)((rows + 63) / 64);
+  const int cap = (kNumSMs * 4 + gx - 1) / gx;
   if (gy > cap) gy = cap;
   if (gy < 1) gy = 1;
-  JMT_DISPATCH_DTYPE(dtype, T, (colsum_kernel<T><<<dim3(gx, gy), 256, 0, (cudaStream_t)stream>>>((const T*)x, ld, rows, cols, out)));
+  const int vec = (cols % 8 == 0 && ld % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) ? 1 : 0;
+  JMT_DISPATCH_DTYPE(dtype, T, (colsum_kernel<T><<<dim3(gx, gy), 256, 0, (cudaStream_t)stream>>>((const T*)x, ld, rows, cols, out, vec)));
   return check_launch("colsum_kernel");
 }
 
@@ -373,7 +407,9 @@ extern "C" int jmt_apply_mask(const void* x, const uint8_t* mask, void* out, int
   JMT_REQUIRE(x && mask && out, "jmt_apply_mask: bad arguments");
   const int64_t total = nb * L * C;
   if (total == 0) return JMT_OK;
-  JMT_DISPATCH_DTYPE(dtype, T, (apply_mask_kernel<T><<<grid_for(total, kEwThreads * 4), kEwThreads, 0, (cudaStream_t)stream>>>((const T*)x, mask, (T*)out, total, L, C, per_channel, scale)));
+  const int vec = (C % 8 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 31) == 0 &&
+                   (reinterpret_cast<uintptr_t>(mask) & 7) == 0) ? 1 : 0;
+  JMT_DISPATCH_DTYPE(dtype, T, (apply_mask_kernel<T><<<grid_for(total / 8 + 1, kEwThreads * 2), kEwThreads, 0, (cudaStream_t)stream>>>((const T*)x, mask, (T*)out, total, L, C, per_channel, scale, vec)));
   return check_launch("apply_mask_kernel");
 }
 

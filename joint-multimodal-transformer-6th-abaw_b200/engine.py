@@ -284,10 +284,11 @@ def copy2d(ctx: Ctx, src: torch.Tensor, dst: torch.Tensor):
 
 
 def split_k_for(red: int, tiles: int) -> int:
-    """Split factor for weight-gradient GEMMs: `red` reduction rows, `tiles` output tiles."""
+    """Split factor for weight-gradient GEMMs (`red` reduction rows, `tiles` output tiles): about one
+    wave of 148 CTAs, each keeping at least 8 k-blocks of work."""
     kblocks = max(1, (red + 63) // 64)
-    want = max(1, (148 * 2) // max(1, tiles))
-    return max(1, min(want, kblocks // 4)) if kblocks >= 8 else 1
+    want = max(1, 148 // max(1, tiles))
+    return max(1, min(want, kblocks // 8)) if kblocks >= 16 else 1
 
 
 # --------------------------------------------------------------------------- differentiable ops
@@ -756,7 +757,7 @@ def causal_conv(ctx: Ctx, x: Var, prefix: str, N: int, Ls: int, cin: int, cout: 
             # wgrad per tap: dW_j (Cout, Cin) = sum_n dy_n^T shift_j(x_n); reduction over (n, t)
             dw = ctx.zeros((cout, k * cin), torch.float32)
             tiles = ((cout + 127) // 128) * ((cin + 255) // 256)
-            sk = split_k_for(N * Ls, tiles * k)
+            sk = split_k_for(N * Ls, tiles)          # each tap is its own launch: fill the chip per launch
             for j in range(k):
                 gemm(ctx, dy, x.data, dw[:, j * cin:(j + 1) * cin], M=cout, N=cin, K=Ls,
                      a_major=L.MAJOR_MN, b_major=L.MAJOR_MN, a_rows=Ls, b_rows=Ls, a_ld=cout, b_ld=cin, d_ld=k * cin,
