@@ -271,7 +271,7 @@ def main():
 
     # ---- roofline of the dominant kernel (gemm_tc_kernel): per-launch CUDA events over timed steps
     roof = None
-    if not args.no_roofline and rank == 0:
+    if not args.no_roofline:              # every rank runs the profiled steps (they contain collectives)
         peaks = {}
         pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(pk_path):
@@ -295,7 +295,7 @@ def main():
                 "gemm_gflop_per_step": tot_fl / nprof / 1e9,
                 "avg_launch_us": 1e3 * tot_ms / max(1, len(sel)),
                 "step_model_gflop": 3 * FWD_GFLOP_PER_WINDOW * B}
-        if args.gemm_table:
+        if args.gemm_table and rank == 0:
             agg = {}
             for r in rec:
                 key = (r[0],) + tuple(r[4])
@@ -310,8 +310,6 @@ def main():
                             f"{a[2] / nprof / 1e9:.1f} {a[2] / (a[1] / 1e3) / 1e12 if a[1] > 0 else 0:.1f}\n")
         if world > 1:
             dist.barrier()
-    elif world > 1 and not args.no_roofline:
-        dist.barrier()
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

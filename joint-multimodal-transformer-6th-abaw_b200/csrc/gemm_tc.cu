@@ -2,7 +2,7 @@
 //
 //   warp 0 (1 elected thread) : TMA producer   -- cp.async.bulk.tensor.4d -> 128B-swizzled smem ring
 //   warp 1 (1 elected thread) : MMA issuer     -- tcgen05.mma.cta_group::1.kind::f16, fp32 accum in TMEM
-//   warps 2..5                : epilogue       -- tcgen05.ld 32x32b -> alpha/bias/activation -> global
+//   warps 2..9                : epilogue       -- tcgen05.ld 32x32b -> alpha/bias/activation -> global
 //
 // Two TMEM accumulator stages (2 x 256 columns) let the epilogue of tile i overlap the mainloop of
 // tile i+1.  One descriptor (jmt_gemm_desc) covers every dense contraction of the JMT path: Linear
@@ -11,6 +11,8 @@
 // Conv1d of the TCN as an implicit GEMM (taps = extra K blocks with a shifted TMA row coordinate;
 // causal zero padding = TMA out-of-bounds fill).
 #include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -21,13 +23,14 @@ namespace jmt {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;           // 64 bf16 = 128 bytes = one swizzle row
 constexpr int kUmmaK = 16;
-constexpr int kTcThreads = 192;
+constexpr int kNumEpiWarps = 8;         // two warps per TMEM lane quarter, interleaved over column chunks
+constexpr int kTcThreads = 64 + 32 * kNumEpiWarps;
 constexpr int kAStageBytes = kBlockM * kBlockK * 2;   // 16 KiB
 constexpr int kMaxStages = 8;
 constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;       // TMEM columns per accumulator stage
 constexpr int kEpiStageBytes = 4096;      // 32 rows x 128 B per epilogue warp
-constexpr int kEpiSmemBytes = 4 * kEpiStageBytes + 4 * 1024;
+constexpr int kEpiSmemBytes = kNumEpiWarps * kEpiStageBytes + 1024;   // staging tiles + one shared bias tile
 constexpr uint32_t kSpinLimit = 1u << 24;   // ~1 s of polling, far beyond any legitimate wait
 
 struct TcParams {
@@ -47,6 +50,8 @@ struct TcParams {
   int64_t d_ld, d_bs0, d_bs1;
   float alpha, slope;
   int d_dtype, act, store_mode, vec_ok;
+  int cluster;        // 1, or 2 = CTA pairs along M sharing the B tile by TMA multicast
+  int m_pairs;        // ceil(m_tiles / cluster)
   int tma_store;      // epilogue through swizzled smem + TMA store / reduce-add (needs 16-byte aligned D geometry)
 };
 
@@ -99,6 +104,25 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+__device__ __forceinline__ void tma_load_4d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3,
+                                               uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -139,13 +163,13 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
 
 struct TileCoord { int m0, n0, batch, it0, it1; };
 
-__device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int t) {
+__device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int t, int crank) {
   TileCoord c;
   const int nt = t % p.n_tiles; t /= p.n_tiles;
-  const int mt = t % p.m_tiles; t /= p.m_tiles;
+  const int mp = t % p.m_pairs; t /= p.m_pairs;
   c.batch = t % p.batch_tiles;
   const int split = t / p.batch_tiles;
-  c.m0 = mt * kBlockM;
+  c.m0 = (mp * p.cluster + crank) * kBlockM;     // an odd tail pair gives rank 1 an all-out-of-range (ghost) tile
   c.n0 = nt * p.block_n;
   c.it0 = (int)(((int64_t)split * p.iters_total) / p.split_k);
   c.it1 = (int)(((int64_t)(split + 1) * p.iters_total) / p.split_k);
@@ -160,9 +184,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = smem_base;
   const uint32_t sB = sA + p.stages * kAStageBytes;
-  const uint32_t sD = sB + p.stages * p.b_stage_bytes;       // 4 epilogue warps x 4 KiB staging (1024-aligned)
-  const uint32_t sBias = sD + 4 * kEpiStageBytes;            // 4 x 256 floats (per-warp private copies)
-  const uint32_t bars = sBias + 4 * 1024;                    // 8-byte aligned
+  const uint32_t sD = sB + p.stages * p.b_stage_bytes;       // epilogue warps x 4 KiB staging (1024-aligned)
+  const uint32_t sBias = sD + kNumEpiWarps * kEpiStageBytes; // 256 floats: this tile's bias slice
+  const uint32_t bars = sBias + 1024;                        // 8-byte aligned
   const uint32_t full_bar = bars, empty_bar = bars + 8 * kMaxStages;
   const uint32_t tfull_bar = bars + 16 * kMaxStages, tempty_bar = tfull_bar + 16;
   const uint32_t tmem_slot = tempty_bar + 16;
@@ -170,10 +194,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_aligned + (tmem_slot - smem_base));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int crank = p.cluster == 2 ? (int)cluster_ctarank() : 0;
+  const int first_tile = blockIdx.x / p.cluster;          // tile (pair) index owned by this CTA's cluster
+  const int tile_stride = gridDim.x / p.cluster;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar + 8 * s, 1); mbar_init(tempty_bar + 8 * s, 4); }
+    for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, p.cluster); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar + 8 * s, 1); mbar_init(tempty_bar + 8 * s, kNumEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -183,6 +210,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();
+  if (p.cluster == 2) cluster_sync_all();       // peer barriers are initialised before any multicast can land
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -193,8 +221,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_b)) : "memory");
       int stage = 0; uint32_t phase = 0;
       const int b_chunks = (p.block_n + 63) / 64;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-        const TileCoord c = decode_tile(p, t);
+      for (int t = first_tile; t < p.total_tiles; t += tile_stride) {
+        const TileCoord c = decode_tile(p, t, crank);
         for (int it = c.it0; it < c.it1; ++it) {
           const int kb = it % p.kblocks;
           const int rb = (it / p.kblocks) % p.rb_n;
@@ -215,7 +243,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             tma_load_4d(a_dst, &tma_a, fb, c.m0, kb * kBlockK + ash, b0, b1);
             tma_load_4d(a_dst + 8192, &tma_a, fb, c.m0 + 64, kb * kBlockK + ash, b0, b1);
           }
-          if (p.b_major == JMT_MAJOR_K) {
+          if (p.cluster == 2) {
+            // each CTA of the pair fetches half of the shared B tile and multicasts it to both
+            if (p.b_major == JMT_MAJOR_K) {
+              const int half = p.block_n >> 1;
+              tma_load_4d_mc(b_dst + crank * half * 128, &tma_b, fb, tap * p.K + kb * kBlockK, c.n0 + crank * half, bb0, bb1, 3);
+            } else {
+              const int hc = b_chunks >> 1;
+              for (int ch = crank * hc; ch < (crank + 1) * hc; ++ch)
+                tma_load_4d_mc(b_dst + ch * 8192, &tma_b, fb, c.n0 + ch * 64, kb * kBlockK + bsh, bb0, bb1, 3);
+            }
+          } else if (p.b_major == JMT_MAJOR_K) {
             tma_load_4d(b_dst, &tma_b, fb, tap * p.K + kb * kBlockK, c.n0, bb0, bb1);
           } else {
             for (int ch = 0; ch < b_chunks; ++ch)
@@ -234,8 +272,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       const uint32_t b_lbo = p.b_major == JMT_MAJOR_K ? 16u : 8192u;
       const uint32_t a_kstep = p.a_major == JMT_MAJOR_K ? (kUmmaK * 2) >> 4 : (kUmmaK * 128) >> 4;   // desc.lo units (16 B)
       const uint32_t b_kstep = p.b_major == JMT_MAJOR_K ? (kUmmaK * 2) >> 4 : (kUmmaK * 128) >> 4;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tile_iter) {
-        const TileCoord c = decode_tile(p, t);
+      for (int t = first_tile; t < p.total_tiles; t += tile_stride, ++tile_iter) {
+        const TileCoord c = decode_tile(p, t, crank);
         const int acc = tile_iter & 1;
         const uint32_t acc_phase = (tile_iter >> 1) & 1;
         mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1);
@@ -250,32 +288,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           for (int k = 0; k < kBlockK / kUmmaK; ++k)
             tc_mma(d_tmem, a_desc + (uint64_t)(k * a_kstep), b_desc + (uint64_t)(k * b_kstep), p.idesc,
                    (it > c.it0 || k > 0) ? 1u : 0u);
-          tc_commit(empty_bar + 8 * stage);      // frees the smem slot once these MMAs retire
+          if (p.cluster == 2) tc_commit_mc(empty_bar + 8 * stage, 3);   // both CTAs' producers write this slot
+          else tc_commit(empty_bar + 8 * stage);  // frees the smem slot once these MMAs retire
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
         tc_commit(tfull_bar + 8 * acc);          // accumulator ready for the epilogue
       }
     }
   } else {
-    // ================================ epilogue (warps 2..5) ================================
+    // ================================ epilogue (warps 2..9) ================================
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
-    const uint32_t stage_smem = sD + q * kEpiStageBytes;
-    const uint32_t bias_smem = sBias + q * 1024;
-    float* bias_ptr = reinterpret_cast<float*>(smem_aligned + (bias_smem - smem_base));
+    const int ew = warp - 2;                      // epilogue warp index 0..7
+    const int half = ew >> 2;                     // which interleaved set of column chunks this warp drains
+    const uint32_t stage_smem = sD + ew * kEpiStageBytes;
+    float* bias_ptr = reinterpret_cast<float*>(smem_aligned + (sBias - smem_base));
+    const int et = threadIdx.x - 64;              // 0..255 among epilogue threads
     const uint32_t row_smem = stage_smem + lane * 128;
     const uint32_t sw = lane & 7;                 // 128B-swizzle phase of this thread's staging row
     int tile_iter = 0;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tile_iter) {
-      const TileCoord c = decode_tile(p, t);
-      const int split = (t / (p.n_tiles * p.m_tiles)) / p.batch_tiles;
+    for (int t = first_tile; t < p.total_tiles; t += tile_stride, ++tile_iter) {
+      const TileCoord c = decode_tile(p, t, crank);
+      const int split = (t / (p.n_tiles * p.m_pairs)) / p.batch_tiles;
       const int acc = tile_iter & 1;
       const uint32_t acc_phase = (tile_iter >> 1) & 1;
       const bool add_bias = p.bias != nullptr && split == 0;
-      // stage this tile's bias slice in shared memory (one private copy per warp; overlaps the mainloop)
-      __syncwarp();
-      for (int i = lane; i < p.block_n; i += 32)
-        bias_ptr[i] = (add_bias && c.n0 + i < p.N) ? __ldg(p.bias + c.n0 + i) : 0.f;
-      __syncwarp();
+      // stage this tile's bias slice in shared memory (overlaps the mainloop); named barrier 1 = epilogue warps
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * kNumEpiWarps) : "memory");     // previous tile's readers are done
+      if (et < p.block_n) bias_ptr[et] = (add_bias && c.n0 + et < p.N) ? __ldg(p.bias + c.n0 + et) : 0.f;
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * kNumEpiWarps) : "memory");
       mbar_wait(tfull_bar + 8 * acc, acc_phase);
       tc_fence_after();
       const int m = c.m0 + q * 32 + lane;
@@ -284,7 +324,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       if (p.tma_store) {
         const bool warp_rows_valid = c.m0 + q * 32 < p.M;      // warp-uniform
         if (p.d_dtype == JMT_BF16) {
-          for (int c0 = 0; c0 < p.block_n; c0 += 64) {
+          for (int c0 = half * 64; c0 < p.block_n; c0 += 128) {
             if (c.n0 + c0 >= p.N) break;
             uint32_t pk[32];
 #pragma unroll
@@ -321,7 +361,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             }
           }
         } else {
-          for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+          for (int c0 = half * 32; c0 < p.block_n; c0 += 64) {
             if (c.n0 + c0 >= p.N) break;
             uint32_t r[32];
             tc_ld32(tbase + c0, r);
@@ -350,7 +390,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       } else {
         // direct (unaligned D geometry): per-thread row stores / atomics
         const int64_t row_off = (int64_t)b0 * p.d_bs0 + (int64_t)b1 * p.d_bs1 + (int64_t)m * p.d_ld;
-        for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+        for (int c0 = half * 32; c0 < p.block_n; c0 += 64) {
           const int n = c.n0 + c0;
           if (n >= p.N) break;                      // warp-uniform
           uint32_t r[32];
@@ -382,6 +422,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
+  if (p.cluster == 2) cluster_sync_all();       // no CTA exits while its peer may still signal / multicast into it
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
@@ -485,7 +526,14 @@ extern "C" int jmt_gemm_bf16(const jmt_gemm_desc* g, void* stream) {
   p.rb_n = p.reduce_batch ? nb : 1;
   p.iters_total = g->ntaps * p.rb_n * p.kblocks;
   p.split_k = g->split_k < p.iters_total ? g->split_k : p.iters_total;
-  const int64_t total = (int64_t)p.m_tiles * p.n_tiles * p.batch_tiles * p.split_k;
+  // CTA pairs along M with B multicast when the M tiling wastes < ~10 % on the ghost tile
+  const int b_chunks_h = (p.block_n + 63) / 64;
+  const bool mc_layout_ok = g->b_major == JMT_MAJOR_K ? true : (b_chunks_h % 2 == 0);
+  const char* env_cl = getenv("JMT_GEMM_CLUSTER");
+  const bool cl_enabled = env_cl ? atoi(env_cl) != 0 : true;
+  p.cluster = (cl_enabled && mc_layout_ok && p.m_tiles >= 2 && (p.m_tiles % 2 == 0 || p.m_tiles >= 9)) ? 2 : 1;
+  p.m_pairs = (p.m_tiles + p.cluster - 1) / p.cluster;
+  const int64_t total = (int64_t)p.m_pairs * p.n_tiles * p.batch_tiles * p.split_k;
   JMT_REQUIRE(total < (1ll << 31), "jmt_gemm_bf16: too many tiles");
   p.total_tiles = (int)total;
   p.nb0 = g->nb0;
@@ -520,7 +568,8 @@ extern "C" int jmt_gemm_bf16(const jmt_gemm_desc* g, void* stream) {
   if (rc != JMT_OK) return rc;
   const int bnb0 = p.b_has_b0 ? g->nb0 : 1, bnb1 = p.b_has_b1 ? g->nb1 : 1;
   if (g->b_major == JMT_MAJOR_K)
-    rc = make_map(&map_b, g->b, (int64_t)g->ntaps * g->K, g->b_rows, g->b_ld, bnb0, g->b_bs0, bnb1, g->b_bs1, p.block_n, "jmt_gemm_bf16(B)");
+    rc = make_map(&map_b, g->b, (int64_t)g->ntaps * g->K, g->b_rows, g->b_ld, bnb0, g->b_bs0, bnb1, g->b_bs1,
+                  p.block_n / p.cluster /* each CTA of a pair fetches (and multicasts) half of the tile's rows */, "jmt_gemm_bf16(B)");
   else
     rc = make_map(&map_b, g->b, g->N, g->b_rows, g->b_ld, bnb0, g->b_bs0, bnb1, g->b_bs1, kBlockK, "jmt_gemm_bf16(B)");
   if (rc != JMT_OK) return rc;
@@ -543,7 +592,26 @@ extern "C" int jmt_gemm_bf16(const jmt_gemm_desc* g, void* stream) {
     if (e != cudaSuccess) { set_error("jmt_gemm_bf16: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); cudaGetLastError(); return JMT_ERR_CUDA; }
     attr_set[dev & 63].store(1, std::memory_order_release);
   }
-  const int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
-  gemm_tc_kernel<<<grid, kTcThreads, smem, (cudaStream_t)stream>>>(map_a, map_b, map_d, p);
+  const int max_groups = kNumSMs / p.cluster;
+  const int groups = p.total_tiles < max_groups ? p.total_tiles : max_groups;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(groups * p.cluster);
+  cfg.blockDim = dim3(kTcThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = p.cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tc_kernel, map_a, map_b, map_d, p);
+  if (le != cudaSuccess) {
+    set_error("jmt_gemm_bf16: cudaLaunchKernelEx: %s", cudaGetErrorString(le));
+    cudaGetLastError();
+    return JMT_ERR_CUDA;
+  }
   return check_launch("gemm_tc_kernel");
 }

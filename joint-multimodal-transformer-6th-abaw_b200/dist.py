@@ -26,7 +26,9 @@ def init_from_env(backend: Optional[str] = None) -> int:
         backend = "nccl" if torch.cuda.is_available() else "gloo"
     if backend == "nccl":
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
-    dist.init_process_group(backend=backend)
+    import datetime
+    # short watchdog: a mismatched collective must fail in minutes, not hang a GPU box
+    dist.init_process_group(backend=backend, timeout=datetime.timedelta(seconds=int(os.environ.get("JMT_DIST_TIMEOUT_S", "180"))))
     return dist.get_rank()
 
 
