@@ -103,6 +103,9 @@ typedef struct {
 
 int jmt_gemm_bf16(const jmt_gemm_desc* g, void* stream);
 int jmt_gemm_f32(const jmt_gemm_desc* g, void* stream);
+/* Debug aid (no reference counterpart): when dev_buf != NULL (device buffer of 148*16 uint64) every later
+ * jmt_gemm_bf16 launch overwrites per-CTA cycle counters of its TMA / MMA / epilogue roles; NULL disables. */
+int jmt_gemm_set_profile_buffer(void* dev_buf);
 
 /* ------------------------------------------------------------------------------------------ *
  * Memory-bound fused row kernels (one warp per row, warp-shuffle reductions, 16-byte accesses).

@@ -44,6 +44,7 @@ SIGNATURES = {
     "jmt_launch_count": [],
     "jmt_gemm_bf16": [C.POINTER(GemmDesc), _P],
     "jmt_gemm_f32": [C.POINTER(GemmDesc), _P],
+    "jmt_gemm_set_profile_buffer": [_P],
     "jmt_l2norm_fwd": [_P, _I, _L, _P, _I, _L, _I, _F, _P, _P],
     "jmt_l2norm_bwd": [_P, _P, _I, _P, _F, _P, _L, _I, _P],
     "jmt_add_layernorm_fwd": [_P, _P, _P, _P, _F, _P, _P, _P, _L, _I, _I, _P],

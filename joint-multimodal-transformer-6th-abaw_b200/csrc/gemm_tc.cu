@@ -1,7 +1,7 @@
 // jmt_gemm_bf16: persistent, warp-specialised tcgen05 GEMM for sm_100a.
 //
 //   warp 0 (1 elected thread) : TMA producer   -- cp.async.bulk.tensor.4d -> 128B-swizzled smem ring
-//   warp 1 (1 elected thread) : MMA issuer     -- tcgen05.mma.cta_group::1.kind::f16, fp32 accum in TMEM
+//   warp 1 (1 elected thread) : MMA issuer     -- tcgen05.mma.cta_group::{1,2}.kind::f16, fp32 accum in TMEM
 //   warps 2..9                : epilogue       -- tcgen05.ld 32x32b -> alpha/bias/activation -> global
 //
 // Two TMEM accumulator stages (2 x 256 columns) let the epilogue of tile i overlap the mainloop of
@@ -10,6 +10,12 @@
 // K- or MN-major operands selected in the UMMA instruction descriptor) and the dilated causal
 // Conv1d of the TCN as an implicit GEMM (taps = extra K blocks with a shifted TMA row coordinate;
 // causal zero padding = TMA out-of-bounds fill).
+//
+// kCta == 2 (template): CTA pairs (cluster of 2) run one tcgen05.mma.cta_group::2 with M = 256: each CTA
+// owns 128 accumulator rows (its own A tile, possibly from another batch element when B is shared across
+// the batch) and stages only HALF of the B tile -- the pair's tensor cores read both halves.  That cuts
+// the L2->SMEM operand traffic per FLOP by a third (48 KB -> 32 KB per 128x256x64 block), which is the
+// measured limit of the 1-CTA kernel (LTS ~12 TB/s => 1.05 PFLOP/s).
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
@@ -33,25 +39,49 @@ constexpr int kEpiStageBytes = 4096;      // 32 rows x 128 B per epilogue warp
 constexpr int kEpiSmemBytes = kNumEpiWarps * kEpiStageBytes + 1024;   // staging tiles + one shared bias tile
 constexpr uint32_t kSpinLimit = 1u << 24;   // ~1 s of polling, far beyond any legitimate wait
 
+// Division by a runtime constant without the ~150-cycle integer-divide sequence: the single-thread TMA / MMA roles
+// decode tile coordinates on their critical path.  q = (n * mul) >> 32 >> shr is exact for 0 <= n < 2^31, d >= 1.
+struct FastDiv {
+  uint32_t mul, shr, d;
+  __host__ void init(uint32_t div) {
+    d = div;
+    if (div == 1) { mul = 0; shr = 0; return; }
+    uint32_t l = 0;
+    while ((1ull << l) < div) ++l;                       // ceil(log2(div))
+    mul = (uint32_t)((((1ull << l) - div) << 32) / div + 1);
+    shr = l - 1;
+  }
+  __device__ __forceinline__ uint32_t div(uint32_t n) const {
+    if (d == 1) return n;
+    const uint32_t hi = __umulhi(n, mul);
+    return (hi + ((n - hi) >> 1)) >> shr;
+  }
+  __device__ __forceinline__ void divmod(uint32_t n, uint32_t& q, uint32_t& r) const { q = div(n); r = n - q * d; }
+};
+
 struct TcParams {
   int M, N, K, block_n;
   int m_tiles, n_tiles, batch_tiles, split_k, total_tiles;
   int kblocks, rb_n, iters_total;
   int nb0;
+  FastDiv fd_ntiles, fd_mpairs, fd_bslots, fd_nb0, fd_kblocks, fd_rbn;
   int a_major, b_major;
   int a_shift0, a_shift_step, b_shift0, b_shift_step;
   int b_has_b0, b_has_b1;
   int reduce_batch;
   uint32_t idesc;
-  int b_stage_bytes, b_tx_bytes, stages;
+  int b_stage_bytes, b_tx_bytes, b_chunks_cta, stages;
   // epilogue
   void* d;
   const float* bias;
   int64_t d_ld, d_bs0, d_bs1;
   float alpha, slope;
   int d_dtype, act, store_mode, vec_ok;
-  int cluster;        // 1, or 2 = CTA pairs along M sharing the B tile by TMA multicast
-  int m_pairs;        // ceil(m_tiles / cluster)
+  int cluster;        // 1, or 2 = CTA pairs issuing cta_group::2 MMAs (each CTA stages half of the B tile)
+  int pair_batch;     // cluster 2 only: 0 = the pair covers two consecutive M tiles, 1 = two consecutive batch entries
+  int m_pairs;        // number of M tile slots per (n, batch): ceil(m_tiles / 2) when pairing along M, else m_tiles
+  int batch_slots;    // batch_tiles, or batch_tiles / 2 when pairing along the batch
+  unsigned long long* prof;   // optional per-CTA cycle counters (16 per CTA), see jmt_gemm_set_profile_buffer
   int tma_store;      // epilogue through swizzled smem + TMA store / reduce-add (needs 16-byte aligned D geometry)
 };
 
@@ -104,15 +134,23 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
 }
-__device__ __forceinline__ void tma_load_4d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3,
-                                               uint16_t mask) {
+// cta_group::2 load: data lands in this CTA's smem, complete_tx is signalled on the LEADER CTA's mbarrier
+__device__ __forceinline__ void tma_load_4d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1, int c2, int c3) {
   asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(mask) : "memory");
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
-__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(bar), "h"(mask) : "memory");
+// shared::cluster address of `addr` (a shared::cta address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_expect_tx_cluster(uint32_t cluster_bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -125,17 +163,36 @@ __device__ __forceinline__ void cluster_sync_all() {
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// tcgen05.commit: arrives on `bar` once all prior MMAs of this thread retire.  kCta == 2: the arrive is
+// multicast to the same barrier offset in both CTAs of the pair.
+template <int kCta>
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+  if constexpr (kCta == 1) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+  } else {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
+  }
 }
+template <int kCta>
 __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+  if constexpr (kCta == 1) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+  }
 }
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+// 32 lanes x 32 columns of fp32 accumulators -> 32 registers per thread (thread = TMEM lane = output row).
+// Issue only; tc_wait_ld() must precede the first use of r[] (several loads can be in flight).
+__device__ __forceinline__ void tc_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -145,7 +202,41 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
         "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr) : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) { tc_ld32_issue(taddr, r); tc_wait_ld(); }
+
+template <int ACT>
+__device__ __forceinline__ float act_t(float x, float slope) {
+  if constexpr (ACT == JMT_ACT_RELU) return fmaxf(x, 0.f);
+  else if constexpr (ACT == JMT_ACT_LEAKY_RELU) return x >= 0.f ? x : x * slope;
+  else return x;
+}
+// 32 accumulator columns -> act(alpha * acc + bias), branch-free (the activation is a template parameter so the
+// compiler can interleave the 32 independent FFMA / FMNMX / F2FP chains)
+template <int ACT>
+__device__ __forceinline__ void epi_math_bf16(const uint32_t (&r)[32], const float* bias, float alpha, float slope, uint32_t* pk) {
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    const float4 bv = *reinterpret_cast<const float4*>(bias + j);
+    const float x0 = act_t<ACT>(fmaf(alpha, __uint_as_float(r[j]), bv.x), slope);
+    const float x1 = act_t<ACT>(fmaf(alpha, __uint_as_float(r[j + 1]), bv.y), slope);
+    const float x2 = act_t<ACT>(fmaf(alpha, __uint_as_float(r[j + 2]), bv.z), slope);
+    const float x3 = act_t<ACT>(fmaf(alpha, __uint_as_float(r[j + 3]), bv.w), slope);
+    pk[j / 2] = pack_bf16(x0, x1);
+    pk[j / 2 + 1] = pack_bf16(x2, x3);
+  }
+}
+template <int ACT>
+__device__ __forceinline__ void epi_math_f32(uint32_t (&r)[32], const float* bias, float alpha, float slope) {
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    const float4 bv = *reinterpret_cast<const float4*>(bias + j);
+    r[j] = __float_as_uint(act_t<ACT>(fmaf(alpha, __uint_as_float(r[j]), bv.x), slope));
+    r[j + 1] = __float_as_uint(act_t<ACT>(fmaf(alpha, __uint_as_float(r[j + 1]), bv.y), slope));
+    r[j + 2] = __float_as_uint(act_t<ACT>(fmaf(alpha, __uint_as_float(r[j + 2]), bv.z), slope));
+    r[j + 3] = __float_as_uint(act_t<ACT>(fmaf(alpha, __uint_as_float(r[j + 3]), bv.w), slope));
+  }
 }
 
 // UMMA shared-memory matrix descriptor, 128-byte swizzle, Blackwell version bits.
@@ -161,26 +252,131 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
   return d;
 }
 
-struct TileCoord { int m0, n0, batch, it0, it1; };
+struct TileCoord { int m0, n0, batch, split, it0, it1; };
 
 __device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int t, int crank) {
   TileCoord c;
-  const int nt = t % p.n_tiles; t /= p.n_tiles;
-  const int mp = t % p.m_pairs; t /= p.m_pairs;
-  c.batch = t % p.batch_tiles;
-  const int split = t / p.batch_tiles;
-  c.m0 = (mp * p.cluster + crank) * kBlockM;     // an odd tail pair gives rank 1 an all-out-of-range (ghost) tile
-  c.n0 = nt * p.block_n;
-  c.it0 = (int)(((int64_t)split * p.iters_total) / p.split_k);
-  c.it1 = (int)(((int64_t)(split + 1) * p.iters_total) / p.split_k);
+  uint32_t q, nt, mp, bs;
+  p.fd_ntiles.divmod((uint32_t)t, q, nt);
+  p.fd_mpairs.divmod(q, q, mp);
+  uint32_t split;
+  p.fd_bslots.divmod(q, split, bs);
+  c.split = (int)split;
+  if (p.pair_batch) {          // the two CTAs of a pair work on consecutive batch entries (B is not batched)
+    c.m0 = (int)mp * kBlockM;
+    c.batch = (int)bs * 2 + crank;
+  } else {                     // consecutive M tiles; an odd tail pair gives rank 1 an all-out-of-range (ghost) tile
+    c.m0 = ((int)mp * p.cluster + crank) * kBlockM;
+    c.batch = (int)bs;
+  }
+  c.n0 = (int)nt * p.block_n;
+  if (p.split_k == 1) { c.it0 = 0; c.it1 = p.iters_total; }
+  else {
+    c.it0 = (int)(((int64_t)c.split * p.iters_total) / p.split_k);
+    c.it1 = (int)(((int64_t)(c.split + 1) * p.iters_total) / p.split_k);
+  }
   return c;
 }
 
+struct EpiCtx {
+  uint32_t tbase, stage_smem, row_smem, sw;
+  const float* bias;          // this tile's bias slice in shared memory (zeros when there is none)
+  int m0w, n0, b0, b1, half, lane;
+};
+
+// One epilogue warp's share of a 128 x block_n accumulator tile: its 32 TMEM lanes (rows) x every other
+// 64-column (bf16 out) / 32-column (fp32 out) chunk -> alpha / bias / activation -> 128B-swizzled staging tile ->
+// TMA store or reduce-add; or per-thread stores when D's geometry is not 16-byte aligned.
+template <int ACT>
+__device__ __forceinline__ void epi_tile(const TcParams& p, const CUtensorMap* tma_d, const EpiCtx& e) {
+  const int lane = e.lane;
+  if (p.tma_store) {
+    const bool warp_rows_valid = e.m0w < p.M;      // warp-uniform
+    if (p.d_dtype == JMT_BF16) {
+      for (int c0 = e.half * 64; c0 < p.block_n; c0 += 128) {
+        if (e.n0 + c0 >= p.N) break;
+        uint32_t pk[32];
+        const bool second = c0 + 32 < p.block_n;      // block_n is a multiple of 32
+        {
+          uint32_t r0[32], r1[32];
+          tc_ld32_issue(e.tbase + c0, r0);
+          if (second) tc_ld32_issue(e.tbase + c0 + 32, r1);
+          tc_wait_ld();
+          epi_math_bf16<ACT>(r0, e.bias + c0, p.alpha, p.slope, pk);
+          if (second) epi_math_bf16<ACT>(r1, e.bias + c0 + 32, p.alpha, p.slope, pk + 16);
+          else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) pk[16 + j] = 0u;
+          }
+        }
+        if (lane == 0) bulk_wait_read0();       // previous TMA store has finished reading the staging tile
+        __syncwarp();
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch)
+          st_shared_v4(e.row_smem + ((ch ^ e.sw) << 4), pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0 && warp_rows_valid) {
+          if (p.store_mode == JMT_STORE) tma_store_4d(tma_d, e.stage_smem, e.n0 + c0, e.m0w, e.b0, e.b1);
+          else tma_reduce_add_4d(tma_d, e.stage_smem, e.n0 + c0, e.m0w, e.b0, e.b1);
+          bulk_commit();
+        }
+      }
+    } else {
+      for (int c0 = e.half * 32; c0 < p.block_n; c0 += 64) {
+        if (e.n0 + c0 >= p.N) break;
+        uint32_t r[32];
+        tc_ld32(e.tbase + c0, r);
+        epi_math_f32<ACT>(r, e.bias + c0, p.alpha, p.slope);
+        if (lane == 0) bulk_wait_read0();
+        __syncwarp();
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch)
+          st_shared_v4(e.row_smem + ((ch ^ e.sw) << 4), r[4 * ch], r[4 * ch + 1], r[4 * ch + 2], r[4 * ch + 3]);
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0 && warp_rows_valid) {
+          if (p.store_mode == JMT_STORE) tma_store_4d(tma_d, e.stage_smem, e.n0 + c0, e.m0w, e.b0, e.b1);
+          else tma_reduce_add_4d(tma_d, e.stage_smem, e.n0 + c0, e.m0w, e.b0, e.b1);
+          bulk_commit();
+        }
+      }
+    }
+  } else {
+    // direct (unaligned D geometry): per-thread row stores / atomics
+    const int m = e.m0w + lane;
+    const int64_t row_off = (int64_t)e.b0 * p.d_bs0 + (int64_t)e.b1 * p.d_bs1 + (int64_t)m * p.d_ld;
+    for (int c0 = e.half * 32; c0 < p.block_n; c0 += 64) {
+      const int n = e.n0 + c0;
+      if (n >= p.N) break;                      // warp-uniform
+      uint32_t r[32];
+      tc_ld32(e.tbase + c0, r);
+      if (m >= p.M) continue;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (n + j >= p.N) break;
+        const float v = act_t<ACT>(fmaf(p.alpha, __uint_as_float(r[j]), e.bias[c0 + j]), p.slope);
+        const int64_t idx = row_off + n + j;
+        if (p.d_dtype == JMT_F32) {
+          float* d = (float*)p.d;
+          if (p.store_mode == JMT_STORE) d[idx] = v;
+          else if (p.store_mode == JMT_ACCUMULATE) d[idx] += v;
+          else atomicAdd(d + idx, v);
+        } else {
+          __nv_bfloat16* d = (__nv_bfloat16*)p.d;
+          d[idx] = __float2bfloat16_rn(p.store_mode == JMT_STORE ? v : __bfloat162float(d[idx]) + v);
+        }
+      }
+    }
+  }
+}
+
+template <int kCta>
 __global__ void __launch_bounds__(kTcThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                const __grid_constant__ CUtensorMap tma_d, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // 1024-byte aligned carve-up (SWIZZLE_128B atoms are 1024 B)
+  // 1024-byte aligned carve-up (SWIZZLE_128B atoms are 1024 B); identical offsets in both CTAs of a pair
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = smem_base;
   const uint32_t sB = sA + p.stages * kAStageBytes;
@@ -194,80 +390,109 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_aligned + (tmem_slot - smem_base));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int crank = p.cluster == 2 ? (int)cluster_ctarank() : 0;
-  const int first_tile = blockIdx.x / p.cluster;          // tile (pair) index owned by this CTA's cluster
-  const int tile_stride = gridDim.x / p.cluster;
+  const int crank = kCta == 2 ? (int)cluster_ctarank() : 0;
+  const int first_tile = blockIdx.x / kCta;          // tile (pair) index owned by this CTA's cluster
+  const int tile_stride = gridDim.x / kCta;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, p.cluster); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar + 8 * s, 1); mbar_init(tempty_bar + 8 * s, kNumEpiWarps); }
+    // full: one arrive(+expect_tx) per CTA of the pair (on the leader's barrier); empty / tfull: one tcgen05.commit
+    // (multicast to both CTAs); tempty: every epilogue warp of every CTA of the pair (on the leader's barrier)
+    for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar + 8 * s, kCta); mbar_init(empty_bar + 8 * s, 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar + 8 * s, 1); mbar_init(tempty_bar + 8 * s, kNumEpiWarps * kCta); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kTmemCols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (kCta == 1) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kTmemCols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kTmemCols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
-  if (p.cluster == 2) cluster_sync_all();       // peer barriers are initialised before any multicast can land
+  if constexpr (kCta == 2) cluster_sync_all();   // peer barriers are initialised before any remote arrive / complete_tx
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp == 0) {
     if (lane == 0) {
-      // ================================ TMA producer ================================
+      // ================================ TMA producer (every CTA) ================================
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_a)) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_b)) : "memory");
       int stage = 0; uint32_t phase = 0;
-      const int b_chunks = (p.block_n + 63) / 64;
+      long long pr_wait = 0; const long long pr_t0 = p.prof ? clock64() : 0;
+      const int b_chunks = p.b_chunks_cta;                    // 64-wide MN chunks staged by this CTA
+      const int n_off = crank * (p.block_n / kCta);           // this CTA's half of the B tile (kCta == 2)
+      const uint32_t full_leader = kCta == 2 ? mapa_rank(full_bar, 0) : full_bar;
       for (int t = first_tile; t < p.total_tiles; t += tile_stride) {
         const TileCoord c = decode_tile(p, t, crank);
+        // (tap, rb, kb) of the first iteration; afterwards the counters advance incrementally (no divisions in the loop)
+        uint32_t q0, kb_u, tap_u, rb_u;
+        p.fd_kblocks.divmod((uint32_t)c.it0, q0, kb_u);
+        p.fd_rbn.divmod(q0, tap_u, rb_u);
+        int kb = (int)kb_u, rb = (int)rb_u, tap = (int)tap_u;
+        uint32_t b1_u, b0_u;
+        p.fd_nb0.divmod((uint32_t)(p.reduce_batch ? rb : c.batch), b1_u, b0_u);
+        int b0 = (int)b0_u, b1 = (int)b1_u;
         for (int it = c.it0; it < c.it1; ++it) {
-          const int kb = it % p.kblocks;
-          const int rb = (it / p.kblocks) % p.rb_n;
-          const int tap = it / (p.kblocks * p.rb_n);
-          const int bidx = p.reduce_batch ? rb : c.batch;
-          const int b0 = bidx % p.nb0, b1 = bidx / p.nb0;
           const int bb0 = p.b_has_b0 ? b0 : 0, bb1 = p.b_has_b1 ? b1 : 0;
           const int ash = p.a_shift0 + tap * p.a_shift_step;
           const int bsh = p.b_shift0 + tap * p.b_shift_step;
+          const long long tw = p.prof ? clock64() : 0;
           mbar_wait(empty_bar + 8 * stage, phase ^ 1);
-          const uint32_t fb = full_bar + 8 * stage;
-          mbar_expect_tx(fb, kAStageBytes + p.b_tx_bytes);
+          if (p.prof) pr_wait += clock64() - tw;
           const uint32_t a_dst = sA + stage * kAStageBytes;
           const uint32_t b_dst = sB + stage * p.b_stage_bytes;
-          if (p.a_major == JMT_MAJOR_K) {
-            tma_load_4d(a_dst, &tma_a, fb, kb * kBlockK, c.m0 + ash, b0, b1);
-          } else {
-            tma_load_4d(a_dst, &tma_a, fb, c.m0, kb * kBlockK + ash, b0, b1);
-            tma_load_4d(a_dst + 8192, &tma_a, fb, c.m0 + 64, kb * kBlockK + ash, b0, b1);
-          }
-          if (p.cluster == 2) {
-            // each CTA of the pair fetches half of the shared B tile and multicasts it to both
-            if (p.b_major == JMT_MAJOR_K) {
-              const int half = p.block_n >> 1;
-              tma_load_4d_mc(b_dst + crank * half * 128, &tma_b, fb, tap * p.K + kb * kBlockK, c.n0 + crank * half, bb0, bb1, 3);
+          if constexpr (kCta == 1) {
+            const uint32_t fb = full_bar + 8 * stage;
+            mbar_expect_tx(fb, kAStageBytes + p.b_tx_bytes);
+            if (p.a_major == JMT_MAJOR_K) {
+              tma_load_4d(a_dst, &tma_a, fb, kb * kBlockK, c.m0 + ash, b0, b1);
             } else {
-              const int hc = b_chunks >> 1;
-              for (int ch = crank * hc; ch < (crank + 1) * hc; ++ch)
-                tma_load_4d_mc(b_dst + ch * 8192, &tma_b, fb, c.n0 + ch * 64, kb * kBlockK + bsh, bb0, bb1, 3);
+              tma_load_4d(a_dst, &tma_a, fb, c.m0, kb * kBlockK + ash, b0, b1);
+              tma_load_4d(a_dst + 8192, &tma_a, fb, c.m0 + 64, kb * kBlockK + ash, b0, b1);
             }
-          } else if (p.b_major == JMT_MAJOR_K) {
-            tma_load_4d(b_dst, &tma_b, fb, tap * p.K + kb * kBlockK, c.n0, bb0, bb1);
+            if (p.b_major == JMT_MAJOR_K) {
+              tma_load_4d(b_dst, &tma_b, fb, tap * p.K + kb * kBlockK, c.n0, bb0, bb1);
+            } else {
+              for (int ch = 0; ch < b_chunks; ++ch)
+                tma_load_4d(b_dst + ch * 8192, &tma_b, fb, c.n0 + ch * 64, kb * kBlockK + bsh, bb0, bb1);
+            }
           } else {
-            for (int ch = 0; ch < b_chunks; ++ch)
-              tma_load_4d(b_dst + ch * 8192, &tma_b, fb, c.n0 + ch * 64, kb * kBlockK + bsh, bb0, bb1);
+            const uint32_t fb = full_leader + 8 * stage;
+            mbar_expect_tx_cluster(fb, kAStageBytes + p.b_tx_bytes);
+            if (p.a_major == JMT_MAJOR_K) {
+              tma_load_4d_2sm(a_dst, &tma_a, fb, kb * kBlockK, c.m0 + ash, b0, b1);
+            } else {
+              tma_load_4d_2sm(a_dst, &tma_a, fb, c.m0, kb * kBlockK + ash, b0, b1);
+              tma_load_4d_2sm(a_dst + 8192, &tma_a, fb, c.m0 + 64, kb * kBlockK + ash, b0, b1);
+            }
+            if (p.b_major == JMT_MAJOR_K) {
+              tma_load_4d_2sm(b_dst, &tma_b, fb, tap * p.K + kb * kBlockK, c.n0 + n_off, bb0, bb1);
+            } else {
+              for (int ch = 0; ch < b_chunks; ++ch)
+                tma_load_4d_2sm(b_dst + ch * 8192, &tma_b, fb, c.n0 + n_off + ch * 64, kb * kBlockK + bsh, bb0, bb1);
+            }
           }
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          if (++kb == p.kblocks) {
+            kb = 0;
+            if (++rb == p.rb_n) { rb = 0; ++tap; }
+            if (p.reduce_batch) { if (++b0 == p.nb0) { b0 = 0; ++b1; } if (rb == 0) { b0 = 0; b1 = 0; } }
+          }
         }
       }
+      if (p.prof) { p.prof[blockIdx.x * 16 + 3] = pr_wait; p.prof[blockIdx.x * 16 + 4] = clock64() - pr_t0; }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ================================ MMA issuer ================================
+    if (lane == 0 && crank == 0) {
+      // ================================ MMA issuer (leader CTA of a pair) ================================
       int stage = 0; uint32_t phase = 0;
       int tile_iter = 0;
+      long long mw_full = 0, mw_tempty = 0; const long long mw_t0 = p.prof ? clock64() : 0;
       const uint32_t a_lbo = p.a_major == JMT_MAJOR_K ? 16u : 8192u;
       const uint32_t b_lbo = p.b_major == JMT_MAJOR_K ? 16u : 8192u;
       const uint32_t a_kstep = p.a_major == JMT_MAJOR_K ? (kUmmaK * 2) >> 4 : (kUmmaK * 128) >> 4;   // desc.lo units (16 B)
@@ -276,24 +501,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         const TileCoord c = decode_tile(p, t, crank);
         const int acc = tile_iter & 1;
         const uint32_t acc_phase = (tile_iter >> 1) & 1;
+        const long long tw0 = p.prof ? clock64() : 0;
         mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1);
+        if (p.prof) mw_tempty += clock64() - tw0;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * kAccStride;
         for (int it = c.it0; it < c.it1; ++it) {
+          const long long tw1 = p.prof ? clock64() : 0;
           mbar_wait(full_bar + 8 * stage, phase);
+          if (p.prof) mw_full += clock64() - tw1;
           tc_fence_after();
           const uint64_t a_desc = make_smem_desc(sA + stage * kAStageBytes, a_lbo, 1024);
           const uint64_t b_desc = make_smem_desc(sB + stage * p.b_stage_bytes, b_lbo, 1024);
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; ++k)
-            tc_mma(d_tmem, a_desc + (uint64_t)(k * a_kstep), b_desc + (uint64_t)(k * b_kstep), p.idesc,
-                   (it > c.it0 || k > 0) ? 1u : 0u);
-          if (p.cluster == 2) tc_commit_mc(empty_bar + 8 * stage, 3);   // both CTAs' producers write this slot
-          else tc_commit(empty_bar + 8 * stage);  // frees the smem slot once these MMAs retire
+            tc_mma<kCta>(d_tmem, a_desc + (uint64_t)(k * a_kstep), b_desc + (uint64_t)(k * b_kstep), p.idesc,
+                         (it > c.it0 || k > 0) ? 1u : 0u);
+          tc_commit<kCta>(empty_bar + 8 * stage);  // frees the smem slot (in both CTAs) once these MMAs retire
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
-        tc_commit(tfull_bar + 8 * acc);          // accumulator ready for the epilogue
+        tc_commit<kCta>(tfull_bar + 8 * acc);      // accumulator ready for the epilogue warps (of both CTAs)
       }
+      if (p.prof) { p.prof[blockIdx.x * 16 + 0] = mw_full; p.prof[blockIdx.x * 16 + 1] = mw_tempty; p.prof[blockIdx.x * 16 + 2] = clock64() - mw_t0; }
     }
   } else {
     // ================================ epilogue (warps 2..9) ================================
@@ -305,127 +534,62 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     const int et = threadIdx.x - 64;              // 0..255 among epilogue threads
     const uint32_t row_smem = stage_smem + lane * 128;
     const uint32_t sw = lane & 7;                 // 128B-swizzle phase of this thread's staging row
+    const uint32_t tempty_leader = kCta == 2 ? mapa_rank(tempty_bar, 0) : tempty_bar;
+    long long ep_tfull = 0, ep_bar = 0, ep_rd = 0; const long long ep_t0 = p.prof ? clock64() : 0;
+    if (p.bias == nullptr) {                      // no bias: one zero fill for the whole kernel
+      bias_ptr[et] = 0.f;
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * kNumEpiWarps) : "memory");
+    }
     int tile_iter = 0;
     for (int t = first_tile; t < p.total_tiles; t += tile_stride, ++tile_iter) {
       const TileCoord c = decode_tile(p, t, crank);
-      const int split = (t / (p.n_tiles * p.m_pairs)) / p.batch_tiles;
+      const int split = c.split;
       const int acc = tile_iter & 1;
       const uint32_t acc_phase = (tile_iter >> 1) & 1;
-      const bool add_bias = p.bias != nullptr && split == 0;
       // stage this tile's bias slice in shared memory (overlaps the mainloop); named barrier 1 = epilogue warps
-      asm volatile("bar.sync 1, %0;" ::"n"(32 * kNumEpiWarps) : "memory");     // previous tile's readers are done
-      if (et < p.block_n) bias_ptr[et] = (add_bias && c.n0 + et < p.N) ? __ldg(p.bias + c.n0 + et) : 0.f;
-      asm volatile("bar.sync 1, %0;" ::"n"(32 * kNumEpiWarps) : "memory");
-      mbar_wait(tfull_bar + 8 * acc, acc_phase);
-      tc_fence_after();
-      const int m = c.m0 + q * 32 + lane;
-      const int b0 = c.batch % p.nb0, b1 = c.batch / p.nb0;
-      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kAccStride);
-      if (p.tma_store) {
-        const bool warp_rows_valid = c.m0 + q * 32 < p.M;      // warp-uniform
-        if (p.d_dtype == JMT_BF16) {
-          for (int c0 = half * 64; c0 < p.block_n; c0 += 128) {
-            if (c.n0 + c0 >= p.N) break;
-            uint32_t pk[32];
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              if (c0 + 32 * h < p.block_n) {
-                uint32_t r[32];
-                tc_ld32(tbase + c0 + 32 * h, r);
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                  const float4 bv = *reinterpret_cast<const float4*>(bias_ptr + c0 + 32 * h + j);
-                  const float x0 = apply_act(fmaf(p.alpha, __uint_as_float(r[j]), bv.x), p.act, p.slope);
-                  const float x1 = apply_act(fmaf(p.alpha, __uint_as_float(r[j + 1]), bv.y), p.act, p.slope);
-                  const float x2 = apply_act(fmaf(p.alpha, __uint_as_float(r[j + 2]), bv.z), p.act, p.slope);
-                  const float x3 = apply_act(fmaf(p.alpha, __uint_as_float(r[j + 3]), bv.w), p.act, p.slope);
-                  pk[16 * h + j / 2] = pack_bf16(x0, x1);
-                  pk[16 * h + j / 2 + 1] = pack_bf16(x2, x3);
-                }
-              } else {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) pk[16 * h + j] = 0u;
-              }
-            }
-            if (lane == 0) bulk_wait_read0();       // previous TMA store has finished reading the staging tile
-            __syncwarp();
-#pragma unroll
-            for (int ch = 0; ch < 8; ++ch)
-              st_shared_v4(row_smem + ((ch ^ sw) << 4), pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
-            fence_async_smem();
-            __syncwarp();
-            if (lane == 0 && warp_rows_valid) {
-              if (p.store_mode == JMT_STORE) tma_store_4d(&tma_d, stage_smem, c.n0 + c0, c.m0 + q * 32, b0, b1);
-              else tma_reduce_add_4d(&tma_d, stage_smem, c.n0 + c0, c.m0 + q * 32, b0, b1);
-              bulk_commit();
-            }
-          }
-        } else {
-          for (int c0 = half * 32; c0 < p.block_n; c0 += 64) {
-            if (c.n0 + c0 >= p.N) break;
-            uint32_t r[32];
-            tc_ld32(tbase + c0, r);
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 bv = *reinterpret_cast<const float4*>(bias_ptr + c0 + j);
-              r[j] = __float_as_uint(apply_act(fmaf(p.alpha, __uint_as_float(r[j]), bv.x), p.act, p.slope));
-              r[j + 1] = __float_as_uint(apply_act(fmaf(p.alpha, __uint_as_float(r[j + 1]), bv.y), p.act, p.slope));
-              r[j + 2] = __float_as_uint(apply_act(fmaf(p.alpha, __uint_as_float(r[j + 2]), bv.z), p.act, p.slope));
-              r[j + 3] = __float_as_uint(apply_act(fmaf(p.alpha, __uint_as_float(r[j + 3]), bv.w), p.act, p.slope));
-            }
-            if (lane == 0) bulk_wait_read0();
-            __syncwarp();
-#pragma unroll
-            for (int ch = 0; ch < 8; ++ch)
-              st_shared_v4(row_smem + ((ch ^ sw) << 4), r[4 * ch], r[4 * ch + 1], r[4 * ch + 2], r[4 * ch + 3]);
-            fence_async_smem();
-            __syncwarp();
-            if (lane == 0 && warp_rows_valid) {
-              if (p.store_mode == JMT_STORE) tma_store_4d(&tma_d, stage_smem, c.n0 + c0, c.m0 + q * 32, b0, b1);
-              else tma_reduce_add_4d(&tma_d, stage_smem, c.n0 + c0, c.m0 + q * 32, b0, b1);
-              bulk_commit();
-            }
-          }
-        }
-      } else {
-        // direct (unaligned D geometry): per-thread row stores / atomics
-        const int64_t row_off = (int64_t)b0 * p.d_bs0 + (int64_t)b1 * p.d_bs1 + (int64_t)m * p.d_ld;
-        for (int c0 = half * 32; c0 < p.block_n; c0 += 64) {
-          const int n = c.n0 + c0;
-          if (n >= p.N) break;                      // warp-uniform
-          uint32_t r[32];
-          tc_ld32(tbase + c0, r);
-          if (m >= p.M) continue;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (n + j >= p.N) break;
-            const float v = apply_act(fmaf(p.alpha, __uint_as_float(r[j]), bias_ptr[c0 + j]), p.act, p.slope);
-            const int64_t idx = row_off + n + j;
-            if (p.d_dtype == JMT_F32) {
-              float* d = (float*)p.d;
-              if (p.store_mode == JMT_STORE) d[idx] = v;
-              else if (p.store_mode == JMT_ACCUMULATE) d[idx] += v;
-              else atomicAdd(d + idx, v);
-            } else {
-              __nv_bfloat16* d = (__nv_bfloat16*)p.d;
-              d[idx] = __float2bfloat16_rn(p.store_mode == JMT_STORE ? v : __bfloat162float(d[idx]) + v);
-            }
-          }
-        }
+      const long long tb0 = p.prof ? clock64() : 0;
+      if (p.bias != nullptr) {
+        const bool add_bias = split == 0;
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kNumEpiWarps) : "memory");     // previous tile's readers are done
+        if (et < p.block_n) bias_ptr[et] = (add_bias && c.n0 + et < p.N) ? __ldg(p.bias + c.n0 + et) : 0.f;
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kNumEpiWarps) : "memory");
       }
+      const long long tb1 = p.prof ? clock64() : 0;
+      mbar_wait(tfull_bar + 8 * acc, acc_phase);
+      if (p.prof) { ep_bar += tb1 - tb0; ep_tfull += clock64() - tb1; }
+      tc_fence_after();
+      uint32_t b1u, b0u;
+      p.fd_nb0.divmod((uint32_t)c.batch, b1u, b0u);
+      EpiCtx ec;
+      ec.tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kAccStride);
+      ec.stage_smem = stage_smem; ec.row_smem = row_smem; ec.sw = sw; ec.bias = bias_ptr;
+      ec.m0w = c.m0 + q * 32; ec.n0 = c.n0; ec.b0 = (int)b0u; ec.b1 = (int)b1u; ec.half = half; ec.lane = lane;
+      if (p.act == JMT_ACT_NONE) epi_tile<JMT_ACT_NONE>(p, &tma_d, ec);
+      else if (p.act == JMT_ACT_RELU) epi_tile<JMT_ACT_RELU>(p, &tma_d, ec);
+      else epi_tile<JMT_ACT_LEAKY_RELU>(p, &tma_d, ec);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar + 8 * acc);
+      if (lane == 0) {
+        if constexpr (kCta == 1) mbar_arrive(tempty_bar + 8 * acc);
+        else mbar_arrive_cluster(tempty_leader + 8 * acc);      // the leader's MMA issuer waits for both CTAs' epilogues
+      }
     }
     if (lane == 0) bulk_wait0();                   // all TMA stores of this warp have completed
+    if (p.prof && ew == 0 && lane == 0) {
+      unsigned long long* o = p.prof + blockIdx.x * 16;
+      o[5] = ep_tfull; o[6] = ep_bar; o[7] = ep_rd; o[8] = clock64() - ep_t0;
+    }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (p.cluster == 2) cluster_sync_all();       // no CTA exits while its peer may still signal / multicast into it
+  if constexpr (kCta == 2) cluster_sync_all();    // no CTA exits (or frees TMEM) while its peer may still read / signal it
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    if constexpr (kCta == 1)
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
   }
 }
 
@@ -510,6 +674,15 @@ static int pick_block_n(int N) {
 
 using namespace jmt;
 
+static std::atomic<unsigned long long*> g_prof_buf{nullptr};
+// Debug aid: when set (device buffer of 16 x 148 uint64), every jmt_gemm_bf16 launch overwrites per-CTA cycle
+// counters: [0] MMA wait-full [1] MMA wait-tmem-empty [2] MMA total [3] TMA wait-empty [4] TMA total
+// [5] epilogue wait-tmem-full [6] epilogue bias barriers [7] epilogue wait-store-read [8] epilogue total
+extern "C" int jmt_gemm_set_profile_buffer(void* dev_buf) {
+  g_prof_buf.store((unsigned long long*)dev_buf);
+  return JMT_OK;
+}
+
 extern "C" int jmt_gemm_bf16(const jmt_gemm_desc* g, void* stream) {
   int rc = jmt_validate_gemm_desc(g, "jmt_gemm_bf16");
   if (rc != JMT_OK) return rc;
@@ -526,33 +699,43 @@ extern "C" int jmt_gemm_bf16(const jmt_gemm_desc* g, void* stream) {
   p.rb_n = p.reduce_batch ? nb : 1;
   p.iters_total = g->ntaps * p.rb_n * p.kblocks;
   p.split_k = g->split_k < p.iters_total ? g->split_k : p.iters_total;
-  // CTA pairs along M with B multicast when the M tiling wastes < ~10 % on the ghost tile
-  const int b_chunks_h = (p.block_n + 63) / 64;
-  const bool mc_layout_ok = g->b_major == JMT_MAJOR_K ? true : (b_chunks_h % 2 == 0);
+  p.b_has_b0 = (g->nb0 > 1 && g->b_bs0 != 0) ? 1 : 0;
+  p.b_has_b1 = (g->nb1 > 1 && g->b_bs1 != 0) ? 1 : 0;
+  // CTA pairs (cta_group::2, M = 256): along M when the ghost tile of an odd tail wastes < ~10 %, else across two
+  // consecutive batch entries when they share B (implicit-GEMM conv: weights are not batched)
   const char* env_cl = getenv("JMT_GEMM_CLUSTER");
   const bool cl_enabled = env_cl ? atoi(env_cl) != 0 : true;
-  p.cluster = (cl_enabled && mc_layout_ok && p.m_tiles >= 2 && (p.m_tiles % 2 == 0 || p.m_tiles >= 9)) ? 2 : 1;
-  p.m_pairs = (p.m_tiles + p.cluster - 1) / p.cluster;
-  const int64_t total = (int64_t)p.m_pairs * p.n_tiles * p.batch_tiles * p.split_k;
+  const bool pair_m_ok = p.m_tiles >= 2 && (p.m_tiles % 2 == 0 || p.m_tiles >= 9);
+  const bool pair_b_ok = !p.reduce_batch && !p.b_has_b0 && !p.b_has_b1 && p.batch_tiles >= 2 && p.batch_tiles % 2 == 0;
+  // (tiles with fewer than 4 k-iterations are epilogue-bound: the pair's shared tempty / full handshakes only cost there)
+  const bool long_enough = p.iters_total / p.split_k >= 4;
+  p.cluster = (cl_enabled && long_enough && (pair_m_ok || pair_b_ok)) ? 2 : 1;
+  p.pair_batch = (p.cluster == 2 && !pair_m_ok) ? 1 : 0;
+  p.m_pairs = (p.cluster == 2 && !p.pair_batch) ? (p.m_tiles + 1) / 2 : p.m_tiles;
+  p.batch_slots = p.pair_batch ? p.batch_tiles / 2 : p.batch_tiles;
+  const int64_t total = (int64_t)p.m_pairs * p.n_tiles * p.batch_slots * p.split_k;
   JMT_REQUIRE(total < (1ll << 31), "jmt_gemm_bf16: too many tiles");
   p.total_tiles = (int)total;
   p.nb0 = g->nb0;
+  p.fd_ntiles.init(p.n_tiles); p.fd_mpairs.init(p.m_pairs); p.fd_bslots.init(p.batch_slots); p.fd_nb0.init(g->nb0);
+  p.fd_kblocks.init(p.kblocks); p.fd_rbn.init(p.rb_n);
   p.a_major = g->a_major; p.b_major = g->b_major;
   p.a_shift0 = g->a_shift0; p.a_shift_step = g->a_shift_step;
   p.b_shift0 = g->b_shift0; p.b_shift_step = g->b_shift_step;
-  p.b_has_b0 = (g->nb0 > 1 && g->b_bs0 != 0) ? 1 : 0;
-  p.b_has_b1 = (g->nb1 > 1 && g->b_bs1 != 0) ? 1 : 0;
   JMT_REQUIRE(!(g->ntaps > 1 && g->b_major == JMT_MAJOR_K && g->K % 8 != 0), "jmt_gemm_bf16: taps need K %% 8 == 0");
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)g->a_major << 15) | ((uint32_t)g->b_major << 16) |
-            ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
-  const int b_chunks = (p.block_n + 63) / 64;
-  p.b_stage_bytes = g->b_major == JMT_MAJOR_K ? p.block_n * 128 : b_chunks * 8192;
+            ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)((kBlockM * p.cluster) >> 4) << 24);
+  // per CTA: the whole B tile, or its half of it under cta_group::2
+  const int b_cols_cta = p.block_n / p.cluster;
+  p.b_chunks_cta = (b_cols_cta + 63) / 64;
+  p.b_stage_bytes = g->b_major == JMT_MAJOR_K ? b_cols_cta * 128 : p.b_chunks_cta * 8192;
   p.b_tx_bytes = p.b_stage_bytes;
   const int stage_bytes = kAStageBytes + p.b_stage_bytes;
   const int budget = 227 * 1024 - 1024 /*align*/ - 512 /*barriers*/ - kEpiSmemBytes;
   p.stages = budget / stage_bytes;
   if (p.stages > kMaxStages) p.stages = kMaxStages;
   JMT_REQUIRE(p.stages >= 2, "jmt_gemm_bf16: shared memory budget");
+  p.prof = g_prof_buf.load();
   p.d = g->d; p.bias = g->bias; p.d_ld = g->d_ld; p.d_bs0 = g->d_bs0; p.d_bs1 = g->d_bs1;
   p.alpha = g->alpha; p.slope = g->slope; p.d_dtype = g->d_dtype; p.act = g->act; p.store_mode = g->store_mode;
   const int64_t es = g->d_dtype == JMT_F32 ? 4 : 2;
@@ -569,7 +752,7 @@ extern "C" int jmt_gemm_bf16(const jmt_gemm_desc* g, void* stream) {
   const int bnb0 = p.b_has_b0 ? g->nb0 : 1, bnb1 = p.b_has_b1 ? g->nb1 : 1;
   if (g->b_major == JMT_MAJOR_K)
     rc = make_map(&map_b, g->b, (int64_t)g->ntaps * g->K, g->b_rows, g->b_ld, bnb0, g->b_bs0, bnb1, g->b_bs1,
-                  p.block_n / p.cluster /* each CTA of a pair fetches (and multicasts) half of the tile's rows */, "jmt_gemm_bf16(B)");
+                  b_cols_cta /* each CTA of a pair stages half of the tile's rows */, "jmt_gemm_bf16(B)");
   else
     rc = make_map(&map_b, g->b, g->N, g->b_rows, g->b_ld, bnb0, g->b_bs0, bnb1, g->b_bs1, kBlockK, "jmt_gemm_bf16(B)");
   if (rc != JMT_OK) return rc;
@@ -588,7 +771,8 @@ extern "C" int jmt_gemm_bf16(const jmt_gemm_desc* g, void* stream) {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); set_error("jmt_gemm_bf16: no CUDA device"); return JMT_ERR_CUDA; }
   if (!attr_set[dev & 63].load(std::memory_order_acquire)) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) { set_error("jmt_gemm_bf16: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); cudaGetLastError(); return JMT_ERR_CUDA; }
     attr_set[dev & 63].store(1, std::memory_order_release);
   }
@@ -607,7 +791,8 @@ extern "C" int jmt_gemm_bf16(const jmt_gemm_desc* g, void* stream) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tc_kernel, map_a, map_b, map_d, p);
+  cudaError_t le = p.cluster == 2 ? cudaLaunchKernelEx(&cfg, gemm_tc_kernel<2>, map_a, map_b, map_d, p)
+                                  : cudaLaunchKernelEx(&cfg, gemm_tc_kernel<1>, map_a, map_b, map_d, p);
   if (le != cudaSuccess) {
     set_error("jmt_gemm_bf16: cudaLaunchKernelEx: %s", cudaGetErrorString(le));
     cudaGetLastError();

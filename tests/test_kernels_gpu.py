@@ -82,6 +82,13 @@ GEMM_CASES = [
     ("conv_wgrad_tap", 96, 64, 40, 1, 1, 3, 1, (0, 0), (-4, 0), True, 2, 0, False, "f32", 2),
     ("n_small", 150, 8, 128, 0, 0, 1, 1, (0, 0), (0, 0), False, 1, 0, True, "f32", 0),
     ("k_small", 150, 300, 16, 0, 0, 2, 1, (0, 0), (0, 0), False, 1, 0, False, "f32", 0),
+    # CTA-pair (cta_group::2) paths: ghost tile of an odd M tail, MN-major B halves that are not 64-multiples,
+    # pairs across two batch entries sharing B (conv), many tiles per CTA pair (persistent loop + both TMEM stages)
+    ("pair_m_ghost", 1100, 160, 192, 0, 0, 1, 1, (0, 0), (0, 0), False, 1, 0, True, "act", 0),
+    ("pair_bmn_n192", 512, 192, 256, 0, 1, 2, 1, (0, 0), (0, 0), False, 1, 0, False, "f32", 0),
+    ("conv_fwd_taps_nb4", 40, 96, 64, 0, 0, 4, 5, (-8, 2), (0, 0), False, 1, 2, True, "act", 0),
+    ("conv_dgrad_taps_nb6", 300, 64, 96, 0, 0, 6, 5, (8, -2), (0, 0), False, 1, 0, False, "act", 1),
+    ("pair_persistent", 128 * 40, 512, 128, 0, 0, 8, 1, (0, 0), (0, 0), False, 1, 1, True, "act", 0),
 ]
 
 
