@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define JMT_ABI_VERSION 1
+#define JMT_ABI_VERSION 2
 
 typedef enum {
   JMT_OK = 0,
@@ -75,6 +75,7 @@ int64_t jmt_launch_count(void);
  *   j*K (weights laid out (n, tap*K + k)).
  *   reduce_batch != 0: the batch index becomes an extra reduction dimension (D is not batched).
  *   split_k > 1 requires store_mode == JMT_ATOMIC_ADD and d_dtype == JMT_F32.
+ *   colmask: see the field comment (channel dropout fused into the epilogue).
  *
  * Replaces: every nn.Linear / in_proj / out_proj / bmm of the fusion path
  * (mm_multi_transformers.py:52-56,120-124,142-167,203-209; two_transformers.py:104-128;
@@ -99,6 +100,11 @@ typedef struct {
   int32_t a_shift0, a_shift_step, b_shift0, b_shift_step;
   int32_t reduce_batch;
   int32_t split_k;              /* >= 1 */
+  /* optional per-(batch, column) keep-mask applied AFTER the activation: D(m, n) *= colmask[b*N + n] ? colmask_scale : 0
+   * (nn.Dropout2d of the TCN fused into the conv epilogue, temporal_convolutional_model.py:29,36); NULL = none.
+   * Needs reduce_batch == 0 and split_k == 1. */
+  const uint8_t* colmask;
+  float colmask_scale;
 } jmt_gemm_desc;
 
 int jmt_gemm_bf16(const jmt_gemm_desc* g, void* stream);
@@ -124,10 +130,11 @@ int jmt_l2norm_bwd(const void* dy, const void* y, int dtype, const float* inv_no
 int jmt_add_layernorm_fwd(const void* x, const void* res, const float* gamma, const float* beta, float eps,
                           void* y, float* mean, float* rstd, int64_t rows, int D, int dtype, void* stream);
 /* dz = d(x+res); dgamma/dbeta (D) fp32 are ACCUMULATED with atomics (caller zeroes).
- * dz_accumulate != 0: dz += result. */
+ * dz_accumulate != 0: dz += result.  dz_colsum (D, nullable): += column sums of dz = the bias gradient of the
+ * Linear that produced the residual branch (out_proj / feed_forward.2), saving a separate pass over dz. */
 int jmt_add_layernorm_bwd(const void* dy, const void* x, const void* res, const float* gamma,
-                          const float* mean, const float* rstd, void* dz, int dz_accumulate,
-                          float* dgamma, float* dbeta, int64_t rows, int D, int dtype, void* stream);
+                          const float* mean, const float* rstd, void* dz, int dz_accumulate, float* dgamma,
+                          float* dbeta, float* dz_colsum, int64_t rows, int D, int dtype, void* stream);
 
 /* P = softmax(S) over the last dim (torch MHA math path, keys axis).  S fp32 (rows, s_ld),
  * P p_dtype (rows, p_ld); columns >= cols of P are written as zero up to p_ld. */
@@ -167,6 +174,12 @@ int jmt_regressor_tail_bwd(int G, const void* const* h, int64_t h_ld, int dtype,
 int jmt_act_bwd(const void* dy, const void* y, void* dx, int64_t n, float slope, int dtype, void* stream);
 /* out[c] += sum_r x[r*ld + c]  (bias gradients), fp32 atomics; caller zeroes. */
 int jmt_colsum(const void* x, int dtype, int64_t ld, int64_t rows, int cols, float* out, void* stream);
+/* One pass for the backward of Linear/Conv1d -> (Leaky)ReLU -> channel dropout (two_transformers.py:104-114 ReLU heads,
+ * mm_multi_transformers.py:52-56 FFN, temporal_convolutional_model.py:24-36):
+ *   dx[r,c] = (mask ? (mask[r / L, c] ? dy*scale : 0) : dy) * (y[r,c] > 0 ? 1 : slope);  colsum[c] += sum_r dx[r,c]
+ * dy/y/dx contiguous (rows, cols), cols % 8 == 0; mask (rows / L, cols) uint8 nullable; colsum fp32 nullable. */
+int jmt_act_bwd_fused(const void* dy, const void* y, const uint8_t* mask, void* dx, int64_t rows, int cols, int L,
+                      float scale, float slope, float* colsum, int dtype, void* stream);
 /* out = cast(in) */
 int jmt_cast(const void* in, int in_dtype, void* out, int out_dtype, int64_t n, void* stream);
 /* y += a*x (same dtype) */

@@ -32,6 +32,7 @@ class GemmDesc(C.Structure):
         ("a_shift0", C.c_int32), ("a_shift_step", C.c_int32),
         ("b_shift0", C.c_int32), ("b_shift_step", C.c_int32),
         ("reduce_batch", C.c_int32), ("split_k", C.c_int32),
+        ("colmask", C.c_void_p), ("colmask_scale", C.c_float),
     ]
 
 
@@ -48,7 +49,7 @@ SIGNATURES = {
     "jmt_l2norm_fwd": [_P, _I, _L, _P, _I, _L, _I, _F, _P, _P],
     "jmt_l2norm_bwd": [_P, _P, _I, _P, _F, _P, _L, _I, _P],
     "jmt_add_layernorm_fwd": [_P, _P, _P, _P, _F, _P, _P, _P, _L, _I, _I, _P],
-    "jmt_add_layernorm_bwd": [_P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _L, _I, _I, _P],
+    "jmt_add_layernorm_bwd": [_P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _L, _I, _I, _P],
     "jmt_softmax_fwd": [_P, _L, _P, _I, _L, _L, _I, _P],
     "jmt_softmax_bwd": [_P, _I, _L, _P, _L, _P, _I, _L, _L, _I, _P],
     "jmt_attn_small_fwd": [_P, _P, _P, _I, _L, _I, _I, _F, _I, _P],
@@ -57,6 +58,7 @@ SIGNATURES = {
     "jmt_regressor_tail_bwd": [_I, _P, _L, _I, _P, _P, _P, _P, _P, _P, _P, _L, _L, _L, _L, _P],
     "jmt_act_bwd": [_P, _P, _P, _L, _F, _I, _P],
     "jmt_colsum": [_P, _I, _L, _L, _I, _P, _P],
+    "jmt_act_bwd_fused": [_P, _P, _P, _P, _L, _I, _I, _F, _F, _P, _I, _P],
     "jmt_cast": [_P, _I, _P, _I, _L, _P],
     "jmt_axpy": [_P, _P, _F, _L, _I, _P],
     "jmt_copy2d": [_P, _I, _L, _P, _I, _L, _L, _I, _P],
@@ -90,7 +92,7 @@ def lib():
             fn = getattr(h, name)           # AttributeError if a declared symbol is not exported
             fn.argtypes = argtypes
             fn.restype = _RESTYPES.get(name, C.c_int)
-        if h.jmt_abi_version() != 1:
+        if h.jmt_abi_version() != 2:
             raise RuntimeError("libjmt_b200.so ABI version mismatch")
         _lib = h
     return _lib

@@ -127,6 +127,50 @@ colsum_kernel(const T* __restrict__ x, int64_t ld, int64_t rows, int cols, float
   }
 }
 
+// dx = (mask ? dy * scale : 0) * (y > 0 ? 1 : slope) and colsum[c] += sum_r dx[r, c] in ONE pass over dy / y
+// (backward of Linear/Conv -> activation -> channel dropout: activation gradient, dropout replay and the bias
+// gradient, which were three kernels = 5 passes over a (rows, C) matrix).  Same block shape as colsum_kernel:
+// 32 column groups of 8 x 8 row lanes.  mask is per (row / L, c) (channel dropout of one sample), nullable.
+template <typename T>
+__global__ void __launch_bounds__(256)
+act_bwd_fused_kernel(const T* __restrict__ dy, const T* __restrict__ y, const uint8_t* __restrict__ mask, T* __restrict__ dx,
+                     int64_t rows, int cols, int L, float scale, float slope, float* __restrict__ colsum) {
+  __shared__ float sh[8][257];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  const int c0 = blockIdx.x * 256 + tx * 8;
+  if (c0 < cols) {
+    for (int64_t r = (int64_t)blockIdx.y * 8 + ty; r < rows; r += (int64_t)gridDim.y * 8) {
+      Vec8<T> g, a; g.load(dy + r * cols + c0); a.load(y + r * cols + c0);
+      if (mask) {
+        const uint2 mk = *reinterpret_cast<const uint2*>(mask + (r / L) * cols + c0);
+        const uint8_t* mb = reinterpret_cast<const uint8_t*>(&mk);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) g.v[k] = mb[k] ? g.v[k] * scale : 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        g.v[k] = a.v[k] > 0.f ? g.v[k] : g.v[k] * slope;
+        acc[k] += g.v[k];
+      }
+      g.store(dx + r * cols + c0);
+    }
+  }
+  if (colsum == nullptr) return;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sh[ty][tx * 8 + i] = acc[i];
+  __syncthreads();
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += sh[i][threadIdx.x];
+    atomicAdd(colsum + c, t);
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kEwThreads)
 apply_mask_kernel(const T* __restrict__ x, const uint8_t* __restrict__ mask, T* __restrict__ out, int64_t total, int L,
@@ -400,6 +444,22 @@ extern "C" int jmt_colsum(const void* x, int dtype, int64_t ld, int64_t rows, in
   const int vec = (cols % 8 == 0 && ld % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) ? 1 : 0;
   JMT_DISPATCH_DTYPE(dtype, T, (colsum_kernel<T><<<dim3(gx, gy), 256, 0, (cudaStream_t)stream>>>((const T*)x, ld, rows, cols, out, vec)));
   return check_launch("colsum_kernel");
+}
+
+extern "C" int jmt_act_bwd_fused(const void* dy, const void* y, const uint8_t* mask, void* dx, int64_t rows, int cols, int L,
+                                 float scale, float slope, float* colsum, int dtype, void* stream) {
+  JMT_REQUIRE(dy && y && dx && rows >= 0 && cols > 0 && cols % 8 == 0 && L >= 1, "jmt_act_bwd_fused: bad arguments (cols %% 8)");
+  JMT_REQUIRE(((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0 &&
+              (reinterpret_cast<uintptr_t>(mask) & 7) == 0, "jmt_act_bwd_fused: pointers must be 16-byte aligned");
+  if (rows == 0) return JMT_OK;
+  const int gx = (cols + 255) / 256;
+  int gy = (int)((rows + 63) / 64);
+  const int cap = (kNumSMs * 8 + gx - 1) / gx;
+  if (gy > cap) gy = cap;
+  if (gy < 1) gy = 1;
+  JMT_DISPATCH_DTYPE(dtype, T, (act_bwd_fused_kernel<T><<<dim3(gx, gy), 256, 0, (cudaStream_t)stream>>>(
+      (const T*)dy, (const T*)y, mask, (T*)dx, rows, cols, L, scale, slope, colsum)));
+  return check_launch("act_bwd_fused_kernel");
 }
 
 extern "C" int jmt_apply_mask(const void* x, const uint8_t* mask, void* out, int64_t nb, int L, int C, int per_channel,

@@ -102,6 +102,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(SimtArgs s) {
       float v = g.alpha * acc[i][j];
       if (g.bias && split == 0) v += g.bias[n];
       v = apply_act(v, g.act, g.slope);
+      if (g.colmask) v = g.colmask[(int64_t)batch * g.N + n] ? v * g.colmask_scale : 0.f;
       const int64_t idx = doff + (int64_t)m * g.d_ld + n;
       if (g.d_dtype == JMT_F32) {
         float* d = (float*)g.d;
@@ -133,6 +134,7 @@ int jmt_validate_gemm_desc(const jmt_gemm_desc* g, const char* who) {
   JMT_REQUIRE(!(g->split_k > 1 && (g->store_mode != JMT_ATOMIC_ADD || g->act != JMT_ACT_NONE)),
               "%s: split_k > 1 needs JMT_ATOMIC_ADD and no activation", who);
   JMT_REQUIRE(g->act >= JMT_ACT_NONE && g->act <= JMT_ACT_LEAKY_RELU, "%s: bad act", who);
+  JMT_REQUIRE(!(g->colmask && (g->reduce_batch || g->split_k > 1)), "%s: colmask needs reduce_batch == 0 and split_k == 1", who);
   return JMT_OK;
 }
 

@@ -36,7 +36,7 @@ constexpr int kMaxStages = 8;
 constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;       // TMEM columns per accumulator stage
 constexpr int kEpiStageBytes = 4096;      // 32 rows x 128 B per epilogue warp
-constexpr int kEpiSmemBytes = kNumEpiWarps * kEpiStageBytes + 1024;   // staging tiles + one shared bias tile
+constexpr int kEpiSmemBytes = kNumEpiWarps * kEpiStageBytes + 2048;   // staging tiles + shared bias tile + column-scale tile
 constexpr uint32_t kSpinLimit = 1u << 24;   // ~1 s of polling, far beyond any legitimate wait
 
 // Division by a runtime constant without the ~150-cycle integer-divide sequence: the single-thread TMA / MMA roles
@@ -74,6 +74,8 @@ struct TcParams {
   // epilogue
   void* d;
   const float* bias;
+  const uint8_t* colmask;     // per (batch, column) keep-mask applied after the activation (nullable)
+  float colmask_scale;
   int64_t d_ld, d_bs0, d_bs1;
   float alpha, slope;
   int d_dtype, act, store_mode, vec_ok;
@@ -214,28 +216,45 @@ __device__ __forceinline__ float act_t(float x, float slope) {
 }
 // 32 accumulator columns -> act(alpha * acc + bias), branch-free (the activation is a template parameter so the
 // compiler can interleave the 32 independent FFMA / FMNMX / F2FP chains)
-template <int ACT>
-__device__ __forceinline__ void epi_math_bf16(const uint32_t (&r)[32], const float* bias, float alpha, float slope, uint32_t* pk) {
+// 32 accumulator columns -> act(alpha * acc + bias) [* column scale] -> bf16 -> this thread's staging row
+// (16-byte pieces `piece0 .. piece0+3` of the 128-byte row, 128B-swizzled).  Branch-free: the activation is a template
+// parameter so the compiler interleaves the independent FFMA / FMNMX / F2FP chains; nothing but r[] stays live.
+template <int ACT, bool MASK>
+__device__ __forceinline__ void epi_math_store_bf16(const uint32_t (&r)[32], const float* bias, float alpha, float slope,
+                                                    uint32_t row_smem, uint32_t sw, int piece0) {
 #pragma unroll
-  for (int j = 0; j < 32; j += 4) {
-    const float4 bv = *reinterpret_cast<const float4*>(bias + j);
-    const float x0 = act_t<ACT>(fmaf(alpha, __uint_as_float(r[j]), bv.x), slope);
-    const float x1 = act_t<ACT>(fmaf(alpha, __uint_as_float(r[j + 1]), bv.y), slope);
-    const float x2 = act_t<ACT>(fmaf(alpha, __uint_as_float(r[j + 2]), bv.z), slope);
-    const float x3 = act_t<ACT>(fmaf(alpha, __uint_as_float(r[j + 3]), bv.w), slope);
-    pk[j / 2] = pack_bf16(x0, x1);
-    pk[j / 2 + 1] = pack_bf16(x2, x3);
+  for (int j = 0; j < 32; j += 8) {
+    float x[8];
+#pragma unroll
+    for (int h = 0; h < 8; h += 4) {
+      const float4 bv = *reinterpret_cast<const float4*>(bias + j + h);
+      x[h] = act_t<ACT>(fmaf(alpha, __uint_as_float(r[j + h]), bv.x), slope);
+      x[h + 1] = act_t<ACT>(fmaf(alpha, __uint_as_float(r[j + h + 1]), bv.y), slope);
+      x[h + 2] = act_t<ACT>(fmaf(alpha, __uint_as_float(r[j + h + 2]), bv.z), slope);
+      x[h + 3] = act_t<ACT>(fmaf(alpha, __uint_as_float(r[j + h + 3]), bv.w), slope);
+      if constexpr (MASK) {          // column scales live 256 floats after the bias tile
+        const float4 cs = *reinterpret_cast<const float4*>(bias + 256 + j + h);
+        x[h] *= cs.x; x[h + 1] *= cs.y; x[h + 2] *= cs.z; x[h + 3] *= cs.w;
+      }
+    }
+    st_shared_v4(row_smem + (((uint32_t)(piece0 + j / 8) ^ sw) << 4), pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]),
+                 pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
   }
 }
-template <int ACT>
+template <int ACT, bool MASK>
 __device__ __forceinline__ void epi_math_f32(uint32_t (&r)[32], const float* bias, float alpha, float slope) {
 #pragma unroll
   for (int j = 0; j < 32; j += 4) {
     const float4 bv = *reinterpret_cast<const float4*>(bias + j);
-    r[j] = __float_as_uint(act_t<ACT>(fmaf(alpha, __uint_as_float(r[j]), bv.x), slope));
-    r[j + 1] = __float_as_uint(act_t<ACT>(fmaf(alpha, __uint_as_float(r[j + 1]), bv.y), slope));
-    r[j + 2] = __float_as_uint(act_t<ACT>(fmaf(alpha, __uint_as_float(r[j + 2]), bv.z), slope));
-    r[j + 3] = __float_as_uint(act_t<ACT>(fmaf(alpha, __uint_as_float(r[j + 3]), bv.w), slope));
+    float x0 = act_t<ACT>(fmaf(alpha, __uint_as_float(r[j]), bv.x), slope);
+    float x1 = act_t<ACT>(fmaf(alpha, __uint_as_float(r[j + 1]), bv.y), slope);
+    float x2 = act_t<ACT>(fmaf(alpha, __uint_as_float(r[j + 2]), bv.z), slope);
+    float x3 = act_t<ACT>(fmaf(alpha, __uint_as_float(r[j + 3]), bv.w), slope);
+    if constexpr (MASK) {
+      const float4 cs = *reinterpret_cast<const float4*>(bias + 256 + j);
+      x0 *= cs.x; x1 *= cs.y; x2 *= cs.z; x3 *= cs.w;
+    }
+    r[j] = __float_as_uint(x0); r[j + 1] = __float_as_uint(x1); r[j + 2] = __float_as_uint(x2); r[j + 3] = __float_as_uint(x3);
   }
 }
 
@@ -287,7 +306,7 @@ struct EpiCtx {
 // One epilogue warp's share of a 128 x block_n accumulator tile: its 32 TMEM lanes (rows) x every other
 // 64-column (bf16 out) / 32-column (fp32 out) chunk -> alpha / bias / activation -> 128B-swizzled staging tile ->
 // TMA store or reduce-add; or per-thread stores when D's geometry is not 16-byte aligned.
-template <int ACT>
+template <int ACT, bool MASK>
 __device__ __forceinline__ void epi_tile(const TcParams& p, const CUtensorMap* tma_d, const EpiCtx& e) {
   const int lane = e.lane;
   if (p.tma_store) {
@@ -295,25 +314,19 @@ __device__ __forceinline__ void epi_tile(const TcParams& p, const CUtensorMap* t
     if (p.d_dtype == JMT_BF16) {
       for (int c0 = e.half * 64; c0 < p.block_n; c0 += 128) {
         if (e.n0 + c0 >= p.N) break;
-        uint32_t pk[32];
         const bool second = c0 + 32 < p.block_n;      // block_n is a multiple of 32
-        {
-          uint32_t r0[32], r1[32];
-          tc_ld32_issue(e.tbase + c0, r0);
-          if (second) tc_ld32_issue(e.tbase + c0 + 32, r1);
-          tc_wait_ld();
-          epi_math_bf16<ACT>(r0, e.bias + c0, p.alpha, p.slope, pk);
-          if (second) epi_math_bf16<ACT>(r1, e.bias + c0 + 32, p.alpha, p.slope, pk + 16);
-          else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) pk[16 + j] = 0u;
-          }
-        }
+        uint32_t r0[32], r1[32];
+        tc_ld32_issue(e.tbase + c0, r0);
+        if (second) tc_ld32_issue(e.tbase + c0 + 32, r1);
         if (lane == 0) bulk_wait_read0();       // previous TMA store has finished reading the staging tile
         __syncwarp();
+        tc_wait_ld();
+        epi_math_store_bf16<ACT, MASK>(r0, e.bias + c0, p.alpha, p.slope, e.row_smem, e.sw, 0);
+        if (second) epi_math_store_bf16<ACT, MASK>(r1, e.bias + c0 + 32, p.alpha, p.slope, e.row_smem, e.sw, 4);
+        else {
 #pragma unroll
-        for (int ch = 0; ch < 8; ++ch)
-          st_shared_v4(e.row_smem + ((ch ^ e.sw) << 4), pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
+          for (int ch = 4; ch < 8; ++ch) st_shared_v4(e.row_smem + (((uint32_t)ch ^ e.sw) << 4), 0u, 0u, 0u, 0u);
+        }
         fence_async_smem();
         __syncwarp();
         if (lane == 0 && warp_rows_valid) {
@@ -327,7 +340,7 @@ __device__ __forceinline__ void epi_tile(const TcParams& p, const CUtensorMap* t
         if (e.n0 + c0 >= p.N) break;
         uint32_t r[32];
         tc_ld32(e.tbase + c0, r);
-        epi_math_f32<ACT>(r, e.bias + c0, p.alpha, p.slope);
+        epi_math_f32<ACT, MASK>(r, e.bias + c0, p.alpha, p.slope);
         if (lane == 0) bulk_wait_read0();
         __syncwarp();
 #pragma unroll
@@ -355,7 +368,8 @@ __device__ __forceinline__ void epi_tile(const TcParams& p, const CUtensorMap* t
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         if (n + j >= p.N) break;
-        const float v = act_t<ACT>(fmaf(p.alpha, __uint_as_float(r[j]), e.bias[c0 + j]), p.slope);
+        float v = act_t<ACT>(fmaf(p.alpha, __uint_as_float(r[j]), e.bias[c0 + j]), p.slope);
+        if constexpr (MASK) v *= e.bias[256 + c0 + j];
         const int64_t idx = row_off + n + j;
         if (p.d_dtype == JMT_F32) {
           float* d = (float*)p.d;
@@ -371,7 +385,7 @@ __device__ __forceinline__ void epi_tile(const TcParams& p, const CUtensorMap* t
   }
 }
 
-template <int kCta>
+template <int kCta, bool kMask>
 __global__ void __launch_bounds__(kTcThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                const __grid_constant__ CUtensorMap tma_d, const TcParams p) {
@@ -382,7 +396,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   const uint32_t sB = sA + p.stages * kAStageBytes;
   const uint32_t sD = sB + p.stages * p.b_stage_bytes;       // epilogue warps x 4 KiB staging (1024-aligned)
   const uint32_t sBias = sD + kNumEpiWarps * kEpiStageBytes; // 256 floats: this tile's bias slice
-  const uint32_t bars = sBias + 1024;                        // 8-byte aligned
+  const uint32_t bars = sBias + 2048;                        // 8-byte aligned (bias tile, then 256 floats of column scales)
   const uint32_t full_bar = bars, empty_bar = bars + 8 * kMaxStages;
   const uint32_t tfull_bar = bars + 16 * kMaxStages, tempty_bar = tfull_bar + 16;
   const uint32_t tmem_slot = tempty_bar + 16;
@@ -536,7 +550,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     const uint32_t sw = lane & 7;                 // 128B-swizzle phase of this thread's staging row
     const uint32_t tempty_leader = kCta == 2 ? mapa_rank(tempty_bar, 0) : tempty_bar;
     long long ep_tfull = 0, ep_bar = 0, ep_rd = 0; const long long ep_t0 = p.prof ? clock64() : 0;
-    if (p.bias == nullptr) {                      // no bias: one zero fill for the whole kernel
+    if (p.bias == nullptr && !kMask) {             // no bias: one zero fill for the whole kernel
       bias_ptr[et] = 0.f;
       asm volatile("bar.sync 1, %0;" ::"n"(32 * kNumEpiWarps) : "memory");
     }
@@ -548,10 +562,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       const uint32_t acc_phase = (tile_iter >> 1) & 1;
       // stage this tile's bias slice in shared memory (overlaps the mainloop); named barrier 1 = epilogue warps
       const long long tb0 = p.prof ? clock64() : 0;
-      if (p.bias != nullptr) {
-        const bool add_bias = split == 0;
+      if (p.bias != nullptr || kMask) {
+        const bool add_bias = p.bias != nullptr && split == 0;
         asm volatile("bar.sync 1, %0;" ::"n"(32 * kNumEpiWarps) : "memory");     // previous tile's readers are done
-        if (et < p.block_n) bias_ptr[et] = (add_bias && c.n0 + et < p.N) ? __ldg(p.bias + c.n0 + et) : 0.f;
+        if (et < p.block_n) {
+          const bool in_n = c.n0 + et < p.N;
+          bias_ptr[et] = (add_bias && in_n) ? __ldg(p.bias + c.n0 + et) : 0.f;
+          if constexpr (kMask)
+            bias_ptr[256 + et] = (in_n && p.colmask[(int64_t)c.batch * p.N + c.n0 + et]) ? p.colmask_scale : 0.f;
+        }
         asm volatile("bar.sync 1, %0;" ::"n"(32 * kNumEpiWarps) : "memory");
       }
       const long long tb1 = p.prof ? clock64() : 0;
@@ -564,9 +583,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       ec.tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kAccStride);
       ec.stage_smem = stage_smem; ec.row_smem = row_smem; ec.sw = sw; ec.bias = bias_ptr;
       ec.m0w = c.m0 + q * 32; ec.n0 = c.n0; ec.b0 = (int)b0u; ec.b1 = (int)b1u; ec.half = half; ec.lane = lane;
-      if (p.act == JMT_ACT_NONE) epi_tile<JMT_ACT_NONE>(p, &tma_d, ec);
-      else if (p.act == JMT_ACT_RELU) epi_tile<JMT_ACT_RELU>(p, &tma_d, ec);
-      else epi_tile<JMT_ACT_LEAKY_RELU>(p, &tma_d, ec);
+      // (kMask: channel dropout fused after the activation, TCN -- a separate kernel instantiation so that its extra
+      //  register pressure never touches the common kernels)
+      if (p.act == JMT_ACT_NONE) epi_tile<JMT_ACT_NONE, kMask>(p, &tma_d, ec);
+      else if (p.act == JMT_ACT_RELU) epi_tile<JMT_ACT_RELU, kMask>(p, &tma_d, ec);
+      else epi_tile<JMT_ACT_LEAKY_RELU, kMask>(p, &tma_d, ec);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -736,6 +757,7 @@ extern "C" int jmt_gemm_bf16(const jmt_gemm_desc* g, void* stream) {
   if (p.stages > kMaxStages) p.stages = kMaxStages;
   JMT_REQUIRE(p.stages >= 2, "jmt_gemm_bf16: shared memory budget");
   p.prof = g_prof_buf.load();
+  p.colmask = g->colmask; p.colmask_scale = g->colmask_scale;
   p.d = g->d; p.bias = g->bias; p.d_ld = g->d_ld; p.d_bs0 = g->d_bs0; p.d_bs1 = g->d_bs1;
   p.alpha = g->alpha; p.slope = g->slope; p.d_dtype = g->d_dtype; p.act = g->act; p.store_mode = g->store_mode;
   const int64_t es = g->d_dtype == JMT_F32 ? 4 : 2;
@@ -771,8 +793,10 @@ extern "C" int jmt_gemm_bf16(const jmt_gemm_desc* g, void* stream) {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); set_error("jmt_gemm_bf16: no CUDA device"); return JMT_ERR_CUDA; }
   if (!attr_set[dev & 63].load(std::memory_order_acquire)) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) { set_error("jmt_gemm_bf16: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); cudaGetLastError(); return JMT_ERR_CUDA; }
     attr_set[dev & 63].store(1, std::memory_order_release);
   }
@@ -791,8 +815,11 @@ extern "C" int jmt_gemm_bf16(const jmt_gemm_desc* g, void* stream) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t le = p.cluster == 2 ? cudaLaunchKernelEx(&cfg, gemm_tc_kernel<2>, map_a, map_b, map_d, p)
-                                  : cudaLaunchKernelEx(&cfg, gemm_tc_kernel<1>, map_a, map_b, map_d, p);
+  cudaError_t le;
+  if (p.colmask) le = p.cluster == 2 ? cudaLaunchKernelEx(&cfg, gemm_tc_kernel<2, true>, map_a, map_b, map_d, p)
+                                     : cudaLaunchKernelEx(&cfg, gemm_tc_kernel<1, true>, map_a, map_b, map_d, p);
+  else le = p.cluster == 2 ? cudaLaunchKernelEx(&cfg, gemm_tc_kernel<2, false>, map_a, map_b, map_d, p)
+                           : cudaLaunchKernelEx(&cfg, gemm_tc_kernel<1, false>, map_a, map_b, map_d, p);
   if (le != cudaSuccess) {
     set_error("jmt_gemm_bf16: cudaLaunchKernelEx: %s", cudaGetErrorString(le));
     cudaGetLastError();

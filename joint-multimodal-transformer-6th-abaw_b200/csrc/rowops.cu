@@ -125,17 +125,18 @@ __global__ void __launch_bounds__(kRowThreads)
 add_layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ res,
                          const float* __restrict__ gamma, const float* __restrict__ mean,
                          const float* __restrict__ rstd, T* __restrict__ dz, int dz_accumulate,
-                         float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t rows) {
+                         float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dz_colsum,
+                         int64_t rows) {
   constexpr int D = NCH * 256;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerBlock + warp;
   const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
-  float g[NCH][8], dg[NCH][8], db[NCH][8];
+  float g[NCH][8], dg[NCH][8], db[NCH][8], dzs[NCH][8];
 #pragma unroll
   for (int j = 0; j < NCH; ++j) {
     Vec8<float> t; t.load(gamma + j * 256 + lane * 8);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { g[j][i] = t.v[i]; dg[j][i] = 0.f; db[j][i] = 0.f; }
+    for (int i = 0; i < 8; ++i) { g[j][i] = t.v[i]; dg[j][i] = 0.f; db[j][i] = 0.f; dzs[j][i] = 0.f; }
   }
   for (int64_t r = warp0; r < rows; r += nwarps) {
     const float mu = mean[r], rs = rstd[r];
@@ -169,6 +170,7 @@ add_layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, cons
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const float v = rs * (gy[j][i] - s1 - xh[j][i] * s2);
+        dzs[j][i] += v;
         o.v[i] = dz_accumulate ? o.v[i] + v : v;
       }
       o.store(dz + r * D + j * 256 + lane * 8);
@@ -176,14 +178,15 @@ add_layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, cons
   }
   // block-level reduction of dgamma / dbeta partials, then one atomic per column per block
   __shared__ float sh[kWarpsPerBlock][D + 8];
-  for (int pass = 0; pass < 2; ++pass) {
+  // (third pass: column sums of dz = the bias gradient of the Linear that produced the residual branch)
+  for (int pass = 0; pass < (dz_colsum ? 3 : 2); ++pass) {
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < NCH; ++j)
 #pragma unroll
-      for (int i = 0; i < 8; ++i) sh[warp][j * 256 + lane * 8 + i] = pass == 0 ? dg[j][i] : db[j][i];
+      for (int i = 0; i < 8; ++i) sh[warp][j * 256 + lane * 8 + i] = pass == 0 ? dg[j][i] : (pass == 1 ? db[j][i] : dzs[j][i]);
     __syncthreads();
-    float* outp = pass == 0 ? dgamma : dbeta;
+    float* outp = pass == 0 ? dgamma : (pass == 1 ? dbeta : dz_colsum);
     for (int c = threadIdx.x; c < D; c += kRowThreads) {
       float s = 0.f;
 #pragma unroll
@@ -282,10 +285,10 @@ extern "C" int jmt_add_layernorm_fwd(const void* x, const void* res, const float
 
 template <typename T>
 static int launch_ln_bwd(const void* dy, const void* x, const void* res, const float* gamma, const float* mean,
-                         const float* rstd, void* dz, int acc, float* dgamma, float* dbeta, int64_t rows, int D,
+                         const float* rstd, void* dz, int acc, float* dgamma, float* dbeta, float* dz_colsum, int64_t rows, int D,
                          cudaStream_t st) {
   const int g = grid_for(rows, kWarpsPerBlock * 16, kNumSMs * 2);   // each warp sweeps many rows: few atomics
-#define JMT_LN_CASE(N) case N: add_layernorm_bwd_kernel<T, N><<<g, kRowThreads, 0, st>>>((const T*)dy, (const T*)x, (const T*)res, gamma, mean, rstd, (T*)dz, acc, dgamma, dbeta, rows); break;
+#define JMT_LN_CASE(N) case N: add_layernorm_bwd_kernel<T, N><<<g, kRowThreads, 0, st>>>((const T*)dy, (const T*)x, (const T*)res, gamma, mean, rstd, (T*)dz, acc, dgamma, dbeta, dz_colsum, rows); break;
   switch (D / 256) { JMT_LN_CASE(1) JMT_LN_CASE(2) JMT_LN_CASE(3) JMT_LN_CASE(4)
     default: set_error("add_layernorm_bwd: D=%d unsupported", D); return JMT_ERR_UNSUPPORTED; }
 #undef JMT_LN_CASE
@@ -294,11 +297,11 @@ static int launch_ln_bwd(const void* dy, const void* x, const void* res, const f
 
 extern "C" int jmt_add_layernorm_bwd(const void* dy, const void* x, const void* res, const float* gamma,
                                      const float* mean, const float* rstd, void* dz, int dz_accumulate, float* dgamma,
-                                     float* dbeta, int64_t rows, int D, int dtype, void* stream) {
+                                     float* dbeta, float* dz_colsum, int64_t rows, int D, int dtype, void* stream) {
   JMT_REQUIRE(dy && x && gamma && mean && rstd && dz && dgamma && dbeta && D % 256 == 0 && D >= 256,
               "jmt_add_layernorm_bwd: bad arguments (D=%d)", D);
   if (rows == 0) return JMT_OK;
-  JMT_DISPATCH_DTYPE(dtype, T, return launch_ln_bwd<T>(dy, x, res, gamma, mean, rstd, dz, dz_accumulate, dgamma, dbeta, rows, D, (cudaStream_t)stream));
+  JMT_DISPATCH_DTYPE(dtype, T, return launch_ln_bwd<T>(dy, x, res, gamma, mean, rstd, dz, dz_accumulate, dgamma, dbeta, dz_colsum, rows, D, (cudaStream_t)stream));
   return JMT_OK;
 }
 

@@ -229,7 +229,8 @@ def gemm_flops(M, N, K, nb, ntaps, a_shift, b_shift, a_rows, b_rows, a_major, b_
 def gemm(ctx: Ctx, a: torch.Tensor, b: torch.Tensor, d: torch.Tensor, *, M: int, N: int, K: int,
          a_major=L.MAJOR_K, b_major=L.MAJOR_K, a_rows=None, b_rows=None, a_ld=None, b_ld=None, d_ld=None,
          nb0=1, nb1=1, a_bs=(0, 0), b_bs=(0, 0), d_bs=(0, 0), bias=None, act=L.ACT_NONE, slope=0.0, alpha=1.0,
-         store=L.STORE, ntaps=1, a_shift=(0, 0), b_shift=(0, 0), reduce_batch=False, split_k=1):
+         store=L.STORE, ntaps=1, a_shift=(0, 0), b_shift=(0, 0), reduce_batch=False, split_k=1,
+         colmask=None, colmask_scale=1.0):
     """One GEMM of the family in include/jmt_b200.h.  a/b/d supply base pointers and dtypes (views
     allowed); strides are in elements."""
     require_cuda(a, b, d)
@@ -255,6 +256,8 @@ def gemm(ctx: Ctx, a: torch.Tensor, b: torch.Tensor, d: torch.Tensor, *, M: int,
     g.b_shift0, g.b_shift_step = b_shift
     g.reduce_batch = 1 if reduce_batch else 0
     g.split_k = split_k
+    g.colmask = colmask.data_ptr() if colmask is not None else None
+    g.colmask_scale = colmask_scale
     prof = PROFILE
     if prof is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -349,11 +352,13 @@ def l2norm(ctx: Ctx, x: torch.Tensor, needs_grad: bool):
 def linear(ctx: Ctx, x: Var, wname: str, bname: Optional[str], act=L.ACT_NONE, slope=0.0,
            out: Optional[torch.Tensor] = None, w_rows: Optional[Tuple[int, int]] = None,
            w_cols: Optional[Tuple[int, int]] = None, accumulate_into: Optional[Var] = None,
-           grad_from: Optional[Tuple[Var, int, int]] = None) -> Var:
+           grad_from: Optional[Tuple[Var, int, int]] = None, bias_grad_external: bool = False) -> Var:
     """y = act(x W[r0:r1, c0:c1]^T + b[r0:r1])  (nn.Linear).  ``out`` may be a strided (rows, N) view
     (concat-free epilogue: a GEMM writes straight into its slice of a wider buffer);
     ``accumulate_into`` adds into an existing Var (Linear over a concatenation = sum of Linears over
-    column blocks of W, FeatureConcatFC / out_layer_pv without materialising the cat)."""
+    column blocks of W, FeatureConcatFC / out_layer_pv without materialising the cat).
+    ``bias_grad_external``: the bias gradient (column sums of dy) is produced by the consumer's backward kernel
+    (add_layernorm's dz column sums), so no separate pass over dy runs here."""
     W = ctx.w(wname)
     if W.dim() == 3:                       # 1x1 Conv1d weight (cout, cin, 1)
         W = W.view(W.shape[0], W.shape[1])
@@ -382,9 +387,10 @@ def linear(ctx: Ctx, x: Var, wname: str, bname: Optional[str], act=L.ACT_NONE, s
                 dy = y.grad
             if dy is None:
                 return
-            if act != L.ACT_NONE:
-                dy = _act_bwd(ctx, y, dy, slope)
-            if bname:
+            need_colsum = bool(bname) and not bias_grad_external
+            if act != L.ACT_NONE:          # activation gradient and bias gradient in one pass over dy
+                dy = _act_bwd(ctx, y, dy, slope, colsum=ctx.pgrad(bname)[r0:r1] if need_colsum else None)
+            elif need_colsum:
                 L.check(ctx.lib.jmt_colsum(_ptr(dy), _DT[dy.dtype], dy.stride(0), M, N, _ptr(ctx.pgrad(bname)[r0:r1]),
                                            _stream()), "jmt_colsum")
             # dW[r0:r1, c0:c1] += dy^T x   (both operands MN-major, split-K over the M rows, fp32 atomics)
@@ -404,18 +410,31 @@ def linear(ctx: Ctx, x: Var, wname: str, bname: Optional[str], act=L.ACT_NONE, s
     return y
 
 
-def _act_bwd(ctx: Ctx, y: Var, dy: torch.Tensor, slope: float) -> torch.Tensor:
-    """dy * act'(y).  In place when this Var is the only owner of its gradient buffer; otherwise (buffer
-    aliased by a sibling, e.g. the two branches of a residual add) into a fresh buffer."""
+def _act_bwd(ctx: Ctx, y: Var, dy: torch.Tensor, slope: float, colsum: Optional[torch.Tensor] = None,
+             mask: Optional[torch.Tensor] = None, mask_rows: int = 1, mask_scale: float = 1.0) -> torch.Tensor:
+    """dy * [channel-dropout mask * scale] * act'(y), optionally with the column sums (bias gradient) of the
+    result accumulated into ``colsum`` -- one pass (jmt_act_bwd_fused).  In place when this Var is the only owner
+    of its gradient buffer; otherwise (buffer aliased by a sibling, e.g. the two branches of a residual add)
+    into a fresh buffer."""
     assert dy.is_contiguous() and y.data.is_contiguous()
     dst = dy if (y.gbuf is not None and y.gbuf.refs == 1 and y.gbuf.t is dy) else ctx.empty(dy.shape, dy.dtype)
+    rows, cols = dy.shape
+    if cols % 8 == 0:
+        L.check(ctx.lib.jmt_act_bwd_fused(_ptr(dy), _ptr(y.data), _ptr(mask), _ptr(dst), rows, cols, mask_rows, mask_scale,
+                                          slope, _ptr(colsum), _DT[dy.dtype], _stream()), "jmt_act_bwd_fused")
+        return dst
+    assert mask is None
     L.check(ctx.lib.jmt_act_bwd(_ptr(dy), _ptr(y.data), _ptr(dst), dy.numel(), slope, _DT[dy.dtype], _stream()),
             "jmt_act_bwd")
+    if colsum is not None:
+        L.check(ctx.lib.jmt_colsum(_ptr(dst), _DT[dst.dtype], dst.stride(0), rows, cols, _ptr(colsum), _stream()), "jmt_colsum")
     return dst
 
 
-def add_layernorm(ctx: Ctx, x: Var, res: Optional[Var], gname: str, bname: str) -> Var:
-    """LayerNorm(x + res) with affine params (post-LN residual, mm_multi_transformers.py:62-69)."""
+def add_layernorm(ctx: Ctx, x: Var, res: Optional[Var], gname: str, bname: str, res_bias: Optional[str] = None) -> Var:
+    """LayerNorm(x + res) with affine params (post-LN residual, mm_multi_transformers.py:62-69).
+    ``res_bias``: name of the bias of the Linear that produced ``res`` (consumed only here): its gradient = column
+    sums of dz, accumulated by the LN backward kernel itself (that Linear is built with bias_grad_external)."""
     rows, D = x.data.shape
     assert x.data.is_contiguous() and (res is None or res.data.is_contiguous())
     y = ctx.empty((rows, D))
@@ -434,7 +453,8 @@ def add_layernorm(ctx: Ctx, x: Var, res: Optional[Var], gname: str, bname: str) 
             dz = GradBuf(ctx.empty((rows, D)))
             L.check(ctx.lib.jmt_add_layernorm_bwd(_ptr(dy), _ptr(x.data), _ptr(res.data) if res else None,
                                                   _ptr(ctx.p(gname)), _ptr(mean), _ptr(rstd), _ptr(dz.t), 0,
-                                                  _ptr(ctx.pgrad(gname)), _ptr(ctx.pgrad(bname)), rows, D, ctx.acode,
+                                                  _ptr(ctx.pgrad(gname)), _ptr(ctx.pgrad(bname)),
+                                                  _ptr(ctx.pgrad(res_bias)) if res_bias else None, rows, D, ctx.acode,
                                                   _stream()), "jmt_add_layernorm_bwd")
             ctx.add_grad(x, dz)
             if res is not None:
@@ -549,7 +569,8 @@ def attention_small(ctx: Ctx, qkv: Var, Lseq: int, N: int, E: int, heads: int) -
     return out
 
 
-def mha_self(ctx: Ctx, x: Var, prefix: str, heads: int, geom: Optional[AttnGeom], small: Optional[Tuple[int, int]] = None) -> Var:
+def mha_self(ctx: Ctx, x: Var, prefix: str, heads: int, geom: Optional[AttnGeom], small: Optional[Tuple[int, int]] = None,
+             out_bias_grad_external: bool = False) -> Var:
     """nn.MultiheadAttention(x, x, x): packed QKV projection (one N=3E GEMM), attention, out-proj."""
     E = x.data.shape[1]
     qkv = linear(ctx, x, prefix + "in_proj_weight", prefix + "in_proj_bias")
@@ -557,7 +578,7 @@ def mha_self(ctx: Ctx, x: Var, prefix: str, heads: int, geom: Optional[AttnGeom]
         o = attention_small(ctx, qkv, small[0], small[1], E, heads)
     else:
         o = attention_core(ctx, qkv, 0, qkv, E, qkv, 2 * E, E, heads, geom, geom)
-    return linear(ctx, o, prefix + "out_proj.weight", prefix + "out_proj.bias")
+    return linear(ctx, o, prefix + "out_proj.weight", prefix + "out_proj.bias", bias_grad_external=out_bias_grad_external)
 
 
 def mha_cross(ctx: Ctx, xq: Var, xkv: Var, prefix: str, heads: int, gq: AttnGeom, gk: AttnGeom,
@@ -577,11 +598,13 @@ def mha_cross(ctx: Ctx, xq: Var, xkv: Var, prefix: str, heads: int, gq: AttnGeom
 
 def encoder_layer(ctx: Ctx, x: Var, prefix: str, heads: int, geom: Optional[AttnGeom], small=None) -> Var:
     """TransformerEncoderLayer.forward (mm_multi_transformers.py:60-70): post-LN MHA + ReLU FFN."""
-    a = mha_self(ctx, x, prefix + "attention.", heads, geom, small)
-    x1 = add_layernorm(ctx, x, a, prefix + "layer_norm1.weight", prefix + "layer_norm1.bias")
+    a = mha_self(ctx, x, prefix + "attention.", heads, geom, small, out_bias_grad_external=True)
+    x1 = add_layernorm(ctx, x, a, prefix + "layer_norm1.weight", prefix + "layer_norm1.bias",
+                       res_bias=prefix + "attention.out_proj.bias")
     h = linear(ctx, x1, prefix + "feed_forward.0.weight", prefix + "feed_forward.0.bias", act=L.ACT_RELU)
-    f = linear(ctx, h, prefix + "feed_forward.2.weight", prefix + "feed_forward.2.bias")
-    return add_layernorm(ctx, x1, f, prefix + "layer_norm2.weight", prefix + "layer_norm2.bias")
+    f = linear(ctx, h, prefix + "feed_forward.2.weight", prefix + "feed_forward.2.bias", bias_grad_external=True)
+    return add_layernorm(ctx, x1, f, prefix + "layer_norm2.weight", prefix + "layer_norm2.bias",
+                         res_bias=prefix + "feed_forward.2.bias")
 
 
 def encoder_block(ctx: Ctx, x: Var, prefix: str, heads: int, layers: int, geom, small=None) -> Var:
@@ -733,16 +756,25 @@ def weight_norm_conv_weights(ctx: Ctx, prefix: str, cout: int, cin: int, k: int)
     return w_fwd, w_dg, dw
 
 
-def causal_conv(ctx: Ctx, x: Var, prefix: str, N: int, Ls: int, cin: int, cout: int, k: int, dil: int, act: int) -> Var:
-    """weight-normed dilated causal Conv1d + Chomp1d + LeakyReLU (temporal_convolutional_model.py:24-28)
+def causal_conv(ctx: Ctx, x: Var, prefix: str, N: int, Ls: int, cin: int, cout: int, k: int, dil: int, act: int,
+                drop_p: float = 0.0) -> Var:
+    """weight-normed dilated causal Conv1d + Chomp1d + LeakyReLU + Dropout2d (temporal_convolutional_model.py:24-29)
     as an implicit GEMM on channels-last data: taps are K blocks whose A rows are shifted by
-    -(k-1-j)*dil inside each sequence; rows before t=0 come back as zeros (TMA OOB fill / predicate)."""
+    -(k-1-j)*dil inside each sequence; rows before t=0 come back as zeros (TMA OOB fill / predicate).
+    Channel dropout (training, p > 0; SURVEY Q12: whole channels per sample) is a per-(sample, channel) scale in the
+    GEMM epilogue; its backward, the activation gradient and the bias gradient are one fused pass."""
     w_fwd, w_dg, dwh = weight_norm_conv_weights(ctx, prefix, cout, cin, k)   # recorded first => runs last in backward
     y = ctx.empty((N * Ls, cout))
     bias = ctx.p(prefix + "bias")
+    mask, mscale = None, 1.0
+    if drop_p > 0.0 and ctx.training:
+        mask = ctx.empty((N * cout,), torch.uint8)
+        L.check(ctx.lib.jmt_dropout_mask(_ptr(mask), N * cout, drop_p, ctx.seed, ctx.rng_offset, _stream()), "jmt_dropout_mask")
+        ctx.rng_offset += (N * cout + 3) // 4
+        mscale = 1.0 / (1.0 - drop_p)
     gemm(ctx, x.data, w_fwd, y, M=Ls, N=cout, K=cin, a_rows=Ls, b_rows=cout, a_ld=cin, b_ld=k * cin, d_ld=cout,
          nb0=1, nb1=N, a_bs=(0, Ls * cin), d_bs=(0, Ls * cout), bias=bias, act=act, slope=LEAKY_SLOPE,
-         ntaps=k, a_shift=(-(k - 1) * dil, dil))
+         ntaps=k, a_shift=(-(k - 1) * dil, dil), colmask=mask, colmask_scale=mscale)
     out = Var(y)
     if ctx.record:
         def bwd():
@@ -750,10 +782,13 @@ def causal_conv(ctx: Ctx, x: Var, prefix: str, N: int, Ls: int, cin: int, cout: 
             if dy is None:
                 return
             assert dy.is_contiguous()
-            if act != L.ACT_NONE:
-                dy = _act_bwd(ctx, out, dy, LEAKY_SLOPE)
-            L.check(ctx.lib.jmt_colsum(_ptr(dy), _DT[dy.dtype], cout, N * Ls, cout, _ptr(ctx.pgrad(prefix + "bias")), _stream()),
-                    "jmt_colsum")
+            # where a channel was dropped y = 0 and the masked dy is 0, so act'(y) of the post-dropout y is exact
+            if act != L.ACT_NONE or mask is not None:
+                dy = _act_bwd(ctx, out, dy, LEAKY_SLOPE if act != L.ACT_NONE else 1.0, colsum=ctx.pgrad(prefix + "bias"),
+                              mask=mask, mask_rows=Ls, mask_scale=mscale)
+            else:
+                L.check(ctx.lib.jmt_colsum(_ptr(dy), _DT[dy.dtype], cout, N * Ls, cout, _ptr(ctx.pgrad(prefix + "bias")),
+                                           _stream()), "jmt_colsum")
             # wgrad per tap: dW_j (Cout, Cin) = sum_n dy_n^T shift_j(x_n); reduction over (n, t)
             dw = ctx.zeros((cout, k * cin), torch.float32)
             tiles = ((cout + 127) // 128) * ((cin + 255) // 256)

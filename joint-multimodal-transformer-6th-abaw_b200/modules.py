@@ -580,10 +580,8 @@ def _tcn_graph(ctx, h, prefix, specs, N, Ls):
     (temporal_convolutional_model.py:54-57, 81-82)."""
     for i, (cin, cout, k, d, p, has_ds) in enumerate(specs):
         pre = f"{prefix}network.{i}."
-        y = E.causal_conv(ctx, h, pre + "conv1.", N, Ls, cin, cout, k, d, L.ACT_LEAKY)
-        y = E.channel_dropout(ctx, y, p, N, Ls, cout)
-        y = E.causal_conv(ctx, y, pre + "conv2.", N, Ls, cout, cout, k, d, L.ACT_LEAKY)
-        y = E.channel_dropout(ctx, y, p, N, Ls, cout)
+        y = E.causal_conv(ctx, h, pre + "conv1.", N, Ls, cin, cout, k, d, L.ACT_LEAKY, drop_p=p)
+        y = E.causal_conv(ctx, y, pre + "conv2.", N, Ls, cout, cout, k, d, L.ACT_LEAKY, drop_p=p)
         res = _conv1x1(ctx, h, pre + "downsample.") if has_ds else h
         h = E.add_act(ctx, y, res, L.ACT_LEAKY, E.LEAKY_SLOPE)
     return h

@@ -153,6 +153,33 @@ def test_gemm(case, precision):
                              f"bad cols {sorted(set(i[2] for i in bad.nonzero().tolist()))[:16]} frac {bad.float().mean().item():.3f}")
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("nb", [3, 4])
+def test_gemm_colmask(precision, nb):
+    """Channel dropout fused into the epilogue: D(m, n) = act(...) * (mask[b, n] ? scale : 0), both kernels,
+    1-CTA (odd batch) and CTA-pair-across-batch (even batch) tile schedules."""
+    torch.manual_seed(11)
+    dev = torch.device("cuda")
+    dt = torch.float32 if precision == "fp32" else torch.bfloat16
+    M, N, K, taps = 70, 160, 64, 3
+    x = (torch.randn(nb, M, K) * 0.5).to(dt)
+    w = (torch.randn(N, taps * K) * 0.5).to(dt)
+    bias = torch.randn(N)
+    mask = (torch.rand(nb, N) > 0.4).to(torch.uint8)
+    ref = _ref_gemm(x.float(), w.float()[None], a_major=0, b_major=0, M=M, N=N, K=K, ntaps=taps, a_shift=(-4, 2), b_shift=(0, 0),
+                    nb=nb, reduce_batch=False, alpha=1.0, bias=bias, act=L.ACT_LEAKY, slope=0.01)
+    ref = ref * (mask.double() * 1.6)[:, None, :]
+    xd, wd, md = x.to(dev), w.to(dev), mask.to(dev)
+    d = torch.empty(nb, M, N, device=dev, dtype=dt)
+    E.gemm(_ctx(precision), xd, wd, d, M=M, N=N, K=K, a_rows=M, b_rows=N, a_ld=K, b_ld=taps * K, d_ld=N, nb0=1, nb1=nb,
+           a_bs=(0, M * K), d_bs=(0, M * N), bias=bias.to(dev), act=L.ACT_LEAKY, slope=0.01, ntaps=taps, a_shift=(-4, 2),
+           colmask=md, colmask_scale=1.6)
+    torch.cuda.synchronize()
+    tol = 2e-4 if precision == "fp32" else 1.2e-2
+    assert (d.float().cpu().double() - ref).abs().max() < tol * (ref.abs().max() + 1e-6)
+    assert (d.float().cpu()[mask[:, None, :].expand(nb, M, N) == 0] == 0).all()
+
+
 def test_gemm_heads_geometry():
     """(b, head) batching through two batch dims with non-monotonic strides (Q of shape (B*T, 3E))."""
     torch.manual_seed(3)
@@ -202,10 +229,12 @@ def test_layernorm_l2norm_softmax(dt):
     dz = torch.empty(rows, D, device=dev, dtype=dt)
     dgam = torch.zeros(D, device=dev)
     dbet = torch.zeros(D, device=dev)
+    dzs = torch.zeros(D, device=dev)
     dy_d = dy.to(dev)
     L.check(lib.jmt_add_layernorm_bwd(E._ptr(dy_d), E._ptr(xd), E._ptr(rd), E._ptr(gd), E._ptr(mean), E._ptr(rstd), E._ptr(dz), 0,
-                                      E._ptr(dgam), E._ptr(dbet), rows, D, code, st), "lnb")
+                                      E._ptr(dgam), E._ptr(dbet), E._ptr(dzs), rows, D, code, st), "lnb")
     assert (dz.float().cpu().double() - z.grad).abs().max() < tol * 8
+    assert (dzs.cpu().double() - z.grad.sum(0)).abs().max() < tol * 40       # fused bias gradient of the residual Linear
     assert (dgam.cpu().double() - gg.grad).abs().max() < tol * 40
     assert (dbet.cpu().double() - bb.grad).abs().max() < tol * 40
     # l2norm
@@ -351,6 +380,24 @@ def test_small_kernels():
     a_d = a.to(dev)
     L.check(lib.jmt_colsum(E._ptr(a_d), L.BF16, 130, 1000, 130, E._ptr(out), st), "cs")
     assert (out.cpu() - a.float().sum(0)).abs().max() < 1e-3
+    # fused activation-gradient + channel-dropout replay + bias gradient
+    for dt, tol in ((torch.float32, 1e-4), (torch.bfloat16, 2e-2)):
+        nb, Lr, Cc = 3, 37, 136
+        dyf = torch.randn(nb * Lr, Cc).to(dt)
+        yf = torch.randn(nb * Lr, Cc).to(dt)
+        mk = (torch.rand(nb, Cc) > 0.3).to(torch.uint8)
+        want = dyf.float() * mk.float().repeat_interleave(Lr, 0) * 1.25 * torch.where(yf.float() > 0, 1.0, 0.01)
+        dy_d, y_d, mk_d = dyf.to(dev), yf.to(dev), mk.to(dev)
+        dx = torch.empty_like(dy_d)
+        cs = torch.zeros(Cc, device=dev)
+        L.check(lib.jmt_act_bwd_fused(E._ptr(dy_d), E._ptr(y_d), E._ptr(mk_d), E._ptr(dx), nb * Lr, Cc, Lr, 1.25, 0.01,
+                                      E._ptr(cs), L.F32 if dt == torch.float32 else L.BF16, st), "abf")
+        assert (dx.float().cpu() - want).abs().max() < tol
+        assert (cs.cpu() - want.sum(0)).abs().max() < 2e-3       # column sums are taken before the bf16 rounding of dx
+        dx2 = torch.empty_like(dy_d)
+        L.check(lib.jmt_act_bwd_fused(E._ptr(dy_d), E._ptr(y_d), None, E._ptr(dx2), nb * Lr, Cc, 1, 1.0, 0.0, None,
+                                      L.F32 if dt == torch.float32 else L.BF16, st), "abf")
+        assert (dx2.float().cpu() - dyf.float() * (yf.float() > 0)).abs().max() < tol
     # weight norm fwd/bwd
     cout, cin, k = 24, 40, 5
     g = torch.rand(cout, 1, 1) + 0.5
