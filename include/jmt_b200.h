@@ -114,6 +114,39 @@ int jmt_gemm_f32(const jmt_gemm_desc* g, void* stream);
 int jmt_gemm_set_profile_buffer(void* dev_buf);
 
 /* ------------------------------------------------------------------------------------------ *
+ * Fused attention core (bf16, tcgen05): two chained GEMMs with the row-wise softmax algebra between them.
+ *   mode 0 (forward):  X = P  = softmax(scale * A1 B1^T) (rows of A1 = queries, rows of B1 = keys);  D = X B2
+ *                      A1 = Q, B1 = K, B2 = V;  X (the probabilities) is also written to `x` for backward.
+ *   mode 1 (backward): X = dS = scale * P o (A1 B1^T - rowsum(P o A1 B1^T)) with P read from p_in;  D (+)= X B2
+ *                      A1 = dO, B1 = V, B2 = K  ->  D = dQ;  X (= dS) is written to `x` (dK = dS^T Q is a plain GEMM).
+ * Operand (r, k) of (head h, batch b) = ptr[b*bs + h*hs + r*ld + k], k < dh contiguous; X / p_in are
+ * (NB, heads, Lq, x_ld) contiguous bf16 with x_ld % 8 == 0.  Supported: dh in {64,128,256,512}, S <= 512 subject to
+ * shared memory (S <= 320 at dh = 512); jmt_attn_chain_supported() says whether a geometry is (the caller
+ * otherwise composes the same attention from jmt_gemm_bf16 + jmt_softmax_*).
+ * Replaces torch's MHA math path (bmm, softmax, bmm) at the nn.MultiheadAttention call sites
+ * mm_multi_transformers.py:62,142-167 and mm_transformers.py:76,125-134, forward and backward.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  const void* a1; const void* b1; const void* b2;   /* bf16 */
+  const void* p_in;                                  /* mode 1: saved probabilities; else NULL */
+  void* x;                                           /* out: P (mode 0) / dS (mode 1), bf16 */
+  void* d;                                           /* out: O (mode 0) / dQ (mode 1), bf16 */
+  int32_t mode;
+  int32_t Lq, S, dh, heads, NB;
+  int64_t a1_ld, a1_hs, a1_bs;
+  int64_t b1_ld, b1_hs, b1_bs;
+  int64_t b2_ld, b2_hs, b2_bs;
+  int64_t d_ld, d_hs, d_bs;
+  int64_t x_ld;
+  float scale;
+  int32_t store_mode;                                /* JMT_STORE / JMT_ACCUMULATE for D */
+} jmt_attn_desc;
+int jmt_attn_chain_supported(const jmt_attn_desc* g);   /* 1 / 0, no launch */
+int jmt_attn_chain_bf16(const jmt_attn_desc* g, void* stream);
+/* Debug aid: per-CTA cycle counters of the TMA / MMA / row-warp roles (148*16 uint64 device buffer; NULL disables). */
+int jmt_attn_set_profile_buffer(void* dev_buf);
+
+/* ------------------------------------------------------------------------------------------ *
  * Memory-bound fused row kernels (one warp per row, warp-shuffle reductions, 16-byte accesses).
  * `dtype` is the activation dtype of x/out tensors; statistics and parameters are fp32.
  * ------------------------------------------------------------------------------------------ */

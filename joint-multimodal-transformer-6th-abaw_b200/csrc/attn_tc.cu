@@ -1,0 +1,546 @@
+// jmt_attn_chain_bf16: fused attention core for sm_100a -- two chained tcgen05 GEMMs with the row-wise
+// softmax algebra in between, nothing but the bf16 probabilities ever leaves the SM.
+//
+//   forward  (mode 0):  T1 = Q K^T            -> P  = softmax(scale * T1)            -> O  = P V
+//   backward (mode 1):  T1 = dO V^T  (= dP)   -> dS = scale * P o (dP - rowsum(P o dP)) -> dQ (+)= dS K
+//
+// One CTA owns a 128-row query tile of one (batch, head):
+//   warp 0 (1 thread)  TMA producer: K-major A1/B1 k-blocks of GEMM1, then MN-major B2 k-blocks of GEMM2, 128B swizzle
+//   warp 1 (1 thread)  MMA issuer  : GEMM1 -> T1 (TMEM columns [0, S_pad)), then GEMM2 with A = X from shared memory
+//                                    -> T2 (TMEM columns [0, dh)); T1 is dead by then, so dh = 512 (one head) fits
+//   warps 2..9         row warps   : thread = TMEM lane = query row, the two warps of a lane quarter split the key
+//                                    columns; max / sum (or the P.dP dot) are in-thread reductions plus one shared-
+//                                    memory exchange; X (= P or dS, bf16) is written straight into the K-major
+//                                    128B-swizzled A-operand layout of GEMM2 and from there to global by TMA (saved
+//                                    P for backward / dS for the dK GEMM); finally the T2 epilogue (bf16, TMA store or
+//                                    reduce-add).
+// Replaces, per attention call, the QK^T GEMM + softmax kernel + PV GEMM (forward) and the dP GEMM + softmax-backward
+// kernel + dQ GEMM (backward) of torch's MHA math path (nn.MultiheadAttention call sites
+// mm_multi_transformers.py:62,142-167, mm_transformers.py:76,125-134): the fp32 scores (92 MB per attention at
+// B=256, T=300) are never materialised.
+#include "tc_common.cuh"
+
+namespace jmt {
+
+constexpr int kAtRowWarps = 8;
+constexpr int kAtThreads = 64 + 32 * kAtRowWarps;
+constexpr int kAtMaxSlots = 6;
+
+struct AtParams {
+  int mode;
+  int Lq, S, dh, heads, NB;
+  int q_tiles, total_tiles;
+  int nk1;              // GEMM1 k-blocks (dh / 64)
+  int nsplit1, n1;      // GEMM1: MMAs per k-step and N of each (T1 spans nsplit1 * n1 TMEM columns)
+  int nkx;              // 64-key chunks of X = GEMM2 k-blocks
+  int nh2, n2;          // GEMM2: N groups and N of each (dh = nh2 * n2)
+  int slots, slot_bytes, b1_bytes, b2_bytes, x_bytes;   // b1_bytes: ONE N-group of B1 (n1 rows)
+  uint32_t idesc1, idesc2;
+  float c_exp;          // scale * log2(e)
+  float scale;
+  const __nv_bfloat16* p_in;   // mode 1: saved probabilities (NB, heads, Lq, x_ld)
+  int64_t x_ld;
+  int store_mode;
+  FastDiv fd_qt, fd_heads;
+  unsigned long long* prof;   // optional per-CTA cycle counters (16 per CTA), jmt_attn_set_profile_buffer
+};
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float bf16lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf16hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
+
+struct AtTile { int q0, head, b; };
+__device__ __forceinline__ AtTile at_decode(const AtParams& p, int t) {
+  uint32_t bh, qt, b, head;
+  p.fd_qt.divmod((uint32_t)t, bh, qt);
+  p.fd_heads.divmod(bh, b, head);
+  AtTile r; r.q0 = (int)qt * kBlockM; r.head = (int)head; r.b = (int)b;
+  return r;
+}
+
+struct RowCtx {
+  uint32_t tb, xrow, sw;
+  int half, row, nch;
+};
+
+// 8 bf16 (one 16-byte piece) of a saved-probability row; zero outside the row / the padded pitch
+__device__ __forceinline__ uint4 ld_p8(const __nv_bfloat16* prow, bool row_ok, int col0, int64_t x_ld) {
+  return (row_ok && col0 < x_ld) ? __ldg(reinterpret_cast<const uint4*>(prow + col0)) : make_uint4(0, 0, 0, 0);
+}
+
+__device__ __forceinline__ float p_elem(const uint4 (&pv)[4], int i, int h) {
+  const uint32_t w = h < 2 ? pv[i].x : (h < 4 ? pv[i].y : (h < 6 ? pv[i].z : pv[i].w));
+  return (h & 1) ? bf16hi(w) : bf16lo(w);
+}
+
+// pass 1 on one 32-key chunk: four independent partial maxima (MODE 0) / partial P.dP dots (MODE 1)
+template <int MODE>
+__device__ __forceinline__ void row_pass1(const uint32_t (&r)[32], const uint4 (&pv)[4], int nvalid, float (&acc)[4]) {
+  if (nvalid >= 32) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int h = 0; h < 8; ++h) {
+        const float v = __uint_as_float(r[i * 8 + h]);
+        if (MODE == 0) acc[h & 3] = fmaxf(acc[h & 3], v);
+        else acc[h & 3] = fmaf(p_elem(pv, i, h), v, acc[h & 3]);
+      }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int h = 0; h < 8; ++h) {
+        const float v = __uint_as_float(r[i * 8 + h]);
+        const bool ok = i * 8 + h < nvalid;
+        if (MODE == 0) acc[h & 3] = ok ? fmaxf(acc[h & 3], v) : acc[h & 3];
+        else acc[h & 3] = ok ? fmaf(p_elem(pv, i, h), v, acc[h & 3]) : acc[h & 3];
+      }
+  }
+}
+
+// pass 2 on one 32-key chunk: X = exp2(T1 * c - shift) (MODE 0) | scale * P * (T1 - shift) (MODE 1) -> bf16 -> swizzled X
+template <int MODE>
+__device__ __forceinline__ void row_pass2(const AtParams& p, const uint32_t (&r)[32], const uint4 (&pv)[4], int nvalid, float shift,
+                                          uint32_t xbase, uint32_t piece0, uint32_t sw, float (&sum)[4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float x[8];
+#pragma unroll
+    for (int h = 0; h < 8; ++h) {
+      const float v = __uint_as_float(r[i * 8 + h]);
+      float y;
+      if (MODE == 0) y = ex2_approx(fmaf(v, p.c_exp, -shift));
+      else y = p.scale * p_elem(pv, i, h) * (v - shift);
+      x[h] = (nvalid >= 32 || i * 8 + h < nvalid) ? y : 0.f;
+      if (MODE == 0) sum[h & 3] += x[h];
+    }
+    st_shared_v4(xbase + (((piece0 + (uint32_t)i) ^ sw) << 4), pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]),
+                 pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
+  }
+}
+
+// The row-wise algebra between the two GEMMs for one thread (= one query row, every other 32-key chunk):
+//   MODE 0: X = softmax(scale * T1) (max exchange, exp2, sum exchange, in-place normalisation)
+//   MODE 1: X = scale * P o (T1 - rowsum(P o T1))  with P from global memory (dot exchange)
+// X goes to shared memory as bf16 in the 128B-swizzled K-major A-operand layout of GEMM2.  The TMEM (and global P)
+// loads of chunk i+1 are in flight while chunk i is processed (two register buffers).
+template <int MODE>
+__device__ __forceinline__ void row_op(const AtParams& p, const RowCtx& rc, const AtTile& c, int grow, float* red) {
+  const int half = rc.half, row = rc.row, nch = rc.nch;
+  const bool row_ok = grow < p.Lq;
+  const __nv_bfloat16* prow = nullptr;
+  if (MODE == 1) prow = p.p_in + ((((int64_t)c.b * p.heads + c.head) * p.Lq + grow) * p.x_ld);
+  uint32_t ra[32], rb[32];
+  uint4 pa[4], pb[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { pa[i] = make_uint4(0, 0, 0, 0); pb[i] = make_uint4(0, 0, 0, 0); }
+#define AT_LOAD(R, P, CH)                                                                    \
+  {                                                                                          \
+    tc_ld32_issue(rc.tb + (CH) * 32, R);                                                     \
+    if (MODE == 1) {                                                                         \
+      _Pragma("unroll") for (int i_ = 0; i_ < 4; ++i_) P[i_] = ld_p8(prow, row_ok, (CH) * 32 + i_ * 8, p.x_ld); \
+    }                                                                                        \
+  }
+  // ---- pass 1
+  float acc[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) acc[i] = MODE == 0 ? -INFINITY : 0.f;
+  if (half < nch) AT_LOAD(ra, pa, half);
+  for (int ch = half; ch < nch; ch += 4) {
+    tc_wait_ld();
+    if (ch + 2 < nch) AT_LOAD(rb, pb, ch + 2);
+    row_pass1<MODE>(ra, pa, p.S - ch * 32, acc);
+    if (ch + 2 >= nch) break;
+    tc_wait_ld();
+    if (ch + 4 < nch) AT_LOAD(ra, pa, ch + 4);
+    row_pass1<MODE>(rb, pb, p.S - (ch + 2) * 32, acc);
+  }
+  red[half * 128 + row] = MODE == 0 ? fmaxf(fmaxf(acc[0], acc[1]), fmaxf(acc[2], acc[3])) : (acc[0] + acc[1]) + (acc[2] + acc[3]);
+  __syncwarp();
+  if (half < nch) AT_LOAD(ra, pa, half);           // pass 2's first chunk is in flight across the barrier (T1 is read-only here)
+  asm volatile("bar.sync 1, %0;" ::"n"(32 * kAtRowWarps) : "memory");      // (also: every warp's X / staging stores have drained)
+  const float shift = MODE == 0 ? fmaxf(red[row], red[128 + row]) * p.c_exp : red[row] + red[128 + row];
+  // ---- pass 2
+  float sum[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int ch = half; ch < nch; ch += 4) {
+    tc_wait_ld();
+    if (ch + 2 < nch) AT_LOAD(rb, pb, ch + 2);
+    row_pass2<MODE>(p, ra, pa, p.S - ch * 32, shift, rc.xrow + (ch >> 1) * 16384, (uint32_t)((ch & 1) * 4), rc.sw, sum);
+    if (ch + 2 >= nch) break;
+    tc_wait_ld();
+    if (ch + 4 < nch) AT_LOAD(ra, pa, ch + 4);
+    row_pass2<MODE>(p, rb, pb, p.S - (ch + 2) * 32, shift, rc.xrow + ((ch + 2) >> 1) * 16384, (uint32_t)((ch & 1) * 4), rc.sw, sum);
+  }
+#undef AT_LOAD
+  if (half == 0) {                               // zero the key columns [32 * nch, 64 * nkx) nobody computes
+    for (int pc = nch * 4; pc < p.nkx * 8; ++pc)
+      st_shared_v4(rc.xrow + (pc >> 3) * 16384 + ((((uint32_t)(pc & 7)) ^ rc.sw) << 4), 0u, 0u, 0u, 0u);
+  }
+  if (MODE == 0) {
+    // ---- pass 3: normalise this thread's pieces in place by 1 / rowsum
+    red[256 + half * 128 + row] = (sum[0] + sum[1]) + (sum[2] + sum[3]);
+    __syncwarp();
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * kAtRowWarps) : "memory");
+    const float inv = 1.f / (red[256 + row] + red[256 + 128 + row]);
+    for (int ch = half; ch < nch; ch += 2) {
+      const uint32_t xbase = rc.xrow + (ch >> 1) * 16384;
+      uint4 v[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] = ld_shared_v4(xbase + ((((uint32_t)((ch & 1) * 4 + i)) ^ rc.sw) << 4));
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        st_shared_v4(xbase + ((((uint32_t)((ch & 1) * 4 + i)) ^ rc.sw) << 4),
+                     pack_bf16(bf16lo(v[i].x) * inv, bf16hi(v[i].x) * inv), pack_bf16(bf16lo(v[i].y) * inv, bf16hi(v[i].y) * inv),
+                     pack_bf16(bf16lo(v[i].z) * inv, bf16hi(v[i].z) * inv), pack_bf16(bf16lo(v[i].w) * inv, bf16hi(v[i].w) * inv));
+    }
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kAtThreads, 1)
+attn_chain_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ CUtensorMap map_b1,
+                  const __grid_constant__ CUtensorMap map_b2, const __grid_constant__ CUtensorMap map_x,
+                  const __grid_constant__ CUtensorMap map_d, const AtParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // The kernel has no static shared memory, so the dynamic window starts 1024-byte aligned (after the driver's
+  // reserved 1 KiB); the 2-slot configuration at S = 300, dh = 512 has no room for alignment slack.  Fail loudly if not.
+  const uint32_t base = smem_u32(smem_raw);
+  if ((base & 1023u) != 0u) __trap();
+  const uint32_t sX = base;                                       // nkx chunks of [128 rows x 128 B]
+  const uint32_t sStage = sX;                                      // 8 x 4 KiB epilogue staging aliases X (dead after GEMM2)
+  const uint32_t sRing = sX + p.x_bytes;
+  const uint32_t sRed = sRing + p.slots * p.slot_bytes;            // 2 x [2][128] floats
+  const uint32_t bars = sRed + 2048;
+  const uint32_t full_bar = bars, empty_bar = bars + 8 * kAtMaxSlots;
+  const uint32_t t1_full = bars + 16 * kAtMaxSlots, x_ready = t1_full + 8, t2_full = t1_full + 16, t_empty = t1_full + 24;
+  const uint32_t tmem_slot = t1_full + 32;
+  uint8_t* smem_aligned = smem_raw + (base - smem_u32(smem_raw));
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_aligned + (tmem_slot - base));
+  float* red = reinterpret_cast<float*>(smem_aligned + (sRed - base));     // [0..255] max / dot, [256..511] sum
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.slots; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
+    mbar_init(t1_full, 1); mbar_init(t2_full, 1);
+    mbar_init(x_ready, kAtRowWarps); mbar_init(t_empty, kAtRowWarps);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ================================ TMA producer ================================
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a1)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b1)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b2)) : "memory");
+      int slot = 0; uint32_t phase = 0;
+      long long pw = 0; const long long pt0 = p.prof ? clock64() : 0;
+      const int b2_chunks = p.n2 >> 6;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const AtTile c = at_decode(p, t);
+        for (int kb = 0; kb < p.nk1; ++kb) {                  // GEMM1 operands: A1 [128 x 64] + B1 group 0, then B1 group 1
+          for (int s = 0; s < p.nsplit1; ++s) {
+
+            const long long tw = p.prof ? clock64() : 0;
+            mbar_wait(empty_bar + 8 * slot, phase ^ 1);
+            if (p.prof) pw += clock64() - tw;
+            const uint32_t fb = full_bar + 8 * slot;
+            const uint32_t dst = sRing + slot * p.slot_bytes;
+            if (s == 0) {
+              mbar_expect_tx(fb, 16384 + p.b1_bytes);
+              tma_load_4d(dst, &map_a1, fb, kb * kBlockK, c.q0, c.head, c.b);
+              tma_load_4d(dst + 16384, &map_b1, fb, kb * kBlockK, 0, c.head, c.b);
+            } else {
+              mbar_expect_tx(fb, p.b1_bytes);
+              tma_load_4d(dst, &map_b1, fb, kb * kBlockK, p.n1, c.head, c.b);
+            }
+            if (++slot == p.slots) { slot = 0; phase ^= 1; }
+          }
+        }
+        for (int nh = 0; nh < p.nh2; ++nh)                    // GEMM2 operand: B2 [64 keys x n2] (MN-major chunks)
+          for (int kb = 0; kb < p.nkx; ++kb) {
+            const long long tw = p.prof ? clock64() : 0;
+            mbar_wait(empty_bar + 8 * slot, phase ^ 1);
+            if (p.prof) pw += clock64() - tw;
+            const uint32_t fb = full_bar + 8 * slot;
+            const uint32_t dst = sRing + slot * p.slot_bytes;
+            mbar_expect_tx(fb, p.b2_bytes);
+            tma_load_5d(dst, &map_b2, fb, 0, kb * kBlockK, nh * b2_chunks, c.head, c.b);     // all n2 / 64 chunks in one instruction
+            if (++slot == p.slots) { slot = 0; phase ^= 1; }
+          }
+      }
+      if (p.prof) { p.prof[blockIdx.x * 16 + 0] = pw; p.prof[blockIdx.x * 16 + 1] = clock64() - pt0; }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ================================ MMA issuer ================================
+      int slot = 0; uint32_t phase = 0;
+      int tile_iter = 0;
+      long long mw1 = 0, mw2 = 0, mwx = 0, mwe = 0; const long long mt0 = p.prof ? clock64() : 0;
+#define AT_TIMED_WAIT(acc, bar, ph) { const long long tw_ = p.prof ? clock64() : 0; mbar_wait(bar, ph); if (p.prof) acc += clock64() - tw_; }
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tile_iter) {
+        const uint32_t par = tile_iter & 1;
+        AT_TIMED_WAIT(mwe, t_empty, par ^ 1);                 // previous tile's T2 has been drained
+        tc_fence_after();
+        for (int kb = 0; kb < p.nk1; ++kb) {                  // GEMM1: T1 = A1 B1^T, one stage per N group of B1
+          AT_TIMED_WAIT(mw1, full_bar + 8 * slot, phase);
+          tc_fence_after();
+          const int slot_a = slot;
+          const uint32_t st = sRing + slot * p.slot_bytes;
+          const uint64_t a_desc = make_smem_desc(st, 16, 1024);
+          const uint64_t b_desc = make_smem_desc(st + 16384, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k)
+            tc_mma<1>(tmem_base, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), p.idesc1, (kb > 0 || k > 0) ? 1u : 0u);
+          if (++slot == p.slots) { slot = 0; phase ^= 1; }
+          if (p.nsplit1 == 2) {
+            AT_TIMED_WAIT(mw1, full_bar + 8 * slot, phase);
+            tc_fence_after();
+            const uint64_t b2_desc = make_smem_desc(sRing + slot * p.slot_bytes, 16, 1024);
+#pragma unroll
+            for (int k = 0; k < kBlockK / kUmmaK; ++k)
+              tc_mma<1>(tmem_base + p.n1, a_desc + (uint64_t)(k * 2), b2_desc + (uint64_t)(k * 2), p.idesc1, (kb > 0 || k > 0) ? 1u : 0u);
+            tc_commit<1>(empty_bar + 8 * slot_a);             // the A tile is shared by both groups: freed only now
+            tc_commit<1>(empty_bar + 8 * slot);
+            if (++slot == p.slots) { slot = 0; phase ^= 1; }
+          } else {
+            tc_commit<1>(empty_bar + 8 * slot_a);
+          }
+        }
+        tc_commit<1>(t1_full);
+        AT_TIMED_WAIT(mwx, x_ready, par);                     // X (P or dS) is in shared memory, T1 is dead
+        tc_fence_after();
+        for (int nh = 0; nh < p.nh2; ++nh)                    // GEMM2: T2[:, nh] = X B2[:, nh]
+          for (int kb = 0; kb < p.nkx; ++kb) {
+            AT_TIMED_WAIT(mw2, full_bar + 8 * slot, phase);
+            tc_fence_after();
+            const uint64_t a_desc = make_smem_desc(sX + kb * 16384, 16, 1024);
+            const uint64_t b_desc = make_smem_desc(sRing + slot * p.slot_bytes, 8192, 1024);
+#pragma unroll
+            for (int k = 0; k < kBlockK / kUmmaK; ++k)
+              tc_mma<1>(tmem_base + nh * p.n2, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 128), p.idesc2,
+                        (kb > 0 || k > 0) ? 1u : 0u);
+            tc_commit<1>(empty_bar + 8 * slot);
+            if (++slot == p.slots) { slot = 0; phase ^= 1; }
+          }
+        tc_commit<1>(t2_full);
+      }
+      if (p.prof) {
+        unsigned long long* o = p.prof + blockIdx.x * 16;
+        o[2] = mw1; o[3] = mw2; o[4] = mwx; o[5] = mwe; o[6] = clock64() - mt0;
+      }
+    }
+  } else {
+    // ================================ row warps (2..9) ================================
+    const int q = warp & 3;                        // TMEM lane quarter
+    const int ew = warp - 2;
+    const int half = ew >> 2;                      // which interleaved set of column chunks this warp owns
+    const int row = q * 32 + lane;                 // row inside the 128-row query tile
+    const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t sw = lane & 7;
+    const uint32_t xrow = sX + row * 128;          // this row inside X chunk 0 (chunk kc: + kc * 16384)
+    const uint32_t stage = sStage + ew * 4096;
+    const int nch = (p.S + 31) >> 5;               // 32-column chunks that contain valid keys
+    long long rw1 = 0, rrow = 0, rw2 = 0, repi = 0; const long long rt0 = p.prof ? clock64() : 0;
+    int tile_iter = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tile_iter) {
+      const AtTile c = at_decode(p, t);
+      const uint32_t par = tile_iter & 1;
+      const int grow = c.q0 + row;
+      const long long ra = p.prof ? clock64() : 0;
+      mbar_wait(t1_full, par);
+      __syncwarp();
+      tc_fence_after();
+      const long long rb = p.prof ? clock64() : 0;
+      RowCtx rc;
+      rc.tb = tb; rc.xrow = xrow; rc.sw = sw; rc.half = half; rc.row = row; rc.nch = nch;
+      if (lane == 0) bulk_wait_read0();              // this warp's / the X stores of the previous tile have finished reading X
+      row_op<MODE>(p, rc, c, grow, red);
+      fence_async_smem();                            // X visible to the tensor core / TMA (async proxy)
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(x_ready);
+      if (ew == 0 && lane == 0) {
+        // saved probabilities (forward) / dS (backward): X chunks -> global, clipped to (S, Lq) by the tensor map
+        mbar_wait(x_ready, par);
+        for (int kc = 0; kc < p.nkx; ++kc) tma_store_4d(&map_x, sX + kc * 16384, kc * 64, c.q0, c.head, c.b);
+        bulk_commit();
+      }
+      // ---- T2 epilogue: O (store) / dQ (reduce-add), bf16
+      const long long rcx = p.prof ? clock64() : 0;
+      mbar_wait(t2_full, par);                       // GEMM2 has consumed X: its first 32 KiB become the epilogue staging
+      if (ew == 0 && lane == 0) bulk_wait_read0();   // ... once the X -> global stores have finished reading it too
+      __syncwarp();                                  // (lane 0 of warp 2 rejoins after issuing the X stores)
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * kAtRowWarps) : "memory");
+      tc_fence_after();
+      const long long rd = p.prof ? clock64() : 0;
+      const bool rows_valid = c.q0 + q * 32 < p.Lq;        // warp-uniform
+      {
+        uint32_t r0[32], r1[32];
+        int buf = 0;
+        int c0 = half * 64;
+        if (c0 < p.dh) { tc_ld32_issue(tb + c0, r0); tc_ld32_issue(tb + c0 + 32, r1); }
+        for (; c0 < p.dh; c0 += 128, buf ^= 1) {
+          const uint32_t stg = stage + buf * (kAtRowWarps * 4096);     // two staging tiles per warp: store i overlaps chunk i+1
+          const uint32_t stg_row = stg + lane * 128;
+          if (lane == 0) bulk_wait_read1();          // the store issued two chunks ago has finished reading this buffer
+          __syncwarp();
+          tc_wait_ld();
+          uint32_t pk[32];
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            pk[j >> 1] = pack_bf16(__uint_as_float(r0[j]), __uint_as_float(r0[j + 1]));
+            pk[16 + (j >> 1)] = pack_bf16(__uint_as_float(r1[j]), __uint_as_float(r1[j + 1]));
+          }
+          if (c0 + 128 < p.dh) { tc_ld32_issue(tb + c0 + 128, r0); tc_ld32_issue(tb + c0 + 160, r1); }   // next chunk in flight
+#pragma unroll
+          for (int pc = 0; pc < 8; ++pc)
+            st_shared_v4(stg_row + ((((uint32_t)pc) ^ sw) << 4), pk[4 * pc], pk[4 * pc + 1], pk[4 * pc + 2], pk[4 * pc + 3]);
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0 && rows_valid) {
+            if (p.store_mode == JMT_STORE) tma_store_4d(&map_d, stg, c0, c.q0 + q * 32, c.head, c.b);
+            else tma_reduce_add_4d(&map_d, stg, c0, c.q0 + q * 32, c.head, c.b);
+          }
+          if (lane == 0) bulk_commit();              // (possibly empty group: keeps the wait_group.read 1 accounting uniform)
+        }
+        tc_wait_ld();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(t_empty);
+      if (p.prof) { const long long re = clock64(); rw1 += rb - ra; rrow += rcx - rb; rw2 += rd - rcx; repi += re - rd; }
+    }
+    if (p.prof && ew == 0 && lane == 0) {
+      unsigned long long* o = p.prof + blockIdx.x * 16;
+      o[7] = rw1; o[8] = rrow; o[9] = rw2; o[10] = repi; o[11] = clock64() - rt0;
+    }
+    if (lane == 0) bulk_wait0();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
+// geometry shared by the support query and the launcher
+static int at_plan(const jmt_attn_desc* g, AtParams* p, int* smem_bytes) {
+  memset(p, 0, sizeof(*p));
+  if (g->dh < 64 || g->dh > 512 || (g->dh & (g->dh - 1)) != 0) return 0;      // 64, 128, 256, 512
+  if (g->S < 1 || g->S > 512 || g->Lq < 1 || g->heads < 1 || g->NB < 1) return 0;
+  p->mode = g->mode; p->Lq = g->Lq; p->S = g->S; p->dh = g->dh; p->heads = g->heads; p->NB = g->NB;
+  p->q_tiles = (g->Lq + kBlockM - 1) / kBlockM;
+  const int64_t total = (int64_t)p->q_tiles * g->heads * g->NB;
+  if (total >= (1ll << 31)) return 0;
+  p->total_tiles = (int)total;
+  p->nk1 = g->dh / 64;
+  const int s16 = (g->S + 15) / 16 * 16;
+  if (s16 <= 256) { p->nsplit1 = 1; p->n1 = s16; }
+  else { p->nsplit1 = 2; p->n1 = (g->S + 31) / 32 * 16; }
+  p->nkx = (g->S + 63) / 64;
+  p->n2 = g->dh > 256 ? 256 : g->dh;
+  p->nh2 = g->dh / p->n2;
+  p->b1_bytes = p->n1 * 128;
+  p->b2_bytes = p->n2 * 128;
+  int slot = 16384 + p->b1_bytes;
+  if (p->b2_bytes > slot) slot = p->b2_bytes;
+  p->slot_bytes = (slot + 1023) / 1024 * 1024;
+  p->x_bytes = p->nkx * 16384;
+  if (p->x_bytes < 2 * kAtRowWarps * 4096) p->x_bytes = 2 * kAtRowWarps * 4096;   // the epilogue staging (2 tiles per warp) aliases X
+  const int fixed = p->x_bytes + 2048 + 256;
+  const int avail = 227 * 1024 - fixed;
+  int slots = avail / p->slot_bytes;
+  if (slots < 2) return 0;
+  if (slots > kAtMaxSlots) slots = kAtMaxSlots;
+  p->slots = slots;
+  *smem_bytes = fixed + slots * p->slot_bytes;
+  p->idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p->n1 >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+  p->idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(p->n2 >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+  p->scale = g->scale;
+  p->c_exp = g->scale * 1.4426950408889634f;
+  p->p_in = (const __nv_bfloat16*)g->p_in;
+  p->x_ld = g->x_ld;
+  p->store_mode = g->store_mode;
+  p->fd_qt.init(p->q_tiles);
+  p->fd_heads.init(g->heads);
+  return 1;
+}
+
+}  // namespace jmt
+
+using namespace jmt;
+
+static std::atomic<unsigned long long*> g_attn_prof{nullptr};
+extern "C" int jmt_attn_set_profile_buffer(void* dev_buf) {
+  g_attn_prof.store((unsigned long long*)dev_buf);
+  return JMT_OK;
+}
+
+extern "C" int jmt_attn_chain_supported(const jmt_attn_desc* g) {
+  if (!g) return 0;
+  AtParams p; int smem = 0;
+  if (!at_plan(g, &p, &smem)) return 0;
+  if (g->x_ld % 8 != 0 || g->x_ld < g->S) return 0;
+  return 1;
+}
+
+extern "C" int jmt_attn_chain_bf16(const jmt_attn_desc* g, void* stream) {
+  JMT_REQUIRE(g && g->a1 && g->b1 && g->b2 && g->x && g->d, "jmt_attn_chain_bf16: null pointer");
+  JMT_REQUIRE(g->mode == 0 || (g->mode == 1 && g->p_in), "jmt_attn_chain_bf16: mode 1 needs the saved probabilities");
+  JMT_REQUIRE(g->store_mode == JMT_STORE || g->store_mode == JMT_ACCUMULATE, "jmt_attn_chain_bf16: bad store_mode");
+  AtParams p; int smem = 0;
+  if (!at_plan(g, &p, &smem) || g->x_ld % 8 != 0 || g->x_ld < g->S) {
+    set_error("jmt_attn_chain_bf16: unsupported geometry (dh=%d S=%d Lq=%d x_ld=%lld): use the unfused path", g->dh, g->S, g->Lq,
+              (long long)g->x_ld);
+    return JMT_ERR_UNSUPPORTED;
+  }
+  p.prof = g_attn_prof.load();
+  CUtensorMap ma1, mb1, mb2, mx, md;
+  int rc = make_map(&ma1, g->a1, g->dh, g->Lq, g->a1_ld, g->heads, g->a1_hs, g->NB, g->a1_bs, kBlockM, "jmt_attn_chain_bf16(A1)");
+  if (rc != JMT_OK) return rc;
+  rc = make_map(&mb1, g->b1, g->dh, g->S, g->b1_ld, g->heads, g->b1_hs, g->NB, g->b1_bs, p.n1, "jmt_attn_chain_bf16(B1)");
+  if (rc != JMT_OK) return rc;
+  rc = make_map_mn5(&mb2, g->b2, g->dh, g->S, g->b2_ld, g->heads, g->b2_hs, g->NB, g->b2_bs, kBlockK, p.n2 / 64, "jmt_attn_chain_bf16(B2)");
+  if (rc != JMT_OK) return rc;
+  rc = make_map(&mx, g->x, g->S, g->Lq, g->x_ld, g->heads, (int64_t)g->Lq * g->x_ld, g->NB, (int64_t)g->heads * g->Lq * g->x_ld, kBlockM,
+                "jmt_attn_chain_bf16(X)");
+  if (rc != JMT_OK) return rc;
+  JMT_REQUIRE((reinterpret_cast<uintptr_t>(g->d) & 15) == 0 && g->d_ld % 8 == 0 && g->d_hs % 8 == 0 && g->d_bs % 8 == 0,
+              "jmt_attn_chain_bf16: D geometry must be 16-byte aligned");
+  rc = make_map_d(&md, g->d, JMT_BF16, g->dh, g->Lq, g->d_ld, g->heads, g->d_hs, g->NB, g->d_bs, "jmt_attn_chain_bf16(D)");
+  if (rc != JMT_OK) return rc;
+  static std::atomic<int> attr_set[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); set_error("jmt_attn_chain_bf16: no CUDA device"); return JMT_ERR_CUDA; }
+  if (!attr_set[dev & 63].load(std::memory_order_acquire)) {
+    cudaError_t e = cudaFuncSetAttribute(attn_chain_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_chain_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) { set_error("jmt_attn_chain_bf16: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); cudaGetLastError(); return JMT_ERR_CUDA; }
+    attr_set[dev & 63].store(1, std::memory_order_release);
+  }
+  const int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
+  if (p.mode == 0) attn_chain_kernel<0><<<grid, kAtThreads, smem, (cudaStream_t)stream>>>(ma1, mb1, mb2, mx, md, p);
+  else attn_chain_kernel<1><<<grid, kAtThreads, smem, (cudaStream_t)stream>>>(ma1, mb1, mb2, mx, md, p);
+  return check_launch("attn_chain_kernel");
+}

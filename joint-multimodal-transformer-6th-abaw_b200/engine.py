@@ -484,11 +484,48 @@ def _proj_grad(ctx: Ctx, v: Var) -> torch.Tensor:
     return v.gbuf.t
 
 
+FUSED_ATTENTION = True      # bf16 mode: use jmt_attn_chain_bf16 when the geometry is supported (else GEMM + softmax kernels)
+FUSED_ATTENTION_BWD = False  # the fused backward (dP -> dS -> dQ) is correct but not yet faster than GEMM + softmax_bwd + GEMM
+
+
+def _attn_chain(ctx: Ctx, mode: int, a1, a1_geo, b1, b1_geo, b2, b2_geo, p_in, x, d, d_geo, Lq, S, dh, heads, NB, x_ld,
+                scale, store, probe_only=False):
+    """One launch of the fused attention core (include/jmt_b200.h: jmt_attn_desc).  *_geo = (ld, head stride,
+    batch stride) in elements."""
+    g = L.AttnDesc()
+    g.a1, g.b1, g.b2 = a1.data_ptr(), b1.data_ptr(), b2.data_ptr()
+    g.p_in = p_in.data_ptr() if p_in is not None else None
+    g.x, g.d = x.data_ptr(), d.data_ptr()
+    g.mode = mode
+    g.Lq, g.S, g.dh, g.heads, g.NB = Lq, S, dh, heads, NB
+    g.a1_ld, g.a1_hs, g.a1_bs = a1_geo
+    g.b1_ld, g.b1_hs, g.b1_bs = b1_geo
+    g.b2_ld, g.b2_hs, g.b2_bs = b2_geo
+    g.d_ld, g.d_hs, g.d_bs = d_geo
+    g.x_ld = x_ld
+    g.scale = scale
+    g.store_mode = store
+    if probe_only:
+        return bool(ctx.lib.jmt_attn_chain_supported(C.byref(g)))
+    prof = PROFILE
+    if prof is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    L.check(ctx.lib.jmt_attn_chain_bf16(C.byref(g), _stream()), "jmt_attn_chain_bf16")
+    if prof is not None:
+        e1.record()
+        prof.append(("attn_chain_kernel", 4.0 * NB * heads * Lq * S * dh, e0, e1, (Lq, S, dh, NB * heads, mode)))
+    return True
+
+
 def attention_core(ctx: Ctx, q: Var, qcol: int, k: Var, kcol: int, v: Var, vcol: int, E: int, heads: int,
                    gq: AttnGeom, gk: AttnGeom) -> Var:
     """softmax((Q/sqrt(dh)) K^T) V per (batch, head) -- torch's MHA math path minus the
     head-averaged weights the reference discards.  q/k/v are column slices [col, col+E) of projection
-    matrices; the output (rows_q, E) is laid out like q's rows."""
+    matrices; the output (rows_q, E) is laid out like q's rows.
+    bf16 mode: one fused kernel forward (QK^T -> softmax -> PV, scores never leave the SM) and one backward
+    (dP -> dS -> dQ) plus two plain GEMMs (dV = P^T dO, dK = dS^T Q); fp32 mode / unsupported geometry: GEMM and
+    softmax kernels."""
     dh = E // heads
     Lq, S, NB = gq.seq, gk.seq, gq.batch
     assert gk.batch == NB and E % heads == 0
@@ -497,18 +534,30 @@ def attention_core(ctx: Ctx, q: Var, qcol: int, k: Var, kcol: int, v: Var, vcol:
     qd, kd, vd = q.data[:, qcol:qcol + E], k.data[:, kcol:kcol + E], v.data[:, vcol:vcol + E]
     qld, kld, vld = q.data.stride(0), k.data.stride(0), v.data.stride(0)
     sb = (Lq * s_ld, heads * Lq * s_ld)
-    scores = ctx.empty((NB, heads, Lq, s_ld), torch.float32)
-    gemm(ctx, qd, kd, scores, M=Lq, N=S, K=dh, a_rows=Lq, b_rows=S,
-         a_ld=gq.seq_stride * qld, b_ld=gk.seq_stride * kld, d_ld=s_ld,
-         nb0=heads, nb1=NB, a_bs=(dh, gq.batch_stride * qld), b_bs=(dh, gk.batch_stride * kld), d_bs=sb, alpha=scale)
-    probs = ctx.empty((NB, heads, Lq, s_ld))
-    rows = NB * heads * Lq
-    L.check(ctx.lib.jmt_softmax_fwd(_ptr(scores), s_ld, _ptr(probs), ctx.acode, s_ld, rows, S, _stream()), "jmt_softmax_fwd")
-    del scores
+    q_geo = (gq.seq_stride * qld, dh, gq.batch_stride * qld)
+    k_geo = (gk.seq_stride * kld, dh, gk.batch_stride * kld)
+    v_geo = (gk.seq_stride * vld, dh, gk.batch_stride * vld)
+    o_geo = (gq.seq_stride * E, dh, gq.batch_stride * E)
     o = ctx.empty((q.data.shape[0], E))
-    gemm(ctx, probs, vd, o, M=Lq, N=dh, K=S, a_rows=Lq, b_major=L.MAJOR_MN, b_rows=S,
-         a_ld=s_ld, b_ld=gk.seq_stride * vld, d_ld=gq.seq_stride * E,
-         nb0=heads, nb1=NB, a_bs=sb, b_bs=(dh, gk.batch_stride * vld), d_bs=(dh, gq.batch_stride * E))
+    fused = False
+    if FUSED_ATTENTION and ctx.adt == torch.bfloat16:
+        fused = _attn_chain(ctx, 0, qd, q_geo, kd, k_geo, vd, v_geo, None, o, o, o_geo, Lq, S, dh, heads, NB, s_ld, scale,
+                            L.STORE, probe_only=True)
+    if fused:
+        probs = ctx.empty((NB, heads, Lq, s_ld))
+        _attn_chain(ctx, 0, qd, q_geo, kd, k_geo, vd, v_geo, None, probs, o, o_geo, Lq, S, dh, heads, NB, s_ld, scale, L.STORE)
+    else:
+        scores = ctx.empty((NB, heads, Lq, s_ld), torch.float32)
+        gemm(ctx, qd, kd, scores, M=Lq, N=S, K=dh, a_rows=Lq, b_rows=S,
+             a_ld=gq.seq_stride * qld, b_ld=gk.seq_stride * kld, d_ld=s_ld,
+             nb0=heads, nb1=NB, a_bs=(dh, gq.batch_stride * qld), b_bs=(dh, gk.batch_stride * kld), d_bs=sb, alpha=scale)
+        probs = ctx.empty((NB, heads, Lq, s_ld))
+        rows = NB * heads * Lq
+        L.check(ctx.lib.jmt_softmax_fwd(_ptr(scores), s_ld, _ptr(probs), ctx.acode, s_ld, rows, S, _stream()), "jmt_softmax_fwd")
+        del scores
+        gemm(ctx, probs, vd, o, M=Lq, N=dh, K=S, a_rows=Lq, b_major=L.MAJOR_MN, b_rows=S,
+             a_ld=s_ld, b_ld=gk.seq_stride * vld, d_ld=gq.seq_stride * E,
+             nb0=heads, nb1=NB, a_bs=sb, b_bs=(dh, gk.batch_stride * vld), d_bs=(dh, gq.batch_stride * E))
     out = Var(o)
     if ctx.record:
         def bwd():
@@ -516,29 +565,38 @@ def attention_core(ctx: Ctx, q: Var, qcol: int, k: Var, kcol: int, v: Var, vcol:
             if do is None:
                 return
             assert do.is_contiguous()
-            dp = ctx.empty((NB, heads, Lq, s_ld), torch.float32)          # dP = dO V^T
-            gemm(ctx, do, vd, dp, M=Lq, N=S, K=dh, a_rows=Lq, b_rows=S,
-                 a_ld=gq.seq_stride * E, b_ld=gk.seq_stride * vld, d_ld=s_ld,
-                 nb0=heads, nb1=NB, a_bs=(dh, gq.batch_stride * E), b_bs=(dh, gk.batch_stride * vld), d_bs=sb)
+            rows = NB * heads * Lq
+            gq_ = _proj_grad(ctx, q)
+            dq_geo = (gq.seq_stride * gq_.stride(0), dh, gq.batch_stride * gq_.stride(0))
             ds = ctx.empty((NB, heads, Lq, s_ld))
-            L.check(ctx.lib.jmt_softmax_bwd(_ptr(probs), ctx.acode, s_ld, _ptr(dp), s_ld, _ptr(ds), ctx.acode, s_ld,
-                                            rows, S, _stream()), "jmt_softmax_bwd")
-            del dp
+            if fused and FUSED_ATTENTION_BWD:
+                # dP = dO V^T -> dS = scale * P o (dP - rowsum(P o dP)) -> dQ += dS K, one kernel; dS is saved for dK
+                _attn_chain(ctx, 1, do, o_geo, vd, v_geo, kd, k_geo, probs, ds, gq_[:, qcol:qcol + E], dq_geo, Lq, S, dh,
+                            heads, NB, s_ld, scale, L.ACCUMULATE)
+                dk_alpha = 1.0
+            else:
+                dp = ctx.empty((NB, heads, Lq, s_ld), torch.float32)          # dP = dO V^T
+                gemm(ctx, do, vd, dp, M=Lq, N=S, K=dh, a_rows=Lq, b_rows=S,
+                     a_ld=gq.seq_stride * E, b_ld=gk.seq_stride * vld, d_ld=s_ld,
+                     nb0=heads, nb1=NB, a_bs=(dh, gq.batch_stride * E), b_bs=(dh, gk.batch_stride * vld), d_bs=sb)
+                L.check(ctx.lib.jmt_softmax_bwd(_ptr(probs), ctx.acode, s_ld, _ptr(dp), s_ld, _ptr(ds), ctx.acode, s_ld,
+                                                rows, S, _stream()), "jmt_softmax_bwd")
+                del dp
+                gemm(ctx, ds, kd, gq_[:, qcol:qcol + E], M=Lq, N=dh, K=S, a_rows=Lq, b_major=L.MAJOR_MN, b_rows=S,
+                     a_ld=s_ld, b_ld=gk.seq_stride * kld, d_ld=gq.seq_stride * gq_.stride(0),
+                     nb0=heads, nb1=NB, a_bs=sb, b_bs=(dh, gk.batch_stride * kld), d_bs=(dh, gq.batch_stride * gq_.stride(0)),
+                     alpha=scale, store=L.ACCUMULATE)                          # dQ = scale * dS K
+                dk_alpha = scale
             gv = _proj_grad(ctx, v)                                        # dV = P^T dO
             gemm(ctx, probs, do, gv[:, vcol:vcol + E], M=S, N=dh, K=Lq, a_major=L.MAJOR_MN, b_major=L.MAJOR_MN,
                  a_rows=Lq, b_rows=Lq, a_ld=s_ld, b_ld=gq.seq_stride * E, d_ld=gk.seq_stride * gv.stride(0),
                  nb0=heads, nb1=NB, a_bs=sb, b_bs=(dh, gq.batch_stride * E), d_bs=(dh, gk.batch_stride * gv.stride(0)),
                  store=L.ACCUMULATE)
-            gq_ = _proj_grad(ctx, q)                                       # dQ = scale * dS K
-            gemm(ctx, ds, kd, gq_[:, qcol:qcol + E], M=Lq, N=dh, K=S, a_rows=Lq, b_major=L.MAJOR_MN, b_rows=S,
-                 a_ld=s_ld, b_ld=gk.seq_stride * kld, d_ld=gq.seq_stride * gq_.stride(0),
-                 nb0=heads, nb1=NB, a_bs=sb, b_bs=(dh, gk.batch_stride * kld), d_bs=(dh, gq.batch_stride * gq_.stride(0)),
-                 alpha=scale, store=L.ACCUMULATE)
             gk_ = _proj_grad(ctx, k)                                       # dK = scale * dS^T Q
             gemm(ctx, ds, qd, gk_[:, kcol:kcol + E], M=S, N=dh, K=Lq, a_major=L.MAJOR_MN, b_major=L.MAJOR_MN,
                  a_rows=Lq, b_rows=Lq, a_ld=s_ld, b_ld=gq.seq_stride * qld, d_ld=gk.seq_stride * gk_.stride(0),
                  nb0=heads, nb1=NB, a_bs=sb, b_bs=(dh, gq.batch_stride * qld), d_bs=(dh, gk.batch_stride * gk_.stride(0)),
-                 alpha=scale, store=L.ACCUMULATE)
+                 alpha=dk_alpha, store=L.ACCUMULATE)
             ctx.release(out)
         ctx.tape.append(bwd)
     return out

@@ -201,6 +201,83 @@ def test_gemm_heads_geometry():
         assert (got - ref).abs().max() < tol * ref.abs().max(), precision
 
 
+ATTN_CASES = [
+    # name, NB, heads, Lq, S, E, cross (separate kv tensor), batch_major (attention across the batch dim)
+    ("t300_h1", 3, 1, 300, 300, 512, False, False),
+    ("t70_s40_h4", 2, 4, 70, 40, 512, True, False),
+    ("t9_h2", 2, 2, 9, 9, 512, False, False),
+    ("t130_s77_h8", 2, 8, 130, 77, 512, True, False),
+    ("t260_h2_e256", 2, 2, 260, 260, 256, False, False),
+    ("batchdim_h2", 5, 2, 37, 37, 512, False, True),
+]
+
+
+@pytest.mark.parametrize("fused", [True, False])
+@pytest.mark.parametrize("case", ATTN_CASES, ids=[c[0] for c in ATTN_CASES])
+def test_attention_core_bf16(case, fused):
+    """softmax(QK^T/sqrt(dh))V forward + dQ/dK/dV through engine.attention_core in bf16 mode: the fused tcgen05
+    kernel (jmt_attn_chain_bf16) and the GEMM + softmax composition against an fp64 reference on the same
+    bf16-rounded operands."""
+    name, NB, h, Lq, S, E_, cross, batch_major = case
+    torch.manual_seed(len(name) * 7 + NB)
+    dev = torch.device("cuda")
+    dh = E_ // h
+    ctx = _ctx("bf16")
+    ctx.record = True
+    old = (E.FUSED_ATTENTION, E.FUSED_ATTENTION_BWD)
+    E.FUSED_ATTENTION = E.FUSED_ATTENTION_BWD = fused
+    try:
+        # projection matrices as the engine holds them: rows = batch*seq (or seq*batch for the batch-major geometry)
+        qm = (torch.randn(NB * Lq, 3 * E_) * 0.7).to(torch.bfloat16)
+        km = (torch.randn(NB * S, 2 * E_) * 0.7).to(torch.bfloat16) if cross else None
+        if batch_major:       # row = s * NB + n: "sequence" index has stride NB, batch stride 1
+            gq = E.AttnGeom(Lq, NB, NB, 1)
+            gk = E.AttnGeom(S, NB, NB, 1)
+            to4 = lambda m, L_, w: m.float().view(L_, NB, w).permute(1, 0, 2)     # noqa: E731  (NB, L, w)
+        else:
+            gq = E.AttnGeom(Lq, NB, 1, Lq)
+            gk = E.AttnGeom(S, NB, 1, S)
+            to4 = lambda m, L_, w: m.float().view(NB, L_, w)                      # noqa: E731
+        qv = E.Var(qm.to(dev))
+        if cross:
+            kv = E.Var(km.to(dev))
+            out = E.attention_core(ctx, qv, 0, kv, 0, kv, E_, E_, h, gq, gk)
+            q4, k4, v4 = to4(qm, Lq, 3 * E_)[..., :E_], to4(km, S, 2 * E_)[..., :E_], to4(km, S, 2 * E_)[..., E_:]
+        else:
+            out = E.attention_core(ctx, qv, 0, qv, E_, qv, 2 * E_, E_, h, gq, gk)
+            a4 = to4(qm, Lq, 3 * E_)
+            q4, k4, v4 = a4[..., :E_], a4[..., E_:2 * E_], a4[..., 2 * E_:]
+        q64 = q4.double().reshape(NB, Lq, h, dh).permute(0, 2, 1, 3).clone().requires_grad_(True)
+        k64 = k4.double().reshape(NB, S, h, dh).permute(0, 2, 1, 3).clone().requires_grad_(True)
+        v64 = v4.double().reshape(NB, S, h, dh).permute(0, 2, 1, 3).clone().requires_grad_(True)
+        ref = torch.softmax(q64 @ k64.transpose(-1, -2) / math.sqrt(dh), -1) @ v64          # (NB, h, Lq, dh)
+        do = (torch.randn(NB * Lq, E_) * 0.5).to(torch.bfloat16)
+        do4 = to4(do, Lq, E_).double().reshape(NB, Lq, h, dh).permute(0, 2, 1, 3)
+        ref.backward(do4)
+        torch.cuda.synchronize()
+        got = to4(out.data.cpu(), Lq, E_).double().reshape(NB, Lq, h, dh).permute(0, 2, 1, 3)
+        assert (got - ref.detach()).abs().max() < 2e-2 * ref.detach().abs().max(), (got - ref.detach()).abs().max()
+        out.gbuf = E.GradBuf(do.to(dev))
+        ctx.backward()
+        torch.cuda.synchronize()
+
+        def back(g4, L_):      # (NB, h, L, dh) -> (NB, L, E)
+            return g4.permute(0, 2, 1, 3).reshape(NB, L_, E_)
+        gqm = to4(qv.grad.cpu(), Lq, 3 * E_).double()
+        want_q = back(q64.grad, Lq)
+        assert (gqm[..., :E_] - want_q).abs().max() < 3e-2 * want_q.abs().max(), "dQ"
+        if cross:
+            gkm = to4(kv.grad.cpu(), S, 2 * E_).double()
+            gk_got, gv_got = gkm[..., :E_], gkm[..., E_:]
+        else:
+            gk_got, gv_got = gqm[..., E_:2 * E_], gqm[..., 2 * E_:]
+        want_k, want_v = back(k64.grad, S), back(v64.grad, S)
+        assert (gk_got - want_k).abs().max() < 3e-2 * want_k.abs().max(), "dK"
+        assert (gv_got - want_v).abs().max() < 3e-2 * want_v.abs().max(), "dV"
+    finally:
+        E.FUSED_ATTENTION, E.FUSED_ATTENTION_BWD = old
+
+
 @pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
 def test_layernorm_l2norm_softmax(dt):
     torch.manual_seed(0)
