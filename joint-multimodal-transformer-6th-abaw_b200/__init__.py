@@ -13,3 +13,4 @@ from .losses import CCCLoss, CCCLossMasked, LiveCCCLoss  # noqa: F401
 from . import cccmetric  # noqa: F401
 from . import padseq  # noqa: F401
 from . import dist  # noqa: F401
+from .graphs import GraphedStep  # noqa: F401

@@ -39,6 +39,7 @@ struct TcParams {
   int a_major, b_major;
   int a_shift0, a_shift_step, b_shift0, b_shift_step;
   int b_has_b0, b_has_b1;
+  int a_mn5, b_mn5;    // MN-major operand tile fetched by ONE 5-D TMA instruction (all its 64-wide chunks) instead of one per chunk
   int reduce_batch;
   uint32_t idesc;
   int b_stage_bytes, b_tx_bytes, b_chunks_cta, stages;
@@ -302,12 +303,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             mbar_expect_tx(fb, kAStageBytes + p.b_tx_bytes);
             if (p.a_major == JMT_MAJOR_K) {
               tma_load_4d(a_dst, &tma_a, fb, kb * kBlockK, c.m0 + ash, b0, b1);
+            } else if (p.a_mn5) {
+              tma_load_5d(a_dst, &tma_a, fb, 0, kb * kBlockK + ash, c.m0 >> 6, b0, b1);
             } else {
               tma_load_4d(a_dst, &tma_a, fb, c.m0, kb * kBlockK + ash, b0, b1);
               tma_load_4d(a_dst + 8192, &tma_a, fb, c.m0 + 64, kb * kBlockK + ash, b0, b1);
             }
             if (p.b_major == JMT_MAJOR_K) {
               tma_load_4d(b_dst, &tma_b, fb, tap * p.K + kb * kBlockK, c.n0, bb0, bb1);
+            } else if (p.b_mn5) {
+              tma_load_5d(b_dst, &tma_b, fb, 0, kb * kBlockK + bsh, c.n0 >> 6, bb0, bb1);
             } else {
               for (int ch = 0; ch < b_chunks; ++ch)
                 tma_load_4d(b_dst + ch * 8192, &tma_b, fb, c.n0 + ch * 64, kb * kBlockK + bsh, bb0, bb1);
@@ -317,12 +322,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             mbar_expect_tx_cluster(fb, kAStageBytes + p.b_tx_bytes);
             if (p.a_major == JMT_MAJOR_K) {
               tma_load_4d_2sm(a_dst, &tma_a, fb, kb * kBlockK, c.m0 + ash, b0, b1);
+            } else if (p.a_mn5) {
+              tma_load_5d_2sm(a_dst, &tma_a, fb, 0, kb * kBlockK + ash, c.m0 >> 6, b0, b1);
             } else {
               tma_load_4d_2sm(a_dst, &tma_a, fb, c.m0, kb * kBlockK + ash, b0, b1);
               tma_load_4d_2sm(a_dst + 8192, &tma_a, fb, c.m0 + 64, kb * kBlockK + ash, b0, b1);
             }
             if (p.b_major == JMT_MAJOR_K) {
               tma_load_4d_2sm(b_dst, &tma_b, fb, tap * p.K + kb * kBlockK, c.n0 + n_off, bb0, bb1);
+            } else if (p.b_mn5) {
+              tma_load_5d_2sm(b_dst, &tma_b, fb, 0, kb * kBlockK + bsh, (c.n0 + n_off) >> 6, bb0, bb1);
             } else {
               for (int ch = 0; ch < b_chunks; ++ch)
                 tma_load_4d_2sm(b_dst + ch * 8192, &tma_b, fb, c.n0 + n_off + ch * 64, kb * kBlockK + bsh, bb0, bb1);
@@ -537,16 +546,23 @@ extern "C" int jmt_gemm_bf16(const jmt_gemm_desc* g, void* stream) {
               (g->d_bs0 * es) % 16 == 0 && (g->d_bs1 * es) % 16 == 0) ? 1 : 0;
 
   CUtensorMap map_a, map_b;
-  // A: K-major -> (K, a_rows) box {64,128}; MN-major -> (M, a_rows = k extent) box {64,64}
+  // A: K-major -> (K, a_rows) box {64,128}; MN-major -> (M, a_rows = k extent): both 64-wide chunks of the 128-row tile in one
+  // 5-D box when M % 64 == 0, else two 4-D {64,64} boxes
+  p.a_mn5 = (g->a_major == JMT_MAJOR_MN && g->M % 64 == 0) ? 1 : 0;
   if (g->a_major == JMT_MAJOR_K)
     rc = make_map(&map_a, g->a, g->K, g->a_rows, g->a_ld, g->nb0, g->a_bs0, g->nb1, g->a_bs1, kBlockM, "jmt_gemm_bf16(A)");
+  else if (p.a_mn5)
+    rc = make_map_mn5(&map_a, g->a, g->M, g->a_rows, g->a_ld, g->nb0, g->a_bs0, g->nb1, g->a_bs1, kBlockK, 2, "jmt_gemm_bf16(A)");
   else
     rc = make_map(&map_a, g->a, g->M, g->a_rows, g->a_ld, g->nb0, g->a_bs0, g->nb1, g->a_bs1, kBlockK, "jmt_gemm_bf16(A)");
   if (rc != JMT_OK) return rc;
   const int bnb0 = p.b_has_b0 ? g->nb0 : 1, bnb1 = p.b_has_b1 ? g->nb1 : 1;
+  p.b_mn5 = (g->b_major == JMT_MAJOR_MN && g->N % 64 == 0 && p.block_n % 64 == 0 && b_cols_cta % 64 == 0) ? 1 : 0;
   if (g->b_major == JMT_MAJOR_K)
     rc = make_map(&map_b, g->b, (int64_t)g->ntaps * g->K, g->b_rows, g->b_ld, bnb0, g->b_bs0, bnb1, g->b_bs1,
                   b_cols_cta /* each CTA of a pair stages half of the tile's rows */, "jmt_gemm_bf16(B)");
+  else if (p.b_mn5)
+    rc = make_map_mn5(&map_b, g->b, g->N, g->b_rows, g->b_ld, bnb0, g->b_bs0, bnb1, g->b_bs1, kBlockK, p.b_chunks_cta, "jmt_gemm_bf16(B)");
   else
     rc = make_map(&map_b, g->b, g->N, g->b_rows, g->b_ld, bnb0, g->b_bs0, bnb1, g->b_bs1, kBlockK, "jmt_gemm_bf16(B)");
   if (rc != JMT_OK) return rc;
