@@ -153,6 +153,8 @@ class ClockSampler(threading.Thread):
 # --------------------------------------------------------------------------------------- GPU arm
 def main():
     args = parse()
+    import signal
+    signal.alarm(1500)            # a wedged collective / teardown must end the process, not the GPU box's time limit
     if args.impl == "reference":
         run_reference(args)
         return
@@ -361,9 +363,20 @@ def main():
                 "roofline": roof, "cpu_baseline": cpu, "final_loss": final_loss,
                 "launch_mode": "cuda_graph" if graphed is not None else "eager", "host_enqueue_ms_per_eager_step": host_enqueue_ms,
                 "model_tflops": 3 * FWD_GFLOP_PER_WINDOW * value / 1e3}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
+    # Teardown: captured graphs hold NCCL kernels; destroying the process group under them hung a 2-GPU run once
+    # (after the JSON line was out).  Drop the graphs, drain the device, meet at a barrier and leave without the
+    # NCCL destructor -- the OS reclaims the communicators.
+    if graphed is not None:
+        graphed.graphs.clear()
+        graphed.losses.clear()
+    torch.cuda.synchronize()
     if world > 1:
-        dist.destroy_process_group()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":
