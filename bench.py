@@ -315,8 +315,21 @@ def main():
         att = [r for r in rec if r[0] == "attn_chain_kernel"]
         att_ms = sum(r[2].elapsed_time(r[3]) for r in att)
         att_fl = sum(r[1] for r in att)
+        # DRAM traffic of the dominant kernel's most frequent launch (76800x512x512 linear, 40 of 191 launches per step)
+        # from the committed `ncu --set full` capture; algorithmic bytes of that launch = A + W + D = 157.8 MB
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, "profiles", "ncu_gemm_tc_r1g_linear_76800x512x512.csv")
+        if kname == "gemm_tc_kernel" and os.path.exists(tpath):
+            import csv
+            rows = {r[0]: r for r in csv.reader(open(tpath)) if len(r) == 3}
+            mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            try:
+                traffic = sum(float(rows[k][2]) * mult[rows[k][1]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+                traffic_src = "profiles/ncu_gemm_tc_r1g_linear_76800x512x512.csv (dram read+write of one 76800x512x512 launch; algorithmic 157.8e6 B)"
+            except (KeyError, ValueError):
+                traffic = None
         roof = {"bound": "tensor", "kernel": kname, "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                "frac": ach / peak, "traffic": None,
+                "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s sustained (of fallback)",
                 "launches_per_step": len(sel) // nprof, "gemm_ms_per_step": tot_ms / nprof,
                 "gemm_gflop_per_step": tot_fl / nprof / 1e9,

@@ -1,0 +1,21 @@
+"""Compact per-kernel summary (key metrics only) from an `ncu --page raw --csv` export."""
+import csv, sys
+KEYS = ["gpu__time_duration.sum", "gpc__cycles_elapsed.avg.per_second", "sm__cycles_elapsed.max", "launch__grid_size", "launch__block_size",
+        "launch__cluster_size", "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+        "sm__ops_path_tensor_op_utchmma_src_bf16_dst_fp32_sparsity_off.avg.pct_of_peak_sustained_elapsed",
+        "sm__inst_executed_pipe_tmem.avg.pct_of_peak_sustained_active", "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+        "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "l1tex__m_xbar2l1tex_read_bytes.sum",
+        "l1tex__m_xbar2l1tex_read_bytes.sum.per_second", "lts__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct",
+        "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__bytes_read.sum.per_second", "dram__bytes_write.sum.per_second",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"]
+rows = list(csv.reader(open(sys.argv[1])))
+hdr, units, vals = rows[0], rows[1], rows[2]
+d = dict(zip(hdr, zip(units, vals)))
+w = csv.writer(sys.stdout)
+w.writerow(["metric", "unit", "value"])
+w.writerow(["Kernel Name", "", d.get("Kernel Name", ("", ""))[1]])
+for k in KEYS:
+    if k in d:
+        w.writerow([k, d[k][0], d[k][1]])
