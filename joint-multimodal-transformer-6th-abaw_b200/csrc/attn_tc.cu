@@ -136,18 +136,17 @@ __device__ __forceinline__ void row_pass2(const AtParams& p, const uint32_t (&r)
 template <int MODE>
 __device__ __forceinline__ void row_op(const AtParams& p, const RowCtx& rc, const AtTile& c, int grow, float* red) {
   const int half = rc.half, row = rc.row, nch = rc.nch;
-  const bool row_ok = grow < p.Lq;
-  const __nv_bfloat16* prow = nullptr;
-  if (MODE == 1) prow = p.p_in + ((((int64_t)c.b * p.heads + c.head) * p.Lq + grow) * p.x_ld);
   uint32_t ra[32], rb[32];
   uint4 pa[4], pb[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) { pa[i] = make_uint4(0, 0, 0, 0); pb[i] = make_uint4(0, 0, 0, 0); }
+  // MODE 1: the P tile was staged into X (same swizzled layout dS will overwrite) before GEMM1 finished
 #define AT_LOAD(R, P, CH)                                                                    \
   {                                                                                          \
     tc_ld32_issue(rc.tb + (CH) * 32, R);                                                     \
     if (MODE == 1) {                                                                         \
-      _Pragma("unroll") for (int i_ = 0; i_ < 4; ++i_) P[i_] = ld_p8(prow, row_ok, (CH) * 32 + i_ * 8, p.x_ld); \
+      _Pragma("unroll") for (int i_ = 0; i_ < 4; ++i_)                                       \
+        P[i_] = ld_shared_v4(rc.xrow + ((CH) >> 1) * 16384 + ((((uint32_t)(((CH) & 1) * 4 + i_)) ^ rc.sw) << 4)); \
     }                                                                                        \
   }
   // ---- pass 1
@@ -209,7 +208,7 @@ template <int MODE>
 __global__ void __launch_bounds__(kAtThreads, 1)
 attn_chain_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ CUtensorMap map_b1,
                   const __grid_constant__ CUtensorMap map_b2, const __grid_constant__ CUtensorMap map_x,
-                  const __grid_constant__ CUtensorMap map_d, const AtParams p) {
+                  const __grid_constant__ CUtensorMap map_d, const __grid_constant__ CUtensorMap map_p, const AtParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // The kernel has no static shared memory, so the dynamic window starts 1024-byte aligned (after the driver's
   // reserved 1 KiB); the 2-slot configuration at S = 300, dh = 512 has no room for alignment slack.  Fail loudly if not.
@@ -222,7 +221,8 @@ attn_chain_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
   const uint32_t bars = sRed + 2048;
   const uint32_t full_bar = bars, empty_bar = bars + 8 * kAtMaxSlots;
   const uint32_t t1_full = bars + 16 * kAtMaxSlots, x_ready = t1_full + 8, t2_full = t1_full + 16, t_empty = t1_full + 24;
-  const uint32_t tmem_slot = t1_full + 32;
+  const uint32_t p_full = t1_full + 32;
+  const uint32_t tmem_slot = t1_full + 40;
   uint8_t* smem_aligned = smem_raw + (base - smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_aligned + (tmem_slot - base));
   float* red = reinterpret_cast<float*>(smem_aligned + (sRed - base));     // [0..255] max / dot, [256..511] sum
@@ -231,7 +231,7 @@ attn_chain_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.slots; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
-    mbar_init(t1_full, 1); mbar_init(t2_full, 1);
+    mbar_init(t1_full, 1); mbar_init(t2_full, 1); mbar_init(p_full, 1);
     mbar_init(x_ready, kAtRowWarps); mbar_init(t_empty, kAtRowWarps);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -365,8 +365,22 @@ attn_chain_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
       const AtTile c = at_decode(p, t);
       const uint32_t par = tile_iter & 1;
       const int grow = c.q0 + row;
+      if (MODE == 1) {
+        // Stage the saved probabilities of this tile into X by TMA while GEMM1 (dP = dO V^T) runs: same 128B-swizzled
+        // chunk layout that dS will overwrite in place.  X is free: GEMM2 of the previous tile has completed (its
+        // t2_full was consumed) and, after this barrier, every warp's TMA stores out of X / the staging tiles have
+        // finished reading it.
+        if (lane == 0) bulk_wait_read0();
+        __syncwarp();
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kAtRowWarps) : "memory");
+        if (ew == 0 && lane == 0) {
+          mbar_expect_tx(p_full, p.nkx * 16384);
+          for (int kc = 0; kc < p.nkx; ++kc) tma_load_4d(sX + kc * 16384, &map_p, p_full, kc * 64, c.q0, c.head, c.b);
+        }
+      }
       const long long ra = p.prof ? clock64() : 0;
       mbar_wait(t1_full, par);
+      if (MODE == 1) mbar_wait(p_full, par);         // the P tile has landed in X
       __syncwarp();
       tc_fence_after();
       const long long rb = p.prof ? clock64() : 0;
@@ -540,7 +554,13 @@ extern "C" int jmt_attn_chain_bf16(const jmt_attn_desc* g, void* stream) {
     attr_set[dev & 63].store(1, std::memory_order_release);
   }
   const int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
-  if (p.mode == 0) attn_chain_kernel<0><<<grid, kAtThreads, smem, (cudaStream_t)stream>>>(ma1, mb1, mb2, mx, md, p);
-  else attn_chain_kernel<1><<<grid, kAtThreads, smem, (cudaStream_t)stream>>>(ma1, mb1, mb2, mx, md, p);
+  CUtensorMap mp = mx;          // mode 1: the saved probabilities, same geometry as X
+  if (p.mode == 1) {
+    rc = make_map(&mp, g->p_in, g->S, g->Lq, g->x_ld, g->heads, (int64_t)g->Lq * g->x_ld, g->NB, (int64_t)g->heads * g->Lq * g->x_ld, kBlockM,
+                  "jmt_attn_chain_bf16(P)");
+    if (rc != JMT_OK) return rc;
+  }
+  if (p.mode == 0) attn_chain_kernel<0><<<grid, kAtThreads, smem, (cudaStream_t)stream>>>(ma1, mb1, mb2, mx, md, mp, p);
+  else attn_chain_kernel<1><<<grid, kAtThreads, smem, (cudaStream_t)stream>>>(ma1, mb1, mb2, mx, md, mp, p);
   return check_launch("attn_chain_kernel");
 }

@@ -268,6 +268,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   if constexpr (kCta == 2) cluster_sync_all();   // peer barriers are initialised before any remote arrive / complete_tx
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  // Everything above (barrier init, TMEM allocation, cluster handshake) touched no global memory, so under programmatic
+  // dependent launch it overlaps the tail of the previous kernel in the stream; from here on its results are needed.
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -596,13 +600,16 @@ extern "C" int jmt_gemm_bf16(const jmt_gemm_desc* g, void* stream) {
   cfg.blockDim = dim3(kTcThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = (cudaStream_t)stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = p.cluster;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  static const bool pdl = []() { const char* e = getenv("JMT_PDL"); return e ? atoi(e) != 0 : true; }();
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl ? 2 : 1;
   cudaError_t le;
   if (p.colmask) le = p.cluster == 2 ? cudaLaunchKernelEx(&cfg, gemm_tc_kernel<2, true>, map_a, map_b, map_d, p)
                                      : cudaLaunchKernelEx(&cfg, gemm_tc_kernel<1, true>, map_a, map_b, map_d, p);
