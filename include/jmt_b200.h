@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define JMT_ABI_VERSION 2
+#define JMT_ABI_VERSION 3
 
 typedef enum {
   JMT_OK = 0,
@@ -105,6 +105,14 @@ typedef struct {
    * Needs reduce_batch == 0 and split_k == 1. */
   const uint8_t* colmask;
   float colmask_scale;
+  /* Flat TCN layout (all sequences stacked in ONE (N*(pad+L), C) matrix, `pad` zero rows in front of every sequence =
+   * the causal left padding of the next conv and the right padding of the previous sequence's dgrad, so a 128-row tile
+   * is never 56 % empty as with M = L = 300 per batch entry):
+   *   colmask_row_period > 0: the keep-mask row is  m / colmask_row_period  instead of the batch index (nb0 = nb1 = 1);
+   *   zero_row_period > 0:    output rows with (m % zero_row_period) < zero_row_count contribute zeros (stored as 0 /
+   *                           nothing added): the padding rows must stay zero for the next layer. */
+  int32_t colmask_row_period;
+  int32_t zero_row_period, zero_row_count;
 } jmt_gemm_desc;
 
 int jmt_gemm_bf16(const jmt_gemm_desc* g, void* stream);
@@ -223,6 +231,12 @@ int jmt_copy2d(const void* in, int in_dtype, int64_t in_ld, void* out, int out_d
 /* batched transpose of the two inner dims with cast: in (nb, R, C) -> out (nb, C, R)
  * ((N,C,L) <-> channels-last (N,L,C) at the TCN boundary, I3DWSDDA.py:44) */
 int jmt_transpose(const void* in, int in_dtype, void* out, int out_dtype, int64_t nb, int R, int C, void* stream);
+/* same with explicit batch strides in elements (0 = dense R*C): scatters into / gathers from the flat padded TCN layout */
+int jmt_transpose_strided(const void* in, int in_dtype, int64_t in_bs, void* out, int out_dtype, int64_t out_bs, int64_t nb,
+                          int R, int C, void* stream);
+/* out[b*out_bs + r*cols + c] = cast(in[b*in_bs + r*cols + c])  (nb, rows, cols) blocks: pad / unpad of the flat layout */
+int jmt_copy_rows3d(const void* in, int in_dtype, int64_t in_bs, void* out, int out_dtype, int64_t out_bs, int64_t nb,
+                    int64_t rows, int cols, void* stream);
 /* out = LeakyReLU(a + b)  (TemporalBlock.forward, temporal_convolutional_model.py:54-57) */
 int jmt_add_act(const void* a, const void* b, void* out, int64_t n, int act, float slope, int dtype, void* stream);
 /* channel dropout (nn.Dropout2d on (N,C,L)) / element dropout with an explicit

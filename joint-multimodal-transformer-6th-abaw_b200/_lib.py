@@ -33,6 +33,7 @@ class GemmDesc(C.Structure):
         ("b_shift0", C.c_int32), ("b_shift_step", C.c_int32),
         ("reduce_batch", C.c_int32), ("split_k", C.c_int32),
         ("colmask", C.c_void_p), ("colmask_scale", C.c_float),
+        ("colmask_row_period", C.c_int32), ("zero_row_period", C.c_int32), ("zero_row_count", C.c_int32),
     ]
 
 
@@ -79,6 +80,8 @@ SIGNATURES = {
     "jmt_axpy": [_P, _P, _F, _L, _I, _P],
     "jmt_copy2d": [_P, _I, _L, _P, _I, _L, _L, _I, _P],
     "jmt_transpose": [_P, _I, _P, _I, _L, _I, _I, _P],
+    "jmt_transpose_strided": [_P, _I, _L, _P, _I, _L, _L, _I, _I, _P],
+    "jmt_copy_rows3d": [_P, _I, _L, _P, _I, _L, _L, _L, _I, _P],
     "jmt_add_act": [_P, _P, _P, _L, _I, _F, _I, _P],
     "jmt_apply_mask": [_P, _P, _P, _L, _I, _I, _I, _F, _I, _P],
     "jmt_dropout_mask": [_P, _L, _F, _U64, _U64, _P],
@@ -108,7 +111,7 @@ def lib():
             fn = getattr(h, name)           # AttributeError if a declared symbol is not exported
             fn.argtypes = argtypes
             fn.restype = _RESTYPES.get(name, C.c_int)
-        if h.jmt_abi_version() != 2:
+        if h.jmt_abi_version() != 3:
             raise RuntimeError("libjmt_b200.so ABI version mismatch")
         _lib = h
     return _lib

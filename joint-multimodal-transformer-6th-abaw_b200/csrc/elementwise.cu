@@ -69,16 +69,36 @@ copy2d_kernel(const TI* __restrict__ in, int64_t in_ld, TO* __restrict__ out, in
   }
 }
 
+// per batch b (blockIdx.y): out[b*out_bs + i] = cast(in[b*in_bs + i]), i < per
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(kEwThreads)
+copy_rows3d_kernel(const TI* __restrict__ in, int64_t in_bs, TO* __restrict__ out, int64_t out_bs, int64_t per, int vec) {
+  const TI* ib = in + (int64_t)blockIdx.y * in_bs;
+  TO* ob = out + (int64_t)blockIdx.y * out_bs;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nt = (int64_t)gridDim.x * blockDim.x;
+  if (vec) {
+    for (int64_t i = tid; i < per / 8; i += nt) {
+      Vec8<TI> v; v.load(ib + i * 8);
+      Vec8<TO> o;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o.v[k] = v.v[k];
+      o.store(ob + i * 8);
+    }
+  } else {
+    for (int64_t i = tid; i < per; i += nt) ob[i] = from_f32<TO>(to_f32(ib[i]));
+  }
+}
+
 // (nb, R, C) -> (nb, C, R) through a padded 32x32 shared tile (coalesced both ways)
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(256)
-transpose_kernel(const TI* __restrict__ in, TO* __restrict__ out, int R, int C) {
+transpose_kernel(const TI* __restrict__ in, TO* __restrict__ out, int R, int C, int64_t in_bs, int64_t out_bs) {
   __shared__ float tile[32][33];
   const int64_t b = blockIdx.z;
   const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const TI* ib = in + b * (int64_t)R * C;
-  TO* ob = out + b * (int64_t)R * C;
+  const TI* ib = in + b * in_bs;
+  TO* ob = out + b * out_bs;
   for (int i = ty; i < 32; i += 8) {
     const int r = r0 + i, c = c0 + tx;
     tile[i][tx] = (r < R && c < C) ? to_f32(ib[(int64_t)r * C + c]) : 0.f;
@@ -423,14 +443,36 @@ extern "C" int jmt_cast(const void* in, int in_dtype, void* out, int out_dtype, 
   return jmt_copy2d(in, in_dtype, n, out, out_dtype, n, 1, (int)n, stream);
 }
 
-extern "C" int jmt_transpose(const void* in, int in_dtype, void* out, int out_dtype, int64_t nb, int R, int C, void* stream) {
+extern "C" int jmt_transpose_strided(const void* in, int in_dtype, int64_t in_bs, void* out, int out_dtype, int64_t out_bs, int64_t nb,
+                                     int R, int C, void* stream) {
   JMT_REQUIRE(in && out && nb >= 0 && R >= 0 && C >= 0 && nb < 65536, "jmt_transpose: bad arguments");
   if (nb * R * C == 0) return JMT_OK;
+  if (in_bs == 0) in_bs = (int64_t)R * C;
+  if (out_bs == 0) out_bs = (int64_t)R * C;
   dim3 grid((C + 31) / 32, (R + 31) / 32, (unsigned)nb);
   cudaStream_t st = (cudaStream_t)stream;
   JMT_DISPATCH_DTYPE(in_dtype, TI, JMT_DISPATCH_DTYPE(out_dtype, TO,
-      (transpose_kernel<TI, TO><<<grid, 256, 0, st>>>((const TI*)in, (TO*)out, R, C))));
+      (transpose_kernel<TI, TO><<<grid, 256, 0, st>>>((const TI*)in, (TO*)out, R, C, in_bs, out_bs))));
   return check_launch("transpose_kernel");
+}
+
+extern "C" int jmt_transpose(const void* in, int in_dtype, void* out, int out_dtype, int64_t nb, int R, int C, void* stream) {
+  return jmt_transpose_strided(in, in_dtype, 0, out, out_dtype, 0, nb, R, C, stream);
+}
+
+extern "C" int jmt_copy_rows3d(const void* in, int in_dtype, int64_t in_bs, void* out, int out_dtype, int64_t out_bs, int64_t nb,
+                               int64_t rows, int cols, void* stream) {
+  JMT_REQUIRE(in && out && nb >= 0 && rows >= 0 && cols >= 0 && nb < 65536, "jmt_copy_rows3d: bad arguments");
+  if (nb * rows * cols == 0) return JMT_OK;
+  const int64_t per = rows * cols;
+  const int vec = (per % 8 == 0 && in_bs % 8 == 0 && out_bs % 8 == 0 &&
+                   ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 31) == 0) ? 1 : 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  int gx = grid_for(per, kEwThreads * 8, kNumSMs * 8);
+  dim3 grid(gx, (unsigned)nb);
+  JMT_DISPATCH_DTYPE(in_dtype, TI, JMT_DISPATCH_DTYPE(out_dtype, TO,
+      (copy_rows3d_kernel<TI, TO><<<grid, kEwThreads, 0, st>>>((const TI*)in, in_bs, (TO*)out, out_bs, per, vec))));
+  return check_launch("copy_rows3d_kernel");
 }
 
 extern "C" int jmt_colsum(const void* x, int dtype, int64_t ld, int64_t rows, int cols, float* out, void* stream) {

@@ -102,7 +102,11 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(SimtArgs s) {
       float v = g.alpha * acc[i][j];
       if (g.bias && split == 0) v += g.bias[n];
       v = apply_act(v, g.act, g.slope);
-      if (g.colmask) v = g.colmask[(int64_t)batch * g.N + n] ? v * g.colmask_scale : 0.f;
+      if (g.colmask) {
+        const int64_t srow = g.colmask_row_period > 0 ? m / g.colmask_row_period : batch;
+        v = g.colmask[srow * g.N + n] ? v * g.colmask_scale : 0.f;
+      }
+      if (g.zero_row_period > 0 && (m % g.zero_row_period) < g.zero_row_count) v = 0.f;
       const int64_t idx = doff + (int64_t)m * g.d_ld + n;
       if (g.d_dtype == JMT_F32) {
         float* d = (float*)g.d;
@@ -135,6 +139,9 @@ int jmt_validate_gemm_desc(const jmt_gemm_desc* g, const char* who) {
               "%s: split_k > 1 needs JMT_ATOMIC_ADD and no activation", who);
   JMT_REQUIRE(g->act >= JMT_ACT_NONE && g->act <= JMT_ACT_LEAKY_RELU, "%s: bad act", who);
   JMT_REQUIRE(!(g->colmask && (g->reduce_batch || g->split_k > 1)), "%s: colmask needs reduce_batch == 0 and split_k == 1", who);
+  JMT_REQUIRE(g->colmask_row_period >= 0 && g->zero_row_period >= 0 && g->zero_row_count >= 0, "%s: negative row period", who);
+  JMT_REQUIRE(!(g->colmask_row_period > 0 && g->nb0 * g->nb1 != 1), "%s: colmask_row_period needs nb0 = nb1 = 1", who);
+  JMT_REQUIRE(!(g->zero_row_period > 0 && g->reduce_batch), "%s: zero_row_period cannot be combined with reduce_batch", who);
   return JMT_OK;
 }
 

@@ -46,8 +46,12 @@ struct TcParams {
   // epilogue
   void* d;
   const float* bias;
-  const uint8_t* colmask;     // per (batch, column) keep-mask applied after the activation (nullable)
+  const uint8_t* colmask;     // per (sample, column) keep-mask applied after the activation (nullable)
   float colmask_scale;
+  int colmask_period;         // > 0: sample = output row / period (flat layout); 0: sample = batch index
+  int colmask_samples;        // number of mask rows (flat layout)
+  int zrow_period, zrow_count; // output rows m with (m % period) < count are written as zeros (period 0: off)
+  FastDiv fd_zrow, fd_cmask;
   int64_t d_ld, d_bs0, d_bs1;
   float alpha, slope;
   int d_dtype, act, store_mode, vec_ok;
@@ -70,9 +74,18 @@ __device__ __forceinline__ float act_t(float x, float slope) {
 // 32 accumulator columns -> act(alpha * acc + bias) [* column scale] -> bf16 -> this thread's staging row
 // (16-byte pieces `piece0 .. piece0+3` of the 128-byte row, 128B-swizzled).  Branch-free: the activation is a template
 // parameter so the compiler interleaves the independent FFMA / FMNMX / F2FP chains; nothing but r[] stays live.
+// keep-flags (one byte per column) of this thread's sample live after the 256-float bias tile: x *= flag ? scale : 0
+__device__ __forceinline__ void apply_flags4(const uint8_t* fl, float mscale, float& x0, float& x1, float& x2, float& x3) {
+  const uint32_t f4 = *reinterpret_cast<const uint32_t*>(fl);
+  x0 = (f4 & 0x000000FFu) ? x0 * mscale : 0.f;
+  x1 = (f4 & 0x0000FF00u) ? x1 * mscale : 0.f;
+  x2 = (f4 & 0x00FF0000u) ? x2 * mscale : 0.f;
+  x3 = (f4 & 0xFF000000u) ? x3 * mscale : 0.f;
+}
+
 template <int ACT, bool MASK>
-__device__ __forceinline__ void epi_math_store_bf16(const uint32_t (&r)[32], const float* bias, float alpha, float slope,
-                                                    uint32_t row_smem, uint32_t sw, int piece0) {
+__device__ __forceinline__ void epi_math_store_bf16(const uint32_t (&r)[32], const float* bias, const uint8_t* flags, float mscale,
+                                                    uint32_t keep, float alpha, float slope, uint32_t row_smem, uint32_t sw, int piece0) {
 #pragma unroll
   for (int j = 0; j < 32; j += 8) {
     float x[8];
@@ -83,17 +96,16 @@ __device__ __forceinline__ void epi_math_store_bf16(const uint32_t (&r)[32], con
       x[h + 1] = act_t<ACT>(fmaf(alpha, __uint_as_float(r[j + h + 1]), bv.y), slope);
       x[h + 2] = act_t<ACT>(fmaf(alpha, __uint_as_float(r[j + h + 2]), bv.z), slope);
       x[h + 3] = act_t<ACT>(fmaf(alpha, __uint_as_float(r[j + h + 3]), bv.w), slope);
-      if constexpr (MASK) {          // column scales live 256 floats after the bias tile
-        const float4 cs = *reinterpret_cast<const float4*>(bias + 256 + j + h);
-        x[h] *= cs.x; x[h + 1] *= cs.y; x[h + 2] *= cs.z; x[h + 3] *= cs.w;
-      }
+      if constexpr (MASK) apply_flags4(flags + j + h, mscale, x[h], x[h + 1], x[h + 2], x[h + 3]);
     }
-    st_shared_v4(row_smem + (((uint32_t)(piece0 + j / 8) ^ sw) << 4), pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]),
-                 pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
+    // keep = 0 for rows that must read back as zeros (padding rows of the flat TCN layout), else all ones
+    st_shared_v4(row_smem + (((uint32_t)(piece0 + j / 8) ^ sw) << 4), pack_bf16(x[0], x[1]) & keep, pack_bf16(x[2], x[3]) & keep,
+                 pack_bf16(x[4], x[5]) & keep, pack_bf16(x[6], x[7]) & keep);
   }
 }
 template <int ACT, bool MASK>
-__device__ __forceinline__ void epi_math_f32(uint32_t (&r)[32], const float* bias, float alpha, float slope) {
+__device__ __forceinline__ void epi_math_f32(uint32_t (&r)[32], const float* bias, const uint8_t* flags, float mscale, uint32_t keep,
+                                             float alpha, float slope) {
 #pragma unroll
   for (int j = 0; j < 32; j += 4) {
     const float4 bv = *reinterpret_cast<const float4*>(bias + j);
@@ -101,11 +113,8 @@ __device__ __forceinline__ void epi_math_f32(uint32_t (&r)[32], const float* bia
     float x1 = act_t<ACT>(fmaf(alpha, __uint_as_float(r[j + 1]), bv.y), slope);
     float x2 = act_t<ACT>(fmaf(alpha, __uint_as_float(r[j + 2]), bv.z), slope);
     float x3 = act_t<ACT>(fmaf(alpha, __uint_as_float(r[j + 3]), bv.w), slope);
-    if constexpr (MASK) {
-      const float4 cs = *reinterpret_cast<const float4*>(bias + 256 + j);
-      x0 *= cs.x; x1 *= cs.y; x2 *= cs.z; x3 *= cs.w;
-    }
-    r[j] = __float_as_uint(x0); r[j + 1] = __float_as_uint(x1); r[j + 2] = __float_as_uint(x2); r[j + 3] = __float_as_uint(x3);
+    if constexpr (MASK) apply_flags4(flags + j, mscale, x0, x1, x2, x3);
+    r[j] = __float_as_uint(x0) & keep; r[j + 1] = __float_as_uint(x1) & keep; r[j + 2] = __float_as_uint(x2) & keep; r[j + 3] = __float_as_uint(x3) & keep;
   }
 }
 
@@ -138,6 +147,8 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int t, int c
 struct EpiCtx {
   uint32_t tbase, stage_smem, row_smem, sw;
   const float* bias;          // this tile's bias slice in shared memory (zeros when there is none)
+  const uint8_t* flags;       // MASK: this thread's sample's keep-flags for the tile's columns (shared memory)
+  uint32_t keep;              // 0 when this thread's output row must be written as zeros, else ~0
   int m0w, n0, b0, b1, half, lane;
 };
 
@@ -159,8 +170,8 @@ __device__ __forceinline__ void epi_tile(const TcParams& p, const CUtensorMap* t
         if (lane == 0) bulk_wait_read0();       // previous TMA store has finished reading the staging tile
         __syncwarp();
         tc_wait_ld();
-        epi_math_store_bf16<ACT, MASK>(r0, e.bias + c0, p.alpha, p.slope, e.row_smem, e.sw, 0);
-        if (second) epi_math_store_bf16<ACT, MASK>(r1, e.bias + c0 + 32, p.alpha, p.slope, e.row_smem, e.sw, 4);
+        epi_math_store_bf16<ACT, MASK>(r0, e.bias + c0, e.flags + c0, p.colmask_scale, e.keep, p.alpha, p.slope, e.row_smem, e.sw, 0);
+        if (second) epi_math_store_bf16<ACT, MASK>(r1, e.bias + c0 + 32, e.flags + c0 + 32, p.colmask_scale, e.keep, p.alpha, p.slope, e.row_smem, e.sw, 4);
         else {
 #pragma unroll
           for (int ch = 4; ch < 8; ++ch) st_shared_v4(e.row_smem + (((uint32_t)ch ^ e.sw) << 4), 0u, 0u, 0u, 0u);
@@ -178,7 +189,7 @@ __device__ __forceinline__ void epi_tile(const TcParams& p, const CUtensorMap* t
         if (e.n0 + c0 >= p.N) break;
         uint32_t r[32];
         tc_ld32(e.tbase + c0, r);
-        epi_math_f32<ACT, MASK>(r, e.bias + c0, p.alpha, p.slope);
+        epi_math_f32<ACT, MASK>(r, e.bias + c0, e.flags + c0, p.colmask_scale, e.keep, p.alpha, p.slope);
         if (lane == 0) bulk_wait_read0();
         __syncwarp();
 #pragma unroll
@@ -207,7 +218,8 @@ __device__ __forceinline__ void epi_tile(const TcParams& p, const CUtensorMap* t
       for (int j = 0; j < 32; ++j) {
         if (n + j >= p.N) break;
         float v = act_t<ACT>(fmaf(p.alpha, __uint_as_float(r[j]), e.bias[c0 + j]), p.slope);
-        if constexpr (MASK) v *= e.bias[256 + c0 + j];
+        if constexpr (MASK) v = e.flags[c0 + j] ? v * p.colmask_scale : 0.f;
+        if (e.keep == 0u) v = 0.f;
         const int64_t idx = row_off + n + j;
         if (p.d_dtype == JMT_F32) {
           float* d = (float*)p.d;
@@ -229,7 +241,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                const __grid_constant__ CUtensorMap tma_d, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte aligned carve-up (SWIZZLE_128B atoms are 1024 B); identical offsets in both CTAs of a pair
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  // no static shared memory in this kernel: the dynamic window starts 1024-byte aligned (SWIZZLE_128B atoms); fail loudly if not
+  const uint32_t smem_base = smem_u32(smem_raw);
+  if ((smem_base & 1023u) != 0u) __trap();
   const uint32_t sA = smem_base;
   const uint32_t sB = sA + p.stages * kAStageBytes;
   const uint32_t sD = sB + p.stages * p.b_stage_bytes;       // epilogue warps x 4 KiB staging (1024-aligned)
@@ -418,8 +432,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         if (et < p.block_n) {
           const bool in_n = c.n0 + et < p.N;
           bias_ptr[et] = (add_bias && in_n) ? __ldg(p.bias + c.n0 + et) : 0.f;
-          if constexpr (kMask)
-            bias_ptr[256 + et] = (in_n && p.colmask[(int64_t)c.batch * p.N + c.n0 + et]) ? p.colmask_scale : 0.f;
+          if constexpr (kMask) {
+            // keep-flags of the (up to two) samples this tile's rows belong to: sample = batch, or row / period (flat layout)
+            uint8_t* fl = reinterpret_cast<uint8_t*>(bias_ptr + 256);
+            const int s0 = p.colmask_period ? (int)p.fd_cmask.div((uint32_t)c.m0) : c.batch;
+            fl[et] = (in_n && p.colmask[(int64_t)s0 * p.N + c.n0 + et]) ? 1 : 0;
+            fl[256 + et] = (in_n && p.colmask_period && s0 + 1 < p.colmask_samples && p.colmask[(int64_t)(s0 + 1) * p.N + c.n0 + et]) ? 1 : 0;
+          }
         }
         asm volatile("bar.sync 1, %0;" ::"n"(32 * kNumEpiWarps) : "memory");
       }
@@ -432,6 +451,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       EpiCtx ec;
       ec.tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kAccStride);
       ec.stage_smem = stage_smem; ec.row_smem = row_smem; ec.sw = sw; ec.bias = bias_ptr;
+      {
+        const uint32_t m = (uint32_t)(c.m0 + q * 32 + lane);
+        ec.keep = ~0u;
+        if (p.zrow_period) { uint32_t qq, rr; p.fd_zrow.divmod(m, qq, rr); ec.keep = rr < (uint32_t)p.zrow_count ? 0u : ~0u; }
+        const uint8_t* fl = reinterpret_cast<const uint8_t*>(bias_ptr + 256);
+        if (kMask && p.colmask_period) fl += (p.fd_cmask.div(m) != p.fd_cmask.div((uint32_t)c.m0)) ? 256 : 0;
+        ec.flags = fl;
+      }
       ec.m0w = c.m0 + q * 32; ec.n0 = c.n0; ec.b0 = (int)b0u; ec.b1 = (int)b1u; ec.half = half; ec.lane = lane;
       // (kMask: channel dropout fused after the activation, TCN -- a separate kernel instantiation so that its extra
       //  register pressure never touches the common kernels)
@@ -537,12 +564,15 @@ extern "C" int jmt_gemm_bf16(const jmt_gemm_desc* g, void* stream) {
   p.b_stage_bytes = g->b_major == JMT_MAJOR_K ? b_cols_cta * 128 : p.b_chunks_cta * 8192;
   p.b_tx_bytes = p.b_stage_bytes;
   const int stage_bytes = kAStageBytes + p.b_stage_bytes;
-  const int budget = 227 * 1024 - 1024 /*align*/ - 512 /*barriers*/ - kEpiSmemBytes;
+  const int budget = 227 * 1024 - 256 /*barriers*/ - kEpiSmemBytes;      // the dynamic window is 1024-aligned (checked in the kernel)
   p.stages = budget / stage_bytes;
   if (p.stages > kMaxStages) p.stages = kMaxStages;
   JMT_REQUIRE(p.stages >= 2, "jmt_gemm_bf16: shared memory budget");
   p.prof = g_prof_buf.load();
   p.colmask = g->colmask; p.colmask_scale = g->colmask_scale;
+  p.colmask_period = g->colmask_row_period; p.colmask_samples = g->colmask_row_period > 0 ? (g->M + g->colmask_row_period - 1) / g->colmask_row_period : 0;
+  p.zrow_period = g->zero_row_period; p.zrow_count = g->zero_row_count;
+  p.fd_zrow.init(g->zero_row_period > 0 ? g->zero_row_period : 1); p.fd_cmask.init(g->colmask_row_period > 0 ? g->colmask_row_period : 1);
   p.d = g->d; p.bias = g->bias; p.d_ld = g->d_ld; p.d_bs0 = g->d_bs0; p.d_bs1 = g->d_bs1;
   p.alpha = g->alpha; p.slope = g->slope; p.d_dtype = g->d_dtype; p.act = g->act; p.store_mode = g->store_mode;
   const int64_t es = g->d_dtype == JMT_F32 ? 4 : 2;
@@ -580,7 +610,7 @@ extern "C" int jmt_gemm_bf16(const jmt_gemm_desc* g, void* stream) {
     rc = make_map_d(&map_d, g->d, g->d_dtype, g->N, g->M, g->d_ld, dnb0, g->d_bs0, dnb1, g->d_bs1, "jmt_gemm_bf16(D)");
     if (rc != JMT_OK) return rc;
   }
-  const int smem = 1024 + p.stages * stage_bytes + kEpiSmemBytes + 512;
+  const int smem = p.stages * stage_bytes + kEpiSmemBytes + 256;
   static std::atomic<int> attr_set[64];     // per device (immutable once set)
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); set_error("jmt_gemm_bf16: no CUDA device"); return JMT_ERR_CUDA; }

@@ -230,7 +230,7 @@ def gemm(ctx: Ctx, a: torch.Tensor, b: torch.Tensor, d: torch.Tensor, *, M: int,
          a_major=L.MAJOR_K, b_major=L.MAJOR_K, a_rows=None, b_rows=None, a_ld=None, b_ld=None, d_ld=None,
          nb0=1, nb1=1, a_bs=(0, 0), b_bs=(0, 0), d_bs=(0, 0), bias=None, act=L.ACT_NONE, slope=0.0, alpha=1.0,
          store=L.STORE, ntaps=1, a_shift=(0, 0), b_shift=(0, 0), reduce_batch=False, split_k=1,
-         colmask=None, colmask_scale=1.0):
+         colmask=None, colmask_scale=1.0, colmask_row_period=0, zero_rows=(0, 0), alg_flops=None):
     """One GEMM of the family in include/jmt_b200.h.  a/b/d supply base pointers and dtypes (views
     allowed); strides are in elements."""
     require_cuda(a, b, d)
@@ -258,6 +258,8 @@ def gemm(ctx: Ctx, a: torch.Tensor, b: torch.Tensor, d: torch.Tensor, *, M: int,
     g.split_k = split_k
     g.colmask = colmask.data_ptr() if colmask is not None else None
     g.colmask_scale = colmask_scale
+    g.colmask_row_period = colmask_row_period
+    g.zero_row_period, g.zero_row_count = zero_rows
     prof = PROFILE
     if prof is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -272,8 +274,9 @@ def gemm(ctx: Ctx, a: torch.Tensor, b: torch.Tensor, d: torch.Tensor, *, M: int,
         raise RuntimeError(f"gemm operand dtypes {a.dtype}/{b.dtype}")
     if prof is not None:
         e1.record()
-        prof.append((kind, gemm_flops(M, N, K, nb0 * nb1, ntaps, tuple(a_shift), tuple(b_shift), g.a_rows, g.b_rows,
-                                      a_major, b_major), e0, e1, (M, N, K, nb0 * nb1, ntaps)))
+        fl = alg_flops if alg_flops is not None else gemm_flops(M, N, K, nb0 * nb1, ntaps, tuple(a_shift), tuple(b_shift),
+                                                                g.a_rows, g.b_rows, a_major, b_major)
+        prof.append((kind, fl, e0, e1, (M, N, K, nb0 * nb1, ntaps)))
 
 
 def copy2d(ctx: Ctx, src: torch.Tensor, dst: torch.Tensor):
@@ -352,7 +355,8 @@ def l2norm(ctx: Ctx, x: torch.Tensor, needs_grad: bool):
 def linear(ctx: Ctx, x: Var, wname: str, bname: Optional[str], act=L.ACT_NONE, slope=0.0,
            out: Optional[torch.Tensor] = None, w_rows: Optional[Tuple[int, int]] = None,
            w_cols: Optional[Tuple[int, int]] = None, accumulate_into: Optional[Var] = None,
-           grad_from: Optional[Tuple[Var, int, int]] = None, bias_grad_external: bool = False) -> Var:
+           grad_from: Optional[Tuple[Var, int, int]] = None, bias_grad_external: bool = False,
+           zero_rows: Tuple[int, int] = (0, 0)) -> Var:
     """y = act(x W[r0:r1, c0:c1]^T + b[r0:r1])  (nn.Linear).  ``out`` may be a strided (rows, N) view
     (concat-free epilogue: a GEMM writes straight into its slice of a wider buffer);
     ``accumulate_into`` adds into an existing Var (Linear over a concatenation = sum of Linears over
@@ -377,7 +381,7 @@ def linear(ctx: Ctx, x: Var, wname: str, bname: Optional[str], act=L.ACT_NONE, s
         if out is None:
             out = ctx.empty((M, N))
         y = Var(out)
-        gemm(ctx, x.data, Wv, out, M=M, N=N, K=K, bias=bias, act=act, slope=slope)
+        gemm(ctx, x.data, Wv, out, M=M, N=N, K=K, bias=bias, act=act, slope=slope, zero_rows=zero_rows)
     if ctx.record:
         def bwd():
             if grad_from is not None:          # `out` is a column slice of a wider buffer owned by grad_from[0]
@@ -767,15 +771,28 @@ def regressor_tail(ctx: Ctx, hidden: List[Var], wnames: List[str], bnames: List[
 
 
 # --------------------------------------------------------------------------- TCN ops
-def transpose_in(ctx: Ctx, x: torch.Tensor, needs_grad: bool):
-    """(N, C, L) external tensor -> channels-last activation Var of shape (N*L, C)."""
+# Flat padded layout: all N sequences live in ONE channels-last matrix of N * (pad + L) rows, row = n*(pad+L) + pad + t,
+# with `pad` >= (k-1)*max_dilation ZERO rows in front of every sequence.  Those rows are the causal left padding of the
+# forward convs (Chomp1d, temporal_convolutional_model.py:12-18) and -- being the rows right after the previous
+# sequence -- the right padding of its anti-causal dgrad, so the implicit GEMM runs over flat 128-row tiles with plain
+# row shifts instead of one M = L problem per sequence (L = 300 fills 2.34 tiles of 128 rows: 22 % of every conv GEMM was
+# padding; L = 7 clips: 95 %).  Every GEMM that writes activations keeps the padding rows zero (zero_rows).
+def tcn_pad(specs) -> int:
+    """Padding rows per sequence for a TemporalConvNet: the largest causal reach (k-1)*dilation of its levels."""
+    return max((k - 1) * d for (_cin, _cout, k, d, _p, _ds) in specs)
+
+
+def transpose_in(ctx: Ctx, x: torch.Tensor, needs_grad: bool, pad: int = 0):
+    """(N, C, L) external tensor -> channels-last activation Var of shape (N*(pad+L), C), padding rows zero."""
     require_cuda(x)
     xc = x.contiguous()
     if xc.dtype not in _DT:
         raise RuntimeError(f"unsupported input dtype {xc.dtype}")
     N, Cc, Ls = xc.shape
-    out = ctx.empty((N * Ls, Cc))
-    L.check(ctx.lib.jmt_transpose(_ptr(xc), _DT[xc.dtype], _ptr(out), ctx.acode, N, Cc, Ls, _stream()), "jmt_transpose")
+    Lp = Ls + pad
+    out = ctx.zeros((N * Lp, Cc)) if pad else ctx.empty((N * Lp, Cc))
+    L.check(ctx.lib.jmt_transpose_strided(_ptr(xc), _DT[xc.dtype], 0, _ptr(out[pad:]), ctx.acode, Lp * Cc, N, Cc, Ls, _stream()),
+            "jmt_transpose")
     v = Var(out, needs_grad)
     holder: dict = {}
     if ctx.record and needs_grad:
@@ -784,7 +801,8 @@ def transpose_in(ctx: Ctx, x: torch.Tensor, needs_grad: bool):
             if v.grad is None:
                 cuda_memset0(dx)
             else:
-                L.check(ctx.lib.jmt_transpose(_ptr(v.grad), ctx.acode, _ptr(dx), L.F32, N, Ls, Cc, _stream()), "jmt_transpose")
+                L.check(ctx.lib.jmt_transpose_strided(_ptr(v.grad[pad:]), ctx.acode, Lp * Cc, _ptr(dx), L.F32, 0, N, Ls, Cc,
+                                                      _stream()), "jmt_transpose")
             ctx.release(v)
             holder["dx"] = dx
         ctx.tape.append(bwd)
@@ -815,14 +833,18 @@ def weight_norm_conv_weights(ctx: Ctx, prefix: str, cout: int, cin: int, k: int)
 
 
 def causal_conv(ctx: Ctx, x: Var, prefix: str, N: int, Ls: int, cin: int, cout: int, k: int, dil: int, act: int,
-                drop_p: float = 0.0) -> Var:
+                drop_p: float = 0.0, pad: int = 0) -> Var:
     """weight-normed dilated causal Conv1d + Chomp1d + LeakyReLU + Dropout2d (temporal_convolutional_model.py:24-29)
-    as an implicit GEMM on channels-last data: taps are K blocks whose A rows are shifted by
-    -(k-1-j)*dil inside each sequence; rows before t=0 come back as zeros (TMA OOB fill / predicate).
+    as an implicit GEMM on the flat padded channels-last layout (see above): taps are K blocks whose A rows are
+    shifted by -(k-1-j)*dil; the zero padding rows in front of every sequence supply the causal zeros.
     Channel dropout (training, p > 0; SURVEY Q12: whole channels per sample) is a per-(sample, channel) scale in the
     GEMM epilogue; its backward, the activation gradient and the bias gradient are one fused pass."""
+    assert pad >= (k - 1) * dil, "the padding rows must cover the causal reach of this conv"
+    Lp = Ls + pad
+    R = N * Lp
+    assert x.data.shape[0] == R
     w_fwd, w_dg, dwh = weight_norm_conv_weights(ctx, prefix, cout, cin, k)   # recorded first => runs last in backward
-    y = ctx.empty((N * Ls, cout))
+    y = ctx.empty((R, cout))
     bias = ctx.p(prefix + "bias")
     mask, mscale = None, 1.0
     if drop_p > 0.0 and ctx.training:
@@ -830,9 +852,12 @@ def causal_conv(ctx: Ctx, x: Var, prefix: str, N: int, Ls: int, cin: int, cout: 
         L.check(ctx.lib.jmt_dropout_mask(_ptr(mask), N * cout, drop_p, ctx.seed, ctx.rng_offset, _stream()), "jmt_dropout_mask")
         ctx.rng_offset += (N * cout + 3) // 4
         mscale = 1.0 / (1.0 - drop_p)
-    gemm(ctx, x.data, w_fwd, y, M=Ls, N=cout, K=cin, a_rows=Ls, b_rows=cout, a_ld=cin, b_ld=k * cin, d_ld=cout,
-         nb0=1, nb1=N, a_bs=(0, Ls * cin), d_bs=(0, Ls * cout), bias=bias, act=act, slope=LEAKY_SLOPE,
-         ntaps=k, a_shift=(-(k - 1) * dil, dil), colmask=mask, colmask_scale=mscale)
+    # algorithmic FLOPs = useful taps only: tap j touches L - (k-1-j)*dil positions of each sequence
+    tap_flops = [2.0 * N * max(0, Ls - (k - 1 - j) * dil) * cout * cin for j in range(k)]
+    gemm(ctx, x.data, w_fwd, y, M=R, N=cout, K=cin, a_rows=R, b_rows=cout, a_ld=cin, b_ld=k * cin, d_ld=cout,
+         bias=bias, act=act, slope=LEAKY_SLOPE, ntaps=k, a_shift=(-(k - 1) * dil, dil),
+         colmask=mask, colmask_scale=mscale, colmask_row_period=Lp if mask is not None else 0, zero_rows=(Lp, pad),
+         alg_flops=sum(tap_flops))
     out = Var(y)
     if ctx.record:
         def bwd():
@@ -840,29 +865,28 @@ def causal_conv(ctx: Ctx, x: Var, prefix: str, N: int, Ls: int, cin: int, cout: 
             if dy is None:
                 return
             assert dy.is_contiguous()
-            # where a channel was dropped y = 0 and the masked dy is 0, so act'(y) of the post-dropout y is exact
+            # where a channel was dropped y = 0 and the masked dy is 0, so act'(y) of the post-dropout y is exact;
+            # padding rows of dy are zero (every producer keeps them so) and stay zero
             if act != L.ACT_NONE or mask is not None:
                 dy = _act_bwd(ctx, out, dy, LEAKY_SLOPE if act != L.ACT_NONE else 1.0, colsum=ctx.pgrad(prefix + "bias"),
-                              mask=mask, mask_rows=Ls, mask_scale=mscale)
+                              mask=mask, mask_rows=Lp, mask_scale=mscale)
             else:
-                L.check(ctx.lib.jmt_colsum(_ptr(dy), _DT[dy.dtype], cout, N * Ls, cout, _ptr(ctx.pgrad(prefix + "bias")),
+                L.check(ctx.lib.jmt_colsum(_ptr(dy), _DT[dy.dtype], cout, R, cout, _ptr(ctx.pgrad(prefix + "bias")),
                                            _stream()), "jmt_colsum")
-            # wgrad per tap: dW_j (Cout, Cin) = sum_n dy_n^T shift_j(x_n); reduction over (n, t)
+            # wgrad per tap: dW_j (Cout, Cin) = dy^T shift_j(x) over all flat rows (split-K, fp32 atomics)
             dw = ctx.zeros((cout, k * cin), torch.float32)
             tiles = ((cout + 127) // 128) * ((cin + 255) // 256)
-            sk = split_k_for(N * Ls, tiles)          # each tap is its own launch: fill the chip per launch
+            sk = split_k_for(R, tiles)          # each tap is its own launch: fill the chip per launch
             for j in range(k):
-                gemm(ctx, dy, x.data, dw[:, j * cin:(j + 1) * cin], M=cout, N=cin, K=Ls,
-                     a_major=L.MAJOR_MN, b_major=L.MAJOR_MN, a_rows=Ls, b_rows=Ls, a_ld=cout, b_ld=cin, d_ld=k * cin,
-                     nb0=1, nb1=N, a_bs=(0, Ls * cout), b_bs=(0, Ls * cin), b_shift=(-(k - 1 - j) * dil, 0),
-                     reduce_batch=True, store=L.ATOMIC_ADD, split_k=sk)
+                gemm(ctx, dy, x.data, dw[:, j * cin:(j + 1) * cin], M=cout, N=cin, K=R,
+                     a_major=L.MAJOR_MN, b_major=L.MAJOR_MN, a_rows=R, b_rows=R, a_ld=cout, b_ld=cin, d_ld=k * cin,
+                     b_shift=(-(k - 1 - j) * dil, 0), store=L.ATOMIC_ADD, split_k=sk, alg_flops=tap_flops[j])
             dwh["t"] = dw
             if x.needs_grad:
-                # dgrad: dx[t] = sum_j W_j^T dy[t + (k-1-j) dil]
+                # dgrad: dx[r] = sum_j W_j^T dy[r + (k-1-j) dil]; rows past a sequence's end are the next one's zero padding
                 dx, mode = ctx.grad_target(x)
-                gemm(ctx, dy, w_dg, dx, M=Ls, N=cin, K=cout, a_rows=Ls, b_rows=cin, a_ld=cout, b_ld=k * cout, d_ld=cin,
-                     nb0=1, nb1=N, a_bs=(0, Ls * cout), d_bs=(0, Ls * cin), ntaps=k, a_shift=((k - 1) * dil, -dil),
-                     store=mode)
+                gemm(ctx, dy, w_dg, dx, M=R, N=cin, K=cout, a_rows=R, b_rows=cin, a_ld=cout, b_ld=k * cout, d_ld=cin,
+                     ntaps=k, a_shift=((k - 1) * dil, -dil), store=mode, zero_rows=(Lp, pad), alg_flops=sum(tap_flops))
             ctx.release(out)
         ctx.tape.append(bwd)
     return out
@@ -914,22 +938,50 @@ def add_act(ctx: Ctx, a: Var, b: Var, act: int, slope: float) -> Var:
     return out
 
 
-def transpose_out(ctx: Ctx, x: Var, N: int, Ls: int, Cc: int):
-    """channels-last (N*L, C) Var -> external fp32 (N, C, L) tensor; returns (tensor, grad setter)."""
+def transpose_out(ctx: Ctx, x: Var, N: int, Ls: int, Cc: int, pad: int = 0):
+    """flat padded channels-last (N*(pad+L), C) Var -> external fp32 (N, C, L) tensor; returns (tensor, grad setter)."""
+    Lp = Ls + pad
     out = ctx.empty((N, Cc, Ls), torch.float32)
-    L.check(ctx.lib.jmt_transpose(_ptr(x.data), ctx.acode, _ptr(out), L.F32, N, Ls, Cc, _stream()), "jmt_transpose")
+    L.check(ctx.lib.jmt_transpose_strided(_ptr(x.data[pad:]), ctx.acode, Lp * Cc, _ptr(out), L.F32, 0, N, Ls, Cc, _stream()),
+            "jmt_transpose")
     g = {"t": None}
     if ctx.record:
         def bwd():
             if g["t"] is None:
                 return
             d = g["t"].contiguous()
-            gb = GradBuf(ctx.empty((N * Ls, Cc)))
-            L.check(ctx.lib.jmt_transpose(_ptr(d), _DT[d.dtype], _ptr(gb.t), ctx.acode, N, Cc, Ls, _stream()), "jmt_transpose")
+            gb = GradBuf(ctx.zeros((N * Lp, Cc)) if pad else ctx.empty((N * Lp, Cc)))
+            L.check(ctx.lib.jmt_transpose_strided(_ptr(d), _DT[d.dtype], 0, _ptr(gb.t[pad:]), ctx.acode, Lp * Cc, N, Cc, Ls,
+                                                  _stream()), "jmt_transpose")
             ctx.add_grad(x, gb)
             gb.refs -= 1
         ctx.tape.append(bwd)
     return out, (lambda t: g.__setitem__("t", t))
+
+
+def unpad_rows(ctx: Ctx, x: Var, N: int, Ls: int, pad: int) -> Var:
+    """flat padded (N*(pad+L), C) Var -> compact (N*L, C) Var (row = n*L + t), e.g. the (B, T, 512) view
+    I3D_WSDDA.forward returns (I3DWSDDA.py:44) that the fusion consumes."""
+    if pad == 0:
+        return x
+    Cc = x.data.shape[1]
+    Lp = Ls + pad
+    y = ctx.empty((N * Ls, Cc))
+    L.check(ctx.lib.jmt_copy_rows3d(_ptr(x.data[pad:]), ctx.acode, Lp * Cc, _ptr(y), ctx.acode, Ls * Cc, N, Ls, Cc, _stream()),
+            "jmt_copy_rows3d")
+    out = Var(y)
+    if ctx.record:
+        def bwd():
+            if out.grad is None:
+                return
+            gb = GradBuf(ctx.zeros((N * Lp, Cc)))
+            L.check(ctx.lib.jmt_copy_rows3d(_ptr(out.grad), ctx.acode, Ls * Cc, _ptr(gb.t[pad:]), ctx.acode, Lp * Cc, N, Ls, Cc,
+                                            _stream()), "jmt_copy_rows3d")
+            ctx.add_grad(x, gb)
+            gb.refs -= 1
+            ctx.release(out)
+        ctx.tape.append(bwd)
+    return out
 
 
 def to_external(ctx: Ctx, x: Var, shape):

@@ -567,29 +567,31 @@ class TemporalConvNet(_JmtModule):
         specs = self.block_specs()
 
         def runner(ctx, xin):
-            h, gx = E.transpose_in(ctx, xin, xin.requires_grad)            # channels-last (N*L, C)
-            h = _tcn_graph(ctx, h, "", specs, N, Ls)
-            out, setter = E.transpose_out(ctx, h, N, Ls, h.data.shape[1])
+            pad = E.tcn_pad(specs)
+            h, gx = E.transpose_in(ctx, xin, xin.requires_grad, pad)       # flat padded channels-last (N*(pad+L), C)
+            h = _tcn_graph(ctx, h, "", specs, N, Ls, pad)
+            out, setter = E.transpose_out(ctx, h, N, Ls, h.data.shape[1], pad)
             return [out], [setter], [gx]
         return self._run(runner, x)[0]
 
 
-def _tcn_graph(ctx, h, prefix, specs, N, Ls):
-    """TemporalConvNet.forward on channels-last rows (row = n*L + t): per level two weight-normed dilated
-    causal convs (+LeakyReLU, channel dropout), residual (1x1 conv when Cin != Cout), LeakyReLU
-    (temporal_convolutional_model.py:54-57, 81-82)."""
+def _tcn_graph(ctx, h, prefix, specs, N, Ls, pad):
+    """TemporalConvNet.forward on the flat padded channels-last layout (row = n*(pad+L) + pad + t, engine.py "TCN ops"):
+    per level two weight-normed dilated causal convs (+LeakyReLU, channel dropout), residual (1x1 conv when
+    Cin != Cout), LeakyReLU (temporal_convolutional_model.py:54-57, 81-82).  Padding rows stay zero throughout."""
     for i, (cin, cout, k, d, p, has_ds) in enumerate(specs):
         pre = f"{prefix}network.{i}."
-        y = E.causal_conv(ctx, h, pre + "conv1.", N, Ls, cin, cout, k, d, L.ACT_LEAKY, drop_p=p)
-        y = E.causal_conv(ctx, y, pre + "conv2.", N, Ls, cout, cout, k, d, L.ACT_LEAKY, drop_p=p)
-        res = _conv1x1(ctx, h, pre + "downsample.") if has_ds else h
+        y = E.causal_conv(ctx, h, pre + "conv1.", N, Ls, cin, cout, k, d, L.ACT_LEAKY, drop_p=p, pad=pad)
+        y = E.causal_conv(ctx, y, pre + "conv2.", N, Ls, cout, cout, k, d, L.ACT_LEAKY, drop_p=p, pad=pad)
+        res = _conv1x1(ctx, h, pre + "downsample.", (Ls + pad, pad)) if has_ds else h
         h = E.add_act(ctx, y, res, L.ACT_LEAKY, E.LEAKY_SLOPE)
     return h
 
 
-def _conv1x1(ctx, x, prefix):
-    """nn.Conv1d(cin, cout, 1) on channels-last rows = a Linear whose (cout, cin, 1) weight is viewed 2-D."""
-    return E.linear(ctx, x, prefix + "weight", prefix + "bias")
+def _conv1x1(ctx, x, prefix, zero_rows=(0, 0)):
+    """nn.Conv1d(cin, cout, 1) on channels-last rows = a Linear whose (cout, cin, 1) weight is viewed 2-D; the
+    padding rows of the flat layout must not pick up the bias."""
+    return E.linear(ctx, x, prefix + "weight", prefix + "bias", zero_rows=zero_rows)
 
 
 class JMTPipeline(_JmtModule):
@@ -627,8 +629,11 @@ class JMTPipeline(_JmtModule):
             if self.tcn is not None:
                 N, C0, Ls = vis.shape
                 assert N == B and Ls == T
-                h, gv = E.transpose_in(ctx, vis, vis.requires_grad)
-                h = _tcn_graph(ctx, h, "tcn.", self.tcn.block_specs(), N, Ls)     # (B*T, 512) == transpose(1,2)
+                specs = self.tcn.block_specs()
+                pad = E.tcn_pad(specs)
+                h, gv = E.transpose_in(ctx, vis, vis.requires_grad, pad)
+                h = _tcn_graph(ctx, h, "tcn.", specs, N, Ls, pad)
+                h = E.unpad_rows(ctx, h, N, Ls, pad)                              # (B*T, 512) == transpose(1,2)
                 video_n = _l2norm_var(ctx, h)
             else:
                 video_n, gv = E.l2norm(ctx, vis, vis.requires_grad)

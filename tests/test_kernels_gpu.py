@@ -180,6 +180,42 @@ def test_gemm_colmask(precision, nb):
     assert (d.float().cpu()[mask[:, None, :].expand(nb, M, N) == 0] == 0).all()
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_gemm_flat_tcn_layout(precision):
+    """Flat padded TCN layout: one GEMM over N*(pad+L) rows with row shifts, padding rows written as zeros
+    (zero_row_period) and the channel-dropout mask row taken from m / period -- against per-sequence causal convs."""
+    torch.manual_seed(5)
+    dev = torch.device("cuda")
+    dt = torch.float32 if precision == "fp32" else torch.bfloat16
+    Nn, Ls, pad, cin, cout, taps, dil = 5, 77, 8, 64, 96, 3, 4
+    Lp = Ls + pad
+    x = torch.zeros(Nn, Lp, cin)
+    x[:, pad:] = (torch.randn(Nn, Ls, cin) * 0.5).to(dt).float()
+    w = (torch.randn(cout, taps * cin) * 0.5).to(dt).float()
+    bias = torch.randn(cout)
+    mask = (torch.rand(Nn, cout) > 0.4).to(torch.uint8)
+    ref = torch.zeros(Nn, Lp, cout, dtype=torch.float64)
+    for n in range(Nn):
+        for t in range(Ls):
+            acc = bias.double().clone()
+            for j in range(taps):
+                src = t - (taps - 1 - j) * dil
+                if src >= 0:
+                    acc += w[:, j * cin:(j + 1) * cin].double() @ x[n, pad + src].double()
+            acc = torch.where(acc >= 0, acc, acc * 0.01)
+            ref[n, pad + t] = acc * mask[n].double() * 1.5
+    xd, wd, md = x.reshape(Nn * Lp, cin).to(dev, dt), w.to(dev, dt), mask.to(dev)
+    d = torch.full((Nn * Lp, cout), float("nan"), device=dev, dtype=dt)
+    E.gemm(_ctx(precision), xd, wd, d, M=Nn * Lp, N=cout, K=cin, a_rows=Nn * Lp, b_rows=cout, a_ld=cin, b_ld=taps * cin, d_ld=cout,
+           bias=bias.to(dev), act=L.ACT_LEAKY, slope=0.01, ntaps=taps, a_shift=(-(taps - 1) * dil, dil),
+           colmask=md, colmask_scale=1.5, colmask_row_period=Lp, zero_rows=(Lp, pad))
+    torch.cuda.synchronize()
+    got = d.float().cpu().double().reshape(Nn, Lp, cout)
+    tol = 2e-4 if precision == "fp32" else 1.2e-2
+    assert (got - ref).abs().max() < tol * (ref.abs().max() + 1e-6), (got - ref).abs().max()
+    assert (got[:, :pad] == 0).all(), "padding rows must be written as zeros"
+
+
 def test_gemm_heads_geometry():
     """(b, head) batching through two batch dims with non-monotonic strides (Q of shape (B*T, 3E))."""
     torch.manual_seed(3)
