@@ -278,6 +278,24 @@ int jmt_label_mask(const float* y, int64_t n, float ignore, uint8_t* mask, void*
  * in (rows, in_w) copied right-aligned. fp32. */
 int jmt_pad_right_align(const float* in, int64_t rows, int in_w, float* out, int out_w, void* stream);
 
+/* ------------------------------------------------------------------------------------------ *
+ * Validation post-processing on the device (val.py:313-382).
+ * jmt_valpost_scatter: one batch of per-frame predictions (element e = b*T + t, fp32) into the per-video
+ *   arrays (all videos concatenated, `offsets` = prefix sums of the lengths): skipped when either label is
+ *   `ignore` (-5) or the 1-based frame id is outside [1, length]; within a batch the element that comes last in
+ *   the reference's loop order wins, across batches the larger `seq` (1, 2, ...) wins.  `stamp` (total frames,
+ *   zero-initialised) is the arbitration state.  Untouched frames keep the caller's initial (0, 0).
+ * jmt_valpost_finalize: per video clip to [-1,1] + uniform_filter1d(size_v / size_a, mode='constant'), optional
+ *   smoothed outputs, and sums (2, 6) fp64 += (N, Sx, Sy, Sxy, Sxx, Syy) for valence / arousal (finalise with
+ *   jmt_ccc_finalize(JMT_CCC_METRIC)).
+ * ------------------------------------------------------------------------------------------ */
+int jmt_valpost_scatter(const float* v, const float* a, const float* lab_v, const float* lab_a, const int32_t* frame_id,
+                        const int32_t* video, int64_t n, const int64_t* offsets, float ignore, uint64_t seq,
+                        uint64_t* stamp, float* pred_v, float* pred_a, float* label_v, float* label_a, void* stream);
+int jmt_valpost_finalize(const float* pred_v, const float* pred_a, const float* label_v, const float* label_a,
+                         const int64_t* offsets, int videos, int64_t total_frames, int size_v, int size_a,
+                         float* smooth_v, float* smooth_a, double* sums, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -91,6 +91,8 @@ SIGNATURES = {
     "jmt_ccc_finalize": [_P, _I, _I, _D, _D, _P, _P, _P],
     "jmt_ccc_bwd": [_P, _P, _L, _I, _L, _P, _P, _I, _I, _F, _P, _P],
     "jmt_label_mask": [_P, _L, _F, _P, _P],
+    "jmt_valpost_scatter": [_P, _P, _P, _P, _P, _P, _L, _P, _F, _U64, _P, _P, _P, _P, _P, _P],
+    "jmt_valpost_finalize": [_P, _P, _P, _P, _P, _I, _L, _I, _I, _P, _P, _P, _P],
     "jmt_pad_right_align": [_P, _L, _I, _P, _I, _P],
 }
 _RESTYPES = {"jmt_last_error": C.c_char_p, "jmt_launch_count": C.c_int64}

@@ -248,3 +248,51 @@ def test_cpu_tensor_is_refused():
     model = jmt_b200.FcLayer(768, 512).to(DEV)
     with pytest.raises(RuntimeError, match="CUDA"):
         model(torch.randn(2, 3, 768))
+
+
+def test_graphed_step_matches_eager():
+    """jmt_b200.GraphedStep (whole training step as one CUDA graph per buffer set) produces the same losses and
+    parameters as launching every kernel from Python."""
+    import copy
+    torch.manual_seed(0)
+    B, T = 4, 24
+    base = jmt_b200.JMTPipeline(jmt_b200.Two_transformers(0.0, 0.0, 2, 1, "TRANSFORMER", "FC", 512, precision="bf16"),
+                                jmt_b200.FcLayer(768, 512, precision="bf16"),
+                                jmt_b200.TemporalConvNet(64, [512] * 2, kernel_size=3, attention=0, dropout=0.0, precision="bf16")).to(DEV).train()
+    gen = torch.Generator().manual_seed(3)
+    sets = []
+    for _ in range(2):
+        sets.append((torch.randn(B, T, 768, generator=gen).to(DEV), torch.randn(B, 64, T, generator=gen).to(DEV),
+                     (torch.rand(B, T, generator=gen) * 2 - 1).to(DEV), (torch.rand(B, T, generator=gen) * 2 - 1).to(DEV)))
+    n = B * T
+    crit = jmt_b200.CCCLoss(digitize_num=1)
+    results = []
+    for graphed in (False, True):
+        model = copy.deepcopy(base)
+        opt = torch.optim.SGD(model.live_parameters(), lr=1e-2)
+
+        def step(aud, vis, lv, la):
+            v, a = model(aud, vis)
+            loss = crit(v.view(-1, n), lv.view(-1, n)) + crit(a.view(-1, n), la.view(-1, n))
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+            opt.step()
+            return loss
+        losses = []
+        if graphed:
+            g = jmt_b200.GraphedStep(step, sets, warmup=2)           # 2 warm-up steps happen before capture ...
+            assert g.launches_per_step > 50
+            for i in range(4):
+                losses.append(float(g.replay(i % 2).item()))
+        else:
+            for i in range(2):                                       # ... so the eager run takes the same 2 first
+                step(*sets[i % 2])
+            for i in range(4):
+                losses.append(float(step(*sets[i % 2]).item()))
+        results.append((losses, [p.detach().float().cpu().clone() for p in model.live_parameters()]))
+    (le, pe), (lg, pg) = results
+    # fp32 atomics in split-K / bias-gradient reductions make bf16 steps reproducible only to rounding noise
+    assert np.allclose(le, lg, atol=2e-3), (le, lg)
+    num = sum(float((a - b).norm() ** 2) for a, b in zip(pe, pg)) ** 0.5
+    den = sum(float(a.norm() ** 2) for a in pe) ** 0.5
+    assert num / den < 1e-3, num / den
