@@ -125,7 +125,7 @@ int jmt_gemm_set_profile_buffer(void* dev_buf);
  * Fused attention core (bf16, tcgen05): two chained GEMMs with the row-wise softmax algebra between them.
  *   mode 0 (forward):  X = P  = softmax(scale * A1 B1^T) (rows of A1 = queries, rows of B1 = keys);  D = X B2
  *                      A1 = Q, B1 = K, B2 = V;  X (the probabilities) is also written to `x` for backward.
- *   mode 1 (backward): X = dS = scale * P o (A1 B1^T - rowsum(P o A1 B1^T)) with P read from p_in;  D (+)= X B2
+ *   mode 1 (backward): X = dS = scale * P o (A1 B1^T - delta), delta = rowsum(dO o O) = rowsum(P o dP), P from p_in;  D (+)= X B2
  *                      A1 = dO, B1 = V, B2 = K  ->  D = dQ;  X (= dS) is written to `x` (dK = dS^T Q is a plain GEMM).
  * Operand (r, k) of (head h, batch b) = ptr[b*bs + h*hs + r*ld + k], k < dh contiguous; X / p_in are
  * (NB, heads, Lq, x_ld) contiguous bf16 with x_ld % 8 == 0.  Supported: dh in {64,128,256,512}, S <= 512 subject to
@@ -137,6 +137,7 @@ int jmt_gemm_set_profile_buffer(void* dev_buf);
 typedef struct {
   const void* a1; const void* b1; const void* b2;   /* bf16 */
   const void* p_in;                                  /* mode 1: saved probabilities; else NULL */
+  const void* o_in;                                  /* mode 1: saved forward output O, same geometry as a1 (= dO); else NULL */
   void* x;                                           /* out: P (mode 0) / dS (mode 1), bf16 */
   void* d;                                           /* out: O (mode 0) / dQ (mode 1), bf16 */
   int32_t mode;

@@ -39,6 +39,9 @@ struct AtParams {
   float c_exp;          // scale * log2(e)
   float scale;
   const __nv_bfloat16* p_in;   // mode 1: saved probabilities (NB, heads, Lq, x_ld)
+  const __nv_bfloat16* do_in;  // mode 1: dO and the saved forward output O (same geometry): delta = rowsum(dO o O)
+  const __nv_bfloat16* o_in;
+  int64_t do_ld, do_hs, do_bs;
   int64_t x_ld;
   int store_mode;
   FastDiv fd_qt, fd_heads;
@@ -82,110 +85,100 @@ __device__ __forceinline__ float p_elem(const uint4 (&pv)[4], int i, int h) {
   return (h & 1) ? bf16hi(w) : bf16lo(w);
 }
 
-// pass 1 on one 32-key chunk: four independent partial maxima (MODE 0) / partial P.dP dots (MODE 1)
-template <int MODE>
-__device__ __forceinline__ void row_pass1(const uint32_t (&r)[32], const uint4 (&pv)[4], int nvalid, float (&acc)[4]) {
-  if (nvalid >= 32) {
+// forward, pass 1 on one 32-key chunk: four independent partial maxima
+__device__ __forceinline__ void row_fwd_max(const uint32_t (&r)[32], int nvalid, float (&mx)[4]) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int h = 0; h < 8; ++h) {
-        const float v = __uint_as_float(r[i * 8 + h]);
-        if (MODE == 0) acc[h & 3] = fmaxf(acc[h & 3], v);
-        else acc[h & 3] = fmaf(p_elem(pv, i, h), v, acc[h & 3]);
-      }
-  } else {
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int h = 0; h < 8; ++h) {
-        const float v = __uint_as_float(r[i * 8 + h]);
-        const bool ok = i * 8 + h < nvalid;
-        if (MODE == 0) acc[h & 3] = ok ? fmaxf(acc[h & 3], v) : acc[h & 3];
-        else acc[h & 3] = ok ? fmaf(p_elem(pv, i, h), v, acc[h & 3]) : acc[h & 3];
-      }
-  }
+  for (int j = 0; j < 32; ++j) mx[j & 3] = (nvalid >= 32 || j < nvalid) ? fmaxf(mx[j & 3], __uint_as_float(r[j])) : mx[j & 3];
 }
-
-// pass 2 on one 32-key chunk: X = exp2(T1 * c - shift) (MODE 0) | scale * P * (T1 - shift) (MODE 1) -> bf16 -> swizzled X
-template <int MODE>
-__device__ __forceinline__ void row_pass2(const AtParams& p, const uint32_t (&r)[32], const uint4 (&pv)[4], int nvalid, float shift,
-                                          uint32_t xbase, uint32_t piece0, uint32_t sw, float (&sum)[4]) {
+// forward, pass 2 on one 32-key chunk: e = exp2(v*c - rowmax*c) -> bf16 -> swizzled X, four independent partial sums
+__device__ __forceinline__ void row_fwd_exp(const AtParams& p, const uint32_t (&r)[32], int nvalid, float shift, float (&sum)[4],
+                                            uint32_t xbase, uint32_t piece0, uint32_t sw) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     float x[8];
 #pragma unroll
     for (int h = 0; h < 8; ++h) {
-      const float v = __uint_as_float(r[i * 8 + h]);
-      float y;
-      if (MODE == 0) y = ex2_approx(fmaf(v, p.c_exp, -shift));
-      else y = p.scale * p_elem(pv, i, h) * (v - shift);
+      const float y = ex2_approx(fmaf(__uint_as_float(r[i * 8 + h]), p.c_exp, -shift));
       x[h] = (nvalid >= 32 || i * 8 + h < nvalid) ? y : 0.f;
-      if (MODE == 0) sum[h & 3] += x[h];
+      sum[h & 3] += x[h];
     }
     st_shared_v4(xbase + (((piece0 + (uint32_t)i) ^ sw) << 4), pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]),
                  pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
   }
 }
 
+// backward, one 32-key chunk: dS = scale * P * (dP - delta) with P read from the X tile it overwrites
+__device__ __forceinline__ void row_bwd_chunk(const AtParams& p, const uint32_t (&r)[32], int nvalid, float delta,
+                                              uint32_t xbase, uint32_t piece0, uint32_t sw) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t addr = xbase + (((piece0 + (uint32_t)i) ^ sw) << 4);
+    const uint4 pv = ld_shared_v4(addr);
+    const uint32_t w[4] = {pv.x, pv.y, pv.z, pv.w};
+    float x[8];
+#pragma unroll
+    for (int h = 0; h < 8; ++h) {
+      const float pf = (h & 1) ? bf16hi(w[h >> 1]) : bf16lo(w[h >> 1]);
+      const float y = p.scale * pf * (__uint_as_float(r[i * 8 + h]) - delta);
+      x[h] = (nvalid >= 32 || i * 8 + h < nvalid) ? y : 0.f;
+    }
+    st_shared_v4(addr, pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
+  }
+}
+
 // The row-wise algebra between the two GEMMs for one thread (= one query row, every other 32-key chunk):
-//   MODE 0: X = softmax(scale * T1) (max exchange, exp2, sum exchange, in-place normalisation)
-//   MODE 1: X = scale * P o (T1 - rowsum(P o T1))  with P from global memory (dot exchange)
-// X goes to shared memory as bf16 in the 128B-swizzled K-major A-operand layout of GEMM2.  The TMEM (and global P)
-// loads of chunk i+1 are in flight while chunk i is processed (two register buffers).
+//   MODE 0: X = softmax(scale * T1): two streaming passes over T1 (row max, then exp2 + row sum; each with one exchange
+//           with the warp that owns the other chunks of the row), then the bf16 values are normalised in shared memory.
+//           (A single-pass online-softmax variant was measured slower: its per-chunk max -> exp dependency serialises
+//           the two warps an SMSP has.)
+//   MODE 1: X = scale * P o (T1 - delta), ONE pass: delta = rowsum(dO o O) (= rowsum(P o dP)) was precomputed into
+//           `delta_buf` while the previous tile's GEMM2 ran, P was staged in X by TMA.
+// X ends up in shared memory as bf16 in the 128B-swizzled K-major A-operand layout of GEMM2.  The TMEM load of chunk
+// i+1 is in flight while chunk i is processed (two register buffers).
 template <int MODE>
-__device__ __forceinline__ void row_op(const AtParams& p, const RowCtx& rc, const AtTile& c, int grow, float* red) {
+__device__ __forceinline__ void row_op(const AtParams& p, const RowCtx& rc, float* red, const float* delta_buf) {
   const int half = rc.half, row = rc.row, nch = rc.nch;
   uint32_t ra[32], rb[32];
-  uint4 pa[4], pb[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) { pa[i] = make_uint4(0, 0, 0, 0); pb[i] = make_uint4(0, 0, 0, 0); }
-  // MODE 1: the P tile was staged into X (same swizzled layout dS will overwrite) before GEMM1 finished
-#define AT_LOAD(R, P, CH)                                                                    \
-  {                                                                                          \
-    tc_ld32_issue(rc.tb + (CH) * 32, R);                                                     \
-    if (MODE == 1) {                                                                         \
-      _Pragma("unroll") for (int i_ = 0; i_ < 4; ++i_)                                       \
-        P[i_] = ld_shared_v4(rc.xrow + ((CH) >> 1) * 16384 + ((((uint32_t)(((CH) & 1) * 4 + i_)) ^ rc.sw) << 4)); \
-    }                                                                                        \
+  float shift = 0.f;
+  if (MODE == 0) {
+    float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    if (half < nch) tc_ld32_issue(rc.tb + half * 32, ra);
+    for (int ch = half; ch < nch; ch += 4) {
+      tc_wait_ld();
+      if (ch + 2 < nch) tc_ld32_issue(rc.tb + (ch + 2) * 32, rb);
+      row_fwd_max(ra, p.S - ch * 32, mx);
+      if (ch + 2 >= nch) break;
+      tc_wait_ld();
+      if (ch + 4 < nch) tc_ld32_issue(rc.tb + (ch + 4) * 32, ra);
+      row_fwd_max(rb, p.S - (ch + 2) * 32, mx);
+    }
+    red[half * 128 + row] = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+    __syncwarp();
+    if (half < nch) tc_ld32_issue(rc.tb + half * 32, ra);        // pass 2's first chunk is in flight across the barrier
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * kAtRowWarps) : "memory");
+    shift = fmaxf(red[row], red[128 + row]) * p.c_exp;
+  } else {
+    shift = delta_buf[row];
+    if (half < nch) tc_ld32_issue(rc.tb + half * 32, ra);
   }
-  // ---- pass 1
-  float acc[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) acc[i] = MODE == 0 ? -INFINITY : 0.f;
-  if (half < nch) AT_LOAD(ra, pa, half);
-  for (int ch = half; ch < nch; ch += 4) {
-    tc_wait_ld();
-    if (ch + 2 < nch) AT_LOAD(rb, pb, ch + 2);
-    row_pass1<MODE>(ra, pa, p.S - ch * 32, acc);
-    if (ch + 2 >= nch) break;
-    tc_wait_ld();
-    if (ch + 4 < nch) AT_LOAD(ra, pa, ch + 4);
-    row_pass1<MODE>(rb, pb, p.S - (ch + 2) * 32, acc);
-  }
-  red[half * 128 + row] = MODE == 0 ? fmaxf(fmaxf(acc[0], acc[1]), fmaxf(acc[2], acc[3])) : (acc[0] + acc[1]) + (acc[2] + acc[3]);
-  __syncwarp();
-  if (half < nch) AT_LOAD(ra, pa, half);           // pass 2's first chunk is in flight across the barrier (T1 is read-only here)
-  asm volatile("bar.sync 1, %0;" ::"n"(32 * kAtRowWarps) : "memory");      // (also: every warp's X / staging stores have drained)
-  const float shift = MODE == 0 ? fmaxf(red[row], red[128 + row]) * p.c_exp : red[row] + red[128 + row];
-  // ---- pass 2
   float sum[4] = {0.f, 0.f, 0.f, 0.f};
   for (int ch = half; ch < nch; ch += 4) {
     tc_wait_ld();
-    if (ch + 2 < nch) AT_LOAD(rb, pb, ch + 2);
-    row_pass2<MODE>(p, ra, pa, p.S - ch * 32, shift, rc.xrow + (ch >> 1) * 16384, (uint32_t)((ch & 1) * 4), rc.sw, sum);
+    if (ch + 2 < nch) tc_ld32_issue(rc.tb + (ch + 2) * 32, rb);
+    if (MODE == 0) row_fwd_exp(p, ra, p.S - ch * 32, shift, sum, rc.xrow + (ch >> 1) * 16384, (uint32_t)((ch & 1) * 4), rc.sw);
+    else row_bwd_chunk(p, ra, p.S - ch * 32, shift, rc.xrow + (ch >> 1) * 16384, (uint32_t)((ch & 1) * 4), rc.sw);
     if (ch + 2 >= nch) break;
     tc_wait_ld();
-    if (ch + 4 < nch) AT_LOAD(ra, pa, ch + 4);
-    row_pass2<MODE>(p, rb, pb, p.S - (ch + 2) * 32, shift, rc.xrow + ((ch + 2) >> 1) * 16384, (uint32_t)((ch & 1) * 4), rc.sw, sum);
+    if (ch + 4 < nch) tc_ld32_issue(rc.tb + (ch + 4) * 32, ra);
+    if (MODE == 0) row_fwd_exp(p, rb, p.S - (ch + 2) * 32, shift, sum, rc.xrow + ((ch + 2) >> 1) * 16384, (uint32_t)((ch & 1) * 4), rc.sw);
+    else row_bwd_chunk(p, rb, p.S - (ch + 2) * 32, shift, rc.xrow + ((ch + 2) >> 1) * 16384, (uint32_t)((ch & 1) * 4), rc.sw);
   }
-#undef AT_LOAD
   if (half == 0) {                               // zero the key columns [32 * nch, 64 * nkx) nobody computes
     for (int pc = nch * 4; pc < p.nkx * 8; ++pc)
       st_shared_v4(rc.xrow + (pc >> 3) * 16384 + ((((uint32_t)(pc & 7)) ^ rc.sw) << 4), 0u, 0u, 0u, 0u);
   }
   if (MODE == 0) {
-    // ---- pass 3: normalise this thread's pieces in place by 1 / rowsum
+    // ---- pass 3 (shared memory only): normalise this thread's pieces in place by 1 / rowsum
     red[256 + half * 128 + row] = (sum[0] + sum[1]) + (sum[2] + sum[3]);
     __syncwarp();
     asm volatile("bar.sync 1, %0;" ::"n"(32 * kAtRowWarps) : "memory");
@@ -204,6 +197,35 @@ __device__ __forceinline__ void row_op(const AtParams& p, const RowCtx& rc, cons
   }
 }
 
+// delta_i = sum_d dO[i, d] * O[i, d] for the 128 rows of one tile: one warp per row, coalesced 16-byte loads, 4 rows in flight
+__device__ __forceinline__ void at_delta(const AtParams& p, const AtTile& c, int ew, int lane, float* out) {
+  const int64_t hb = (int64_t)c.b * p.do_bs + (int64_t)c.head * p.do_hs;
+  const int npc = p.dh >> 3;
+  for (int r0 = ew; r0 < kBlockM; r0 += 4 * kAtRowWarps) {
+    float d[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int r = r0 + u * kAtRowWarps;
+      if (c.q0 + r < p.Lq) {
+        const int64_t off = hb + (int64_t)(c.q0 + r) * p.do_ld;
+        for (int pc = lane; pc < npc; pc += 32) {
+          const uint4 x = __ldg(reinterpret_cast<const uint4*>(p.do_in + off + pc * 8));
+          const uint4 y = __ldg(reinterpret_cast<const uint4*>(p.o_in + off + pc * 8));
+          d[u] = fmaf(bf16lo(x.x), bf16lo(y.x), d[u]); d[u] = fmaf(bf16hi(x.x), bf16hi(y.x), d[u]);
+          d[u] = fmaf(bf16lo(x.y), bf16lo(y.y), d[u]); d[u] = fmaf(bf16hi(x.y), bf16hi(y.y), d[u]);
+          d[u] = fmaf(bf16lo(x.z), bf16lo(y.z), d[u]); d[u] = fmaf(bf16hi(x.z), bf16hi(y.z), d[u]);
+          d[u] = fmaf(bf16lo(x.w), bf16lo(y.w), d[u]); d[u] = fmaf(bf16hi(x.w), bf16hi(y.w), d[u]);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float t = warp_sum(d[u]);
+      if (lane == 0) out[r0 + u * kAtRowWarps] = t;
+    }
+  }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(kAtThreads, 1)
 attn_chain_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ CUtensorMap map_b1,
@@ -218,7 +240,7 @@ attn_chain_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
   const uint32_t sStage = sX;                                      // 8 x 4 KiB epilogue staging aliases X (dead after GEMM2)
   const uint32_t sRing = sX + p.x_bytes;
   const uint32_t sRed = sRing + p.slots * p.slot_bytes;            // 2 x [2][128] floats
-  const uint32_t bars = sRed + 2048;
+  const uint32_t bars = sRed + 2048;     // mode 0: [0,256) max / [256,512) sum exchange; mode 1: [0,256) two delta buffers
   const uint32_t full_bar = bars, empty_bar = bars + 8 * kAtMaxSlots;
   const uint32_t t1_full = bars + 16 * kAtMaxSlots, x_ready = t1_full + 8, t2_full = t1_full + 16, t_empty = t1_full + 24;
   const uint32_t p_full = t1_full + 32;
@@ -377,6 +399,11 @@ attn_chain_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
           mbar_expect_tx(p_full, p.nkx * 16384);
           for (int kc = 0; kc < p.nkx; ++kc) tma_load_4d(sX + kc * 16384, &map_p, p_full, kc * 64, c.q0, c.head, c.b);
         }
+        // delta of this tile while GEMM1 runs.  (Measured: ~9 k cycles per tile of latency-bound global loads that GEMM1
+        // only partly hides; computing it for the next tile under GEMM2 instead put 30 k cycles on the critical path.)
+        at_delta(p, c, ew, lane, red);
+        __syncwarp();
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kAtRowWarps) : "memory");     // delta of every row is visible
       }
       const long long ra = p.prof ? clock64() : 0;
       mbar_wait(t1_full, par);
@@ -387,7 +414,7 @@ attn_chain_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
       RowCtx rc;
       rc.tb = tb; rc.xrow = xrow; rc.sw = sw; rc.half = half; rc.row = row; rc.nch = nch;
       if (lane == 0) bulk_wait_read0();              // this warp's / the X stores of the previous tile have finished reading X
-      row_op<MODE>(p, rc, c, grow, red);
+      row_op<MODE>(p, rc, red, red);
       fence_async_smem();                            // X visible to the tensor core / TMA (async proxy)
       tc_fence_before();
       __syncwarp();
@@ -494,6 +521,8 @@ static int at_plan(const jmt_attn_desc* g, AtParams* p, int* smem_bytes) {
   p->scale = g->scale;
   p->c_exp = g->scale * 1.4426950408889634f;
   p->p_in = (const __nv_bfloat16*)g->p_in;
+  p->do_in = (const __nv_bfloat16*)g->a1; p->o_in = (const __nv_bfloat16*)g->o_in;
+  p->do_ld = g->a1_ld; p->do_hs = g->a1_hs; p->do_bs = g->a1_bs;
   p->x_ld = g->x_ld;
   p->store_mode = g->store_mode;
   p->fd_qt.init(p->q_tiles);
@@ -521,7 +550,7 @@ extern "C" int jmt_attn_chain_supported(const jmt_attn_desc* g) {
 
 extern "C" int jmt_attn_chain_bf16(const jmt_attn_desc* g, void* stream) {
   JMT_REQUIRE(g && g->a1 && g->b1 && g->b2 && g->x && g->d, "jmt_attn_chain_bf16: null pointer");
-  JMT_REQUIRE(g->mode == 0 || (g->mode == 1 && g->p_in), "jmt_attn_chain_bf16: mode 1 needs the saved probabilities");
+  JMT_REQUIRE(g->mode == 0 || (g->mode == 1 && g->p_in && g->o_in), "jmt_attn_chain_bf16: mode 1 needs the saved probabilities and output");
   JMT_REQUIRE(g->store_mode == JMT_STORE || g->store_mode == JMT_ACCUMULATE, "jmt_attn_chain_bf16: bad store_mode");
   AtParams p; int smem = 0;
   if (!at_plan(g, &p, &smem) || g->x_ld % 8 != 0 || g->x_ld < g->S) {

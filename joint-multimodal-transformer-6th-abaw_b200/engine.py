@@ -493,12 +493,13 @@ FUSED_ATTENTION_BWD = False  # the fused backward (dP -> dS -> dQ) is correct bu
 
 
 def _attn_chain(ctx: Ctx, mode: int, a1, a1_geo, b1, b1_geo, b2, b2_geo, p_in, x, d, d_geo, Lq, S, dh, heads, NB, x_ld,
-                scale, store, probe_only=False):
+                scale, store, probe_only=False, o_in=None):
     """One launch of the fused attention core (include/jmt_b200.h: jmt_attn_desc).  *_geo = (ld, head stride,
     batch stride) in elements."""
     g = L.AttnDesc()
     g.a1, g.b1, g.b2 = a1.data_ptr(), b1.data_ptr(), b2.data_ptr()
     g.p_in = p_in.data_ptr() if p_in is not None else None
+    g.o_in = o_in.data_ptr() if o_in is not None else None
     g.x, g.d = x.data_ptr(), d.data_ptr()
     g.mode = mode
     g.Lq, g.S, g.dh, g.heads, g.NB = Lq, S, dh, heads, NB
@@ -576,7 +577,7 @@ def attention_core(ctx: Ctx, q: Var, qcol: int, k: Var, kcol: int, v: Var, vcol:
             if fused and FUSED_ATTENTION_BWD:
                 # dP = dO V^T -> dS = scale * P o (dP - rowsum(P o dP)) -> dQ += dS K, one kernel; dS is saved for dK
                 _attn_chain(ctx, 1, do, o_geo, vd, v_geo, kd, k_geo, probs, ds, gq_[:, qcol:qcol + E], dq_geo, Lq, S, dh,
-                            heads, NB, s_ld, scale, L.ACCUMULATE)
+                            heads, NB, s_ld, scale, L.ACCUMULATE, o_in=o)
                 dk_alpha = 1.0
             else:
                 dp = ctx.empty((NB, heads, Lq, s_ld), torch.float32)          # dP = dO V^T
