@@ -89,24 +89,45 @@ copy_rows3d_kernel(const TI* __restrict__ in, int64_t in_bs, TO* __restrict__ ou
   }
 }
 
-// (nb, R, C) -> (nb, C, R) through a padded 32x32 shared tile (coalesced both ways)
+// (nb, R, C) -> (nb, C, R) through a padded 64x64 shared tile; every thread moves PAIRS of adjacent elements on both
+// sides (4-byte accesses for bf16, 8-byte for fp32), so a warp touches 128-256 contiguous bytes per instruction.
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(256)
 transpose_kernel(const TI* __restrict__ in, TO* __restrict__ out, int R, int C, int64_t in_bs, int64_t out_bs) {
-  __shared__ float tile[32][33];
+  __shared__ float tile[64][65];
   const int64_t b = blockIdx.z;
-  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const TI* ib = in + b * in_bs;
   TO* ob = out + b * out_bs;
-  for (int i = ty; i < 32; i += 8) {
-    const int r = r0 + i, c = c0 + tx;
-    tile[i][tx] = (r < R && c < C) ? to_f32(ib[(int64_t)r * C + c]) : 0.f;
+  const bool in_vec = (C % 2 == 0) && (in_bs % 2 == 0) && ((reinterpret_cast<uintptr_t>(in) & (2 * sizeof(TI) - 1)) == 0);
+  const bool out_vec = (R % 2 == 0) && (out_bs % 2 == 0) && ((reinterpret_cast<uintptr_t>(out) & (2 * sizeof(TO) - 1)) == 0);
+  for (int i = ty; i < 64; i += 8) {
+    const int r = r0 + i, c = c0 + 2 * tx;
+    float v0 = 0.f, v1 = 0.f;
+    if (r < R) {
+      if (in_vec && c + 1 < C) {
+        if constexpr (sizeof(TI) == 2) { const __nv_bfloat162 t = *reinterpret_cast<const __nv_bfloat162*>(ib + (int64_t)r * C + c); v0 = __low2float(t); v1 = __high2float(t); }
+        else { const float2 t = *reinterpret_cast<const float2*>(ib + (int64_t)r * C + c); v0 = t.x; v1 = t.y; }
+      } else {
+        if (c < C) v0 = to_f32(ib[(int64_t)r * C + c]);
+        if (c + 1 < C) v1 = to_f32(ib[(int64_t)r * C + c + 1]);
+      }
+    }
+    tile[i][2 * tx] = v0; tile[i][2 * tx + 1] = v1;
   }
   __syncthreads();
-  for (int i = ty; i < 32; i += 8) {
-    const int c = c0 + i, r = r0 + tx;
-    if (r < R && c < C) ob[(int64_t)c * R + r] = from_f32<TO>(tile[tx][i]);
+  for (int i = ty; i < 64; i += 8) {
+    const int c = c0 + i, r = r0 + 2 * tx;
+    if (c >= C) continue;
+    const float v0 = tile[2 * tx][i], v1 = tile[2 * tx + 1][i];
+    if (out_vec && r + 1 < R) {
+      if constexpr (sizeof(TO) == 2) *reinterpret_cast<__nv_bfloat162*>(ob + (int64_t)c * R + r) = __floats2bfloat162_rn(v0, v1);
+      else *reinterpret_cast<float2*>(ob + (int64_t)c * R + r) = make_float2(v0, v1);
+    } else {
+      if (r < R) ob[(int64_t)c * R + r] = from_f32<TO>(v0);
+      if (r + 1 < R) ob[(int64_t)c * R + r + 1] = from_f32<TO>(v1);
+    }
   }
 }
 
@@ -248,16 +269,20 @@ dropout_mask_kernel(uint8_t* __restrict__ mask, int64_t n, float p, uint64_t see
   }
 }
 
-// weight_norm: one block per output channel
+// weight_norm: w = g * v / ||v|| per output channel (legacy torch weight_norm), emitted in the two
+// implicit-GEMM layouts.  One block per output channel stages its (cin, k) slice in shared memory so that both the
+// read of v (cin-major, tap-minor) and the write of w_fwd (tap-major, cin-minor) are coalesced; the dgrad layout
+// (cin, k*cout) is a per-tap transpose of w_fwd done by a tiled kernel (coalesced both ways).
 template <typename TO>
 __global__ void __launch_bounds__(256)
 weight_norm_fwd_kernel(const float* __restrict__ g, const float* __restrict__ v, TO* __restrict__ w_fwd,
-                       TO* __restrict__ w_dgrad, float* __restrict__ norm, int cout, int cin, int k) {
+                       float* __restrict__ norm, int cout, int cin, int k) {
+  extern __shared__ float wn_sh[];            // inner floats
   const int co = blockIdx.x;
   const int inner = cin * k;
   const float* vr = v + (int64_t)co * inner;
   float ss = 0.f;
-  for (int i = threadIdx.x; i < inner; i += blockDim.x) ss = fmaf(vr[i], vr[i], ss);
+  for (int i = threadIdx.x; i < inner; i += blockDim.x) { const float x = vr[i]; wn_sh[i] = x; ss = fmaf(x, x, ss); }
   __shared__ float sh[8];
   ss = warp_sum(ss);
   if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = ss;
@@ -268,26 +293,51 @@ weight_norm_fwd_kernel(const float* __restrict__ g, const float* __restrict__ v,
   const float nrm = sqrtf(tot);
   if (threadIdx.x == 0 && norm) norm[co] = nrm;
   const float sc = g[co] / nrm;
-  for (int i = threadIdx.x; i < inner; i += blockDim.x) {
-    const int ci = i / k, j = i - ci * k;
-    const TO w = from_f32<TO>(vr[i] * sc);
-    w_fwd[(int64_t)co * inner + (int64_t)j * cin + ci] = w;
-    if (w_dgrad) w_dgrad[(int64_t)ci * ((int64_t)k * cout) + (int64_t)j * cout + co] = w;
+  for (int o = threadIdx.x; o < inner; o += blockDim.x) {        // o = j * cin + ci  <-  v index ci * k + j
+    const int j = o / cin, ci = o - j * cin;
+    w_fwd[(int64_t)co * inner + o] = from_f32<TO>(wn_sh[ci * k + j] * sc);
   }
 }
 
+// w_dgrad[ci, j*cout + co] = w_fwd[co, j*cin + ci]: per tap j (blockIdx.z) a (cout x cin) -> (cin x cout) transpose with row
+// pitches k*cin / k*cout, 32x32 tiles through shared memory
+template <typename T>
+__global__ void __launch_bounds__(256)
+weight_norm_dgrad_layout_kernel(const T* __restrict__ w_fwd, T* __restrict__ w_dgrad, int cout, int cin, int k) {
+  __shared__ float tile[32][33];
+  const int j = blockIdx.z;
+  const int co0 = blockIdx.y * 32, ci0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8) {
+    const int co = co0 + i, ci = ci0 + tx;
+    tile[i][tx] = (co < cout && ci < cin) ? to_f32(w_fwd[(int64_t)co * k * cin + (int64_t)j * cin + ci]) : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int ci = ci0 + i, co = co0 + tx;
+    if (ci < cin && co < cout) w_dgrad[(int64_t)ci * k * cout + (int64_t)j * cout + co] = from_f32<T>(tile[tx][i]);
+  }
+}
+
+// dg[co] = <dw, v> / ||v||,  dv = g/||v|| * (dw - v * <dw, v> / ||v||^2); dw arrives tap-major (co, j*cin + ci): both rows are
+// staged in shared memory so every global access is coalesced
 __global__ void __launch_bounds__(256)
 weight_norm_bwd_kernel(const float* __restrict__ dw_fwd, const float* __restrict__ g, const float* __restrict__ v,
                        const float* __restrict__ norm, float* __restrict__ dg, float* __restrict__ dv, int cout,
                        int cin, int k) {
+  extern __shared__ float wn_sh[];            // [0, inner): v row (ci*k + j order), [inner, 2*inner): dw row (j*cin + ci order)
   const int co = blockIdx.x;
   const int inner = cin * k;
+  float* vs = wn_sh;
+  float* ds = wn_sh + inner;
   const float* vr = v + (int64_t)co * inner;
   const float* dwr = dw_fwd + (int64_t)co * inner;
+  for (int i = threadIdx.x; i < inner; i += blockDim.x) { vs[i] = vr[i]; ds[i] = dwr[i]; }
+  __syncthreads();
   float dot = 0.f;
-  for (int i = threadIdx.x; i < inner; i += blockDim.x) {
-    const int ci = i / k, j = i - ci * k;
-    dot = fmaf(dwr[(int64_t)j * cin + ci], vr[i], dot);
+  for (int o = threadIdx.x; o < inner; o += blockDim.x) {        // o = j * cin + ci
+    const int j = o / cin, ci = o - j * cin;
+    dot = fmaf(ds[o], vs[ci * k + j], dot);
   }
   __shared__ float sh[8];
   dot = warp_sum(dot);
@@ -299,9 +349,9 @@ weight_norm_bwd_kernel(const float* __restrict__ dw_fwd, const float* __restrict
   const float nrm = norm[co];
   if (threadIdx.x == 0) dg[co] = tot / nrm;
   const float sc = g[co] / nrm, proj = tot / (nrm * nrm);
-  for (int i = threadIdx.x; i < inner; i += blockDim.x) {
+  for (int i = threadIdx.x; i < inner; i += blockDim.x) {        // i = ci * k + j
     const int ci = i / k, j = i - ci * k;
-    dv[(int64_t)co * inner + i] = sc * (dwr[(int64_t)j * cin + ci] - vr[i] * proj);
+    dv[(int64_t)co * inner + i] = sc * (ds[j * cin + ci] - vs[i] * proj);
   }
 }
 
@@ -449,7 +499,7 @@ extern "C" int jmt_transpose_strided(const void* in, int in_dtype, int64_t in_bs
   if (nb * R * C == 0) return JMT_OK;
   if (in_bs == 0) in_bs = (int64_t)R * C;
   if (out_bs == 0) out_bs = (int64_t)R * C;
-  dim3 grid((C + 31) / 32, (R + 31) / 32, (unsigned)nb);
+  dim3 grid((C + 63) / 64, (R + 63) / 64, (unsigned)nb);
   cudaStream_t st = (cudaStream_t)stream;
   JMT_DISPATCH_DTYPE(in_dtype, TI, JMT_DISPATCH_DTYPE(out_dtype, TO,
       (transpose_kernel<TI, TO><<<grid, 256, 0, st>>>((const TI*)in, (TO*)out, R, C, in_bs, out_bs))));
@@ -525,14 +575,27 @@ extern "C" int jmt_dropout_mask(uint8_t* mask, int64_t n, float p, uint64_t seed
 extern "C" int jmt_weight_norm_fwd(const float* g, const float* v, void* w_fwd, void* w_dgrad, int out_dtype, float* norm,
                                    int cout, int cin, int k, void* stream) {
   JMT_REQUIRE(g && v && w_fwd && cout > 0 && cin > 0 && k > 0, "jmt_weight_norm_fwd: bad arguments");
-  JMT_DISPATCH_DTYPE(out_dtype, TO, (weight_norm_fwd_kernel<TO><<<cout, 256, 0, (cudaStream_t)stream>>>(g, v, (TO*)w_fwd, (TO*)w_dgrad, norm, cout, cin, k)));
-  return check_launch("weight_norm_fwd_kernel");
+  const size_t sh = (size_t)cin * k * sizeof(float);
+  JMT_REQUIRE(sh <= 96 * 1024, "jmt_weight_norm_fwd: cin*k too large for the shared-memory staging (%d x %d)", cin, k);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (sh > 48 * 1024) {
+    JMT_DISPATCH_DTYPE(out_dtype, TO, cudaFuncSetAttribute(weight_norm_fwd_kernel<TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+  }
+  JMT_DISPATCH_DTYPE(out_dtype, TO, (weight_norm_fwd_kernel<TO><<<cout, 256, sh, st>>>(g, v, (TO*)w_fwd, norm, cout, cin, k)));
+  int rc = check_launch("weight_norm_fwd_kernel");
+  if (rc != JMT_OK || !w_dgrad) return rc;
+  dim3 grid((cin + 31) / 32, (cout + 31) / 32, k);
+  JMT_DISPATCH_DTYPE(out_dtype, TO, (weight_norm_dgrad_layout_kernel<TO><<<grid, 256, 0, st>>>((const TO*)w_fwd, (TO*)w_dgrad, cout, cin, k)));
+  return check_launch("weight_norm_dgrad_layout_kernel");
 }
 
 extern "C" int jmt_weight_norm_bwd(const float* dw_fwd, const float* g, const float* v, const float* norm, float* dg,
                                    float* dv, int cout, int cin, int k, void* stream) {
   JMT_REQUIRE(dw_fwd && g && v && norm && dg && dv, "jmt_weight_norm_bwd: bad arguments");
-  weight_norm_bwd_kernel<<<cout, 256, 0, (cudaStream_t)stream>>>(dw_fwd, g, v, norm, dg, dv, cout, cin, k);
+  const size_t sh = 2 * (size_t)cin * k * sizeof(float);
+  JMT_REQUIRE(sh <= 96 * 1024, "jmt_weight_norm_bwd: cin*k too large for the shared-memory staging (%d x %d)", cin, k);
+  if (sh > 48 * 1024) cudaFuncSetAttribute(weight_norm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+  weight_norm_bwd_kernel<<<cout, 256, sh, (cudaStream_t)stream>>>(dw_fwd, g, v, norm, dg, dv, cout, cin, k);
   return check_launch("weight_norm_bwd_kernel");
 }
 
