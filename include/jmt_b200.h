@@ -238,6 +238,11 @@ int jmt_transpose_strided(const void* in, int in_dtype, int64_t in_bs, void* out
 /* out[b*out_bs + r*cols + c] = cast(in[b*in_bs + r*cols + c])  (nb, rows, cols) blocks: pad / unpad of the flat layout */
 int jmt_copy_rows3d(const void* in, int in_dtype, int64_t in_bs, void* out, int out_dtype, int64_t out_bs, int64_t nb,
                     int64_t rows, int cols, void* stream);
+/* max over time of channels-last sequences without materialising `transpose(1,2)` (I3DWSDDA.py:44 then
+ * tsav.py:216 `torch.max(ft, 1)`): x element (n, t, c) at x[n*batch_stride + t*C + c], t < L; out (nb, C) in `dtype`,
+ * arg (nb, C) = first t attaining the maximum; backward scatters dout to those positions of a pre-zeroed dx. */
+int jmt_time_max_fwd(const void* x, int64_t batch_stride, int64_t nb, int L, int C, void* out, int32_t* arg, int dtype, void* stream);
+int jmt_time_max_bwd(const void* dout, const int32_t* arg, int64_t batch_stride, int64_t nb, int C, void* dx, int dtype, void* stream);
 /* out = LeakyReLU(a + b)  (TemporalBlock.forward, temporal_convolutional_model.py:54-57) */
 int jmt_add_act(const void* a, const void* b, void* out, int64_t n, int act, float slope, int dtype, void* stream);
 /* channel dropout (nn.Dropout2d on (N,C,L)) / element dropout with an explicit

@@ -15,3 +15,4 @@ from . import padseq  # noqa: F401
 from . import dist  # noqa: F401
 from .graphs import GraphedStep  # noqa: F401
 from . import valpost  # noqa: F401
+from . import checkpoint  # noqa: F401

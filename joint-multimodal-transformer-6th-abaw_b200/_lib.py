@@ -83,6 +83,8 @@ SIGNATURES = {
     "jmt_transpose_strided": [_P, _I, _L, _P, _I, _L, _L, _I, _I, _P],
     "jmt_copy_rows3d": [_P, _I, _L, _P, _I, _L, _L, _L, _I, _P],
     "jmt_add_act": [_P, _P, _P, _L, _I, _F, _I, _P],
+    "jmt_time_max_fwd": [_P, _L, _L, _I, _I, _P, _P, _I, _P],
+    "jmt_time_max_bwd": [_P, _P, _L, _L, _I, _P, _I, _P],
     "jmt_apply_mask": [_P, _P, _P, _L, _I, _I, _I, _F, _I, _P],
     "jmt_dropout_mask": [_P, _L, _F, _U64, _U64, _P],
     "jmt_weight_norm_fwd": [_P, _P, _P, _P, _I, _P, _I, _I, _I, _P],

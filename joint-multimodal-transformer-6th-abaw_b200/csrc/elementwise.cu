@@ -355,6 +355,31 @@ weight_norm_bwd_kernel(const float* __restrict__ dw_fwd, const float* __restrict
   }
 }
 
+// max over time of a channels-last sequence batch (`temporal(features).transpose(1,2)` then
+// `torch.max(ft, 1)`, I3DWSDDA.py:44 + tsav.py:216, without materialising the transpose): x rows n*bs_rows + t, t < L.
+// out (N, C) in the activation dtype, arg (N, C) int32 = first t attaining the maximum (torch.max tie rule).
+template <typename T>
+__global__ void __launch_bounds__(256)
+time_max_fwd_kernel(const T* __restrict__ x, int64_t batch_stride, int L, int C, int64_t total, T* __restrict__ out, int32_t* __restrict__ arg) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t n = i / C; const int c = (int)(i - n * C);
+    const T* p = x + n * batch_stride + c;
+    float best = to_f32(p[0]); int bi = 0;
+    for (int t = 1; t < L; ++t) { const float v = to_f32(p[(int64_t)t * C]); if (v > best) { best = v; bi = t; } }
+    out[i] = from_f32<T>(best);
+    arg[i] = bi;
+  }
+}
+// dx[n, arg[n,c], c] = dout[n, c] (dx pre-zeroed)
+template <typename T>
+__global__ void __launch_bounds__(256)
+time_max_bwd_kernel(const T* __restrict__ dout, const int32_t* __restrict__ arg, int64_t batch_stride, int C, int64_t total, T* __restrict__ dx) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t n = i / C; const int c = (int)(i - n * C);
+    dx[n * batch_stride + (int64_t)arg[i] * C + c] = dout[i];
+  }
+}
+
 // ---------------------------------------------------------------- tiny-sequence attention
 constexpr int kMaxSmallL = 8;
 
@@ -597,6 +622,22 @@ extern "C" int jmt_weight_norm_bwd(const float* dw_fwd, const float* g, const fl
   if (sh > 48 * 1024) cudaFuncSetAttribute(weight_norm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
   weight_norm_bwd_kernel<<<cout, 256, sh, (cudaStream_t)stream>>>(dw_fwd, g, v, norm, dg, dv, cout, cin, k);
   return check_launch("weight_norm_bwd_kernel");
+}
+
+extern "C" int jmt_time_max_fwd(const void* x, int64_t batch_stride, int64_t nb, int L, int C, void* out, int32_t* arg, int dtype, void* stream) {
+  JMT_REQUIRE(x && out && arg && nb >= 0 && L >= 1 && C >= 1, "jmt_time_max_fwd: bad arguments");
+  if (nb == 0) return JMT_OK;
+  const int64_t total = nb * C;
+  JMT_DISPATCH_DTYPE(dtype, T, (time_max_fwd_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const T*)x, batch_stride, L, C, total, (T*)out, arg)));
+  return check_launch("time_max_fwd_kernel");
+}
+
+extern "C" int jmt_time_max_bwd(const void* dout, const int32_t* arg, int64_t batch_stride, int64_t nb, int C, void* dx, int dtype, void* stream) {
+  JMT_REQUIRE(dout && arg && dx && nb >= 0 && C >= 1, "jmt_time_max_bwd: bad arguments");
+  if (nb == 0) return JMT_OK;
+  const int64_t total = nb * C;
+  JMT_DISPATCH_DTYPE(dtype, T, (time_max_bwd_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const T*)dout, arg, batch_stride, C, total, (T*)dx)));
+  return check_launch("time_max_bwd_kernel");
 }
 
 extern "C" int jmt_attn_small_fwd(const void* qkv, void* out, float* probs, int L, int64_t N, int E, int heads,

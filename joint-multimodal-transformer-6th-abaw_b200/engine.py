@@ -985,6 +985,29 @@ def unpad_rows(ctx: Ctx, x: Var, N: int, Ls: int, pad: int) -> Var:
     return out
 
 
+def time_max(ctx: Ctx, x: Var, N: int, Ls: int, pad: int) -> Var:
+    """max over the L positions of every sequence of a flat padded channels-last Var -> (N, C) Var
+    (`torch.max(temporal(...).transpose(1,2), 1)`: I3DWSDDA.py:44 + tsav.py:216)."""
+    Cc = x.data.shape[1]
+    Lp = Ls + pad
+    y = ctx.empty((N, Cc))
+    arg = ctx.empty((N, Cc), torch.int32)
+    L.check(ctx.lib.jmt_time_max_fwd(_ptr(x.data[pad:]), Lp * Cc, N, Ls, Cc, _ptr(y), _ptr(arg), ctx.acode, _stream()), "jmt_time_max_fwd")
+    out = Var(y)
+    if ctx.record:
+        def bwd():
+            if out.grad is None:
+                return
+            gb = GradBuf(ctx.zeros((N * Lp, Cc)))
+            L.check(ctx.lib.jmt_time_max_bwd(_ptr(out.grad), _ptr(arg), Lp * Cc, N, Cc, _ptr(gb.t[pad:]), ctx.acode, _stream()),
+                    "jmt_time_max_bwd")
+            ctx.add_grad(x, gb)
+            gb.refs -= 1
+            ctx.release(out)
+        ctx.tape.append(bwd)
+    return out
+
+
 def to_external(ctx: Ctx, x: Var, shape):
     """Activation Var -> external fp32 tensor of `shape` (row-major compatible); returns (tensor, setter)."""
     out = ctx.empty(shape, torch.float32)

@@ -574,6 +574,25 @@ class TemporalConvNet(_JmtModule):
             return [out], [setter], [gx]
         return self._run(runner, x)[0]
 
+    def forward_sequence_features(self, x, max_over_time: bool = False):
+        """The way the reference consumes the TCN: `temporal(features).transpose(1, 2)` ->
+        (N, L, C_last) (I3D_WSDDA.forward, I3DWSDDA.py:44); with max_over_time the `torch.max(ft, 1)` of
+        tsav.py:216 is fused in -> (N, C_last).  x: (N, C, L).  No (N, C_last, L) tensor is ever materialised."""
+        N, C0, Ls = x.shape
+        specs = self.block_specs()
+
+        def runner(ctx, xin):
+            pad = E.tcn_pad(specs)
+            h, gx = E.transpose_in(ctx, xin, xin.requires_grad, pad)
+            h = _tcn_graph(ctx, h, "", specs, N, Ls, pad)
+            Cl = h.data.shape[1]
+            if max_over_time:
+                out, setter = E.to_external(ctx, E.time_max(ctx, h, N, Ls, pad), (N, Cl))
+            else:
+                out, setter = E.to_external(ctx, E.unpad_rows(ctx, h, N, Ls, pad), (N, Ls, Cl))
+            return [out], [setter], [gx]
+        return self._run(runner, x)[0]
+
 
 def _tcn_graph(ctx, h, prefix, specs, N, Ls, pad):
     """TemporalConvNet.forward on the flat padded channels-last layout (row = n*(pad+L) + pad + t, engine.py "TCN ops"):

@@ -130,3 +130,30 @@ def test_data_parallel_host_logic_gloo_world2():
         p.join(60)
     assert [r[1] for r in res] == [True, True], res
     assert res[0][2] == (0, 500) and res[1][2] == (500, 1001)
+
+
+def test_checkpoint_roundtrip_reference_file_names(tmp_path):
+    """state_dicts are written under the reference's file names (main.py:116-176), load back with
+    strict=True (incl. a DataParallel `module.` prefix, main.py:54-70), and optimizer state makes a true resume."""
+    import jmt_b200
+    from jmt_b200 import checkpoint as CK
+    torch.manual_seed(0)
+    fusion = jmt_b200.Two_transformers(0.0, 0.0, 2, 1, "FC", "FC", 512, precision="fp32")
+    fc = jmt_b200.FcLayer(768, 512, precision="fp32")
+    opt = torch.optim.SGD(list(fusion.parameters()) + list(fc.parameters()), lr=0.1, momentum=0.9)
+    for p in fusion.parameters():
+        p.grad = torch.ones_like(p)
+    opt.step()                                            # creates momentum buffers
+    CK.dump_models_into_disk(str(tmp_path), {"fusion_model": fusion, "fc_layer_for_audio_concat": fc}, epoch=7, optimizer=opt)
+    assert sorted(os.listdir(tmp_path)) == ["fc_layer_for_audio_concat.pt", "fusion_w.pt", "resume_state.pt"]
+    # a DataParallel-style checkpoint of the same weights
+    sd = torch.load(os.path.join(tmp_path, "fusion_w.pt"), weights_only=True)
+    torch.save({"module." + k: v for k, v in sd.items()}, os.path.join(tmp_path, "fusion_w.pt"))
+    fusion2 = jmt_b200.Two_transformers(0.0, 0.0, 2, 1, "FC", "FC", 512, precision="fp32")
+    fc2 = jmt_b200.FcLayer(768, 512, precision="fp32")
+    opt2 = torch.optim.SGD(list(fusion2.parameters()) + list(fc2.parameters()), lr=0.1, momentum=0.9)
+    info = CK.load_models_from_disk(str(tmp_path), {"fusion_model": fusion2, "fc_layer_for_audio_concat": fc2}, optimizer=opt2)
+    assert info["epoch"] == 7
+    for (k, a), (_, b) in zip(fusion.state_dict().items(), fusion2.state_dict().items()):
+        assert torch.equal(a, b), k
+    assert len(opt2.state_dict()["state"]) == len(opt.state_dict()["state"]) > 0

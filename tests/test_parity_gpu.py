@@ -296,3 +296,34 @@ def test_graphed_step_matches_eager():
     num = sum(float((a - b).norm() ** 2) for a, b in zip(pe, pg)) ** 0.5
     den = sum(float(a.norm() ** 2) for a in pe) ** 0.5
     assert num / den < 1e-3, num / den
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_tcn_sequence_features_and_time_max(precision, golden_meta, golden_dir):
+    """temporal(x).transpose(1,2) (I3DWSDDA.py:44) and the fused torch.max(ft, 1) (tsav.py:216) on the
+    reference-faithful placement (many clips of L = 7), against the golden TCN output of the reference."""
+    m = golden_meta["tcn_1024_512x4_k5_L7"]
+    g = np.load(os.path.join(golden_dir, "tcn_1024_512x4_k5_L7.npz"))
+    params = O.synth_params(O.tcn_shapes(m["cin"], m["chans"], m["k"]), m["param_seed"])
+    model = jmt_b200.TemporalConvNet(m["cin"], m["chans"], kernel_size=m["k"], attention=0, dropout=0.1, precision=precision)
+    model.load_state_dict(O.tcn_state_dict(params), strict=True)
+    model = model.to(DEV).eval()
+    gen = torch.Generator().manual_seed(m["x_seed"])
+    x = torch.randn(m["N"], m["cin"], m["L"], generator=gen)
+    ref = torch.from_numpy(g["out"]).transpose(1, 2)                     # (N, L, 512)
+    xd = x.to(DEV).requires_grad_(True)
+    seq = model.forward_sequence_features(xd)
+    assert tuple(seq.shape) == tuple(ref.shape)
+    assert _rel(seq.detach().cpu(), ref) < PRED_TOL[precision]
+    pooled = model.forward_sequence_features(xd, max_over_time=True)
+    want, idx = ref.max(1)
+    assert _rel(pooled.detach().cpu(), want) < PRED_TOL[precision]
+    # backward of the pooled path = backward of gathering the arg-max positions of the sequence path
+    w = torch.linspace(-1, 1, pooled.numel()).reshape(pooled.shape).to(DEV)
+    (pooled * w).sum().backward()
+    g_pool = xd.grad.clone()
+    xd.grad = None
+    seq2 = model.forward_sequence_features(xd)
+    am = seq2.detach().argmax(1, keepdim=True)
+    (seq2.gather(1, am).squeeze(1) * w).sum().backward()
+    assert _rl2(g_pool.cpu(), xd.grad.cpu()) < (1e-4 if precision == "fp32" else 3e-2)
