@@ -16,3 +16,4 @@ from . import dist  # noqa: F401
 from .graphs import GraphedStep  # noqa: F401
 from . import valpost  # noqa: F401
 from . import checkpoint  # noqa: F401
+from . import features  # noqa: F401

@@ -157,3 +157,27 @@ def test_checkpoint_roundtrip_reference_file_names(tmp_path):
     for (k, a), (_, b) in zip(fusion.state_dict().items(), fusion2.state_dict().items()):
         assert torch.equal(a, b), k
     assert len(opt2.state_dict()["state"]) == len(opt.state_dict()["state"]) > 0
+
+
+def test_feature_shard_roundtrip(tmp_path):
+    """a packed shard round-trips bit-exactly (bf16 features = torch's round-to-nearest-even, fp32 labels
+    with the -5 sentinel untouched)."""
+    from jmt_b200 import features as F
+    rng = np.random.RandomState(0)
+    W, T = 5, 12
+    vis = rng.randn(W, 32, T).astype(np.float32)
+    aud = rng.randn(W, T, 24).astype(np.float32)
+    lv = rng.uniform(-1, 1, (W, T)).astype(np.float32)
+    la = rng.uniform(-1, 1, (W, T)).astype(np.float32)
+    lv[0, 3] = -5.0
+    p = str(tmp_path / "a.jmtshard")
+    F.write_shard(p, vis, aud, lv, la)
+    s = F.Shard(p)
+    assert s.header["windows"] == W and s.header["seq_len"] == T
+    want_v = torch.from_numpy(vis).to(torch.bfloat16)
+    got_v = torch.from_numpy(np.array(s.visual).view(np.int16)).view(torch.bfloat16)
+    assert torch.equal(got_v, want_v)
+    got_a = torch.from_numpy(np.array(s.audio).view(np.int16)).view(torch.bfloat16)
+    assert torch.equal(got_a, torch.from_numpy(aud).to(torch.bfloat16))
+    assert np.array_equal(np.array(s.labels_v), lv) and np.array_equal(np.array(s.labels_a), la)
+    assert os.path.getsize(p) == F.HEADER_BYTES + W * 32 * T * 2 + W * T * 24 * 2 + 2 * W * T * 4

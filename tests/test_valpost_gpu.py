@@ -59,3 +59,36 @@ def test_valpost_on_engine_predictions():
     accv, acca, _, _ = VO.val_ccc(batches, lengths)
     gv, ga = acc.finalize()
     assert abs(gv - accv) < 1e-6 and abs(ga - acca) < 1e-6
+
+
+def test_feature_shard_loader(tmp_path):
+    """the asynchronous loader yields every window of its rank's share once, in order, bit-exact."""
+    from jmt_b200 import features as F
+    rng = np.random.RandomState(1)
+    W, T, B = 22, 10, 4
+    paths = []
+    allv, alll = [], []
+    for k in range(2):
+        vis = rng.randn(W, 16, T).astype(np.float32)
+        aud = rng.randn(W, T, 8).astype(np.float32)
+        lv = rng.uniform(-1, 1, (W, T)).astype(np.float32)
+        la = rng.uniform(-1, 1, (W, T)).astype(np.float32)
+        p = str(tmp_path / f"s{k}.jmtshard")
+        F.write_shard(p, vis, aud, lv, la)
+        paths.append(p)
+        allv.append(torch.from_numpy(vis).to(torch.bfloat16))
+        alll.append(torch.from_numpy(lv))
+    for rank, world in ((0, 1), (1, 2)):
+        got_v, got_l = [], []
+        for aud_d, vis_d, lv_d, la_d in F.FeatureShardLoader(paths, B, "cuda", rank=rank, world=world):
+            assert vis_d.is_cuda and vis_d.dtype == torch.bfloat16 and tuple(vis_d.shape) == (B, 16, T)
+            got_v.append(vis_d.cpu().clone())
+            got_l.append(lv_d.cpu().clone())
+        want_v, want_l = [], []
+        for k in range(2):
+            lo, hi = (rank * W) // world, ((rank + 1) * W) // world
+            nfull = (hi - lo) // B * B
+            want_v.append(allv[k][lo:lo + nfull])
+            want_l.append(alll[k][lo:lo + nfull])
+        assert torch.equal(torch.cat(got_v), torch.cat(want_v))
+        assert torch.equal(torch.cat(got_l), torch.cat(want_l))
