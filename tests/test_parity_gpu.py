@@ -327,3 +327,46 @@ def test_tcn_sequence_features_and_time_max(precision, golden_meta, golden_dir):
     am = seq2.detach().argmax(1, keepdim=True)
     (seq2.gather(1, am).squeeze(1) * w).sum().backward()
     assert _rl2(g_pool.cpu(), xd.grad.cpu()) < (1e-4 if precision == "fp32" else 3e-2)
+
+
+def test_full_size_properties():
+    """BASELINE.json configs[1] size (B=256 windows, T=300): the oracle cannot run it in seconds, so parity is carried by
+    size-independent properties of the domain:
+      (1) windows are independent (the path shards along the batch): the first 16 windows give the same
+          predictions alone as inside the full batch of 256;
+      (2) the two independent implementations (tcgen05 bf16 vs FFMA fp32 kernels) agree on 64 full-length windows;
+      (3) the six CCC sums are additive over shards (the quantity the ranks all-reduce); ccc(x, x) = 1 and, for centred x,
+          ccc(x, -x) = -1."""
+    torch.manual_seed(0)
+    B, T = 256, 300
+    mods = {}
+    for prec in ("bf16", "fp32"):
+        torch.manual_seed(1)
+        mods[prec] = jmt_b200.JMTPipeline(jmt_b200.Two_transformers(0.0, 0.0, 1, 1, "TRANSFORMER", "FC", 512, precision=prec),
+                                          jmt_b200.FcLayer(768, 512, precision=prec),
+                                          jmt_b200.TemporalConvNet(1024, [512] * 4, kernel_size=5, attention=0, dropout=0.1,
+                                                                   precision=prec)).to(DEV).eval()
+    mods["fp32"].load_state_dict(mods["bf16"].state_dict(), strict=True)
+    gen = torch.Generator().manual_seed(2)
+    aud = torch.randn(B, T, 768, generator=gen).to(DEV)
+    vis = torch.randn(B, 1024, T, generator=gen).to(DEV)
+    with torch.no_grad():
+        v_full, a_full = mods["bf16"](aud, vis)                       # (T, B): SURVEY Q1
+        v_16, a_16 = mods["bf16"](aud[:16].contiguous(), vis[:16].contiguous())
+        v_32f, a_32f = mods["fp32"](aud[:64].contiguous(), vis[:64].contiguous())
+    assert tuple(v_full.shape) == (T, B)
+    # (1) every kernel reduces each output element in a batch-independent order: bit-exact
+    assert torch.equal(v_full[:, :16], v_16) and torch.equal(a_full[:, :16], a_16)
+    # (2) bf16-operand tcgen05 path vs fp32 FFMA path, default-init weights
+    for got, want in ((v_full[:, :64], v_32f), (a_full[:, :64], a_32f)):
+        assert _rl2(got.cpu(), want.cpu()) < 3e-2, _rl2(got.cpu(), want.cpu())
+    # (3) CCC: shard additivity of the sums and the metric's fixed points, at the full 76 800 predictions
+    from jmt_b200.losses import six_sums
+    x = v_full.t().contiguous()                                       # (B, T)
+    y = torch.rand(B, T, generator=gen).to(DEV) * 2 - 1
+    whole = six_sums(x.reshape(1, -1), y.reshape(1, -1))
+    parts = sum(six_sums(x[i::8].reshape(1, -1).contiguous(), y[i::8].reshape(1, -1).contiguous()) for i in range(8))
+    assert torch.allclose(whole, parts, rtol=1e-12, atol=1e-9)
+    assert abs(jmt_b200.cccmetric.ccc(x.reshape(-1), x.reshape(-1)) - 1.0) < 1e-6
+    xc = (x - x.mean()).reshape(-1)
+    assert abs(jmt_b200.cccmetric.ccc(xc, -xc) + 1.0) < 1e-4
