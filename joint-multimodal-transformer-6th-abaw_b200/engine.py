@@ -72,11 +72,16 @@ def cuda_memset0(t: torch.Tensor):
 
 
 class GradBuf:
-    __slots__ = ("t", "refs")
+    """A gradient buffer.  ``written`` is None when every column holds a valid value; otherwise it lists the column
+    ranges written so far of a buffer that was allocated WITHOUT zero-filling (projection gradients whose Q | K | V
+    column slices are each produced by one attention-backward GEMM: the first write of a slice is a plain store, so the
+    236 MB memset and the read-modify-write of an accumulate are skipped)."""
+    __slots__ = ("t", "refs", "written")
 
-    def __init__(self, t):
+    def __init__(self, t, written=None):
         self.t = t
         self.refs = 1
+        self.written = written
 
 
 class Var:
@@ -90,7 +95,19 @@ class Var:
 
     @property
     def grad(self) -> Optional[torch.Tensor]:
-        return None if self.gbuf is None else self.gbuf.t
+        if self.gbuf is None:
+            return None
+        w = self.gbuf.written
+        if w is not None:                 # slice-wise buffer: it may only be consumed once every column has been written
+            cols, pos = self.gbuf.t.shape[-1], 0
+            for c0, c1 in sorted(w):
+                if c0 > pos:
+                    break
+                pos = max(pos, c1)
+            if pos < cols:
+                raise RuntimeError(f"gradient buffer consumed with unwritten columns [{pos}, ...) of {cols}")
+            self.gbuf.written = None
+        return self.gbuf.t
 
 
 class Ctx:
@@ -174,7 +191,7 @@ class Ctx:
             new = self.empty(old.t.shape, old.t.dtype)
             copy2d(self, old.t, new)
             old.refs -= 1
-            v.gbuf = GradBuf(new)
+            v.gbuf = GradBuf(new, None if old.written is None else list(old.written))
         return v.gbuf.t, L.ACCUMULATE
 
     def add_grad(self, v: Var, gb: GradBuf):
@@ -479,13 +496,34 @@ class AttnGeom:
 
 
 def _proj_grad(ctx: Ctx, v: Var) -> torch.Tensor:
-    """Gradient buffer of a projection matrix whose column slices are written by attention backward
-    (zero-filled on first touch, then accumulated)."""
+    """Gradient buffer of a Var that is written piecewise with ACCUMULATE semantics (zero-filled on first touch)."""
     if v.gbuf is None:
         v.gbuf = GradBuf(ctx.zeros(v.data.shape, v.data.dtype))
     elif v.gbuf.refs > 1:
         ctx.grad_target(v)
+    elif v.gbuf.written is not None:
+        _ = v.grad                       # checks full coverage
     return v.gbuf.t
+
+
+def _proj_grad_slice(ctx: Ctx, v: Var, c0: int, c1: int) -> Tuple[torch.Tensor, int]:
+    """Column slice [c0, c1) of the gradient buffer of projection matrix `v` and the store mode for writing it: the first
+    write of a slice STOREs into an un-initialised buffer, later writes of the same slice (a Q projection shared by two
+    attention calls) ACCUMULATE."""
+    if v.gbuf is None:
+        v.gbuf = GradBuf(ctx.empty(v.data.shape, v.data.dtype), written=[])
+    elif v.gbuf.refs > 1:
+        ctx.grad_target(v)
+    gb = v.gbuf
+    if gb.written is None:
+        return gb.t[:, c0:c1], L.ACCUMULATE
+    for (a, b) in gb.written:
+        if (a, b) == (c0, c1):
+            return gb.t[:, c0:c1], L.ACCUMULATE
+        if a < c1 and c0 < b:
+            raise RuntimeError("overlapping projection-gradient slices")
+    gb.written.append((c0, c1))
+    return gb.t[:, c0:c1], L.STORE
 
 
 FUSED_ATTENTION = True      # bf16 mode: use jmt_attn_chain_bf16 when the geometry is supported (else GEMM + softmax kernels)
@@ -571,13 +609,14 @@ def attention_core(ctx: Ctx, q: Var, qcol: int, k: Var, kcol: int, v: Var, vcol:
                 return
             assert do.is_contiguous()
             rows = NB * heads * Lq
-            gq_ = _proj_grad(ctx, q)
-            dq_geo = (gq.seq_stride * gq_.stride(0), dh, gq.batch_stride * gq_.stride(0))
+            gq_s, q_mode = _proj_grad_slice(ctx, q, qcol, qcol + E)
+            q_gld = gq_s.stride(0)
+            dq_geo = (gq.seq_stride * q_gld, dh, gq.batch_stride * q_gld)
             ds = ctx.empty((NB, heads, Lq, s_ld))
             if fused and FUSED_ATTENTION_BWD:
                 # dP = dO V^T -> dS = scale * P o (dP - rowsum(P o dP)) -> dQ += dS K, one kernel; dS is saved for dK
-                _attn_chain(ctx, 1, do, o_geo, vd, v_geo, kd, k_geo, probs, ds, gq_[:, qcol:qcol + E], dq_geo, Lq, S, dh,
-                            heads, NB, s_ld, scale, L.ACCUMULATE, o_in=o)
+                _attn_chain(ctx, 1, do, o_geo, vd, v_geo, kd, k_geo, probs, ds, gq_s, dq_geo, Lq, S, dh,
+                            heads, NB, s_ld, scale, q_mode, o_in=o)
                 dk_alpha = 1.0
             else:
                 dp = ctx.empty((NB, heads, Lq, s_ld), torch.float32)          # dP = dO V^T
@@ -587,21 +626,21 @@ def attention_core(ctx: Ctx, q: Var, qcol: int, k: Var, kcol: int, v: Var, vcol:
                 L.check(ctx.lib.jmt_softmax_bwd(_ptr(probs), ctx.acode, s_ld, _ptr(dp), s_ld, _ptr(ds), ctx.acode, s_ld,
                                                 rows, S, _stream()), "jmt_softmax_bwd")
                 del dp
-                gemm(ctx, ds, kd, gq_[:, qcol:qcol + E], M=Lq, N=dh, K=S, a_rows=Lq, b_major=L.MAJOR_MN, b_rows=S,
-                     a_ld=s_ld, b_ld=gk.seq_stride * kld, d_ld=gq.seq_stride * gq_.stride(0),
-                     nb0=heads, nb1=NB, a_bs=sb, b_bs=(dh, gk.batch_stride * kld), d_bs=(dh, gq.batch_stride * gq_.stride(0)),
-                     alpha=scale, store=L.ACCUMULATE)                          # dQ = scale * dS K
+                gemm(ctx, ds, kd, gq_s, M=Lq, N=dh, K=S, a_rows=Lq, b_major=L.MAJOR_MN, b_rows=S,
+                     a_ld=s_ld, b_ld=gk.seq_stride * kld, d_ld=gq.seq_stride * q_gld,
+                     nb0=heads, nb1=NB, a_bs=sb, b_bs=(dh, gk.batch_stride * kld), d_bs=(dh, gq.batch_stride * q_gld),
+                     alpha=scale, store=q_mode)                                # dQ = scale * dS K
                 dk_alpha = scale
-            gv = _proj_grad(ctx, v)                                        # dV = P^T dO
-            gemm(ctx, probs, do, gv[:, vcol:vcol + E], M=S, N=dh, K=Lq, a_major=L.MAJOR_MN, b_major=L.MAJOR_MN,
+            gv, v_mode = _proj_grad_slice(ctx, v, vcol, vcol + E)         # dV = P^T dO
+            gemm(ctx, probs, do, gv, M=S, N=dh, K=Lq, a_major=L.MAJOR_MN, b_major=L.MAJOR_MN,
                  a_rows=Lq, b_rows=Lq, a_ld=s_ld, b_ld=gq.seq_stride * E, d_ld=gk.seq_stride * gv.stride(0),
                  nb0=heads, nb1=NB, a_bs=sb, b_bs=(dh, gq.batch_stride * E), d_bs=(dh, gk.batch_stride * gv.stride(0)),
-                 store=L.ACCUMULATE)
-            gk_ = _proj_grad(ctx, k)                                       # dK = scale * dS^T Q
-            gemm(ctx, ds, qd, gk_[:, kcol:kcol + E], M=S, N=dh, K=Lq, a_major=L.MAJOR_MN, b_major=L.MAJOR_MN,
+                 store=v_mode)
+            gk_, k_mode = _proj_grad_slice(ctx, k, kcol, kcol + E)        # dK = scale * dS^T Q
+            gemm(ctx, ds, qd, gk_, M=S, N=dh, K=Lq, a_major=L.MAJOR_MN, b_major=L.MAJOR_MN,
                  a_rows=Lq, b_rows=Lq, a_ld=s_ld, b_ld=gq.seq_stride * qld, d_ld=gk.seq_stride * gk_.stride(0),
                  nb0=heads, nb1=NB, a_bs=sb, b_bs=(dh, gq.batch_stride * qld), d_bs=(dh, gk.batch_stride * gk_.stride(0)),
-                 alpha=dk_alpha, store=L.ACCUMULATE)
+                 alpha=dk_alpha, store=k_mode)
             ctx.release(out)
         ctx.tape.append(bwd)
     return out

@@ -264,7 +264,8 @@ def test_attention_core_bf16(case, fused):
     E.FUSED_ATTENTION = E.FUSED_ATTENTION_BWD = fused
     try:
         # projection matrices as the engine holds them: rows = batch*seq (or seq*batch for the batch-major geometry)
-        qm = (torch.randn(NB * Lq, 3 * E_) * 0.7).to(torch.bfloat16)
+        qw = E_ if cross else 3 * E_          # a cross-attention Q projection is (rows, E); self-attention packs Q | K | V
+        qm = (torch.randn(NB * Lq, qw) * 0.7).to(torch.bfloat16)
         km = (torch.randn(NB * S, 2 * E_) * 0.7).to(torch.bfloat16) if cross else None
         if batch_major:       # row = s * NB + n: "sequence" index has stride NB, batch stride 1
             gq = E.AttnGeom(Lq, NB, NB, 1)
@@ -278,7 +279,7 @@ def test_attention_core_bf16(case, fused):
         if cross:
             kv = E.Var(km.to(dev))
             out = E.attention_core(ctx, qv, 0, kv, 0, kv, E_, E_, h, gq, gk)
-            q4, k4, v4 = to4(qm, Lq, 3 * E_)[..., :E_], to4(km, S, 2 * E_)[..., :E_], to4(km, S, 2 * E_)[..., E_:]
+            q4, k4, v4 = to4(qm, Lq, E_), to4(km, S, 2 * E_)[..., :E_], to4(km, S, 2 * E_)[..., E_:]
         else:
             out = E.attention_core(ctx, qv, 0, qv, E_, qv, 2 * E_, E_, h, gq, gk)
             a4 = to4(qm, Lq, 3 * E_)
@@ -299,7 +300,7 @@ def test_attention_core_bf16(case, fused):
 
         def back(g4, L_):      # (NB, h, L, dh) -> (NB, L, E)
             return g4.permute(0, 2, 1, 3).reshape(NB, L_, E_)
-        gqm = to4(qv.grad.cpu(), Lq, 3 * E_).double()
+        gqm = to4(qv.grad.cpu(), Lq, qw).double()
         want_q = back(q64.grad, Lq)
         assert (gqm[..., :E_] - want_q).abs().max() < 3e-2 * want_q.abs().max(), "dQ"
         if cross:
