@@ -75,16 +75,6 @@ struct RowCtx {
   int half, row, nch;
 };
 
-// 8 bf16 (one 16-byte piece) of a saved-probability row; zero outside the row / the padded pitch
-__device__ __forceinline__ uint4 ld_p8(const __nv_bfloat16* prow, bool row_ok, int col0, int64_t x_ld) {
-  return (row_ok && col0 < x_ld) ? __ldg(reinterpret_cast<const uint4*>(prow + col0)) : make_uint4(0, 0, 0, 0);
-}
-
-__device__ __forceinline__ float p_elem(const uint4 (&pv)[4], int i, int h) {
-  const uint32_t w = h < 2 ? pv[i].x : (h < 4 ? pv[i].y : (h < 6 ? pv[i].z : pv[i].w));
-  return (h & 1) ? bf16hi(w) : bf16lo(w);
-}
-
 // forward, pass 1 on one 32-key chunk: four independent partial maxima
 __device__ __forceinline__ void row_fwd_max(const uint32_t (&r)[32], int nvalid, float (&mx)[4]) {
 #pragma unroll

@@ -932,31 +932,6 @@ def causal_conv(ctx: Ctx, x: Var, prefix: str, N: int, Ls: int, cin: int, cout: 
     return out
 
 
-def channel_dropout(ctx: Ctx, x: Var, p: float, N: int, Ls: int, Cc: int) -> Var:
-    """nn.Dropout2d on (N, C, L) = drop whole channels per sample; training only."""
-    if p <= 0.0 or not ctx.training:
-        return x
-    mask = ctx.empty((N * Cc,), torch.uint8)
-    L.check(ctx.lib.jmt_dropout_mask(_ptr(mask), N * Cc, p, ctx.seed, ctx.rng_offset, _stream()), "jmt_dropout_mask")
-    ctx.rng_offset += (N * Cc + 3) // 4
-    scale = 1.0 / (1.0 - p)
-    y = ctx.empty(x.data.shape)
-    L.check(ctx.lib.jmt_apply_mask(_ptr(x.data), _ptr(mask), _ptr(y), N, Ls, Cc, 1, scale, ctx.acode, _stream()), "jmt_apply_mask")
-    out = Var(y)
-    if ctx.record:
-        def bwd():
-            dy = out.grad
-            if dy is None:
-                return
-            dx = GradBuf(ctx.empty(x.data.shape))
-            L.check(ctx.lib.jmt_apply_mask(_ptr(dy), _ptr(mask), _ptr(dx.t), N, Ls, Cc, 1, scale, ctx.acode, _stream()), "jmt_apply_mask")
-            ctx.add_grad(x, dx)
-            dx.refs -= 1
-            ctx.release(out)
-        ctx.tape.append(bwd)
-    return out
-
-
 def add_act(ctx: Ctx, a: Var, b: Var, act: int, slope: float) -> Var:
     """act(a + b)  (TemporalBlock residual, temporal_convolutional_model.py:54-57)."""
     assert a.data.is_contiguous() and b.data.is_contiguous()
