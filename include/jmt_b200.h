@@ -138,8 +138,9 @@ typedef struct {
   const void* a1; const void* b1; const void* b2;   /* bf16 */
   const void* p_in;                                  /* mode 1: saved probabilities; else NULL */
   const void* o_in;                                  /* mode 1: saved forward output O, same geometry as a1 (= dO); else NULL */
+  const float* delta_in;                             /* mode 1: precomputed delta (NB, heads, Lq) fp32 (jmt_rowdot_bf16), or NULL: from o_in */
   void* x;                                           /* out: P (mode 0) / dS (mode 1), bf16 */
-  void* d;                                           /* out: O (mode 0) / dQ (mode 1), bf16 */
+  void* d;                                           /* out: O (mode 0) / dQ (mode 1), bf16; mode 1 with d == NULL: stop after X = dS */
   int32_t mode;
   int32_t Lq, S, dh, heads, NB;
   int64_t a1_ld, a1_hs, a1_bs;
@@ -152,6 +153,10 @@ typedef struct {
 } jmt_attn_desc;
 int jmt_attn_chain_supported(const jmt_attn_desc* g);   /* 1 / 0, no launch */
 int jmt_attn_chain_bf16(const jmt_attn_desc* g, void* stream);
+/* out[(b*heads + h)*rows + r] = sum_d a[b,h,r,d] * b[b,h,r,d] (element (r, d) of (h, b) at b*bs + h*hs + r*ld + d): the
+ * delta_i = dO_i . O_i = sum_j P_ij dP_ij term of the softmax backward, one pass over dO and O. */
+int jmt_rowdot_bf16(const void* a, const void* b, int64_t ld, int64_t hs, int64_t bs, int NB, int heads, int rows, int dh,
+                    float* out, void* stream);
 /* Debug aid: per-CTA cycle counters of the TMA / MMA / row-warp roles (148*16 uint64 device buffer; NULL disables). */
 int jmt_attn_set_profile_buffer(void* dev_buf);
 

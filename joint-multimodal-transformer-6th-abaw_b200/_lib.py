@@ -40,7 +40,7 @@ class GemmDesc(C.Structure):
 class AttnDesc(C.Structure):
     """Mirror of jmt_attn_desc (include/jmt_b200.h)."""
     _fields_ = [
-        ("a1", C.c_void_p), ("b1", C.c_void_p), ("b2", C.c_void_p), ("p_in", C.c_void_p), ("o_in", C.c_void_p), ("x", C.c_void_p), ("d", C.c_void_p),
+        ("a1", C.c_void_p), ("b1", C.c_void_p), ("b2", C.c_void_p), ("p_in", C.c_void_p), ("o_in", C.c_void_p), ("delta_in", C.c_void_p), ("x", C.c_void_p), ("d", C.c_void_p),
         ("mode", C.c_int32), ("Lq", C.c_int32), ("S", C.c_int32), ("dh", C.c_int32), ("heads", C.c_int32), ("NB", C.c_int32),
         ("a1_ld", C.c_int64), ("a1_hs", C.c_int64), ("a1_bs", C.c_int64),
         ("b1_ld", C.c_int64), ("b1_hs", C.c_int64), ("b1_bs", C.c_int64),
@@ -63,6 +63,7 @@ SIGNATURES = {
     "jmt_attn_chain_supported": [C.POINTER(AttnDesc)],
     "jmt_attn_chain_bf16": [C.POINTER(AttnDesc), _P],
     "jmt_attn_set_profile_buffer": [_P],
+    "jmt_rowdot_bf16": [_P, _P, _L, _L, _L, _I, _I, _I, _I, _P, _P],
     "jmt_l2norm_fwd": [_P, _I, _L, _P, _I, _L, _I, _F, _P, _P],
     "jmt_l2norm_bwd": [_P, _P, _I, _P, _F, _P, _L, _I, _P],
     "jmt_add_layernorm_fwd": [_P, _P, _P, _P, _F, _P, _P, _P, _L, _I, _I, _P],

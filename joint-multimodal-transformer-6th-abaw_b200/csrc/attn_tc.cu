@@ -42,6 +42,8 @@ struct AtParams {
   const __nv_bfloat16* do_in;  // mode 1: dO and the saved forward output O (same geometry): delta = rowsum(dO o O)
   const __nv_bfloat16* o_in;
   int64_t do_ld, do_hs, do_bs;
+  const float* delta_in;       // mode 1: precomputed delta (NB, heads, Lq) fp32, or NULL (computed in-kernel from dO, O)
+  int skip2;                   // mode 1: stop after X = dS (no GEMM2 / dQ): dQ, dK, dV are plain GEMMs on the saved dS
   int64_t x_ld;
   int store_mode;
   FastDiv fd_qt, fd_heads;
@@ -287,7 +289,7 @@ attn_chain_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
             if (++slot == p.slots) { slot = 0; phase ^= 1; }
           }
         }
-        for (int nh = 0; nh < p.nh2; ++nh)                    // GEMM2 operand: B2 [64 keys x n2] (MN-major chunks)
+        for (int nh = 0; nh < (p.skip2 ? 0 : p.nh2); ++nh)    // GEMM2 operand: B2 [64 keys x n2] (MN-major chunks)
           for (int kb = 0; kb < p.nkx; ++kb) {
             const long long tw = p.prof ? clock64() : 0;
             mbar_wait(empty_bar + 8 * slot, phase ^ 1);
@@ -310,7 +312,7 @@ attn_chain_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
 #define AT_TIMED_WAIT(acc, bar, ph) { const long long tw_ = p.prof ? clock64() : 0; mbar_wait(bar, ph); if (p.prof) acc += clock64() - tw_; }
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tile_iter) {
         const uint32_t par = tile_iter & 1;
-        AT_TIMED_WAIT(mwe, t_empty, par ^ 1);                 // previous tile's T2 has been drained
+        if (!p.skip2) AT_TIMED_WAIT(mwe, t_empty, par ^ 1);   // previous tile's T2 has been drained
         tc_fence_after();
         for (int kb = 0; kb < p.nk1; ++kb) {                  // GEMM1: T1 = A1 B1^T, one stage per N group of B1
           AT_TIMED_WAIT(mw1, full_bar + 8 * slot, phase);
@@ -340,6 +342,7 @@ attn_chain_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
         tc_commit<1>(t1_full);
         AT_TIMED_WAIT(mwx, x_ready, par);                     // X (P or dS) is in shared memory, T1 is dead
         tc_fence_after();
+        if (p.skip2) continue;                                // T1 has been consumed (x_ready): next tile's GEMM1 may overwrite it
         for (int nh = 0; nh < p.nh2; ++nh)                    // GEMM2: T2[:, nh] = X B2[:, nh]
           for (int kb = 0; kb < p.nkx; ++kb) {
             AT_TIMED_WAIT(mw2, full_bar + 8 * slot, phase);
@@ -391,7 +394,14 @@ attn_chain_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
         }
         // delta of this tile while GEMM1 runs.  (Measured: ~9 k cycles per tile of latency-bound global loads that GEMM1
         // only partly hides; computing it for the next tile under GEMM2 instead put 30 k cycles on the critical path.)
-        at_delta(p, c, ew, lane, red);
+        if (p.delta_in != nullptr) {              // precomputed (jmt_rowdot): one coalesced load per row
+          if (ew == 0) {
+            const float* dl = p.delta_in + ((int64_t)c.b * p.heads + c.head) * p.Lq;
+            for (int r = lane; r < kBlockM; r += 32) red[r] = c.q0 + r < p.Lq ? __ldg(dl + c.q0 + r) : 0.f;
+          }
+        } else {
+          at_delta(p, c, ew, lane, red);
+        }
         __syncwarp();
         asm volatile("bar.sync 1, %0;" ::"n"(32 * kAtRowWarps) : "memory");     // delta of every row is visible
       }
@@ -415,6 +425,7 @@ attn_chain_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
         for (int kc = 0; kc < p.nkx; ++kc) tma_store_4d(&map_x, sX + kc * 16384, kc * 64, c.q0, c.head, c.b);
         bulk_commit();
       }
+      if (p.skip2) continue;                         // dS-only mode: no GEMM2, nothing to drain
       // ---- T2 epilogue: O (store) / dQ (reduce-add), bf16
       const long long rcx = p.prof ? clock64() : 0;
       mbar_wait(t2_full, par);                       // GEMM2 has consumed X: its first 32 KiB become the epilogue staging
@@ -513,6 +524,7 @@ static int at_plan(const jmt_attn_desc* g, AtParams* p, int* smem_bytes) {
   p->p_in = (const __nv_bfloat16*)g->p_in;
   p->do_in = (const __nv_bfloat16*)g->a1; p->o_in = (const __nv_bfloat16*)g->o_in;
   p->do_ld = g->a1_ld; p->do_hs = g->a1_hs; p->do_bs = g->a1_bs;
+  p->delta_in = g->delta_in; p->skip2 = (g->mode == 1 && g->d == nullptr) ? 1 : 0;
   p->x_ld = g->x_ld;
   p->store_mode = g->store_mode;
   p->fd_qt.init(p->q_tiles);
@@ -523,6 +535,43 @@ static int at_plan(const jmt_attn_desc* g, AtParams* p, int* smem_bytes) {
 }  // namespace jmt
 
 using namespace jmt;
+
+namespace jmt {
+// out[(b*heads + h)*rows + r] = sum_d A[b, h, r, d] * B[b, h, r, d]  (delta_i = dO_i . O_i of the attention backward):
+// one warp per (b, h, r), coalesced 16-byte loads
+__global__ void __launch_bounds__(256)
+rowdot_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b, int64_t ld, int64_t hs, int64_t bs,
+              int rows, int heads, int dh, int64_t total, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  for (int64_t w = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); w < total; w += (int64_t)gridDim.x * 8) {
+    const int64_t bh = w / rows; const int r = (int)(w - bh * rows);
+    const int64_t bi = bh / heads; const int h = (int)(bh - bi * heads);
+    const int64_t off = bi * bs + (int64_t)h * hs + (int64_t)r * ld;
+    float d = 0.f;
+    for (int pc = lane; pc < (dh >> 3); pc += 32) {
+      const uint4 x = __ldg(reinterpret_cast<const uint4*>(a + off + pc * 8));
+      const uint4 y = __ldg(reinterpret_cast<const uint4*>(b + off + pc * 8));
+      d = fmaf(bf16lo(x.x), bf16lo(y.x), d); d = fmaf(bf16hi(x.x), bf16hi(y.x), d);
+      d = fmaf(bf16lo(x.y), bf16lo(y.y), d); d = fmaf(bf16hi(x.y), bf16hi(y.y), d);
+      d = fmaf(bf16lo(x.z), bf16lo(y.z), d); d = fmaf(bf16hi(x.z), bf16hi(y.z), d);
+      d = fmaf(bf16lo(x.w), bf16lo(y.w), d); d = fmaf(bf16hi(x.w), bf16hi(y.w), d);
+    }
+    d = warp_sum(d);
+    if (lane == 0) out[w] = d;
+  }
+}
+}  // namespace jmt
+
+extern "C" int jmt_rowdot_bf16(const void* a, const void* b, int64_t ld, int64_t hs, int64_t bs, int NB, int heads, int rows, int dh,
+                               float* out, void* stream) {
+  JMT_REQUIRE(a && b && out && NB >= 1 && heads >= 1 && rows >= 1 && dh >= 8 && dh % 8 == 0, "jmt_rowdot_bf16: bad arguments");
+  JMT_REQUIRE(ld % 8 == 0 && hs % 8 == 0 && bs % 8 == 0 && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15) == 0,
+              "jmt_rowdot_bf16: 16-byte aligned geometry required");
+  const int64_t total = (int64_t)NB * heads * rows;
+  rowdot_kernel<<<grid_for(total, 8, kNumSMs * 16), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)b, ld, hs, bs,
+                                                                                  rows, heads, dh, total, out);
+  return check_launch("rowdot_kernel");
+}
 
 static std::atomic<unsigned long long*> g_attn_prof{nullptr};
 extern "C" int jmt_attn_set_profile_buffer(void* dev_buf) {
@@ -539,8 +588,11 @@ extern "C" int jmt_attn_chain_supported(const jmt_attn_desc* g) {
 }
 
 extern "C" int jmt_attn_chain_bf16(const jmt_attn_desc* g, void* stream) {
-  JMT_REQUIRE(g && g->a1 && g->b1 && g->b2 && g->x && g->d, "jmt_attn_chain_bf16: null pointer");
-  JMT_REQUIRE(g->mode == 0 || (g->mode == 1 && g->p_in && g->o_in), "jmt_attn_chain_bf16: mode 1 needs the saved probabilities and output");
+  JMT_REQUIRE(g && g->a1 && g->b1 && g->x, "jmt_attn_chain_bf16: null pointer");
+  JMT_REQUIRE(g->mode == 0 || g->mode == 1, "jmt_attn_chain_bf16: bad mode");
+  JMT_REQUIRE(g->mode == 1 || (g->b2 && g->d), "jmt_attn_chain_bf16: mode 0 needs B2 and D");
+  JMT_REQUIRE(g->mode == 0 || (g->p_in && (g->delta_in || g->o_in)), "jmt_attn_chain_bf16: mode 1 needs the saved probabilities and delta (or O)");
+  JMT_REQUIRE(g->mode == 0 || g->d == nullptr || g->b2, "jmt_attn_chain_bf16: mode 1 with D needs B2");
   JMT_REQUIRE(g->store_mode == JMT_STORE || g->store_mode == JMT_ACCUMULATE, "jmt_attn_chain_bf16: bad store_mode");
   AtParams p; int smem = 0;
   if (!at_plan(g, &p, &smem) || g->x_ld % 8 != 0 || g->x_ld < g->S) {
@@ -554,15 +606,21 @@ extern "C" int jmt_attn_chain_bf16(const jmt_attn_desc* g, void* stream) {
   if (rc != JMT_OK) return rc;
   rc = make_map(&mb1, g->b1, g->dh, g->S, g->b1_ld, g->heads, g->b1_hs, g->NB, g->b1_bs, p.n1, "jmt_attn_chain_bf16(B1)");
   if (rc != JMT_OK) return rc;
-  rc = make_map_mn5(&mb2, g->b2, g->dh, g->S, g->b2_ld, g->heads, g->b2_hs, g->NB, g->b2_bs, kBlockK, p.n2 / 64, "jmt_attn_chain_bf16(B2)");
-  if (rc != JMT_OK) return rc;
+  mb2 = mb1;                    // (unused in the dS-only mode)
+  if (!p.skip2) {
+    rc = make_map_mn5(&mb2, g->b2, g->dh, g->S, g->b2_ld, g->heads, g->b2_hs, g->NB, g->b2_bs, kBlockK, p.n2 / 64, "jmt_attn_chain_bf16(B2)");
+    if (rc != JMT_OK) return rc;
+  }
   rc = make_map(&mx, g->x, g->S, g->Lq, g->x_ld, g->heads, (int64_t)g->Lq * g->x_ld, g->NB, (int64_t)g->heads * g->Lq * g->x_ld, kBlockM,
                 "jmt_attn_chain_bf16(X)");
   if (rc != JMT_OK) return rc;
-  JMT_REQUIRE((reinterpret_cast<uintptr_t>(g->d) & 15) == 0 && g->d_ld % 8 == 0 && g->d_hs % 8 == 0 && g->d_bs % 8 == 0,
-              "jmt_attn_chain_bf16: D geometry must be 16-byte aligned");
-  rc = make_map_d(&md, g->d, JMT_BF16, g->dh, g->Lq, g->d_ld, g->heads, g->d_hs, g->NB, g->d_bs, "jmt_attn_chain_bf16(D)");
-  if (rc != JMT_OK) return rc;
+  md = mx;
+  if (!p.skip2) {
+    JMT_REQUIRE((reinterpret_cast<uintptr_t>(g->d) & 15) == 0 && g->d_ld % 8 == 0 && g->d_hs % 8 == 0 && g->d_bs % 8 == 0,
+                "jmt_attn_chain_bf16: D geometry must be 16-byte aligned");
+    rc = make_map_d(&md, g->d, JMT_BF16, g->dh, g->Lq, g->d_ld, g->heads, g->d_hs, g->NB, g->d_bs, "jmt_attn_chain_bf16(D)");
+    if (rc != JMT_OK) return rc;
+  }
   static std::atomic<int> attr_set[64];
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); set_error("jmt_attn_chain_bf16: no CUDA device"); return JMT_ERR_CUDA; }

@@ -207,6 +207,13 @@ static inline EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+// L2 promotion of operand loads (experiment knob JMT_TMA_L2PROMO = 0 none, 1 64B, 2 128B, 3 256B; default 256B)
+static inline CUtensorMapL2promotion tma_l2_promotion() {
+  static const int v = []() { const char* e = getenv("JMT_TMA_L2PROMO"); return e ? atoi(e) : 3; }();
+  return v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : v == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+       : v == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+}
+
 // 4-D bf16 tensor map over (inner, rows, b0, b1) with a {64, box_rows, 1, 1} box, 128B swizzle, zero OOB fill
 static inline int make_map(CUtensorMap* map, const void* ptr, int64_t inner, int64_t rows, int64_t ld, int64_t nb0, int64_t bs0,
                     int64_t nb1, int64_t bs1, int box_rows, const char* who) {
@@ -223,7 +230,7 @@ static inline int make_map(CUtensorMap* map, const void* ptr, int64_t inner, int
   const cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)box_rows, 1, 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, tma_l2_promotion(),
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("%s: cuTensorMapEncodeTiled failed (%d) inner=%lld rows=%lld ld=%lld nb0=%lld bs0=%lld nb1=%lld bs1=%lld box_rows=%d",
@@ -257,7 +264,7 @@ static inline int make_map_mn5(CUtensorMap* map, const void* ptr, int64_t inner,
   const cuuint32_t box[5] = {(cuuint32_t)kBlockK, (cuuint32_t)box_rows, (cuuint32_t)box_chunks, 1, 1};
   const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, tma_l2_promotion(),
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("%s: cuTensorMapEncodeTiled(5-D) failed (%d) inner=%lld rows=%lld ld=%lld box_rows=%d box_chunks=%d", who, (int)r,

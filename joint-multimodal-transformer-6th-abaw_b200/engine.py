@@ -527,24 +527,26 @@ def _proj_grad_slice(ctx: Ctx, v: Var, c0: int, c1: int) -> Tuple[torch.Tensor, 
 
 
 FUSED_ATTENTION = True      # bf16 mode: use jmt_attn_chain_bf16 when the geometry is supported (else GEMM + softmax kernels)
-FUSED_ATTENTION_BWD = False  # the fused backward (dP -> dS -> dQ) is correct but not yet faster than GEMM + softmax_bwd + GEMM
+FUSED_ATTENTION_BWD = "ds"   # "ds": dP GEMM + softmax backward fused (dS on chip, dQ/dK/dV plain GEMMs); "full": dP -> dS -> dQ in one
+                             # kernel (correct, not faster than the composition yet); False: GEMM + softmax_bwd kernel
 
 
 def _attn_chain(ctx: Ctx, mode: int, a1, a1_geo, b1, b1_geo, b2, b2_geo, p_in, x, d, d_geo, Lq, S, dh, heads, NB, x_ld,
-                scale, store, probe_only=False, o_in=None):
+                scale, store, probe_only=False, o_in=None, delta_in=None):
     """One launch of the fused attention core (include/jmt_b200.h: jmt_attn_desc).  *_geo = (ld, head stride,
     batch stride) in elements."""
     g = L.AttnDesc()
-    g.a1, g.b1, g.b2 = a1.data_ptr(), b1.data_ptr(), b2.data_ptr()
+    g.a1, g.b1, g.b2 = a1.data_ptr(), b1.data_ptr(), (b2.data_ptr() if b2 is not None else None)
     g.p_in = p_in.data_ptr() if p_in is not None else None
     g.o_in = o_in.data_ptr() if o_in is not None else None
-    g.x, g.d = x.data_ptr(), d.data_ptr()
+    g.delta_in = delta_in.data_ptr() if delta_in is not None else None
+    g.x, g.d = x.data_ptr(), (d.data_ptr() if d is not None else None)
     g.mode = mode
     g.Lq, g.S, g.dh, g.heads, g.NB = Lq, S, dh, heads, NB
     g.a1_ld, g.a1_hs, g.a1_bs = a1_geo
     g.b1_ld, g.b1_hs, g.b1_bs = b1_geo
-    g.b2_ld, g.b2_hs, g.b2_bs = b2_geo
-    g.d_ld, g.d_hs, g.d_bs = d_geo
+    g.b2_ld, g.b2_hs, g.b2_bs = b2_geo if b2_geo is not None else (0, 0, 0)
+    g.d_ld, g.d_hs, g.d_bs = d_geo if d_geo is not None else (0, 0, 0)
     g.x_ld = x_ld
     g.scale = scale
     g.store_mode = store
@@ -557,7 +559,7 @@ def _attn_chain(ctx: Ctx, mode: int, a1, a1_geo, b1, b1_geo, b2, b2_geo, p_in, x
     L.check(ctx.lib.jmt_attn_chain_bf16(C.byref(g), _stream()), "jmt_attn_chain_bf16")
     if prof is not None:
         e1.record()
-        prof.append(("attn_chain_kernel", 4.0 * NB * heads * Lq * S * dh, e0, e1, (Lq, S, dh, NB * heads, mode)))
+        prof.append(("attn_chain_kernel", (2.0 if d is None else 4.0) * NB * heads * Lq * S * dh, e0, e1, (Lq, S, dh, NB * heads, mode)))
     return True
 
 
@@ -613,7 +615,20 @@ def attention_core(ctx: Ctx, q: Var, qcol: int, k: Var, kcol: int, v: Var, vcol:
             q_gld = gq_s.stride(0)
             dq_geo = (gq.seq_stride * q_gld, dh, gq.batch_stride * q_gld)
             ds = ctx.empty((NB, heads, Lq, s_ld))
-            if fused and FUSED_ATTENTION_BWD:
+            if fused and FUSED_ATTENTION_BWD == "ds":
+                # delta = rowsum(dO o O); dP = dO V^T -> dS = scale * P o (dP - delta) in one kernel (fp32 dP never leaves
+                # the SM); dQ = dS K, dK = dS^T Q, dV = P^T dO stay plain GEMMs (the scale is already in dS)
+                delta = ctx.empty((NB, heads, Lq), torch.float32)
+                L.check(ctx.lib.jmt_rowdot_bf16(_ptr(do), _ptr(o), o_geo[0], o_geo[1], o_geo[2], NB, heads, Lq, dh, _ptr(delta),
+                                                _stream()), "jmt_rowdot_bf16")
+                _attn_chain(ctx, 1, do, o_geo, vd, v_geo, None, None, probs, ds, None, None, Lq, S, dh, heads, NB, s_ld, scale,
+                            L.STORE, delta_in=delta)
+                gemm(ctx, ds, kd, gq_s, M=Lq, N=dh, K=S, a_rows=Lq, b_major=L.MAJOR_MN, b_rows=S,
+                     a_ld=s_ld, b_ld=gk.seq_stride * kld, d_ld=gq.seq_stride * q_gld,
+                     nb0=heads, nb1=NB, a_bs=sb, b_bs=(dh, gk.batch_stride * kld), d_bs=(dh, gq.batch_stride * q_gld),
+                     store=q_mode)
+                dk_alpha = 1.0
+            elif fused and FUSED_ATTENTION_BWD:
                 # dP = dO V^T -> dS = scale * P o (dP - rowsum(P o dP)) -> dQ += dS K, one kernel; dS is saved for dK
                 _attn_chain(ctx, 1, do, o_geo, vd, v_geo, kd, k_geo, probs, ds, gq_s, dq_geo, Lq, S, dh,
                             heads, NB, s_ld, scale, q_mode, o_in=o)
