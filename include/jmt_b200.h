@@ -140,7 +140,7 @@ typedef struct {
   const void* o_in;                                  /* mode 1: saved forward output O, same geometry as a1 (= dO); else NULL */
   const float* delta_in;                             /* mode 1: precomputed delta (NB, heads, Lq) fp32 (jmt_rowdot_bf16), or NULL: from o_in */
   void* x;                                           /* out: P (mode 0) / dS (mode 1), bf16 */
-  void* d;                                           /* out: O (mode 0) / dQ (mode 1), bf16; mode 1 with d == NULL: stop after X = dS */
+  void* d;                                           /* out: O (mode 0) / dQ (mode 1), bf16; NULL: stop after X (P / dS) -- GEMM2 is then a plain jmt_gemm_bf16 */
   int32_t mode;
   int32_t Lq, S, dh, heads, NB;
   int64_t a1_ld, a1_hs, a1_bs;

@@ -524,7 +524,7 @@ static int at_plan(const jmt_attn_desc* g, AtParams* p, int* smem_bytes) {
   p->p_in = (const __nv_bfloat16*)g->p_in;
   p->do_in = (const __nv_bfloat16*)g->a1; p->o_in = (const __nv_bfloat16*)g->o_in;
   p->do_ld = g->a1_ld; p->do_hs = g->a1_hs; p->do_bs = g->a1_bs;
-  p->delta_in = g->delta_in; p->skip2 = (g->mode == 1 && g->d == nullptr) ? 1 : 0;
+  p->delta_in = g->delta_in; p->skip2 = g->d == nullptr ? 1 : 0;
   p->x_ld = g->x_ld;
   p->store_mode = g->store_mode;
   p->fd_qt.init(p->q_tiles);
@@ -590,9 +590,8 @@ extern "C" int jmt_attn_chain_supported(const jmt_attn_desc* g) {
 extern "C" int jmt_attn_chain_bf16(const jmt_attn_desc* g, void* stream) {
   JMT_REQUIRE(g && g->a1 && g->b1 && g->x, "jmt_attn_chain_bf16: null pointer");
   JMT_REQUIRE(g->mode == 0 || g->mode == 1, "jmt_attn_chain_bf16: bad mode");
-  JMT_REQUIRE(g->mode == 1 || (g->b2 && g->d), "jmt_attn_chain_bf16: mode 0 needs B2 and D");
+  JMT_REQUIRE(g->d == nullptr || g->b2, "jmt_attn_chain_bf16: D needs B2");
   JMT_REQUIRE(g->mode == 0 || (g->p_in && (g->delta_in || g->o_in)), "jmt_attn_chain_bf16: mode 1 needs the saved probabilities and delta (or O)");
-  JMT_REQUIRE(g->mode == 0 || g->d == nullptr || g->b2, "jmt_attn_chain_bf16: mode 1 with D needs B2");
   JMT_REQUIRE(g->store_mode == JMT_STORE || g->store_mode == JMT_ACCUMULATE, "jmt_attn_chain_bf16: bad store_mode");
   AtParams p; int smem = 0;
   if (!at_plan(g, &p, &smem) || g->x_ld % 8 != 0 || g->x_ld < g->S) {

@@ -248,7 +248,7 @@ ATTN_CASES = [
 ]
 
 
-@pytest.mark.parametrize("fused", ["full", "ds", False])
+@pytest.mark.parametrize("fused", [("full", "full"), ("full", "ds"), ("p", "ds"), (False, False)], ids=["full-full", "full-ds", "p-ds", "composed"])
 @pytest.mark.parametrize("case", ATTN_CASES, ids=[c[0] for c in ATTN_CASES])
 def test_attention_core_bf16(case, fused):
     """softmax(QK^T/sqrt(dh))V forward + dQ/dK/dV through engine.attention_core in bf16 mode: the fused tcgen05
@@ -261,7 +261,7 @@ def test_attention_core_bf16(case, fused):
     ctx = _ctx("bf16")
     ctx.record = True
     old = (E.FUSED_ATTENTION, E.FUSED_ATTENTION_BWD)
-    E.FUSED_ATTENTION, E.FUSED_ATTENTION_BWD = bool(fused), fused
+    E.FUSED_ATTENTION, E.FUSED_ATTENTION_BWD = (True if fused[0] == "full" else fused[0]), fused[1]
     try:
         # projection matrices as the engine holds them: rows = batch*seq (or seq*batch for the batch-major geometry)
         qw = E_ if cross else 3 * E_          # a cross-attention Q projection is (rows, E); self-attention packs Q | K | V
