@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define JMT_ABI_VERSION 3
+#define JMT_ABI_VERSION 4
 
 typedef enum {
   JMT_OK = 0,
@@ -170,7 +170,7 @@ int jmt_l2norm_fwd(const void* x, int in_dtype, int64_t in_ld, void* out, int ou
                    int D, float eps, float* inv_norm, void* stream);
 /* dx = r*(dy - y*(y.dy)) (r = inv_norm; rows with ||x|| < eps: dx = r*dy).  y = saved output. */
 int jmt_l2norm_bwd(const void* dy, const void* y, int dtype, const float* inv_norm, float eps,
-                   float* dx, int64_t rows, int D, void* stream);
+                   void* dx, int dx_dtype, int64_t rows, int D, void* stream);
 
 /* y = LayerNorm(x + res) * gamma + beta  (post-LN residual: mm_multi_transformers.py:62-69).
  * res nullable.  Saves mean/rstd (rows) fp32. */

@@ -65,7 +65,7 @@ SIGNATURES = {
     "jmt_attn_set_profile_buffer": [_P],
     "jmt_rowdot_bf16": [_P, _P, _L, _L, _L, _I, _I, _I, _I, _P, _P],
     "jmt_l2norm_fwd": [_P, _I, _L, _P, _I, _L, _I, _F, _P, _P],
-    "jmt_l2norm_bwd": [_P, _P, _I, _P, _F, _P, _L, _I, _P],
+    "jmt_l2norm_bwd": [_P, _P, _I, _P, _F, _P, _I, _L, _I, _P],
     "jmt_add_layernorm_fwd": [_P, _P, _P, _P, _F, _P, _P, _P, _L, _I, _I, _P],
     "jmt_add_layernorm_bwd": [_P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _L, _I, _I, _P],
     "jmt_softmax_fwd": [_P, _L, _P, _I, _L, _L, _I, _P],
@@ -116,7 +116,7 @@ def lib():
             fn = getattr(h, name)           # AttributeError if a declared symbol is not exported
             fn.argtypes = argtypes
             fn.restype = _RESTYPES.get(name, C.c_int)
-        if h.jmt_abi_version() != 3:
+        if h.jmt_abi_version() != 4:
             raise RuntimeError("libjmt_b200.so ABI version mismatch")
         _lib = h
     return _lib

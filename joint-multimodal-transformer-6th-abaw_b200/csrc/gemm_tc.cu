@@ -84,23 +84,19 @@ __device__ __forceinline__ void apply_flags4(const uint8_t* fl, float mscale, fl
 }
 
 template <int ACT, bool MASK>
-__device__ __forceinline__ void epi_math_store_bf16(const uint32_t (&r)[32], const float* bias, const uint8_t* flags, float mscale,
-                                                    uint32_t keep, float alpha, float slope, uint32_t row_smem, uint32_t sw, int piece0) {
+__device__ __forceinline__ void epi_math_bf16(const uint32_t (&r)[32], const float* bias, const uint8_t* flags, float mscale,
+                                              uint32_t keep, float alpha, float slope, uint32_t* pk /*16 packed words*/) {
 #pragma unroll
-  for (int j = 0; j < 32; j += 8) {
-    float x[8];
-#pragma unroll
-    for (int h = 0; h < 8; h += 4) {
-      const float4 bv = *reinterpret_cast<const float4*>(bias + j + h);
-      x[h] = act_t<ACT>(fmaf(alpha, __uint_as_float(r[j + h]), bv.x), slope);
-      x[h + 1] = act_t<ACT>(fmaf(alpha, __uint_as_float(r[j + h + 1]), bv.y), slope);
-      x[h + 2] = act_t<ACT>(fmaf(alpha, __uint_as_float(r[j + h + 2]), bv.z), slope);
-      x[h + 3] = act_t<ACT>(fmaf(alpha, __uint_as_float(r[j + h + 3]), bv.w), slope);
-      if constexpr (MASK) apply_flags4(flags + j + h, mscale, x[h], x[h + 1], x[h + 2], x[h + 3]);
-    }
+  for (int j = 0; j < 32; j += 4) {
+    const float4 bv = *reinterpret_cast<const float4*>(bias + j);
+    float x0 = act_t<ACT>(fmaf(alpha, __uint_as_float(r[j]), bv.x), slope);
+    float x1 = act_t<ACT>(fmaf(alpha, __uint_as_float(r[j + 1]), bv.y), slope);
+    float x2 = act_t<ACT>(fmaf(alpha, __uint_as_float(r[j + 2]), bv.z), slope);
+    float x3 = act_t<ACT>(fmaf(alpha, __uint_as_float(r[j + 3]), bv.w), slope);
+    if constexpr (MASK) apply_flags4(flags + j, mscale, x0, x1, x2, x3);
     // keep = 0 for rows that must read back as zeros (padding rows of the flat TCN layout), else all ones
-    st_shared_v4(row_smem + (((uint32_t)(piece0 + j / 8) ^ sw) << 4), pack_bf16(x[0], x[1]) & keep, pack_bf16(x[2], x[3]) & keep,
-                 pack_bf16(x[4], x[5]) & keep, pack_bf16(x[6], x[7]) & keep);
+    pk[j / 2] = pack_bf16(x0, x1) & keep;
+    pk[j / 2 + 1] = pack_bf16(x2, x3) & keep;
   }
 }
 template <int ACT, bool MASK>
@@ -164,18 +160,25 @@ __device__ __forceinline__ void epi_tile(const TcParams& p, const CUtensorMap* t
       for (int c0 = e.half * 64; c0 < p.block_n; c0 += 128) {
         if (e.n0 + c0 >= p.N) break;
         const bool second = c0 + 32 < p.block_n;      // block_n is a multiple of 32
-        uint32_t r0[32], r1[32];
-        tc_ld32_issue(e.tbase + c0, r0);
-        if (second) tc_ld32_issue(e.tbase + c0 + 32, r1);
+        uint32_t pk[32];
+        {
+          uint32_t r0[32], r1[32];
+          tc_ld32_issue(e.tbase + c0, r0);
+          if (second) tc_ld32_issue(e.tbase + c0 + 32, r1);
+          tc_wait_ld();
+          // the math runs while the previous TMA store of this warp is still reading the staging tile
+          epi_math_bf16<ACT, MASK>(r0, e.bias + c0, e.flags + c0, p.colmask_scale, e.keep, p.alpha, p.slope, pk);
+          if (second) epi_math_bf16<ACT, MASK>(r1, e.bias + c0 + 32, e.flags + c0 + 32, p.colmask_scale, e.keep, p.alpha, p.slope, pk + 16);
+          else {
+#pragma unroll
+            for (int j = 16; j < 32; ++j) pk[j] = 0u;
+          }
+        }
         if (lane == 0) bulk_wait_read0();       // previous TMA store has finished reading the staging tile
         __syncwarp();
-        tc_wait_ld();
-        epi_math_store_bf16<ACT, MASK>(r0, e.bias + c0, e.flags + c0, p.colmask_scale, e.keep, p.alpha, p.slope, e.row_smem, e.sw, 0);
-        if (second) epi_math_store_bf16<ACT, MASK>(r1, e.bias + c0 + 32, e.flags + c0 + 32, p.colmask_scale, e.keep, p.alpha, p.slope, e.row_smem, e.sw, 4);
-        else {
 #pragma unroll
-          for (int ch = 4; ch < 8; ++ch) st_shared_v4(e.row_smem + (((uint32_t)ch ^ e.sw) << 4), 0u, 0u, 0u, 0u);
-        }
+        for (int ch = 0; ch < 8; ++ch)
+          st_shared_v4(e.row_smem + (((uint32_t)ch ^ e.sw) << 4), pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
         fence_async_smem();
         __syncwarp();
         if (lane == 0 && warp_rows_valid) {

@@ -39,10 +39,10 @@ l2norm_fwd_kernel(const TI* __restrict__ x, int64_t in_ld, TO* __restrict__ out,
   }
 }
 
-template <typename T>
+template <typename T, typename TO>
 __global__ void __launch_bounds__(kRowThreads)
 l2norm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ y, const float* __restrict__ inv_norm, float eps,
-                  float* __restrict__ dx, int64_t rows, int D) {
+                  TO* __restrict__ dx, int64_t rows, int D) {
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
@@ -59,10 +59,10 @@ l2norm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ y, const float
     dot = warp_sum(dot);
     // ||x|| clamped by eps: y = x/eps is linear in x, no projection term
     if (inv >= 1.f / eps) dot = 0.f;
-    float* dxr = dx + r * (int64_t)D;
+    TO* dxr = dx + r * (int64_t)D;
     for (int c = lane * 8; c < D; c += 256) {
       Vec8<T> a, b; a.load(dyr + c); b.load(yr + c);
-      Vec8<float> o;
+      Vec8<TO> o;
 #pragma unroll
       for (int i = 0; i < 8; ++i) o.v[i] = inv * (a.v[i] - b.v[i] * dot);
       o.store(dxr + c);
@@ -254,13 +254,13 @@ extern "C" int jmt_l2norm_fwd(const void* x, int in_dtype, int64_t in_ld, void* 
   return check_launch("l2norm_fwd_kernel");
 }
 
-extern "C" int jmt_l2norm_bwd(const void* dy, const void* y, int dtype, const float* inv_norm, float eps, float* dx,
+extern "C" int jmt_l2norm_bwd(const void* dy, const void* y, int dtype, const float* inv_norm, float eps, void* dx, int dx_dtype,
                               int64_t rows, int D, void* stream) {
   JMT_REQUIRE(dy && y && inv_norm && dx && D > 0 && D % 8 == 0, "jmt_l2norm_bwd: bad arguments");
   if (rows == 0) return JMT_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  JMT_DISPATCH_DTYPE(dtype, T,
-      (l2norm_bwd_kernel<T><<<row_grid(rows), kRowThreads, 0, st>>>((const T*)dy, (const T*)y, inv_norm, eps, dx, rows, D)));
+  JMT_DISPATCH_DTYPE(dtype, T, JMT_DISPATCH_DTYPE(dx_dtype, TO,
+      (l2norm_bwd_kernel<T, TO><<<row_grid(rows), kRowThreads, 0, st>>>((const T*)dy, (const T*)y, inv_norm, eps, (TO*)dx, rows, D))));
   return check_launch("l2norm_bwd_kernel");
 }
 

@@ -360,7 +360,7 @@ def l2norm(ctx: Ctx, x: torch.Tensor, needs_grad: bool):
             if v.grad is None:
                 cuda_memset0(dx)
             else:
-                L.check(ctx.lib.jmt_l2norm_bwd(_ptr(v.grad), _ptr(out), ctx.acode, _ptr(inv), 1e-12, _ptr(dx), rows, D,
+                L.check(ctx.lib.jmt_l2norm_bwd(_ptr(v.grad), _ptr(out), ctx.acode, _ptr(inv), 1e-12, _ptr(dx), L.F32, rows, D,
                                                _stream()), "jmt_l2norm_bwd")
             ctx.release(v)
             holder["dx"] = dx

@@ -674,14 +674,9 @@ def _l2norm_var(ctx, x):
         def bwd():
             if y.grad is None:
                 return
-            dx32 = ctx.empty((rows, D), torch.float32)
-            L.check(ctx.lib.jmt_l2norm_bwd(E._ptr(y.grad), E._ptr(out), ctx.acode, E._ptr(inv), 1e-12, E._ptr(dx32), rows, D,
+            gb = E.GradBuf(ctx.empty((rows, D)))         # straight into the activation dtype (no fp32 round trip)
+            L.check(ctx.lib.jmt_l2norm_bwd(E._ptr(y.grad), E._ptr(out), ctx.acode, E._ptr(inv), 1e-12, E._ptr(gb.t), ctx.acode, rows, D,
                                            E._stream()), "jmt_l2norm_bwd")
-            if ctx.adt == torch.float32:
-                gb = E.GradBuf(dx32)
-            else:
-                gb = E.GradBuf(ctx.empty((rows, D)))
-                E.copy2d(ctx, dx32, gb.t)
             ctx.add_grad(x, gb)
             gb.refs -= 1
             ctx.release(y)

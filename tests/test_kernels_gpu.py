@@ -365,7 +365,7 @@ def test_layernorm_l2norm_softmax(dt):
     refn.backward(dyn.double())
     dx = torch.empty(rows, 768, device=dev)
     dyn_d = dyn.to(dev)
-    L.check(lib.jmt_l2norm_bwd(E._ptr(dyn_d), E._ptr(out), code, E._ptr(inv), 1e-12, E._ptr(dx), rows, 768, st), "l2b")
+    L.check(lib.jmt_l2norm_bwd(E._ptr(dyn_d), E._ptr(out), code, E._ptr(inv), 1e-12, E._ptr(dx), L.F32, rows, 768, st), "l2b")
     m = torch.ones(rows, dtype=torch.bool)
     m[5] = False
     assert (dx.cpu().double()[m] - xr.grad[m]).abs().max() < tol * 4
