@@ -370,3 +370,26 @@ def test_full_size_properties():
     assert abs(jmt_b200.cccmetric.ccc(x.reshape(-1), x.reshape(-1)) - 1.0) < 1e-6
     xc = (x - x.mean()).reshape(-1)
     assert abs(jmt_b200.cccmetric.ccc(xc, -xc) + 1.0) < 1e-4
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("B,T,heads,joint,fmt", [(1, 1, 8, "TRANSFORMER", "FC"), (1, 2, 1, "TRANSFORMER", "SELF_ATTEN"),
+                                                 (3, 1, 2, "NONE", "FC"), (1, 5, 4, "FC", "FC")])
+def test_degenerate_shapes_against_oracle(B, T, heads, joint, fmt, precision):
+    """Smallest inputs the reference accepts (one window, one time step: attention over a single key; a batch-dimension
+    attention of length 3): forward and input gradients against the CPU oracle on the same seeded weights."""
+    params = O.synth_params(O.two_transformers_shapes(1, joint, fmt, 512), 77)
+    model = _load(jmt_b200.Two_transformers(0.0, 0.0, heads, 1, joint, fmt, 512, precision=precision), params).eval()
+    aud, vis = O.synth_features(B, T, [512, 512], 78)
+    po = {k: v.clone() for k, v in params.items()}
+    ao, vo_in = aud.clone().requires_grad_(True), vis.clone().requires_grad_(True)
+    vo, aout = O.two_transformers_forward(ao, vo_in, po, heads, 1, joint, fmt)
+    (vo.sum() + 2 * aout.sum()).backward()
+    ad, vd = aud.to(DEV).requires_grad_(True), vis.to(DEV).requires_grad_(True)
+    v, a = model(ad, vd)
+    assert tuple(v.shape) == tuple(vo.shape)
+    tol = 1e-3 if precision == "fp32" else PRED_TOL["bf16"]
+    assert _rel(v.detach().cpu(), vo.detach()) < tol and _rel(a.detach().cpu(), aout.detach()) < tol
+    (v.sum() + 2 * a.sum()).backward()
+    gt = 2e-3 if precision == "fp32" else GRAD_L2["bf16"]
+    assert _rl2(ad.grad.cpu(), ao.grad) < gt and _rl2(vd.grad.cpu(), vo_in.grad) < gt
