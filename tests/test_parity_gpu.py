@@ -393,3 +393,33 @@ def test_degenerate_shapes_against_oracle(B, T, heads, joint, fmt, precision):
     (v.sum() + 2 * a.sum()).backward()
     gt = 2e-3 if precision == "fp32" else GRAD_L2["bf16"]
     assert _rl2(ad.grad.cpu(), ao.grad) < gt and _rl2(vd.grad.cpu(), vo_in.grad) < gt
+
+
+def test_training_reduces_ccc_loss():
+    """End-to-end sanity beyond single-step parity: a few dozen Adam steps of the bf16 pipeline (TCN + FcLayer +
+    Two_transformers, CCC loss) on a learnable synthetic target lower the loss substantially and stay finite."""
+    torch.manual_seed(0)
+    B, T = 8, 40
+    model = jmt_b200.JMTPipeline(jmt_b200.Two_transformers(0.0, 0.0, 2, 1, "TRANSFORMER", "FC", 512, precision="bf16"),
+                                 jmt_b200.FcLayer(768, 512, precision="bf16"),
+                                 jmt_b200.TemporalConvNet(64, [512] * 2, kernel_size=3, attention=0, dropout=0.0,
+                                                          precision="bf16")).to(DEV).train()
+    gen = torch.Generator().manual_seed(1)
+    aud = torch.randn(B, T, 768, generator=gen).to(DEV)
+    vis = torch.randn(B, 64, T, generator=gen).to(DEV)
+    # targets the model can express: smooth functions of a few input channels, laid out like the (T, B) predictions (Q1)
+    tv = torch.tanh(aud[:, :, :4].sum(-1)).t().contiguous()
+    ta = torch.tanh(vis[:, :4, :].sum(1)).t().contiguous()
+    crit = jmt_b200.CCCLoss(digitize_num=1)
+    opt = torch.optim.Adam(model.live_parameters(), lr=3e-4)
+    n = B * T
+    losses = []
+    for _ in range(60):
+        v, a = model(aud, vis)
+        loss = crit(v.view(-1, n), tv.view(-1, n)) + crit(a.view(-1, n), ta.view(-1, n))
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        losses.append(float(loss.item()))
+    assert all(np.isfinite(losses)), losses
+    assert losses[-1] < 0.5 * losses[0], (losses[0], losses[-1])
