@@ -156,7 +156,9 @@ class Ctx:
         if t is None:
             key = (par.data_ptr(), par._version, tuple(par.shape))
             ent = self.wcache.get(name)
-            if ent is None or ent[0] != key:
+            # Under CUDA-graph capture the cast must be PART of the graph: a replay runs after optimizer steps that the
+            # version check at capture time cannot see (torch.cuda.make_graphed_callables warms up without an optimizer).
+            if ent is None or ent[0] != key or torch.cuda.is_current_stream_capturing():
                 out = torch.empty(par.shape, dtype=self.adt, device=par.device)
                 L.check(self.lib.jmt_cast(_ptr(par), L.F32, _ptr(out), self.acode, par.numel(), _stream()), "jmt_cast")
                 ent = (key, out)
