@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define JMT_ABI_VERSION 4
+#define JMT_ABI_VERSION 5
 
 typedef enum {
   JMT_OK = 0,
@@ -255,7 +255,11 @@ int jmt_add_act(const void* a, const void* b, void* out, int64_t n, int act, flo
 int jmt_apply_mask(const void* x, const uint8_t* mask, void* out, int64_t nb, int L, int C, int per_channel,
                    float scale, int dtype, void* stream);
 /* Philox-4x32-10 keep-mask generator: mask[i] = uniform(seed, offset+i) >= p */
-int jmt_dropout_mask(uint8_t* mask, int64_t n, float p, uint64_t seed, uint64_t offset, void* stream);
+int jmt_dropout_mask(uint8_t* mask, int64_t n, float p, uint64_t seed, uint64_t offset, const uint64_t* dev_state, void* stream);
+/* dev_state (nullable): device uint64[2] = (seed increment, Philox counter offset) added to seed / offset inside the kernel,
+ * so that a captured CUDA graph (which bakes the host arguments in) draws fresh masks on every replay;
+ * jmt_rng_advance bumps the counter offset by `inc` in stream order (once per forward, after its last mask). */
+int jmt_rng_advance(uint64_t* dev_state, uint64_t inc, void* stream);
 
 /* weight_norm (legacy, dim=0): w[co,:] = g[co] * v[co,:] / ||v[co,:]||  (Cout rows of `inner`
  * = Cin*k elements; temporal_convolutional_model.py:24-33).  Writes w re-laid out for the

@@ -87,7 +87,8 @@ SIGNATURES = {
     "jmt_time_max_fwd": [_P, _L, _L, _I, _I, _P, _P, _I, _P],
     "jmt_time_max_bwd": [_P, _P, _L, _L, _I, _P, _I, _P],
     "jmt_apply_mask": [_P, _P, _P, _L, _I, _I, _I, _F, _I, _P],
-    "jmt_dropout_mask": [_P, _L, _F, _U64, _U64, _P],
+    "jmt_dropout_mask": [_P, _L, _F, _U64, _U64, _P, _P],
+    "jmt_rng_advance": [_P, _U64, _P],
     "jmt_weight_norm_fwd": [_P, _P, _P, _P, _I, _P, _I, _I, _I, _P],
     "jmt_weight_norm_bwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
     "jmt_ccc_sums": [_P, _P, _L, _I, _L, _I, _F, _P, _P],
@@ -116,7 +117,7 @@ def lib():
             fn = getattr(h, name)           # AttributeError if a declared symbol is not exported
             fn.argtypes = argtypes
             fn.restype = _RESTYPES.get(name, C.c_int)
-        if h.jmt_abi_version() != 4:
+        if h.jmt_abi_version() != 5:
             raise RuntimeError("libjmt_b200.so ABI version mismatch")
         _lib = h
     return _lib

@@ -253,8 +253,12 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
   return ctr;
 }
 
+// `state` (nullable): device-resident (seed increment, counter offset) added to the host-side values.  A captured CUDA graph
+// bakes the host values in; the device counter (advanced once per forward by rng_advance_kernel) is what makes every
+// REPLAY draw fresh masks -- the same scheme torch uses for graph-safe RNG.
 __global__ void __launch_bounds__(kEwThreads)
-dropout_mask_kernel(uint8_t* __restrict__ mask, int64_t n, float p, uint64_t seed, uint64_t offset) {
+dropout_mask_kernel(uint8_t* __restrict__ mask, int64_t n, float p, uint64_t seed, uint64_t offset, const uint64_t* __restrict__ state) {
+  if (state) { seed += state[0]; offset += state[1]; }
   const int64_t n4 = (n + 3) / 4;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     const uint64_t c = offset + (uint64_t)i;
@@ -268,6 +272,8 @@ dropout_mask_kernel(uint8_t* __restrict__ mask, int64_t n, float p, uint64_t see
     }
   }
 }
+
+__global__ void rng_advance_kernel(uint64_t* state, uint64_t inc) { state[1] += inc; }
 
 // weight_norm: w = g * v / ||v|| per output channel (legacy torch weight_norm), emitted in the two
 // implicit-GEMM layouts.  One block per output channel stages its (cin, k) slice in shared memory so that both the
@@ -590,11 +596,18 @@ extern "C" int jmt_apply_mask(const void* x, const uint8_t* mask, void* out, int
   return check_launch("apply_mask_kernel");
 }
 
-extern "C" int jmt_dropout_mask(uint8_t* mask, int64_t n, float p, uint64_t seed, uint64_t offset, void* stream) {
+extern "C" int jmt_dropout_mask(uint8_t* mask, int64_t n, float p, uint64_t seed, uint64_t offset, const uint64_t* dev_state,
+                                void* stream) {
   JMT_REQUIRE(mask && n >= 0 && p >= 0.f && p < 1.f, "jmt_dropout_mask: bad arguments");
   if (n == 0) return JMT_OK;
-  dropout_mask_kernel<<<grid_for((n + 3) / 4, kEwThreads), kEwThreads, 0, (cudaStream_t)stream>>>(mask, n, p, seed, offset);
+  dropout_mask_kernel<<<grid_for((n + 3) / 4, kEwThreads), kEwThreads, 0, (cudaStream_t)stream>>>(mask, n, p, seed, offset, dev_state);
   return check_launch("dropout_mask_kernel");
+}
+
+extern "C" int jmt_rng_advance(uint64_t* dev_state, uint64_t inc, void* stream) {
+  JMT_REQUIRE(dev_state, "jmt_rng_advance: null state");
+  rng_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(dev_state, inc);
+  return check_launch("rng_advance_kernel");
 }
 
 extern "C" int jmt_weight_norm_fwd(const float* g, const float* v, void* w_fwd, void* w_dgrad, int out_dtype, float* norm,

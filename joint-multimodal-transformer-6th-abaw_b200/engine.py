@@ -114,7 +114,7 @@ class Ctx:
     """One forward(+backward) pass: precision, parameter access, tape, flat gradient bucket."""
 
     def __init__(self, params: Dict[str, torch.Tensor], precision: str, record: bool, training: bool,
-                 wcache: Optional[dict] = None, seed: int = 0):
+                 wcache: Optional[dict] = None, seed: int = 0, rng_state: Optional[torch.Tensor] = None):
         assert precision in ("bf16", "fp32"), precision
         self.params = params
         self.precision = precision
@@ -130,6 +130,7 @@ class Ctx:
         self.bucket: Optional[torch.Tensor] = None
         self.seed = seed
         self.rng_offset = 0
+        self.rng_state = rng_state          # device int64[2]: graph-replay-safe RNG state (see jmt_dropout_mask)
         self.qcache: Dict[Tuple[str, int], Var] = {}
         self.dev = next(iter(params.values())).device if params else torch.device("cuda", torch.cuda.current_device())
         self.keep: List[object] = []          # host arrays that must outlive async launches
@@ -213,6 +214,11 @@ class Ctx:
         if v.gbuf is not None:
             v.gbuf.refs -= 1
             v.gbuf = None
+
+    def finish_forward(self):
+        """Advance the device RNG counter past everything this forward drew (stream-ordered after its last mask)."""
+        if self.rng_state is not None and self.rng_offset > 0:
+            L.check(self.lib.jmt_rng_advance(_ptr(self.rng_state), self.rng_offset, _stream()), "jmt_rng_advance")
 
     def backward(self):
         for fn in reversed(self.tape):
@@ -748,7 +754,7 @@ def dropout(ctx: Ctx, x: Var, p: float) -> Tuple[Var, float]:
     n = x.data.numel()
     assert x.data.is_contiguous()
     mask = ctx.empty((n,), torch.uint8)
-    L.check(ctx.lib.jmt_dropout_mask(_ptr(mask), n, p, ctx.seed, ctx.rng_offset, _stream()), "jmt_dropout_mask")
+    L.check(ctx.lib.jmt_dropout_mask(_ptr(mask), n, p, ctx.seed, ctx.rng_offset, _ptr(ctx.rng_state), _stream()), "jmt_dropout_mask")
     ctx.rng_offset += (n + 3) // 4
     scale = 1.0 / (1.0 - p)
     y = ctx.empty(x.data.shape)
@@ -914,7 +920,7 @@ def causal_conv(ctx: Ctx, x: Var, prefix: str, N: int, Ls: int, cin: int, cout: 
     mask, mscale = None, 1.0
     if drop_p > 0.0 and ctx.training:
         mask = ctx.empty((N * cout,), torch.uint8)
-        L.check(ctx.lib.jmt_dropout_mask(_ptr(mask), N * cout, drop_p, ctx.seed, ctx.rng_offset, _stream()), "jmt_dropout_mask")
+        L.check(ctx.lib.jmt_dropout_mask(_ptr(mask), N * cout, drop_p, ctx.seed, ctx.rng_offset, _ptr(ctx.rng_state), _stream()), "jmt_dropout_mask")
         ctx.rng_offset += (N * cout + 3) // 4
         mscale = 1.0 / (1.0 - drop_p)
     # algorithmic FLOPs = useful taps only: tap j touches L - (k-1-j)*dil positions of each sequence

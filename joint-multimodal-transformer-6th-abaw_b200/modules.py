@@ -96,8 +96,17 @@ class _TapeFn(torch.autograd.Function):
         seed = (torch.initial_seed() * 1000003 + owner._calls) & ((1 << 62) - 1)
         dev_key = params[0].device.index if params else 0
         wc = owner.__dict__.setdefault("_wcache", {}).setdefault(dev_key, {})
-        ctx = E.Ctx(pd, owner.precision, record, owner.training, wc, seed)
+        # dropout draws: host seed (varies per eager call) + a device-resident counter that every forward advances, so a
+        # CUDA-graph replay (host arguments frozen at capture) still gets fresh masks
+        rng = None
+        if owner.training:
+            rs = owner.__dict__.setdefault("_rng_state", {})
+            rng = rs.get(dev_key)
+            if rng is None:
+                rng = rs[dev_key] = torch.zeros(2, dtype=torch.int64, device=params[0].device if params else inputs[0].device)
+        ctx = E.Ctx(pd, owner.precision, record, owner.training, wc, seed, rng)
         outs, setters, getters = runner(ctx, *inputs)
+        ctx.finish_forward()
         actx.jctx, actx.setters, actx.getters, actx.names, actx.owner = ctx, setters, getters, names, owner
         actx.n_in = n_in
         actx.in_shapes = [tuple(i.shape) for i in inputs]

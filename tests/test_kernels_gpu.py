@@ -538,9 +538,16 @@ def test_small_kernels():
     n = 1 << 20
     m1 = torch.empty(n, dtype=torch.uint8, device=dev)
     m2 = torch.empty(n, dtype=torch.uint8, device=dev)
-    L.check(lib.jmt_dropout_mask(E._ptr(m1), n, 0.3, 1234, 0, st), "dm")
-    L.check(lib.jmt_dropout_mask(E._ptr(m2), n, 0.3, 1234, 0, st), "dm")
+    L.check(lib.jmt_dropout_mask(E._ptr(m1), n, 0.3, 1234, 0, None, st), "dm")
+    L.check(lib.jmt_dropout_mask(E._ptr(m2), n, 0.3, 1234, 0, None, st), "dm")
     assert torch.equal(m1, m2) and abs(m1.float().mean().item() - 0.7) < 3e-3
+    # device-resident RNG state: same host arguments, fresh mask after jmt_rng_advance (what a graph replay relies on)
+    state = torch.zeros(2, dtype=torch.int64, device=dev)
+    L.check(lib.jmt_dropout_mask(E._ptr(m2), n, 0.3, 1234, 0, E._ptr(state), st), "dm")
+    assert torch.equal(m1, m2)
+    L.check(lib.jmt_rng_advance(E._ptr(state), (n + 3) // 4, st), "adv")
+    L.check(lib.jmt_dropout_mask(E._ptr(m2), n, 0.3, 1234, 0, E._ptr(state), st), "dm")
+    assert not torch.equal(m1, m2) and abs(m2.float().mean().item() - 0.7) < 3e-3
     # tiny attention fwd/bwd vs torch
     Ls, N, Em, h = 6, 50, 64, 2
     qkv = torch.randn(Ls, N, 3 * Em, requires_grad=True, dtype=torch.float64)

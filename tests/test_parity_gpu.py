@@ -455,3 +455,30 @@ def test_make_graphed_callables_trains_like_eager():
     eager, graph = out
     assert eager[-1] < eager[0] - 0.02, eager                 # the toy problem is being learned (weights really change)
     assert np.allclose(eager, graph, atol=5e-3), (eager, graph)  # ... identically through the graphed callable
+
+
+def test_dropout_masks_vary_across_graph_replays():
+    """Dropout under CUDA-graph replay: the Philox counter lives on the device and every forward advances it, so two
+    replays of the same captured step draw different masks (host-side seeds are frozen into the graph at capture)."""
+    torch.manual_seed(0)
+    model = jmt_b200.Two_transformers(0.5, 0.5, 2, 1, "FC", "FC", 512, precision="bf16").to(DEV).train()
+    aud, vis = (t.to(DEV) for t in O.synth_features(2, 16, [512, 512], 3))
+    outs = []
+
+    def fwd(a_, v_):
+        with torch.no_grad():
+            v, a = model(a_, v_)
+        outs.append(v)
+        return v.sum()
+    g = jmt_b200.GraphedStep(fwd, [(aud, vis)], warmup=2)
+    static_v = outs[-1]                      # the tensor the captured graph writes
+    g.replay(0)
+    v1 = static_v.clone()
+    g.replay(0)
+    v2 = static_v.clone()
+    assert not torch.equal(v1, v2)
+    model.eval()                             # eval: no dropout, deterministic
+    with torch.no_grad():
+        e1, _ = model(aud, vis)
+        e2, _ = model(aud, vis)
+    assert torch.equal(e1, e2)
