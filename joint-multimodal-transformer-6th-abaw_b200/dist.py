@@ -37,19 +37,47 @@ def shard_bounds(n_items: int, rank: int, world: int):
     return (rank * n_items) // world, ((rank + 1) * n_items) // world
 
 
-def make_grad_sync(group=None, average: bool = True):
-    """Hook for `module.set_grad_sync`: all-reduce the flat gradient bucket in place."""
-    def sync(bucket: torch.Tensor):
-        if not dist.is_initialized() or dist.get_world_size(group) == 1:
+class GradSync:
+    """All-reduce of the flat fp32 gradient bucket, optionally in pieces that overlap the rest of backward.
+
+    `start(t)` launches an asynchronous all-reduce (average) of a bucket slice whose gradients are final -- NCCL runs it
+    on its own stream while the tape keeps executing (JMTPipeline starts the fusion slice before the TCN / FcLayer
+    backward) -- and `finish()` makes the compute stream wait for everything started.  Calling the object with the whole
+    bucket does both (the plain end-of-backward all-reduce)."""
+
+    def __init__(self, group=None, average: bool = True):
+        self.group, self.average, self.works, self.pending = group, average, [], []
+
+    def active(self) -> bool:
+        return dist.is_initialized() and dist.get_world_size(self.group) > 1
+
+    def start(self, t: torch.Tensor):
+        if not self.active() or t.numel() == 0:
             return
-        # NCCL averages in the collective itself (no extra pass over the 47 MB bucket); gloo (CPU tests) has no AVG
-        if average and dist.get_backend(group) == "nccl":
-            dist.all_reduce(bucket, op=dist.ReduceOp.AVG, group=group)
-        else:
-            dist.all_reduce(bucket, op=dist.ReduceOp.SUM, group=group)
-            if average:
-                bucket.mul_(1.0 / dist.get_world_size(group))
-    return sync
+        if self.average and dist.get_backend(self.group) == "nccl":
+            # NCCL averages in the collective itself (no extra pass over the bucket)
+            self.works.append(dist.all_reduce(t, op=dist.ReduceOp.AVG, group=self.group, async_op=True))
+        else:                                   # gloo (CPU tests) has no AVG
+            self.works.append(dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            if self.average:
+                self.pending.append(t)
+
+    def finish(self):
+        for w in self.works:
+            w.wait()
+        self.works = []
+        for t in self.pending:
+            t.mul_(1.0 / dist.get_world_size(self.group))
+        self.pending = []
+
+    def __call__(self, bucket: torch.Tensor):
+        self.start(bucket)
+        self.finish()
+
+
+def make_grad_sync(group=None, average: bool = True) -> GradSync:
+    """Hook for `module.set_grad_sync`: all-reduce the flat gradient bucket in place (see GradSync)."""
+    return GradSync(group, average)
 
 
 def allreduce_sums(sums: torch.Tensor, group=None) -> torch.Tensor:

@@ -134,6 +134,9 @@ class Ctx:
         self.qcache: Dict[Tuple[str, int], Var] = {}
         self.dev = next(iter(params.values())).device if params else torch.device("cuda", torch.cuda.current_device())
         self.keep: List[object] = []          # host arrays that must outlive async launches
+        self.bucket_ranges: Dict[str, Tuple[int, int]] = {}
+        self.synced_upto = 0                  # bucket elements whose all-reduce has already been started (overlap)
+        self.grad_sync = None                 # the owner's GradSync hook (set by the autograd bridge)
 
     # ---------------------------------------------------------------- memory helpers
     def empty(self, shape, dtype=None) -> torch.Tensor:
@@ -177,6 +180,7 @@ class Ctx:
             offs.append((n, total, k))
             total += (k + 63) // 64 * 64
         self.bucket = self.zeros((max(total, 64),), torch.float32)
+        self.bucket_ranges = {n: (o, (k + 63) // 64 * 64) for n, o, k in offs}
         for n, o, k in offs:
             self.pgrads[n] = self.bucket[o:o + k].view(self.params[n].shape)
 

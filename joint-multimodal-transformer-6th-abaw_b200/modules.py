@@ -8,6 +8,7 @@ Extra keyword (not in the reference): ``precision`` in {'bf16' (default), 'fp32'
 from __future__ import annotations
 
 import math
+import os
 from typing import List, Optional, Tuple
 
 import torch
@@ -118,13 +119,18 @@ class _TapeFn(torch.autograd.Function):
         if ctx is None:
             raise RuntimeError("jmt_b200: backward through the same forward twice is not supported")
         ctx.prepare_param_grads(actx.names)
+        hook = getattr(actx.owner, "_grad_sync", None)
+        ctx.grad_sync = hook
         for s, g in zip(actx.setters, gouts):
             if g is not None:
                 s(g)
         ctx.backward()
-        hook = getattr(actx.owner, "_grad_sync", None)
-        if hook is not None:
-            hook(ctx.bucket)                      # NCCL all-reduce of the flat live-gradient bucket
+        if hook is not None:                      # NCCL all-reduce of the flat live-gradient bucket
+            if ctx.synced_upto > 0 and hasattr(hook, "start"):
+                hook.start(ctx.bucket[ctx.synced_upto:])      # the head of the bucket is already in flight (overlap)
+                hook.finish()
+            else:
+                hook(ctx.bucket)
         gin = [g().view(sh) if g is not None else None for g, sh in zip(actx.getters, actx.in_shapes)]
         gp = [ctx.pgrads[n] for n in actx.names]
         actx.jctx = None
@@ -665,6 +671,20 @@ class JMTPipeline(_JmtModule):
                 video_n = _l2norm_var(ctx, h)
             else:
                 video_n, gv = E.l2norm(ctx, vis, vis.requires_grad)
+            if ctx.record:
+                # Backward runs the tape in reverse: everything recorded after this point (the fusion) is done when this
+                # entry executes, so the fusion slice of the gradient bucket (it comes first: fusion.* parameters are
+                # registered first) can be all-reduced while the TCN / FcLayer backward still runs.
+                def start_fusion_sync():
+                    hook = ctx.grad_sync
+                    if hook is None or not hasattr(hook, "start") or os.environ.get("JMT_GRAD_OVERLAP", "1") == "0":
+                        return
+                    hi = max((o + k for n, (o, k) in ctx.bucket_ranges.items() if n.startswith("fusion.")), default=0)
+                    lo = min((o for n, (o, k) in ctx.bucket_ranges.items() if not n.startswith("fusion.")), default=hi)
+                    if 0 < hi <= lo:
+                        hook.start(ctx.bucket[:hi])
+                        ctx.synced_upto = hi
+                ctx.tape.append(start_fusion_sync)
             outs, setters = _two_transformers_graph(ctx, fusion, "fusion.", video_n, audio_n, B, T)
             return outs, setters, [ga, gv]
         v, a = self._run(runner, audio, visual)

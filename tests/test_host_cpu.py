@@ -107,6 +107,13 @@ def _dist_worker(rank, world, port, q):
     bucket = torch.full((257,), float(rank + 1))
     jmt_b200.dist.make_grad_sync()(bucket)
     ok &= bool(torch.allclose(bucket, torch.full((257,), (1 + world) / 2)))
+    # overlapped form: the head of the bucket is started early, the tail at the end, one finish()
+    gs = jmt_b200.dist.make_grad_sync()
+    b2 = torch.arange(300, dtype=torch.float32) * (rank + 1)
+    gs.start(b2[:128])
+    gs.start(b2[128:])
+    gs.finish()
+    ok &= bool(torch.allclose(b2, torch.arange(300, dtype=torch.float32) * (1 + world) / 2))
     p = torch.nn.Linear(3, 3)
     jmt_b200.dist.broadcast_parameters(p)
     flat = torch.cat([t.reshape(-1) for t in p.parameters()]).detach()
