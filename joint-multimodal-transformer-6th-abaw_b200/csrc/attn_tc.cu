@@ -79,29 +79,42 @@ struct RowCtx {
 
 // forward, pass 1 on one 32-key chunk: four independent partial maxima
 __device__ __forceinline__ void row_fwd_max(const uint32_t (&r)[32], int nvalid, float (&mx)[4]) {
+  if (nvalid >= 32) {                      // whole chunk valid (all but the last chunk of a row): no per-element predicate
 #pragma unroll
-  for (int j = 0; j < 32; ++j) mx[j & 3] = (nvalid >= 32 || j < nvalid) ? fmaxf(mx[j & 3], __uint_as_float(r[j])) : mx[j & 3];
+    for (int j = 0; j < 32; ++j) mx[j & 3] = fmaxf(mx[j & 3], __uint_as_float(r[j]));
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) mx[j & 3] = j < nvalid ? fmaxf(mx[j & 3], __uint_as_float(r[j])) : mx[j & 3];
+  }
 }
 // forward, pass 2 on one 32-key chunk: e = exp2(v*c - rowmax*c) -> bf16 -> swizzled X, four independent partial sums
-__device__ __forceinline__ void row_fwd_exp(const AtParams& p, const uint32_t (&r)[32], int nvalid, float shift, float (&sum)[4],
-                                            uint32_t xbase, uint32_t piece0, uint32_t sw) {
+template <bool FULL>
+__device__ __forceinline__ void row_fwd_exp_t(const AtParams& p, const uint32_t (&r)[32], int nvalid, float shift, float (&sum)[4],
+                                              uint32_t xbase, uint32_t piece0, uint32_t sw) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     float x[8];
 #pragma unroll
     for (int h = 0; h < 8; ++h) {
       const float y = ex2_approx(fmaf(__uint_as_float(r[i * 8 + h]), p.c_exp, -shift));
-      x[h] = (nvalid >= 32 || i * 8 + h < nvalid) ? y : 0.f;
+      x[h] = (FULL || i * 8 + h < nvalid) ? y : 0.f;
       sum[h & 3] += x[h];
     }
     st_shared_v4(xbase + (((piece0 + (uint32_t)i) ^ sw) << 4), pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]),
                  pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
   }
 }
+__device__ __forceinline__ void row_fwd_exp(const AtParams& p, const uint32_t (&r)[32], int nvalid, float shift, float (&sum)[4],
+                                            uint32_t xbase, uint32_t piece0, uint32_t sw) {
+  if (nvalid >= 32) row_fwd_exp_t<true>(p, r, nvalid, shift, sum, xbase, piece0, sw);
+  else row_fwd_exp_t<false>(p, r, nvalid, shift, sum, xbase, piece0, sw);
+}
 
 // backward, one 32-key chunk: dS = scale * P * (dP - delta) with P read from the X tile it overwrites
-__device__ __forceinline__ void row_bwd_chunk(const AtParams& p, const uint32_t (&r)[32], int nvalid, float delta,
-                                              uint32_t xbase, uint32_t piece0, uint32_t sw) {
+template <bool FULL>
+__device__ __forceinline__ void row_bwd_chunk_t(const AtParams& p, const uint32_t (&r)[32], int nvalid, float delta,
+                                                uint32_t xbase, uint32_t piece0, uint32_t sw) {
+  const float ds = p.scale * delta;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const uint32_t addr = xbase + (((piece0 + (uint32_t)i) ^ sw) << 4);
@@ -111,11 +124,16 @@ __device__ __forceinline__ void row_bwd_chunk(const AtParams& p, const uint32_t 
 #pragma unroll
     for (int h = 0; h < 8; ++h) {
       const float pf = (h & 1) ? bf16hi(w[h >> 1]) : bf16lo(w[h >> 1]);
-      const float y = p.scale * pf * (__uint_as_float(r[i * 8 + h]) - delta);
-      x[h] = (nvalid >= 32 || i * 8 + h < nvalid) ? y : 0.f;
+      const float y = pf * fmaf(p.scale, __uint_as_float(r[i * 8 + h]), -ds);       // scale * P * (dP - delta)
+      x[h] = (FULL || i * 8 + h < nvalid) ? y : 0.f;
     }
     st_shared_v4(addr, pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
   }
+}
+__device__ __forceinline__ void row_bwd_chunk(const AtParams& p, const uint32_t (&r)[32], int nvalid, float delta,
+                                              uint32_t xbase, uint32_t piece0, uint32_t sw) {
+  if (nvalid >= 32) row_bwd_chunk_t<true>(p, r, nvalid, delta, xbase, piece0, sw);
+  else row_bwd_chunk_t<false>(p, r, nvalid, delta, xbase, piece0, sw);
 }
 
 // The row-wise algebra between the two GEMMs for one thread (= one query row, every other 32-key chunk):
