@@ -375,6 +375,7 @@ def main():
                 "config": workload_config(args), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
                 "roofline": roof, "cpu_baseline": cpu, "final_loss": final_loss,
                 "launch_mode": "cuda_graph" if graphed is not None else "eager", "host_enqueue_ms_per_eager_step": host_enqueue_ms,
+                "peak_hbm_gb": torch.cuda.max_memory_allocated(dev) / 1e9,
                 "model_tflops": 3 * FWD_GFLOP_PER_WINDOW * value / 1e3}
         print(json.dumps(line), flush=True)
     # Teardown: captured graphs hold NCCL kernels; destroying the process group under them hung a 2-GPU run once
