@@ -42,7 +42,29 @@ __global__ void __launch_bounds__(256) regressor_tail_fwd_kernel(TailArgs a) {
   }
 }
 
-template <typename T>
+// 4 consecutive hidden units of one row (lane l owns columns 4l .. 4l+3): one 8-byte (bf16) / 16-byte (fp32) access
+__device__ __forceinline__ void load4(const float* p, float (&v)[4]) {
+  const float4 t = *reinterpret_cast<const float4*>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+__device__ __forceinline__ void load4(const __nv_bfloat16* p, float (&v)[4]) {
+  const uint2 r = *reinterpret_cast<const uint2*>(p);
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r.x));
+  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r.y));
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+__device__ __forceinline__ void store4(float* p, const float (&v)[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void store4(__nv_bfloat16* p, const float (&v)[4]) {
+  uint2 r;
+  *reinterpret_cast<__nv_bfloat162*>(&r.x) = __floats2bfloat162_rn(v[0], v[1]);
+  *reinterpret_cast<__nv_bfloat162*>(&r.y) = __floats2bfloat162_rn(v[2], v[3]);
+  *reinterpret_cast<uint2*>(p) = r;
+}
+
+// kVec: rows are 4-element aligned (pointers and pitch), so lane l owns columns 4l..4l+3 and moves them with one vector
+// access; otherwise lane l owns columns l, l+32, l+64, l+96 (scalar accesses).  dw[g][j] is the column col(j) either way.
+template <typename T, bool kVec>
 __global__ void __launch_bounds__(256) regressor_tail_bwd_kernel(TailArgs a) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t w0 = (int64_t)blockIdx.x * 8 + warp;
@@ -61,14 +83,29 @@ __global__ void __launch_bounds__(256) regressor_tail_bwd_kernel(TailArgs a) {
       const T* hr = (const T*)a.h[g] + m * a.h_ld;
       T* dr = (T*)a.dh[g] + m * a.h_ld;
       if (lane == 0) db[g] += go;
+      if constexpr (kVec) {
+        float hv[4], v[4], old[4];
+        load4(hr + 4 * lane, hv);
+        const float4 wv = __ldg(reinterpret_cast<const float4*>(a.w[g]) + lane);
+        const float wr[4] = {wv.x, wv.y, wv.z, wv.w};
+        if (a.accumulate[g]) load4(dr + 4 * lane, old);
 #pragma unroll
-      for (int j = 0; j < kHid / 32; ++j) {
-        const int c = lane + 32 * j;
-        const float hv = to_f32(hr[c]);
-        dw[g][j] = fmaf(go, hv, dw[g][j]);
-        float v = hv > 0.f ? go * __ldg(a.w[g] + c) * a.scale[g] : 0.f;
-        if (a.accumulate[g]) v += to_f32(dr[c]);
-        dr[c] = from_f32<T>(v);
+        for (int j = 0; j < 4; ++j) {
+          dw[g][j] = fmaf(go, hv[j], dw[g][j]);
+          v[j] = hv[j] > 0.f ? go * wr[j] * a.scale[g] : 0.f;
+          if (a.accumulate[g]) v[j] += old[j];
+        }
+        store4(dr + 4 * lane, v);
+      } else {
+#pragma unroll
+        for (int j = 0; j < kHid / 32; ++j) {
+          const int c = lane + 32 * j;
+          const float hv = to_f32(hr[c]);
+          dw[g][j] = fmaf(go, hv, dw[g][j]);
+          float v = hv > 0.f ? go * __ldg(a.w[g] + c) * a.scale[g] : 0.f;
+          if (a.accumulate[g]) v += to_f32(dr[c]);
+          dr[c] = from_f32<T>(v);
+        }
       }
     }
   }
@@ -78,7 +115,7 @@ __global__ void __launch_bounds__(256) regressor_tail_bwd_kernel(TailArgs a) {
     if (g >= a.G) break;
     __syncthreads();
 #pragma unroll
-    for (int j = 0; j < kHid / 32; ++j) sh[warp][lane + 32 * j] = dw[g][j];
+    for (int j = 0; j < kHid / 32; ++j) sh[warp][kVec ? 4 * lane + j : lane + 32 * j] = dw[g][j];
     if (lane == 0) sh[warp][kHid] = db[g];
     __syncthreads();
     if (threadIdx.x <= kHid) {
@@ -131,7 +168,14 @@ extern "C" int jmt_regressor_tail_bwd(int G, const void* const* h, int64_t h_ld,
     a.accumulate[g] = accumulate[g]; a.scale[g] = scale[g];
   }
   if (M == 0) return JMT_OK;
-  const int grid = grid_for(M, 8 * 32, kNumSMs * 2);
-  JMT_DISPATCH_DTYPE(dtype, T_, (regressor_tail_bwd_kernel<T_><<<grid, 256, 0, (cudaStream_t)stream>>>(a)));
+  // 8 rows per block-iteration; enough blocks (6 per SM) to cover the latency of the strided d(out) gather
+  const int grid = grid_for(M, 8 * 8, kNumSMs * 6);
+  const size_t esz = dtype == JMT_BF16 ? 2 : 4;
+  bool vec = (h_ld % 4) == 0;
+  for (int g = 0; g < G; ++g)
+    vec = vec && ((reinterpret_cast<uintptr_t>(h[g]) | reinterpret_cast<uintptr_t>(dh[g])) % (4 * esz)) == 0 &&
+          (reinterpret_cast<uintptr_t>(w[g]) & 15) == 0;
+  if (vec) JMT_DISPATCH_DTYPE(dtype, T_, (regressor_tail_bwd_kernel<T_, true><<<grid, 256, 0, (cudaStream_t)stream>>>(a)));
+  else JMT_DISPATCH_DTYPE(dtype, T_, (regressor_tail_bwd_kernel<T_, false><<<grid, 256, 0, (cudaStream_t)stream>>>(a)));
   return check_launch("regressor_tail_bwd_kernel");
 }

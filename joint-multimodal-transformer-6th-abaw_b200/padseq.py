@@ -38,3 +38,25 @@ class TrainPadSequence:
         visual = torch.stack([x[0] for x in sorted_batch])
         return (visual, audio, torch.stack([x[2] for x in sorted_batch]), torch.stack([x[3] for x in sorted_batch]),
                 [x[4] for x in sorted_batch])
+
+
+class ValPadSequence:
+    """padSequence.py:34-72: samples (clip, spectrogram, frameids, v_ids, v_lengths, labelV, labelA, wavfile)."""
+
+    def __call__(self, sorted_batch):
+        audio = pad_spectrograms([x[1] for x in sorted_batch])
+        visual = torch.stack([x[0] for x in sorted_batch])
+        return (visual, audio, [x[2] for x in sorted_batch], [x[3] for x in sorted_batch], [x[4] for x in sorted_batch],
+                torch.stack([x[5] for x in sorted_batch]), torch.stack([x[6] for x in sorted_batch]),
+                [x[7] for x in sorted_batch])
+
+
+class TestPadSequence:
+    """padSequence.py:75-101: samples (clip, spectrogram, frameids, v_ids, v_lengths, wavfile); no labels."""
+    __test__ = False          # not a pytest class
+
+    def __call__(self, sorted_batch):
+        audio = pad_spectrograms([x[1] for x in sorted_batch])
+        visual = torch.stack([x[0] for x in sorted_batch])
+        return (visual, audio, [x[2] for x in sorted_batch], [x[3] for x in sorted_batch], [x[4] for x in sorted_batch],
+                [x[5] for x in sorted_batch])

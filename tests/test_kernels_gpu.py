@@ -477,6 +477,81 @@ def test_padseq_golden(golden_meta, golden_dir):
     np.testing.assert_allclose(out.double().sum().numpy(), g["audio_sum"], rtol=1e-12)
 
 
+def _pad_restated(specs):
+    """padSequence.py:9-24 zero-fill written directly in torch (right-aligned copy)."""
+    mw = max(s.shape[3] for s in specs)
+    out = torch.zeros(len(specs), 16, 1, 64, mw)
+    for i, s in enumerate(specs):
+        out[i, :, :, :, mw - s.shape[3]:] = s.cpu()
+    return out
+
+
+def test_val_and_test_padsequence_tuples():
+    gen = torch.Generator().manual_seed(77)
+    widths = [104, 97, 104, 88]
+    samples = []
+    for i, w in enumerate(widths):
+        clip = torch.randn(16, 3, 2, 4, 4, generator=gen).cuda()
+        spec = torch.randn(16, 1, 64, w, generator=gen).cuda()
+        samples.append((clip, spec, list(range(i, i + 16)), f"vid{i}", 100 + i,
+                        torch.randn(16, generator=gen).cuda(), torch.randn(16, generator=gen).cuda(), f"w{i}.wav"))
+    want_audio = _pad_restated([s[1] for s in samples])
+    vis, aud, fids, vids, vlens, lv, la, wav = jmt_b200.padseq.ValPadSequence()(samples)
+    assert torch.equal(aud.cpu(), want_audio)
+    assert torch.equal(vis, torch.stack([s[0] for s in samples]))
+    assert fids == [s[2] for s in samples] and vids == [s[3] for s in samples] and vlens == [s[4] for s in samples]
+    assert torch.equal(lv, torch.stack([s[5] for s in samples])) and torch.equal(la, torch.stack([s[6] for s in samples]))
+    assert wav == [s[7] for s in samples]
+    tsamples = [(s[0], s[1], s[2], s[3], s[4], s[7]) for s in samples]
+    out = jmt_b200.padseq.TestPadSequence()(tsamples)
+    assert len(out) == 6 and torch.equal(out[1].cpu(), want_audio) and out[5] == wav and out[4] == vlens
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("misalign", [0, 1])
+def test_regressor_tail_bwd_kernel(dt, misalign):
+    """Backward of the fused Linear(128, 1) tails (two_transformers.py:104-114): d(hidden) through the ReLU mask, dW, db for
+    two groups sharing one hidden buffer (accumulate) and a third with its own; vector path and (misaligned rows) scalar path."""
+    import ctypes as C
+    torch.manual_seed(11)
+    dev = torch.device("cuda")
+    lib, st = L.lib(), E._stream()
+    B, T, ld = 5, 37, 264
+    M = B * T
+    code = L.BF16 if dt == torch.bfloat16 else L.F32
+    hbuf = [torch.relu(torch.randn(M * ld + 8)).to(dt).to(dev) for _ in range(2)]
+    hs = [hbuf[0][misalign:misalign + M * ld].view(M, ld), hbuf[1][misalign:misalign + M * ld].view(M, ld)]
+    groups = [0, 0, 1]                                   # groups 0 and 1 read the same hidden rows (columns 0..127)
+    ws = [torch.randn(128, device=dev) for _ in groups]
+    douts = [torch.randn(T, B, device=dev) for _ in groups]          # (T, B) output layout: row m = b*T + t -> [t, b]
+    dhbuf = [torch.full((M * ld + 8,), 7.0, device=dev).to(dt) for _ in range(2)]
+    dhs = [dhbuf[i][misalign:misalign + M * ld].view(M, ld) for i in range(2)]
+    dws = [torch.zeros(128, device=dev) for _ in groups]
+    dbs = [torch.zeros(1, device=dev) for _ in groups]
+    scale = [1.0, 2.0, 1.25]
+    arr = lambda ts: (C.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
+    L.check(lib.jmt_regressor_tail_bwd(3, arr([hs[g] for g in groups]), ld, code, arr(ws), arr(douts),
+                                       arr([dhs[g] for g in groups]), (C.c_int * 3)(0, 1, 0), (C.c_float * 3)(*scale),
+                                       arr(dws), arr(dbs), M, T, 1, B, st), "tail_bwd")
+    torch.cuda.synchronize()
+    tol = 2e-2 if dt == torch.bfloat16 else 1e-5
+    want_dh = [torch.zeros(M, 128, dtype=torch.float64), torch.zeros(M, 128, dtype=torch.float64)]
+    for g, hg in enumerate(groups):
+        h = hs[hg][:, :128].double().cpu()
+        go = douts[g].t().reshape(M).double().cpu()              # row m = b*T + t
+        want_dh[hg] += (h > 0) * go[:, None] * ws[g].double().cpu()[None, :] * scale[g]
+        assert _close(dws[g].cpu(), (go[:, None] * h).sum(0), 1e-4)
+        assert _close(dbs[g].cpu(), go.sum()[None], 1e-4)
+    for hg in range(2):
+        assert _close(dhs[hg][:, :128].cpu(), want_dh[hg], tol)
+        assert torch.all(dhs[hg][:, 128:] == 7.0)                    # columns past the 128 hidden units are not touched
+
+
+def _close(got, want, tol):
+    got, want = got.double(), want.double()
+    return float((got - want).abs().max()) <= tol * max(1.0, float(want.abs().max()))
+
+
 def test_small_kernels():
     torch.manual_seed(5)
     dev = torch.device("cuda")
@@ -494,6 +569,14 @@ def test_small_kernels():
     a_d = a.to(dev)
     L.check(lib.jmt_colsum(E._ptr(a_d), L.BF16, 130, 1000, 130, E._ptr(out), st), "cs")
     assert (out.cpu() - a.float().sum(0)).abs().max() < 1e-3
+    # vectorised path: 4x unrolled body + tail, on a strided column slice (ld > cols), accumulating into out
+    for rows in (5003, 9, 76800):
+        a = torch.randn(rows, 1536).to(torch.bfloat16)
+        a_d = a.to(dev)
+        out = torch.ones(512, device=dev)
+        L.check(lib.jmt_colsum(E._ptr(a_d[:, 512:1024]), L.BF16, 1536, rows, 512, E._ptr(out), st), "cs")
+        want = 1.0 + a[:, 512:1024].double().sum(0)
+        assert (out.cpu().double() - want).abs().max() < 2e-3 * max(1.0, rows ** 0.5 / 30)
     # fused activation-gradient + channel-dropout replay + bias gradient
     for dt, tol in ((torch.float32, 1e-4), (torch.bfloat16, 2e-2)):
         nb, Lr, Cc = 3, 37, 136

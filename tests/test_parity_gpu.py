@@ -244,6 +244,56 @@ def test_training_semantics_dropout_and_modes():
     assert "vregressor.3.weight" in changed and "mm_transformer.fc.weight" in changed
 
 
+def test_replicas_from_python_threads_are_reentrant():
+    """MyDataParallel (main.py:487-489) calls forward of replicated modules from one Python thread per replica: the
+    library keeps no global mutable state (thread-local error text, per-call tensor maps, stream taken from the caller),
+    so concurrent forward+backward on two streams gives exactly what the same calls give one after the other."""
+    import copy, threading
+    torch.manual_seed(0)
+    base = jmt_b200.Two_transformers(0.0, 0.0, 2, 1, "TRANSFORMER", "FC", 512, precision="bf16").to(DEV).train()
+    feats = [tuple(t.to(DEV) for t in O.synth_features(3, 40, [512, 512], 10 + i)) for i in range(2)]
+
+    def run(model, aud, vis, out, idx, stream=None):
+        for _ in range(4):
+            model.zero_grad(set_to_none=True)
+            with torch.cuda.stream(stream) if stream is not None else contextlib.nullcontext():
+                v, a = model(aud, vis)
+                (v.float().sum() + 2 * a.float().sum()).backward()
+            if stream is not None:
+                stream.synchronize()
+        out[idx] = (v.detach().clone(), a.detach().clone(),
+                    {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None})
+
+    import contextlib
+    serial, threaded = [None, None], [None, None]
+    for i in range(2):
+        run(copy.deepcopy(base), *feats[i], serial, i)
+    torch.cuda.synchronize()
+    errors = []
+
+    def guarded(*args):
+        try:
+            run(*args)
+        except Exception as e:       # surface worker exceptions in the main thread
+            errors.append(e)
+
+    threads = [threading.Thread(target=guarded, args=(copy.deepcopy(base), *feats[i], threaded, i, torch.cuda.Stream()))
+               for i in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    torch.cuda.synchronize()
+    assert not errors, errors
+    for i in range(2):
+        # split-K / reduce-add GEMMs accumulate with fp32 atomics, so the order (not the operands) may differ between runs
+        for j in range(2):
+            assert _rel(threaded[i][j].float().cpu(), serial[i][j].float().cpu()) < 1e-2
+        assert serial[i][2].keys() == threaded[i][2].keys()
+        for k in serial[i][2]:
+            assert _rel(threaded[i][2][k].float().cpu(), serial[i][2][k].float().cpu()) < 1e-2, k
+
+
 def test_cpu_tensor_is_refused():
     model = jmt_b200.FcLayer(768, 512).to(DEV)
     with pytest.raises(RuntimeError, match="CUDA"):
