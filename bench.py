@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying the captured step")
+    ap.add_argument("--strong", action="store_true",
+                    help="strong scaling (SURVEY C3): --batch is the GLOBAL number of windows, split evenly over the ranks")
     ap.add_argument("--gemm-table", default=None, help="write the per-shape GEMM timing table (roofline pass) to this file")
     return ap.parse_args()
 
@@ -167,6 +169,10 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    if args.strong:
+        if args.batch % world:
+            raise SystemExit(f"--strong needs --batch ({args.batch}) divisible by the number of ranks ({world})")
+        args.batch //= world
     B, T = args.batch, args.seq
 
     torch.manual_seed(0)                                   # identical weights on every rank
@@ -370,8 +376,8 @@ def main():
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "windows/s", "n_gpus": world, "steps": args.steps,
-                "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": args.precision if args.precision == "bf16" else "f32", "data": "synthetic",
+                "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": args.precision if args.precision == "bf16" else "f32", "data": "synthetic",
                 "config": workload_config(args), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
                 "roofline": roof, "cpu_baseline": cpu, "final_loss": final_loss,
                 "launch_mode": "cuda_graph" if graphed is not None else "eager", "host_enqueue_ms_per_eager_step": host_enqueue_ms,

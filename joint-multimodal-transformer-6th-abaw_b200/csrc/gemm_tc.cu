@@ -39,6 +39,7 @@ struct TcParams {
   int a_major, b_major;
   int a_shift0, a_shift_step, b_shift0, b_shift_step;
   int b_has_b0, b_has_b1;
+  int a_has_b0, a_has_b1;   // 0: A is shared by every entry of that batch dimension (stride 0), its coordinate stays 0
   int a_mn5, b_mn5;    // MN-major operand tile fetched by ONE 5-D TMA instruction (all its 64-wide chunks) instead of one per chunk
   int reduce_batch;
   uint32_t idesc;
@@ -312,6 +313,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         int b0 = (int)b0_u, b1 = (int)b1_u;
         for (int it = c.it0; it < c.it1; ++it) {
           const int bb0 = p.b_has_b0 ? b0 : 0, bb1 = p.b_has_b1 ? b1 : 0;
+          const int ab0 = p.a_has_b0 ? b0 : 0, ab1 = p.a_has_b1 ? b1 : 0;
           const int ash = p.a_shift0 + tap * p.a_shift_step;
           const int bsh = p.b_shift0 + tap * p.b_shift_step;
           const long long tw = p.prof ? clock64() : 0;
@@ -323,12 +325,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             const uint32_t fb = full_bar + 8 * stage;
             mbar_expect_tx(fb, kAStageBytes + p.b_tx_bytes);
             if (p.a_major == JMT_MAJOR_K) {
-              tma_load_4d(a_dst, &tma_a, fb, kb * kBlockK, c.m0 + ash, b0, b1);
+              tma_load_4d(a_dst, &tma_a, fb, kb * kBlockK, c.m0 + ash, ab0, ab1);
             } else if (p.a_mn5) {
-              tma_load_5d(a_dst, &tma_a, fb, 0, kb * kBlockK + ash, c.m0 >> 6, b0, b1);
+              tma_load_5d(a_dst, &tma_a, fb, 0, kb * kBlockK + ash, c.m0 >> 6, ab0, ab1);
             } else {
-              tma_load_4d(a_dst, &tma_a, fb, c.m0, kb * kBlockK + ash, b0, b1);
-              tma_load_4d(a_dst + 8192, &tma_a, fb, c.m0 + 64, kb * kBlockK + ash, b0, b1);
+              tma_load_4d(a_dst, &tma_a, fb, c.m0, kb * kBlockK + ash, ab0, ab1);
+              tma_load_4d(a_dst + 8192, &tma_a, fb, c.m0 + 64, kb * kBlockK + ash, ab0, ab1);
             }
             if (p.b_major == JMT_MAJOR_K) {
               tma_load_4d(b_dst, &tma_b, fb, tap * p.K + kb * kBlockK, c.n0, bb0, bb1);
@@ -342,12 +344,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             const uint32_t fb = full_leader + 8 * stage;
             mbar_expect_tx_cluster(fb, kAStageBytes + p.b_tx_bytes);
             if (p.a_major == JMT_MAJOR_K) {
-              tma_load_4d_2sm(a_dst, &tma_a, fb, kb * kBlockK, c.m0 + ash, b0, b1);
+              tma_load_4d_2sm(a_dst, &tma_a, fb, kb * kBlockK, c.m0 + ash, ab0, ab1);
             } else if (p.a_mn5) {
-              tma_load_5d_2sm(a_dst, &tma_a, fb, 0, kb * kBlockK + ash, c.m0 >> 6, b0, b1);
+              tma_load_5d_2sm(a_dst, &tma_a, fb, 0, kb * kBlockK + ash, c.m0 >> 6, ab0, ab1);
             } else {
-              tma_load_4d_2sm(a_dst, &tma_a, fb, c.m0, kb * kBlockK + ash, b0, b1);
-              tma_load_4d_2sm(a_dst + 8192, &tma_a, fb, c.m0 + 64, kb * kBlockK + ash, b0, b1);
+              tma_load_4d_2sm(a_dst, &tma_a, fb, c.m0, kb * kBlockK + ash, ab0, ab1);
+              tma_load_4d_2sm(a_dst + 8192, &tma_a, fb, c.m0 + 64, kb * kBlockK + ash, ab0, ab1);
             }
             if (p.b_major == JMT_MAJOR_K) {
               tma_load_4d_2sm(b_dst, &tma_b, fb, tap * p.K + kb * kBlockK, c.n0 + n_off, bb0, bb1);
@@ -537,6 +539,8 @@ extern "C" int jmt_gemm_bf16(const jmt_gemm_desc* g, void* stream) {
   p.split_k = g->split_k < p.iters_total ? g->split_k : p.iters_total;
   p.b_has_b0 = (g->nb0 > 1 && g->b_bs0 != 0) ? 1 : 0;
   p.b_has_b1 = (g->nb1 > 1 && g->b_bs1 != 0) ? 1 : 0;
+  p.a_has_b0 = (g->nb0 > 1 && g->a_bs0 != 0) ? 1 : 0;
+  p.a_has_b1 = (g->nb1 > 1 && g->a_bs1 != 0) ? 1 : 0;
   // CTA pairs (cta_group::2, M = 256): along M when the ghost tile of an odd tail wastes < ~10 %, else across two
   // consecutive batch entries when they share B (implicit-GEMM conv: weights are not batched)
   const char* env_cl = getenv("JMT_GEMM_CLUSTER");
@@ -586,12 +590,13 @@ extern "C" int jmt_gemm_bf16(const jmt_gemm_desc* g, void* stream) {
   // A: K-major -> (K, a_rows) box {64,128}; MN-major -> (M, a_rows = k extent): both 64-wide chunks of the 128-row tile in one
   // 5-D box when M % 64 == 0, else two 4-D {64,64} boxes
   p.a_mn5 = (g->a_major == JMT_MAJOR_MN && g->M % 64 == 0) ? 1 : 0;
+  const int anb0 = p.a_has_b0 ? g->nb0 : 1, anb1 = p.a_has_b1 ? g->nb1 : 1;
   if (g->a_major == JMT_MAJOR_K)
-    rc = make_map(&map_a, g->a, g->K, g->a_rows, g->a_ld, g->nb0, g->a_bs0, g->nb1, g->a_bs1, kBlockM, "jmt_gemm_bf16(A)");
+    rc = make_map(&map_a, g->a, g->K, g->a_rows, g->a_ld, anb0, g->a_bs0, anb1, g->a_bs1, kBlockM, "jmt_gemm_bf16(A)");
   else if (p.a_mn5)
-    rc = make_map_mn5(&map_a, g->a, g->M, g->a_rows, g->a_ld, g->nb0, g->a_bs0, g->nb1, g->a_bs1, kBlockK, 2, "jmt_gemm_bf16(A)");
+    rc = make_map_mn5(&map_a, g->a, g->M, g->a_rows, g->a_ld, anb0, g->a_bs0, anb1, g->a_bs1, kBlockK, 2, "jmt_gemm_bf16(A)");
   else
-    rc = make_map(&map_a, g->a, g->M, g->a_rows, g->a_ld, g->nb0, g->a_bs0, g->nb1, g->a_bs1, kBlockK, "jmt_gemm_bf16(A)");
+    rc = make_map(&map_a, g->a, g->M, g->a_rows, g->a_ld, anb0, g->a_bs0, anb1, g->a_bs1, kBlockK, "jmt_gemm_bf16(A)");
   if (rc != JMT_OK) return rc;
   const int bnb0 = p.b_has_b0 ? g->nb0 : 1, bnb1 = p.b_has_b1 ? g->nb1 : 1;
   p.b_mn5 = (g->b_major == JMT_MAJOR_MN && g->N % 64 == 0 && p.block_n % 64 == 0 && b_cols_cta % 64 == 0) ? 1 : 0;

@@ -326,6 +326,20 @@ def split_k_for(red: int, tiles: int) -> int:
     return max(1, min(want, kblocks // 8)) if kblocks >= 16 else 1
 
 
+def split_k_waves(red: int, tiles: int, units: int = 74) -> int:
+    """Split factor for a weight-gradient GEMM with many output tiles (`tiles` CTA-pair tiles, `units` CTA pairs on the chip):
+    the smallest-traffic split whose tiles*split fills whole waves best (every extra split costs one more fp32 reduce-add
+    pass over the output), keeping at least 8 k-blocks per split."""
+    kblocks = max(1, (red + 63) // 64)
+    best, best_score = 1, -1.0
+    for sk in range(1, max(1, min(32, kblocks // 8)) + 1):
+        n = tiles * sk
+        score = n / (units * ((n + units - 1) // units)) - 0.004 * sk
+        if score > best_score:
+            best, best_score = sk, score
+    return best
+
+
 # --------------------------------------------------------------------------- differentiable ops
 def from_external(ctx: Ctx, x: torch.Tensor, needs_grad: bool):
     """External (.., D) tensor -> activation-dtype Var (cast copy).  Returns (Var, grad getter)."""
@@ -948,14 +962,18 @@ def causal_conv(ctx: Ctx, x: Var, prefix: str, N: int, Ls: int, cin: int, cout: 
             else:
                 L.check(ctx.lib.jmt_colsum(_ptr(dy), _DT[dy.dtype], cout, R, cout, _ptr(ctx.pgrad(prefix + "bias")),
                                            _stream()), "jmt_colsum")
-            # wgrad per tap: dW_j (Cout, Cin) = dy^T shift_j(x) over all flat rows (split-K, fp32 atomics)
+            # wgrad: dW_j (Cout, Cin) = dy^T shift_j(x) over all flat rows (split-K, fp32 reduce-add).  The k taps are ONE
+            # launch: tap j is batch entry j, whose B operand is x moved down by j*dil rows (an overlapping batch stride) under a
+            # common shift of -(k-1)*dil, whose A operand dy is shared (stride 0) and whose D is column block j of dW.  The
+            # rows the common shift zero-fills but tap j would have read (x rows 0 .. j*dil-1) are padding rows of the first
+            # sequence, i.e. zeros (pad >= (k-1)*dil is asserted above).
             dw = ctx.zeros((cout, k * cin), torch.float32)
-            tiles = ((cout + 127) // 128) * ((cin + 255) // 256)
-            sk = split_k_for(R, tiles)          # each tap is its own launch: fill the chip per launch
-            for j in range(k):
-                gemm(ctx, dy, x.data, dw[:, j * cin:(j + 1) * cin], M=cout, N=cin, K=R,
-                     a_major=L.MAJOR_MN, b_major=L.MAJOR_MN, a_rows=R, b_rows=R, a_ld=cout, b_ld=cin, d_ld=k * cin,
-                     b_shift=(-(k - 1 - j) * dil, 0), store=L.ATOMIC_ADD, split_k=sk, alg_flops=tap_flops[j])
+            tiles = ((cout + 255) // 256) * ((cin + 255) // 256) * k
+            # (B's row extent stops (k-1)*dil short of R: with tap j's base moved down by j*dil rows nothing past row R-1 of
+            # x is ever addressed, also not by the zero-filled tail of the last 64-row k-block)
+            gemm(ctx, dy, x.data, dw, M=cout, N=cin, K=R, a_major=L.MAJOR_MN, b_major=L.MAJOR_MN, a_rows=R,
+                 b_rows=R - (k - 1) * dil, a_ld=cout, b_ld=cin, d_ld=k * cin, nb1=k, a_bs=(0, 0), b_bs=(0, dil * cin), d_bs=(0, cin),
+                 b_shift=(-(k - 1) * dil, 0), store=L.ATOMIC_ADD, split_k=split_k_waves(R, tiles), alg_flops=sum(tap_flops))
             dwh["t"] = dw
             if x.needs_grad:
                 # dgrad: dx[r] = sum_j W_j^T dy[r + (k-1-j) dil]; rows past a sequence's end are the next one's zero padding

@@ -216,6 +216,45 @@ def test_gemm_flat_tcn_layout(precision):
     assert (got[:, :pad] == 0).all(), "padding rows must be written as zeros"
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("geom", [(5, 77, 8, 64, 96, 3, 4, 1), (6, 300, 32, 128, 512, 5, 8, 3), (3, 50, 16, 256, 128, 5, 2, 2)],
+                         ids=["small", "c2like", "wide_in"])
+def test_gemm_wgrad_taps_batched(precision, geom):
+    """Conv weight gradient on the flat padded TCN layout with all taps in ONE launch: tap j = batch entry j, A = dy shared
+    (batch stride 0), B = x at an overlapping batch stride of dil rows under one common shift, D = column block j of dW,
+    split-K with fp32 reduce-add -- against per-tap dy^T shift_j(x) in fp64."""
+    Nn, Ls, pad, cin, cout, taps, dil, split = geom
+    assert pad >= (taps - 1) * dil
+    torch.manual_seed(9)
+    dev = torch.device("cuda")
+    dt = torch.float32 if precision == "fp32" else torch.bfloat16
+    Lp = Ls + pad
+    R = Nn * Lp
+    x = torch.zeros(Nn, Lp, cin)
+    x[:, pad:] = (torch.randn(Nn, Ls, cin) * 0.5).to(dt).float()
+    dy = torch.zeros(Nn, Lp, cout)
+    dy[:, pad:] = (torch.randn(Nn, Ls, cout) * 0.5).to(dt).float()
+    xf, dyf = x.reshape(R, cin).double(), dy.reshape(R, cout).double()
+    ref = torch.zeros(cout, taps * cin, dtype=torch.float64)
+    for j in range(taps):
+        sh = (taps - 1 - j) * dil                      # dW_j = sum_r dy[r]^T x[r - sh]
+        ref[:, j * cin:(j + 1) * cin] = dyf[sh:].t() @ xf[:R - sh] if sh else dyf.t() @ xf
+    init = torch.randn(cout, taps * cin) * 0.1
+    dw = init.clone().to(dev)
+    # NaN rows right behind both operands: the last 64-row k-block must not pick them up (0 * NaN)
+    xbuf = torch.full((R + 64, cin), float("nan"), device=dev, dtype=dt)
+    dybuf = torch.full((R + 64, cout), float("nan"), device=dev, dtype=dt)
+    xbuf[:R], dybuf[:R] = xf.to(dev, dt), dyf.to(dev, dt)
+    xd, dyd = xbuf[:R], dybuf[:R]
+    E.gemm(_ctx(precision), dyd, xd, dw, M=cout, N=cin, K=R, a_major=L.MAJOR_MN, b_major=L.MAJOR_MN, a_rows=R,
+           b_rows=R - (taps - 1) * dil, a_ld=cout, b_ld=cin, d_ld=taps * cin, nb1=taps, a_bs=(0, 0), b_bs=(0, dil * cin), d_bs=(0, cin),
+           b_shift=(-(taps - 1) * dil, 0), store=L.ATOMIC_ADD, split_k=split)
+    torch.cuda.synchronize()
+    want = ref + init.double()
+    tol = 2e-4 if precision == "fp32" else 2e-3       # bf16 operands are exact here (inputs pre-rounded); fp32 accumulation
+    assert (dw.cpu().double() - want).abs().max() < tol * want.abs().max()
+
+
 def test_gemm_heads_geometry():
     """(b, head) batching through two batch dims with non-monotonic strides (Q of shape (B*T, 3E))."""
     torch.manual_seed(3)
