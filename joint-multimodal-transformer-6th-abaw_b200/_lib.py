@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libjmt_b200.so")
+LIB_PATH = os.environ.get("JMT_B200_LIB") or os.path.join(_HERE, "libjmt_b200.so")   # (override: A/B runs of two builds)
 
 F32, BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
