@@ -25,8 +25,6 @@ namespace jmt {
 // epilogue warps per CTA (template parameter kEpi): 8 = two per TMEM lane quarter, 16 = four per quarter (interleaved over the
 // tile's column chunks).  The epilogue is latency-bound (tcgen05.ld -> math -> staging -> TMA store, one chain per warp), so
 // short-K tiles, whose mainloop is shorter than one warp-pair's drain of the accumulator, want the 16-warp kernel.
-constexpr int kMaxEpiWarps = 16;
-constexpr int kShortTileIters = 16;      // tiles with at most this many 64-deep k-blocks use the 16-warp epilogue
 constexpr int kAStageBytes = kBlockM * kBlockK * 2;   // 16 KiB
 constexpr int kMaxStages = 8;
 constexpr int kAccStride = 256;       // TMEM columns per accumulator stage
@@ -150,6 +148,9 @@ struct EpiCtx {
   const float* bias;          // this tile's bias slice in shared memory (zeros when there is none)
   const uint8_t* flags;       // MASK: this thread's sample's keep-flags for the tile's columns (shared memory)
   uint32_t keep;              // 0 when this thread's output row must be written as zeros, else ~0
+#ifdef JMT_EPI_PROF
+  long long* prof;
+#endif
   uint32_t tempty;            // accumulator-stage 'empty' barrier (leader CTA's, cluster address when kCta == 2)
   int m0w, n0, b0, b1, part, parts, lane;   // part / parts: this warp's interleaved share of the tile's column chunks
 };
@@ -157,6 +158,16 @@ struct EpiCtx {
 // One epilogue warp's share of a 128 x block_n accumulator tile: its 32 TMEM lanes (rows) x every other
 // 64-column (bf16 out) / 32-column (fp32 out) chunk -> alpha / bias / activation -> 128B-swizzled staging tile ->
 // TMA store or reduce-add; or per-thread stores when D's geometry is not 16-byte aligned.
+#ifdef JMT_EPI_PROF
+// diagnostic build only (scratch/epi_prof.sh): cycles of epilogue warp 0 of CTA 0 per phase, accumulated in registers
+__device__ unsigned long long g_epi_prof[8];
+#define EPI_T(i) do { const long long t_ = clock64(); e.prof[i] += t_ - tprev; tprev = t_; } while (0)
+#define EPI_T0() long long tprev = clock64()
+#else
+#define EPI_T(i) do { } while (0)
+#define EPI_T0() do { } while (0)
+#endif
+
 template <int kCta>
 __device__ __forceinline__ void epi_release(uint32_t tempty, int lane) {
   tc_fence_before();
@@ -182,16 +193,21 @@ __device__ __forceinline__ bool epi_tile(const TcParams& p, const CUtensorMap* t
         if (e.n0 + c0 >= p.N) break;
         const bool second = c0 + 32 < p.block_n;      // block_n is a multiple of 32
         uint32_t r[32], pk[16];
+        EPI_T0();
         tc_ld32_issue(e.tbase + c0, r);
         tc_wait_ld();
+        EPI_T(0);
         epi_math_bf16<ACT, MASK>(r, e.bias + c0, e.flags + c0, p.colmask_scale, e.keep, p.alpha, p.slope, pk);
         if (second) tc_ld32_issue(e.tbase + c0 + 32, r);
+        EPI_T(1);
         if (lane == 0) bulk_wait_read0();       // previous TMA store has finished reading the staging tile
         __syncwarp();
+        EPI_T(2);
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch)
           st_shared_v4(e.row_smem + (((uint32_t)ch ^ e.sw) << 4), pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
         if (second) tc_wait_ld();
+        EPI_T(3);
         // last chunk of this warp's share: every TMEM read of the tile has landed in registers, hand the accumulator stage
         // back to the MMA issuer before the remaining math / staging / store
         const int c_next = c0 + 64 * e.parts;
@@ -205,6 +221,7 @@ __device__ __forceinline__ bool epi_tile(const TcParams& p, const CUtensorMap* t
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch)
           st_shared_v4(e.row_smem + (((uint32_t)(ch + 4) ^ e.sw) << 4), pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
+        EPI_T(4);
         fence_async_smem();
         __syncwarp();
         if (lane == 0 && warp_rows_valid) {
@@ -212,6 +229,7 @@ __device__ __forceinline__ bool epi_tile(const TcParams& p, const CUtensorMap* t
           else tma_reduce_add_4d(tma_d, e.stage_smem, e.n0 + c0, e.m0w, e.b0, e.b1);
           bulk_commit();
         }
+        EPI_T(5);
       }
     } else {
       for (int c0 = e.part * 32; c0 < p.block_n; c0 += 32 * e.parts) {
@@ -311,7 +329,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();
-  if constexpr (kCta == 2) cluster_sync_all();   // peer barriers are initialised before any remote arrive / complete_tx
+  if constexpr (kCta == 2) cluster_sync_relaxed();   // peer barriers are initialised before any remote arrive / complete_tx
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   // Everything above (barrier init, TMEM allocation, cluster handshake) touched no global memory, so under programmatic
@@ -451,6 +469,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       if (et < 256) bias_ptr[et] = 0.f;
       asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpi) : "memory");
     }
+#ifdef JMT_EPI_PROF
+    long long eprof[6] = {0, 0, 0, 0, 0, 0};
+#endif
     int tile_iter = 0;
     for (int t = first_tile; t < p.total_tiles; t += tile_stride, ++tile_iter) {
       const TileCoord c = decode_tile(p, t, crank);
@@ -500,6 +521,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       // (kMask: channel dropout fused after the activation, TCN -- a separate kernel instantiation so that its extra
       //  register pressure never touches the common kernels)
       ec.tempty = (kCta == 1 ? tempty_bar : tempty_leader) + 8 * acc;
+#ifdef JMT_EPI_PROF
+      ec.prof = eprof;
+#endif
       bool released;
       if (p.act == JMT_ACT_NONE) released = epi_tile<JMT_ACT_NONE, kMask, kCta>(p, &tma_d, ec);
       else if (p.act == JMT_ACT_RELU) released = epi_tile<JMT_ACT_RELU, kMask, kCta>(p, &tma_d, ec);
@@ -507,6 +531,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       if (!released) epi_release<kCta>(ec.tempty, lane);
     }
     if (lane == 0) bulk_wait0();                   // all TMA stores of this warp have completed
+#ifdef JMT_EPI_PROF
+    if (blockIdx.x == 0 && threadIdx.x == 64) for (int i = 0; i < 6; ++i) g_epi_prof[i] = (unsigned long long)eprof[i];
+#endif
     if (p.prof && ew == 0 && lane == 0) {
       unsigned long long* o = p.prof + blockIdx.x * 16;
       o[5] = ep_tfull; o[6] = ep_bar; o[7] = ep_rd; o[8] = clock64() - ep_t0;
@@ -515,7 +542,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
-  if constexpr (kCta == 2) cluster_sync_all();    // no CTA exits (or frees TMEM) while its peer may still read / signal it
+  if constexpr (kCta == 2) cluster_sync_relaxed();    // no CTA exits (or frees TMEM) while its peer may still read / signal it
   if (warp == 1) {
     tc_fence_after();
     if constexpr (kCta == 1)
@@ -549,6 +576,14 @@ extern "C" int jmt_gemm_set_profile_buffer(void* dev_buf) {
   g_prof_buf.store((unsigned long long*)dev_buf);
   return JMT_OK;
 }
+
+#ifdef JMT_EPI_PROF
+extern "C" int jmt_gemm_epi_prof_read(unsigned long long* host8, int reset) {
+  cudaMemcpyFromSymbol(host8, jmt::g_epi_prof, 8 * sizeof(unsigned long long));
+  if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(jmt::g_epi_prof, z, sizeof(z)); }
+  return 0;
+}
+#endif
 
 extern "C" int jmt_gemm_bf16(const jmt_gemm_desc* g, void* stream) {
   int rc = jmt_validate_gemm_desc(g, "jmt_gemm_bf16");
