@@ -280,6 +280,13 @@ def main():
         h2d = sum(t.numel() * t.element_size() for t in host[0])
         for ev in consumed:
             ev.record()
+        # every step's loss is copied to pinned host memory on a third stream as soon as that step is done and is read by
+        # the host one step later, so the next step is already enqueued while the host waits (asynchronous logging; the
+        # loss tensor of a buffer set is only overwritten two steps later)
+        d2h_stream = torch.cuda.Stream()
+        host_loss = torch.zeros(args.steps, dtype=torch.float32).pin_memory()
+        step_done = [torch.cuda.Event(), torch.cuda.Event()]
+        d2h_done = [torch.cuda.Event(), torch.cuda.Event()]
         barrier()
         t0 = time.perf_counter()
         prefetch(0)
@@ -290,7 +297,16 @@ def main():
             torch.cuda.current_stream().wait_event(ready[i % 2])
             l = graphed.replay(i % 2) if graphed is not None else step(*dbuf[i % 2])
             consumed[i % 2].record()
-            lsum += float(l.item())                          # D2H of the step's result (synchronises)
+            step_done[i % 2].record()
+            with torch.cuda.stream(d2h_stream):
+                d2h_stream.wait_event(step_done[i % 2])
+                host_loss[i:i + 1].copy_(l.detach().reshape(1).float(), non_blocking=True)   # D2H of the step's result
+                d2h_done[i % 2].record(d2h_stream)
+            if i >= 1:
+                d2h_done[(i - 1) % 2].synchronize()
+                lsum += float(host_loss[i - 1])
+        d2h_done[(args.steps - 1) % 2].synchronize()
+        lsum += float(host_loss[args.steps - 1])
         barrier()
         dt = time.perf_counter() - t0
         tt = torch.tensor([dt], device=dev, dtype=torch.float64)
