@@ -27,6 +27,7 @@ namespace jmt {
 // short-K tiles, whose mainloop is shorter than one warp-pair's drain of the accumulator, want the 16-warp kernel.
 constexpr int kAStageBytes = kBlockM * kBlockK * 2;   // 16 KiB
 constexpr int kMaxStages = 8;
+constexpr int kWideMinIters = 8;       // k-iterations per tile from which the 256 x 512 pair tile pays (JMT_GEMM_WIDE=<n> overrides)
 constexpr int kAccStride = 256;       // TMEM columns per accumulator stage
 constexpr int kEpiStageBytes = 4096;      // 32 rows x 128 B per epilogue warp
 constexpr int epi_smem_bytes(int epi_warps) { return epi_warps * kEpiStageBytes + 2048; }   // staging tiles + bias tile + keep-flag tile
@@ -58,6 +59,9 @@ struct TcParams {
   float alpha, slope;
   int d_dtype, act, store_mode, vec_ok;
   int epi_warps;      // 8 or 16 (kernel template parameter kEpi)
+  int wide;           // CTA pairs only: 256 x 512 tile = two N=256 MMAs per k-step sharing the A tile, ONE accumulator stage
+                      // (all 512 TMEM columns).  Per 128x256x64 block a CTA stages 24 KB instead of 32 KB: for long-K tiles
+                      // (L2->SM ingest-bound) that outweighs the lost epilogue / mainloop overlap
   int cluster;        // 1, or 2 = CTA pairs issuing cta_group::2 MMAs (each CTA stages half of the B tile)
   int pair_batch;     // cluster 2 only: 0 = the pair covers two consecutive M tiles, 1 = two consecutive batch entries
   int m_pairs;        // number of M tile slots per (n, batch): ceil(m_tiles / 2) when pairing along M, else m_tiles
@@ -397,7 +401,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
               tma_load_4d_2sm(a_dst, &tma_a, fb, c.m0, kb * kBlockK + ash, ab0, ab1);
               tma_load_4d_2sm(a_dst + 8192, &tma_a, fb, c.m0 + 64, kb * kBlockK + ash, ab0, ab1);
             }
-            if (p.b_major == JMT_MAJOR_K) {
+            if (p.wide) {          // two 128-column pieces: this CTA's share of the B operand of each of the two MMAs
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const int n_h = c.n0 + h * 256 + crank * 128;
+                if (p.b_major == JMT_MAJOR_K) tma_load_4d_2sm(b_dst + h * 16384, &tma_b, fb, tap * p.K + kb * kBlockK, n_h, bb0, bb1);
+                else tma_load_5d_2sm(b_dst + h * 16384, &tma_b, fb, 0, kb * kBlockK + bsh, n_h >> 6, bb0, bb1);
+              }
+            } else if (p.b_major == JMT_MAJOR_K) {
               tma_load_4d_2sm(b_dst, &tma_b, fb, tap * p.K + kb * kBlockK, c.n0 + n_off, bb0, bb1);
             } else if (p.b_mn5) {
               tma_load_5d_2sm(b_dst, &tma_b, fb, 0, kb * kBlockK + bsh, (c.n0 + n_off) >> 6, bb0, bb1);
@@ -428,8 +439,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       const uint32_t b_kstep = p.b_major == JMT_MAJOR_K ? (kUmmaK * 2) >> 4 : (kUmmaK * 128) >> 4;
       for (int t = first_tile; t < p.total_tiles; t += tile_stride, ++tile_iter) {
         const TileCoord c = decode_tile(p, t, crank);
-        const int acc = tile_iter & 1;
-        const uint32_t acc_phase = (tile_iter >> 1) & 1;
+        const int acc = p.wide ? 0 : (tile_iter & 1);
+        const uint32_t acc_phase = (p.wide ? tile_iter : (tile_iter >> 1)) & 1;
         const long long tw0 = p.prof ? clock64() : 0;
         mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1);
         if (p.prof) mw_tempty += clock64() - tw0;
@@ -443,9 +454,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           const uint64_t a_desc = make_smem_desc(sA + stage * kAStageBytes, a_lbo, 1024);
           const uint64_t b_desc = make_smem_desc(sB + stage * p.b_stage_bytes, b_lbo, 1024);
 #pragma unroll
-          for (int k = 0; k < kBlockK / kUmmaK; ++k)
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
             tc_mma<kCta>(d_tmem, a_desc + (uint64_t)(k * a_kstep), b_desc + (uint64_t)(k * b_kstep), p.idesc,
                          (it > c.it0 || k > 0) ? 1u : 0u);
+            if (p.wide)      // columns 256..511 of the tile: same A, second B piece (16 KB further), TMEM columns 256..511
+              tc_mma<kCta>(d_tmem + 256, a_desc + (uint64_t)(k * a_kstep), b_desc + (uint64_t)(1024 + k * b_kstep), p.idesc,
+                           (it > c.it0 || k > 0) ? 1u : 0u);
+          }
           tc_commit<kCta>(empty_bar + 8 * stage);  // frees the smem slot (in both CTAs) once these MMAs retire
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
@@ -466,7 +481,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     const uint32_t tempty_leader = kCta == 2 ? mapa_rank(tempty_bar, 0) : tempty_bar;
     long long ep_tfull = 0, ep_bar = 0, ep_rd = 0; const long long ep_t0 = p.prof ? clock64() : 0;
     if (p.bias == nullptr && !kMask) {             // no bias: one zero fill for the whole kernel
-      if (et < 256) bias_ptr[et] = 0.f;
+      for (int e2 = et; e2 < 512; e2 += 32 * kEpi) bias_ptr[e2] = 0.f;
       asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpi) : "memory");
     }
 #ifdef JMT_EPI_PROF
@@ -476,18 +491,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     for (int t = first_tile; t < p.total_tiles; t += tile_stride, ++tile_iter) {
       const TileCoord c = decode_tile(p, t, crank);
       const int split = c.split;
-      const int acc = tile_iter & 1;
-      const uint32_t acc_phase = (tile_iter >> 1) & 1;
+      const int acc = p.wide ? 0 : (tile_iter & 1);
+      const uint32_t acc_phase = (p.wide ? tile_iter : (tile_iter >> 1)) & 1;
       // stage this tile's bias slice in shared memory (overlaps the mainloop); named barrier 1 = epilogue warps
       const long long tb0 = p.prof ? clock64() : 0;
       // kMask == false: the bias tile is double-buffered by tile parity (the keep-flag area is free), so ONE barrier per tile
       // suffices -- buffer (i & 1) was last read for tile i - 2, and every warp finished those reads before it arrived at the
       // barrier of tile i - 1, which this writer has passed
-      float* bias_tile = bias_ptr + ((!kMask && p.bias != nullptr) ? (tile_iter & 1) * 256 : 0);
+      // (a wide tile's 512 bias values fill both halves: single buffer, two barriers, like kMask)
+      const bool bias_dbuf = !kMask && !p.wide;
+      float* bias_tile = bias_ptr + ((bias_dbuf && p.bias != nullptr) ? (tile_iter & 1) * 256 : 0);
       if (p.bias != nullptr || kMask) {
         const bool add_bias = p.bias != nullptr && split == 0;
-        if constexpr (kMask) asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpi) : "memory");     // previous tile's readers are done
-        if (et < p.block_n) {
+        if (!bias_dbuf) asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpi) : "memory");     // previous tile's readers are done
+        if (p.wide) {
+          for (int e2 = et; e2 < 512; e2 += 32 * kEpi) bias_tile[e2] = (add_bias && c.n0 + e2 < p.N) ? __ldg(p.bias + c.n0 + e2) : 0.f;
+        } else if (et < p.block_n) {
           const bool in_n = c.n0 + et < p.N;
           bias_tile[et] = (add_bias && in_n) ? __ldg(p.bias + c.n0 + et) : 0.f;
           if constexpr (kMask) {
@@ -615,6 +634,14 @@ extern "C" int jmt_gemm_bf16(const jmt_gemm_desc* g, void* stream) {
   const bool long_enough = p.iters_total / p.split_k >= 4;
   p.cluster = (cl_enabled && long_enough && (pair_m_ok || pair_b_ok)) ? 2 : 1;
   p.pair_batch = (p.cluster == 2 && !pair_m_ok) ? 1 : 0;
+  // wide tiles (256 x 512 per pair) for long-K GEMMs whose N is a multiple of 512; JMT_GEMM_WIDE=0 disables
+  {
+    static const int wide_env = []() { const char* e = getenv("JMT_GEMM_WIDE"); return e ? atoi(e) : 1; }();
+    const int min_iters = wide_env > 1 ? wide_env : kWideMinIters;
+    p.wide = (wide_env != 0 && p.cluster == 2 && !p.pair_batch && g->colmask == nullptr && g->N % 512 == 0 &&
+              p.iters_total / p.split_k >= min_iters) ? 1 : 0;
+    if (p.wide) { p.block_n = 512; p.n_tiles = g->N / 512; }
+  }
   p.m_pairs = (p.cluster == 2 && !p.pair_batch) ? (p.m_tiles + 1) / 2 : p.m_tiles;
   p.batch_slots = p.pair_batch ? p.batch_tiles / 2 : p.batch_tiles;
   const int64_t total = (int64_t)p.m_pairs * p.n_tiles * p.batch_slots * p.split_k;
@@ -628,11 +655,12 @@ extern "C" int jmt_gemm_bf16(const jmt_gemm_desc* g, void* stream) {
   p.b_shift0 = g->b_shift0; p.b_shift_step = g->b_shift_step;
   JMT_REQUIRE(!(g->ntaps > 1 && g->b_major == JMT_MAJOR_K && g->K % 8 != 0), "jmt_gemm_bf16: taps need K %% 8 == 0");
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)g->a_major << 15) | ((uint32_t)g->b_major << 16) |
-            ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)((kBlockM * p.cluster) >> 4) << 24);
+            ((uint32_t)((p.wide ? 256 : p.block_n) >> 3) << 17) | ((uint32_t)((kBlockM * p.cluster) >> 4) << 24);
   // per CTA: the whole B tile, or its half of it under cta_group::2
-  const int b_cols_cta = p.block_n / p.cluster;
+  // (wide: two 128-column pieces per CTA, one per MMA, 16 KB each)
+  const int b_cols_cta = p.wide ? 128 : p.block_n / p.cluster;
   p.b_chunks_cta = (b_cols_cta + 63) / 64;
-  p.b_stage_bytes = g->b_major == JMT_MAJOR_K ? b_cols_cta * 128 : p.b_chunks_cta * 8192;
+  p.b_stage_bytes = (g->b_major == JMT_MAJOR_K ? b_cols_cta * 128 : p.b_chunks_cta * 8192) * (p.wide ? 2 : 1);
   p.b_tx_bytes = p.b_stage_bytes;
   const int stage_bytes = kAStageBytes + p.b_stage_bytes;
   // 16 epilogue warps when a tile's mainloop is short (the accumulator drain, not the MMAs, bounds those tiles); 8 otherwise

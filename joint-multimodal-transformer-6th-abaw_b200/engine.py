@@ -318,26 +318,29 @@ def copy2d(ctx: Ctx, src: torch.Tensor, dst: torch.Tensor):
                                rows, cols, _stream()), "jmt_copy2d")
 
 
-def split_k_for(red: int, tiles: int) -> int:
-    """Split factor for weight-gradient GEMMs (`red` reduction rows, `tiles` output tiles): about one
-    wave of 148 CTAs, each keeping at least 8 k-blocks of work."""
-    kblocks = max(1, (red + 63) // 64)
-    want = max(1, 148 // max(1, tiles))
-    return max(1, min(want, kblocks // 8)) if kblocks >= 16 else 1
-
-
 def split_k_waves(red: int, tiles: int, units: int = 74) -> int:
-    """Split factor for a weight-gradient GEMM with many output tiles (`tiles` CTA-pair tiles, `units` CTA pairs on the chip):
-    the smallest-traffic split whose tiles*split fills whole waves best (every extra split costs one more fp32 reduce-add
-    pass over the output), keeping at least 8 k-blocks per split."""
+    """Split factor for a weight-gradient GEMM (`tiles` output tiles, `units` CTAs / CTA pairs on the chip): the split whose
+    tiles*split fills whole waves best, lightly penalised per split (every split is one more fp32 reduce-add pass over the
+    output), keeping at least 8 k-blocks per split."""
     kblocks = max(1, (red + 63) // 64)
     best, best_score = 1, -1.0
-    for sk in range(1, max(1, min(32, kblocks // 8)) + 1):
+    for sk in range(1, max(1, min(64, kblocks // 8)) + 1):
         n = tiles * sk
         score = n / (units * ((n + units - 1) // units)) - 0.004 * sk
         if score > best_score:
             best, best_score = sk, score
     return best
+
+
+def wgrad_split(red: int, m_out: int, n_out: int, batch: int = 1) -> int:
+    """split_k for dW (m_out x n_out, `batch` independent outputs) = dy^T x over `red` rows, mirroring jmt_gemm_bf16's tiling
+    (csrc/gemm_tc.cu): CTA pairs own 256 x 256 tiles, or 256 x 512 "wide" tiles when n_out is a multiple of 512; an odd number
+    (< 9) of 128-row tiles runs unpaired 128 x 256 tiles on all 148 CTAs."""
+    m_tiles = (m_out + 127) // 128
+    if m_tiles >= 2 and (m_tiles % 2 == 0 or m_tiles >= 9):
+        n_tiles = n_out // 512 if n_out % 512 == 0 else (n_out + 255) // 256
+        return split_k_waves(red, ((m_tiles + 1) // 2) * n_tiles * batch, 74)
+    return split_k_waves(red, m_tiles * ((n_out + 255) // 256) * batch, 148)
 
 
 # --------------------------------------------------------------------------- differentiable ops
@@ -445,9 +448,8 @@ def linear(ctx: Ctx, x: Var, wname: str, bname: Optional[str], act=L.ACT_NONE, s
             if dWf.dim() == 3:
                 dWf = dWf.view(dWf.shape[0], dWf.shape[1])
             dW = dWf[r0:r1, c0:c1]
-            tiles = ((N + 127) // 128) * ((K + 255) // 256)
             gemm(ctx, dy, x.data, dW, M=N, N=K, K=M, a_major=L.MAJOR_MN, b_major=L.MAJOR_MN,
-                 store=L.ATOMIC_ADD, split_k=split_k_for(M, tiles))
+                 store=L.ATOMIC_ADD, split_k=wgrad_split(M, N, K))
             if x.needs_grad:
                 dx, mode = ctx.grad_target(x)
                 gemm(ctx, dy, Wv, dx, M=M, N=K, K=N, b_major=L.MAJOR_MN, store=mode)
@@ -968,12 +970,11 @@ def causal_conv(ctx: Ctx, x: Var, prefix: str, N: int, Ls: int, cin: int, cout: 
             # rows the common shift zero-fills but tap j would have read (x rows 0 .. j*dil-1) are padding rows of the first
             # sequence, i.e. zeros (pad >= (k-1)*dil is asserted above).
             dw = ctx.zeros((cout, k * cin), torch.float32)
-            tiles = ((cout + 255) // 256) * ((cin + 255) // 256) * k
             # (B's row extent stops (k-1)*dil short of R: with tap j's base moved down by j*dil rows nothing past row R-1 of
             # x is ever addressed, also not by the zero-filled tail of the last 64-row k-block)
             gemm(ctx, dy, x.data, dw, M=cout, N=cin, K=R, a_major=L.MAJOR_MN, b_major=L.MAJOR_MN, a_rows=R,
                  b_rows=R - (k - 1) * dil, a_ld=cout, b_ld=cin, d_ld=k * cin, nb1=k, a_bs=(0, 0), b_bs=(0, dil * cin), d_bs=(0, cin),
-                 b_shift=(-(k - 1) * dil, 0), store=L.ATOMIC_ADD, split_k=split_k_waves(R, tiles), alg_flops=sum(tap_flops))
+                 b_shift=(-(k - 1) * dil, 0), store=L.ATOMIC_ADD, split_k=wgrad_split(R, cout, cin, k), alg_flops=sum(tap_flops))
             dwh["t"] = dw
             if x.needs_grad:
                 # dgrad: dx[r] = sum_j W_j^T dy[r + (k-1-j) dil]; rows past a sequence's end are the next one's zero padding

@@ -89,6 +89,12 @@ GEMM_CASES = [
     ("conv_fwd_taps_nb4", 40, 96, 64, 0, 0, 4, 5, (-8, 2), (0, 0), False, 1, 2, True, "act", 0),
     ("conv_dgrad_taps_nb6", 300, 64, 96, 0, 0, 6, 5, (8, -2), (0, 0), False, 1, 0, False, "act", 1),
     ("pair_persistent", 128 * 40, 512, 128, 0, 0, 8, 1, (0, 0), (0, 0), False, 1, 1, True, "act", 0),
+    # wide pair tiles (256 x 512, two MMAs per k-step, one accumulator stage): >= 24 k-iterations per tile and N % 512 == 0
+    ("wide_tn_relu", 1024, 1024, 1600, 0, 0, 1, 1, (0, 0), (0, 0), False, 1, 1, True, "act", 0),
+    ("wide_tn_ghost_f32_acc", 1100, 512, 1544, 0, 0, 2, 1, (0, 0), (0, 0), False, 1, 0, True, "f32", 1),
+    ("wide_wgrad_mnmn", 512, 512, 3200, 1, 1, 1, 1, (0, 0), (0, 0), False, 2, 0, False, "f32", 2),
+    ("wide_conv_dgrad_taps", 1100, 512, 320, 0, 0, 1, 5, (8, -2), (0, 0), False, 1, 0, False, "act", 0),
+    ("wide_nn_bmn", 512, 512, 1600, 0, 1, 2, 1, (0, 0), (0, 0), False, 1, 0, False, "act", 0),
 ]
 
 
