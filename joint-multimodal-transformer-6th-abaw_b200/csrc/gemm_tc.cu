@@ -30,7 +30,8 @@ constexpr int kMaxStages = 8;
 constexpr int kWideMinIters = 8;       // k-iterations per tile from which the 256 x 512 pair tile pays (JMT_GEMM_WIDE=<n> overrides)
 constexpr int kAccStride = 256;       // TMEM columns per accumulator stage
 constexpr int kEpiStageBytes = 4096;      // 32 rows x 128 B per epilogue warp
-constexpr int epi_smem_bytes(int epi_warps) { return epi_warps * kEpiStageBytes + 2048; }   // staging tiles + bias tile + keep-flag tile
+constexpr int kBiasFlagBytes = 2048 + 256;   // 512-float bias tile (two 256-float buffers for narrow tiles) + 2 x 16 keep-flag words
+constexpr int epi_smem_bytes(int epi_warps) { return epi_warps * kEpiStageBytes + kBiasFlagBytes; }
 
 struct TcParams {
   int M, N, K, block_n;
@@ -81,17 +82,17 @@ __device__ __forceinline__ float act_t(float x, float slope) {
 // 32 accumulator columns -> act(alpha * acc + bias) [* column scale] -> bf16 -> this thread's staging row
 // (16-byte pieces `piece0 .. piece0+3` of the 128-byte row, 128B-swizzled).  Branch-free: the activation is a template
 // parameter so the compiler interleaves the independent FFMA / FMNMX / F2FP chains; nothing but r[] stays live.
-// keep-flags (one byte per column) of this thread's sample live after the 256-float bias tile: x *= flag ? scale : 0
-__device__ __forceinline__ void apply_flags4(const uint8_t* fl, float mscale, float& x0, float& x1, float& x2, float& x3) {
-  const uint32_t f4 = *reinterpret_cast<const uint32_t*>(fl);
-  x0 = (f4 & 0x000000FFu) ? x0 * mscale : 0.f;
-  x1 = (f4 & 0x0000FF00u) ? x1 * mscale : 0.f;
-  x2 = (f4 & 0x00FF0000u) ? x2 * mscale : 0.f;
-  x3 = (f4 & 0xFF000000u) ? x3 * mscale : 0.f;
+// keep-flags of this thread's sample: one BIT per column, one 32-bit word per 32-column group (behind the 512-float bias tile):
+// x *= flag ? scale : 0
+__device__ __forceinline__ void apply_flags4(uint32_t fbits, int j, float mscale, float& x0, float& x1, float& x2, float& x3) {
+  x0 = (fbits >> j) & 1u ? x0 * mscale : 0.f;
+  x1 = (fbits >> (j + 1)) & 1u ? x1 * mscale : 0.f;
+  x2 = (fbits >> (j + 2)) & 1u ? x2 * mscale : 0.f;
+  x3 = (fbits >> (j + 3)) & 1u ? x3 * mscale : 0.f;
 }
 
 template <int ACT, bool MASK>
-__device__ __forceinline__ void epi_math_bf16(const uint32_t (&r)[32], const float* bias, const uint8_t* flags, float mscale,
+__device__ __forceinline__ void epi_math_bf16(const uint32_t (&r)[32], const float* bias, uint32_t fbits, float mscale,
                                               uint32_t keep, float alpha, float slope, uint32_t* pk /*16 packed words*/) {
 #pragma unroll
   for (int j = 0; j < 32; j += 4) {
@@ -100,14 +101,14 @@ __device__ __forceinline__ void epi_math_bf16(const uint32_t (&r)[32], const flo
     float x1 = act_t<ACT>(fmaf(alpha, __uint_as_float(r[j + 1]), bv.y), slope);
     float x2 = act_t<ACT>(fmaf(alpha, __uint_as_float(r[j + 2]), bv.z), slope);
     float x3 = act_t<ACT>(fmaf(alpha, __uint_as_float(r[j + 3]), bv.w), slope);
-    if constexpr (MASK) apply_flags4(flags + j, mscale, x0, x1, x2, x3);
+    if constexpr (MASK) apply_flags4(fbits, j, mscale, x0, x1, x2, x3);
     // keep = 0 for rows that must read back as zeros (padding rows of the flat TCN layout), else all ones
     pk[j / 2] = pack_bf16(x0, x1) & keep;
     pk[j / 2 + 1] = pack_bf16(x2, x3) & keep;
   }
 }
 template <int ACT, bool MASK>
-__device__ __forceinline__ void epi_math_f32(uint32_t (&r)[32], const float* bias, const uint8_t* flags, float mscale, uint32_t keep,
+__device__ __forceinline__ void epi_math_f32(uint32_t (&r)[32], const float* bias, uint32_t fbits, float mscale, uint32_t keep,
                                              float alpha, float slope) {
 #pragma unroll
   for (int j = 0; j < 32; j += 4) {
@@ -116,7 +117,7 @@ __device__ __forceinline__ void epi_math_f32(uint32_t (&r)[32], const float* bia
     float x1 = act_t<ACT>(fmaf(alpha, __uint_as_float(r[j + 1]), bv.y), slope);
     float x2 = act_t<ACT>(fmaf(alpha, __uint_as_float(r[j + 2]), bv.z), slope);
     float x3 = act_t<ACT>(fmaf(alpha, __uint_as_float(r[j + 3]), bv.w), slope);
-    if constexpr (MASK) apply_flags4(flags + j, mscale, x0, x1, x2, x3);
+    if constexpr (MASK) apply_flags4(fbits, j, mscale, x0, x1, x2, x3);
     r[j] = __float_as_uint(x0) & keep; r[j + 1] = __float_as_uint(x1) & keep; r[j + 2] = __float_as_uint(x2) & keep; r[j + 3] = __float_as_uint(x3) & keep;
   }
 }
@@ -150,7 +151,7 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int t, int c
 struct EpiCtx {
   uint32_t tbase, stage_smem, row_smem, sw;
   const float* bias;          // this tile's bias slice in shared memory (zeros when there is none)
-  const uint8_t* flags;       // MASK: this thread's sample's keep-flags for the tile's columns (shared memory)
+  const uint32_t* fwords;     // MASK: this thread's sample's keep-flag words (one bit per column of the tile, shared memory)
   uint32_t keep;              // 0 when this thread's output row must be written as zeros, else ~0
 #ifdef JMT_EPI_PROF
   long long* prof;
@@ -201,7 +202,7 @@ __device__ __forceinline__ bool epi_tile(const TcParams& p, const CUtensorMap* t
         tc_ld32_issue(e.tbase + c0, r);
         tc_wait_ld();
         EPI_T(0);
-        epi_math_bf16<ACT, MASK>(r, e.bias + c0, e.flags + c0, p.colmask_scale, e.keep, p.alpha, p.slope, pk);
+        epi_math_bf16<ACT, MASK>(r, e.bias + c0, MASK ? e.fwords[c0 >> 5] : 0u, p.colmask_scale, e.keep, p.alpha, p.slope, pk);
         if (second) tc_ld32_issue(e.tbase + c0 + 32, r);
         EPI_T(1);
         if (lane == 0) bulk_wait_read0();       // previous TMA store has finished reading the staging tile
@@ -217,7 +218,7 @@ __device__ __forceinline__ bool epi_tile(const TcParams& p, const CUtensorMap* t
         const int c_next = c0 + 64 * e.parts;
         if (c_next >= p.block_n || e.n0 + c_next >= p.N) { epi_release<kCta>(e.tempty, lane); released = true; }
         if (second) {
-          epi_math_bf16<ACT, MASK>(r, e.bias + c0 + 32, e.flags + c0 + 32, p.colmask_scale, e.keep, p.alpha, p.slope, pk);
+          epi_math_bf16<ACT, MASK>(r, e.bias + c0 + 32, MASK ? e.fwords[(c0 >> 5) + 1] : 0u, p.colmask_scale, e.keep, p.alpha, p.slope, pk);
         } else {
 #pragma unroll
           for (int j = 0; j < 16; ++j) pk[j] = 0u;
@@ -242,7 +243,7 @@ __device__ __forceinline__ bool epi_tile(const TcParams& p, const CUtensorMap* t
         tc_ld32(e.tbase + c0, r);
         const int c_next = c0 + 32 * e.parts;
         if (c_next >= p.block_n || e.n0 + c_next >= p.N) { epi_release<kCta>(e.tempty, lane); released = true; }
-        epi_math_f32<ACT, MASK>(r, e.bias + c0, e.flags + c0, p.colmask_scale, e.keep, p.alpha, p.slope);
+        epi_math_f32<ACT, MASK>(r, e.bias + c0, MASK ? e.fwords[c0 >> 5] : 0u, p.colmask_scale, e.keep, p.alpha, p.slope);
         if (lane == 0) bulk_wait_read0();
         __syncwarp();
 #pragma unroll
@@ -271,7 +272,7 @@ __device__ __forceinline__ bool epi_tile(const TcParams& p, const CUtensorMap* t
       for (int j = 0; j < 32; ++j) {
         if (n + j >= p.N) break;
         float v = act_t<ACT>(fmaf(p.alpha, __uint_as_float(r[j]), e.bias[c0 + j]), p.slope);
-        if constexpr (MASK) v = e.flags[c0 + j] ? v * p.colmask_scale : 0.f;
+        if constexpr (MASK) v = (e.fwords[c0 >> 5] >> j) & 1u ? v * p.colmask_scale : 0.f;
         if (e.keep == 0u) v = 0.f;
         const int64_t idx = row_off + n + j;
         if (p.d_dtype == JMT_F32) {
@@ -302,7 +303,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   const uint32_t sB = sA + p.stages * kAStageBytes;
   const uint32_t sD = sB + p.stages * p.b_stage_bytes;       // epilogue warps x 4 KiB staging (1024-aligned)
   const uint32_t sBias = sD + kEpi * kEpiStageBytes;         // 256 floats: this tile's bias slice
-  const uint32_t bars = sBias + 2048;                        // 8-byte aligned (bias tile, then 256 floats of column scales)
+  const uint32_t bars = sBias + kBiasFlagBytes;              // 8-byte aligned (behind the bias tile and the keep-flag words)
   const uint32_t full_bar = bars, empty_bar = bars + 8 * kMaxStages;
   const uint32_t tfull_bar = bars + 16 * kMaxStages, tempty_bar = tfull_bar + 16;
   const uint32_t tmem_slot = tempty_bar + 16;
@@ -498,23 +499,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       // kMask == false: the bias tile is double-buffered by tile parity (the keep-flag area is free), so ONE barrier per tile
       // suffices -- buffer (i & 1) was last read for tile i - 2, and every warp finished those reads before it arrived at the
       // barrier of tile i - 1, which this writer has passed
-      // (a wide tile's 512 bias values fill both halves: single buffer, two barriers, like kMask)
+      // (a wide tile's 512 bias values fill both buffers: single buffer, two barriers, like kMask)
       const bool bias_dbuf = !kMask && !p.wide;
       float* bias_tile = bias_ptr + ((bias_dbuf && p.bias != nullptr) ? (tile_iter & 1) * 256 : 0);
       if (p.bias != nullptr || kMask) {
         const bool add_bias = p.bias != nullptr && split == 0;
         if (!bias_dbuf) asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpi) : "memory");     // previous tile's readers are done
-        if (p.wide) {
-          for (int e2 = et; e2 < 512; e2 += 32 * kEpi) bias_tile[e2] = (add_bias && c.n0 + e2 < p.N) ? __ldg(p.bias + c.n0 + e2) : 0.f;
-        } else if (et < p.block_n) {
-          const bool in_n = c.n0 + et < p.N;
-          bias_tile[et] = (add_bias && in_n) ? __ldg(p.bias + c.n0 + et) : 0.f;
+        // every epilogue thread takes columns et, et + 32 * kEpi, ... of the tile (warp-uniform trip count: block_n % 32 == 0)
+        for (int e2 = et; e2 < p.block_n; e2 += 32 * kEpi) {
+          const bool in_n = c.n0 + e2 < p.N;
+          bias_tile[e2] = (add_bias && in_n) ? __ldg(p.bias + c.n0 + e2) : 0.f;
           if constexpr (kMask) {
-            // keep-flags of the (up to two) samples this tile's rows belong to: sample = batch, or row / period (flat layout)
-            uint8_t* fl = reinterpret_cast<uint8_t*>(bias_ptr + 256);
+            // keep-flags of the (up to two) samples this tile's rows belong to: sample = batch, or row / period (flat layout);
+            // one ballot per 32 columns and sample
+            uint32_t* fw = reinterpret_cast<uint32_t*>(bias_ptr + 512);
             const int s0 = p.colmask_period ? (int)p.fd_cmask.div((uint32_t)c.m0) : c.batch;
-            fl[et] = (in_n && p.colmask[(int64_t)s0 * p.N + c.n0 + et]) ? 1 : 0;
-            fl[256 + et] = (in_n && p.colmask_period && s0 + 1 < p.colmask_samples && p.colmask[(int64_t)(s0 + 1) * p.N + c.n0 + et]) ? 1 : 0;
+            const uint32_t w0 = __ballot_sync(0xffffffffu, in_n && p.colmask[(int64_t)s0 * p.N + c.n0 + e2]);
+            const uint32_t w1 = __ballot_sync(0xffffffffu, in_n && p.colmask_period && s0 + 1 < p.colmask_samples &&
+                                                            p.colmask[(int64_t)(s0 + 1) * p.N + c.n0 + e2]);
+            if (lane == 0) { fw[e2 >> 5] = w0; fw[16 + (e2 >> 5)] = w1; }
           }
         }
         asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpi) : "memory");
@@ -532,9 +535,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         const uint32_t m = (uint32_t)(c.m0 + q * 32 + lane);
         ec.keep = ~0u;
         if (p.zrow_period) { uint32_t qq, rr; p.fd_zrow.divmod(m, qq, rr); ec.keep = rr < (uint32_t)p.zrow_count ? 0u : ~0u; }
-        const uint8_t* fl = reinterpret_cast<const uint8_t*>(bias_ptr + 256);
-        if (kMask && p.colmask_period) fl += (p.fd_cmask.div(m) != p.fd_cmask.div((uint32_t)c.m0)) ? 256 : 0;
-        ec.flags = fl;
+        const uint32_t* fw = reinterpret_cast<const uint32_t*>(bias_ptr + 512);
+        if (kMask && p.colmask_period) fw += (p.fd_cmask.div(m) != p.fd_cmask.div((uint32_t)c.m0)) ? 16 : 0;
+        ec.fwords = fw;
       }
       ec.m0w = c.m0 + q * 32; ec.n0 = c.n0; ec.b0 = (int)b0u; ec.b1 = (int)b1u; ec.part = part; ec.parts = kEpi / 4; ec.lane = lane;
       // (kMask: channel dropout fused after the activation, TCN -- a separate kernel instantiation so that its extra
@@ -638,7 +641,7 @@ extern "C" int jmt_gemm_bf16(const jmt_gemm_desc* g, void* stream) {
   {
     static const int wide_env = []() { const char* e = getenv("JMT_GEMM_WIDE"); return e ? atoi(e) : 1; }();
     const int min_iters = wide_env > 1 ? wide_env : kWideMinIters;
-    p.wide = (wide_env != 0 && p.cluster == 2 && !p.pair_batch && g->colmask == nullptr && g->N % 512 == 0 &&
+    p.wide = (wide_env != 0 && p.cluster == 2 && !p.pair_batch && g->N % 512 == 0 &&
               p.iters_total / p.split_k >= min_iters) ? 1 : 0;
     if (p.wide) { p.block_n = 512; p.n_tiles = g->N / 512; }
   }

@@ -187,13 +187,14 @@ def test_gemm_colmask(precision, nb):
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
-def test_gemm_flat_tcn_layout(precision):
+@pytest.mark.parametrize("geom", [(5, 77, 8, 64, 96, 3, 4), (6, 77, 8, 192, 512, 3, 4)], ids=["narrow", "wide512"])
+def test_gemm_flat_tcn_layout(precision, geom):
     """Flat padded TCN layout: one GEMM over N*(pad+L) rows with row shifts, padding rows written as zeros
     (zero_row_period) and the channel-dropout mask row taken from m / period -- against per-sequence causal convs."""
     torch.manual_seed(5)
     dev = torch.device("cuda")
     dt = torch.float32 if precision == "fp32" else torch.bfloat16
-    Nn, Ls, pad, cin, cout, taps, dil = 5, 77, 8, 64, 96, 3, 4
+    Nn, Ls, pad, cin, cout, taps, dil = geom      # wide512: 256 x 512 pair tiles with the channel-dropout keep-flag words
     Lp = Ls + pad
     x = torch.zeros(Nn, Lp, cin)
     x[:, pad:] = (torch.randn(Nn, Ls, cin) * 0.5).to(dt).float()
