@@ -2,10 +2,10 @@
 //
 //   warp 0 (1 elected thread) : TMA producer   -- cp.async.bulk.tensor.4d -> 128B-swizzled smem ring
 //   warp 1 (1 elected thread) : MMA issuer     -- tcgen05.mma.cta_group::{1,2}.kind::f16, fp32 accum in TMEM
-//   warps 2..9                : epilogue       -- tcgen05.ld 32x32b -> alpha/bias/activation -> global
+//   warps 2..9                : epilogue       -- tcgen05.ld 32x32b -> alpha/bias/activation -> swizzled smem -> TMA store
 //
 // Two TMEM accumulator stages (2 x 256 columns) let the epilogue of tile i overlap the mainloop of
-// tile i+1.  One descriptor (jmt_gemm_desc) covers every dense contraction of the JMT path: Linear
+// tile i+1; an epilogue warp hands its stage back as soon as its last tcgen05.ld of the tile has landed.  One descriptor (jmt_gemm_desc) covers every dense contraction of the JMT path: Linear
 // fwd/dgrad/wgrad, QK^T / PV and their gradients (batched over (b, head) through 4-D tensor maps,
 // K- or MN-major operands selected in the UMMA instruction descriptor) and the dilated causal
 // Conv1d of the TCN as an implicit GEMM (taps = extra K blocks with a shifted TMA row coordinate;
@@ -16,6 +16,9 @@
 // the batch) and stages only HALF of the B tile -- the pair's tensor cores read both halves.  That cuts
 // the L2->SMEM operand traffic per FLOP by a third (48 KB -> 32 KB per 128x256x64 block), which is the
 // measured limit of the 1-CTA kernel (LTS ~12 TB/s => 1.05 PFLOP/s).
+// Wide pair tiles (TcParams::wide, N % 512 == 0, >= 8 k-iterations): the pair computes 256 x 512 with TWO N=256 MMAs per k-step
+// that share the A tile (TMEM columns 0-255 and 256-511, i.e. a single accumulator stage): 24 KB per 128x256x64 block and CTA.
+// The kernel is bound by what an SM can ingest from L2 (~44 B/clk), so bytes per FLOP decide: K=3072 linear 1150 -> 1437 TFLOP/s.
 #include "tc_common.cuh"
 
 int jmt_validate_gemm_desc(const jmt_gemm_desc* g, const char* who);
