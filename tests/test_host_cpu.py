@@ -188,3 +188,24 @@ def test_feature_shard_roundtrip(tmp_path):
     assert torch.equal(got_a, torch.from_numpy(aud).to(torch.bfloat16))
     assert np.array_equal(np.array(s.labels_v), lv) and np.array_equal(np.array(s.labels_a), la)
     assert os.path.getsize(p) == F.HEADER_BYTES + W * 32 * T * 2 + W * T * 24 * 2 + 2 * W * T * 4
+
+
+def test_wgrad_split_fills_whole_waves():
+    """engine.wgrad_split mirrors the tiling of jmt_gemm_bf16 (CTA pairs, wide 256x512 tiles when N % 512 == 0): the chosen
+    split keeps >= 8 k-blocks per slice and leaves at most ~6 % of the last wave idle for the shapes of the C2 step."""
+    from jmt_b200 import engine as E
+    for red, m_out, n_out, batch in [(76800, 512, 512, 1), (76800, 1024, 512, 1), (76800, 512, 1024, 1), (76800, 1536, 512, 1),
+                                     (76800, 1024, 3072, 1), (84992, 512, 512, 5), (84992, 512, 1024, 5), (76800, 128, 1024, 1)]:
+        sk = E.wgrad_split(red, m_out, n_out, batch)
+        kblocks = (red + 63) // 64
+        assert 1 <= sk <= kblocks // 8
+        m_tiles = (m_out + 127) // 128
+        paired = m_tiles >= 2 and (m_tiles % 2 == 0 or m_tiles >= 9)
+        if paired:
+            tiles, units = ((m_tiles + 1) // 2) * (n_out // 512 if n_out % 512 == 0 else (n_out + 255) // 256) * batch, 74
+        else:
+            tiles, units = m_tiles * ((n_out + 255) // 256) * batch, 148
+        n = tiles * sk
+        assert n / (units * ((n + units - 1) // units)) >= 0.94, (red, m_out, n_out, batch, sk)
+    # short reductions are never split
+    assert E.wgrad_split(500, 512, 512) == 1 and E.split_k_waves(64 * 15, 4) == 1
