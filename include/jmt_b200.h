@@ -64,7 +64,9 @@ int64_t jmt_launch_count(void);
  *
  * Operand addressing (elements):  K-major operand X: X(r, k) = x[batch_off + r*ld + k]
  *                                 MN-major operand X: X(r, k) = x[batch_off + k*ld + r]
- *   batch b = b1*nb0 + b0, batch_off = b0*bs0 + b1*bs1 (B may use strides 0,0 = shared).
+ *   batch b = b1*nb0 + b0, batch_off = b0*bs0 + b1*bs1.  A stride of 0 on a batch dimension (A or B) = that operand is
+ *   shared by every entry of the dimension.  Batch strides may be smaller than the operand (overlapping entries): the k taps
+ *   of a conv weight gradient are ONE launch with b_bs1 = dilation rows and d_bs1 = one column block of dW.
  *   `*_rows` is the number of valid rows of the 2-D matrix (m/n extent for K-major, k extent for
  *   MN-major); rows outside [0, rows) read as zero (TMA out-of-bounds fill) -- this is how the
  *   causal left padding of the TCN (temporal_convolutional_model.py:12-18,24-27) and ragged tile
