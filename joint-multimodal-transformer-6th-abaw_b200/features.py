@@ -46,6 +46,35 @@ def write_shard(path: str, visual: np.ndarray, audio: np.ndarray, labels_v: np.n
         f.write(np.ascontiguousarray(labels_a, dtype="<f4").tobytes())
 
 
+def read_clip_features(root: str, video: str, clip_ids: Sequence) -> np.ndarray:
+    """One window of per-clip feature vectors from the reference's on-disk layout `<root>/<video>/<clip>.npy`
+    (create_wavlm_audio_feat.py:30-33 writes one 1-D vector per clip; train.py:150-171 reads them back one `np.load` per clip
+    per step).  Returns (T, D) float32.  A missing file repeats the previous clip's vector, which is what the reference's loop
+    does (train.py:157-159 keeps the last `feat_numpy` when `os.path.exists` fails); a missing FIRST clip is an error there
+    (unbound variable) and here."""
+    import os
+    rows, prev = [], None
+    for c in clip_ids:
+        f = os.path.join(root, str(video), f"{c}.npy")
+        if os.path.exists(f):
+            prev = np.load(f).astype(np.float32, copy=False).reshape(-1)
+        elif prev is None:
+            raise FileNotFoundError(f"{f}: the first clip of a window has no feature file (the reference fails here too)")
+        rows.append(prev)
+    return np.stack(rows, axis=0)
+
+
+def pack_npy_tree(path: str, audio_root: str, windows: Sequence[Tuple[str, Sequence]], visual: np.ndarray,
+                  labels_v: np.ndarray, labels_a: np.ndarray):
+    """Pack W windows into one shard: window i takes its audio from the per-clip tree (`windows[i] = (video, clip_ids)`,
+    see read_clip_features) and its visual features / labels from row i of the given arrays (visual (W, Cv, T) as the TCN
+    consumes it, labels (W, T) with -5 = ignore)."""
+    audio = np.stack([read_clip_features(audio_root, v, ids) for v, ids in windows], axis=0)
+    if audio.shape[:2] != (visual.shape[0], visual.shape[2]):
+        raise ValueError(f"audio windows {audio.shape[:2]} do not match visual (W, T) = {(visual.shape[0], visual.shape[2])}")
+    write_shard(path, visual, audio, labels_v, labels_a)
+
+
 class Shard:
     """Memory-mapped view of one shard: .visual / .audio are uint16 (bf16 bit patterns), .labels_v / .labels_a float32."""
 

@@ -190,6 +190,39 @@ def test_feature_shard_roundtrip(tmp_path):
     assert os.path.getsize(p) == F.HEADER_BYTES + W * 32 * T * 2 + W * T * 24 * 2 + 2 * W * T * 4
 
 
+def test_pack_reference_npy_tree(tmp_path):
+    """the reference's per-clip layout <root>/<video>/<clip>.npy (create_wavlm_audio_feat.py:30-33) packed into a
+    shard, window by window, with train.py:157-159's behaviour for a missing clip file (the previous clip's vector is reused)."""
+    from jmt_b200 import features as F
+    rng = np.random.RandomState(1)
+    root = tmp_path / "wavlm"
+    T, D, Cv = 6, 16, 8
+    clips = {"vidA": rng.randn(10, D).astype(np.float32), "vidB": rng.randn(7, D).astype(np.float32)}
+    for vid, arr in clips.items():
+        (root / vid).mkdir(parents=True)
+        for i, row in enumerate(arr):
+            if (vid, i + 1) != ("vidB", 4):                       # vidB/4.npy is missing on disk
+                np.save(str(root / vid / f"{i + 1}.npy"), row)    # 1-based clip names, one 1-D vector per file
+    windows = [("vidA", range(1, 7)), ("vidA", range(5, 11)), ("vidB", range(2, 8))]
+    want = np.stack([clips["vidA"][0:6], clips["vidA"][4:10], clips["vidB"][1:7]])
+    want[2, 2] = want[2, 1]                                       # clip 4 of vidB repeats clip 3
+    got = np.stack([F.read_clip_features(str(root), v, ids) for v, ids in windows])
+    assert np.array_equal(got, want)
+    with pytest.raises(FileNotFoundError):
+        F.read_clip_features(str(root), "vidB", [4, 5])
+    vis = rng.randn(3, Cv, T).astype(np.float32)
+    lv = rng.uniform(-1, 1, (3, T)).astype(np.float32)
+    la = rng.uniform(-1, 1, (3, T)).astype(np.float32)
+    p = str(tmp_path / "w.jmtshard")
+    F.pack_npy_tree(p, str(root), windows, vis, lv, la)
+    s = F.Shard(p)
+    got_a = torch.from_numpy(np.array(s.audio).view(np.int16)).view(torch.bfloat16)
+    assert torch.equal(got_a, torch.from_numpy(want).to(torch.bfloat16))
+    assert s.header["audio_dim"] == D and s.header["seq_len"] == T and s.windows == 3
+    with pytest.raises(ValueError):
+        F.pack_npy_tree(p, str(root), windows[:2], vis, lv, la)
+
+
 def test_wgrad_split_fills_whole_waves():
     """engine.wgrad_split mirrors the tiling of jmt_gemm_bf16 (CTA pairs, wide 256x512 tiles when N % 512 == 0): the chosen
     split keeps >= 8 k-blocks per slice and leaves at most ~6 % of the last wave idle for the shapes of the C2 step."""
