@@ -183,7 +183,8 @@ def main():
     crit = jmt_b200.CCCLoss(digitize_num=1, global_stats=world > 1)
     if world > 1:
         jmt_b200.dist.broadcast_parameters(model)
-        model.set_grad_sync(jmt_b200.dist.make_grad_sync())
+        # the loss is the GLOBAL-batch CCC (sums all-reduced in the forward): its parameter gradient is the SUM over ranks
+        model.set_grad_sync(jmt_b200.dist.make_grad_sync(global_loss=True))
     opt = torch.optim.SGD(model.live_parameters(), lr=1e-3)
 
     # synthetic features, per-rank seed; host copies pinned (bf16 feature shards), device copies resident

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define JMT_ABI_VERSION 5
+#define JMT_ABI_VERSION 6
 
 typedef enum {
   JMT_OK = 0,
@@ -119,6 +119,14 @@ typedef struct {
 
 int jmt_gemm_bf16(const jmt_gemm_desc* g, void* stream);
 int jmt_gemm_f32(const jmt_gemm_desc* g, void* stream);
+/* "bf16x3" high-precision tensor-core mode (SURVEY 7 hard part 4; the 1e-3 / 1e-4 parity gate of north_star): both
+ * operands are fp32 values split into two bf16 matrices of IDENTICAL geometry, x = hi + lo (jmt_split_bf16x2); g->a / g->b
+ * point at the hi parts, a_lo / b_lo at the lo parts.  Every k-step issues three tcgen05.mma into the same fp32 TMEM
+ * accumulator: A_hi B_hi + A_hi B_lo + A_lo B_hi (16 operand mantissa bits; the dropped lo x lo term is 2^-16 relative).
+ * Everything else (taps, batches, epilogue, store modes) as jmt_gemm_bf16. */
+int jmt_gemm_bf16x3(const jmt_gemm_desc* g, const void* a_lo, const void* b_lo, void* stream);
+/* hi[i] = bf16(x[i]), lo[i] = bf16(x[i] - hi[i]) over n contiguous fp32 values (all pointers 16-byte aligned) */
+int jmt_split_bf16x2(const float* x, void* hi, void* lo, int64_t n, void* stream);
 /* Debug aid (no reference counterpart): when dev_buf != NULL (device buffer of 148*16 uint64) every later
  * jmt_gemm_bf16 launch overwrites per-CTA cycle counters of its TMA / MMA / epilogue roles; NULL disables. */
 int jmt_gemm_set_profile_buffer(void* dev_buf);

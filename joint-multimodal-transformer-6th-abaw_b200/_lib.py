@@ -59,6 +59,8 @@ SIGNATURES = {
     "jmt_launch_count": [],
     "jmt_gemm_bf16": [C.POINTER(GemmDesc), _P],
     "jmt_gemm_f32": [C.POINTER(GemmDesc), _P],
+    "jmt_gemm_bf16x3": [C.POINTER(GemmDesc), _P, _P, _P],
+    "jmt_split_bf16x2": [_P, _P, _P, _L, _P],
     "jmt_gemm_set_profile_buffer": [_P],
     "jmt_attn_chain_supported": [C.POINTER(AttnDesc)],
     "jmt_attn_chain_bf16": [C.POINTER(AttnDesc), _P],
@@ -117,7 +119,7 @@ def lib():
             fn = getattr(h, name)           # AttributeError if a declared symbol is not exported
             fn.argtypes = argtypes
             fn.restype = _RESTYPES.get(name, C.c_int)
-        if h.jmt_abi_version() != 5:
+        if h.jmt_abi_version() != 6:
             raise RuntimeError("libjmt_b200.so ABI version mismatch")
         _lib = h
     return _lib

@@ -77,9 +77,12 @@ class CCCMetric(object):
         self.sums = None
 
     def get(self, group=None):
+        """CCC of everything accumulated.  group=None (default): this process's sums only -- safe to call on one rank for
+        logging.  group=True / a ProcessGroup: all-reduce the partial sums first (a COLLECTIVE: every rank of the group must
+        call it), same convention as losses.six_sums and valpost.ValPostprocessor."""
         if self.sums is None:
             raise ValueError("CCCMetric.get() before update()")
         s = self.sums.clone()
-        if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
-            torch.distributed.all_reduce(s, group=group)
+        if group is not None:
+            torch.distributed.all_reduce(s, group=None if group is True else group)
         return float(_finalize(s, L.CCC_METRIC)[0])

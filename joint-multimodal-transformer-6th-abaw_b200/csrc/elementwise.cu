@@ -547,6 +547,37 @@ extern "C" int jmt_cast(const void* in, int in_dtype, void* out, int out_dtype, 
   return jmt_copy2d(in, in_dtype, n, out, out_dtype, n, 1, (int)n, stream);
 }
 
+// bf16x3 operand split: hi = bf16(x), lo = bf16(x - hi); x ~= hi + lo to 2^-17 relative
+__global__ void __launch_bounds__(kEwThreads)
+split_bf16x2_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int64_t n) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nt = (int64_t)gridDim.x * blockDim.x;
+  const int64_t n8 = n / 8;
+  for (int64_t i = tid; i < n8; i += nt) {
+    Vec8<float> v; v.load(x + i * 8);
+    Vec8<__nv_bfloat16> h, l;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float hf = __bfloat162float(__float2bfloat16_rn(v.v[k]));
+      h.v[k] = hf; l.v[k] = v.v[k] - hf;
+    }
+    h.store(hi + i * 8); l.store(lo + i * 8);
+  }
+  for (int64_t i = n8 * 8 + tid; i < n; i += nt) {
+    const __nv_bfloat16 hb = __float2bfloat16_rn(x[i]);
+    hi[i] = hb; lo[i] = __float2bfloat16_rn(x[i] - __bfloat162float(hb));
+  }
+}
+
+extern "C" int jmt_split_bf16x2(const float* x, void* hi, void* lo, int64_t n, void* stream) {
+  if (n == 0) return JMT_OK;
+  JMT_REQUIRE(x && hi && lo && n > 0, "jmt_split_bf16x2: bad arguments");
+  JMT_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(hi) | reinterpret_cast<uintptr_t>(lo)) & 15) == 0,
+              "jmt_split_bf16x2: x, hi and lo must be 16-byte aligned");
+  split_bf16x2_kernel<<<grid_for((n + 7) / 8, kEwThreads), kEwThreads, 0, (cudaStream_t)stream>>>(
+      x, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, n);
+  return check_launch("split_bf16x2_kernel");
+}
+
 extern "C" int jmt_transpose_strided(const void* in, int in_dtype, int64_t in_bs, void* out, int out_dtype, int64_t out_bs, int64_t nb,
                                      int R, int C, void* stream) {
   JMT_REQUIRE(in && out && nb >= 0 && R >= 0 && C >= 0 && nb < 65536, "jmt_transpose: bad arguments");

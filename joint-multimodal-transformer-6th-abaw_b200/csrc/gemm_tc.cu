@@ -293,18 +293,25 @@ __device__ __forceinline__ bool epi_tile(const TcParams& p, const CUtensorMap* t
   return released;
 }
 
-template <int kCta, bool kMask, int kEpi>
+// kX3: "bf16x3" split-operand mode (SURVEY 7 hard part 4): every fp32 operand is given as two bf16 matrices of identical
+// geometry, x = hi + lo (hi = bf16(x), lo = bf16(x - hi), 16 mantissa bits together).  A stage holds the four tiles
+// A_hi | A_lo and B_hi | B_lo, and every k-step issues THREE tcgen05.mma into the same fp32 TMEM accumulator:
+// A_hi B_hi + A_hi B_lo + A_lo B_hi  (the dropped lo x lo term is 2^-16 relative) -- the 1e-3 parity gate on tensor cores.
+template <int kCta, bool kMask, int kEpi, bool kX3>
 __global__ void __launch_bounds__(64 + 32 * kEpi, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-               const __grid_constant__ CUtensorMap tma_d, const TcParams p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a_hi, const __grid_constant__ CUtensorMap tma_b_hi,
+               const __grid_constant__ CUtensorMap tma_d, const __grid_constant__ CUtensorMap tma_a_lo,
+               const __grid_constant__ CUtensorMap tma_b_lo, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte aligned carve-up (SWIZZLE_128B atoms are 1024 B); identical offsets in both CTAs of a pair
   // no static shared memory in this kernel: the dynamic window starts 1024-byte aligned (SWIZZLE_128B atoms); fail loudly if not
   const uint32_t smem_base = smem_u32(smem_raw);
   if ((smem_base & 1023u) != 0u) __trap();
+  constexpr int kOps = kX3 ? 2 : 1;                          // tiles per operand and stage (hi | lo)
+  const uint32_t a_stride = kOps * kAStageBytes, b_stride = kOps * p.b_stage_bytes;
   const uint32_t sA = smem_base;
-  const uint32_t sB = sA + p.stages * kAStageBytes;
-  const uint32_t sD = sB + p.stages * p.b_stage_bytes;       // epilogue warps x 4 KiB staging (1024-aligned)
+  const uint32_t sB = sA + p.stages * a_stride;
+  const uint32_t sD = sB + p.stages * b_stride;              // epilogue warps x 4 KiB staging (1024-aligned)
   const uint32_t sBias = sD + kEpi * kEpiStageBytes;         // 256 floats: this tile's bias slice
   const uint32_t bars = sBias + kBiasFlagBytes;              // 8-byte aligned (behind the bias tile and the keep-flag words)
   const uint32_t full_bar = bars, empty_bar = bars + 8 * kMaxStages;
@@ -348,8 +355,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   if (warp == 0) {
     if (lane == 0) {
       // ================================ TMA producer (every CTA) ================================
-      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_a)) : "memory");
-      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_b)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_a_hi)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_b_hi)) : "memory");
+      if constexpr (kX3) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_a_lo)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_b_lo)) : "memory");
+      }
       int stage = 0; uint32_t phase = 0;
       long long pr_wait = 0; const long long pr_t0 = p.prof ? clock64() : 0;
       const int b_chunks = p.b_chunks_cta;                    // 64-wide MN chunks staged by this CTA
@@ -373,11 +384,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           const long long tw = p.prof ? clock64() : 0;
           mbar_wait(empty_bar + 8 * stage, phase ^ 1);
           if (p.prof) pr_wait += clock64() - tw;
-          const uint32_t a_dst = sA + stage * kAStageBytes;
-          const uint32_t b_dst = sB + stage * p.b_stage_bytes;
+          if constexpr (kCta == 1) mbar_expect_tx(full_bar + 8 * stage, kOps * (kAStageBytes + p.b_tx_bytes));
+          else mbar_expect_tx_cluster(full_leader + 8 * stage, kOps * (kAStageBytes + p.b_tx_bytes));
+#pragma unroll
+          for (int part = 0; part < kOps; ++part) {          // kX3: part 0 = hi tiles, part 1 = lo tiles (same coordinates)
+          const CUtensorMap& tma_a = part == 0 ? tma_a_hi : tma_a_lo;
+          const CUtensorMap& tma_b = part == 0 ? tma_b_hi : tma_b_lo;
+          const uint32_t a_dst = sA + stage * a_stride + part * kAStageBytes;
+          const uint32_t b_dst = sB + stage * b_stride + part * p.b_stage_bytes;
           if constexpr (kCta == 1) {
             const uint32_t fb = full_bar + 8 * stage;
-            mbar_expect_tx(fb, kAStageBytes + p.b_tx_bytes);
             if (p.a_major == JMT_MAJOR_K) {
               tma_load_4d(a_dst, &tma_a, fb, kb * kBlockK, c.m0 + ash, ab0, ab1);
             } else if (p.a_mn5) {
@@ -396,7 +412,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             }
           } else {
             const uint32_t fb = full_leader + 8 * stage;
-            mbar_expect_tx_cluster(fb, kAStageBytes + p.b_tx_bytes);
             if (p.a_major == JMT_MAJOR_K) {
               tma_load_4d_2sm(a_dst, &tma_a, fb, kb * kBlockK, c.m0 + ash, ab0, ab1);
             } else if (p.a_mn5) {
@@ -420,6 +435,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
               for (int ch = 0; ch < b_chunks; ++ch)
                 tma_load_4d_2sm(b_dst + ch * 8192, &tma_b, fb, c.n0 + n_off + ch * 64, kb * kBlockK + bsh, bb0, bb1);
             }
+          }
           }
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
           if (++kb == p.kblocks) {
@@ -455,12 +471,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           mbar_wait(full_bar + 8 * stage, phase);
           if (p.prof) mw_full += clock64() - tw1;
           tc_fence_after();
-          const uint64_t a_desc = make_smem_desc(sA + stage * kAStageBytes, a_lbo, 1024);
-          const uint64_t b_desc = make_smem_desc(sB + stage * p.b_stage_bytes, b_lbo, 1024);
+          const uint64_t a_desc = make_smem_desc(sA + stage * a_stride, a_lbo, 1024);
+          const uint64_t b_desc = make_smem_desc(sB + stage * b_stride, b_lbo, 1024);
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; ++k) {
             tc_mma<kCta>(d_tmem, a_desc + (uint64_t)(k * a_kstep), b_desc + (uint64_t)(k * b_kstep), p.idesc,
                          (it > c.it0 || k > 0) ? 1u : 0u);
+            if constexpr (kX3) {   // + A_hi B_lo + A_lo B_hi (the lo tiles sit one tile behind the hi tiles; descriptor units of 16 B)
+              tc_mma<kCta>(d_tmem, a_desc + (uint64_t)(k * a_kstep), b_desc + (uint64_t)((p.b_stage_bytes >> 4) + k * b_kstep), p.idesc, 1u);
+              tc_mma<kCta>(d_tmem, a_desc + (uint64_t)((kAStageBytes >> 4) + k * a_kstep), b_desc + (uint64_t)(k * b_kstep), p.idesc, 1u);
+            }
             if (p.wide)      // columns 256..511 of the tile: same A, second B piece (16 KB further), TMEM columns 256..511
               tc_mma<kCta>(d_tmem + 256, a_desc + (uint64_t)(k * a_kstep), b_desc + (uint64_t)(1024 + k * b_kstep), p.idesc,
                            (it > c.it0 || k > 0) ? 1u : 0u);
@@ -610,9 +630,11 @@ extern "C" int jmt_gemm_epi_prof_read(unsigned long long* host8, int reset) {
 }
 #endif
 
-extern "C" int jmt_gemm_bf16(const jmt_gemm_desc* g, void* stream) {
+// a_lo / b_lo != NULL: the bf16x3 split-operand mode (g->a / g->b are the hi parts; lo parts have identical geometry)
+static int gemm_tc_launch(const jmt_gemm_desc* g, const void* a_lo, const void* b_lo, void* stream) {
   int rc = jmt_validate_gemm_desc(g, "jmt_gemm_bf16");
   if (rc != JMT_OK) return rc;
+  const bool x3 = a_lo != nullptr;
   TcParams p;
   memset(&p, 0, sizeof(p));
   p.M = g->M; p.N = g->N; p.K = g->K;
@@ -644,7 +666,7 @@ extern "C" int jmt_gemm_bf16(const jmt_gemm_desc* g, void* stream) {
   {
     static const int wide_env = []() { const char* e = getenv("JMT_GEMM_WIDE"); return e ? atoi(e) : 1; }();
     const int min_iters = wide_env > 1 ? wide_env : kWideMinIters;
-    p.wide = (wide_env != 0 && p.cluster == 2 && !p.pair_batch && g->N % 512 == 0 &&
+    p.wide = (wide_env != 0 && !x3 && p.cluster == 2 && !p.pair_batch && g->N % 512 == 0 &&
               p.iters_total / p.split_k >= min_iters) ? 1 : 0;
     if (p.wide) { p.block_n = 512; p.n_tiles = g->N / 512; }
   }
@@ -668,14 +690,10 @@ extern "C" int jmt_gemm_bf16(const jmt_gemm_desc* g, void* stream) {
   p.b_chunks_cta = (b_cols_cta + 63) / 64;
   p.b_stage_bytes = (g->b_major == JMT_MAJOR_K ? b_cols_cta * 128 : p.b_chunks_cta * 8192) * (p.wide ? 2 : 1);
   p.b_tx_bytes = p.b_stage_bytes;
-  const int stage_bytes = kAStageBytes + p.b_stage_bytes;
-  // 16 epilogue warps when a tile's mainloop is short (the accumulator drain, not the MMAs, bounds those tiles); 8 otherwise
-  // (more registers per thread, one more pipeline stage).  JMT_GEMM_EPI_WARPS = 8 | 16 overrides.
-  {
-    const char* env_ep = getenv("JMT_GEMM_EPI_WARPS");
-    const int forced = env_ep ? atoi(env_ep) : 0;
-    p.epi_warps = (forced == 8 || forced == 16) ? forced : 8;
-  }
+  const int stage_bytes = (kAStageBytes + p.b_stage_bytes) * (x3 ? 2 : 1);     // x3: hi and lo tile of each operand
+  // 8 epilogue warps, two per TMEM lane quarter (a 16-warp variant measured 3-10 % slower on every shape in round 1: the
+  // epilogue waits on the stage hand-over, it is not short of warps; the instantiation was dropped)
+  p.epi_warps = 8;
   const int budget = 227 * 1024 - 256 /*barriers*/ - epi_smem_bytes(p.epi_warps);      // the dynamic window is 1024-aligned (checked in the kernel)
   p.stages = budget / stage_bytes;
   if (p.stages > kMaxStages) p.stages = kMaxStages;
@@ -714,6 +732,24 @@ extern "C" int jmt_gemm_bf16(const jmt_gemm_desc* g, void* stream) {
     rc = make_map(&map_b, g->b, g->N, g->b_rows, g->b_ld, bnb0, g->b_bs0, bnb1, g->b_bs1, kBlockK, "jmt_gemm_bf16(B)");
   if (rc != JMT_OK) return rc;
 
+  CUtensorMap map_a_lo = map_a, map_b_lo = map_b;
+  if (x3) {
+    if (g->a_major == JMT_MAJOR_K)
+      rc = make_map(&map_a_lo, a_lo, g->K, g->a_rows, g->a_ld, anb0, g->a_bs0, anb1, g->a_bs1, kBlockM, "jmt_gemm_bf16x3(A lo)");
+    else if (p.a_mn5)
+      rc = make_map_mn5(&map_a_lo, a_lo, g->M, g->a_rows, g->a_ld, anb0, g->a_bs0, anb1, g->a_bs1, kBlockK, 2, "jmt_gemm_bf16x3(A lo)");
+    else
+      rc = make_map(&map_a_lo, a_lo, g->M, g->a_rows, g->a_ld, anb0, g->a_bs0, anb1, g->a_bs1, kBlockK, "jmt_gemm_bf16x3(A lo)");
+    if (rc != JMT_OK) return rc;
+    if (g->b_major == JMT_MAJOR_K)
+      rc = make_map(&map_b_lo, b_lo, (int64_t)g->ntaps * g->K, g->b_rows, g->b_ld, bnb0, g->b_bs0, bnb1, g->b_bs1, b_cols_cta, "jmt_gemm_bf16x3(B lo)");
+    else if (p.b_mn5)
+      rc = make_map_mn5(&map_b_lo, b_lo, g->N, g->b_rows, g->b_ld, bnb0, g->b_bs0, bnb1, g->b_bs1, kBlockK, p.b_chunks_cta, "jmt_gemm_bf16x3(B lo)");
+    else
+      rc = make_map(&map_b_lo, b_lo, g->N, g->b_rows, g->b_ld, bnb0, g->b_bs0, bnb1, g->b_bs1, kBlockK, "jmt_gemm_bf16x3(B lo)");
+    if (rc != JMT_OK) return rc;
+  }
+
   // D through TMA (store / reduce-add) when its geometry is 16-byte aligned; bf16 read-modify-write
   // accumulation and fp32 atomics both become cp.reduce.async.bulk.tensor .add
   CUtensorMap map_d = map_a;
@@ -730,10 +766,10 @@ extern "C" int jmt_gemm_bf16(const jmt_gemm_desc* g, void* stream) {
   if (!attr_set[dev & 63].load(std::memory_order_acquire)) {
     cudaError_t e = cudaSuccess;
     auto set_smem = [&e](const void* fn) { if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); };
-    set_smem((const void*)gemm_tc_kernel<1, false, 8>); set_smem((const void*)gemm_tc_kernel<2, false, 8>);
-    set_smem((const void*)gemm_tc_kernel<1, true, 8>); set_smem((const void*)gemm_tc_kernel<2, true, 8>);
-    set_smem((const void*)gemm_tc_kernel<1, false, 16>); set_smem((const void*)gemm_tc_kernel<2, false, 16>);
-    set_smem((const void*)gemm_tc_kernel<1, true, 16>); set_smem((const void*)gemm_tc_kernel<2, true, 16>);
+    set_smem((const void*)gemm_tc_kernel<1, false, 8, false>); set_smem((const void*)gemm_tc_kernel<2, false, 8, false>);
+    set_smem((const void*)gemm_tc_kernel<1, true, 8, false>); set_smem((const void*)gemm_tc_kernel<2, true, 8, false>);
+    set_smem((const void*)gemm_tc_kernel<1, false, 8, true>); set_smem((const void*)gemm_tc_kernel<2, false, 8, true>);
+    set_smem((const void*)gemm_tc_kernel<1, true, 8, true>); set_smem((const void*)gemm_tc_kernel<2, true, 8, true>);
     if (e != cudaSuccess) { set_error("jmt_gemm_bf16: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); cudaGetLastError(); return JMT_ERR_CUDA; }
     attr_set[dev & 63].store(1, std::memory_order_release);
   }
@@ -756,11 +792,11 @@ extern "C" int jmt_gemm_bf16(const jmt_gemm_desc* g, void* stream) {
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 2 : 1;
   cudaError_t le;
-#define JMT_TC_LAUNCH(CTA, MASK, EPI) le = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<CTA, MASK, EPI>, map_a, map_b, map_d, p)
-#define JMT_TC_LAUNCH_EPI(CTA, MASK) do { if (p.epi_warps == 16) JMT_TC_LAUNCH(CTA, MASK, 16); else JMT_TC_LAUNCH(CTA, MASK, 8); } while (0)
-  if (p.colmask) { if (p.cluster == 2) JMT_TC_LAUNCH_EPI(2, true); else JMT_TC_LAUNCH_EPI(1, true); }
-  else { if (p.cluster == 2) JMT_TC_LAUNCH_EPI(2, false); else JMT_TC_LAUNCH_EPI(1, false); }
-#undef JMT_TC_LAUNCH_EPI
+#define JMT_TC_LAUNCH(CTA, MASK, X3) le = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<CTA, MASK, 8, X3>, map_a, map_b, map_d, map_a_lo, map_b_lo, p)
+#define JMT_TC_LAUNCH_X(CTA, MASK) do { if (x3) JMT_TC_LAUNCH(CTA, MASK, true); else JMT_TC_LAUNCH(CTA, MASK, false); } while (0)
+  if (p.colmask) { if (p.cluster == 2) JMT_TC_LAUNCH_X(2, true); else JMT_TC_LAUNCH_X(1, true); }
+  else { if (p.cluster == 2) JMT_TC_LAUNCH_X(2, false); else JMT_TC_LAUNCH_X(1, false); }
+#undef JMT_TC_LAUNCH_X
 #undef JMT_TC_LAUNCH
   if (le != cudaSuccess) {
     set_error("jmt_gemm_bf16: cudaLaunchKernelEx: %s", cudaGetErrorString(le));
@@ -768,4 +804,11 @@ extern "C" int jmt_gemm_bf16(const jmt_gemm_desc* g, void* stream) {
     return JMT_ERR_CUDA;
   }
   return check_launch("gemm_tc_kernel");
+}
+
+extern "C" int jmt_gemm_bf16(const jmt_gemm_desc* g, void* stream) { return gemm_tc_launch(g, nullptr, nullptr, stream); }
+
+extern "C" int jmt_gemm_bf16x3(const jmt_gemm_desc* g, const void* a_lo, const void* b_lo, void* stream) {
+  JMT_REQUIRE(a_lo && b_lo, "jmt_gemm_bf16x3: the lo parts of both operands are required");
+  return gemm_tc_launch(g, a_lo, b_lo, stream);
 }

@@ -1,7 +1,8 @@
 """Data-parallel plumbing (one process per GPU, torch.distributed / NCCL over NVLink).
 
 The path shards along the batch of clip windows; the only collectives are
-  (1) training: one all-reduce(sum)/n over the flat fp32 live-gradient bucket at the end of backward,
+  (1) training: one all-reduce over the flat fp32 live-gradient bucket at the end of backward -- SUM when the loss is the
+      global-batch CCC (CCCLoss(global_stats=True)), MEAN for per-rank losses (see make_grad_sync),
   (2) eval / global loss: one all-reduce(sum) of the (2, 6) fp64 CCC partial sums.
 `joint_modalities='NONE'` attends across the batch and is therefore per-shard
 ("replicas only") exactly as the reference's DataParallel scatter would make it.
@@ -75,8 +76,18 @@ class GradSync:
         self.finish()
 
 
-def make_grad_sync(group=None, average: bool = True) -> GradSync:
-    """Hook for `module.set_grad_sync`: all-reduce the flat gradient bucket in place (see GradSync)."""
+def make_grad_sync(group=None, average: Optional[bool] = None, global_loss: bool = False) -> GradSync:
+    """Hook for `module.set_grad_sync`: all-reduce the flat gradient bucket in place (see GradSync).
+
+    Which reduction is right depends on the loss:
+      * per-rank loss (each rank computes the CCC of ITS shard): the data-parallel convention is the MEAN of the per-rank
+        gradients -> average=True (default when global_loss is False);
+      * global-batch loss (`CCCLoss(global_stats=True)`: the six sums are all-reduced inside the forward, so every rank
+        back-propagates d L_global / d(its own predictions)): the gradient of that ONE loss w.r.t. the replicated
+        parameters is the SUM of the per-rank pieces -> pass global_loss=True (average=False).  Averaging there would
+        shrink the gradient by 1/world and make training depend on the number of GPUs."""
+    if average is None:
+        average = not global_loss
     return GradSync(group, average)
 
 

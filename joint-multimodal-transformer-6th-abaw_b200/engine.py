@@ -8,8 +8,11 @@ flat fp32 bucket (the NCCL all-reduce unit) and (d) the step is CU
 capturable (no host synchronisation anywhere).
 
 Precision modes (SURVEY.md 7 "hard parts" #4):
-  'bf16' : bf16 operands / activations, fp32 accumulate (tcgen05 path), fp32 LN/softmax statistics
-  'fp32' : fp32 operands / activations on the FFMA GEMM -- the parity mode for the 1e-3 gate
+  'bf16'   : bf16 operands / activations, fp32 accumulate (tcgen05 path), fp32 LN/softmax statistics
+  'bf16x3' : fp32 activations; every GEMM operand is split into two bf16 parts (x = hi + lo) and the tcgen05 kernel issues
+             three MMAs per k-step (hi*hi + hi*lo + lo*hi) into one fp32 TMEM accumulator -- the tensor-core mode that
+             meets the 1e-3 prediction / 1e-4 CCC parity gate of north_star
+  'fp32'   : fp32 operands / activations on the FFMA GEMM -- kept as an independent on-device cross-check only
 """
 from __future__ import annotations
 
@@ -23,6 +26,14 @@ from . import _lib as L
 
 _DT = {torch.float32: L.F32, torch.bfloat16: L.BF16}
 LEAKY_SLOPE = 0.01
+PRECISIONS = ("bf16", "bf16x3", "fp32")
+_PARAM_GENERATION = [0]
+
+
+def bump_param_generation():
+    """Invalidate every cached bf16 operand copy of a parameter: call after parameters were changed behind autograd's back
+    (a CUDA-graph replay containing optimizer.step(): in-place `_version` counters do not move)."""
+    _PARAM_GENERATION[0] += 1
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -115,10 +126,13 @@ class Ctx:
 
     def __init__(self, params: Dict[str, torch.Tensor], precision: str, record: bool, training: bool,
                  wcache: Optional[dict] = None, seed: int = 0, rng_state: Optional[torch.Tensor] = None):
-        assert precision in ("bf16", "fp32"), precision
+        assert precision in PRECISIONS, precision
         self.params = params
         self.precision = precision
         self.adt = torch.bfloat16 if precision == "bf16" else torch.float32
+        self.x3 = precision == "bf16x3"
+        self.x3_const: List[Tuple[int, int]] = []      # address ranges of parameters (their splits are reused within this pass)
+        self.x3_cache: Dict[Tuple[int, int], Tuple[torch.Tensor, torch.Tensor]] = {}
         self.acode = _DT[self.adt]
         self.record = record
         self.training = training
@@ -155,18 +169,27 @@ class Ctx:
         """Parameter as a GEMM operand in the activation dtype (cast once per parameter version)."""
         par = self.params[name]
         if self.adt == torch.float32:
+            if self.x3 and name not in self._w:
+                self._w[name] = par
+                self.x3_const.append((par.data_ptr(), par.data_ptr() + par.numel() * 4))
             return par
         t = self._w.get(name)
         if t is None:
-            key = (par.data_ptr(), par._version, tuple(par.shape))
-            ent = self.wcache.get(name)
-            # Under CUDA-graph capture the cast must be PART of the graph: a replay runs after optimizer steps that the
-            # version check at capture time cannot see (torch.cuda.make_graphed_callables warms up without an optimizer).
-            if ent is None or ent[0] != key or torch.cuda.is_current_stream_capturing():
+            # The cache entry is valid for one (storage, in-place version, replay generation): a CUDA-graph replay that
+            # contains optimizer.step() updates the parameters on the device WITHOUT bumping `_version`, so every replay
+            # (GraphedStep.replay) bumps the generation instead.
+            key = (par.data_ptr(), par._version, tuple(par.shape), _PARAM_GENERATION[0])
+            capturing = torch.cuda.is_current_stream_capturing()
+            ent = None if capturing else self.wcache.get(name)
+            if ent is None or ent[0] != key:
+                # Under capture the cast is always PART of the graph (a replay runs after optimizer steps the version
+                # check at capture time cannot see) and stays private to it: a graph-pool tensor has no content before
+                # the first replay and must never be handed to a later eager forward.
                 out = torch.empty(par.shape, dtype=self.adt, device=par.device)
                 L.check(self.lib.jmt_cast(_ptr(par), L.F32, _ptr(out), self.acode, par.numel(), _stream()), "jmt_cast")
                 ent = (key, out)
-                self.wcache[name] = ent
+                if not capturing:
+                    self.wcache[name] = ent
             t = ent[1]
             self._w[name] = t
         return t
@@ -296,6 +319,15 @@ def gemm(ctx: Ctx, a: torch.Tensor, b: torch.Tensor, d: torch.Tensor, *, M: int,
     if a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16:
         L.check(ctx.lib.jmt_gemm_bf16(C.byref(g), _stream()), "jmt_gemm_bf16")
         kind = "gemm_tc_kernel"
+    elif ctx.x3 and a.dtype == torch.float32 and b.dtype == torch.float32:
+        # bf16x3: split both fp32 operands over the address span the descriptor can touch (same strides for hi / lo)
+        a_inner = K if a_major == L.MAJOR_K else M
+        b_inner = ntaps * K if b_major == L.MAJOR_K else N
+        a_hi, a_lo = _split_x3(ctx, a, (nb1 - 1) * g.a_bs1 + (nb0 - 1) * g.a_bs0 + (g.a_rows - 1) * g.a_ld + a_inner)
+        b_hi, b_lo = _split_x3(ctx, b, (nb1 - 1) * g.b_bs1 + (nb0 - 1) * g.b_bs0 + (g.b_rows - 1) * g.b_ld + b_inner)
+        g.a, g.b = a_hi.data_ptr(), b_hi.data_ptr()
+        L.check(ctx.lib.jmt_gemm_bf16x3(C.byref(g), _ptr(a_lo), _ptr(b_lo), _stream()), "jmt_gemm_bf16x3")
+        kind = "gemm_tc_kernel"
     elif a.dtype == torch.float32 and b.dtype == torch.float32:
         L.check(ctx.lib.jmt_gemm_f32(C.byref(g), _stream()), "jmt_gemm_f32")
         kind = "gemm_simt_kernel"
@@ -306,6 +338,24 @@ def gemm(ctx: Ctx, a: torch.Tensor, b: torch.Tensor, d: torch.Tensor, *, M: int,
         fl = alg_flops if alg_flops is not None else gemm_flops(M, N, K, nb0 * nb1, ntaps, tuple(a_shift), tuple(b_shift),
                                                                 g.a_rows, g.b_rows, a_major, b_major)
         prof.append((kind, fl, e0, e1, (M, N, K, nb0 * nb1, ntaps)))
+
+
+def _split_x3(ctx: Ctx, t: torch.Tensor, span: int):
+    """(hi, lo) bf16 buffers of `span` elements with hi[i] + lo[i] ~= t.flat[i] for the elements from t's first one on
+    (jmt_split_bf16x2); element offsets -- hence ld / batch strides -- are those of the fp32 operand.  Splits of parameters are
+    reused for the rest of the pass (forward GEMM and dgrad read the same weight)."""
+    ptr = t.data_ptr()
+    const = any(lo <= ptr < hi for lo, hi in ctx.x3_const)
+    if const:
+        hit = ctx.x3_cache.get((ptr, span))
+        if hit is not None:
+            return hit
+    hi = torch.empty((span,), dtype=torch.bfloat16, device=t.device)
+    lo = torch.empty((span,), dtype=torch.bfloat16, device=t.device)
+    L.check(ctx.lib.jmt_split_bf16x2(C.c_void_p(ptr), _ptr(hi), _ptr(lo), span, _stream()), "jmt_split_bf16x2")
+    if const:
+        ctx.x3_cache[(ptr, span)] = (hi, lo)
+    return hi, lo
 
 
 def copy2d(ctx: Ctx, src: torch.Tensor, dst: torch.Tensor):

@@ -46,30 +46,36 @@ def write_shard(path: str, visual: np.ndarray, audio: np.ndarray, labels_v: np.n
         f.write(np.ascontiguousarray(labels_a, dtype="<f4").tobytes())
 
 
-def read_clip_features(root: str, video: str, clip_ids: Sequence) -> np.ndarray:
+def read_clip_features(root: str, video: str, clip_ids: Sequence, prev: Optional[np.ndarray] = None):
     """One window of per-clip feature vectors from the reference's on-disk layout `<root>/<video>/<clip>.npy`
     (create_wavlm_audio_feat.py:30-33 writes one 1-D vector per clip; train.py:150-171 reads them back one `np.load` per clip
-    per step).  Returns (T, D) float32.  A missing file repeats the previous clip's vector, which is what the reference's loop
-    does (train.py:157-159 keeps the last `feat_numpy` when `os.path.exists` fails); a missing FIRST clip is an error there
-    (unbound variable) and here."""
+    per step).  Returns ((T, D) float32, last vector).  A missing file repeats the most recently loaded vector, which is what
+    the reference's loop does: `feat_numpy` (train.py:157-159) survives across clips, windows AND batches, so `prev` carries
+    the last vector of the previous window in; only a missing file before ANY clip was ever loaded fails (unbound
+    variable in the reference, FileNotFoundError here)."""
     import os
-    rows, prev = [], None
+    rows = []
     for c in clip_ids:
         f = os.path.join(root, str(video), f"{c}.npy")
         if os.path.exists(f):
             prev = np.load(f).astype(np.float32, copy=False).reshape(-1)
         elif prev is None:
-            raise FileNotFoundError(f"{f}: the first clip of a window has no feature file (the reference fails here too)")
+            raise FileNotFoundError(f"{f}: no feature file and no previously loaded clip to repeat "
+                                    "(the reference raises UnboundLocalError here, train.py:157-171)")
         rows.append(prev)
-    return np.stack(rows, axis=0)
+    return np.stack(rows, axis=0), prev
 
 
 def pack_npy_tree(path: str, audio_root: str, windows: Sequence[Tuple[str, Sequence]], visual: np.ndarray,
                   labels_v: np.ndarray, labels_a: np.ndarray):
     """Pack W windows into one shard: window i takes its audio from the per-clip tree (`windows[i] = (video, clip_ids)`,
-    see read_clip_features) and its visual features / labels from row i of the given arrays (visual (W, Cv, T) as the TCN
-    consumes it, labels (W, T) with -5 = ignore)."""
-    audio = np.stack([read_clip_features(audio_root, v, ids) for v, ids in windows], axis=0)
+    see read_clip_features; the last loaded vector carries over from window to window as in train.py:150-171) and its visual
+    features / labels from row i of the given arrays (visual (W, Cv, T) as the TCN consumes it, labels (W, T) with -5 = ignore)."""
+    mats, prev = [], None
+    for v, ids in windows:
+        m, prev = read_clip_features(audio_root, v, ids, prev)
+        mats.append(m)
+    audio = np.stack(mats, axis=0)
     if audio.shape[:2] != (visual.shape[0], visual.shape[2]):
         raise ValueError(f"audio windows {audio.shape[:2]} do not match visual (W, T) = {(visual.shape[0], visual.shape[2])}")
     write_shard(path, visual, audio, labels_v, labels_a)
@@ -112,6 +118,7 @@ class FeatureShardLoader:
         self.stream = torch.cuda.Stream(device=self.device)
         self.ready = [torch.cuda.Event() for _ in range(2)]
         self.copied = [torch.cuda.Event() for _ in range(2)]      # H2D out of the pinned set has completed
+        self.consumed = [torch.cuda.Event() for _ in range(2)]    # the consumer's work queued so far (reads of dev[slot]) is done
 
     def _plan(self):
         for s in self.shards:
@@ -130,16 +137,31 @@ class FeatureShardLoader:
         lv.numpy()[:n] = s.labels_v[w0:w0 + n]
         la.numpy()[:n] = s.labels_a[w0:w0 + n]
 
+    def _stage_guarded(self, box: dict, slot: int, s: Shard, w0: int, n: int):
+        try:
+            self._stage(slot, s, w0, n)
+        except BaseException as e:       # re-raised on the consumer thread after join(): never yield stale pinned data
+            box["error"] = e
+
     def __iter__(self) -> Iterator[Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]]:
         plan = list(self._plan())
         worker: Optional[threading.Thread] = None
+        box: dict = {}
         if plan:
-            worker = threading.Thread(target=self._stage, args=(0, *plan[0]))
+            worker = threading.Thread(target=self._stage_guarded, args=(box, 0, *plan[0]))
             worker.start()
         for i, (s, w0, n) in enumerate(plan):
             slot = i % 2
             worker.join()                                            # batch i is in the pinned set `slot`
+            if "error" in box:
+                raise RuntimeError("FeatureShardLoader: staging a batch failed") from box["error"]
+            cur = torch.cuda.current_stream(self.device)
+            # write-after-read on the device buffers: dev[slot] was handed out as batch i-2 and everything the consumer
+            # queued on its stream up to now (that step's kernels; the host may run several steps ahead of the GPU) must
+            # have finished reading it before the copy engine overwrites it
+            self.consumed[slot].record(cur)
             with torch.cuda.stream(self.stream):
+                self.stream.wait_event(self.consumed[slot])
                 for d, h in zip(self.dev[slot], self.host[slot]):
                     d[:n].copy_(h[:n], non_blocking=True)
                 self.copied[slot].record(self.stream)
@@ -147,7 +169,7 @@ class FeatureShardLoader:
             if i + 1 < len(plan):                                    # stage batch i+1 while batch i copies / trains
                 nslot = (i + 1) % 2
                 self.copied[nslot].synchronize()                     # its previous H2D (batch i-1) has drained
-                worker = threading.Thread(target=self._stage, args=(nslot, *plan[i + 1]))
+                worker = threading.Thread(target=self._stage_guarded, args=(box, nslot, *plan[i + 1]))
                 worker.start()
-            torch.cuda.current_stream(self.device).wait_event(self.ready[slot])
+            cur.wait_event(self.ready[slot])
             yield tuple(d[:n] for d in self.dev[slot])

@@ -51,4 +51,8 @@ class GraphedStep:
     def replay(self, which: int = 0) -> torch.Tensor:
         """Launch the graph bound to buffer set `which`; returns its (static) device loss tensor."""
         self.graphs[which].replay()
+        # the replayed optimizer step changed the parameters without touching their `_version`: eager forwards that follow
+        # (validation between training epochs) must re-cast their bf16 operand copies
+        from .engine import bump_param_generation
+        bump_param_generation()
         return self.losses[which]

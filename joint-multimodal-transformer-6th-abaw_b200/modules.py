@@ -3,7 +3,7 @@ signatures, forward signatures, state_dict keys/shapes and (seeded) initialisati
 main.py / train.py / val.py can swap them in.  ``forward`` never touches ATen math:
 it runs the tape engine over libjmt_b200.so and is wired into torch.autograd with one Function.
 
-Extra keyword (not in the reference): ``precision`` in {'bf16' (default), 'fp32'}.
+Extra keyword (not in the reference): ``precision`` in {'bf16' (default), 'bf16x3', 'fp32'} (engine.py).
 """
 from __future__ import annotations
 
@@ -362,7 +362,7 @@ class Two_transformers(_JmtModule):
         assert isinstance(vision_in_ft, int), type(vision_in_ft)
         assert vision_in_ft > 0, vision_in_ft
         self.vision_in_ft = vision_in_ft
-        assert precision in ("bf16", "fp32"), precision
+        assert precision in E.PRECISIONS, precision
         self.precision = precision
 
         self.linear = None

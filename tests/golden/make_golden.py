@@ -272,6 +272,169 @@ def gen_misc(R, meta):
     meta["padseq"] = dict(widths=widths, seed=71)
 
 
+# ----------------------------------------------------------------------------------------------------------------------
+# Default-init, benchmark-size cases (round 2).  Weights are NOT synthetic here: reference modules are constructed under
+# torch.manual_seed(seed) and the drop-in modules, constructed under the same seed, must come out bit-identical (the
+# constructors mirror the reference's initialisation order; pinned by `param_sums` + tests/test_host_cpu.py).  Large
+# tensors are stored as strided channel samples (every row = every (n, t) position is kept: tile borders and dilations
+# live on the row axis) plus whole-tensor L2 norms.
+# ----------------------------------------------------------------------------------------------------------------------
+def _param_sums(module):
+    return {k: float(v.double().sum()) for k, v in module.state_dict().items()
+            if "final_encoder" not in k and not k.split(".")[-2].startswith("net") and ".net." not in k}
+
+
+def _check_same_init(ours, ref, what):
+    """The drop-in constructor must reproduce the reference's seeded initialisation bit for bit."""
+    so, sr = ours.state_dict(), ref.state_dict()
+    assert list(so.keys()) == list(sr.keys()), what
+    for k in sr:
+        assert torch.equal(so[k], sr[k].detach()), (what, k)
+
+
+def _cot(shape, seed):
+    return torch.randn(shape, generator=torch.Generator().manual_seed(seed))
+
+
+def gen_default_init(R, meta):
+    import jmt_b200
+    live = _live_loss(R)
+
+    # ---- Two_transformers variants with default init; gradients for BOTH the live CCC loss and a well-conditioned random
+    #      cotangent (the latter is what the bf16 backward is compared with: reference gradients, not the repo's own fp32 engine)
+    cases = [("ttd_transformer_fc_h1", 2, 24, 1, 1, "TRANSFORMER", "FC", 512, 201),
+             ("ttd_transformer_sa_h2", 2, 9, 2, 1, "TRANSFORMER", "SELF_ATTEN", 512, 202),
+             ("ttd_fc_fc", 3, 10, 1, 1, "FC", "FC", 512, 203),
+             ("ttd_none_fc_h2", 5, 7, 2, 1, "NONE", "FC", 512, 204),
+             # batch-dimension attention (SURVEY Q2) over more than one 128-row tile, and beyond the fused kernel's S <= 320
+             # limit at dh = 512 (the long-S path): L = S = B
+             ("ttd_none_fc_b300_t2", 300, 2, 1, 1, "NONE", "FC", 512, 205),
+             ("ttd_none_fc_b400_t2", 400, 2, 1, 1, "NONE", "FC", 512, 206),
+             ("ttd_none_fc_b600_t1_h2", 600, 1, 2, 1, "NONE", "FC", 512, 207)]
+    for (name, B, T, h, L, joint, fmt, vin, seed) in cases:
+        torch.manual_seed(seed)
+        model = R["Two_transformers"](0.0, 0.0, h, L, joint, fmt, vin).eval()
+        torch.manual_seed(seed)
+        _check_same_init(jmt_b200.Two_transformers(0.0, 0.0, h, L, joint, fmt, vin), model, name)
+        aud, vis = O.synth_features(B, T, [512, vin], seed=seed + 1000)
+        lv, la = O.synth_labels(B, T, seed=seed + 2000)
+        aud.requires_grad_(True)
+        vis.requires_grad_(True)
+        v, a = model(aud, vis)
+        n = v.shape[0] * v.shape[1]
+        loss = live(v.reshape(-1, n), lv.reshape(-1, n)) + live(a.reshape(-1, n), la.reshape(-1, n))
+        loss.backward(retain_graph=True)
+        names, l2, s, head = _grad_summary(model)
+        d_aud, d_vis = aud.grad.clone(), vis.grad.clone()
+        model.zero_grad(set_to_none=True)
+        aud.grad = vis.grad = None
+        cv, ca = _cot(v.shape, seed + 3000), _cot(a.shape, seed + 3001)
+        torch.autograd.backward([v, a], [cv, ca])
+        names2, l2c, sc, headc = _grad_summary(model)
+        assert names2 == names
+        big = B * T * 512 > 40000
+        sl = (slice(None), slice(None), slice(None, None, 16)) if big else (slice(None),) * 3
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), vout=v.detach().numpy(), aout=a.detach().numpy(),
+                            loss=loss.detach().numpy(), d_aud=d_aud.numpy()[sl], d_vis=d_vis.numpy()[sl],
+                            d_aud_l2=float(d_aud.norm()), d_vis_l2=float(d_vis.norm()),
+                            grad_l2=l2, grad_sum=s, grad_head=head,
+                            c_d_aud=aud.grad.numpy()[sl], c_d_vis=vis.grad.numpy()[sl],
+                            c_d_aud_l2=float(aud.grad.norm()), c_d_vis_l2=float(vis.grad.norm()),
+                            c_grad_l2=l2c, c_grad_sum=sc, c_grad_head=headc)
+        meta[name] = dict(B=B, T=T, heads=h, layers=L, joint=joint, fmt=fmt, vin=vin, init_seed=seed, feat_seed=seed + 1000,
+                          label_seed=seed + 2000, cot_seeds=[seed + 3000, seed + 3001], grad_names=names,
+                          out_shape=list(v.shape), sample_stride=16 if big else 1, param_sums=_param_sums(model))
+        print(name, tuple(v.shape), float(loss))
+
+    # ---- TCN at the benchmarked length: (N=4, 1024, L=300), all four dilations cross 128-row tile borders of the flat layout
+    name, N, L, seed = "tcnd_1024_512x4_k5_L300", 4, 300, 211
+    torch.manual_seed(seed)
+    m = R["TCN"](1024, [512] * 4, kernel_size=5, attention=0, dropout=0.1).eval()
+    torch.manual_seed(seed)
+    _check_same_init(jmt_b200.TemporalConvNet(1024, [512] * 4, kernel_size=5, attention=0, dropout=0.1), m, name)
+    x = torch.randn(N, 1024, L, generator=torch.Generator().manual_seed(seed + 1), requires_grad=True)
+    out = m(x)
+    cot = _cot(out.shape, seed + 2)
+    (out * cot).sum().backward()
+    names, l2, s, head = _grad_summary(m)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), out=out.detach().numpy()[:, ::16], out_l2=float(out.norm()),
+                        d_x=x.grad.numpy()[:, ::32], d_x_l2=float(x.grad.norm()), grad_l2=l2, grad_sum=s, grad_head=head)
+    meta[name] = dict(N=N, L=L, init_seed=seed, x_seed=seed + 1, cot_seed=seed + 2, grad_names=names,
+                      out_stride=16, dx_stride=32, param_sums=_param_sums(m))
+    print(name, tuple(out.shape))
+
+    # ---- the benchmarked pipeline (BASELINE.json configs[1] at B=4): TCN -> transpose (I3DWSDDA.py:44) | FcLayer(768,512)
+    #      -> Two_transformers(TRANSFORMER, FC, h=1, L=1) -> live CCC loss (train.py:283-311), forward + backward
+    name, B, T, seed = "piped_b4_t300", 4, 300, 221
+    torch.manual_seed(seed)
+    fusion = R["Two_transformers"](0.0, 0.0, 1, 1, "TRANSFORMER", "FC", 512).eval()
+    fc = R["FcLayer"](768, 512).eval()
+    tcn = R["TCN"](1024, [512] * 4, kernel_size=5, attention=0, dropout=0.1).eval()
+    torch.manual_seed(seed)
+    ours = jmt_b200.JMTPipeline(jmt_b200.Two_transformers(0.0, 0.0, 1, 1, "TRANSFORMER", "FC", 512), jmt_b200.FcLayer(768, 512),
+                                jmt_b200.TemporalConvNet(1024, [512] * 4, kernel_size=5, attention=0, dropout=0.1))
+    _check_same_init(ours.fusion, fusion, name)
+    _check_same_init(ours.fc_audio, fc, name)
+    _check_same_init(ours.tcn, tcn, name)
+    g = torch.Generator().manual_seed(seed + 1)
+    vis = torch.randn(B, 1024, T, generator=g, requires_grad=True)
+    aud = torch.randn(B, T, 768, generator=g, requires_grad=True)
+    lv, la = O.synth_labels(B, T, seed=seed + 2)
+    v, a = fusion(fc(aud), tcn(vis).transpose(1, 2).contiguous())
+    n = v.shape[0] * v.shape[1]
+    loss = live(v.reshape(-1, n), lv.reshape(-1, n)) + live(a.reshape(-1, n), la.reshape(-1, n))
+    mods = {"fusion": fusion, "fc_audio": fc, "tcn": tcn}
+
+    def summary():
+        names, l2, s, head = [], [], [], []
+        for pre, mod in mods.items():
+            nm, a_, b_, c_ = _grad_summary(mod)
+            names += [pre + "." + k for k in nm]
+            l2.append(a_); s.append(b_); head.append(c_)
+        return names, np.concatenate(l2), np.concatenate(s), np.concatenate(head)
+    loss.backward(retain_graph=True)
+    names, l2, s, head = summary()
+    d_aud, d_vis = aud.grad.clone(), vis.grad.clone()
+    for mod in mods.values():
+        mod.zero_grad(set_to_none=True)
+    aud.grad = vis.grad = None
+    cv, ca = _cot(v.shape, seed + 3), _cot(a.shape, seed + 4)
+    torch.autograd.backward([v, a], [cv, ca])
+    names2, l2c, sc, headc = summary()
+    assert names2 == names
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), vout=v.detach().numpy(), aout=a.detach().numpy(),
+                        loss=loss.detach().numpy(), d_aud=d_aud.numpy()[:, :, ::32], d_vis=d_vis.numpy()[:, ::64],
+                        d_aud_l2=float(d_aud.norm()), d_vis_l2=float(d_vis.norm()), grad_l2=l2, grad_sum=s, grad_head=head,
+                        c_d_aud=aud.grad.numpy()[:, :, ::32], c_d_vis=vis.grad.numpy()[:, ::64],
+                        c_d_aud_l2=float(aud.grad.norm()), c_d_vis_l2=float(vis.grad.norm()),
+                        c_grad_l2=l2c, c_grad_sum=sc, c_grad_head=headc)
+    sums = {}
+    for pre, mod in mods.items():
+        sums.update({pre + "." + k: vv for k, vv in _param_sums(mod).items()})
+    meta[name] = dict(B=B, T=T, init_seed=seed, data_seed=seed + 1, label_seed=seed + 2, cot_seeds=[seed + 3, seed + 4],
+                      grad_names=names, out_shape=list(v.shape), aud_stride=32, vis_stride=64, param_sums=sums)
+    print(name, tuple(v.shape), float(loss))
+
+    # ---- intra-modal fusion at BASELINE.json configs[3]'s length: B=2, T=1024 (M = 2*B*T = 4096 rows of L=2 'sequences')
+    name, B, T, seed = "intrad_b2_t1024", 2, 1024, 231
+    torch.manual_seed(seed)
+    m = R["Intra"](512, 1, 512, 1).eval()
+    torch.manual_seed(seed)
+    _check_same_init(jmt_b200.Intra_modal_transformer_fusion(512, 1, 512, 1), m, name)
+    fa, fb = O.synth_features(B, T, [512, 768], seed=seed + 1)
+    fa.requires_grad_(True)
+    fb.requires_grad_(True)
+    out = m(fa, fb)
+    (out * _cot(out.shape, seed + 2)).sum().backward()
+    names, l2, s, head = _grad_summary(m)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), out=out.detach().numpy()[:, :, ::16], out_l2=float(out.norm()),
+                        d_a=fa.grad.numpy()[:, :, ::32], d_b=fb.grad.numpy()[:, :, ::32], d_a_l2=float(fa.grad.norm()),
+                        d_b_l2=float(fb.grad.norm()), grad_l2=l2, grad_sum=s, grad_head=head)
+    meta[name] = dict(B=B, T=T, heads=1, layers=1, init_seed=seed, feat_seed=seed + 1, cot_seed=seed + 2, grad_names=names,
+                      out_stride=16, d_stride=32, param_sums=_param_sums(m))
+    print(name, tuple(out.shape))
+
+
 def main():
     torch.set_num_threads(8)
     R = _import_reference()
@@ -282,6 +445,7 @@ def main():
     gen_intra(R, meta)
     gen_tcn(R, meta)
     gen_misc(R, meta)
+    gen_default_init(R, meta)
     meta["_generator"] = dict(torch=torch.__version__, numpy=np.__version__, reference=REF)
     with open(os.path.join(HERE, "golden_meta.json"), "w") as f:
         json.dump(meta, f, indent=1)

@@ -35,9 +35,15 @@ def _rl2(a, b):
 # tolerances: fp32-operand mode is the north-star 1e-3 gate; bf16-operand mode is stated separately
 # (bf16 bounds are ~1.5x the worst deltas measured on B200 with the deliberately "hot" synthetic weights of
 #  oracle.synth_params -- 1.5/sqrt(fan_in) -- see DESIGN.md "Numerics"; default-init weights give ~1e-2.)
-PRED_TOL = {"fp32": 1e-3, "bf16": 1.5e-1}     # max-abs relative on predictions / features
-PRED_L2 = {"fp32": 5e-4, "bf16": 8e-2}
-GRAD_L2 = {"fp32": 2e-3, "bf16": 3e-1}
+# 'bf16x3' = the tensor-core mode that must meet the north-star gate (three tcgen05.mma per k-step on hi/lo split operands);
+# 'fp32' (FFMA kernel) is kept as an independent cross-check with the same bounds
+PRED_TOL = {"bf16x3": 1e-3, "fp32": 1e-3, "bf16": 1.5e-1}     # max-abs relative on predictions / features
+PRED_L2 = {"bf16x3": 5e-4, "fp32": 5e-4, "bf16": 8e-2}
+# gradients through the CCC loss of the tiny golden cases (B*T = 18..80 predictions) are ill-conditioned (nearly constant
+# cotangent -> cancelling terms amplify operand rounding ~200x): bf16x3 (2^-16 operands) measured 4.0e-3 worst
+# (tt_transformer_fc_h4_l2), the fp32 FFMA cross-check 3e-5; well-conditioned cotangents are tested on the *_default cases
+GRAD_L2 = {"bf16x3": 6e-3, "fp32": 2e-3, "bf16": 3e-1}
+GATE = ("bf16x3", "fp32")
 
 
 def _load(module, params):
@@ -62,7 +68,7 @@ def _grad_summary(module, names):
     return np.array(l2), np.stack(head)
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("precision", ["bf16x3", "fp32", "bf16"])
 @pytest.mark.parametrize("name", TT_NAMES)
 def test_two_transformers(name, precision, golden_meta, golden_dir):
     m = golden_meta[name]
@@ -84,7 +90,7 @@ def test_two_transformers(name, precision, golden_meta, golden_dir):
     crit = jmt_b200.CCCLoss(digitize_num=1)
     n = v.shape[0] * v.shape[1]
     loss = crit(v.view(-1, n), lv.to(DEV).view(-1, n)) + crit(a.view(-1, n), la.to(DEV).view(-1, n))
-    ltol = 1e-4 if precision == "fp32" else 3e-2
+    ltol = 1e-4 if precision in GATE else 3e-2
     assert abs(loss.item() - float(g["loss"])) < ltol, (loss.item(), float(g["loss"]))
     gtol = GRAD_L2[precision]
     if precision == "bf16":
@@ -114,7 +120,7 @@ def test_two_transformers(name, precision, golden_meta, golden_dir):
     l2, head = _grad_summary(model, m["grad_names"])
     rel_l2 = np.abs(l2 - want_l2) / (want_l2 + 1e-12)
     assert rel_l2.max() < gtol * 2, (m["grad_names"][int(rel_l2.argmax())], rel_l2.max())
-    if precision == "fp32":
+    if precision in GATE:
         for i, nme in enumerate(m["grad_names"]):
             sc = np.abs(g["grad_head"][i]).max() + 1e-9
             assert np.abs(head[i] - g["grad_head"][i]).max() < 5e-3 * max(sc, g["grad_l2"][i] / 50), nme
@@ -124,7 +130,7 @@ def test_two_transformers(name, precision, golden_meta, golden_dir):
             assert p.grad is None, nme
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("precision", ["bf16x3", "fp32", "bf16"])
 def test_c1_config(precision, golden_meta, golden_dir):
     """BASELINE.json configs[0]: FcLayer(768,512) + Two_transformers(TRANSFORMER, FC), B=8, T=300."""
     m = golden_meta["c1_b8_t300"]
@@ -144,10 +150,10 @@ def test_c1_config(precision, golden_meta, golden_dir):
     lv, _ = O.synth_labels(m["B"], m["T"], 5)
     c_ref = O.ccc_metric(g["vout"].reshape(-1).astype(np.float64), lv.numpy().reshape(-1).astype(np.float64))
     c_new = jmt_b200.cccmetric.ccc(v.reshape(-1), lv.to(DEV).reshape(-1))
-    assert abs(c_ref - c_new) < (1e-4 if precision == "fp32" else 1e-2), (c_ref, c_new)
+    assert abs(c_ref - c_new) < (1e-4 if precision in GATE else 1e-2), (c_ref, c_new)
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("precision", ["bf16x3", "fp32", "bf16"])
 @pytest.mark.parametrize("name", ["intra_512_768_h2", "intra_512_512_h1_l2"])
 def test_intra_modal(name, precision, golden_meta, golden_dir):
     m = golden_meta[name]
@@ -166,7 +172,7 @@ def test_intra_modal(name, precision, golden_meta, golden_dir):
     assert (np.abs(l2 - g["grad_l2"]) / (g["grad_l2"] + 1e-12)).max() < gtol * 2
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("precision", ["bf16x3", "fp32", "bf16"])
 @pytest.mark.parametrize("name", ["tcn_1024_512x4_k5_L7", "tcn_1024_512x4_k5_L40", "tcn_16_8x2_k3_L19"])
 def test_tcn(name, precision, golden_meta, golden_dir):
     m = golden_meta[name]
@@ -348,7 +354,7 @@ def test_graphed_step_matches_eager():
     assert num / den < 1e-3, num / den
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("precision", ["bf16x3", "fp32", "bf16"])
 def test_tcn_sequence_features_and_time_max(precision, golden_meta, golden_dir):
     """temporal(x).transpose(1,2) (I3DWSDDA.py:44) and the fused torch.max(ft, 1) (tsav.py:216) on the
     reference-faithful placement (many clips of L = 7), against the golden TCN output of the reference."""
@@ -376,7 +382,7 @@ def test_tcn_sequence_features_and_time_max(precision, golden_meta, golden_dir):
     seq2 = model.forward_sequence_features(xd)
     am = seq2.detach().argmax(1, keepdim=True)
     (seq2.gather(1, am).squeeze(1) * w).sum().backward()
-    assert _rl2(g_pool.cpu(), xd.grad.cpu()) < (1e-4 if precision == "fp32" else 3e-2)
+    assert _rl2(g_pool.cpu(), xd.grad.cpu()) < (1e-4 if precision in GATE else 3e-2)
 
 
 def test_full_size_properties():
@@ -422,7 +428,7 @@ def test_full_size_properties():
     assert abs(jmt_b200.cccmetric.ccc(xc, -xc) + 1.0) < 1e-4
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("precision", ["bf16x3", "fp32", "bf16"])
 @pytest.mark.parametrize("B,T,heads,joint,fmt", [(1, 1, 8, "TRANSFORMER", "FC"), (1, 2, 1, "TRANSFORMER", "SELF_ATTEN"),
                                                  (3, 1, 2, "NONE", "FC"), (1, 5, 4, "FC", "FC")])
 def test_degenerate_shapes_against_oracle(B, T, heads, joint, fmt, precision):
@@ -438,10 +444,10 @@ def test_degenerate_shapes_against_oracle(B, T, heads, joint, fmt, precision):
     ad, vd = aud.to(DEV).requires_grad_(True), vis.to(DEV).requires_grad_(True)
     v, a = model(ad, vd)
     assert tuple(v.shape) == tuple(vo.shape)
-    tol = 1e-3 if precision == "fp32" else PRED_TOL["bf16"]
+    tol = 1e-3 if precision in GATE else PRED_TOL["bf16"]
     assert _rel(v.detach().cpu(), vo.detach()) < tol and _rel(a.detach().cpu(), aout.detach()) < tol
     (v.sum() + 2 * a.sum()).backward()
-    gt = 2e-3 if precision == "fp32" else GRAD_L2["bf16"]
+    gt = 2e-3 if precision in GATE else GRAD_L2["bf16"]
     assert _rl2(ad.grad.cpu(), ao.grad) < gt and _rl2(vd.grad.cpu(), vo_in.grad) < gt
 
 
