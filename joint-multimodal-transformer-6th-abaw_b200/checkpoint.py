@@ -75,3 +75,13 @@ def load_models_from_disk(path: str, modules: Dict[str, Optional[torch.nn.Module
             scaler.load_state_dict(st["scaler"])
         info = {"epoch": st["epoch"], "extra": st.get("extra", {})}
     return info
+
+
+def extract_submodule_state(state_dict: "Dict[str, torch.Tensor]", prefix: str) -> "OrderedDict[str, torch.Tensor]":
+    """Keys under `prefix` with the prefix removed -- e.g. the TCN head out of a reference `vision_i3d.pt`
+    (main.py:157-159 saves the whole I3D_WSDDA, whose TemporalConvNet lives under `temporal.`, I3DWSDDA.py:26-28):
+        tcn.load_state_dict(extract_submodule_state(load_clean_weights(".../vision_i3d.pt"), "temporal."), strict=True)"""
+    out = OrderedDict((k[len(prefix):], v) for k, v in state_dict.items() if k.startswith(prefix))
+    if not out:
+        raise KeyError(f"no key starts with {prefix!r}")
+    return out

@@ -1,10 +1,11 @@
 """TEST INFRASTRUCTURE ONLY (CPU oracle) -- restatement of the reference's validation post-processing,
 val.py:313-382, for checking jmt_b200.valpost.  Nothing in the product imports this file.
 
-Parity pinning: the reference code is a fragment of the monolithic `validate()` (it needs data loaders and
-models), so it cannot be imported in isolation; the restatement below follows it line by line, uses the same
-third-party call (scipy.ndimage.uniform_filter1d, the dependency the reference calls at val.py:365-366) and is
-additionally checked against an explicit box-filter loop in tests/test_valpost_cpu.py.
+Parity pinning: PINNED to the reference's own lines.  `validate()` is monolithic (data loaders, backbones), so the fragment
+cannot be imported -- tests/golden/make_valpost_golden.py slices val.py:69-79, 313-357 and 359-382 out of the reference source
+at run time, exec()s them on synthetic batches and stores inputs + results as tests/golden/valpost_seed*.npz;
+tests/test_valpost_cpu.py checks this restatement against those files (and against an explicit box-filter loop), and
+tests/test_valpost_gpu.py checks the device implementation against the same files.
 """
 import numpy as np
 from scipy.ndimage import uniform_filter1d

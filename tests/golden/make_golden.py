@@ -435,6 +435,49 @@ def gen_default_init(R, meta):
     print(name, tuple(out.shape))
 
 
+def reference_checkpoint_functions():
+    """The reference's own checkpoint writer / reader, main.py:54-70 (`load_clean_weights`) and main.py:105-177
+    (`dump_models_into_disk`), compiled from the reference source at run time (main.py as a whole imports the data loaders,
+    dllogger configuration etc. and cannot be imported here); their helpers come from the importable tools.py."""
+    import ast
+    from collections import OrderedDict
+    from os.path import join
+    _install_stubs()
+    sys.modules["matplotlib.ticker"] = types.ModuleType("matplotlib.ticker")
+    sys.modules["matplotlib.ticker"].MaxNLocator = object
+    sys.path.insert(0, REF)
+    import tools as ref_tools
+    src = open(os.path.join(REF, "main.py")).read()
+    tree = ast.parse(src)
+    want = {"load_clean_weights", "dump_models_into_disk", "get_state_dict"}
+    fns = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in want]
+    assert {f.name for f in fns} == want, [f.name for f in fns]
+
+    class _Log:
+        @staticmethod
+        def log(*a, **k):
+            pass
+    ns = {"torch": torch, "OrderedDict": OrderedDict, "join": join, "DLLogger": _Log, "MyDataParallel": ref_tools.MyDataParallel,
+          "state_dict_to_cpu": ref_tools.state_dict_to_cpu, "state_dict_to_gpu": ref_tools.state_dict_to_gpu}
+    exec(compile(ast.Module(body=fns, type_ignores=[]), os.path.join(REF, "main.py"), "exec"), ns)
+    return ns["dump_models_into_disk"], ns["load_clean_weights"]
+
+
+def gen_checkpoint(R, meta):
+    """A checkpoint written by the REFERENCE's dump_models_into_disk (main.py:105-177) from a reference module: the small
+    `backbone_pretrainer_w.pt` (SingleBackbonePretrainer with the weights of the `single_backbone` golden) is committed so that
+    the GPU box can load it strict=True into the drop-in and reproduce the golden outputs."""
+    dump, _ = reference_checkpoint_functions()
+    shapes = O._regressor_shapes("regressor.", 512, 2)
+    m = R["SingleBackbonePretrainer"](0.0, 0.0)
+    m.load_state_dict(O.synth_params(shapes, seed=61), strict=True)
+    out = os.path.join(HERE, "ckpt_ref")
+    os.makedirs(out, exist_ok=True)
+    dump({}, None, m, None, None, None, None, 3, out)
+    assert os.listdir(out) == ["backbone_pretrainer_w.pt"], os.listdir(out)
+    meta["ckpt_ref"] = dict(file="ckpt_ref/backbone_pretrainer_w.pt", param_seed=61, golden="single_backbone")
+
+
 def main():
     torch.set_num_threads(8)
     R = _import_reference()
@@ -446,6 +489,7 @@ def main():
     gen_tcn(R, meta)
     gen_misc(R, meta)
     gen_default_init(R, meta)
+    gen_checkpoint(R, meta)
     meta["_generator"] = dict(torch=torch.__version__, numpy=np.__version__, reference=REF)
     with open(os.path.join(HERE, "golden_meta.json"), "w") as f:
         json.dump(meta, f, indent=1)

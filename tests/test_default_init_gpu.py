@@ -25,7 +25,6 @@ from oracle import jmt_oracle as O  # noqa: E402
 
 DEV = "cuda"
 PRECISIONS = ["bf16x3", "fp32", "bf16"]
-GATE = ("bf16x3", "fp32")
 MEASURED = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "parity_measured.jsonl")
 
 
@@ -49,10 +48,10 @@ def _record(name, precision, vals):
 
 
 def _check(name, precision, vals, bounds):
-    """vals: measured deltas; bounds: {metric: {precision-class: bound}}.  Everything is recorded, then asserted."""
+    """vals: measured deltas; bounds: {metric: (bf16x3, fp32, bf16)}.  Everything is recorded, then asserted."""
     _record(name, precision, vals)
-    cls = "gate" if precision in GATE else "bf16"
-    bad = {k: (v, bounds[k][cls]) for k, v in vals.items() if k in bounds and not v < bounds[k][cls]}
+    i = PRECISIONS.index(precision)
+    bad = {k: (v, bounds[k][i]) for k, v in vals.items() if k in bounds and not v < bounds[k][i]}
     assert not bad, (name, precision, bad)
 
 
@@ -65,41 +64,48 @@ def _check_sums(module, sums, prefix=""):
         assert abs(float(sd[kk].double().sum()) - s) <= 1e-6 * max(1.0, abs(s)), f"seeded init differs from the reference: {k}"
 
 
-def _grad_l2(module, names, prefix=""):
+def _grad_l2(module, names):
+    """per-parameter gradient L2 norms, first 8 entries and element counts"""
     named = dict(module.named_parameters())
-    out, head = [], []
+    out, head, numel = [], [], []
     for n in names:
-        g = named[n[len(prefix):] if prefix and n.startswith(prefix) else n].grad
+        g = named[n].grad
         assert g is not None, n
         g = g.detach().double().reshape(-1).cpu()
         out.append(float(g.norm()))
+        numel.append(g.numel())
         h = np.zeros(8)
         h[: min(8, g.numel())] = g[:8].numpy()
         head.append(h)
-    return np.array(out), np.stack(head)
+    return np.array(out), (np.stack(head), np.array(numel))
 
 
-def _grad_metrics(l2, head, want_l2, want_head):
-    """worst relative deviation of the per-parameter gradient norms and of the first 8 entries (relative to the larger of
-    the head's magnitude and the tensor's rms)."""
+def _grad_metrics(l2, head_numel, want_l2, want_head):
+    """worst relative deviation of the per-parameter gradient norms, and of the first 8 entries of every gradient relative
+    to the larger of their own magnitude and the tensor's rms (a head of ~zeros must not blow the ratio up)."""
+    head, numel = head_numel
     rel_l2 = float((np.abs(l2 - want_l2) / (want_l2 + 1e-30)).max())
     worst = 0.0
     for i in range(len(want_l2)):
-        sc = max(np.abs(want_head[i]).max(), 1e-30)
+        sc = max(np.abs(want_head[i]).max(), want_l2[i] / np.sqrt(numel[i]), 1e-30)
         worst = max(worst, float(np.abs(head[i] - want_head[i]).max() / sc))
     return rel_l2, worst
 
 
-# bounds: measured on B200 (round 2) in the comment, bound <= 1.5x measured (gate class = max over bf16x3 / fp32)
+# Bounds per precision (bf16x3, fp32, bf16), each <= ~1.5-2x the worst value measured on B200 in round 2 (in the comment);
+# pred_rel / ccc_delta of the gate precisions stay at the north-star numbers (1e-3 / 1e-4) they have to meet.
+# Gradient deltas of the gate precisions are dominated by single ReLU / LeakyReLU sign decisions on pre-activations that are ~0
+# (an O(1) change of a few entries), input gradients of bf16 by the cancellation in the F.normalize backward
+# (dx = r (dy - y (y.dy)) on bf16-rounded dy).
 TT_BOUNDS = {
-    "pred_rel": {"gate": 1e-3, "bf16": 2.5e-2},
-    "pred_l2": {"gate": 5e-4, "bf16": 1.5e-2},
-    "loss": {"gate": 1e-4, "bf16": 5e-3},
-    "ccc_delta": {"gate": 1e-4, "bf16": 5e-3},
-    "c_din_l2": {"gate": 2e-3, "bf16": 5e-2},
-    "c_grad_l2": {"gate": 2e-3, "bf16": 5e-2},
-    "live_din_l2": {"gate": 6e-3, "bf16": 1e9},
-    "live_grad_l2": {"gate": 6e-3, "bf16": 1e9},
+    "pred_rel": (1e-3, 1e-3, 3.5e-2),        # 1.9e-5   2.2e-6   2.3e-2 (SELF_ATTEN h2; 1.6e-3 .. 9.6e-3 elsewhere)
+    "pred_l2": (5e-5, 5e-6, 2.1e-2),         # 1.6e-5   1.5e-6   1.4e-2
+    "loss": (1e-5, 1e-5, 2.5e-4),            # 4.8e-7   1.2e-7   1.5e-4
+    "ccc_delta": (1e-4, 1e-4, 1e-4),         # 3.5e-7   7.9e-9   6.1e-5   <- plain bf16 meets the 1e-4 CCC gate on default init
+    "c_din_l2": (2e-3, 1e-3, 1.5e-1),        # 1.2e-3   3.8e-4   9.8e-2
+    "c_grad_l2": (2e-4, 2e-4, 3.2e-2),       # 8.5e-5   6.8e-5   2.1e-2
+    "live_din_l2": (1e-3, 1e-3, 2e-1),       # 2.5e-4   2.5e-4   1.3e-1
+    "live_grad_l2": (3e-3, 3e-3, 1e-1),      # 1.1e-3   9.2e-4   6.1e-2
 }
 TT_DEFAULT = ["ttd_transformer_fc_h1", "ttd_transformer_sa_h2", "ttd_fc_fc", "ttd_none_fc_h2", "ttd_none_fc_b300_t2",
               "ttd_none_fc_b400_t2", "ttd_none_fc_b600_t1_h2"]
@@ -154,8 +160,12 @@ def test_two_transformers_default_init(name, precision, golden_meta, golden_dir)
     _check(name, precision, vals, TT_BOUNDS)
 
 
-TCN_BOUNDS = {"out_rel": {"gate": 1e-3, "bf16": 3e-2}, "out_l2": {"gate": 5e-4, "bf16": 1.5e-2},
-              "dx_l2": {"gate": 2e-3, "bf16": 3e-2}, "grad_l2": {"gate": 2e-3, "bf16": 3e-2}}
+TCN_BOUNDS = {
+    "out_rel": (1e-3, 1e-3, 1e-2),           # 8.4e-6   1.1e-6   6.8e-3
+    "out_l2": (3e-5, 3e-6, 6e-3),            # 9.4e-6   6.1e-7   3.9e-3
+    "dx_l2": (3e-3, 2e-3, 6.5e-2),           # 1.7e-3   1.0e-3   4.3e-2
+    "grad_l2": (1e-3, 6e-4, 1e-2),           # 4.4e-4   2.6e-4   6.5e-3
+}
 
 
 @pytest.mark.parametrize("precision", PRECISIONS)
@@ -182,10 +192,14 @@ def test_tcn_L300_default_init(precision, golden_meta, golden_dir):
 
 
 PIPE_BOUNDS = {
-    "pred_rel": {"gate": 1e-3, "bf16": 3e-2}, "pred_l2": {"gate": 5e-4, "bf16": 2e-2},
-    "loss": {"gate": 1e-4, "bf16": 5e-3}, "ccc_delta": {"gate": 1e-4, "bf16": 5e-3},
-    "c_din_l2": {"gate": 2e-3, "bf16": 6e-2}, "c_grad_l2": {"gate": 2e-3, "bf16": 6e-2},
-    "live_din_l2": {"gate": 6e-3, "bf16": 1e9}, "live_grad_l2": {"gate": 6e-3, "bf16": 1e9},
+    "pred_rel": (1e-3, 1e-3, 1.8e-2),        # 2.4e-5   2.6e-6   1.2e-2
+    "pred_l2": (3e-5, 5e-6, 8.5e-3),         # 8.5e-6   1.0e-6   5.5e-3
+    "loss": (1e-5, 1e-5, 1e-5),              # 0        0        2.0e-6
+    "ccc_delta": (1e-4, 1e-4, 1e-5),         # 5.8e-9   3.4e-9   1.8e-6
+    "c_din_l2": (2e-3, 5e-4, 1.2e-1),        # 1.1e-3   2.0e-4   7.6e-2
+    "c_grad_l2": (5e-4, 1e-4, 2.6e-2),       # 2.4e-4   4.3e-5   1.7e-2
+    "live_din_l2": (2e-3, 2e-3, 1.5e-1),     # 8.7e-4   7.3e-4   1.0e-1
+    "live_grad_l2": (1e-2, 3e-3, 5.5e-1),    # 5.9e-3   1.2e-3   3.6e-1  (CCC cotangent: nearly constant, cancelling terms)
 }
 
 
@@ -239,8 +253,12 @@ def test_pipeline_b4_t300_default_init(precision, golden_meta, golden_dir):
     _check(name, precision, vals, PIPE_BOUNDS)
 
 
-INTRA_BOUNDS = {"out_rel": {"gate": 1e-3, "bf16": 3e-2}, "out_l2": {"gate": 5e-4, "bf16": 1.5e-2},
-                "din_l2": {"gate": 2e-3, "bf16": 4e-2}, "grad_l2": {"gate": 2e-3, "bf16": 4e-2}}
+INTRA_BOUNDS = {
+    "out_rel": (1e-3, 1e-3, 7.5e-3),         # 8.1e-6   8.7e-7   4.8e-3
+    "out_l2": (3e-5, 3e-6, 8e-3),            # 8.7e-6   8.1e-7   5.4e-3
+    "din_l2": (1e-4, 5e-6, 2e-2),            # 3.0e-5   1.0e-6   1.3e-2
+    "grad_l2": (3e-5, 5e-7, 2.2e-3),         # 8.3e-6   7.9e-8   1.4e-3
+}
 
 
 @pytest.mark.parametrize("precision", PRECISIONS)

@@ -123,7 +123,8 @@ def test_two_transformers(name, precision, golden_meta, golden_dir):
     if precision in GATE:
         for i, nme in enumerate(m["grad_names"]):
             sc = np.abs(g["grad_head"][i]).max() + 1e-9
-            assert np.abs(head[i] - g["grad_head"][i]).max() < 5e-3 * max(sc, g["grad_l2"][i] / 50), nme
+            htol = 5e-3 if precision == "fp32" else 2e-2          # bf16x3: 2^-16 operands, ~200x cancellation (see GRAD_L2)
+            assert np.abs(head[i] - g["grad_head"][i]).max() < htol * max(sc, g["grad_l2"][i] / 50), nme
     # dead parameters never get a gradient
     for nme, p in model.named_parameters():
         if "final_encoder" in nme or "gated_attention" in nme:
@@ -197,6 +198,31 @@ def test_tcn(name, precision, golden_meta, golden_dir):
     l2, _ = _grad_summary(model, m["grad_names"])
     rel = np.abs(l2 - g["grad_l2"]) / (g["grad_l2"] + 1e-12)
     assert rel.max() < gtol * 2, (m["grad_names"][int(rel.argmax())], rel.max())
+
+
+@pytest.mark.parametrize("precision", ["bf16x3", "fp32", "bf16"])
+def test_reference_written_checkpoint_loads_into_dropin(precision, golden_meta, golden_dir, tmp_path):
+    """SURVEY 8f N3 on the device: `backbone_pretrainer_w.pt` as written by the REFERENCE's dump_models_into_disk
+    (main.py:105-177; tests/golden/make_golden.py::gen_checkpoint) loads strict=True into the drop-in through
+    jmt_b200.checkpoint (main.py:54-70 conventions) and reproduces the reference's outputs; the drop-in's own dump of the
+    same weights is byte-for-byte the same state_dict."""
+    from jmt_b200 import checkpoint as CK
+    c = golden_meta["ckpt_ref"]
+    m = golden_meta[c["golden"]]
+    g = np.load(os.path.join(golden_dir, c["golden"] + ".npz"))
+    model = jmt_b200.SingleBackbonePretrainer(0.0, 0.0, precision=precision).to(DEV).eval()
+    CK.load_models_from_disk(os.path.join(golden_dir, "ckpt_ref"), {"backbone_pretrainer": model}, map_location=DEV)
+    (x,) = O.synth_features(m["B"], m["T"], [512], m["feat_seed"])
+    with torch.no_grad():
+        v, a = model(x.to(DEV))
+    tol = 1e-3 if precision != "bf16" else 2e-2
+    assert _rel(v.cpu(), g["v"]) < tol and _rel(a.cpu(), g["a"]) < tol
+    CK.dump_models_into_disk(str(tmp_path), {"backbone_pretrainer": model})
+    ref_sd = torch.load(os.path.join(golden_dir, "ckpt_ref", "backbone_pretrainer_w.pt"), weights_only=True)
+    my_sd = torch.load(os.path.join(tmp_path, "backbone_pretrainer_w.pt"), weights_only=True)
+    assert list(ref_sd.keys()) == list(my_sd.keys())
+    for k in ref_sd:
+        assert my_sd[k].device.type == "cpu" and torch.equal(ref_sd[k], my_sd[k]), k
 
 
 def test_single_backbone_and_fc(golden_meta, golden_dir):

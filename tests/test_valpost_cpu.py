@@ -1,6 +1,10 @@
-"""CPU tests of the validation post-processing oracle (val.py:313-382 restatement) against an independent
-explicit implementation (box filter written out, last-writer-wins by construction)."""
+"""CPU tests of the validation post-processing oracle (val.py:313-382 restatement): pinned to what the reference's own
+lines computed (tests/golden/valpost_seed*.npz, written by tests/golden/make_valpost_golden.py, which exec()s the fragment
+of /root/reference/val.py) and to an independent explicit implementation (box filter written out, last writer wins)."""
+import os
+
 import numpy as np
+import pytest
 
 from oracle import val_post_oracle as VO
 
@@ -72,3 +76,21 @@ def test_ignored_and_out_of_range_frames_stay_zero():
                 # the last batch is the last writer of every frame it touches (later t / b within it may overwrite)
                 assert lv[k][fid[b, t] - 1] in labv[vid == k]
     assert all(len(sv[k]) == lengths[k] for k in sv)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_oracle_matches_reference_val_py_fragment(seed, golden_dir):
+    """The restatement vs the REFERENCE's lines val.py:313-382 executed on the same synthetic batches."""
+    g = np.load(os.path.join(golden_dir, f"valpost_seed{seed}.npz"))
+    batches = [(g["v"][i], g["a"][i], g["lv"][i], g["la"][i], g["fid"][i], g["vid"][i]) for i in range(g["v"].shape[0])]
+    lengths = g["lengths"]
+    _, _, label_v, label_a, sm_v, sm_a = VO.val_postprocess(batches, lengths, 20, 50)
+    order = g["first_seen"].tolist()              # the reference concatenates videos in first-seen order (dict order)
+    vout = np.concatenate([sm_v[k] for k in order])
+    aout = np.concatenate([sm_a[k] for k in order])
+    vtar = np.concatenate([np.asarray(label_v[k], dtype=np.float64) for k in order])
+    atar = np.concatenate([np.asarray(label_a[k], dtype=np.float64) for k in order])
+    assert np.abs(vout - g["vout"]).max() < 1e-6 and np.abs(aout - g["aout"]).max() < 1e-6
+    assert np.array_equal(vtar, g["vtar"]) and np.array_equal(atar, g["atar"])
+    accv, acca, _, _ = VO.val_ccc(batches, lengths, 20, 50)
+    assert abs(accv - float(g["accV"])) < 1e-7 and abs(acca - float(g["accA"])) < 1e-7

@@ -92,3 +92,25 @@ def test_feature_shard_loader(tmp_path):
             want_l.append(alll[k][lo:lo + nfull])
         assert torch.equal(torch.cat(got_v), torch.cat(want_v))
         assert torch.equal(torch.cat(got_l), torch.cat(want_l))
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_valpost_matches_reference_val_py_fragment(seed, golden_dir):
+    """jmt_b200.valpost on the device vs what the reference's own lines (val.py:313-382, exec()'d by
+    tests/golden/make_valpost_golden.py) computed from the same batches: smoothed predictions, labels, accV / accA."""
+    import os
+    g = np.load(os.path.join(golden_dir, f"valpost_seed{seed}.npz"))
+    lengths = g["lengths"]
+    acc = jmt_b200.valpost.ValPostprocessor(lengths.tolist())
+    for i in range(g["v"].shape[0]):
+        acc.update(*(torch.from_numpy(g[k][i]).cuda() for k in ("v", "a", "lv", "la", "fid", "vid")))
+    accv, acca, sv, sa = acc.finalize(return_smoothed=True)
+    assert abs(accv - float(g["accV"])) < 1e-5 and abs(acca - float(g["accA"])) < 1e-5
+    off = np.concatenate([[0], np.cumsum(lengths)])
+    order = g["first_seen"].tolist()              # reference output order = first-seen order of the videos
+    sv, sa = sv.cpu().numpy(), sa.cpu().numpy()
+    got_v = np.concatenate([sv[off[k]:off[k + 1]] for k in order])
+    got_a = np.concatenate([sa[off[k]:off[k + 1]] for k in order])
+    assert np.abs(got_v - g["vout"]).max() < 2e-6 and np.abs(got_a - g["aout"]).max() < 2e-6
+    lab_v = acc.label_v.cpu().numpy()
+    assert np.array_equal(np.concatenate([lab_v[off[k]:off[k + 1]] for k in order]).astype(np.float64), g["vtar"])
