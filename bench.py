@@ -4,7 +4,7 @@
     python bench.py --gpus 1 --steps 10 --warmup 3
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \\
         bench.py --gpus N --steps K --warmup W
-    python bench.py --impl reference ...        # the reference algorithm's CPU port on the host cores
+    python bench.py --impl reference ...        # the reference's own modules (oracle/_ref) on the host cores
 
 Workload (BASELINE.json configs[1], SURVEY.md 8d "C2"): one training step of
     TemporalConvNet(1024,[512]*4,k=5) on visual (B,1024,T)  +  FcLayer(768,512) on audio (B,T,768)
@@ -40,9 +40,11 @@ def parse():
     ap.add_argument("--impl", default="jmt", choices=["jmt", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="windows per GPU")
     ap.add_argument("--seq", type=int, default=300)
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3", "fp32"])
     ap.add_argument("--heads", type=int, default=1)
-    ap.add_argument("--cpu-sample", type=int, default=4, help="windows in the CPU-baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=32, help="windows per step of the CPU baseline / reference arm")
+    ap.add_argument("--no-parity", action="store_true", help="skip the in-process parity record (pred_rel / ccc_delta)")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling sub-record of a multi-GPU run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -53,10 +55,10 @@ def parse():
     return ap.parse_args()
 
 
-# --------------------------------------------------------------------------------------- CPU port
+# --------------------------------------------------------------------------------------- CPU arms
 def cpu_port_step(B, T, heads, threads, seed=0):
     """One fwd+bwd of the same pipeline through the CPU oracle (the reference algorithm restated with plain
-    torch CPU ops, fp32, all host threads).  Returns (seconds, windows)."""
+    torch CPU ops, fp32, all host threads).  Returns (seconds, windows).  Fallback when oracle/_ref is absent."""
     from oracle import jmt_oracle as O
     torch.set_num_threads(threads)
     gen = torch.Generator().manual_seed(seed)
@@ -75,41 +77,117 @@ def cpu_port_step(B, T, heads, threads, seed=0):
     return time.perf_counter() - t0, B
 
 
+class ReferenceCpuStep:
+    """The REFERENCE'S OWN modules (oracle/_ref, see oracle/make_ref.py) running the benchmarked training step on the host
+    cores: TemporalConvNet(1024,[512]*4,k=5) -> transpose (I3DWSDDA.py:44) | FcLayer(768,512) -> Two_transformers(TRANSFORMER,
+    FC) -> live CCC loss (train.py:283-311) -> backward -> SGD step, fp32, training mode, stock code path
+    (nn.MultiheadAttention with need_weights=True and all)."""
+
+    def __init__(self, heads, threads):
+        from oracle import make_ref
+        R = make_ref.import_reference()
+        torch.set_num_threads(threads)
+        torch.manual_seed(0)
+        self.fusion = R["Two_transformers"](0.0, 0.0, heads, 1, "TRANSFORMER", "FC", 512).train()
+        self.fc = R["FcLayer"](768, 512).train()
+        self.tcn = R["TemporalConvNet"](1024, [512] * 4, kernel_size=5, attention=0, dropout=0.1).train()
+        self.crit = R["live_loss"]
+        params = [p for m in (self.fusion, self.fc, self.tcn) for p in m.parameters()]
+        self.opt = torch.optim.SGD(params, lr=1e-3)
+
+    def __call__(self, B, T, seed=0):
+        gen = torch.Generator().manual_seed(seed)
+        vis = torch.randn(B, 1024, T, generator=gen)
+        aud = torch.randn(B, T, 768, generator=gen)
+        lv = torch.rand(B, T, generator=gen) * 2 - 1
+        la = torch.rand(B, T, generator=gen) * 2 - 1
+        n = B * T
+        t0 = time.perf_counter()
+        vfeat = self.tcn(vis).transpose(1, 2).contiguous()
+        v, a = self.fusion(self.fc(aud), vfeat)
+        loss = self.crit(v.reshape(-1, n), lv.reshape(-1, n)) + self.crit(a.reshape(-1, n), la.reshape(-1, n))
+        self.opt.zero_grad(set_to_none=True)
+        loss.backward()
+        self.opt.step()
+        return time.perf_counter() - t0, B
+
+
+def make_cpu_arm(heads, threads):
+    """(callable(B, T) -> (seconds, windows), kind, description)"""
+    from oracle import make_ref
+    if make_ref.available():
+        return ReferenceCpuStep(heads, threads), "reference", "the reference's own modules from oracle/_ref (fp32, torch CPU)"
+    return (lambda B, T: cpu_port_step(B, T, heads, threads)), "port", "oracle/jmt_oracle.py (restatement; oracle/_ref absent)"
+
+
 def run_reference(args):
-    """Reference arm: the reference's own CPU path cannot travel to the GPU box (/root/reference is absent
-    there), so this times its restatement (oracle port, same torch CPU kernels underneath) on all host cores."""
+    """Reference arm: the reference's own CPU implementation of the path on the box's host cores, on my arm's config /
+    metric / unit; each step is a bounded sample (--cpu-sample windows) of the 256-window workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
     B = args.cpu_sample
-    for _ in range(min(args.warmup, 1)):
-        cpu_port_step(B, args.seq, args.heads, cores)
+    arm, kind, what = make_cpu_arm(args.heads, cores)
+    for _ in range(args.warmup):
+        arm(B, args.seq)
     times = []
     for _ in range(args.steps):
-        dt, _ = cpu_port_step(B, args.seq, args.heads, cores)
+        dt, _ = arm(B, args.seq)
         times.append(dt)
-        if sum(times) > 150:
+        if sum(times) > 240:
             break
     med = float(np.median(times))
     val = B / med
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "windows/s", "n_gpus": args.gpus,
-            "steps": len(times), "warmup": min(args.warmup, 1), "ms_per_step": med * 1e3, "higher_is_better": True,
+            "steps": len(times), "warmup": args.warmup, "ms_per_step": med * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, sample=B),
-            "cpu_baseline": {"value": val, "unit": "windows/s", "cores": cores, "kind": "port",
-                             "sample": f"{B} windows x T={args.seq}, fwd+bwd, fp32, torch CPU ops via oracle/jmt_oracle.py"},
+            "config": workload_config(args),
+            "cpu_baseline": {"value": val, "unit": "windows/s", "cores": cores, "kind": kind,
+                             "sample": f"{B} windows x T={args.seq} per step (bounded sample of the {args.batch}-window step), "
+                                       f"fwd+bwd+SGD, fp32, {what}, median of {len(times)} steps"},
             "e2e": {"value": val, "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
-def workload_config(args, sample=None):
+def workload_config(args):
     return {"workload": "C2: TCN(1024,[512]*4,k=5)+FcLayer(768,512)+Two_transformers(TRANSFORMER,FC,h=%d,L=1)+CCC train step" % args.heads,
-            "windows_per_gpu": sample if sample is not None else args.batch, "seq_len": args.seq,
-            "global_windows": (sample if sample is not None else args.batch * args.gpus),
+            "windows_per_gpu": args.batch, "seq_len": args.seq, "global_windows": args.batch * args.gpus,
             "parallelism": f"dp{args.gpus} (batch of windows sharded, NCCL grad all-reduce + CCC-sum all-reduce)",
             "optimizer": "SGD(lr=1e-3)", "l2": "inputs+activations per step (>1 GB) exceed the 126 MB L2; no explicit flush",
             "host_feature_dtype": "bf16"}
+
+
+# --------------------------------------------------------------------------------------- parity record
+def parity_record(precision, dev):
+    """BASELINE.json metric, third part ("CCC delta vs ref"): the benchmarked pipeline at B = 4, T = 300 with default-init
+    weights (seeded constructors reproduce the reference's initialisation bit for bit, tests/test_host_cpu.py) against the
+    REFERENCE's outputs stored in tests/golden/piped_b4_t300.npz (tests/golden/make_golden.py).  No oracle involved."""
+    import jmt_b200
+    meta = json.load(open(os.path.join(ROOT, "tests", "golden", "golden_meta.json")))["piped_b4_t300"]
+    g = np.load(os.path.join(ROOT, "tests", "golden", "piped_b4_t300.npz"))
+    B, T = meta["B"], meta["T"]
+    torch.manual_seed(meta["init_seed"])
+    model = jmt_b200.JMTPipeline(jmt_b200.Two_transformers(0.0, 0.0, 1, 1, "TRANSFORMER", "FC", 512, precision=precision),
+                                 jmt_b200.FcLayer(768, 512, precision=precision),
+                                 jmt_b200.TemporalConvNet(1024, [512] * 4, kernel_size=5, attention=0, dropout=0.1,
+                                                          precision=precision)).to(dev).eval()
+    gen = torch.Generator().manual_seed(meta["data_seed"])
+    vis = torch.randn(B, 1024, T, generator=gen)
+    aud = torch.randn(B, T, 768, generator=gen)
+    with torch.no_grad():
+        v, a = model(aud.to(dev), vis.to(dev))
+    ref_v, ref_a = torch.from_numpy(g["vout"]).to(dev), torch.from_numpy(g["aout"]).to(dev)
+    lv, la = torch.from_numpy(g["lv"]).to(dev), torch.from_numpy(g["la"]).to(dev)     # (B, T); predictions are (T, B): SURVEY Q1
+    pred_rel = max(float((v - ref_v).abs().max() / ref_v.abs().max()), float((a - ref_a).abs().max() / ref_a.abs().max()))
+    ccc = jmt_b200.cccmetric.ccc
+    d_v = abs(ccc(v.reshape(-1), lv.reshape(-1)) - ccc(ref_v.reshape(-1), lv.reshape(-1)))     # flattened like train.py:303-307
+    d_a = abs(ccc(a.reshape(-1), la.reshape(-1)) - ccc(ref_a.reshape(-1), la.reshape(-1)))
+    crit = jmt_b200.CCCLoss(digitize_num=1)
+    n = B * T
+    loss = float((crit(v.view(-1, n), lv.view(-1, n)) + crit(a.view(-1, n), la.view(-1, n))).item())
+    return {"case": "piped_b4_t300: the benchmarked pipeline at B=4, T=300, default init, vs the reference's outputs (tests/golden)",
+            "precision": precision, "pred_rel": pred_rel, "ccc_delta": max(d_v, d_a), "loss_delta": abs(loss - float(g["loss"]))}
 
 
 # --------------------------------------------------------------------------------------- clocks
@@ -205,7 +283,9 @@ def main():
 
     def step(aud, vis, lv, la):
         v, a = model(aud, vis)
-        loss = crit(v.view(-1, n), lv.view(-1, n)) + crit(a.view(-1, n), la.view(-1, n))   # train.py:303-311
+        # train.py:303-311: v_loss + a_loss on the independently flattened predictions / labels; one fused call so that the
+        # valence and arousal sums share ONE all-reduce across ranks
+        loss = crit.forward_va(v.view(-1, n), lv.view(-1, n), a.view(-1, n), la.view(-1, n))
         opt.zero_grad(set_to_none=True)
         loss.backward()
         opt.step()
@@ -330,7 +410,7 @@ def main():
             step(*resident[i % n_buf])
         torch.cuda.synchronize()
         rec, E.PROFILE = E.PROFILE, None
-        kname = "gemm_tc_kernel" if args.precision == "bf16" else "gemm_simt_kernel"
+        kname = "gemm_simt_kernel" if args.precision == "fp32" else "gemm_tc_kernel"
         sel = [r for r in rec if r[0] == kname]
         tot_ms = sum(r[2].elapsed_time(r[3]) for r in sel)
         tot_fl = sum(r[1] for r in sel)
@@ -378,25 +458,67 @@ def main():
         if world > 1:
             dist.barrier()
 
+    # ---- strong scaling: the SAME global batch of args.batch windows split over the ranks, K replayed steps
+    strong = None
+    if world > 1 and not args.strong and not args.no_strong and args.batch % world == 0 and not args.no_graph:
+        Bs = args.batch // world
+        ns = Bs * T
+        sres = [tuple(t[:Bs].contiguous() for t in r) for r in resident]
+
+        def sstep(aud, vis, lv, la):
+            v, a = model(aud, vis)
+            loss = crit.forward_va(v.view(-1, ns), lv.view(-1, ns), a.view(-1, ns), la.view(-1, ns))
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+            opt.step()
+            return loss
+        sg = jmt_b200.GraphedStep(sstep, sres, warmup=3)
+        for i in range(3):
+            sg.replay(i % n_buf)
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for i in range(args.steps):
+            sg.replay(i % n_buf)
+        s1.record()
+        barrier()
+        sms = torch.tensor([s0.elapsed_time(s1)], device=dev, dtype=torch.float64)
+        dist.all_reduce(sms, op=dist.ReduceOp.MAX)
+        strong = {"global_windows": args.batch, "windows_per_gpu": Bs, "ms_per_step": float(sms.item()) / args.steps,
+                  "value": args.batch * args.steps / (float(sms.item()) / 1e3), "unit": "windows/s", "scaling": "strong",
+                  "note": "same global batch as the 1-GPU run split over the ranks; CUDA-graph replay, device-timed, max over ranks"}
+        sg.graphs.clear()
+        sg.losses.clear()
+
+    # ---- parity of the benchmarked precision (and of the bf16x3 gate mode) against the reference's outputs
+    parity = None
+    if rank == 0 and not args.no_parity:
+        parity = {args.precision: parity_record(args.precision, dev)}
+        if args.precision != "bf16x3":
+            parity["bf16x3"] = parity_record("bf16x3", dev)
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        cpu_port_step(1, T, args.heads, cores)                 # warm-up (thread pools, allocator)
+        arm, kind, what = make_cpu_arm(args.heads, cores)
+        arm(2, T)                                              # warm-up (thread pools, allocator)
         times = []
         t_start = time.perf_counter()
-        while len(times) < 3 and time.perf_counter() - t_start < 40:
-            dt, _ = cpu_port_step(args.cpu_sample, T, args.heads, cores)
+        while len(times) < 5 and time.perf_counter() - t_start < 30:
+            dt, _ = arm(args.cpu_sample, T)
             times.append(dt)
         med = float(np.median(times))
-        cpu = {"value": args.cpu_sample / med, "unit": "windows/s", "cores": cores, "kind": "port",
-               "sample": f"{args.cpu_sample} windows x T={T}, fwd+bwd, fp32, median of {len(times)} runs of oracle/jmt_oracle.py (torch CPU ops)"}
+        cpu = {"value": args.cpu_sample / med, "unit": "windows/s", "cores": cores, "kind": kind,
+               "sample": f"{args.cpu_sample} windows x T={T} per step, fwd+bwd+SGD, fp32, median of {len(times)} steps of {what}"}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "windows/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-                "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": args.precision if args.precision == "bf16" else "f32", "data": "synthetic",
+                "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": {"bf16": "bf16", "bf16x3": "bf16x3 (fp32 values as two bf16 parts, three tcgen05.mma per k-step)", "fp32": "f32"}[args.precision], "data": "synthetic",
                 "config": workload_config(args), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
                 "roofline": roof, "cpu_baseline": cpu, "final_loss": final_loss,
+                "ccc_delta": parity[args.precision]["ccc_delta"] if parity else None,
+                "pred_rel": parity[args.precision]["pred_rel"] if parity else None, "parity": parity, "strong": strong,
                 "launch_mode": "cuda_graph" if graphed is not None else "eager", "host_enqueue_ms_per_eager_step": host_enqueue_ms,
                 "peak_hbm_gb": torch.cuda.max_memory_allocated(dev) / 1e9,
                 "model_tflops": 3 * FWD_GFLOP_PER_WINDOW * value / 1e3}

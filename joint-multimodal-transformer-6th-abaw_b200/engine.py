@@ -18,6 +18,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -149,7 +150,7 @@ class Ctx:
         self.dev = next(iter(params.values())).device if params else torch.device("cuda", torch.cuda.current_device())
         self.keep: List[object] = []          # host arrays that must outlive async launches
         self.bucket_ranges: Dict[str, Tuple[int, int]] = {}
-        self.synced_upto = 0                  # bucket elements whose all-reduce has already been started (overlap)
+        self.synced: List[Tuple[int, int]] = []   # bucket ranges whose all-reduce has already been started (overlap)
         self.grad_sync = None                 # the owner's GradSync hook (set by the autograd bridge)
 
     # ---------------------------------------------------------------- memory helpers
@@ -209,6 +210,41 @@ class Ctx:
 
     def pgrad(self, name: str) -> torch.Tensor:
         return self.pgrads[name]
+
+    def sync_point(self, prefix: str):
+        """Record a tape entry that -- when backward reaches it, i.e. after everything recorded AFTER this call has run its
+        backward -- starts the asynchronous all-reduce of the bucket slice holding the parameters named `prefix*` (their
+        gradients are final then; the slice is contiguous because parameters are laid out in registration order).  NCCL runs
+        it on its own stream under the rest of the backward pass."""
+        if not self.record:
+            return
+
+        def start():
+            hook = self.grad_sync
+            if hook is None or not hasattr(hook, "start") or os.environ.get("JMT_GRAD_OVERLAP", "1") == "0":
+                return
+            mine = [(o, o + k) for n, (o, k) in self.bucket_ranges.items() if n.startswith(prefix)]
+            if not mine:
+                return
+            lo, hi = min(a for a, _ in mine), max(b for _, b in mine)
+            other = [(o, o + k) for n, (o, k) in self.bucket_ranges.items() if not n.startswith(prefix)]
+            if any(a < hi and lo < b for a, b in other) or any(a < hi and lo < b for a, b in self.synced):
+                return                                    # not contiguous / already in flight: leave it to the final pass
+            hook.start(self.bucket[lo:hi])
+            self.synced.append((lo, hi))
+        self.tape.append(start)
+
+    def unsynced_ranges(self) -> List[Tuple[int, int]]:
+        """Bucket ranges not covered by an all-reduce started at a sync_point."""
+        total = self.bucket.numel() if self.bucket is not None else 0
+        out, pos = [], 0
+        for lo, hi in sorted(self.synced):
+            if lo > pos:
+                out.append((pos, lo))
+            pos = max(pos, hi)
+        if pos < total:
+            out.append((pos, total))
+        return out
 
     # ---------------------------------------------------------------- gradient plumbing
     def grad_target(self, v: Var) -> Tuple[torch.Tensor, int]:

@@ -126,8 +126,9 @@ class _TapeFn(torch.autograd.Function):
                 s(g)
         ctx.backward()
         if hook is not None:                      # NCCL all-reduce of the flat live-gradient bucket
-            if ctx.synced_upto > 0 and hasattr(hook, "start"):
-                hook.start(ctx.bucket[ctx.synced_upto:])      # the head of the bucket is already in flight (overlap)
+            if ctx.synced and hasattr(hook, "start"):
+                for lo, hi in ctx.unsynced_ranges():          # the other slices are already in flight (overlap)
+                    hook.start(ctx.bucket[lo:hi])
                 hook.finish()
             else:
                 hook(ctx.bucket)
@@ -615,6 +616,7 @@ def _tcn_graph(ctx, h, prefix, specs, N, Ls, pad):
     Cin != Cout), LeakyReLU (temporal_convolutional_model.py:54-57, 81-82).  Padding rows stay zero throughout."""
     for i, (cin, cout, k, d, p, has_ds) in enumerate(specs):
         pre = f"{prefix}network.{i}."
+        ctx.sync_point(pre)          # reached in backward once this level's dW / weight-norm gradients are final
         y = E.causal_conv(ctx, h, pre + "conv1.", N, Ls, cin, cout, k, d, L.ACT_LEAKY, drop_p=p, pad=pad)
         y = E.causal_conv(ctx, y, pre + "conv2.", N, Ls, cout, cout, k, d, L.ACT_LEAKY, drop_p=p, pad=pad)
         res = _conv1x1(ctx, h, pre + "downsample.", (Ls + pad, pad)) if has_ds else h
@@ -671,20 +673,10 @@ class JMTPipeline(_JmtModule):
                 video_n = _l2norm_var(ctx, h)
             else:
                 video_n, gv = E.l2norm(ctx, vis, vis.requires_grad)
-            if ctx.record:
-                # Backward runs the tape in reverse: everything recorded after this point (the fusion) is done when this
-                # entry executes, so the fusion slice of the gradient bucket (it comes first: fusion.* parameters are
-                # registered first) can be all-reduced while the TCN / FcLayer backward still runs.
-                def start_fusion_sync():
-                    hook = ctx.grad_sync
-                    if hook is None or not hasattr(hook, "start") or os.environ.get("JMT_GRAD_OVERLAP", "1") == "0":
-                        return
-                    hi = max((o + k for n, (o, k) in ctx.bucket_ranges.items() if n.startswith("fusion.")), default=0)
-                    lo = min((o for n, (o, k) in ctx.bucket_ranges.items() if not n.startswith("fusion.")), default=hi)
-                    if 0 < hi <= lo:
-                        hook.start(ctx.bucket[:hi])
-                        ctx.synced_upto = hi
-                ctx.tape.append(start_fusion_sync)
+            # Backward runs the tape in reverse: everything recorded after this point (the fusion) is done when this entry
+            # executes, so the fusion slice of the gradient bucket is all-reduced while the TCN / FcLayer backward still
+            # runs; the TCN levels likewise start theirs as each level's weight gradients complete (_tcn_graph).
+            ctx.sync_point("fusion.")
             outs, setters = _two_transformers_graph(ctx, fusion, "fusion.", video_n, audio_n, B, T)
             return outs, setters, [ga, gv]
         v, a = self._run(runner, audio, visual)

@@ -403,6 +403,7 @@ def gen_default_init(R, meta):
     names2, l2c, sc, headc = summary()
     assert names2 == names
     np.savez_compressed(os.path.join(HERE, name + ".npz"), vout=v.detach().numpy(), aout=a.detach().numpy(),
+                        lv=lv.numpy(), la=la.numpy(),
                         loss=loss.detach().numpy(), d_aud=d_aud.numpy()[:, :, ::32], d_vis=d_vis.numpy()[:, ::64],
                         d_aud_l2=float(d_aud.norm()), d_vis_l2=float(d_vis.norm()), grad_l2=l2, grad_sum=s, grad_head=head,
                         c_d_aud=aud.grad.numpy()[:, :, ::32], c_d_vis=vis.grad.numpy()[:, ::64],
