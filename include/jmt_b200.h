@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define JMT_ABI_VERSION 6
+#define JMT_ABI_VERSION 7
 
 typedef enum {
   JMT_OK = 0,
@@ -149,7 +149,8 @@ typedef struct {
   const void* p_in;                                  /* mode 1: saved probabilities; else NULL */
   const void* o_in;                                  /* mode 1: saved forward output O, same geometry as a1 (= dO); else NULL */
   const float* delta_in;                             /* mode 1: precomputed delta (NB, heads, Lq) fp32 (jmt_rowdot_bf16), or NULL: from o_in */
-  void* x;                                           /* out: P (mode 0) / dS (mode 1), bf16 */
+  void* x;                                           /* out: P (mode 0) / dS (mode 1), bf16; mode 0 with D: may be NULL (forward-only callers: the
+                                                        probabilities are then never written to memory) */
   void* d;                                           /* out: O (mode 0) / dQ (mode 1), bf16; NULL: stop after X (P / dS) -- GEMM2 is then a plain jmt_gemm_bf16 */
   int32_t mode;
   int32_t Lq, S, dh, heads, NB;
@@ -160,6 +161,7 @@ typedef struct {
   int64_t x_ld;
   float scale;
   int32_t store_mode;                                /* JMT_STORE / JMT_ACCUMULATE for D */
+  float* lse_out;                                    /* mode 0, nullable: logsumexp_j(scale * q_i . k_j) per query row, (NB, heads, Lq) fp32 */
 } jmt_attn_desc;
 int jmt_attn_chain_supported(const jmt_attn_desc* g);   /* 1 / 0, no launch */
 int jmt_attn_chain_bf16(const jmt_attn_desc* g, void* stream);
@@ -167,6 +169,16 @@ int jmt_attn_chain_bf16(const jmt_attn_desc* g, void* stream);
  * delta_i = dO_i . O_i = sum_j P_ij dP_ij term of the softmax backward, one pass over dO and O. */
 int jmt_rowdot_bf16(const void* a, const void* b, int64_t ld, int64_t hs, int64_t bs, int NB, int heads, int rows, int dh,
                     float* out, void* stream);
+/* Attention over long key sequences (S beyond what one jmt_attn_chain_bf16 tile holds on chip; SURVEY 7.6a, the batch-dimension
+ * attention of MultimodalTransformer_wo_JR at large batch, mm_transformers.py:120-122): the caller runs the forward chain kernel
+ * over key CHUNKS (x = NULL, lse_out set) and merges with the running log-sum-exp -- flash-attention's algebra across launches,
+ * no (L, S) score or probability tensor ever exists in memory:
+ *   lse' = logaddexp(lse_acc, lse_chunk);  acc' = acc * exp(lse_acc - lse') + o_chunk * exp(lse_chunk - lse')
+ * o_chunk bf16, element (r, d) of (head h, batch b) at b*bs + h*hs + r*ld + d; acc fp32 with the same offsets; lse_* (NB, heads, rows)
+ * fp32.  first != 0: acc / lse_acc are initialised from the chunk.  out != NULL (last chunk): the bf16 result goes to `out` (same
+ * offsets) instead of acc. */
+int jmt_attn_merge(const void* o_chunk, int64_t ld, int64_t hs, int64_t bs, const float* lse_chunk, float* acc, float* lse_acc,
+                   void* out, int first, int NB, int heads, int rows, int dh, void* stream);
 /* Debug aid: per-CTA cycle counters of the TMA / MMA / row-warp roles (148*16 uint64 device buffer; NULL disables). */
 int jmt_attn_set_profile_buffer(void* dev_buf);
 
@@ -253,6 +265,11 @@ int jmt_transpose_strided(const void* in, int in_dtype, int64_t in_bs, void* out
 /* out[b*out_bs + r*cols + c] = cast(in[b*in_bs + r*cols + c])  (nb, rows, cols) blocks: pad / unpad of the flat layout */
 int jmt_copy_rows3d(const void* in, int in_dtype, int64_t in_bs, void* out, int out_dtype, int64_t out_bs, int64_t nb,
                     int64_t rows, int cols, void* stream);
+/* out[i0*os0 + i1*os1 + c] = cast(in[i0*is0 + i1*is1 + c]), i0 < n0, i1 < n1, c < cols: row permutation with cast in one
+ * launch -- the (B, T, D) -> (T, B, D) layout MultimodalTransformer_w_JR's FC head returns (mm_multi_transformers.py:201-211,
+ * SURVEY Q1) and its gradient's way back. */
+int jmt_copy3d(const void* in, int in_dtype, int64_t is0, int64_t is1, void* out, int out_dtype, int64_t os0, int64_t os1,
+               int64_t n0, int64_t n1, int cols, void* stream);
 /* max over time of channels-last sequences without materialising `transpose(1,2)` (I3DWSDDA.py:44 then
  * tsav.py:216 `torch.max(ft, 1)`): x element (n, t, c) at x[n*batch_stride + t*C + c], t < L; out (nb, C) in `dtype`,
  * arg (nb, C) = first t attaining the maximum; backward scatters dout to those positions of a pre-zeroed dx. */

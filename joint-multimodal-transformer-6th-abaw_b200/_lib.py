@@ -46,7 +46,7 @@ class AttnDesc(C.Structure):
         ("b1_ld", C.c_int64), ("b1_hs", C.c_int64), ("b1_bs", C.c_int64),
         ("b2_ld", C.c_int64), ("b2_hs", C.c_int64), ("b2_bs", C.c_int64),
         ("d_ld", C.c_int64), ("d_hs", C.c_int64), ("d_bs", C.c_int64),
-        ("x_ld", C.c_int64), ("scale", C.c_float), ("store_mode", C.c_int32),
+        ("x_ld", C.c_int64), ("scale", C.c_float), ("store_mode", C.c_int32), ("lse_out", C.c_void_p),
     ]
 
 
@@ -65,6 +65,7 @@ SIGNATURES = {
     "jmt_attn_chain_supported": [C.POINTER(AttnDesc)],
     "jmt_attn_chain_bf16": [C.POINTER(AttnDesc), _P],
     "jmt_attn_set_profile_buffer": [_P],
+    "jmt_attn_merge": [_P, _L, _L, _L, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "jmt_rowdot_bf16": [_P, _P, _L, _L, _L, _I, _I, _I, _I, _P, _P],
     "jmt_l2norm_fwd": [_P, _I, _L, _P, _I, _L, _I, _F, _P, _P],
     "jmt_l2norm_bwd": [_P, _P, _I, _P, _F, _P, _I, _L, _I, _P],
@@ -85,6 +86,7 @@ SIGNATURES = {
     "jmt_transpose": [_P, _I, _P, _I, _L, _I, _I, _P],
     "jmt_transpose_strided": [_P, _I, _L, _P, _I, _L, _L, _I, _I, _P],
     "jmt_copy_rows3d": [_P, _I, _L, _P, _I, _L, _L, _L, _I, _P],
+    "jmt_copy3d": [_P, _I, _L, _L, _P, _I, _L, _L, _L, _L, _I, _P],
     "jmt_add_act": [_P, _P, _P, _L, _I, _F, _I, _P],
     "jmt_time_max_fwd": [_P, _L, _L, _I, _I, _P, _P, _I, _P],
     "jmt_time_max_bwd": [_P, _P, _L, _L, _I, _P, _I, _P],
@@ -119,7 +121,7 @@ def lib():
             fn = getattr(h, name)           # AttributeError if a declared symbol is not exported
             fn.argtypes = argtypes
             fn.restype = _RESTYPES.get(name, C.c_int)
-        if h.jmt_abi_version() != 6:
+        if h.jmt_abi_version() != 7:
             raise RuntimeError("libjmt_b200.so ABI version mismatch")
         _lib = h
     return _lib

@@ -46,6 +46,9 @@ struct AtParams {
   int skip2;                   // mode 1: stop after X = dS (no GEMM2 / dQ): dQ, dK, dV are plain GEMMs on the saved dS
   int64_t x_ld;
   int store_mode;
+  int store_x;                 // write X (P / dS) to global memory (0: forward-only callers that never run a backward)
+  float* lse_out;              // mode 0, optional: log-sum-exp of scale * scores per query row, (NB, heads, Lq) fp32 (natural log):
+                               // what a caller needs to merge attention over key CHUNKS (long S, see jmt_attn_merge)
   FastDiv fd_qt, fd_heads;
   unsigned long long* prof;   // optional per-CTA cycle counters (16 per CTA), jmt_attn_set_profile_buffer
 };
@@ -146,7 +149,7 @@ __device__ __forceinline__ void row_bwd_chunk(const AtParams& p, const uint32_t 
 // X ends up in shared memory as bf16 in the 128B-swizzled K-major A-operand layout of GEMM2.  The TMEM load of chunk
 // i+1 is in flight while chunk i is processed (two register buffers).
 template <int MODE>
-__device__ __forceinline__ void row_op(const AtParams& p, const RowCtx& rc, float* red, const float* delta_buf) {
+__device__ __forceinline__ void row_op(const AtParams& p, const RowCtx& rc, float* red, const float* delta_buf, float* lse_row) {
   const int half = rc.half, row = rc.row, nch = rc.nch;
   uint32_t ra[32], rb[32];
   float shift = 0.f;
@@ -192,7 +195,10 @@ __device__ __forceinline__ void row_op(const AtParams& p, const RowCtx& rc, floa
     red[256 + half * 128 + row] = (sum[0] + sum[1]) + (sum[2] + sum[3]);
     __syncwarp();
     asm volatile("bar.sync 1, %0;" ::"n"(32 * kAtRowWarps) : "memory");
-    const float inv = 1.f / (red[256 + row] + red[256 + 128 + row]);
+    const float total = red[256 + row] + red[256 + 128 + row];
+    const float inv = 1.f / total;
+    // log-sum-exp of this row's scaled scores: shift is rowmax * scale * log2(e), the exponentials were taken base 2
+    if (lse_row != nullptr && half == 0) *lse_row = (shift + log2f(total)) * 0.6931471805599453f;
     for (int ch = half; ch < nch; ch += 2) {
       const uint32_t xbase = rc.xrow + (ch >> 1) * 16384;
       uint4 v[4];
@@ -432,12 +438,15 @@ attn_chain_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
       RowCtx rc;
       rc.tb = tb; rc.xrow = xrow; rc.sw = sw; rc.half = half; rc.row = row; rc.nch = nch;
       if (lane == 0) bulk_wait_read0();              // this warp's / the X stores of the previous tile have finished reading X
-      row_op<MODE>(p, rc, red, red);
+      float* lse_row = nullptr;
+      if (MODE == 0 && p.lse_out != nullptr && grow < p.Lq)
+        lse_row = p.lse_out + ((int64_t)c.b * p.heads + c.head) * p.Lq + grow;
+      row_op<MODE>(p, rc, red, red, lse_row);
       fence_async_smem();                            // X visible to the tensor core / TMA (async proxy)
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(x_ready);
-      if (ew == 0 && lane == 0) {
+      if (p.store_x && ew == 0 && lane == 0) {
         // saved probabilities (forward) / dS (backward): X chunks -> global, clipped to (S, Lq) by the tensor map
         mbar_wait(x_ready, par);
         for (int kc = 0; kc < p.nkx; ++kc) tma_store_4d(&map_x, sX + kc * 16384, kc * 64, c.q0, c.head, c.b);
@@ -545,6 +554,8 @@ static int at_plan(const jmt_attn_desc* g, AtParams* p, int* smem_bytes) {
   p->delta_in = g->delta_in; p->skip2 = g->d == nullptr ? 1 : 0;
   p->x_ld = g->x_ld;
   p->store_mode = g->store_mode;
+  p->store_x = g->x != nullptr ? 1 : 0;
+  p->lse_out = g->mode == 0 ? g->lse_out : nullptr;
   p->fd_qt.init(p->q_tiles);
   p->fd_heads.init(g->heads);
   return 1;
@@ -591,6 +602,66 @@ extern "C" int jmt_rowdot_bf16(const void* a, const void* b, int64_t ld, int64_t
   return check_launch("rowdot_kernel");
 }
 
+namespace jmt {
+// Merge of attention computed over key CHUNKS (long S): chunk c gave O_c = softmax_c(s) V_c and lse_c = logsumexp_c(s) per query row;
+// softmax over all keys = sum_c exp(lse_c - lse) O_c with lse = logsumexp_c(lse_c).  Running form, one warp per (b, head, query row):
+//   lse' = logaddexp(lse_acc, lse_c);  acc' = acc * exp(lse_acc - lse') + O_c * exp(lse_c - lse')
+// acc is fp32 (rows, E) contiguous with the rows of O; the last chunk writes the bf16 result instead of acc.
+__global__ void __launch_bounds__(256)
+attn_merge_kernel(const __nv_bfloat16* __restrict__ oc, int64_t ld, int64_t hs, int64_t bs, const float* __restrict__ lse_c,
+                  float* __restrict__ acc, float* __restrict__ lse_acc, __nv_bfloat16* __restrict__ out, int first,
+                  int rows, int heads, int dh, int64_t total) {
+  const int lane = threadIdx.x & 31;
+  for (int64_t w = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); w < total; w += (int64_t)gridDim.x * 8) {
+    const int64_t bh = w / rows; const int r = (int)(w - bh * rows);
+    const int64_t bi = bh / heads; const int h = (int)(bh - bi * heads);
+    const int64_t off = bi * bs + (int64_t)h * hs + (int64_t)r * ld;
+    const float lc = lse_c[w];
+    float wa = 0.f, wc = 1.f, ln = lc;
+    if (!first) {
+      const float la = lse_acc[w];
+      const float m = fmaxf(la, lc);
+      ln = m + __logf(__expf(la - m) + __expf(lc - m));
+      wa = __expf(la - ln); wc = __expf(lc - ln);
+    }
+    for (int pc = lane; pc < (dh >> 3); pc += 32) {
+      Vec8<__nv_bfloat16> x; x.load(oc + off + pc * 8);
+      Vec8<float> a;
+      if (!first) {
+        a.load(acc + off + pc * 8);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a.v[k] = fmaf(a.v[k], wa, x.v[k] * wc);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a.v[k] = x.v[k];
+      }
+      if (out != nullptr) {
+        Vec8<__nv_bfloat16> o;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o.v[k] = a.v[k];
+        o.store(out + off + pc * 8);
+      } else {
+        a.store(acc + off + pc * 8);
+      }
+    }
+    if (lane == 0) lse_acc[w] = ln;
+  }
+}
+}  // namespace jmt
+
+extern "C" int jmt_attn_merge(const void* o_chunk, int64_t ld, int64_t hs, int64_t bs, const float* lse_chunk, float* acc,
+                              float* lse_acc, void* out, int first, int NB, int heads, int rows, int dh, void* stream) {
+  JMT_REQUIRE(o_chunk && lse_chunk && acc && lse_acc && NB >= 1 && heads >= 1 && rows >= 1 && dh >= 8 && dh % 8 == 0,
+              "jmt_attn_merge: bad arguments");
+  JMT_REQUIRE(ld % 8 == 0 && hs % 8 == 0 && bs % 8 == 0 &&
+              ((reinterpret_cast<uintptr_t>(o_chunk) | reinterpret_cast<uintptr_t>(acc) | reinterpret_cast<uintptr_t>(out)) & 31) == 0,
+              "jmt_attn_merge: 32-byte aligned geometry required");
+  const int64_t total = (int64_t)NB * heads * rows;
+  attn_merge_kernel<<<grid_for(total, 8, kNumSMs * 16), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)o_chunk, ld, hs, bs, lse_chunk, acc, lse_acc, (__nv_bfloat16*)out, first, rows, heads, dh, total);
+  return check_launch("attn_merge_kernel");
+}
+
 static std::atomic<unsigned long long*> g_attn_prof{nullptr};
 extern "C" int jmt_attn_set_profile_buffer(void* dev_buf) {
   g_attn_prof.store((unsigned long long*)dev_buf);
@@ -601,18 +672,19 @@ extern "C" int jmt_attn_chain_supported(const jmt_attn_desc* g) {
   if (!g) return 0;
   AtParams p; int smem = 0;
   if (!at_plan(g, &p, &smem)) return 0;
-  if (g->x_ld % 8 != 0 || g->x_ld < g->S) return 0;
+  if (g->x != nullptr && (g->x_ld % 8 != 0 || g->x_ld < g->S)) return 0;
   return 1;
 }
 
 extern "C" int jmt_attn_chain_bf16(const jmt_attn_desc* g, void* stream) {
-  JMT_REQUIRE(g && g->a1 && g->b1 && g->x, "jmt_attn_chain_bf16: null pointer");
+  JMT_REQUIRE(g && g->a1 && g->b1, "jmt_attn_chain_bf16: null pointer");
+  JMT_REQUIRE(g->x || (g->mode == 0 && g->d), "jmt_attn_chain_bf16: X may only be omitted by a forward call that produces D");
   JMT_REQUIRE(g->mode == 0 || g->mode == 1, "jmt_attn_chain_bf16: bad mode");
   JMT_REQUIRE(g->d == nullptr || g->b2, "jmt_attn_chain_bf16: D needs B2");
   JMT_REQUIRE(g->mode == 0 || (g->p_in && (g->delta_in || g->o_in)), "jmt_attn_chain_bf16: mode 1 needs the saved probabilities and delta (or O)");
   JMT_REQUIRE(g->store_mode == JMT_STORE || g->store_mode == JMT_ACCUMULATE, "jmt_attn_chain_bf16: bad store_mode");
   AtParams p; int smem = 0;
-  if (!at_plan(g, &p, &smem) || g->x_ld % 8 != 0 || g->x_ld < g->S) {
+  if (!at_plan(g, &p, &smem) || (g->x != nullptr && (g->x_ld % 8 != 0 || g->x_ld < g->S))) {
     set_error("jmt_attn_chain_bf16: unsupported geometry (dh=%d S=%d Lq=%d x_ld=%lld): use the unfused path", g->dh, g->S, g->Lq,
               (long long)g->x_ld);
     return JMT_ERR_UNSUPPORTED;
@@ -628,9 +700,12 @@ extern "C" int jmt_attn_chain_bf16(const jmt_attn_desc* g, void* stream) {
     rc = make_map_mn5(&mb2, g->b2, g->dh, g->S, g->b2_ld, g->heads, g->b2_hs, g->NB, g->b2_bs, kBlockK, p.n2 / 64, "jmt_attn_chain_bf16(B2)");
     if (rc != JMT_OK) return rc;
   }
-  rc = make_map(&mx, g->x, g->S, g->Lq, g->x_ld, g->heads, (int64_t)g->Lq * g->x_ld, g->NB, (int64_t)g->heads * g->Lq * g->x_ld, kBlockM,
-                "jmt_attn_chain_bf16(X)");
-  if (rc != JMT_OK) return rc;
+  mx = ma1;                     // (unused when X is not stored)
+  if (g->x != nullptr) {
+    rc = make_map(&mx, g->x, g->S, g->Lq, g->x_ld, g->heads, (int64_t)g->Lq * g->x_ld, g->NB, (int64_t)g->heads * g->Lq * g->x_ld, kBlockM,
+                  "jmt_attn_chain_bf16(X)");
+    if (rc != JMT_OK) return rc;
+  }
   md = mx;
   if (!p.skip2) {
     JMT_REQUIRE((reinterpret_cast<uintptr_t>(g->d) & 15) == 0 && g->d_ld % 8 == 0 && g->d_hs % 8 == 0 && g->d_bs % 8 == 0,

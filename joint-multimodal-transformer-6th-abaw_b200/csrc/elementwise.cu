@@ -547,6 +547,45 @@ extern "C" int jmt_cast(const void* in, int in_dtype, void* out, int out_dtype, 
   return jmt_copy2d(in, in_dtype, n, out, out_dtype, n, 1, (int)n, stream);
 }
 
+// out[i0*os0 + i1*os1 + c] = cast(in[i0*is0 + i1*is1 + c]): a row permutation with cast in ONE launch
+// (e.g. (B, T, D) activations -> the (T, B, D) layout MultimodalTransformer_w_JR returns)
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(kEwThreads)
+copy3d_kernel(const TI* __restrict__ in, int64_t is0, int64_t is1, TO* __restrict__ out, int64_t os0, int64_t os1,
+              int64_t n0, int64_t n1, int cols, int vec) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nt = (int64_t)gridDim.x * blockDim.x;
+  const int cw = vec ? cols / 8 : cols;
+  const int64_t total = n0 * n1 * cw;
+  for (int64_t i = tid; i < total; i += nt) {
+    const int64_t r = i / cw; const int c = (int)(i - r * cw);
+    const int64_t i0 = r / n1, i1 = r - i0 * n1;
+    const TI* ip = in + i0 * is0 + i1 * is1;
+    TO* op = out + i0 * os0 + i1 * os1;
+    if (vec) {
+      Vec8<TI> v; v.load(ip + c * 8);
+      Vec8<TO> o;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o.v[k] = v.v[k];
+      o.store(op + c * 8);
+    } else {
+      op[c] = from_f32<TO>(to_f32(ip[c]));
+    }
+  }
+}
+
+extern "C" int jmt_copy3d(const void* in, int in_dtype, int64_t is0, int64_t is1, void* out, int out_dtype, int64_t os0, int64_t os1,
+                          int64_t n0, int64_t n1, int cols, void* stream) {
+  JMT_REQUIRE(in && out && n0 >= 0 && n1 >= 0 && cols >= 0, "jmt_copy3d: bad arguments");
+  if (n0 * n1 * cols == 0) return JMT_OK;
+  const int vec = (cols % 8 == 0 && is0 % 8 == 0 && is1 % 8 == 0 && os0 % 8 == 0 && os1 % 8 == 0 &&
+                   ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 31) == 0) ? 1 : 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = grid_for(n0 * n1 * (vec ? cols / 8 : cols), kEwThreads);
+  JMT_DISPATCH_DTYPE(in_dtype, TI, JMT_DISPATCH_DTYPE(out_dtype, TO,
+      (copy3d_kernel<TI, TO><<<grid, kEwThreads, 0, st>>>((const TI*)in, is0, is1, (TO*)out, os0, os1, n0, n1, cols, vec))));
+  return check_launch("copy3d_kernel");
+}
+
 // bf16x3 operand split: hi = bf16(x), lo = bf16(x - hi); x ~= hi + lo to 2^-17 relative
 __global__ void __launch_bounds__(kEwThreads)
 split_bf16x2_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int64_t n) {

@@ -167,7 +167,7 @@ struct EpiCtx {
 // 64-column (bf16 out) / 32-column (fp32 out) chunk -> alpha / bias / activation -> 128B-swizzled staging tile ->
 // TMA store or reduce-add; or per-thread stores when D's geometry is not 16-byte aligned.
 #ifdef JMT_EPI_PROF
-// diagnostic build only (scratch/epi_prof.sh): cycles of epilogue warp 0 of CTA 0 per phase, accumulated in registers
+// diagnostic build only (profiles/tools/epi_prof.sh): cycles of epilogue warp 0 of CTA 0 per phase, accumulated in registers
 __device__ unsigned long long g_epi_prof[8];
 #define EPI_T(i) do { const long long t_ = clock64(); e.prof[i] += t_ - tprev; tprev = t_; } while (0)
 #define EPI_T0() long long tprev = clock64()

@@ -642,12 +642,13 @@ def _proj_grad_slice(ctx: Ctx, v: Var, c0: int, c1: int) -> Tuple[torch.Tensor, 
 
 FUSED_ATTENTION = True      # bf16 mode: True = QK^T -> softmax -> PV in one kernel when the geometry is supported; "p" = QK^T +
                             # softmax fused, PV a plain GEMM (measured 1.4 % slower per step); False = GEMM + softmax kernels
+LONG_S_CHUNKED = True       # forward-only attention beyond the fused kernel's key limit: chunked fused kernel + log-sum-exp merge
 FUSED_ATTENTION_BWD = "ds"   # "ds": dP GEMM + softmax backward fused (dS on chip, dQ/dK/dV plain GEMMs); "full": dP -> dS -> dQ in one
                              # kernel (correct, not faster than the composition yet); False: GEMM + softmax_bwd kernel
 
 
 def _attn_chain(ctx: Ctx, mode: int, a1, a1_geo, b1, b1_geo, b2, b2_geo, p_in, x, d, d_geo, Lq, S, dh, heads, NB, x_ld,
-                scale, store, probe_only=False, o_in=None, delta_in=None):
+                scale, store, probe_only=False, o_in=None, delta_in=None, lse_out=None):
     """One launch of the fused attention core (include/jmt_b200.h: jmt_attn_desc).  *_geo = (ld, head stride,
     batch stride) in elements."""
     g = L.AttnDesc()
@@ -655,7 +656,8 @@ def _attn_chain(ctx: Ctx, mode: int, a1, a1_geo, b1, b1_geo, b2, b2_geo, p_in, x
     g.p_in = p_in.data_ptr() if p_in is not None else None
     g.o_in = o_in.data_ptr() if o_in is not None else None
     g.delta_in = delta_in.data_ptr() if delta_in is not None else None
-    g.x, g.d = x.data_ptr(), (d.data_ptr() if d is not None else None)
+    g.x, g.d = (x.data_ptr() if x is not None else None), (d.data_ptr() if d is not None else None)
+    g.lse_out = lse_out.data_ptr() if lse_out is not None else None
     g.mode = mode
     g.Lq, g.S, g.dh, g.heads, g.NB = Lq, S, dh, heads, NB
     g.a1_ld, g.a1_hs, g.a1_bs = a1_geo
@@ -703,6 +705,27 @@ def attention_core(ctx: Ctx, q: Var, qcol: int, k: Var, kcol: int, v: Var, vcol:
     if FUSED_ATTENTION and ctx.adt == torch.bfloat16:
         fused = _attn_chain(ctx, 0, qd, q_geo, kd, k_geo, vd, v_geo, None, o, o, o_geo, Lq, S, dh, heads, NB, s_ld, scale,
                             L.STORE, probe_only=True)
+    if not fused and FUSED_ATTENTION and ctx.adt == torch.bfloat16 and not ctx.record and LONG_S_CHUNKED:
+        # Long key sequences, forward only (evaluation; SURVEY 7.6a: the batch-dimension attention of the NONE variant at
+        # large batch): the fused kernel over key chunks + running log-sum-exp merge.  Neither the (L, S) scores nor the
+        # probabilities ever reach memory.  (A backward needs the probabilities: training keeps the composed path below.)
+        chunk = next((c for c in (320, 256, 192, 128, 64) if c <= S and _attn_chain(
+            ctx, 0, qd, q_geo, kd, k_geo, vd, v_geo, None, None, o, o_geo, Lq, c, dh, heads, NB, 0, scale, L.STORE, probe_only=True)), 0)
+        if chunk:
+            oc = ctx.empty((q.data.shape[0], E))
+            acc = ctx.empty((q.data.shape[0], E), torch.float32)
+            lse_c = ctx.empty((NB, heads, Lq), torch.float32)
+            lse_acc = ctx.empty((NB, heads, Lq), torch.float32)
+            for s0 in range(0, S, chunk):
+                sc = min(chunk, S - s0)
+                kc, vc = kd[s0 * gk.seq_stride:], vd[s0 * gk.seq_stride:]       # key s <-> row s * seq_stride (+ batch offset)
+                _attn_chain(ctx, 0, qd, q_geo, kc, k_geo, vc, v_geo, None, None, oc, o_geo, Lq, sc, dh, heads, NB, 0, scale,
+                            L.STORE, lse_out=lse_c)
+                last = s0 + chunk >= S
+                L.check(ctx.lib.jmt_attn_merge(_ptr(oc), o_geo[0], o_geo[1], o_geo[2], _ptr(lse_c), _ptr(acc), _ptr(lse_acc),
+                                               _ptr(o) if last else None, 1 if s0 == 0 else 0, NB, heads, Lq, dh, _stream()),
+                        "jmt_attn_merge")
+            return Var(o)
     if fused and FUSED_ATTENTION == "p":
         # QK^T + softmax on chip (fp32 scores never leave the SM), PV as a plain GEMM
         probs = ctx.empty((NB, heads, Lq, s_ld))

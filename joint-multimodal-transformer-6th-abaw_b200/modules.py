@@ -267,20 +267,20 @@ def _features_out(ctx, feats, B, T, time_major):
     if not time_major:
         return E.to_external(ctx, feats, (B, T, D))
     out = ctx.empty((T, B, D), torch.float32)
-    # out[t, b, :] = feats[b*T + t, :]: one strided copy per b (rows t with pitch B*D)
-    for b in range(B):
-        L.check(ctx.lib.jmt_copy2d(E._ptr(feats.data[b * T:(b + 1) * T]), ctx.acode, feats.data.stride(0),
-                                   E._ptr(out[:, b]), L.F32, B * D, T, D, E._stream()), "jmt_copy2d")
+    ld = feats.data.stride(0)
+    # out[t, b, :] = feats[b*T + t, :]: one launch (row permutation + cast)
+    L.check(ctx.lib.jmt_copy3d(E._ptr(feats.data), ctx.acode, T * ld, ld, E._ptr(out), L.F32, D, B * D, B, T, D, E._stream()), "jmt_copy3d")
     g = {"t": None}
     if ctx.record:
         def bwd():
             if g["t"] is None:
                 return
-            d = g["t"].contiguous()
+            d = g["t"]
+            if not d.is_contiguous() or d.dtype not in E._DT:
+                raise RuntimeError("jmt_b200: the gradient of the (T, B, D) feature output must be a contiguous fp32 / bf16 tensor")
             gb = E.GradBuf(ctx.empty(feats.data.shape))
-            for b in range(B):
-                L.check(ctx.lib.jmt_copy2d(E._ptr(d[:, b]), E._DT[d.dtype], B * D, E._ptr(gb.t[b * T:(b + 1) * T]),
-                                           ctx.acode, D, T, D, E._stream()), "jmt_copy2d")
+            L.check(ctx.lib.jmt_copy3d(E._ptr(d), E._DT[d.dtype], D, B * D, E._ptr(gb.t), ctx.acode, T * D, D, B, T, D, E._stream()),
+                    "jmt_copy3d")
             ctx.add_grad(feats, gb)
             gb.refs -= 1
         ctx.tape.append(bwd)

@@ -1,4 +1,4 @@
-"""Per-phase cycles of one epilogue warp (needs the diagnostic build: scratch/epi_prof.sh, JMT_B200_LIB=scratch/ab/lib_prof.so)."""
+"""Per-phase cycles of one epilogue warp (needs the diagnostic build: profiles/tools/epi_prof.sh, JMT_B200_LIB=profiles/tools/ab/lib_prof.so)."""
 import ctypes as C, sys, torch
 sys.path.insert(0, '.')
 import jmt_b200

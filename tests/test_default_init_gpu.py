@@ -160,6 +160,40 @@ def test_two_transformers_default_init(name, precision, golden_meta, golden_dir)
     _check(name, precision, vals, TT_BOUNDS)
 
 
+@pytest.mark.parametrize("name", ["ttd_none_fc_b400_t2", "ttd_none_fc_b600_t1_h2", "ttd_none_fc_b300_t2"])
+def test_long_key_attention_forward_only_chunked(name, golden_meta, golden_dir):
+    """Evaluation (no_grad) of the NONE variant whose encoders attend across the batch (L = S = B) beyond the fused
+    kernel's key limit: the engine runs the fused kernel over key chunks and merges with the running log-sum-exp
+    (jmt_attn_merge) -- no (L, S) score / probability tensor is materialised.  Against the REFERENCE's predictions, and against
+    the composed path (GEMM -> fp32 scores -> softmax -> GEMM) the training graph uses at these lengths."""
+    from jmt_b200 import engine as E
+    m = golden_meta[name]
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    torch.manual_seed(m["init_seed"])
+    model = jmt_b200.Two_transformers(0.0, 0.0, m["heads"], m["layers"], m["joint"], m["fmt"], m["vin"], precision="bf16").to(DEV).eval()
+    aud, vis = (t.to(DEV) for t in O.synth_features(m["B"], m["T"], [512, m["vin"]], m["feat_seed"]))
+    n0 = jmt_b200.launch_count()
+    with torch.no_grad():
+        v, a = model(aud, vis)
+    n_chunked = jmt_b200.launch_count() - n0
+    E.LONG_S_CHUNKED = False
+    try:
+        n0 = jmt_b200.launch_count()
+        with torch.no_grad():
+            v2, a2 = model(aud, vis)
+        n_composed = jmt_b200.launch_count() - n0
+    finally:
+        E.LONG_S_CHUNKED = True
+    vals = {"pred_rel": max(_rel(v.cpu(), g["vout"]), _rel(a.cpu(), g["aout"])),
+            "pred_l2": max(_rl2(v.cpu(), g["vout"]), _rl2(a.cpu(), g["aout"])),
+            "vs_composed": max(_rel(v.cpu(), v2.cpu()), _rel(a.cpu(), a2.cpu()))}
+    _record(name + "/chunked_eval", "bf16", vals)
+    if m["B"] > 320:
+        assert n_chunked != n_composed, "the chunked path was not taken"
+    assert vals["pred_rel"] < TT_BOUNDS["pred_rel"][2] and vals["pred_l2"] < TT_BOUNDS["pred_l2"][2], vals
+    assert vals["vs_composed"] < 2e-2, vals
+
+
 TCN_BOUNDS = {
     "out_rel": (1e-3, 1e-3, 1e-2),           # 8.4e-6   1.1e-6   6.8e-3
     "out_l2": (3e-5, 3e-6, 6e-3),            # 9.4e-6   6.1e-7   3.9e-3

@@ -97,7 +97,7 @@ def test_two_transformers(name, precision, golden_meta, golden_dir):
         # The CCC cotangent of a tiny case (B*T = 18..80 predictions) is nearly constant across elements, so the
         # parameter gradients are differences of large cancelling terms: a 2 % bf16 prediction delta became a 40 %
         # gradient delta on tt_transformer_sa_h2_l1 (and shrinks 4x per halving of the deliberately hot weights --
-        # scratch/debug_sa2.py), which says nothing about the operators.  So the bf16 backward is checked
+        # a round-1 weight-scale sweep), which says nothing about the operators.  So the bf16 backward is checked
         # operator-for-operator: the SAME well-conditioned random cotangent goes through the bf16 engine and the
         # fp32 engine (whose CCC-loss gradients are pinned to the golden vectors by the fp32 leg of this test).
         ref = _load(jmt_b200.Two_transformers(0.0, 0.0, m["heads"], m["layers"], m["joint"], m["fmt"], m["vin"],
@@ -223,6 +223,31 @@ def test_reference_written_checkpoint_loads_into_dropin(precision, golden_meta, 
     assert list(ref_sd.keys()) == list(my_sd.keys())
     for k in ref_sd:
         assert my_sd[k].device.type == "cpu" and torch.equal(ref_sd[k], my_sd[k]), k
+
+
+@pytest.mark.parametrize("precision", ["bf16x3", "bf16"])
+@pytest.mark.parametrize("fmt", ["FC", "SELF_ATTEN"])
+def test_w_jr_standalone_layouts(fmt, precision):
+    """MultimodalTransformer_w_JR used on its own (mm_multi_transformers.py:118-214): the FC head returns (T, B, 1024) -- the
+    reference never permutes back -- the SELF_ATTEN head (B, T, 512); forward and input gradients vs the oracle."""
+    B, T, heads = 3, 11, 2
+    shapes = [(k[len("mm_transformer."):], sh) for k, sh in O.two_transformers_shapes(1, "TRANSFORMER", fmt, 512) if k.startswith("mm_transformer.")]
+    params = O.synth_params(shapes, 77)
+    model = _load(jmt_b200.MultimodalTransformer_w_JR(512, 512, heads, 512, 1, fmt, precision=precision), params).eval()
+    vis, aud = O.synth_features(B, T, [512, 512], 78)
+    vis_d, aud_d = vis.to(DEV).requires_grad_(True), aud.to(DEV).requires_grad_(True)
+    out = model(vis_d, aud_d)
+    vo, ao = vis.clone().requires_grad_(True), aud.clone().requires_grad_(True)
+    po = {k: t.clone() for k, t in params.items()}
+    want = O.w_jr_forward(vo, ao, po, "", heads, 1, fmt)
+    assert tuple(out.shape) == tuple(want.shape) == ((T, B, 1024) if fmt == "FC" else (B, T, 512))
+    tol = 1e-3 if precision == "bf16x3" else PRED_TOL["bf16"]
+    assert _rel(out.detach().cpu(), want.detach()) < tol, _rel(out.detach().cpu(), want.detach())
+    cot = torch.randn(want.shape, generator=torch.Generator().manual_seed(79))
+    (want * cot).sum().backward()
+    (out * cot.to(DEV)).sum().backward()
+    gt = 2e-3 if precision == "bf16x3" else GRAD_L2["bf16"]
+    assert _rl2(vis_d.grad.cpu(), vo.grad) < gt and _rl2(aud_d.grad.cpu(), ao.grad) < gt
 
 
 def test_single_backbone_and_fc(golden_meta, golden_dir):
