@@ -70,6 +70,13 @@ struct TcParams {
   int pair_batch;     // cluster 2 only: 0 = the pair covers two consecutive M tiles, 1 = two consecutive batch entries
   int m_pairs;        // number of M tile slots per (n, batch): ceil(m_tiles / 2) when pairing along M, else m_tiles
   int batch_slots;    // batch_tiles, or batch_tiles / 2 when pairing along the batch
+  // Tail split (wave quantisation): tiles are dealt round-robin to `units` CTAs / CTA pairs, so 300 tiles on 74 pairs take 5 rounds
+  // although they are 4.05 rounds of work.  The tiles of the last, nearly empty round (t >= tail_start in regular numbering) are
+  // cut along N into tail_split pieces of tail_bn columns each (own UMMA instruction descriptor, own B tensor map with a smaller
+  // box), so that round costs a fraction of a tile instead of a whole one.
+  int tail_start, tail_split, tail_bn, b_tail_bytes;
+  uint32_t idesc_tail;
+  FastDiv fd_tsplit;
   unsigned long long* prof;   // optional per-CTA cycle counters (16 per CTA), see jmt_gemm_set_profile_buffer
   int tma_store;      // epilogue through swizzled smem + TMA store / reduce-add (needs 16-byte aligned D geometry)
 };
@@ -125,11 +132,19 @@ __device__ __forceinline__ void epi_math_f32(uint32_t (&r)[32], const float* bia
   }
 }
 
-struct TileCoord { int m0, n0, batch, split, it0, it1; };
+struct TileCoord { int m0, n0, batch, split, it0, it1, bn, tail; };   // bn: columns of this tile (block_n, or tail_bn for a tail piece)
 
 __device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int t, int crank) {
   TileCoord c;
   uint32_t q, nt, mp, bs;
+  uint32_t sub = 0;
+  c.tail = t >= p.tail_start ? 1 : 0;
+  c.bn = c.tail ? p.tail_bn : p.block_n;
+  if (c.tail) {                // piece `sub` of regular tile tail_start + (t - tail_start) / tail_split
+    uint32_t u;
+    p.fd_tsplit.divmod((uint32_t)(t - p.tail_start), u, sub);
+    t = p.tail_start + (int)u;
+  }
   p.fd_ntiles.divmod((uint32_t)t, q, nt);
   p.fd_mpairs.divmod(q, q, mp);
   uint32_t split;
@@ -142,7 +157,7 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int t, int c
     c.m0 = ((int)mp * p.cluster + crank) * kBlockM;
     c.batch = (int)bs;
   }
-  c.n0 = (int)nt * p.block_n;
+  c.n0 = (int)nt * p.block_n + (int)sub * p.tail_bn;
   if (p.split_k == 1) { c.it0 = 0; c.it1 = p.iters_total; }
   else {
     c.it0 = (int)(((int64_t)c.split * p.iters_total) / p.split_k);
@@ -161,6 +176,7 @@ struct EpiCtx {
 #endif
   uint32_t tempty;            // accumulator-stage 'empty' barrier (leader CTA's, cluster address when kCta == 2)
   int m0w, n0, b0, b1, part, parts, lane;   // part / parts: this warp's interleaved share of the tile's column chunks
+  int bn;                                   // columns of this tile
 };
 
 // One epilogue warp's share of a 128 x block_n accumulator tile: its 32 TMEM lanes (rows) x every other
@@ -197,9 +213,9 @@ __device__ __forceinline__ bool epi_tile(const TcParams& p, const CUtensorMap* t
       // one 64-column chunk (a [32 rows x 128 B] staging tile) per iteration, in two 32-column halves so that only
       // r[32] + pk[16] are live (the 16-warp kernel has 112 registers per thread): the second half's tcgen05.ld is in
       // flight while the first half waits for the previous TMA store and is written to the staging tile
-      for (int c0 = e.part * 64; c0 < p.block_n; c0 += 64 * e.parts) {
+      for (int c0 = e.part * 64; c0 < e.bn; c0 += 64 * e.parts) {
         if (e.n0 + c0 >= p.N) break;
-        const bool second = c0 + 32 < p.block_n;      // block_n is a multiple of 32
+        const bool second = c0 + 32 < e.bn;      // block_n is a multiple of 32
         uint32_t r[32], pk[16];
         EPI_T0();
         tc_ld32_issue(e.tbase + c0, r);
@@ -219,7 +235,7 @@ __device__ __forceinline__ bool epi_tile(const TcParams& p, const CUtensorMap* t
         // last chunk of this warp's share: every TMEM read of the tile has landed in registers, hand the accumulator stage
         // back to the MMA issuer before the remaining math / staging / store
         const int c_next = c0 + 64 * e.parts;
-        if (c_next >= p.block_n || e.n0 + c_next >= p.N) { epi_release<kCta>(e.tempty, lane); released = true; }
+        if (c_next >= e.bn || e.n0 + c_next >= p.N) { epi_release<kCta>(e.tempty, lane); released = true; }
         if (second) {
           epi_math_bf16<ACT, MASK>(r, e.bias + c0 + 32, MASK ? e.fwords[(c0 >> 5) + 1] : 0u, p.colmask_scale, e.keep, p.alpha, p.slope, pk);
         } else {
@@ -240,12 +256,12 @@ __device__ __forceinline__ bool epi_tile(const TcParams& p, const CUtensorMap* t
         EPI_T(5);
       }
     } else {
-      for (int c0 = e.part * 32; c0 < p.block_n; c0 += 32 * e.parts) {
+      for (int c0 = e.part * 32; c0 < e.bn; c0 += 32 * e.parts) {
         if (e.n0 + c0 >= p.N) break;
         uint32_t r[32];
         tc_ld32(e.tbase + c0, r);
         const int c_next = c0 + 32 * e.parts;
-        if (c_next >= p.block_n || e.n0 + c_next >= p.N) { epi_release<kCta>(e.tempty, lane); released = true; }
+        if (c_next >= e.bn || e.n0 + c_next >= p.N) { epi_release<kCta>(e.tempty, lane); released = true; }
         epi_math_f32<ACT, MASK>(r, e.bias + c0, MASK ? e.fwords[c0 >> 5] : 0u, p.colmask_scale, e.keep, p.alpha, p.slope);
         if (lane == 0) bulk_wait_read0();
         __syncwarp();
@@ -265,7 +281,7 @@ __device__ __forceinline__ bool epi_tile(const TcParams& p, const CUtensorMap* t
     // direct (unaligned D geometry): per-thread row stores / atomics
     const int m = e.m0w + lane;
     const int64_t row_off = (int64_t)e.b0 * p.d_bs0 + (int64_t)e.b1 * p.d_bs1 + (int64_t)m * p.d_ld;
-    for (int c0 = e.part * 32; c0 < p.block_n; c0 += 32 * e.parts) {
+    for (int c0 = e.part * 32; c0 < e.bn; c0 += 32 * e.parts) {
       const int n = e.n0 + c0;
       if (n >= p.N) break;                      // warp-uniform
       uint32_t r[32];
@@ -384,8 +400,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a_hi, const __grid_consta
           const long long tw = p.prof ? clock64() : 0;
           mbar_wait(empty_bar + 8 * stage, phase ^ 1);
           if (p.prof) pr_wait += clock64() - tw;
-          if constexpr (kCta == 1) mbar_expect_tx(full_bar + 8 * stage, kOps * (kAStageBytes + p.b_tx_bytes));
-          else mbar_expect_tx_cluster(full_leader + 8 * stage, kOps * (kAStageBytes + p.b_tx_bytes));
+          const int b_tx = c.tail ? p.b_tail_bytes : p.b_tx_bytes;
+          if constexpr (kCta == 1) mbar_expect_tx(full_bar + 8 * stage, kOps * (kAStageBytes + b_tx));
+          else mbar_expect_tx_cluster(full_leader + 8 * stage, kOps * (kAStageBytes + b_tx));
 #pragma unroll
           for (int part = 0; part < kOps; ++part) {          // kX3: part 0 = hi tiles, part 1 = lo tiles (same coordinates)
           const CUtensorMap& tma_a = part == 0 ? tma_a_hi : tma_a_lo;
@@ -402,7 +419,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a_hi, const __grid_consta
               tma_load_4d(a_dst, &tma_a, fb, c.m0, kb * kBlockK + ash, ab0, ab1);
               tma_load_4d(a_dst + 8192, &tma_a, fb, c.m0 + 64, kb * kBlockK + ash, ab0, ab1);
             }
-            if (p.b_major == JMT_MAJOR_K) {
+            if (!kX3 && c.tail) {      // tail piece: the tail map's box holds exactly this piece (tma_b_lo slot, unused without kX3)
+              if (p.b_major == JMT_MAJOR_K) tma_load_4d(b_dst, &tma_b_lo, fb, tap * p.K + kb * kBlockK, c.n0, bb0, bb1);
+              else tma_load_5d(b_dst, &tma_b_lo, fb, 0, kb * kBlockK + bsh, c.n0 >> 6, bb0, bb1);
+            } else if (p.b_major == JMT_MAJOR_K) {
               tma_load_4d(b_dst, &tma_b, fb, tap * p.K + kb * kBlockK, c.n0, bb0, bb1);
             } else if (p.b_mn5) {
               tma_load_5d(b_dst, &tma_b, fb, 0, kb * kBlockK + bsh, c.n0 >> 6, bb0, bb1);
@@ -420,7 +440,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a_hi, const __grid_consta
               tma_load_4d_2sm(a_dst, &tma_a, fb, c.m0, kb * kBlockK + ash, ab0, ab1);
               tma_load_4d_2sm(a_dst + 8192, &tma_a, fb, c.m0 + 64, kb * kBlockK + ash, ab0, ab1);
             }
-            if (p.wide) {          // two 128-column pieces: this CTA's share of the B operand of each of the two MMAs
+            if (!kX3 && c.tail) {      // tail piece: this CTA's half of it through the tail map (tma_b_lo slot, unused without kX3)
+              const int n_t = c.n0 + crank * (p.tail_bn / kCta);
+              if (p.b_major == JMT_MAJOR_K) tma_load_4d_2sm(b_dst, &tma_b_lo, fb, tap * p.K + kb * kBlockK, n_t, bb0, bb1);
+              else tma_load_5d_2sm(b_dst, &tma_b_lo, fb, 0, kb * kBlockK + bsh, n_t >> 6, bb0, bb1);
+            } else if (p.wide) {          // two 128-column pieces: this CTA's share of the B operand of each of the two MMAs
 #pragma unroll
               for (int h = 0; h < 2; ++h) {
                 const int n_h = c.n0 + h * 256 + crank * 128;
@@ -475,13 +499,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a_hi, const __grid_consta
           const uint64_t b_desc = make_smem_desc(sB + stage * b_stride, b_lbo, 1024);
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-            tc_mma<kCta>(d_tmem, a_desc + (uint64_t)(k * a_kstep), b_desc + (uint64_t)(k * b_kstep), p.idesc,
+            tc_mma<kCta>(d_tmem, a_desc + (uint64_t)(k * a_kstep), b_desc + (uint64_t)(k * b_kstep), c.tail ? p.idesc_tail : p.idesc,
                          (it > c.it0 || k > 0) ? 1u : 0u);
             if constexpr (kX3) {   // + A_hi B_lo + A_lo B_hi (the lo tiles sit one tile behind the hi tiles; descriptor units of 16 B)
               tc_mma<kCta>(d_tmem, a_desc + (uint64_t)(k * a_kstep), b_desc + (uint64_t)((p.b_stage_bytes >> 4) + k * b_kstep), p.idesc, 1u);
               tc_mma<kCta>(d_tmem, a_desc + (uint64_t)((kAStageBytes >> 4) + k * a_kstep), b_desc + (uint64_t)(k * b_kstep), p.idesc, 1u);
             }
-            if (p.wide)      // columns 256..511 of the tile: same A, second B piece (16 KB further), TMEM columns 256..511
+            if (p.wide && !c.tail)      // columns 256..511 of the tile: same A, second B piece (16 KB further), TMEM columns 256..511
               tc_mma<kCta>(d_tmem + 256, a_desc + (uint64_t)(k * a_kstep), b_desc + (uint64_t)(1024 + k * b_kstep), p.idesc,
                            (it > c.it0 || k > 0) ? 1u : 0u);
           }
@@ -529,7 +553,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a_hi, const __grid_consta
         const bool add_bias = p.bias != nullptr && split == 0;
         if (!bias_dbuf) asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpi) : "memory");     // previous tile's readers are done
         // every epilogue thread takes columns et, et + 32 * kEpi, ... of the tile (warp-uniform trip count: block_n % 32 == 0)
-        for (int e2 = et; e2 < p.block_n; e2 += 32 * kEpi) {
+        for (int e2 = et; e2 < c.bn; e2 += 32 * kEpi) {
           const bool in_n = c.n0 + e2 < p.N;
           bias_tile[e2] = (add_bias && in_n) ? __ldg(p.bias + c.n0 + e2) : 0.f;
           if constexpr (kMask) {
@@ -563,6 +587,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a_hi, const __grid_consta
         ec.fwords = fw;
       }
       ec.m0w = c.m0 + q * 32; ec.n0 = c.n0; ec.b0 = (int)b0u; ec.b1 = (int)b1u; ec.part = part; ec.parts = kEpi / 4; ec.lane = lane;
+      ec.bn = c.bn;
       // (kMask: channel dropout fused after the activation, TCN -- a separate kernel instantiation so that its extra
       //  register pressure never touches the common kernels)
       ec.tempty = (kCta == 1 ? tempty_bar : tempty_leader) + 8 * acc;
@@ -749,6 +774,36 @@ static int gemm_tc_launch(const jmt_gemm_desc* g, const void* a_lo, const void* 
       rc = make_map(&map_b_lo, b_lo, g->N, g->b_rows, g->b_ld, bnb0, g->b_bs0, bnb1, g->b_bs1, kBlockK, "jmt_gemm_bf16x3(B lo)");
     if (rc != JMT_OK) return rc;
   }
+
+  // Tail split: cut the tiles of a nearly empty last round along N (see TcParams).  Needs whole tiles per CTA in one pass (no
+  // split-K / batch reduction) and, for MN-major B, whole 64-column chunks per CTA.  JMT_GEMM_TAIL=0 disables.
+  p.tail_start = p.total_tiles; p.tail_split = 1; p.tail_bn = p.block_n; p.idesc_tail = p.idesc; p.b_tail_bytes = p.b_tx_bytes;
+  {
+    static const int tail_env = []() { const char* e = getenv("JMT_GEMM_TAIL"); return e ? atoi(e) : 1; }();
+    const int units = kNumSMs / p.cluster;
+    const int rem = p.total_tiles % units;
+    const int gran = g->b_major == JMT_MAJOR_K ? 64 : 64 * p.cluster;
+    const bool b_ok = g->b_major == JMT_MAJOR_K || p.b_mn5;
+    if (tail_env && !x3 && p.split_k == 1 && !p.reduce_batch && b_ok && p.total_tiles > units && rem > 0 && 2 * rem <= units) {
+      int sp = 1;
+      while (sp < 8 && rem * sp * 2 <= units && p.block_n % (sp * 2) == 0 && (p.block_n / (sp * 2)) % gran == 0) sp *= 2;
+      if (sp > 1 && p.block_n / sp <= 256) {
+        p.tail_split = sp;
+        p.tail_bn = p.block_n / sp;
+        p.tail_start = p.total_tiles - rem;
+        p.total_tiles = p.tail_start + rem * sp;
+        p.idesc_tail = (p.idesc & ~(0x3Fu << 17)) | ((uint32_t)(p.tail_bn >> 3) << 17);
+        const int rows_cta = p.tail_bn / p.cluster;
+        p.b_tail_bytes = g->b_major == JMT_MAJOR_K ? rows_cta * 128 : (rows_cta / 64) * 8192;
+        if (g->b_major == JMT_MAJOR_K)
+          rc = make_map(&map_b_lo, g->b, (int64_t)g->ntaps * g->K, g->b_rows, g->b_ld, bnb0, g->b_bs0, bnb1, g->b_bs1, rows_cta, "jmt_gemm_bf16(B tail)");
+        else
+          rc = make_map_mn5(&map_b_lo, g->b, g->N, g->b_rows, g->b_ld, bnb0, g->b_bs0, bnb1, g->b_bs1, kBlockK, rows_cta / 64, "jmt_gemm_bf16(B tail)");
+        if (rc != JMT_OK) return rc;
+      }
+    }
+  }
+  p.fd_tsplit.init(p.tail_split);
 
   // D through TMA (store / reduce-add) when its geometry is 16-byte aligned; bf16 read-modify-write
   // accumulation and fp32 atomics both become cp.reduce.async.bulk.tensor .add

@@ -643,6 +643,8 @@ def _proj_grad_slice(ctx: Ctx, v: Var, c0: int, c1: int) -> Tuple[torch.Tensor, 
 FUSED_ATTENTION = True      # bf16 mode: True = QK^T -> softmax -> PV in one kernel when the geometry is supported; "p" = QK^T +
                             # softmax fused, PV a plain GEMM (measured 1.4 % slower per step); False = GEMM + softmax kernels
 LONG_S_CHUNKED = True       # forward-only attention beyond the fused kernel's key limit: chunked fused kernel + log-sum-exp merge
+LONG_S_CHUNK_MIN_BYTES = 2 << 30   # ... once the fp32 score tensor of the composed path would exceed this (measured: NONE eval at
+                                   # B = 1024, 1.26 GB of scores, 7.4 ms composed vs 9.1 ms chunked; B = 4096, 20 GB: chunked only)
 FUSED_ATTENTION_BWD = "ds"   # "ds": dP GEMM + softmax backward fused (dS on chip, dQ/dK/dV plain GEMMs); "full": dP -> dS -> dQ in one
                              # kernel (correct, not faster than the composition yet); False: GEMM + softmax_bwd kernel
 
@@ -705,7 +707,8 @@ def attention_core(ctx: Ctx, q: Var, qcol: int, k: Var, kcol: int, v: Var, vcol:
     if FUSED_ATTENTION and ctx.adt == torch.bfloat16:
         fused = _attn_chain(ctx, 0, qd, q_geo, kd, k_geo, vd, v_geo, None, o, o, o_geo, Lq, S, dh, heads, NB, s_ld, scale,
                             L.STORE, probe_only=True)
-    if not fused and FUSED_ATTENTION and ctx.adt == torch.bfloat16 and not ctx.record and LONG_S_CHUNKED:
+    if (not fused and FUSED_ATTENTION and ctx.adt == torch.bfloat16 and not ctx.record and LONG_S_CHUNKED and
+            4 * NB * heads * Lq * s_ld >= LONG_S_CHUNK_MIN_BYTES):
         # Long key sequences, forward only (evaluation; SURVEY 7.6a: the batch-dimension attention of the NONE variant at
         # large batch): the fused kernel over key chunks + running log-sum-exp merge.  Neither the (L, S) scores nor the
         # probabilities ever reach memory.  (A backward needs the probabilities: training keeps the composed path below.)

@@ -160,7 +160,7 @@ def test_two_transformers_default_init(name, precision, golden_meta, golden_dir)
     _check(name, precision, vals, TT_BOUNDS)
 
 
-@pytest.mark.parametrize("name", ["ttd_none_fc_b400_t2", "ttd_none_fc_b600_t1_h2", "ttd_none_fc_b300_t2"])
+@pytest.mark.parametrize("name", ["ttd_none_fc_b600_t1_h2", "ttd_none_fc_b400_t2"])
 def test_long_key_attention_forward_only_chunked(name, golden_meta, golden_dir):
     """Evaluation (no_grad) of the NONE variant whose encoders attend across the batch (L = S = B) beyond the fused
     kernel's key limit: the engine runs the fused kernel over key chunks and merges with the running log-sum-exp
@@ -172,6 +172,9 @@ def test_long_key_attention_forward_only_chunked(name, golden_meta, golden_dir):
     torch.manual_seed(m["init_seed"])
     model = jmt_b200.Two_transformers(0.0, 0.0, m["heads"], m["layers"], m["joint"], m["fmt"], m["vin"], precision="bf16").to(DEV).eval()
     aud, vis = (t.to(DEV) for t in O.synth_features(m["B"], m["T"], [512, m["vin"]], m["feat_seed"]))
+    E.LONG_S_CHUNK_MIN_BYTES = 0           # (the engine keeps the composed path while the fp32 scores are small)
+    with torch.no_grad():
+        model(aud, vis)                   # warm the bf16 operand cache so that the launch counts below are comparable
     n0 = jmt_b200.launch_count()
     with torch.no_grad():
         v, a = model(aud, vis)
@@ -184,12 +187,15 @@ def test_long_key_attention_forward_only_chunked(name, golden_meta, golden_dir):
         n_composed = jmt_b200.launch_count() - n0
     finally:
         E.LONG_S_CHUNKED = True
+        E.LONG_S_CHUNK_MIN_BYTES = 2 << 30
     vals = {"pred_rel": max(_rel(v.cpu(), g["vout"]), _rel(a.cpu(), g["aout"])),
             "pred_l2": max(_rl2(v.cpu(), g["vout"]), _rl2(a.cpu(), g["aout"])),
             "vs_composed": max(_rel(v.cpu(), v2.cpu()), _rel(a.cpu(), a2.cpu()))}
     _record(name + "/chunked_eval", "bf16", vals)
-    if m["B"] > 320:
+    if m["B"] > 512:                      # S = B = 600 > 512 keys: beyond one fused tile -> chunks + merge launches
         assert n_chunked != n_composed, "the chunked path was not taken"
+    else:                                 # S = 400 at dh = 512 still fits one fused tile (fewer operand slots)
+        assert n_chunked == n_composed
     assert vals["pred_rel"] < TT_BOUNDS["pred_rel"][2] and vals["pred_l2"] < TT_BOUNDS["pred_l2"][2], vals
     assert vals["vs_composed"] < 2e-2, vals
 

@@ -30,10 +30,9 @@ def _ref_gemm(A, B, *, a_major, b_major, M, N, K, ntaps, a_shift, b_shift, nb, r
             a2 = A[b].double()
             if a_major == L.MAJOR_K:        # stored (a_rows, K): row m+ash
                 Am = torch.zeros(M, K, dtype=torch.float64)
-                for m in range(M):
-                    r = m + ash
-                    if 0 <= r < a2.shape[0]:
-                        Am[m] = a2[r, :K]
+                rows = torch.arange(M) + ash
+                ok = (rows >= 0) & (rows < a2.shape[0])
+                Am[ok] = a2[rows[ok], :K]
             else:                            # stored (k rows, M): row k+ash
                 Am = torch.zeros(M, K, dtype=torch.float64)
                 for k in range(K):
@@ -95,6 +94,12 @@ GEMM_CASES = [
     ("wide_wgrad_mnmn", 512, 512, 3200, 1, 1, 1, 1, (0, 0), (0, 0), False, 2, 0, False, "f32", 2),
     ("wide_conv_dgrad_taps", 1100, 512, 320, 0, 0, 1, 5, (8, -2), (0, 0), False, 1, 0, False, "act", 0),
     ("wide_nn_bmn", 512, 512, 1600, 0, 1, 2, 1, (0, 0), (0, 0), False, 1, 0, False, "act", 0),
+    # tail split: the tiles of a nearly empty last round (78 pair tiles on 74 CTA pairs, 156 tiles on 148 CTAs) are cut along N
+    # into pieces with their own UMMA descriptor and B tensor map
+    ("tail_tn_bias_relu", 256 * 78, 256, 128, 0, 0, 1, 1, (0, 0), (0, 0), False, 1, 1, True, "act", 0),
+    ("tail_wide_nn_bmn_acc", 256 * 78, 512, 512, 0, 1, 1, 1, (0, 0), (0, 0), False, 1, 0, False, "act", 1),
+    ("tail_wide_tn_f32", 256 * 78 - 40, 512, 576, 0, 0, 1, 1, (0, 0), (0, 0), False, 1, 2, True, "f32", 0),
+    ("tail_1cta_batched", 300, 256, 64, 0, 0, 52, 1, (0, 0), (0, 0), False, 1, 0, True, "act", 0),
 ]
 
 
@@ -188,7 +193,8 @@ def test_gemm_colmask(precision, nb):
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16x3", "bf16"])
-@pytest.mark.parametrize("geom", [(5, 77, 8, 64, 96, 3, 4), (6, 77, 8, 192, 512, 3, 4)], ids=["narrow", "wide512"])
+@pytest.mark.parametrize("geom", [(5, 77, 8, 64, 96, 3, 4), (6, 77, 8, 192, 512, 3, 4), (236, 77, 8, 192, 512, 3, 4)],
+                         ids=["narrow", "wide512", "wide512_tail"])
 def test_gemm_flat_tcn_layout(precision, geom):
     """Flat padded TCN layout: one GEMM over N*(pad+L) rows with row shifts, padding rows written as zeros
     (zero_row_period) and the channel-dropout mask row taken from m / period -- against per-sequence causal convs."""
@@ -203,15 +209,14 @@ def test_gemm_flat_tcn_layout(precision, geom):
     bias = torch.randn(cout)
     mask = (torch.rand(Nn, cout) > 0.4).to(torch.uint8)
     ref = torch.zeros(Nn, Lp, cout, dtype=torch.float64)
-    for n in range(Nn):
-        for t in range(Ls):
-            acc = bias.double().clone()
-            for j in range(taps):
-                src = t - (taps - 1 - j) * dil
-                if src >= 0:
-                    acc += w[:, j * cin:(j + 1) * cin].double() @ x[n, pad + src].double()
-            acc = torch.where(acc >= 0, acc, acc * 0.01)
-            ref[n, pad + t] = acc * mask[n].double() * 1.5
+    xs = x[:, pad:].double()                                           # (Nn, Ls, cin)
+    acc = bias.double().expand(Nn, Ls, cout).clone()
+    for j in range(taps):
+        sh = (taps - 1 - j) * dil                                      # out[t] += W_j x[t - sh], zeros for t < sh
+        if sh < Ls:
+            acc[:, sh:] += xs[:, :Ls - sh] @ w[:, j * cin:(j + 1) * cin].double().t()
+    acc = torch.where(acc >= 0, acc, acc * 0.01)
+    ref[:, pad:] = acc * (mask.double() * 1.5)[:, None, :]
     xd, wd, md = x.reshape(Nn * Lp, cin).to(dev, dt), w.to(dev, dt), mask.to(dev)
     d = torch.full((Nn * Lp, cout), float("nan"), device=dev, dtype=dt)
     E.gemm(_ctx(precision), xd, wd, d, M=Nn * Lp, N=cout, K=cin, a_rows=Nn * Lp, b_rows=cout, a_ld=cin, b_ld=taps * cin, d_ld=cout,
