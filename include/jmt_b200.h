@@ -111,6 +111,8 @@ typedef struct {
    * the causal left padding of the next conv and the right padding of the previous sequence's dgrad, so a 128-row tile
    * is never 56 % empty as with M = L = 300 per batch entry):
    *   colmask_row_period > 0: the keep-mask row is  m / colmask_row_period  instead of the batch index (nb0 = nb1 = 1);
+   *                           must be >= 127 (a 128-row tile stages the keep-flags of at most two samples; shorter sequences:
+   *                           run the GEMM without colmask and apply the mask with jmt_apply_mask);
    *   zero_row_period > 0:    output rows with (m % zero_row_period) < zero_row_count contribute zeros (stored as 0 /
    *                           nothing added): the padding rows must stay zero for the next layer. */
   int32_t colmask_row_period;

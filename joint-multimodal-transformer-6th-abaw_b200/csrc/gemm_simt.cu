@@ -141,6 +141,10 @@ int jmt_validate_gemm_desc(const jmt_gemm_desc* g, const char* who) {
   JMT_REQUIRE(!(g->colmask && (g->reduce_batch || g->split_k > 1)), "%s: colmask needs reduce_batch == 0 and split_k == 1", who);
   JMT_REQUIRE(g->colmask_row_period >= 0 && g->zero_row_period >= 0 && g->zero_row_count >= 0, "%s: negative row period", who);
   JMT_REQUIRE(!(g->colmask_row_period > 0 && g->nb0 * g->nb1 != 1), "%s: colmask_row_period needs nb0 = nb1 = 1", who);
+  // the tensor-core epilogue stages the keep-flags of at most TWO samples per 128-row tile
+  JMT_REQUIRE(!(g->colmask && g->colmask_row_period > 0 && g->colmask_row_period < 127),
+              "%s: colmask_row_period must be >= 127 (a 128-row tile may span at most two samples); apply the mask with "
+              "jmt_apply_mask instead", who);
   JMT_REQUIRE(!(g->zero_row_period > 0 && g->reduce_batch), "%s: zero_row_period cannot be combined with reduce_batch", who);
   return JMT_OK;
 }

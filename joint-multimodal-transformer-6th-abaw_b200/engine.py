@@ -195,6 +195,35 @@ class Ctx:
             self._w[name] = t
         return t
 
+    def cat_params(self, names: Sequence[str], as_operand: bool) -> torch.Tensor:
+        """Row-wise concatenation of same-width parameters in one buffer (operand dtype when `as_operand`, else fp32): lets
+        independent Linears that read the same input run as ONE GEMM (the valence | arousal regressor heads,
+        two_transformers.py:104-114).  Cached like w() (per storage / version / replay generation, never across a capture)."""
+        key_name = "|".join(names) + ("|op" if as_operand else "|f32")
+        t = self._w.get(key_name)
+        if t is not None:
+            return t
+        pars = [self.params[n] for n in names]
+        dt = self.adt if as_operand else torch.float32
+        key = tuple((p.data_ptr(), p._version, tuple(p.shape)) for p in pars) + (_PARAM_GENERATION[0],)
+        capturing = torch.cuda.is_current_stream_capturing()
+        ent = None if capturing else self.wcache.get(key_name)
+        if ent is None or ent[0] != key:
+            rows = sum(p.shape[0] for p in pars)
+            out = torch.empty((rows,) + tuple(pars[0].shape[1:]), dtype=dt, device=pars[0].device)
+            r0 = 0
+            for p in pars:
+                L.check(self.lib.jmt_cast(_ptr(p), L.F32, _ptr(out[r0:r0 + p.shape[0]]), _DT[dt], p.numel(), _stream()), "jmt_cast")
+                r0 += p.shape[0]
+            ent = (key, out)
+            if not capturing:
+                self.wcache[key_name] = ent
+        t = ent[1]
+        self._w[key_name] = t
+        if self.x3 and as_operand:
+            self.x3_const.append((t.data_ptr(), t.data_ptr() + t.numel() * 4))
+        return t
+
     def prepare_param_grads(self, names: Sequence[str]):
         """Allocate the flat fp32 gradient bucket (zeroed) with one 256-byte aligned view per parameter."""
         total = 0
@@ -973,6 +1002,71 @@ def regressor_tail(ctx: Ctx, hidden: List[Var], wnames: List[str], bnames: List[
     return outs, set_gout
 
 
+def regressor_heads(ctx: Ctx, x: Var, pre: Sequence[str], B: int, T: int, time_major: bool):
+    """The two regressor heads `Linear(dim,128) -> ReLU -> Dropout(p = 0) -> Linear(128,1)` (two_transformers.py:104-114) on the
+    same features: the hidden layers run as ONE N = 256 GEMM on the stacked weights (valence rows | arousal rows), the
+    Linear(128,1) pair as the fused regressor tail, the backward as one batched wgrad launch (the two CTAs of a pair take the
+    two heads and share the x tile), one K = 256 dgrad and the tail kernel (which already applies the ReLU mask).
+    `pre` = the two parameter prefixes, e.g. ("vregressor.", "aregressor.").  Returns (outputs, gradient setter)."""
+    wn, bn = [p + "0.weight" for p in pre], [p + "0.bias" for p in pre]
+    Wc = ctx.cat_params(wn, True)                       # (256, dim) operand dtype
+    bc = ctx.cat_params(bn, False)                      # (256,) fp32
+    M, K = x.data.shape
+    H = ctx.empty((M, 256))
+    gemm(ctx, x.data, Wc, H, M=M, N=256, K=K, bias=bc, act=L.ACT_RELU)
+    shape = (T, B) if time_major else (B, T)
+    sb, st = (1, B) if time_major else (T, 1)
+    outs = [ctx.empty(shape, torch.float32) for _ in range(2)]
+    hl = [H[:, 0:128], H[:, 128:256]]
+    ws = [ctx.p(p + "3.weight")[0] for p in pre]
+    bs = [ctx.p(p + "3.bias")[0:1] for p in pre]
+    L.check(ctx.lib.jmt_regressor_tail_fwd(2, _ptr_array(ctx, hl), 256, ctx.acode, _ptr_array(ctx, ws), _ptr_array(ctx, bs),
+                                           _ptr_array(ctx, outs), M, T, sb, st, _stream()), "jmt_regressor_tail_fwd")
+    gouts: List[Optional[torch.Tensor]] = [None, None]
+    if ctx.record:
+        def bwd():
+            douts = []
+            for g in range(2):
+                d = gouts[g]
+                if d is None:
+                    d = ctx.zeros(shape, torch.float32)
+                elif not d.is_contiguous() or d.dtype != torch.float32:
+                    raise RuntimeError("jmt_b200: output gradients must be contiguous fp32 tensors")
+                douts.append(d)
+            dH = ctx.empty((M, 256))
+            dhl = [dH[:, 0:128], dH[:, 128:256]]
+            dws = [ctx.pgrad(p + "3.weight")[0] for p in pre]
+            dbs = [ctx.pgrad(p + "3.bias")[0:1] for p in pre]
+            acc_arr, sc_arr = (C.c_int * 2)(0, 0), (C.c_float * 2)(1.0, 1.0)
+            ctx.keep += [acc_arr, sc_arr]
+            # dH = d(pre-activation hidden): the tail kernel applies the ReLU mask (h > 0) itself
+            L.check(ctx.lib.jmt_regressor_tail_bwd(2, _ptr_array(ctx, hl), 256, ctx.acode, _ptr_array(ctx, ws), _ptr_array(ctx, douts),
+                                                   _ptr_array(ctx, dhl), acc_arr, sc_arr, _ptr_array(ctx, dws), _ptr_array(ctx, dbs),
+                                                   M, T, sb, st, _stream()), "jmt_regressor_tail_bwd")
+            for g in range(2):
+                L.check(ctx.lib.jmt_colsum(_ptr(dhl[g]), ctx.acode, 256, M, 128, _ptr(ctx.pgrad(bn[g])), _stream()), "jmt_colsum")
+            # dW_v | dW_a = dH_v^T x | dH_a^T x: one launch, batch entry = head (A = column half of dH, B = x shared, D = the two
+            # parameter gradients at their distance in the flat bucket)
+            g0, g1 = ctx.pgrad(wn[0]), ctx.pgrad(wn[1])
+            dist = (g1.data_ptr() - g0.data_ptr()) // 4
+            if dist > 0 and dist % 4 == 0:
+                gemm(ctx, dH, x.data, g0, M=128, N=K, K=M, a_major=L.MAJOR_MN, b_major=L.MAJOR_MN, a_rows=M, b_rows=M,
+                     a_ld=256, b_ld=x.data.stride(0), d_ld=K, nb1=2, a_bs=(0, 128), b_bs=(0, 0), d_bs=(0, dist),
+                     store=L.ATOMIC_ADD, split_k=wgrad_split(M, 128, K, 2))
+            else:
+                for g, gw in enumerate((g0, g1)):
+                    gemm(ctx, dhl[g], x.data, gw, M=128, N=K, K=M, a_major=L.MAJOR_MN, b_major=L.MAJOR_MN, a_rows=M, b_rows=M,
+                         a_ld=256, store=L.ATOMIC_ADD, split_k=wgrad_split(M, 128, K))
+            if x.needs_grad:
+                dx, mode = ctx.grad_target(x)
+                gemm(ctx, dH, Wc, dx, M=M, N=K, K=256, b_major=L.MAJOR_MN, store=mode)
+        ctx.tape.append(bwd)
+
+    def set_gout(g, t):
+        gouts[g] = t
+    return outs, set_gout
+
+
 # --------------------------------------------------------------------------- TCN ops
 # Flat padded layout: all N sequences live in ONE channels-last matrix of N * (pad + L) rows, row = n*(pad+L) + pad + t,
 # with `pad` >= (k-1)*max_dilation ZERO rows in front of every sequence.  Those rows are the causal left padding of the
@@ -1057,10 +1151,15 @@ def causal_conv(ctx: Ctx, x: Var, prefix: str, N: int, Ls: int, cin: int, cout: 
         mscale = 1.0 / (1.0 - drop_p)
     # algorithmic FLOPs = useful taps only: tap j touches L - (k-1-j)*dil positions of each sequence
     tap_flops = [2.0 * N * max(0, Ls - (k - 1 - j) * dil) * cout * cin for j in range(k)]
+    # the GEMM epilogue stages the keep-flags of at most two samples per 128-row tile: sequences shorter than that (the
+    # reference-faithful placement with L = 7 clips, tsav.py:214-216) get the mask from a separate pass over y
+    fuse_mask = mask is not None and Lp >= 127
     gemm(ctx, x.data, w_fwd, y, M=R, N=cout, K=cin, a_rows=R, b_rows=cout, a_ld=cin, b_ld=k * cin, d_ld=cout,
          bias=bias, act=act, slope=LEAKY_SLOPE, ntaps=k, a_shift=(-(k - 1) * dil, dil),
-         colmask=mask, colmask_scale=mscale, colmask_row_period=Lp if mask is not None else 0, zero_rows=(Lp, pad),
-         alg_flops=sum(tap_flops))
+         colmask=mask if fuse_mask else None, colmask_scale=mscale, colmask_row_period=Lp if fuse_mask else 0,
+         zero_rows=(Lp, pad), alg_flops=sum(tap_flops))
+    if mask is not None and not fuse_mask:
+        L.check(ctx.lib.jmt_apply_mask(_ptr(y), _ptr(mask), _ptr(y), N, Lp, cout, 1, mscale, ctx.acode, _stream()), "jmt_apply_mask")
     out = Var(y)
     if ctx.record:
         def bwd():

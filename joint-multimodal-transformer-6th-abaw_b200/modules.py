@@ -421,6 +421,11 @@ def _two_transformers_graph(ctx, mod, prefix, video, audio, B, T):
         feats = _concat_fc_graph(ctx, video, audio, m)
     else:
         feats = _wo_jr_graph(ctx, video, audio, m, mod.num_heads, mod.num_layers, B, T)
+    drop_on = ctx.training and (mod.v_dropout > 0.0 or mod.a_dropout > 0.0)
+    if not drop_on and os.environ.get("JMT_REGRESSOR_PAIR", "1") != "0":
+        # (the reference default, config_file.json:69-70: p = 0) both hidden layers as one N = 256 GEMM
+        outs, set_gout = E.regressor_heads(ctx, feats, (prefix + "vregressor.", prefix + "aregressor."), B, T, time_major)
+        return outs, [lambda t: set_gout(0, t), lambda t: set_gout(1, t)]
     hv = E.linear(ctx, feats, prefix + "vregressor.0.weight", prefix + "vregressor.0.bias", act=L.ACT_RELU)
     ha = E.linear(ctx, feats, prefix + "aregressor.0.weight", prefix + "aregressor.0.bias", act=L.ACT_RELU)
     hv, _ = E.dropout(ctx, hv, mod.v_dropout)

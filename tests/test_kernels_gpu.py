@@ -193,7 +193,7 @@ def test_gemm_colmask(precision, nb):
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16x3", "bf16"])
-@pytest.mark.parametrize("geom", [(5, 77, 8, 64, 96, 3, 4), (6, 77, 8, 192, 512, 3, 4), (236, 77, 8, 192, 512, 3, 4)],
+@pytest.mark.parametrize("geom", [(5, 130, 8, 64, 96, 3, 4), (6, 130, 8, 192, 512, 3, 4), (146, 130, 8, 192, 512, 3, 4)],
                          ids=["narrow", "wide512", "wide512_tail"])
 def test_gemm_flat_tcn_layout(precision, geom):
     """Flat padded TCN layout: one GEMM over N*(pad+L) rows with row shifts, padding rows written as zeros
@@ -227,6 +227,42 @@ def test_gemm_flat_tcn_layout(precision, geom):
     tol = {"fp32": 2e-4, "bf16x3": 6e-5, "bf16": 1.2e-2}[precision]
     assert (got - ref).abs().max() < tol * (ref.abs().max() + 1e-6), (got - ref).abs().max()
     assert (got[:, :pad] == 0).all(), "padding rows must be written as zeros"
+    if precision != "fp32":
+        # sequences shorter than a tile would need the keep-flags of more than two samples per tile: refused, not mis-computed
+        with pytest.raises(RuntimeError, match="colmask_row_period"):
+            E.gemm(_ctx(precision), xd, wd, d, M=Nn * Lp, N=cout, K=cin, a_rows=Nn * Lp, b_rows=cout, a_ld=cin, b_ld=taps * cin,
+                   d_ld=cout, ntaps=taps, a_shift=(-(taps - 1) * dil, dil), colmask=md, colmask_scale=1.5, colmask_row_period=64)
+
+
+@pytest.mark.parametrize("precision", ["bf16x3", "bf16"])
+@pytest.mark.parametrize("Ls", [7, 200])
+def test_causal_conv_channel_dropout_short_and_long_sequences(precision, Ls):
+    """Dropout2d of the TCN in training mode (whole channels per sample) through engine.causal_conv: fused into the
+    GEMM epilogue for sequences of >= 127 flat rows, a separate mask pass for the reference's 7-frame clips (tsav.py:214-216)
+    -- both against the no-dropout convolution times the regenerated Philox keep-mask."""
+    torch.manual_seed(2)
+    Nn, cin, cout, k, dil, pad, p_drop = 37, 64, 96, 3, 2, 4, 0.4
+    Lp = Ls + pad
+    dt = torch.bfloat16 if precision == "bf16" else torch.float32
+    params = {"c.weight_g": (torch.rand(cout, 1, 1) + 0.5).cuda(), "c.weight_v": (torch.randn(cout, cin, k) * 0.2).cuda(),
+              "c.bias": (torch.randn(cout) * 0.1).cuda()}
+    x = torch.zeros(Nn, Lp, cin)
+    x[:, pad:] = torch.randn(Nn, Ls, cin)
+    xd = x.reshape(Nn * Lp, cin).to("cuda", dt)
+    seed = 1234
+    ctx_t = E.Ctx(params, precision, False, True, seed=seed)          # training: channel dropout on
+    y_t = E.causal_conv(ctx_t, E.Var(xd), "c.", Nn, Ls, cin, cout, k, dil, L.ACT_LEAKY, drop_p=p_drop, pad=pad).data.float()
+    ctx_e = E.Ctx(params, precision, False, False, seed=seed)         # eval: same conv, no dropout
+    y_e = E.causal_conv(ctx_e, E.Var(xd), "c.", Nn, Ls, cin, cout, k, dil, L.ACT_LEAKY, drop_p=p_drop, pad=pad).data.float()
+    mask = torch.empty(Nn * cout, dtype=torch.uint8, device="cuda")
+    L.check(L.lib().jmt_dropout_mask(E._ptr(mask), Nn * cout, p_drop, seed, 0, None, E._stream()), "jmt_dropout_mask")
+    torch.cuda.synchronize()
+    keep = mask.view(Nn, 1, cout).float()
+    assert 0.3 < 1 - keep.mean().item() < 0.5
+    want = y_e.view(Nn, Lp, cout) * keep / (1 - p_drop)
+    got = y_t.view(Nn, Lp, cout)
+    assert (got - want).abs().max() < (1e-5 if precision == "bf16x3" else 2e-2) * want.abs().max()
+    assert (got[:, :pad] == 0).all()
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16x3", "bf16"])
