@@ -74,6 +74,8 @@ struct TcParams {
   // although they are 4.05 rounds of work.  The tiles of the last, nearly empty round (t >= tail_start in regular numbering) are
   // cut along N into tail_split pieces of tail_bn columns each (own UMMA instruction descriptor, own B tensor map with a smaller
   // box), so that round costs a fraction of a tile instead of a whole one.
+  int two_phase;      // wide tiles: the two 256-column halves of the accumulator are handed back separately (tempty[0] / tempty[1]):
+                      // the epilogue drains half 0 first, and the next tile's MMAs into half 0 run while half 1 is still drained
   int tail_start, tail_split, tail_bn, b_tail_bytes;
   uint32_t idesc_tail;
   FastDiv fd_tsplit;
@@ -174,7 +176,9 @@ struct EpiCtx {
 #ifdef JMT_EPI_PROF
   long long* prof;
 #endif
-  uint32_t tempty;            // accumulator-stage 'empty' barrier (leader CTA's, cluster address when kCta == 2)
+  uint32_t tempty;            // accumulator-stage 'empty' barrier (leader CTA's, cluster address when kCta == 2), released at the end
+  uint32_t tempty_mid;        // two-phase wide tile: barrier of accumulator half 0, released once columns [0, 256) are drained (0: none)
+  uint32_t tempty_end2;       // a second barrier to release at the end (tail piece inside a two-phase launch), 0: none
   int m0w, n0, b0, b1, part, parts, lane;   // part / parts: this warp's interleaved share of the tile's column chunks
   int bn;                                   // columns of this tile
 };
@@ -235,6 +239,7 @@ __device__ __forceinline__ bool epi_tile(const TcParams& p, const CUtensorMap* t
         // last chunk of this warp's share: every TMEM read of the tile has landed in registers, hand the accumulator stage
         // back to the MMA issuer before the remaining math / staging / store
         const int c_next = c0 + 64 * e.parts;
+        if (e.tempty_mid != 0u && c0 < 256 && c_next >= 256) epi_release<kCta>(e.tempty_mid, lane);   // accumulator half 0 drained
         if (c_next >= e.bn || e.n0 + c_next >= p.N) { epi_release<kCta>(e.tempty, lane); released = true; }
         if (second) {
           epi_math_bf16<ACT, MASK>(r, e.bias + c0 + 32, MASK ? e.fwords[(c0 >> 5) + 1] : 0u, p.colmask_scale, e.keep, p.alpha, p.slope, pk);
@@ -261,6 +266,7 @@ __device__ __forceinline__ bool epi_tile(const TcParams& p, const CUtensorMap* t
         uint32_t r[32];
         tc_ld32(e.tbase + c0, r);
         const int c_next = c0 + 32 * e.parts;
+        if (e.tempty_mid != 0u && c0 < 256 && c_next >= 256) epi_release<kCta>(e.tempty_mid, lane);   // accumulator half 0 drained
         if (c_next >= e.bn || e.n0 + c_next >= p.N) { epi_release<kCta>(e.tempty, lane); released = true; }
         epi_math_f32<ACT, MASK>(r, e.bias + c0, MASK ? e.fwords[c0 >> 5] : 0u, p.colmask_scale, e.keep, p.alpha, p.slope);
         if (lane == 0) bulk_wait_read0();
@@ -286,6 +292,7 @@ __device__ __forceinline__ bool epi_tile(const TcParams& p, const CUtensorMap* t
       if (n >= p.N) break;                      // warp-uniform
       uint32_t r[32];
       tc_ld32(e.tbase + c0, r);
+      if (e.tempty_mid != 0u && c0 < 256 && c0 + 32 * e.parts >= 256) epi_release<kCta>(e.tempty_mid, lane);
       if (m >= p.M) continue;
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
@@ -487,9 +494,57 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a_hi, const __grid_consta
         const uint32_t acc_phase = (p.wide ? tile_iter : (tile_iter >> 1)) & 1;
         const long long tw0 = p.prof ? clock64() : 0;
         mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1);
+        if (p.two_phase && c.tail) mbar_wait(tempty_bar + 8, acc_phase ^ 1);     // a tail piece consumes a phase of both halves
         if (p.prof) mw_tempty += clock64() - tw0;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * kAccStride;
+        if (!kX3 && p.two_phase && !c.tail) {
+          // Two-phase wide tile: half 0 (columns 0..255) is free, half 1 (256..511) may still be drained by the epilogue of
+          // the previous tile.  Issue the half-0 MMAs of up to `stages` k-blocks ahead; their half-1 MMAs (and the commits
+          // that free the shared-memory slots) follow as soon as tempty[1] flips.
+          bool h1_free = false;
+          int pend = 0, pend_stage = stage, pend_it = c.it0;
+          for (int it = c.it0; it < c.it1; ++it) {
+            const long long tw1 = p.prof ? clock64() : 0;
+            mbar_wait(full_bar + 8 * stage, phase);
+            if (p.prof) mw_full += clock64() - tw1;
+            tc_fence_after();
+            {
+              const uint64_t a_desc = make_smem_desc(sA + stage * a_stride, a_lbo, 1024);
+              const uint64_t b_desc = make_smem_desc(sB + stage * b_stride, b_lbo, 1024);
+#pragma unroll
+              for (int k = 0; k < kBlockK / kUmmaK; ++k)
+                tc_mma<kCta>(d_tmem, a_desc + (uint64_t)(k * a_kstep), b_desc + (uint64_t)(k * b_kstep), p.idesc, (it > c.it0 || k > 0) ? 1u : 0u);
+            }
+            ++pend;
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            if (!h1_free) {
+              if (pend == p.stages || it == c.it1 - 1) {
+                const long long tw2 = p.prof ? clock64() : 0;
+                mbar_wait(tempty_bar + 8, acc_phase ^ 1);
+                if (p.prof) mw_tempty += clock64() - tw2;
+                h1_free = true;
+              } else {
+                h1_free = mbar_test(tempty_bar + 8, acc_phase ^ 1);
+              }
+              if (h1_free) tc_fence_after();
+            }
+            if (h1_free) {
+              for (; pend > 0; --pend, ++pend_it) {
+                const uint64_t a_desc = make_smem_desc(sA + pend_stage * a_stride, a_lbo, 1024);
+                const uint64_t b_desc = make_smem_desc(sB + pend_stage * b_stride, b_lbo, 1024);
+#pragma unroll
+                for (int k = 0; k < kBlockK / kUmmaK; ++k)
+                  tc_mma<kCta>(d_tmem + 256, a_desc + (uint64_t)(k * a_kstep), b_desc + (uint64_t)(1024 + k * b_kstep), p.idesc,
+                               (pend_it > c.it0 || k > 0) ? 1u : 0u);
+                tc_commit<kCta>(empty_bar + 8 * pend_stage);
+                if (++pend_stage == p.stages) pend_stage = 0;
+              }
+            }
+          }
+          tc_commit<kCta>(tfull_bar);
+          continue;
+        }
         for (int it = c.it0; it < c.it1; ++it) {
           const long long tw1 = p.prof ? clock64() : 0;
           mbar_wait(full_bar + 8 * stage, phase);
@@ -590,7 +645,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a_hi, const __grid_consta
       ec.bn = c.bn;
       // (kMask: channel dropout fused after the activation, TCN -- a separate kernel instantiation so that its extra
       //  register pressure never touches the common kernels)
-      ec.tempty = (kCta == 1 ? tempty_bar : tempty_leader) + 8 * acc;
+      {
+        const uint32_t te = kCta == 1 ? tempty_bar : tempty_leader;
+        ec.tempty = te + 8 * acc; ec.tempty_mid = 0u; ec.tempty_end2 = 0u;
+        if (p.two_phase) {
+          if (c.tail) ec.tempty_end2 = te + 8;                   // a tail piece uses (and hands back) both halves at once
+          else { ec.tempty_mid = te; ec.tempty = te + 8; }       // half 0 after columns [0, 256), half 1 at the end
+        }
+      }
 #ifdef JMT_EPI_PROF
       ec.prof = eprof;
 #endif
@@ -598,7 +660,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a_hi, const __grid_consta
       if (p.act == JMT_ACT_NONE) released = epi_tile<JMT_ACT_NONE, kMask, kCta>(p, &tma_d, ec);
       else if (p.act == JMT_ACT_RELU) released = epi_tile<JMT_ACT_RELU, kMask, kCta>(p, &tma_d, ec);
       else released = epi_tile<JMT_ACT_LEAKY_RELU, kMask, kCta>(p, &tma_d, ec);
-      if (!released) epi_release<kCta>(ec.tempty, lane);
+      if (!released) {
+        // (a two-phase tile that ended before its half boundary -- columns beyond N -- still owes the half-0 arrive)
+        if (ec.tempty_mid != 0u) epi_release<kCta>(ec.tempty_mid, lane);
+        epi_release<kCta>(ec.tempty, lane);
+      }
+      if (ec.tempty_end2 != 0u) epi_release<kCta>(ec.tempty_end2, lane);
     }
     if (lane == 0) bulk_wait0();                   // all TMA stores of this warp have completed
 #ifdef JMT_EPI_PROF
@@ -694,6 +761,8 @@ static int gemm_tc_launch(const jmt_gemm_desc* g, const void* a_lo, const void* 
     p.wide = (wide_env != 0 && !x3 && p.cluster == 2 && !p.pair_batch && g->N % 512 == 0 &&
               p.iters_total / p.split_k >= min_iters) ? 1 : 0;
     if (p.wide) { p.block_n = 512; p.n_tiles = g->N / 512; }
+    static const int two_env = []() { const char* e = getenv("JMT_GEMM_TWO_PHASE"); return e ? atoi(e) : 1; }();
+    p.two_phase = (p.wide && two_env != 0) ? 1 : 0;
   }
   p.m_pairs = (p.cluster == 2 && !p.pair_batch) ? (p.m_tiles + 1) / 2 : p.m_tiles;
   p.batch_slots = p.pair_batch ? p.batch_tiles / 2 : p.batch_tiles;

@@ -941,6 +941,20 @@ def _ptr_array(ctx: Ctx, tensors):
     return arr
 
 
+def contig_f32_2d(ctx: Ctx, d: torch.Tensor) -> torch.Tensor:
+    """A 2-D gradient handed in by autograd as a contiguous fp32 tensor: `.sum().backward()` and friends deliver expanded
+    (stride-0) or otherwise strided views; they are materialised by one strided-copy launch (jmt_copy3d), not by ATen."""
+    require_cuda(d)
+    if d.is_contiguous() and d.dtype == torch.float32:
+        return d
+    if d.dim() != 2 or d.dtype not in _DT:
+        return d.contiguous().to(torch.float32)          # exotic layouts / dtypes only
+    out = ctx.empty(tuple(d.shape), torch.float32)
+    L.check(ctx.lib.jmt_copy3d(_ptr(d), _DT[d.dtype], d.stride(0), d.stride(1), _ptr(out), L.F32, d.shape[1], 1,
+                               d.shape[0], d.shape[1], 1, _stream()), "jmt_copy3d")
+    return out
+
+
 def regressor_tail(ctx: Ctx, hidden: List[Var], wnames: List[str], bnames: List[str], w_row: List[int],
                    B: int, T: int, time_major: bool):
     """Final Linear(128, k) of the heads as one fused kernel over G groups (hidden[g] may repeat).
@@ -976,7 +990,7 @@ def regressor_tail(ctx: Ctx, hidden: List[Var], wnames: List[str], bnames: List[
                 d = gouts[g]
                 if d is None:
                     d = ctx.zeros(shape, torch.float32)
-                douts.append(d.contiguous().to(torch.float32) if (not d.is_contiguous() or d.dtype != torch.float32) else d)
+                douts.append(contig_f32_2d(ctx, d))
             dws = [ctx.pgrad(wnames[g])[w_row[g]] for g in range(G)]
             dbs = [ctx.pgrad(bnames[g])[w_row[g]:w_row[g] + 1] for g in range(G)]
             acc_arr = (C.c_int * G)(*acc)
@@ -1028,11 +1042,7 @@ def regressor_heads(ctx: Ctx, x: Var, pre: Sequence[str], B: int, T: int, time_m
             douts = []
             for g in range(2):
                 d = gouts[g]
-                if d is None:
-                    d = ctx.zeros(shape, torch.float32)
-                elif not d.is_contiguous() or d.dtype != torch.float32:
-                    raise RuntimeError("jmt_b200: output gradients must be contiguous fp32 tensors")
-                douts.append(d)
+                douts.append(ctx.zeros(shape, torch.float32) if d is None else contig_f32_2d(ctx, d))
             dH = ctx.empty((M, 256))
             dhl = [dH[:, 0:128], dH[:, 128:256]]
             dws = [ctx.pgrad(p + "3.weight")[0] for p in pre]
