@@ -253,6 +253,9 @@ int jmt_act_bwd_fused(const void* dy, const void* y, const uint8_t* mask, void* 
                       float scale, float slope, float* colsum, int dtype, void* stream);
 /* out = cast(in) */
 int jmt_cast(const void* in, int in_dtype, void* out, int out_dtype, int64_t n, void* stream);
+/* dst[e][i] = bf16(src[e][i]), i < n[e], for `count` tensors in one launch (HOST arrays of device pointers, 16-byte aligned):
+ * the bf16 operand copies of all weight matrices of a module, refreshed once per optimizer step */
+int jmt_cast_multi(int count, const float* const* src, void* const* dst, const int64_t* n, void* stream);
 /* y += a*x (same dtype) */
 int jmt_axpy(const void* x, void* y, float a, int64_t n, int dtype, void* stream);
 /* strided 2-D copy with cast: out[r*out_ld + c] = in[r*in_ld + c] */
@@ -296,6 +299,14 @@ int jmt_rng_advance(uint64_t* dev_state, uint64_t inc, void* stream);
  * (k*... see DESIGN.md); norm (Cout) fp32 saved. */
 int jmt_weight_norm_fwd(const float* g, const float* v, void* w_fwd, void* w_dgrad, int out_dtype,
                         float* norm, int cout, int cin, int k, void* stream);
+/* The same for n <= 16 convolutions in ONE launch each (every conv of a TemporalConvNet per pass: the per-conv kernels are
+ * latency-bound).  Arrays are HOST arrays of length n; w_dgrad (or single entries of it) may be NULL. */
+int jmt_weight_norm_fwd_batched(int n, const float* const* g, const float* const* v, void* const* w_fwd, void* const* w_dgrad,
+                                int out_dtype, float* const* norm, const int* cout, const int* cin, int k, void* stream);
+/* dw_fwd[e] == NULL: conv e received no gradient, its dg / dv are left untouched */
+int jmt_weight_norm_bwd_batched(int n, const float* const* dw_fwd, const float* const* g, const float* const* v,
+                                const float* const* norm, float* const* dg, float* const* dv, const int* cout, const int* cin,
+                                int k, void* stream);
 /* dv, dg from dw_fwd ((Cout, k*Cin) fp32, tap-major): dg = (dw.v)/||v||, dv = g/||v|| (dw - v (dw.v)/||v||^2) */
 int jmt_weight_norm_bwd(const float* dw_fwd, const float* g, const float* v, const float* norm, float* dg,
                         float* dv, int cout, int cin, int k, void* stream);

@@ -82,6 +82,7 @@ SIGNATURES = {
     "jmt_act_bwd_fused": [_P, _P, _P, _P, _L, _I, _I, _F, _F, _P, _I, _P],
     "jmt_cast": [_P, _I, _P, _I, _L, _P],
     "jmt_axpy": [_P, _P, _F, _L, _I, _P],
+    "jmt_cast_multi": [_I, _P, _P, _P, _P],
     "jmt_copy2d": [_P, _I, _L, _P, _I, _L, _L, _I, _P],
     "jmt_transpose": [_P, _I, _P, _I, _L, _I, _I, _P],
     "jmt_transpose_strided": [_P, _I, _L, _P, _I, _L, _L, _I, _I, _P],
@@ -95,6 +96,8 @@ SIGNATURES = {
     "jmt_rng_advance": [_P, _U64, _P],
     "jmt_weight_norm_fwd": [_P, _P, _P, _P, _I, _P, _I, _I, _I, _P],
     "jmt_weight_norm_bwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
+    "jmt_weight_norm_fwd_batched": [_I, _P, _P, _P, _P, _I, _P, _P, _P, _I, _P],
+    "jmt_weight_norm_bwd_batched": [_I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P],
     "jmt_ccc_sums": [_P, _P, _L, _I, _L, _I, _F, _P, _P],
     "jmt_ccc_finalize": [_P, _I, _I, _D, _D, _P, _P, _P],
     "jmt_ccc_bwd": [_P, _P, _L, _I, _L, _P, _P, _I, _I, _F, _P, _P],

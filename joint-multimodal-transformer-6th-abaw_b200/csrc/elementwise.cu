@@ -302,14 +302,29 @@ __global__ void rng_advance_kernel(uint64_t* state, uint64_t inc) { state[1] += 
 // implicit-GEMM layouts.  One block per output channel stages its (cin, k) slice in shared memory so that both the
 // read of v (cin-major, tap-minor) and the write of w_fwd (tap-major, cin-minor) are coalesced; the dgrad layout
 // (cin, k*cout) is a per-tap transpose of w_fwd done by a tiled kernel (coalesced both ways).
+// One launch serves up to kWnMax weight-normed convolutions (all convs of a TemporalConvNet: 8 tiny kernels per pass were
+// latency-bound at ~10 us each): blockIdx.y (fwd / bwd) or blockIdx.z / k (layout) selects the conv.
+constexpr int kWnMax = 16;
+struct WnBatch {
+  const float* g[kWnMax]; const float* v[kWnMax];
+  void* w_fwd[kWnMax]; void* w_dg[kWnMax]; float* norm[kWnMax];
+  const float* dw[kWnMax]; float* dgr[kWnMax]; float* dv[kWnMax];
+  int cout[kWnMax], cin[kWnMax];
+  int n, k;
+};
+
 template <typename TO>
 __global__ void __launch_bounds__(256)
-weight_norm_fwd_kernel(const float* __restrict__ g, const float* __restrict__ v, TO* __restrict__ w_fwd,
-                       float* __restrict__ norm, int cout, int cin, int k) {
+weight_norm_fwd_kernel(const WnBatch b) {
   extern __shared__ float wn_sh[];            // inner floats
-  const int co = blockIdx.x;
+  const int e = blockIdx.y, co = blockIdx.x;
+  const int cout = b.cout[e], cin = b.cin[e], k = b.k;
+  if (co >= cout) return;
+  const float* __restrict__ g = b.g[e];
+  TO* __restrict__ w_fwd = (TO*)b.w_fwd[e];
+  float* __restrict__ norm = b.norm[e];
   const int inner = cin * k;
-  const float* vr = v + (int64_t)co * inner;
+  const float* vr = b.v[e] + (int64_t)co * inner;
   float ss = 0.f;
   for (int i = threadIdx.x; i < inner; i += blockDim.x) { const float x = vr[i]; wn_sh[i] = x; ss = fmaf(x, x, ss); }
   __shared__ float sh[8];
@@ -328,14 +343,19 @@ weight_norm_fwd_kernel(const float* __restrict__ g, const float* __restrict__ v,
   }
 }
 
-// w_dgrad[ci, j*cout + co] = w_fwd[co, j*cin + ci]: per tap j (blockIdx.z) a (cout x cin) -> (cin x cout) transpose with row
+// dgrad layout: w_dgrad[ci, j*cout + co] = w_fwd[co, j*cin + ci]: per tap a (cout x cin) -> (cin x cout) transpose with row
 // pitches k*cin / k*cout, 32x32 tiles through shared memory
 template <typename T>
 __global__ void __launch_bounds__(256)
-weight_norm_dgrad_layout_kernel(const T* __restrict__ w_fwd, T* __restrict__ w_dgrad, int cout, int cin, int k) {
+weight_norm_dgrad_layout_kernel(const WnBatch b) {
   __shared__ float tile[32][33];
-  const int j = blockIdx.z;
+  const int e = blockIdx.z / b.k, j = blockIdx.z - e * b.k;
+  const int cout = b.cout[e], cin = b.cin[e], k = b.k;
+  const T* __restrict__ w_fwd = (const T*)b.w_fwd[e];
+  T* __restrict__ w_dgrad = (T*)b.w_dg[e];
+  if (w_dgrad == nullptr) return;
   const int co0 = blockIdx.y * 32, ci0 = blockIdx.x * 32;
+  if (co0 >= cout || ci0 >= cin) return;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   for (int i = ty; i < 32; i += 8) {
     const int co = co0 + i, ci = ci0 + tx;
@@ -351,9 +371,16 @@ weight_norm_dgrad_layout_kernel(const T* __restrict__ w_fwd, T* __restrict__ w_d
 // dg[co] = <dw, v> / ||v||,  dv = g/||v|| * (dw - v * <dw, v> / ||v||^2); dw arrives tap-major (co, j*cin + ci): both rows are
 // staged in shared memory so every global access is coalesced
 __global__ void __launch_bounds__(256)
-weight_norm_bwd_kernel(const float* __restrict__ dw_fwd, const float* __restrict__ g, const float* __restrict__ v,
-                       const float* __restrict__ norm, float* __restrict__ dg, float* __restrict__ dv, int cout,
-                       int cin, int k) {
+weight_norm_bwd_kernel(const WnBatch b) {
+  const int e = blockIdx.y;
+  const int cout = b.cout[e], cin = b.cin[e], k = b.k;
+  if ((int)blockIdx.x >= cout || b.dw[e] == nullptr) return;      // (a conv whose output never received a gradient)
+  const float* __restrict__ dw_fwd = b.dw[e];
+  const float* __restrict__ g = b.g[e];
+  const float* __restrict__ v = b.v[e];
+  const float* __restrict__ norm = b.norm[e];
+  float* __restrict__ dg = b.dgr[e];
+  float* __restrict__ dv = b.dv[e];
   extern __shared__ float wn_sh[];            // [0, inner): v row (ci*k + j order), [inner, 2*inner): dw row (j*cin + ci order)
   const int co = blockIdx.x;
   const int inner = cin * k;
@@ -586,6 +613,45 @@ extern "C" int jmt_copy3d(const void* in, int in_dtype, int64_t is0, int64_t is1
   return check_launch("copy3d_kernel");
 }
 
+// fp32 -> bf16 casts of up to kCastMax tensors in one launch (the bf16 operand copies of all weight matrices of a module,
+// refreshed once per optimizer step: 24 separate ~4 us launches before)
+constexpr int kCastMax = 96;
+struct CastBatch { const float* src[kCastMax]; __nv_bfloat16* dst[kCastMax]; int64_t n[kCastMax]; int count; };
+__global__ void __launch_bounds__(kEwThreads)
+cast_multi_kernel(const CastBatch b) {
+  const int e = blockIdx.y;
+  const float* __restrict__ x = b.src[e];
+  __nv_bfloat16* __restrict__ y = b.dst[e];
+  const int64_t n = b.n[e], n8 = n / 8;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nt = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = tid; i < n8; i += nt) {
+    Vec8<float> v; v.load(x + i * 8);
+    Vec8<__nv_bfloat16> o;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o.v[k] = v.v[k];
+    o.store(y + i * 8);
+  }
+  for (int64_t i = n8 * 8 + tid; i < n; i += nt) y[i] = __float2bfloat16_rn(x[i]);
+}
+
+extern "C" int jmt_cast_multi(int count, const float* const* src, void* const* dst, const int64_t* n, void* stream) {
+  JMT_REQUIRE(count >= 0 && src && dst && n, "jmt_cast_multi: bad arguments");
+  for (int base = 0; base < count; base += kCastMax) {
+    CastBatch b;
+    b.count = count - base < kCastMax ? count - base : kCastMax;
+    for (int e = 0; e < b.count; ++e) {
+      JMT_REQUIRE(src[base + e] && dst[base + e] && n[base + e] >= 0, "jmt_cast_multi: bad entry %d", base + e);
+      JMT_REQUIRE(((reinterpret_cast<uintptr_t>(src[base + e]) | reinterpret_cast<uintptr_t>(dst[base + e])) & 15) == 0,
+                  "jmt_cast_multi: entry %d is not 16-byte aligned", base + e);
+      b.src[e] = src[base + e]; b.dst[e] = (__nv_bfloat16*)dst[base + e]; b.n[e] = n[base + e];
+    }
+    cast_multi_kernel<<<dim3(24, b.count), kEwThreads, 0, (cudaStream_t)stream>>>(b);
+    int rc = check_launch("cast_multi_kernel");
+    if (rc != JMT_OK) return rc;
+  }
+  return JMT_OK;
+}
+
 // bf16x3 operand split: hi = bf16(x), lo = bf16(x - hi); x ~= hi + lo to 2^-17 relative
 __global__ void __launch_bounds__(kEwThreads)
 split_bf16x2_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int64_t n) {
@@ -703,31 +769,81 @@ extern "C" int jmt_rng_advance(uint64_t* dev_state, uint64_t inc, void* stream) 
   return check_launch("rng_advance_kernel");
 }
 
-extern "C" int jmt_weight_norm_fwd(const float* g, const float* v, void* w_fwd, void* w_dgrad, int out_dtype, float* norm,
-                                   int cout, int cin, int k, void* stream) {
-  JMT_REQUIRE(g && v && w_fwd && cout > 0 && cin > 0 && k > 0, "jmt_weight_norm_fwd: bad arguments");
-  const size_t sh = (size_t)cin * k * sizeof(float);
-  JMT_REQUIRE(sh <= 96 * 1024, "jmt_weight_norm_fwd: cin*k too large for the shared-memory staging (%d x %d)", cin, k);
-  cudaStream_t st = (cudaStream_t)stream;
+static int wn_fwd_launch(const jmt::WnBatch& b, int out_dtype, bool any_dgrad, cudaStream_t st) {
+  int max_cout = 0, max_cin = 0;
+  for (int e = 0; e < b.n; ++e) { max_cout = b.cout[e] > max_cout ? b.cout[e] : max_cout; max_cin = b.cin[e] > max_cin ? b.cin[e] : max_cin; }
+  const size_t sh = (size_t)max_cin * b.k * sizeof(float);
+  JMT_REQUIRE(sh <= 96 * 1024, "jmt_weight_norm_fwd: cin*k too large for the shared-memory staging (%d x %d)", max_cin, b.k);
   if (sh > 48 * 1024) {
     JMT_DISPATCH_DTYPE(out_dtype, TO, cudaFuncSetAttribute(weight_norm_fwd_kernel<TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
   }
-  JMT_DISPATCH_DTYPE(out_dtype, TO, (weight_norm_fwd_kernel<TO><<<cout, 256, sh, st>>>(g, v, (TO*)w_fwd, norm, cout, cin, k)));
+  JMT_DISPATCH_DTYPE(out_dtype, TO, (weight_norm_fwd_kernel<TO><<<dim3(max_cout, b.n), 256, sh, st>>>(b)));
   int rc = check_launch("weight_norm_fwd_kernel");
-  if (rc != JMT_OK || !w_dgrad) return rc;
-  dim3 grid((cin + 31) / 32, (cout + 31) / 32, k);
-  JMT_DISPATCH_DTYPE(out_dtype, TO, (weight_norm_dgrad_layout_kernel<TO><<<grid, 256, 0, st>>>((const TO*)w_fwd, (TO*)w_dgrad, cout, cin, k)));
+  if (rc != JMT_OK || !any_dgrad) return rc;
+  dim3 grid((max_cin + 31) / 32, (max_cout + 31) / 32, b.k * b.n);
+  JMT_DISPATCH_DTYPE(out_dtype, TO, (weight_norm_dgrad_layout_kernel<TO><<<grid, 256, 0, st>>>(b)));
   return check_launch("weight_norm_dgrad_layout_kernel");
+}
+
+extern "C" int jmt_weight_norm_fwd(const float* g, const float* v, void* w_fwd, void* w_dgrad, int out_dtype, float* norm,
+                                   int cout, int cin, int k, void* stream) {
+  JMT_REQUIRE(g && v && w_fwd && cout > 0 && cin > 0 && k > 0, "jmt_weight_norm_fwd: bad arguments");
+  jmt::WnBatch b;
+  memset(&b, 0, sizeof(b));
+  b.n = 1; b.k = k; b.g[0] = g; b.v[0] = v; b.w_fwd[0] = w_fwd; b.w_dg[0] = w_dgrad; b.norm[0] = norm; b.cout[0] = cout; b.cin[0] = cin;
+  return wn_fwd_launch(b, out_dtype, w_dgrad != nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int jmt_weight_norm_fwd_batched(int n, const float* const* g, const float* const* v, void* const* w_fwd, void* const* w_dgrad,
+                                           int out_dtype, float* const* norm, const int* cout, const int* cin, int k, void* stream) {
+  JMT_REQUIRE(n >= 1 && n <= jmt::kWnMax && g && v && w_fwd && norm && cout && cin && k > 0, "jmt_weight_norm_fwd_batched: bad arguments");
+  jmt::WnBatch b;
+  memset(&b, 0, sizeof(b));
+  b.n = n; b.k = k;
+  bool any_dg = false;
+  for (int e = 0; e < n; ++e) {
+    JMT_REQUIRE(g[e] && v[e] && w_fwd[e] && cout[e] > 0 && cin[e] > 0, "jmt_weight_norm_fwd_batched: bad entry %d", e);
+    b.g[e] = g[e]; b.v[e] = v[e]; b.w_fwd[e] = w_fwd[e]; b.w_dg[e] = w_dgrad ? w_dgrad[e] : nullptr; b.norm[e] = norm[e];
+    b.cout[e] = cout[e]; b.cin[e] = cin[e];
+    any_dg = any_dg || b.w_dg[e] != nullptr;
+  }
+  return wn_fwd_launch(b, out_dtype, any_dg, (cudaStream_t)stream);
+}
+
+static int wn_bwd_launch(const jmt::WnBatch& b, cudaStream_t st) {
+  int max_cout = 0, max_cin = 0;
+  for (int e = 0; e < b.n; ++e) { max_cout = b.cout[e] > max_cout ? b.cout[e] : max_cout; max_cin = b.cin[e] > max_cin ? b.cin[e] : max_cin; }
+  const size_t sh = 2 * (size_t)max_cin * b.k * sizeof(float);
+  JMT_REQUIRE(sh <= 96 * 1024, "jmt_weight_norm_bwd: cin*k too large for the shared-memory staging (%d x %d)", max_cin, b.k);
+  if (sh > 48 * 1024) cudaFuncSetAttribute(weight_norm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+  weight_norm_bwd_kernel<<<dim3(max_cout, b.n), 256, sh, st>>>(b);
+  return check_launch("weight_norm_bwd_kernel");
 }
 
 extern "C" int jmt_weight_norm_bwd(const float* dw_fwd, const float* g, const float* v, const float* norm, float* dg,
                                    float* dv, int cout, int cin, int k, void* stream) {
   JMT_REQUIRE(dw_fwd && g && v && norm && dg && dv, "jmt_weight_norm_bwd: bad arguments");
-  const size_t sh = 2 * (size_t)cin * k * sizeof(float);
-  JMT_REQUIRE(sh <= 96 * 1024, "jmt_weight_norm_bwd: cin*k too large for the shared-memory staging (%d x %d)", cin, k);
-  if (sh > 48 * 1024) cudaFuncSetAttribute(weight_norm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-  weight_norm_bwd_kernel<<<cout, 256, sh, (cudaStream_t)stream>>>(dw_fwd, g, v, norm, dg, dv, cout, cin, k);
-  return check_launch("weight_norm_bwd_kernel");
+  jmt::WnBatch b;
+  memset(&b, 0, sizeof(b));
+  b.n = 1; b.k = k; b.dw[0] = dw_fwd; b.g[0] = g; b.v[0] = v; b.norm[0] = const_cast<float*>(norm); b.dgr[0] = dg; b.dv[0] = dv;
+  b.cout[0] = cout; b.cin[0] = cin;
+  return wn_bwd_launch(b, (cudaStream_t)stream);
+}
+
+extern "C" int jmt_weight_norm_bwd_batched(int n, const float* const* dw_fwd, const float* const* g, const float* const* v,
+                                           const float* const* norm, float* const* dg, float* const* dv, const int* cout,
+                                           const int* cin, int k, void* stream) {
+  JMT_REQUIRE(n >= 1 && n <= jmt::kWnMax && dw_fwd && g && v && norm && dg && dv && cout && cin && k > 0, "jmt_weight_norm_bwd_batched: bad arguments");
+  jmt::WnBatch b;
+  memset(&b, 0, sizeof(b));
+  b.n = n; b.k = k;
+  for (int e = 0; e < n; ++e) {
+    JMT_REQUIRE(g[e] && v[e] && norm[e] && dg[e] && dv[e] && cout[e] > 0 && cin[e] > 0, "jmt_weight_norm_bwd_batched: bad entry %d", e);
+    b.dw[e] = dw_fwd[e];      // NULL: that conv received no gradient (its dg / dv stay untouched)
+    b.g[e] = g[e]; b.v[e] = v[e]; b.norm[e] = const_cast<float*>(norm[e]); b.dgr[e] = dg[e]; b.dv[e] = dv[e];
+    b.cout[e] = cout[e]; b.cin[e] = cin[e];
+  }
+  return wn_bwd_launch(b, (cudaStream_t)stream);
 }
 
 extern "C" int jmt_time_max_fwd(const void* x, int64_t batch_stride, int64_t nb, int L, int C, void* out, int32_t* arg, int dtype, void* stream) {

@@ -761,7 +761,9 @@ static int gemm_tc_launch(const jmt_gemm_desc* g, const void* a_lo, const void* 
     p.wide = (wide_env != 0 && !x3 && p.cluster == 2 && !p.pair_batch && g->N % 512 == 0 &&
               p.iters_total / p.split_k >= min_iters) ? 1 : 0;
     if (p.wide) { p.block_n = 512; p.n_tiles = g->N / 512; }
-    static const int two_env = []() { const char* e = getenv("JMT_GEMM_TWO_PHASE"); return e ? atoi(e) : 1; }();
+    // measured (round 2, profiles/gemm_roles_r2h_tp*.txt): the MMA issuer's wait for the accumulator halves (20.9 k -> 11.7 k of 62 k
+    // cycles on 76800x512x512) but the launch is not faster (44.7 -> 45.3 us; K = 3072: 336 -> 352 us) -- off unless JMT_GEMM_TWO_PHASE=1
+    static const int two_env = []() { const char* e = getenv("JMT_GEMM_TWO_PHASE"); return e ? atoi(e) : 0; }();
     p.two_phase = (p.wide && two_env != 0) ? 1 : 0;
   }
   p.m_pairs = (p.cluster == 2 && !p.pair_batch) ? (p.m_tiles + 1) / 2 : p.m_tiles;

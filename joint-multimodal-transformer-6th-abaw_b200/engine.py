@@ -141,6 +141,7 @@ class Ctx:
         self.lib = L.lib()
         self.wcache = wcache if wcache is not None else {}
         self._w: Dict[str, torch.Tensor] = {}
+        self._bulk_done = False
         self.pgrads: Dict[str, torch.Tensor] = {}
         self.bucket: Optional[torch.Tensor] = None
         self.seed = seed
@@ -176,24 +177,47 @@ class Ctx:
             return par
         t = self._w.get(name)
         if t is None:
-            # The cache entry is valid for one (storage, in-place version, replay generation): a CUDA-graph replay that
-            # contains optimizer.step() updates the parameters on the device WITHOUT bumping `_version`, so every replay
-            # (GraphedStep.replay) bumps the generation instead.
-            key = (par.data_ptr(), par._version, tuple(par.shape), _PARAM_GENERATION[0])
-            capturing = torch.cuda.is_current_stream_capturing()
-            ent = None if capturing else self.wcache.get(name)
-            if ent is None or ent[0] != key:
-                # Under capture the cast is always PART of the graph (a replay runs after optimizer steps the version
-                # check at capture time cannot see) and stays private to it: a graph-pool tensor has no content before
-                # the first replay and must never be handed to a later eager forward.
-                out = torch.empty(par.shape, dtype=self.adt, device=par.device)
-                L.check(self.lib.jmt_cast(_ptr(par), L.F32, _ptr(out), self.acode, par.numel(), _stream()), "jmt_cast")
-                ent = (key, out)
-                if not capturing:
-                    self.wcache[name] = ent
-            t = ent[1]
-            self._w[name] = t
+            self._cast_all_weights()
+            t = self._w.get(name)
+        if t is None:               # not a bulk-cast candidate (e.g. a 1-D parameter used as an operand): cast it alone
+            out = torch.empty(par.shape, dtype=self.adt, device=par.device)
+            L.check(self.lib.jmt_cast(_ptr(par), L.F32, _ptr(out), self.acode, par.numel(), _stream()), "jmt_cast")
+            self._w[name] = t = out
         return t
+
+    def _cast_all_weights(self):
+        """bf16 operand copies of ALL weight matrices of this pass in one launch (jmt_cast_multi) into one buffer.  The cached
+        buffer is valid for one (storages, in-place versions, replay generation): a CUDA-graph replay that contains
+        optimizer.step() updates the parameters on the device WITHOUT bumping `_version`, so every replay
+        (GraphedStep.replay) bumps the generation instead.  Under capture the cast is always PART of the graph (a replay runs
+        after optimizer steps the version check at capture time cannot see) and stays private to it: a graph-pool tensor has no
+        content before the first replay and must never be handed to a later eager forward."""
+        if self._bulk_done:
+            return
+        self._bulk_done = True
+        names = [n for n, p in self.params.items() if p.dim() >= 2 and not n.endswith("weight_v") and not n.endswith("weight_g")]
+        if not names:
+            return
+        pars = [self.params[n] for n in names]
+        key = tuple((p.data_ptr(), p._version, tuple(p.shape)) for p in pars) + (_PARAM_GENERATION[0],)
+        capturing = torch.cuda.is_current_stream_capturing()
+        ent = None if capturing else self.wcache.get("__bulk__")
+        if ent is None or ent[0] != key:
+            offs, total = [], 0
+            for p in pars:
+                offs.append(total)
+                total += (p.numel() + 63) // 64 * 64
+            buf = torch.empty((total,), dtype=self.adt, device=pars[0].device)
+            views = [buf[o:o + p.numel()].view(p.shape) for o, p in zip(offs, pars)]
+            n = len(pars)
+            src = (C.c_void_p * n)(*[p.data_ptr() for p in pars])
+            dst = (C.c_void_p * n)(*[v.data_ptr() for v in views])
+            cnt = (C.c_int64 * n)(*[p.numel() for p in pars])
+            L.check(self.lib.jmt_cast_multi(n, src, dst, cnt, _stream()), "jmt_cast_multi")
+            ent = (key, dict(zip(names, views)), buf)
+            if not capturing:
+                self.wcache["__bulk__"] = ent
+        self._w.update(ent[1])
 
     def cat_params(self, names: Sequence[str], as_operand: bool) -> torch.Tensor:
         """Row-wise concatenation of same-width parameters in one buffer (operand dtype when `as_operand`, else fp32): lets
@@ -465,6 +489,10 @@ def from_external(ctx: Ctx, x: torch.Tensor, needs_grad: bool):
     x2 = x.reshape(-1, x.shape[-1])
     if x2.stride(-1) != 1 or x2.dtype not in _DT:
         raise RuntimeError("inputs must be fp32/bf16 with a contiguous feature dimension")
+    if x2.dtype == ctx.adt and x2.is_contiguous() and not needs_grad:
+        # already in the activation dtype (bf16 feature shards): read in place, no copy.  Like any tensor autograd saves for
+        # backward, the caller must not overwrite it between forward and backward.
+        return Var(x2, False), None
     out = ctx.empty(x2.shape)
     copy2d(ctx, x2, out)
     v = Var(out, needs_grad)
@@ -1139,8 +1167,49 @@ def weight_norm_conv_weights(ctx: Ctx, prefix: str, cout: int, cin: int, k: int)
     return w_fwd, w_dg, dw
 
 
+def weight_norm_all(ctx: Ctx, convs: Sequence[Tuple[str, int, int]], k: int):
+    """weight_norm of several convolutions (prefix, cout, cin) -- every conv of a TemporalConvNet -- in ONE launch per layout
+    (jmt_weight_norm_fwd_batched; the per-conv kernels are latency-bound, 8 x 2 x ~10 us per pass).  Returns
+    {prefix: (w_fwd, w_dgrad, dw holder, norm)}; the backward is recorded per group by weight_norm_bwd_group."""
+    out, g, v, wf, wd, nm, co, ci = {}, [], [], [], [], [], [], []
+    for prefix, cout, cin in convs:
+        w_fwd = ctx.empty((cout, k * cin))
+        w_dg = ctx.empty((cin, k * cout)) if ctx.record else None
+        norm = ctx.empty((cout,), torch.float32)
+        out[prefix] = (w_fwd, w_dg, {"t": None}, norm)
+        g.append(ctx.p(prefix + "weight_g")); v.append(ctx.p(prefix + "weight_v"))
+        wf.append(w_fwd); wd.append(w_dg); nm.append(norm); co.append(cout); ci.append(cin)
+    n = len(convs)
+    arr = lambda ts: (C.c_void_p * n)(*[(t.data_ptr() if t is not None else None) for t in ts])     # noqa: E731
+    ia = lambda xs: (C.c_int * n)(*xs)                                                               # noqa: E731
+    L.check(ctx.lib.jmt_weight_norm_fwd_batched(n, arr(g), arr(v), arr(wf), arr(wd), ctx.acode, arr(nm), ia(co), ia(ci), k, _stream()),
+            "jmt_weight_norm_fwd_batched")
+    return out
+
+
+def weight_norm_bwd_group(ctx: Ctx, weights: dict, convs: Sequence[Tuple[str, int, int]], k: int):
+    """Record ONE weight_norm backward launch for a group of convolutions (a TCN level): record it BEFORE the convs so that it
+    runs after their weight-gradient GEMMs in the reversed tape."""
+    if not ctx.record:
+        return
+
+    def bwd():
+        n = len(convs)
+        dws = [weights[p][2]["t"] for p, _, _ in convs]
+        if all(d is None for d in dws):
+            return
+        arr = lambda ts: (C.c_void_p * n)(*[(t.data_ptr() if t is not None else None) for t in ts])     # noqa: E731
+        ia = lambda xs: (C.c_int * n)(*xs)                                                               # noqa: E731
+        L.check(ctx.lib.jmt_weight_norm_bwd_batched(
+            n, arr(dws), arr([ctx.p(p + "weight_g") for p, _, _ in convs]), arr([ctx.p(p + "weight_v") for p, _, _ in convs]),
+            arr([weights[p][3] for p, _, _ in convs]), arr([ctx.pgrad(p + "weight_g") for p, _, _ in convs]),
+            arr([ctx.pgrad(p + "weight_v") for p, _, _ in convs]), ia([c for _, c, _ in convs]), ia([c for _, _, c in convs]), k,
+            _stream()), "jmt_weight_norm_bwd_batched")
+    ctx.tape.append(bwd)
+
+
 def causal_conv(ctx: Ctx, x: Var, prefix: str, N: int, Ls: int, cin: int, cout: int, k: int, dil: int, act: int,
-                drop_p: float = 0.0, pad: int = 0) -> Var:
+                drop_p: float = 0.0, pad: int = 0, weights: Optional[tuple] = None) -> Var:
     """weight-normed dilated causal Conv1d + Chomp1d + LeakyReLU + Dropout2d (temporal_convolutional_model.py:24-29)
     as an implicit GEMM on the flat padded channels-last layout (see above): taps are K blocks whose A rows are
     shifted by -(k-1-j)*dil; the zero padding rows in front of every sequence supply the causal zeros.
@@ -1150,7 +1219,10 @@ def causal_conv(ctx: Ctx, x: Var, prefix: str, N: int, Ls: int, cin: int, cout: 
     Lp = Ls + pad
     R = N * Lp
     assert x.data.shape[0] == R
-    w_fwd, w_dg, dwh = weight_norm_conv_weights(ctx, prefix, cout, cin, k)   # recorded first => runs last in backward
+    if weights is not None:            # computed (and differentiated) together with the other convs: weight_norm_all
+        w_fwd, w_dg, dwh = weights[0], weights[1], weights[2]
+    else:
+        w_fwd, w_dg, dwh = weight_norm_conv_weights(ctx, prefix, cout, cin, k)   # recorded first => runs last in backward
     y = ctx.empty((R, cout))
     bias = ctx.p(prefix + "bias")
     mask, mscale = None, 1.0

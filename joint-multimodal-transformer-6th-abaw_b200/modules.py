@@ -619,11 +619,21 @@ def _tcn_graph(ctx, h, prefix, specs, N, Ls, pad):
     """TemporalConvNet.forward on the flat padded channels-last layout (row = n*(pad+L) + pad + t, engine.py "TCN ops"):
     per level two weight-normed dilated causal convs (+LeakyReLU, channel dropout), residual (1x1 conv when
     Cin != Cout), LeakyReLU (temporal_convolutional_model.py:54-57, 81-82).  Padding rows stay zero throughout."""
+    ks = {k for (_ci, _co, k, _d, _p, _ds) in specs}
+    wn = None
+    if len(ks) == 1 and 2 * len(specs) <= 16:      # all weight_norm reparametrisations of the net in one launch per layout
+        convs = [(f"{prefix}network.{i}.conv{c}.", cout, cin if c == 1 else cout)
+                 for i, (cin, cout, _k, _d, _p, _ds) in enumerate(specs) for c in (1, 2)]
+        wn = E.weight_norm_all(ctx, convs, next(iter(ks)))
     for i, (cin, cout, k, d, p, has_ds) in enumerate(specs):
         pre = f"{prefix}network.{i}."
         ctx.sync_point(pre)          # reached in backward once this level's dW / weight-norm gradients are final
-        y = E.causal_conv(ctx, h, pre + "conv1.", N, Ls, cin, cout, k, d, L.ACT_LEAKY, drop_p=p, pad=pad)
-        y = E.causal_conv(ctx, y, pre + "conv2.", N, Ls, cout, cout, k, d, L.ACT_LEAKY, drop_p=p, pad=pad)
+        w1 = w2 = None
+        if wn is not None:
+            E.weight_norm_bwd_group(ctx, wn, [(pre + "conv1.", cout, cin), (pre + "conv2.", cout, cout)], k)
+            w1, w2 = wn[pre + "conv1."], wn[pre + "conv2."]
+        y = E.causal_conv(ctx, h, pre + "conv1.", N, Ls, cin, cout, k, d, L.ACT_LEAKY, drop_p=p, pad=pad, weights=w1)
+        y = E.causal_conv(ctx, y, pre + "conv2.", N, Ls, cout, cout, k, d, L.ACT_LEAKY, drop_p=p, pad=pad, weights=w2)
         res = _conv1x1(ctx, h, pre + "downsample.", (Ls + pad, pad)) if has_ds else h
         h = E.add_act(ctx, y, res, L.ACT_LEAKY, E.LEAKY_SLOPE)
     return h
