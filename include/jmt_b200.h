@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define JMT_ABI_VERSION 7
+#define JMT_ABI_VERSION 8
 
 typedef enum {
   JMT_OK = 0,
@@ -117,6 +117,18 @@ typedef struct {
    *                           nothing added): the padding rows must stay zero for the next layer. */
   int32_t colmask_row_period;
   int32_t zero_row_period, zero_row_count;
+  /* Backward epilogue extensions (jmt_gemm_bf16 only; bf16 D with 16-byte aligned geometry, act == JMT_ACT_NONE, split_k == 1,
+   * reduce_batch == 0), so that the activation-gradient pass and the bias-gradient column sums need no kernel of their own:
+   *   epi_aux  (nullable, bf16, SAME element offsets as D): the stored / added value is multiplied by act'(aux) =
+   *            (aux > 0 ? 1 : aux_slope) -- aux is the saved forward output y = act(...) of the layer whose input gradient this
+   *            GEMM produces (ReLU: slope 0, mm_multi_transformers.py:52-56; LeakyReLU 0.01, temporal_convolutional_model.py:28,35);
+   *   d_colsum (nullable, fp32): d_colsum[b0 * colsum_bs0 + n] += sum over rows m (and b1) of the values this launch stores / adds
+   *            to D(m, n) (fp32 atomics; the caller zeroes it) = this launch's share of the bias gradient of the Linear / conv
+   *            that produced D's forward counterpart. */
+  const void* epi_aux;
+  float aux_slope;
+  float* d_colsum;
+  int64_t colsum_bs0;
 } jmt_gemm_desc;
 
 int jmt_gemm_bf16(const jmt_gemm_desc* g, void* stream);

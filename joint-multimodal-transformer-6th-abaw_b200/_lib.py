@@ -34,6 +34,7 @@ class GemmDesc(C.Structure):
         ("reduce_batch", C.c_int32), ("split_k", C.c_int32),
         ("colmask", C.c_void_p), ("colmask_scale", C.c_float),
         ("colmask_row_period", C.c_int32), ("zero_row_period", C.c_int32), ("zero_row_count", C.c_int32),
+        ("epi_aux", C.c_void_p), ("aux_slope", C.c_float), ("d_colsum", C.c_void_p), ("colsum_bs0", C.c_int64),
     ]
 
 
@@ -124,7 +125,7 @@ def lib():
             fn = getattr(h, name)           # AttributeError if a declared symbol is not exported
             fn.argtypes = argtypes
             fn.restype = _RESTYPES.get(name, C.c_int)
-        if h.jmt_abi_version() != 7:
+        if h.jmt_abi_version() != 8:
             raise RuntimeError("libjmt_b200.so ABI version mismatch")
         _lib = h
     return _lib

@@ -645,7 +645,7 @@ extern "C" int jmt_cast_multi(int count, const float* const* src, void* const* d
                   "jmt_cast_multi: entry %d is not 16-byte aligned", base + e);
       b.src[e] = src[base + e]; b.dst[e] = (__nv_bfloat16*)dst[base + e]; b.n[e] = n[base + e];
     }
-    cast_multi_kernel<<<dim3(24, b.count), kEwThreads, 0, (cudaStream_t)stream>>>(b);
+    cast_multi_kernel<<<dim3(96, b.count), kEwThreads, 0, (cudaStream_t)stream>>>(b);
     int rc = check_launch("cast_multi_kernel");
     if (rc != JMT_OK) return rc;
   }

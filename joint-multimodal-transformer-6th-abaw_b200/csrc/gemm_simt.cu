@@ -146,12 +146,15 @@ int jmt_validate_gemm_desc(const jmt_gemm_desc* g, const char* who) {
               "%s: colmask_row_period must be >= 127 (a 128-row tile may span at most two samples); apply the mask with "
               "jmt_apply_mask instead", who);
   JMT_REQUIRE(!(g->zero_row_period > 0 && g->reduce_batch), "%s: zero_row_period cannot be combined with reduce_batch", who);
+  JMT_REQUIRE(!((g->epi_aux || g->d_colsum) && (g->d_dtype != JMT_BF16 || g->act != JMT_ACT_NONE || g->split_k != 1 || g->reduce_batch)),
+              "%s: epi_aux / d_colsum need bf16 D, no activation, split_k == 1 and reduce_batch == 0", who);
   return JMT_OK;
 }
 
 extern "C" int jmt_gemm_f32(const jmt_gemm_desc* g, void* stream) {
   int rc = jmt_validate_gemm_desc(g, "jmt_gemm_f32");
   if (rc != JMT_OK) return rc;
+  JMT_REQUIRE(!g->epi_aux && !g->d_colsum, "jmt_gemm_f32: epi_aux / d_colsum are extensions of jmt_gemm_bf16 only");
   SimtArgs s;
   s.g = *g;
   s.kblocks = (g->K + kTK - 1) / kTK;

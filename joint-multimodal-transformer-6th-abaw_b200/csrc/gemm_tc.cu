@@ -74,6 +74,11 @@ struct TcParams {
   // although they are 4.05 rounds of work.  The tiles of the last, nearly empty round (t >= tail_start in regular numbering) are
   // cut along N into tail_split pieces of tail_bn columns each (own UMMA instruction descriptor, own B tensor map with a smaller
   // box), so that round costs a fraction of a tile instead of a whole one.
+  // Extended backward epilogue (bf16 D through TMA, no activation): D_out = value * act'(aux) and / or column sums of D_out
+  const __nv_bfloat16* aux;   // same element offsets as D (ld, batch strides); value *= aux > 0 ? 1 : aux_slope   (nullable)
+  float aux_slope;
+  float* colsum;              // colsum[b0 * colsum_bs0 + n] += sum over the rows this launch writes (fp32 atomics; nullable)
+  int64_t colsum_bs0;
   int two_phase;      // wide tiles: the two 256-column halves of the accumulator are handed back separately (tempty[0] / tempty[1]):
                       // the epilogue drains half 0 first, and the next tile's MMAs into half 0 run while half 1 is still drained
   int tail_start, tail_split, tail_bn, b_tail_bytes;
@@ -316,11 +321,158 @@ __device__ __forceinline__ bool epi_tile(const TcParams& p, const CUtensorMap* t
   return released;
 }
 
+// Column sums of a 32 x 32 block held row-wise (thread = row, v[j] = column j): butterfly transpose-reduce, 31 shuffles; on
+// return lane l holds the sum of column l in v[0].
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16, cnt = 32; off >= 1; off >>= 1, cnt >>= 1) {
+    const bool up = (lane & off) != 0;
+    const int half = cnt >> 1;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      if (i < half) {
+        const float send = up ? v[i] : v[i + half];
+        const float keep = up ? v[i + half] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+      }
+    }
+  }
+  return v[0];
+}
+
+// Extended epilogue of the backward GEMMs (bf16 D through TMA store / reduce-add, no activation):
+//   value = alpha * acc (+ bias) [* channel keep-flag scale] [* (aux > 0 ? 1 : aux_slope)]      <- activation gradient folded in
+//   colsum[n] += sum_m value(m, n)                                                               <- bias gradient of the producer
+// so that neither the act-bwd pass over the gradient nor the column-sum pass runs as a separate kernel (SURVEY 8a kernel column).
+// aux is read straight from global memory (64 contiguous bytes per thread and 32-column half).
+struct ExtRow {
+  const __nv_bfloat16* aux_row;   // aux + this thread's row offset (nullptr: no fold)
+  float* csum;                    // colsum + batch offset (nullptr: no column sums)
+  bool row_valid, zero_row;
+};
+
+// 32 accumulator columns [cb, cb + 32) of this thread's row: r -> x (math), fold, pack into pk[16], column sums
+template <bool MASK>
+__device__ __forceinline__ void ext_half(const TcParams& p, const EpiCtx& e, const ExtRow& xr, const uint32_t (&r)[32], const uint32_t (&aw)[16],
+                                         bool ax_vec, int cb, uint32_t (&pk)[16]) {
+  float x[32];
+  const float* bias = e.bias + cb;
+  const uint32_t fbits = MASK ? e.fwords[cb >> 5] : 0u;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    float v = fmaf(p.alpha, __uint_as_float(r[j]), bias[j]);
+    if constexpr (MASK) v = (fbits >> j) & 1u ? v * p.colmask_scale : 0.f;
+    x[j] = v;
+  }
+  if (xr.aux_row != nullptr && xr.row_valid) {
+    if (ax_vec) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) {
+        const float y0 = __uint_as_float(aw[j >> 1] << 16), y1 = __uint_as_float(aw[j >> 1] & 0xFFFF0000u);
+        x[j] = y0 > 0.f ? x[j] : x[j] * p.aux_slope;
+        x[j + 1] = y1 > 0.f ? x[j + 1] : x[j + 1] * p.aux_slope;
+      }
+    } else {                                       // ragged N tail / unaligned: element-wise
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (e.n0 + cb + j < p.N) {
+          const float y = __bfloat162float(xr.aux_row[e.n0 + cb + j]);
+          x[j] = y > 0.f ? x[j] : x[j] * p.aux_slope;
+        }
+    }
+  }
+  if (xr.zero_row) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) x[j] = 0.f;
+  }
+#pragma unroll
+  for (int j = 0; j < 32; j += 2) pk[j >> 1] = pack_bf16(x[j], x[j + 1]);
+  if (xr.csum != nullptr) {
+    const float cs = warp_colsum32(x, e.lane);
+    if (e.n0 + cb + e.lane < p.N && cs != 0.f) atomicAdd(xr.csum + e.n0 + cb + e.lane, cs);
+  }
+}
+
+template <bool MASK, int kCta>
+__device__ __forceinline__ bool epi_tile_ext(const TcParams& p, const CUtensorMap* tma_d, const EpiCtx& e) {
+  const int lane = e.lane;
+  bool released = false;
+  const bool warp_rows_valid = e.m0w < p.M;      // warp-uniform
+  const int m = e.m0w + lane;
+  ExtRow xr;
+  xr.row_valid = m < p.M;
+  xr.zero_row = e.keep == 0u || !xr.row_valid;
+  const int64_t row_off = (int64_t)e.b0 * p.d_bs0 + (int64_t)e.b1 * p.d_bs1 + (int64_t)m * p.d_ld;
+  xr.aux_row = p.aux != nullptr ? p.aux + row_off : nullptr;
+  xr.csum = p.colsum != nullptr ? p.colsum + (int64_t)e.b0 * p.colsum_bs0 : nullptr;
+  const bool aux_aligned = xr.aux_row != nullptr && ((reinterpret_cast<uintptr_t>(xr.aux_row) | (uintptr_t)(e.n0 * 2)) & 15) == 0;
+  for (int c0 = e.part * 64; c0 < e.bn; c0 += 64 * e.parts) {
+    if (e.n0 + c0 >= p.N) break;
+    const bool second = c0 + 32 < e.bn;
+    uint32_t r[32], pk[16];
+    uint32_t ax[16] = {};
+    tc_ld32_issue(e.tbase + c0, r);
+    // ---- columns [c0, c0 + 32)
+    bool ax_vec = aux_aligned && xr.row_valid && e.n0 + c0 + 32 <= p.N;
+    if (ax_vec) {
+      const uint4* ap = reinterpret_cast<const uint4*>(xr.aux_row + e.n0 + c0);
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) { const uint4 t = __ldg(ap + q4); ax[4 * q4] = t.x; ax[4 * q4 + 1] = t.y; ax[4 * q4 + 2] = t.z; ax[4 * q4 + 3] = t.w; }
+    }
+    tc_wait_ld();
+    {
+      uint32_t r0[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) r0[j] = r[j];
+      if (second) tc_ld32_issue(e.tbase + c0 + 32, r);      // the second half's TMEM load is in flight under the math
+      ext_half<MASK>(p, e, xr, r0, ax, ax_vec, c0, pk);
+    }
+    if (lane == 0) bulk_wait_read0();       // previous TMA store has finished reading the staging tile
+    __syncwarp();
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch)
+      st_shared_v4(e.row_smem + (((uint32_t)ch ^ e.sw) << 4), pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
+    // ---- columns [c0 + 32, c0 + 64)
+    if (second) {
+      ax_vec = aux_aligned && xr.row_valid && e.n0 + c0 + 64 <= p.N;
+      if (ax_vec) {
+        const uint4* ap = reinterpret_cast<const uint4*>(xr.aux_row + e.n0 + c0 + 32);
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) { const uint4 t = __ldg(ap + q4); ax[4 * q4] = t.x; ax[4 * q4 + 1] = t.y; ax[4 * q4 + 2] = t.z; ax[4 * q4 + 3] = t.w; }
+      }
+      tc_wait_ld();
+    }
+    // every TMEM read of this chunk has landed: hand the accumulator (half) back before the remaining math / staging / store
+    const int c_next = c0 + 64 * e.parts;
+    if (e.tempty_mid != 0u && c0 < 256 && c_next >= 256) epi_release<kCta>(e.tempty_mid, lane);
+    if (c_next >= e.bn || e.n0 + c_next >= p.N) { epi_release<kCta>(e.tempty, lane); released = true; }
+    if (second) {
+      ext_half<MASK>(p, e, xr, r, ax, ax_vec, c0 + 32, pk);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) pk[j] = 0u;
+    }
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch)
+      st_shared_v4(e.row_smem + (((uint32_t)(ch + 4) ^ e.sw) << 4), pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
+    fence_async_smem();
+    __syncwarp();
+    if (lane == 0 && warp_rows_valid) {
+      if (p.store_mode == JMT_STORE) tma_store_4d(tma_d, e.stage_smem, e.n0 + c0, e.m0w, e.b0, e.b1);
+      else tma_reduce_add_4d(tma_d, e.stage_smem, e.n0 + c0, e.m0w, e.b0, e.b1);
+      bulk_commit();
+    }
+  }
+  return released;
+}
+
 // kX3: "bf16x3" split-operand mode (SURVEY 7 hard part 4): every fp32 operand is given as two bf16 matrices of identical
 // geometry, x = hi + lo (hi = bf16(x), lo = bf16(x - hi), 16 mantissa bits together).  A stage holds the four tiles
 // A_hi | A_lo and B_hi | B_lo, and every k-step issues THREE tcgen05.mma into the same fp32 TMEM accumulator:
 // A_hi B_hi + A_hi B_lo + A_lo B_hi  (the dropped lo x lo term is 2^-16 relative) -- the 1e-3 parity gate on tensor cores.
-template <int kCta, bool kMask, int kEpi, bool kX3>
+// kExt: the extended backward epilogue (epi_tile_ext) -- its own instantiation so that the common kernels keep their register
+// allocation (127 registers, no spills; the extended epilogue needs ~170)
+template <int kCta, bool kMask, int kEpi, bool kX3, bool kExt>
 __global__ void __launch_bounds__(64 + 32 * kEpi, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a_hi, const __grid_constant__ CUtensorMap tma_b_hi,
                const __grid_constant__ CUtensorMap tma_d, const __grid_constant__ CUtensorMap tma_a_lo,
@@ -657,9 +809,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a_hi, const __grid_consta
       ec.prof = eprof;
 #endif
       bool released;
-      if (p.act == JMT_ACT_NONE) released = epi_tile<JMT_ACT_NONE, kMask, kCta>(p, &tma_d, ec);
-      else if (p.act == JMT_ACT_RELU) released = epi_tile<JMT_ACT_RELU, kMask, kCta>(p, &tma_d, ec);
-      else released = epi_tile<JMT_ACT_LEAKY_RELU, kMask, kCta>(p, &tma_d, ec);
+      if constexpr (kExt) {
+        released = epi_tile_ext<kMask, kCta>(p, &tma_d, ec);
+      } else {
+        if (p.act == JMT_ACT_NONE) released = epi_tile<JMT_ACT_NONE, kMask, kCta>(p, &tma_d, ec);
+        else if (p.act == JMT_ACT_RELU) released = epi_tile<JMT_ACT_RELU, kMask, kCta>(p, &tma_d, ec);
+        else released = epi_tile<JMT_ACT_LEAKY_RELU, kMask, kCta>(p, &tma_d, ec);
+      }
       if (!released) {
         // (a two-phase tile that ended before its half boundary -- columns beyond N -- still owes the half-0 arrive)
         if (ec.tempty_mid != 0u) epi_release<kCta>(ec.tempty_mid, lane);
@@ -801,6 +957,8 @@ static int gemm_tc_launch(const jmt_gemm_desc* g, const void* a_lo, const void* 
   p.fd_zrow.init(g->zero_row_period > 0 ? g->zero_row_period : 1); p.fd_cmask.init(g->colmask_row_period > 0 ? g->colmask_row_period : 1);
   p.d = g->d; p.bias = g->bias; p.d_ld = g->d_ld; p.d_bs0 = g->d_bs0; p.d_bs1 = g->d_bs1;
   p.alpha = g->alpha; p.slope = g->slope; p.d_dtype = g->d_dtype; p.act = g->act; p.store_mode = g->store_mode;
+  p.aux = (const __nv_bfloat16*)g->epi_aux; p.aux_slope = g->aux_slope; p.colsum = g->d_colsum; p.colsum_bs0 = g->colsum_bs0;
+  JMT_REQUIRE(!(x3 && (g->epi_aux || g->d_colsum)), "jmt_gemm_bf16x3: epi_aux / d_colsum are not available in the split-operand mode");
   const int64_t es = g->d_dtype == JMT_F32 ? 4 : 2;
   p.vec_ok = ((reinterpret_cast<uintptr_t>(g->d) & 15) == 0 && (g->d_ld * es) % 16 == 0 &&
               (g->d_bs0 * es) % 16 == 0 && (g->d_bs1 * es) % 16 == 0) ? 1 : 0;
@@ -880,6 +1038,7 @@ static int gemm_tc_launch(const jmt_gemm_desc* g, const void* a_lo, const void* 
   // accumulation and fp32 atomics both become cp.reduce.async.bulk.tensor .add
   CUtensorMap map_d = map_a;
   p.tma_store = p.vec_ok;
+  JMT_REQUIRE(!((g->epi_aux || g->d_colsum) && !p.tma_store), "jmt_gemm_bf16: epi_aux / d_colsum need a 16-byte aligned D geometry");
   if (p.tma_store) {
     const int dnb0 = p.reduce_batch ? 1 : g->nb0, dnb1 = p.reduce_batch ? 1 : g->nb1;
     rc = make_map_d(&map_d, g->d, g->d_dtype, g->N, g->M, g->d_ld, dnb0, g->d_bs0, dnb1, g->d_bs1, "jmt_gemm_bf16(D)");
@@ -892,10 +1051,12 @@ static int gemm_tc_launch(const jmt_gemm_desc* g, const void* a_lo, const void* 
   if (!attr_set[dev & 63].load(std::memory_order_acquire)) {
     cudaError_t e = cudaSuccess;
     auto set_smem = [&e](const void* fn) { if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); };
-    set_smem((const void*)gemm_tc_kernel<1, false, 8, false>); set_smem((const void*)gemm_tc_kernel<2, false, 8, false>);
-    set_smem((const void*)gemm_tc_kernel<1, true, 8, false>); set_smem((const void*)gemm_tc_kernel<2, true, 8, false>);
-    set_smem((const void*)gemm_tc_kernel<1, false, 8, true>); set_smem((const void*)gemm_tc_kernel<2, false, 8, true>);
-    set_smem((const void*)gemm_tc_kernel<1, true, 8, true>); set_smem((const void*)gemm_tc_kernel<2, true, 8, true>);
+    set_smem((const void*)gemm_tc_kernel<1, false, 8, false, false>); set_smem((const void*)gemm_tc_kernel<2, false, 8, false, false>);
+    set_smem((const void*)gemm_tc_kernel<1, true, 8, false, false>); set_smem((const void*)gemm_tc_kernel<2, true, 8, false, false>);
+    set_smem((const void*)gemm_tc_kernel<1, false, 8, true, false>); set_smem((const void*)gemm_tc_kernel<2, false, 8, true, false>);
+    set_smem((const void*)gemm_tc_kernel<1, true, 8, true, false>); set_smem((const void*)gemm_tc_kernel<2, true, 8, true, false>);
+    set_smem((const void*)gemm_tc_kernel<1, false, 8, false, true>); set_smem((const void*)gemm_tc_kernel<2, false, 8, false, true>);
+    set_smem((const void*)gemm_tc_kernel<1, true, 8, false, true>); set_smem((const void*)gemm_tc_kernel<2, true, 8, false, true>);
     if (e != cudaSuccess) { set_error("jmt_gemm_bf16: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); cudaGetLastError(); return JMT_ERR_CUDA; }
     attr_set[dev & 63].store(1, std::memory_order_release);
   }
@@ -918,8 +1079,10 @@ static int gemm_tc_launch(const jmt_gemm_desc* g, const void* a_lo, const void* 
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 2 : 1;
   cudaError_t le;
-#define JMT_TC_LAUNCH(CTA, MASK, X3) le = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<CTA, MASK, 8, X3>, map_a, map_b, map_d, map_a_lo, map_b_lo, p)
-#define JMT_TC_LAUNCH_X(CTA, MASK) do { if (x3) JMT_TC_LAUNCH(CTA, MASK, true); else JMT_TC_LAUNCH(CTA, MASK, false); } while (0)
+#define JMT_TC_LAUNCH(CTA, MASK, X3, EXT) le = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<CTA, MASK, 8, X3, EXT>, map_a, map_b, map_d, map_a_lo, map_b_lo, p)
+#define JMT_TC_LAUNCH_X(CTA, MASK) do { if (x3) JMT_TC_LAUNCH(CTA, MASK, true, false); else if (ext) JMT_TC_LAUNCH(CTA, MASK, false, true); \
+                                        else JMT_TC_LAUNCH(CTA, MASK, false, false); } while (0)
+  const bool ext = p.aux != nullptr || p.colsum != nullptr;
   if (p.colmask) { if (p.cluster == 2) JMT_TC_LAUNCH_X(2, true); else JMT_TC_LAUNCH_X(1, true); }
   else { if (p.cluster == 2) JMT_TC_LAUNCH_X(2, false); else JMT_TC_LAUNCH_X(1, false); }
 #undef JMT_TC_LAUNCH_X

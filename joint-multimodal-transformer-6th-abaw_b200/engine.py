@@ -97,13 +97,26 @@ class GradBuf:
 
 
 class Var:
-    """An activation on the tape: ``data`` is a 2-D (rows, cols) view with unit inner stride."""
-    __slots__ = ("data", "gbuf", "needs_grad")
+    """An activation on the tape: ``data`` is a 2-D (rows, cols) view with unit inner stride.
+
+    Backward-epilogue bookkeeping (bf16 mode, jmt_gemm_desc.epi_aux / d_colsum):
+      track_colsum : this Var is the output of a Linear / conv with a bias: GEMMs that write its gradient also add the column
+                     sums of what they write into ``colsum_tmp`` (= the bias gradient) -- valid as long as EVERY writer did
+                     (``colsum_ok``); otherwise the producer falls back to a column-sum pass over the finished gradient.
+      fold         : (slope, mask, mask_scale, mask_rows) when this Var is act(pre) [* channel-dropout mask] and its only
+                     consumer is a GEMM: that GEMM's dgrad epilogue multiplies by act'(data) (and the mask), so the gradient
+                     buffer holds d(pre) (``folded``) and no act-bwd pass runs."""
+    __slots__ = ("data", "gbuf", "needs_grad", "track_colsum", "colsum_tmp", "colsum_ok", "fold", "folded")
 
     def __init__(self, data: torch.Tensor, needs_grad: bool = True):
         self.data = data
         self.gbuf: Optional[GradBuf] = None
         self.needs_grad = needs_grad
+        self.track_colsum = False
+        self.colsum_tmp: Optional[torch.Tensor] = None
+        self.colsum_ok = True
+        self.fold: Optional[tuple] = None
+        self.folded = False
 
     @property
     def grad(self) -> Optional[torch.Tensor]:
@@ -300,8 +313,30 @@ class Ctx:
         return out
 
     # ---------------------------------------------------------------- gradient plumbing
-    def grad_target(self, v: Var) -> Tuple[torch.Tensor, int]:
-        """Tensor to write d(v) into and the store mode (STORE the first time, ACCUMULATE after)."""
+    def ext_on(self) -> bool:
+        """backward-epilogue extensions (activation-gradient fold, bias-gradient column sums) are a bf16 tensor-core feature"""
+        return self.precision == "bf16" and EPI_EXT
+
+    def colsum_target(self, v: Var, c0: int = 0, c1: Optional[int] = None) -> Optional[torch.Tensor]:
+        """fp32 accumulator slice for the column sums of a gradient contribution to v[:, c0:c1] written by a capable GEMM
+        (None: not tracked).  Callers must have obtained the gradient buffer with capable=True."""
+        if not (v.track_colsum and self.ext_on()):
+            return None
+        if v.colsum_tmp is None:
+            v.colsum_tmp = self.zeros((v.data.shape[1],), torch.float32)
+        return v.colsum_tmp[c0:c1 if c1 is not None else v.data.shape[1]]
+
+    def _incapable_writer(self, v: Var):
+        """a writer of d(v) that cannot fold the activation gradient / emit column sums"""
+        v.colsum_ok = False
+        if v.fold is not None:
+            raise RuntimeError("jmt_b200 engine: an activation marked fold_act has a consumer that is not a GEMM")
+
+    def grad_target(self, v: Var, capable: bool = False) -> Tuple[torch.Tensor, int]:
+        """Tensor to write d(v) into and the store mode (STORE the first time, ACCUMULATE after).  capable: the caller is a
+        GEMM that honours v.fold and adds its column sums to colsum_target(v)."""
+        if not (capable and self.ext_on()):
+            self._incapable_writer(v)
         if v.gbuf is None:
             v.gbuf = GradBuf(self.empty(v.data.shape, v.data.dtype))
             return v.gbuf.t, L.STORE
@@ -317,6 +352,7 @@ class Ctx:
         """d(v) += gb.  A Var without gradient aliases the buffer (ref-counted) instead of copying."""
         if not v.needs_grad:
             return
+        self._incapable_writer(v)
         if v.gbuf is None:
             gb.refs += 1
             v.gbuf = gb
@@ -371,7 +407,8 @@ def gemm(ctx: Ctx, a: torch.Tensor, b: torch.Tensor, d: torch.Tensor, *, M: int,
          a_major=L.MAJOR_K, b_major=L.MAJOR_K, a_rows=None, b_rows=None, a_ld=None, b_ld=None, d_ld=None,
          nb0=1, nb1=1, a_bs=(0, 0), b_bs=(0, 0), d_bs=(0, 0), bias=None, act=L.ACT_NONE, slope=0.0, alpha=1.0,
          store=L.STORE, ntaps=1, a_shift=(0, 0), b_shift=(0, 0), reduce_batch=False, split_k=1,
-         colmask=None, colmask_scale=1.0, colmask_row_period=0, zero_rows=(0, 0), alg_flops=None):
+         colmask=None, colmask_scale=1.0, colmask_row_period=0, zero_rows=(0, 0), alg_flops=None,
+         epi_aux=None, aux_slope=0.0, d_colsum=None, colsum_bs0=0):
     """One GEMM of the family in include/jmt_b200.h.  a/b/d supply base pointers and dtypes (views
     allowed); strides are in elements."""
     require_cuda(a, b, d)
@@ -401,6 +438,10 @@ def gemm(ctx: Ctx, a: torch.Tensor, b: torch.Tensor, d: torch.Tensor, *, M: int,
     g.colmask_scale = colmask_scale
     g.colmask_row_period = colmask_row_period
     g.zero_row_period, g.zero_row_count = zero_rows
+    g.epi_aux = epi_aux.data_ptr() if epi_aux is not None else None
+    g.aux_slope = aux_slope
+    g.d_colsum = d_colsum.data_ptr() if d_colsum is not None else None
+    g.colsum_bs0 = colsum_bs0
     prof = PROFILE
     if prof is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -545,13 +586,15 @@ def linear(ctx: Ctx, x: Var, wname: str, bname: Optional[str], act=L.ACT_NONE, s
            out: Optional[torch.Tensor] = None, w_rows: Optional[Tuple[int, int]] = None,
            w_cols: Optional[Tuple[int, int]] = None, accumulate_into: Optional[Var] = None,
            grad_from: Optional[Tuple[Var, int, int]] = None, bias_grad_external: bool = False,
-           zero_rows: Tuple[int, int] = (0, 0)) -> Var:
+           zero_rows: Tuple[int, int] = (0, 0), fold_act: bool = False) -> Var:
     """y = act(x W[r0:r1, c0:c1]^T + b[r0:r1])  (nn.Linear).  ``out`` may be a strided (rows, N) view
     (concat-free epilogue: a GEMM writes straight into its slice of a wider buffer);
     ``accumulate_into`` adds into an existing Var (Linear over a concatenation = sum of Linears over
     column blocks of W, FeatureConcatFC / out_layer_pv without materialising the cat).
     ``bias_grad_external``: the bias gradient (column sums of dy) is produced by the consumer's backward kernel
-    (add_layernorm's dz column sums), so no separate pass over dy runs here."""
+    (add_layernorm's dz column sums), so no separate pass over dy runs here.
+    ``fold_act``: the caller guarantees that y's only consumer is another GEMM op (Linear / conv): that op's dgrad epilogue
+    multiplies by act'(y) and emits the column sums, so neither the act-bwd nor the bias-gradient pass runs (bf16 mode)."""
     W = ctx.w(wname)
     if W.dim() == 3:                       # 1x1 Conv1d weight (cout, cin, 1)
         W = W.view(W.shape[0], W.shape[1])
@@ -571,6 +614,11 @@ def linear(ctx: Ctx, x: Var, wname: str, bname: Optional[str], act=L.ACT_NONE, s
             out = ctx.empty((M, N))
         y = Var(out)
         gemm(ctx, x.data, Wv, out, M=M, N=N, K=K, bias=bias, act=act, slope=slope, zero_rows=zero_rows)
+        if ctx.record and ctx.ext_on() and grad_from is None and out.is_contiguous():
+            # writers of d(y) that are GEMMs add their column sums (= this bias gradient) on the fly
+            y.track_colsum = bool(bname) and not bias_grad_external and (act == L.ACT_NONE or fold_act)
+            if fold_act and act != L.ACT_NONE and zero_rows == (0, 0):
+                y.fold = (slope, None, 1.0, 0)
     if ctx.record:
         def bwd():
             if grad_from is not None:          # `out` is a column slice of a wider buffer owned by grad_from[0]
@@ -581,7 +629,11 @@ def linear(ctx: Ctx, x: Var, wname: str, bname: Optional[str], act=L.ACT_NONE, s
             if dy is None:
                 return
             need_colsum = bool(bname) and not bias_grad_external
-            if act != L.ACT_NONE:          # activation gradient and bias gradient in one pass over dy
+            if need_colsum and y.track_colsum and y.colsum_ok and y.colsum_tmp is not None and (act == L.ACT_NONE or y.folded):
+                # every writer of dy was a GEMM that already summed its columns: add the (N,) accumulator to the bias gradient
+                L.check(ctx.lib.jmt_axpy(_ptr(y.colsum_tmp), _ptr(ctx.pgrad(bname)[r0:r1]), 1.0, N, L.F32, _stream()), "jmt_axpy")
+                need_colsum = False
+            if act != L.ACT_NONE and not y.folded:          # activation gradient and bias gradient in one pass over dy
                 dy = _act_bwd(ctx, y, dy, slope, colsum=ctx.pgrad(bname)[r0:r1] if need_colsum else None)
             elif need_colsum:
                 L.check(ctx.lib.jmt_colsum(_ptr(dy), _DT[dy.dtype], dy.stride(0), M, N, _ptr(ctx.pgrad(bname)[r0:r1]),
@@ -594,12 +646,30 @@ def linear(ctx: Ctx, x: Var, wname: str, bname: Optional[str], act=L.ACT_NONE, s
             gemm(ctx, dy, x.data, dW, M=N, N=K, K=M, a_major=L.MAJOR_MN, b_major=L.MAJOR_MN,
                  store=L.ATOMIC_ADD, split_k=wgrad_split(M, N, K))
             if x.needs_grad:
-                dx, mode = ctx.grad_target(x)
-                gemm(ctx, dy, Wv, dx, M=M, N=K, K=N, b_major=L.MAJOR_MN, store=mode)
+                dx, mode = ctx.grad_target(x, capable=True)
+                _dgrad_gemm(ctx, x, dy, Wv, dx, mode, M=M, N=K, K=N, b_major=L.MAJOR_MN)
             if accumulate_into is None:
                 ctx.release(y)
         ctx.tape.append(bwd)
     return y
+
+
+def _dgrad_gemm(ctx: Ctx, x: Var, dy: torch.Tensor, w: torch.Tensor, dx: torch.Tensor, mode: int, **kw):
+    """The GEMM that writes d(x): with the backward-epilogue extensions it multiplies by act'(x) (and the channel-dropout mask)
+    when x is marked `fold`, and adds the column sums of what it writes to x's bias-gradient accumulator."""
+    if ctx.ext_on() and dx.dtype == torch.bfloat16:
+        if x.fold is not None:
+            slope, mask, mscale, mrows = x.fold
+            kw.update(epi_aux=x.data, aux_slope=slope)
+            if mask is not None:
+                kw.update(colmask=mask, colmask_scale=mscale, colmask_row_period=mrows)
+            x.folded = True
+        cs = ctx.colsum_target(x)
+        if cs is not None:
+            kw.update(d_colsum=cs)
+    elif x.fold is not None or x.track_colsum:
+        ctx._incapable_writer(x)
+    gemm(ctx, dy, w, dx, store=mode, **kw)
 
 
 def _act_bwd(ctx: Ctx, y: Var, dy: torch.Tensor, slope: float, colsum: Optional[torch.Tensor] = None,
@@ -668,6 +738,7 @@ class AttnGeom:
 
 def _proj_grad(ctx: Ctx, v: Var) -> torch.Tensor:
     """Gradient buffer of a Var that is written piecewise with ACCUMULATE semantics (zero-filled on first touch)."""
+    ctx._incapable_writer(v)
     if v.gbuf is None:
         v.gbuf = GradBuf(ctx.zeros(v.data.shape, v.data.dtype))
     elif v.gbuf.refs > 1:
@@ -677,14 +748,16 @@ def _proj_grad(ctx: Ctx, v: Var) -> torch.Tensor:
     return v.gbuf.t
 
 
-def _proj_grad_slice(ctx: Ctx, v: Var, c0: int, c1: int) -> Tuple[torch.Tensor, int]:
+def _proj_grad_slice(ctx: Ctx, v: Var, c0: int, c1: int, capable: bool = False) -> Tuple[torch.Tensor, int]:
     """Column slice [c0, c1) of the gradient buffer of projection matrix `v` and the store mode for writing it: the first
     write of a slice STOREs into an un-initialised buffer, later writes of the same slice (a Q projection shared by two
     attention calls) ACCUMULATE."""
+    if not (capable and ctx.ext_on()):
+        ctx._incapable_writer(v)
     if v.gbuf is None:
         v.gbuf = GradBuf(ctx.empty(v.data.shape, v.data.dtype), written=[])
     elif v.gbuf.refs > 1:
-        ctx.grad_target(v)
+        ctx.grad_target(v, capable=capable)
     gb = v.gbuf
     if gb.written is None:
         return gb.t[:, c0:c1], L.ACCUMULATE
@@ -699,6 +772,7 @@ def _proj_grad_slice(ctx: Ctx, v: Var, c0: int, c1: int) -> Tuple[torch.Tensor, 
 
 FUSED_ATTENTION = True      # bf16 mode: True = QK^T -> softmax -> PV in one kernel when the geometry is supported; "p" = QK^T +
                             # softmax fused, PV a plain GEMM (measured 1.4 % slower per step); False = GEMM + softmax kernels
+EPI_EXT = os.environ.get("JMT_EPI_EXT", "1") != "0"   # fold act' / emit bias-gradient column sums in the backward GEMM epilogues
 LONG_S_CHUNKED = True       # forward-only attention beyond the fused kernel's key limit: chunked fused kernel + log-sum-exp merge
 LONG_S_CHUNK_MIN_BYTES = 2 << 30   # ... once the fp32 score tensor of the composed path would exceed this (measured: NONE eval at
                                    # B = 1024, 1.26 GB of scores, 7.4 ms composed vs 9.1 ms chunked; B = 4096, 20 GB: chunked only)
@@ -816,7 +890,10 @@ def attention_core(ctx: Ctx, q: Var, qcol: int, k: Var, kcol: int, v: Var, vcol:
                 return
             assert do.is_contiguous()
             rows = NB * heads * Lq
-            gq_s, q_mode = _proj_grad_slice(ctx, q, qcol, qcol + E)
+            # the plain GEMMs that write dQ / dK / dV also add their column sums to the projection's bias-gradient accumulator
+            gemm_dq = not (fused and FUSED_ATTENTION_BWD and FUSED_ATTENTION_BWD != "ds")
+            gq_s, q_mode = _proj_grad_slice(ctx, q, qcol, qcol + E, capable=gemm_dq)
+            cs_q = dict(d_colsum=ctx.colsum_target(q, qcol, qcol + E), colsum_bs0=dh) if gemm_dq and q.track_colsum and ctx.ext_on() else {}
             q_gld = gq_s.stride(0)
             dq_geo = (gq.seq_stride * q_gld, dh, gq.batch_stride * q_gld)
             ds = ctx.empty((NB, heads, Lq, s_ld))
@@ -831,7 +908,7 @@ def attention_core(ctx: Ctx, q: Var, qcol: int, k: Var, kcol: int, v: Var, vcol:
                 gemm(ctx, ds, kd, gq_s, M=Lq, N=dh, K=S, a_rows=Lq, b_major=L.MAJOR_MN, b_rows=S,
                      a_ld=s_ld, b_ld=gk.seq_stride * kld, d_ld=gq.seq_stride * q_gld,
                      nb0=heads, nb1=NB, a_bs=sb, b_bs=(dh, gk.batch_stride * kld), d_bs=(dh, gq.batch_stride * q_gld),
-                     store=q_mode)
+                     store=q_mode, **cs_q)
                 dk_alpha = 1.0
             elif fused and FUSED_ATTENTION_BWD:
                 # dP = dO V^T -> dS = scale * P o (dP - rowsum(P o dP)) -> dQ += dS K, one kernel; dS is saved for dK
@@ -849,18 +926,20 @@ def attention_core(ctx: Ctx, q: Var, qcol: int, k: Var, kcol: int, v: Var, vcol:
                 gemm(ctx, ds, kd, gq_s, M=Lq, N=dh, K=S, a_rows=Lq, b_major=L.MAJOR_MN, b_rows=S,
                      a_ld=s_ld, b_ld=gk.seq_stride * kld, d_ld=gq.seq_stride * q_gld,
                      nb0=heads, nb1=NB, a_bs=sb, b_bs=(dh, gk.batch_stride * kld), d_bs=(dh, gq.batch_stride * q_gld),
-                     alpha=scale, store=q_mode)                                # dQ = scale * dS K
+                     alpha=scale, store=q_mode, **cs_q)                        # dQ = scale * dS K
                 dk_alpha = scale
-            gv, v_mode = _proj_grad_slice(ctx, v, vcol, vcol + E)         # dV = P^T dO
+            gv, v_mode = _proj_grad_slice(ctx, v, vcol, vcol + E, capable=True)         # dV = P^T dO
+            cs_v = dict(d_colsum=ctx.colsum_target(v, vcol, vcol + E), colsum_bs0=dh) if v.track_colsum and ctx.ext_on() else {}
             gemm(ctx, probs, do, gv, M=S, N=dh, K=Lq, a_major=L.MAJOR_MN, b_major=L.MAJOR_MN,
                  a_rows=Lq, b_rows=Lq, a_ld=s_ld, b_ld=gq.seq_stride * E, d_ld=gk.seq_stride * gv.stride(0),
                  nb0=heads, nb1=NB, a_bs=sb, b_bs=(dh, gq.batch_stride * E), d_bs=(dh, gk.batch_stride * gv.stride(0)),
-                 store=v_mode)
-            gk_, k_mode = _proj_grad_slice(ctx, k, kcol, kcol + E)        # dK = scale * dS^T Q
+                 store=v_mode, **cs_v)
+            gk_, k_mode = _proj_grad_slice(ctx, k, kcol, kcol + E, capable=True)        # dK = scale * dS^T Q
+            cs_k = dict(d_colsum=ctx.colsum_target(k, kcol, kcol + E), colsum_bs0=dh) if k.track_colsum and ctx.ext_on() else {}
             gemm(ctx, ds, qd, gk_, M=S, N=dh, K=Lq, a_major=L.MAJOR_MN, b_major=L.MAJOR_MN,
                  a_rows=Lq, b_rows=Lq, a_ld=s_ld, b_ld=gq.seq_stride * qld, d_ld=gk.seq_stride * gk_.stride(0),
                  nb0=heads, nb1=NB, a_bs=sb, b_bs=(dh, gq.batch_stride * qld), d_bs=(dh, gk.batch_stride * gk_.stride(0)),
-                 alpha=dk_alpha, store=k_mode)
+                 alpha=dk_alpha, store=k_mode, **cs_k)
             ctx.release(out)
         ctx.tape.append(bwd)
     return out
@@ -923,7 +1002,7 @@ def encoder_layer(ctx: Ctx, x: Var, prefix: str, heads: int, geom: Optional[Attn
     a = mha_self(ctx, x, prefix + "attention.", heads, geom, small, out_bias_grad_external=True)
     x1 = add_layernorm(ctx, x, a, prefix + "layer_norm1.weight", prefix + "layer_norm1.bias",
                        res_bias=prefix + "attention.out_proj.bias")
-    h = linear(ctx, x1, prefix + "feed_forward.0.weight", prefix + "feed_forward.0.bias", act=L.ACT_RELU)
+    h = linear(ctx, x1, prefix + "feed_forward.0.weight", prefix + "feed_forward.0.bias", act=L.ACT_RELU, fold_act=True)
     f = linear(ctx, h, prefix + "feed_forward.2.weight", prefix + "feed_forward.2.bias", bias_grad_external=True)
     return add_layernorm(ctx, x1, f, prefix + "layer_norm2.weight", prefix + "layer_norm2.bias",
                          res_bias=prefix + "feed_forward.2.bias")
@@ -1096,8 +1175,8 @@ def regressor_heads(ctx: Ctx, x: Var, pre: Sequence[str], B: int, T: int, time_m
                     gemm(ctx, dhl[g], x.data, gw, M=128, N=K, K=M, a_major=L.MAJOR_MN, b_major=L.MAJOR_MN, a_rows=M, b_rows=M,
                          a_ld=256, store=L.ATOMIC_ADD, split_k=wgrad_split(M, 128, K))
             if x.needs_grad:
-                dx, mode = ctx.grad_target(x)
-                gemm(ctx, dH, Wc, dx, M=M, N=K, K=256, b_major=L.MAJOR_MN, store=mode)
+                dx, mode = ctx.grad_target(x, capable=True)
+                _dgrad_gemm(ctx, x, dH, Wc, dx, mode, M=M, N=K, K=256, b_major=L.MAJOR_MN)
         ctx.tape.append(bwd)
 
     def set_gout(g, t):
@@ -1209,7 +1288,7 @@ def weight_norm_bwd_group(ctx: Ctx, weights: dict, convs: Sequence[Tuple[str, in
 
 
 def causal_conv(ctx: Ctx, x: Var, prefix: str, N: int, Ls: int, cin: int, cout: int, k: int, dil: int, act: int,
-                drop_p: float = 0.0, pad: int = 0, weights: Optional[tuple] = None) -> Var:
+                drop_p: float = 0.0, pad: int = 0, weights: Optional[tuple] = None, fold_act: bool = False) -> Var:
     """weight-normed dilated causal Conv1d + Chomp1d + LeakyReLU + Dropout2d (temporal_convolutional_model.py:24-29)
     as an implicit GEMM on the flat padded channels-last layout (see above): taps are K blocks whose A rows are
     shifted by -(k-1-j)*dil; the zero padding rows in front of every sequence supply the causal zeros.
@@ -1243,6 +1322,11 @@ def causal_conv(ctx: Ctx, x: Var, prefix: str, N: int, Ls: int, cin: int, cout: 
     if mask is not None and not fuse_mask:
         L.check(ctx.lib.jmt_apply_mask(_ptr(y), _ptr(mask), _ptr(y), N, Lp, cout, 1, mscale, ctx.acode, _stream()), "jmt_apply_mask")
     out = Var(y)
+    if ctx.record and ctx.ext_on() and fold_act and act != L.ACT_NONE and (mask is None or fuse_mask):
+        # the only consumer is the next conv's GEMM: its dgrad epilogue applies the channel mask and LeakyReLU'(y) and sums the
+        # columns (this conv's bias gradient), so no pass over d(y) runs here
+        out.fold = (LEAKY_SLOPE, mask, mscale, Lp if mask is not None else 0)
+        out.track_colsum = True
     if ctx.record:
         def bwd():
             dy = out.grad
@@ -1251,7 +1335,12 @@ def causal_conv(ctx: Ctx, x: Var, prefix: str, N: int, Ls: int, cin: int, cout: 
             assert dy.is_contiguous()
             # where a channel was dropped y = 0 and the masked dy is 0, so act'(y) of the post-dropout y is exact;
             # padding rows of dy are zero (every producer keeps them so) and stay zero
-            if act != L.ACT_NONE or mask is not None:
+            if out.folded:
+                if out.colsum_ok and out.colsum_tmp is not None:
+                    L.check(ctx.lib.jmt_axpy(_ptr(out.colsum_tmp), _ptr(ctx.pgrad(prefix + "bias")), 1.0, cout, L.F32, _stream()), "jmt_axpy")
+                else:
+                    L.check(ctx.lib.jmt_colsum(_ptr(dy), _DT[dy.dtype], cout, R, cout, _ptr(ctx.pgrad(prefix + "bias")), _stream()), "jmt_colsum")
+            elif act != L.ACT_NONE or mask is not None:
                 dy = _act_bwd(ctx, out, dy, LEAKY_SLOPE if act != L.ACT_NONE else 1.0, colsum=ctx.pgrad(prefix + "bias"),
                               mask=mask, mask_rows=Lp, mask_scale=mscale)
             else:
@@ -1271,9 +1360,9 @@ def causal_conv(ctx: Ctx, x: Var, prefix: str, N: int, Ls: int, cin: int, cout: 
             dwh["t"] = dw
             if x.needs_grad:
                 # dgrad: dx[r] = sum_j W_j^T dy[r + (k-1-j) dil]; rows past a sequence's end are the next one's zero padding
-                dx, mode = ctx.grad_target(x)
-                gemm(ctx, dy, w_dg, dx, M=R, N=cin, K=cout, a_rows=R, b_rows=cin, a_ld=cout, b_ld=k * cout, d_ld=cin,
-                     ntaps=k, a_shift=((k - 1) * dil, -dil), store=mode, zero_rows=(Lp, pad), alg_flops=sum(tap_flops))
+                dx, mode = ctx.grad_target(x, capable=True)
+                _dgrad_gemm(ctx, x, dy, w_dg, dx, mode, M=R, N=cin, K=cout, a_rows=R, b_rows=cin, a_ld=cout, b_ld=k * cout, d_ld=cin,
+                            ntaps=k, a_shift=((k - 1) * dil, -dil), zero_rows=(Lp, pad), alg_flops=sum(tap_flops))
             ctx.release(out)
         ctx.tape.append(bwd)
     return out

@@ -632,7 +632,7 @@ def _tcn_graph(ctx, h, prefix, specs, N, Ls, pad):
         if wn is not None:
             E.weight_norm_bwd_group(ctx, wn, [(pre + "conv1.", cout, cin), (pre + "conv2.", cout, cout)], k)
             w1, w2 = wn[pre + "conv1."], wn[pre + "conv2."]
-        y = E.causal_conv(ctx, h, pre + "conv1.", N, Ls, cin, cout, k, d, L.ACT_LEAKY, drop_p=p, pad=pad, weights=w1)
+        y = E.causal_conv(ctx, h, pre + "conv1.", N, Ls, cin, cout, k, d, L.ACT_LEAKY, drop_p=p, pad=pad, weights=w1, fold_act=True)
         y = E.causal_conv(ctx, y, pre + "conv2.", N, Ls, cout, cout, k, d, L.ACT_LEAKY, drop_p=p, pad=pad, weights=w2)
         res = _conv1x1(ctx, h, pre + "downsample.", (Ls + pad, pad)) if has_ds else h
         h = E.add_act(ctx, y, res, L.ACT_LEAKY, E.LEAKY_SLOPE)

@@ -304,6 +304,49 @@ def test_gemm_wgrad_taps_batched(precision, geom):
     assert (dw.cpu().double() - want).abs().max() < tol * want.abs().max()
 
 
+@pytest.mark.parametrize("case", ["wide_fold_colsum", "narrow_colsum_acc", "heads_colsum", "ragged_fold"])
+def test_gemm_backward_epilogue_extensions(case):
+    """jmt_gemm_desc.epi_aux / d_colsum: the dgrad epilogue multiplies by act'(aux) and adds the column sums of what it stores
+    (the producer's bias gradient) -- against the plain GEMM followed by the separate passes."""
+    torch.manual_seed(21)
+    dev = torch.device("cuda")
+    ctx = _ctx("bf16")
+    if case == "heads_colsum":
+        B, T, E_, h = 5, 150, 256, 4
+        dh = E_ // h
+        ds = (torch.randn(B, h, T, 152) * 0.3).to(torch.bfloat16).to(dev)
+        kk = (torch.randn(B * T, E_) * 0.5).to(torch.bfloat16).to(dev)
+        dq = torch.zeros(B * T, E_, dtype=torch.bfloat16, device=dev)
+        cs = torch.zeros(E_, dtype=torch.float32, device=dev)
+        E.gemm(ctx, ds, kk, dq, M=T, N=dh, K=T, a_rows=T, b_major=L.MAJOR_MN, b_rows=T, a_ld=152, b_ld=E_, d_ld=E_,
+               nb0=h, nb1=B, a_bs=(T * 152, h * T * 152), b_bs=(dh, T * E_), d_bs=(dh, T * E_), d_colsum=cs, colsum_bs0=dh)
+        torch.cuda.synchronize()
+        ref = torch.einsum("bhts,bshd->bthd", ds.float()[..., :T], kk.float().view(B, T, h, dh)).reshape(B * T, E_)
+        assert (dq.float() - ref).abs().max() < 2e-2 * ref.abs().max()
+        want = ref.double().sum(0)
+        assert (cs.double() - want).abs().max() < 2e-3 * want.abs().max() + 1e-3, (cs.double() - want).abs().max()
+        return
+    M, N, K, store, slope, use_aux = {"wide_fold_colsum": (256 * 78, 512, 512, L.STORE, 0.0, True),
+                                      "narrow_colsum_acc": (1000, 384, 192, L.ACCUMULATE, 0.0, False),
+                                      "ragged_fold": (333, 200, 136, L.STORE, 0.01, True)}[case]
+    a = (torch.randn(M, K) * 0.5).to(torch.bfloat16).to(dev)
+    w = (torch.randn(K, N) * 0.5).to(torch.bfloat16).to(dev)               # B MN-major (dgrad of a Linear)
+    aux = torch.randn(M, N).to(torch.bfloat16).to(dev)
+    d0 = (torch.randn(M, N) * 0.1).to(torch.bfloat16).to(dev)
+    d = d0.clone()
+    cs = torch.full((N,), 0.5, dtype=torch.float32, device=dev)             # accumulates on top of what is there
+    E.gemm(ctx, a, w, d, M=M, N=N, K=K, b_major=L.MAJOR_MN, store=store, epi_aux=aux if use_aux else None, aux_slope=slope,
+           d_colsum=cs)
+    torch.cuda.synchronize()
+    val = a.double() @ w.double()
+    if use_aux:
+        val = torch.where(aux.double() > 0, val, val * slope)
+    want_d = val if store == L.STORE else val + d0.double()
+    assert (d.double() - want_d).abs().max() < 1.2e-2 * want_d.abs().max()
+    want_cs = val.sum(0) + 0.5
+    assert (cs.double() - want_cs).abs().max() < 2e-3 * want_cs.abs().max() + 1e-2, (cs.double() - want_cs).abs().max()
+
+
 def test_gemm_heads_geometry():
     """(b, head) batching through two batch dims with non-monotonic strides (Q of shape (B*T, 3E))."""
     torch.manual_seed(3)
