@@ -103,10 +103,12 @@ class Var:
       track_colsum : this Var is the output of a Linear / conv with a bias: GEMMs that write its gradient also add the column
                      sums of what they write into ``colsum_tmp`` (= the bias gradient) -- valid as long as EVERY writer did
                      (``colsum_ok``); otherwise the producer falls back to a column-sum pass over the finished gradient.
+      colsum_direct: the graph GUARANTEES that every writer is such a GEMM (projections feeding the GEMM-based attention backward,
+                     folded activations): the column sums go straight into the bias gradient, no accumulator, no extra launch.
       fold         : (slope, mask, mask_scale, mask_rows) when this Var is act(pre) [* channel-dropout mask] and its only
                      consumer is a GEMM: that GEMM's dgrad epilogue multiplies by act'(data) (and the mask), so the gradient
                      buffer holds d(pre) (``folded``) and no act-bwd pass runs."""
-    __slots__ = ("data", "gbuf", "needs_grad", "track_colsum", "colsum_tmp", "colsum_ok", "fold", "folded")
+    __slots__ = ("data", "gbuf", "needs_grad", "track_colsum", "colsum_tmp", "colsum_ok", "fold", "folded", "colsum_direct")
 
     def __init__(self, data: torch.Tensor, needs_grad: bool = True):
         self.data = data
@@ -117,6 +119,7 @@ class Var:
         self.colsum_ok = True
         self.fold: Optional[tuple] = None
         self.folded = False
+        self.colsum_direct: Optional[Callable[[], torch.Tensor]] = None   # getter of the bias-gradient slice the writers add into
 
     @property
     def grad(self) -> Optional[torch.Tensor]:
@@ -322,15 +325,19 @@ class Ctx:
         (None: not tracked).  Callers must have obtained the gradient buffer with capable=True."""
         if not (v.track_colsum and self.ext_on()):
             return None
+        c1 = c1 if c1 is not None else v.data.shape[1]
+        if v.colsum_direct is not None:
+            return v.colsum_direct()[c0:c1]
         if v.colsum_tmp is None:
             v.colsum_tmp = self.zeros((v.data.shape[1],), torch.float32)
-        return v.colsum_tmp[c0:c1 if c1 is not None else v.data.shape[1]]
+        return v.colsum_tmp[c0:c1]
 
     def _incapable_writer(self, v: Var):
         """a writer of d(v) that cannot fold the activation gradient / emit column sums"""
         v.colsum_ok = False
-        if v.fold is not None:
-            raise RuntimeError("jmt_b200 engine: an activation marked fold_act has a consumer that is not a GEMM")
+        if v.fold is not None or v.colsum_direct is not None:
+            raise RuntimeError("jmt_b200 engine: an activation whose gradient must be written by GEMMs only (fold_act / "
+                               "gemm_writers_only) got another kind of consumer")
 
     def grad_target(self, v: Var, capable: bool = False) -> Tuple[torch.Tensor, int]:
         """Tensor to write d(v) into and the store mode (STORE the first time, ACCUMULATE after).  capable: the caller is a
@@ -586,7 +593,7 @@ def linear(ctx: Ctx, x: Var, wname: str, bname: Optional[str], act=L.ACT_NONE, s
            out: Optional[torch.Tensor] = None, w_rows: Optional[Tuple[int, int]] = None,
            w_cols: Optional[Tuple[int, int]] = None, accumulate_into: Optional[Var] = None,
            grad_from: Optional[Tuple[Var, int, int]] = None, bias_grad_external: bool = False,
-           zero_rows: Tuple[int, int] = (0, 0), fold_act: bool = False) -> Var:
+           zero_rows: Tuple[int, int] = (0, 0), fold_act: bool = False, gemm_writers_only: bool = False) -> Var:
     """y = act(x W[r0:r1, c0:c1]^T + b[r0:r1])  (nn.Linear).  ``out`` may be a strided (rows, N) view
     (concat-free epilogue: a GEMM writes straight into its slice of a wider buffer);
     ``accumulate_into`` adds into an existing Var (Linear over a concatenation = sum of Linears over
@@ -594,7 +601,9 @@ def linear(ctx: Ctx, x: Var, wname: str, bname: Optional[str], act=L.ACT_NONE, s
     ``bias_grad_external``: the bias gradient (column sums of dy) is produced by the consumer's backward kernel
     (add_layernorm's dz column sums), so no separate pass over dy runs here.
     ``fold_act``: the caller guarantees that y's only consumer is another GEMM op (Linear / conv): that op's dgrad epilogue
-    multiplies by act'(y) and emits the column sums, so neither the act-bwd nor the bias-gradient pass runs (bf16 mode)."""
+    multiplies by act'(y) and emits the column sums, so neither the act-bwd nor the bias-gradient pass runs (bf16 mode).
+    ``gemm_writers_only``: the caller guarantees that every writer of d(y) is a GEMM that emits column sums (the projections
+    consumed by attention_core): the bias gradient is accumulated in place by those GEMMs."""
     W = ctx.w(wname)
     if W.dim() == 3:                       # 1x1 Conv1d weight (cout, cin, 1)
         W = W.view(W.shape[0], W.shape[1])
@@ -619,6 +628,8 @@ def linear(ctx: Ctx, x: Var, wname: str, bname: Optional[str], act=L.ACT_NONE, s
             y.track_colsum = bool(bname) and not bias_grad_external and (act == L.ACT_NONE or fold_act)
             if fold_act and act != L.ACT_NONE and zero_rows == (0, 0):
                 y.fold = (slope, None, 1.0, 0)
+            if y.track_colsum and (y.fold is not None or (gemm_writers_only and act == L.ACT_NONE)):
+                y.colsum_direct = lambda: ctx.pgrad(bname)[r0:r1]
     if ctx.record:
         def bwd():
             if grad_from is not None:          # `out` is a column slice of a wider buffer owned by grad_from[0]
@@ -629,6 +640,8 @@ def linear(ctx: Ctx, x: Var, wname: str, bname: Optional[str], act=L.ACT_NONE, s
             if dy is None:
                 return
             need_colsum = bool(bname) and not bias_grad_external
+            if need_colsum and y.colsum_direct is not None and (act == L.ACT_NONE or y.folded):
+                need_colsum = False            # the GEMMs that wrote dy added their column sums to the bias gradient already
             if need_colsum and y.track_colsum and y.colsum_ok and y.colsum_tmp is not None and (act == L.ACT_NONE or y.folded):
                 # every writer of dy was a GEMM that already summed its columns: add the (N,) accumulator to the bias gradient
                 L.check(ctx.lib.jmt_axpy(_ptr(y.colsum_tmp), _ptr(ctx.pgrad(bname)[r0:r1]), 1.0, N, L.F32, _stream()), "jmt_axpy")
@@ -945,6 +958,11 @@ def attention_core(ctx: Ctx, q: Var, qcol: int, k: Var, kcol: int, v: Var, vcol:
     return out
 
 
+def _attn_bwd_by_gemms() -> bool:
+    """attention_core's backward writes dQ / dK / dV with plain GEMMs (always, except in the experimental "full" chain mode)"""
+    return FUSED_ATTENTION_BWD in ("ds", False, None)
+
+
 def attention_small(ctx: Ctx, qkv: Var, Lseq: int, N: int, E: int, heads: int) -> Var:
     """Self-attention over tiny sequences (L <= 8): qkv is (L*N, 3E) with row = l*N + n."""
     scale = 1.0 / math.sqrt(E // heads)
@@ -974,7 +992,7 @@ def mha_self(ctx: Ctx, x: Var, prefix: str, heads: int, geom: Optional[AttnGeom]
              out_bias_grad_external: bool = False) -> Var:
     """nn.MultiheadAttention(x, x, x): packed QKV projection (one N=3E GEMM), attention, out-proj."""
     E = x.data.shape[1]
-    qkv = linear(ctx, x, prefix + "in_proj_weight", prefix + "in_proj_bias")
+    qkv = linear(ctx, x, prefix + "in_proj_weight", prefix + "in_proj_bias", gemm_writers_only=small is None and _attn_bwd_by_gemms())
     if small is not None:
         o = attention_small(ctx, qkv, small[0], small[1], E, heads)
     else:
@@ -990,9 +1008,9 @@ def mha_cross(ctx: Ctx, xq: Var, xkv: Var, prefix: str, heads: int, gq: AttnGeom
     key = (prefix, id(xq))
     q = ctx.qcache.get(key)
     if q is None:
-        q = linear(ctx, xq, prefix + "in_proj_weight", prefix + "in_proj_bias", w_rows=(0, E))
+        q = linear(ctx, xq, prefix + "in_proj_weight", prefix + "in_proj_bias", w_rows=(0, E), gemm_writers_only=_attn_bwd_by_gemms())
         ctx.qcache[key] = q
-    kv = linear(ctx, xkv, prefix + "in_proj_weight", prefix + "in_proj_bias", w_rows=(E, 3 * E))
+    kv = linear(ctx, xkv, prefix + "in_proj_weight", prefix + "in_proj_bias", w_rows=(E, 3 * E), gemm_writers_only=_attn_bwd_by_gemms())
     o = attention_core(ctx, q, 0, kv, 0, kv, E, E, heads, gq, gk)
     return linear(ctx, o, prefix + "out_proj.weight", prefix + "out_proj.bias", out=out, grad_from=grad_from)
 
@@ -1246,6 +1264,22 @@ def weight_norm_conv_weights(ctx: Ctx, prefix: str, cout: int, cin: int, k: int)
     return w_fwd, w_dg, dw
 
 
+def channel_dropout_masks(ctx: Ctx, N: int, couts: Sequence[int], p: float) -> List[Optional[torch.Tensor]]:
+    """Philox keep-masks (N, cout_i) of every Dropout2d of a TemporalConvNet in ONE launch (eight ~3 us launches before);
+    None entries when dropout is off."""
+    if p <= 0.0 or not ctx.training:
+        return [None] * len(couts)
+    sizes = [(N * c + 15) // 16 * 16 for c in couts]          # 16-byte aligned slices
+    buf = ctx.empty((sum(sizes),), torch.uint8)
+    L.check(ctx.lib.jmt_dropout_mask(_ptr(buf), buf.numel(), p, ctx.seed, ctx.rng_offset, _ptr(ctx.rng_state), _stream()), "jmt_dropout_mask")
+    ctx.rng_offset += (buf.numel() + 3) // 4
+    out, o = [], 0
+    for c, sz in zip(couts, sizes):
+        out.append(buf[o:o + N * c])
+        o += sz
+    return out
+
+
 def weight_norm_all(ctx: Ctx, convs: Sequence[Tuple[str, int, int]], k: int):
     """weight_norm of several convolutions (prefix, cout, cin) -- every conv of a TemporalConvNet -- in ONE launch per layout
     (jmt_weight_norm_fwd_batched; the per-conv kernels are latency-bound, 8 x 2 x ~10 us per pass).  Returns
@@ -1288,7 +1322,8 @@ def weight_norm_bwd_group(ctx: Ctx, weights: dict, convs: Sequence[Tuple[str, in
 
 
 def causal_conv(ctx: Ctx, x: Var, prefix: str, N: int, Ls: int, cin: int, cout: int, k: int, dil: int, act: int,
-                drop_p: float = 0.0, pad: int = 0, weights: Optional[tuple] = None, fold_act: bool = False) -> Var:
+                drop_p: float = 0.0, pad: int = 0, weights: Optional[tuple] = None, fold_act: bool = False,
+                keep_mask: Optional[torch.Tensor] = None) -> Var:
     """weight-normed dilated causal Conv1d + Chomp1d + LeakyReLU + Dropout2d (temporal_convolutional_model.py:24-29)
     as an implicit GEMM on the flat padded channels-last layout (see above): taps are K blocks whose A rows are
     shifted by -(k-1-j)*dil; the zero padding rows in front of every sequence supply the causal zeros.
@@ -1306,9 +1341,12 @@ def causal_conv(ctx: Ctx, x: Var, prefix: str, N: int, Ls: int, cin: int, cout: 
     bias = ctx.p(prefix + "bias")
     mask, mscale = None, 1.0
     if drop_p > 0.0 and ctx.training:
-        mask = ctx.empty((N * cout,), torch.uint8)
-        L.check(ctx.lib.jmt_dropout_mask(_ptr(mask), N * cout, drop_p, ctx.seed, ctx.rng_offset, _ptr(ctx.rng_state), _stream()), "jmt_dropout_mask")
-        ctx.rng_offset += (N * cout + 3) // 4
+        if keep_mask is not None:          # drawn together with the masks of the other convs (channel_dropout_masks)
+            mask = keep_mask
+        else:
+            mask = ctx.empty((N * cout,), torch.uint8)
+            L.check(ctx.lib.jmt_dropout_mask(_ptr(mask), N * cout, drop_p, ctx.seed, ctx.rng_offset, _ptr(ctx.rng_state), _stream()), "jmt_dropout_mask")
+            ctx.rng_offset += (N * cout + 3) // 4
         mscale = 1.0 / (1.0 - drop_p)
     # algorithmic FLOPs = useful taps only: tap j touches L - (k-1-j)*dil positions of each sequence
     tap_flops = [2.0 * N * max(0, Ls - (k - 1 - j) * dil) * cout * cin for j in range(k)]
@@ -1327,6 +1365,7 @@ def causal_conv(ctx: Ctx, x: Var, prefix: str, N: int, Ls: int, cin: int, cout: 
         # columns (this conv's bias gradient), so no pass over d(y) runs here
         out.fold = (LEAKY_SLOPE, mask, mscale, Lp if mask is not None else 0)
         out.track_colsum = True
+        out.colsum_direct = lambda: ctx.pgrad(prefix + "bias")
     if ctx.record:
         def bwd():
             dy = out.grad
@@ -1336,10 +1375,7 @@ def causal_conv(ctx: Ctx, x: Var, prefix: str, N: int, Ls: int, cin: int, cout: 
             # where a channel was dropped y = 0 and the masked dy is 0, so act'(y) of the post-dropout y is exact;
             # padding rows of dy are zero (every producer keeps them so) and stay zero
             if out.folded:
-                if out.colsum_ok and out.colsum_tmp is not None:
-                    L.check(ctx.lib.jmt_axpy(_ptr(out.colsum_tmp), _ptr(ctx.pgrad(prefix + "bias")), 1.0, cout, L.F32, _stream()), "jmt_axpy")
-                else:
-                    L.check(ctx.lib.jmt_colsum(_ptr(dy), _DT[dy.dtype], cout, R, cout, _ptr(ctx.pgrad(prefix + "bias")), _stream()), "jmt_colsum")
+                pass                   # dy is d(pre-activation) and its column sums are in the bias gradient (consumer's dgrad epilogue)
             elif act != L.ACT_NONE or mask is not None:
                 dy = _act_bwd(ctx, out, dy, LEAKY_SLOPE if act != L.ACT_NONE else 1.0, colsum=ctx.pgrad(prefix + "bias"),
                               mask=mask, mask_rows=Lp, mask_scale=mscale)

@@ -625,6 +625,10 @@ def _tcn_graph(ctx, h, prefix, specs, N, Ls, pad):
         convs = [(f"{prefix}network.{i}.conv{c}.", cout, cin if c == 1 else cout)
                  for i, (cin, cout, _k, _d, _p, _ds) in enumerate(specs) for c in (1, 2)]
         wn = E.weight_norm_all(ctx, convs, next(iter(ks)))
+    ps = {p for (_ci, _co, _k, _d, p, _ds) in specs}
+    masks = None
+    if len(ps) == 1:                               # every Dropout2d keep-mask of the net in one launch
+        masks = E.channel_dropout_masks(ctx, N, [cout for (_ci, cout, _k, _d, _p, _ds) in specs for _ in (1, 2)], next(iter(ps)))
     for i, (cin, cout, k, d, p, has_ds) in enumerate(specs):
         pre = f"{prefix}network.{i}."
         ctx.sync_point(pre)          # reached in backward once this level's dW / weight-norm gradients are final
@@ -632,8 +636,10 @@ def _tcn_graph(ctx, h, prefix, specs, N, Ls, pad):
         if wn is not None:
             E.weight_norm_bwd_group(ctx, wn, [(pre + "conv1.", cout, cin), (pre + "conv2.", cout, cout)], k)
             w1, w2 = wn[pre + "conv1."], wn[pre + "conv2."]
-        y = E.causal_conv(ctx, h, pre + "conv1.", N, Ls, cin, cout, k, d, L.ACT_LEAKY, drop_p=p, pad=pad, weights=w1, fold_act=True)
-        y = E.causal_conv(ctx, y, pre + "conv2.", N, Ls, cout, cout, k, d, L.ACT_LEAKY, drop_p=p, pad=pad, weights=w2)
+        m1, m2 = (masks[2 * i], masks[2 * i + 1]) if masks is not None else (None, None)
+        y = E.causal_conv(ctx, h, pre + "conv1.", N, Ls, cin, cout, k, d, L.ACT_LEAKY, drop_p=p, pad=pad, weights=w1, fold_act=True,
+                          keep_mask=m1)
+        y = E.causal_conv(ctx, y, pre + "conv2.", N, Ls, cout, cout, k, d, L.ACT_LEAKY, drop_p=p, pad=pad, weights=w2, keep_mask=m2)
         res = _conv1x1(ctx, h, pre + "downsample.", (Ls + pad, pad)) if has_ds else h
         h = E.add_act(ctx, y, res, L.ACT_LEAKY, E.LEAKY_SLOPE)
     return h
