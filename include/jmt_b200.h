@@ -162,7 +162,8 @@ typedef struct {
   const void* a1; const void* b1; const void* b2;   /* bf16 */
   const void* p_in;                                  /* mode 1: saved probabilities; else NULL */
   const void* o_in;                                  /* mode 1: saved forward output O, same geometry as a1 (= dO); else NULL */
-  const float* delta_in;                             /* mode 1: precomputed delta (NB, heads, Lq) fp32 (jmt_rowdot_bf16), or NULL: from o_in */
+  const float* delta_in;                             /* mode 1: precomputed delta (NB, heads, Lq) fp32 (jmt_rowdot_bf16), or NULL: from o_in;
+                                                        both NULL: delta = rowsum(P o dP) inside the kernel (no separate pass over dO / O) */
   void* x;                                           /* out: P (mode 0) / dS (mode 1), bf16; mode 0 with D: may be NULL (forward-only callers: the
                                                         probabilities are then never written to memory) */
   void* d;                                           /* out: O (mode 0) / dQ (mode 1), bf16; NULL: stop after X (P / dS) -- GEMM2 is then a plain jmt_gemm_bf16 */

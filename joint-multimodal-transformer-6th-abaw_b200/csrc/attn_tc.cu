@@ -43,6 +43,8 @@ struct AtParams {
   const __nv_bfloat16* o_in;
   int64_t do_ld, do_hs, do_bs;
   const float* delta_in;       // mode 1: precomputed delta (NB, heads, Lq) fp32, or NULL (computed in-kernel from dO, O)
+  int delta_pdp;               // mode 1 without delta_in / O: delta = rowsum(P o dP) from the staged P and the dP accumulator (one more
+                               // pass over TMEM / shared memory instead of a separate rowdot kernel over dO and O)
   int skip2;                   // mode 1: stop after X = dS (no GEMM2 / dQ): dQ, dK, dV are plain GEMMs on the saved dS
   int64_t x_ld;
   int store_mode;
@@ -139,6 +141,21 @@ __device__ __forceinline__ void row_bwd_chunk(const AtParams& p, const uint32_t 
   else row_bwd_chunk_t<false>(p, r, nvalid, delta, xbase, piece0, sw);
 }
 
+// backward, delta pass on one 32-key chunk: acc += P * dP with P read from the X tile (staged by TMA), four independent partial sums
+__device__ __forceinline__ void row_bwd_dot(const uint32_t (&r)[32], int nvalid, uint32_t xbase, uint32_t piece0, uint32_t sw, float (&acc)[4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint4 pv = ld_shared_v4(xbase + (((piece0 + (uint32_t)i) ^ sw) << 4));
+    const uint32_t w[4] = {pv.x, pv.y, pv.z, pv.w};
+#pragma unroll
+    for (int h = 0; h < 8; ++h) {
+      const float pf = (h & 1) ? bf16hi(w[h >> 1]) : bf16lo(w[h >> 1]);
+      const float dp = i * 8 + h < nvalid ? __uint_as_float(r[i * 8 + h]) : 0.f;
+      acc[h & 3] = fmaf(pf, dp, acc[h & 3]);
+    }
+  }
+}
+
 // The row-wise algebra between the two GEMMs for one thread (= one query row, every other 32-key chunk):
 //   MODE 0: X = softmax(scale * T1): two streaming passes over T1 (row max, then exp2 + row sum; each with one exchange
 //           with the warp that owns the other chunks of the row), then the bf16 values are normalised in shared memory.
@@ -170,6 +187,25 @@ __device__ __forceinline__ void row_op(const AtParams& p, const RowCtx& rc, floa
     if (half < nch) tc_ld32_issue(rc.tb + half * 32, ra);        // pass 2's first chunk is in flight across the barrier
     asm volatile("bar.sync 1, %0;" ::"n"(32 * kAtRowWarps) : "memory");
     shift = fmaxf(red[row], red[128 + row]) * p.c_exp;
+  } else if (p.delta_pdp) {
+    // delta_i = sum_j P_ij dP_ij: one pass over this warp's chunks of the dP accumulator and the staged P, then the exchange with
+    // the warp that owns the other chunks of the row (same structure as the forward's row-max pass)
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    if (half < nch) tc_ld32_issue(rc.tb + half * 32, ra);
+    for (int ch = half; ch < nch; ch += 4) {
+      tc_wait_ld();
+      if (ch + 2 < nch) tc_ld32_issue(rc.tb + (ch + 2) * 32, rb);
+      row_bwd_dot(ra, p.S - ch * 32, rc.xrow + (ch >> 1) * 16384, (uint32_t)((ch & 1) * 4), rc.sw, acc);
+      if (ch + 2 >= nch) break;
+      tc_wait_ld();
+      if (ch + 4 < nch) tc_ld32_issue(rc.tb + (ch + 4) * 32, ra);
+      row_bwd_dot(rb, p.S - (ch + 2) * 32, rc.xrow + ((ch + 2) >> 1) * 16384, (uint32_t)((ch & 1) * 4), rc.sw, acc);
+    }
+    red[half * 128 + row] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+    __syncwarp();
+    if (half < nch) tc_ld32_issue(rc.tb + half * 32, ra);        // the dS pass's first chunk is in flight across the barrier
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * kAtRowWarps) : "memory");
+    shift = red[row] + red[128 + row];
   } else {
     shift = delta_buf[row];
     if (half < nch) tc_ld32_issue(rc.tb + half * 32, ra);
@@ -418,7 +454,9 @@ attn_chain_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
         }
         // delta of this tile while GEMM1 runs.  (Measured: ~9 k cycles per tile of latency-bound global loads that GEMM1
         // only partly hides; computing it for the next tile under GEMM2 instead put 30 k cycles on the critical path.)
-        if (p.delta_in != nullptr) {              // precomputed (jmt_rowdot): one coalesced load per row
+        if (p.delta_pdp) {
+          // (delta comes out of the row pass itself)
+        } else if (p.delta_in != nullptr) {       // precomputed (jmt_rowdot): one coalesced load per row
           if (ew == 0) {
             const float* dl = p.delta_in + ((int64_t)c.b * p.heads + c.head) * p.Lq;
             for (int r = lane; r < kBlockM; r += 32) red[r] = c.q0 + r < p.Lq ? __ldg(dl + c.q0 + r) : 0.f;
@@ -552,6 +590,7 @@ static int at_plan(const jmt_attn_desc* g, AtParams* p, int* smem_bytes) {
   p->do_in = (const __nv_bfloat16*)g->a1; p->o_in = (const __nv_bfloat16*)g->o_in;
   p->do_ld = g->a1_ld; p->do_hs = g->a1_hs; p->do_bs = g->a1_bs;
   p->delta_in = g->delta_in; p->skip2 = g->d == nullptr ? 1 : 0;
+  p->delta_pdp = (g->mode == 1 && g->delta_in == nullptr && g->o_in == nullptr) ? 1 : 0;
   p->x_ld = g->x_ld;
   p->store_mode = g->store_mode;
   p->store_x = g->x != nullptr ? 1 : 0;
@@ -681,7 +720,7 @@ extern "C" int jmt_attn_chain_bf16(const jmt_attn_desc* g, void* stream) {
   JMT_REQUIRE(g->x || (g->mode == 0 && g->d), "jmt_attn_chain_bf16: X may only be omitted by a forward call that produces D");
   JMT_REQUIRE(g->mode == 0 || g->mode == 1, "jmt_attn_chain_bf16: bad mode");
   JMT_REQUIRE(g->d == nullptr || g->b2, "jmt_attn_chain_bf16: D needs B2");
-  JMT_REQUIRE(g->mode == 0 || (g->p_in && (g->delta_in || g->o_in)), "jmt_attn_chain_bf16: mode 1 needs the saved probabilities and delta (or O)");
+  JMT_REQUIRE(g->mode == 0 || g->p_in, "jmt_attn_chain_bf16: mode 1 needs the saved probabilities");
   JMT_REQUIRE(g->store_mode == JMT_STORE || g->store_mode == JMT_ACCUMULATE, "jmt_attn_chain_bf16: bad store_mode");
   AtParams p; int smem = 0;
   if (!at_plan(g, &p, &smem) || (g->x != nullptr && (g->x_ld % 8 != 0 || g->x_ld < g->S))) {

@@ -786,6 +786,7 @@ def _proj_grad_slice(ctx: Ctx, v: Var, c0: int, c1: int, capable: bool = False) 
 FUSED_ATTENTION = True      # bf16 mode: True = QK^T -> softmax -> PV in one kernel when the geometry is supported; "p" = QK^T +
                             # softmax fused, PV a plain GEMM (measured 1.4 % slower per step); False = GEMM + softmax kernels
 EPI_EXT = os.environ.get("JMT_EPI_EXT", "1") != "0"   # fold act' / emit bias-gradient column sums in the backward GEMM epilogues
+ATTN_DELTA_IN_KERNEL = os.environ.get("JMT_ATTN_DELTA", "1") != "0"   # softmax-backward delta = rowsum(P o dP) inside the dS kernel
 LONG_S_CHUNKED = True       # forward-only attention beyond the fused kernel's key limit: chunked fused kernel + log-sum-exp merge
 LONG_S_CHUNK_MIN_BYTES = 2 << 30   # ... once the fp32 score tensor of the composed path would exceed this (measured: NONE eval at
                                    # B = 1024, 1.26 GB of scores, 7.4 ms composed vs 9.1 ms chunked; B = 4096, 20 GB: chunked only)
@@ -913,9 +914,11 @@ def attention_core(ctx: Ctx, q: Var, qcol: int, k: Var, kcol: int, v: Var, vcol:
             if fused and FUSED_ATTENTION_BWD == "ds":
                 # delta = rowsum(dO o O); dP = dO V^T -> dS = scale * P o (dP - delta) in one kernel (fp32 dP never leaves
                 # the SM); dQ = dS K, dK = dS^T Q, dV = P^T dO stay plain GEMMs (the scale is already in dS)
-                delta = ctx.empty((NB, heads, Lq), torch.float32)
-                L.check(ctx.lib.jmt_rowdot_bf16(_ptr(do), _ptr(o), o_geo[0], o_geo[1], o_geo[2], NB, heads, Lq, dh, _ptr(delta),
-                                                _stream()), "jmt_rowdot_bf16")
+                delta = None
+                if not ATTN_DELTA_IN_KERNEL:        # delta = rowsum(dO o O) by a separate pass (round-1 path)
+                    delta = ctx.empty((NB, heads, Lq), torch.float32)
+                    L.check(ctx.lib.jmt_rowdot_bf16(_ptr(do), _ptr(o), o_geo[0], o_geo[1], o_geo[2], NB, heads, Lq, dh, _ptr(delta),
+                                                    _stream()), "jmt_rowdot_bf16")
                 _attn_chain(ctx, 1, do, o_geo, vd, v_geo, None, None, probs, ds, None, None, Lq, S, dh, heads, NB, s_ld, scale,
                             L.STORE, delta_in=delta)
                 gemm(ctx, ds, kd, gq_s, M=Lq, N=dh, K=S, a_rows=Lq, b_major=L.MAJOR_MN, b_rows=S,
