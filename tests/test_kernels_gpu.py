@@ -304,7 +304,7 @@ def test_gemm_wgrad_taps_batched(precision, geom):
     assert (dw.cpu().double() - want).abs().max() < tol * want.abs().max()
 
 
-@pytest.mark.parametrize("case", ["wide_fold_colsum", "narrow_colsum_acc", "heads_colsum", "ragged_fold"])
+@pytest.mark.parametrize("case", ["wide_fold_colsum", "narrow_colsum_acc", "heads_colsum", "ragged_fold", "n1024_colsum_global_atomics"])
 def test_gemm_backward_epilogue_extensions(case):
     """jmt_gemm_desc.epi_aux / d_colsum: the dgrad epilogue multiplies by act'(aux) and adds the column sums of what it stores
     (the producer's bias gradient) -- against the plain GEMM followed by the separate passes."""
@@ -328,7 +328,8 @@ def test_gemm_backward_epilogue_extensions(case):
         return
     M, N, K, store, slope, use_aux = {"wide_fold_colsum": (256 * 78, 512, 512, L.STORE, 0.0, True),
                                       "narrow_colsum_acc": (1000, 384, 192, L.ACCUMULATE, 0.0, False),
-                                      "ragged_fold": (333, 200, 136, L.STORE, 0.01, True)}[case]
+                                      "ragged_fold": (333, 200, 136, L.STORE, 0.01, True),
+                                      "n1024_colsum_global_atomics": (2100, 1024, 256, L.STORE, 0.0, True)}[case]
     a = (torch.randn(M, K) * 0.5).to(torch.bfloat16).to(dev)
     w = (torch.randn(K, N) * 0.5).to(torch.bfloat16).to(dev)               # B MN-major (dgrad of a Linear)
     aux = torch.randn(M, N).to(torch.bfloat16).to(dev)
