@@ -323,7 +323,7 @@ class Ctx:
     def colsum_target(self, v: Var, c0: int = 0, c1: Optional[int] = None) -> Optional[torch.Tensor]:
         """fp32 accumulator slice for the column sums of a gradient contribution to v[:, c0:c1] written by a capable GEMM
         (None: not tracked).  Callers must have obtained the gradient buffer with capable=True."""
-        if not (v.track_colsum and self.ext_on()):
+        if not (v.track_colsum and self.ext_on() and EPI_COLSUM):
             return None
         c1 = c1 if c1 is not None else v.data.shape[1]
         if v.colsum_direct is not None:
@@ -628,7 +628,7 @@ def linear(ctx: Ctx, x: Var, wname: str, bname: Optional[str], act=L.ACT_NONE, s
             y.track_colsum = bool(bname) and not bias_grad_external and (act == L.ACT_NONE or fold_act)
             if fold_act and act != L.ACT_NONE and zero_rows == (0, 0):
                 y.fold = (slope, None, 1.0, 0)
-            if y.track_colsum and (y.fold is not None or (gemm_writers_only and act == L.ACT_NONE)):
+            if EPI_COLSUM and y.track_colsum and (y.fold is not None or (gemm_writers_only and act == L.ACT_NONE)):
                 y.colsum_direct = lambda: ctx.pgrad(bname)[r0:r1]
     if ctx.record:
         def bwd():
@@ -785,7 +785,15 @@ def _proj_grad_slice(ctx: Ctx, v: Var, c0: int, c1: int, capable: bool = False) 
 
 FUSED_ATTENTION = True      # bf16 mode: True = QK^T -> softmax -> PV in one kernel when the geometry is supported; "p" = QK^T +
                             # softmax fused, PV a plain GEMM (measured 1.4 % slower per step); False = GEMM + softmax kernels
-EPI_EXT = os.environ.get("JMT_EPI_EXT", "1") != "0"   # fold act' / emit bias-gradient column sums in the backward GEMM epilogues
+# Backward GEMM epilogue extensions (jmt_gemm_desc.epi_aux / d_colsum), JMT_EPI_EXT = 0 | 1 (default) | 2:
+#   1: the activation gradient of FFN-ReLU / TCN conv1-LeakyReLU(+channel mask) is folded into the consumer's dgrad epilogue
+#      (the act-bwd pass, 3 passes over the gradient, shrinks to the bias-gradient column sum, 1 pass);
+#   2: additionally the GEMMs that write a gradient emit its column sums themselves (no colsum kernels).  Measured on B200
+#      (profiles/gemm_table_r2q_*.txt): the butterfly transpose-reduce makes the attention-backward GEMMs 15-19 % slower, which
+#      costs what the 0.33 ms of colsum kernels cost -- kept as an option, not the default.
+_EPI_MODE = int(os.environ.get("JMT_EPI_EXT", "1"))
+EPI_EXT = _EPI_MODE >= 1
+EPI_COLSUM = _EPI_MODE >= 2
 ATTN_DELTA_IN_KERNEL = os.environ.get("JMT_ATTN_DELTA", "1") != "0"   # softmax-backward delta = rowsum(P o dP) inside the dS kernel
 LONG_S_CHUNKED = True       # forward-only attention beyond the fused kernel's key limit: chunked fused kernel + log-sum-exp merge
 LONG_S_CHUNK_MIN_BYTES = 2 << 30   # ... once the fp32 score tensor of the composed path would exceed this (measured: NONE eval at
@@ -1368,7 +1376,8 @@ def causal_conv(ctx: Ctx, x: Var, prefix: str, N: int, Ls: int, cin: int, cout: 
         # columns (this conv's bias gradient), so no pass over d(y) runs here
         out.fold = (LEAKY_SLOPE, mask, mscale, Lp if mask is not None else 0)
         out.track_colsum = True
-        out.colsum_direct = lambda: ctx.pgrad(prefix + "bias")
+        if EPI_COLSUM:
+            out.colsum_direct = lambda: ctx.pgrad(prefix + "bias")
     if ctx.record:
         def bwd():
             dy = out.grad
@@ -1378,7 +1387,9 @@ def causal_conv(ctx: Ctx, x: Var, prefix: str, N: int, Ls: int, cin: int, cout: 
             # where a channel was dropped y = 0 and the masked dy is 0, so act'(y) of the post-dropout y is exact;
             # padding rows of dy are zero (every producer keeps them so) and stay zero
             if out.folded:
-                pass                   # dy is d(pre-activation) and its column sums are in the bias gradient (consumer's dgrad epilogue)
+                # dy is d(pre-activation) already (consumer's dgrad epilogue); its column sums = the bias gradient
+                if out.colsum_direct is None:
+                    L.check(ctx.lib.jmt_colsum(_ptr(dy), _DT[dy.dtype], cout, R, cout, _ptr(ctx.pgrad(prefix + "bias")), _stream()), "jmt_colsum")
             elif act != L.ACT_NONE or mask is not None:
                 dy = _act_bwd(ctx, out, dy, LEAKY_SLOPE if act != L.ACT_NONE else 1.0, colsum=ctx.pgrad(prefix + "bias"),
                               mask=mask, mask_rows=Lp, mask_scale=mscale)

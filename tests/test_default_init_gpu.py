@@ -243,6 +243,16 @@ PIPE_BOUNDS = {
 }
 
 
+@pytest.mark.parametrize("mode", ["gemm_colsum", "no_ext"])
+def test_pipeline_b4_t300_backward_epilogue_modes(mode, golden_meta, golden_dir, monkeypatch):
+    """The non-default backward-epilogue modes of the bf16 engine (JMT_EPI_EXT = 2: the GEMMs that write a gradient also emit
+    its column sums = the bias gradients; 0: no epilogue extensions at all) against the same reference gradients and bounds."""
+    from jmt_b200 import engine as E
+    monkeypatch.setattr(E, "EPI_EXT", mode != "no_ext")
+    monkeypatch.setattr(E, "EPI_COLSUM", mode == "gemm_colsum")
+    test_pipeline_b4_t300_default_init("bf16", golden_meta, golden_dir)
+
+
 @pytest.mark.parametrize("precision", PRECISIONS)
 def test_pipeline_b4_t300_default_init(precision, golden_meta, golden_dir):
     """The benchmarked pipeline (BASELINE.json configs[1]) at B = 4, T = 300 through jmt_b200.JMTPipeline -- TCN on the flat
