@@ -357,13 +357,37 @@ struct ExtRow {
 };
 
 // 32 accumulator columns [cb, cb + 32) of this thread's row: r -> x (math), fold, pack into pk[16], column sums
-template <bool MASK>
+template <bool MASK, bool CSUM>
 __device__ __forceinline__ void ext_half(const TcParams& p, const EpiCtx& e, const ExtRow& xr, const uint32_t (&r)[32], const uint32_t (&aw)[16],
                                          bool ax_vec, int cb, uint32_t (&pk)[16]) {
-  float x[32];
   const float* bias = e.bias + cb;
   const bool has_bias = p.bias != nullptr;        // (without a bias the bias-tile area may hold the column-sum accumulators)
   const uint32_t fbits = MASK ? e.fwords[cb >> 5] : 0u;
+  if constexpr (!CSUM) {
+    // fold only: stream pairs of columns straight from the accumulator registers into the packed output (no x[32] array)
+    const bool fold_vec = xr.aux_row != nullptr && xr.row_valid && ax_vec;
+    const bool fold_el = xr.aux_row != nullptr && xr.row_valid && !ax_vec;
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) {
+      float x0 = has_bias ? fmaf(p.alpha, __uint_as_float(r[j]), bias[j]) : p.alpha * __uint_as_float(r[j]);
+      float x1 = has_bias ? fmaf(p.alpha, __uint_as_float(r[j + 1]), bias[j + 1]) : p.alpha * __uint_as_float(r[j + 1]);
+      if constexpr (MASK) {
+        x0 = (fbits >> j) & 1u ? x0 * p.colmask_scale : 0.f;
+        x1 = (fbits >> (j + 1)) & 1u ? x1 * p.colmask_scale : 0.f;
+      }
+      if (fold_vec) {
+        const float y0 = __uint_as_float(aw[j >> 1] << 16), y1 = __uint_as_float(aw[j >> 1] & 0xFFFF0000u);
+        x0 = y0 > 0.f ? x0 : x0 * p.aux_slope;
+        x1 = y1 > 0.f ? x1 : x1 * p.aux_slope;
+      } else if (fold_el) {
+        if (e.n0 + cb + j < p.N) { const float y = __bfloat162float(xr.aux_row[e.n0 + cb + j]); x0 = y > 0.f ? x0 : x0 * p.aux_slope; }
+        if (e.n0 + cb + j + 1 < p.N) { const float y = __bfloat162float(xr.aux_row[e.n0 + cb + j + 1]); x1 = y > 0.f ? x1 : x1 * p.aux_slope; }
+      }
+      pk[j >> 1] = xr.zero_row ? 0u : pack_bf16(x0, x1);
+    }
+    return;
+  }
+  float x[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
     float v = has_bias ? fmaf(p.alpha, __uint_as_float(r[j]), bias[j]) : p.alpha * __uint_as_float(r[j]);
@@ -393,13 +417,26 @@ __device__ __forceinline__ void ext_half(const TcParams& p, const EpiCtx& e, con
   }
 #pragma unroll
   for (int j = 0; j < 32; j += 2) pk[j >> 1] = pack_bf16(x[j], x[j + 1]);
-  if (xr.csum != nullptr) {
-    const float cs = warp_colsum32(x, e.lane);
-    if (e.n0 + cb + e.lane < p.N && cs != 0.f) atomicAdd(xr.csum + e.n0 + cb + e.lane, cs);
+  if constexpr (CSUM) {
+    if (xr.csum != nullptr) {
+      const float cs = warp_colsum32(x, e.lane);
+      if (e.n0 + cb + e.lane < p.N && cs != 0.f) atomicAdd(xr.csum + e.n0 + cb + e.lane, cs);
+    }
   }
 }
 
-template <bool MASK, int kCta>
+// 16 packed bf16 pairs (32 columns) of this thread's aux row, straight from global memory; returns whether the vector path applied
+__device__ __forceinline__ bool ext_load_aux(const TcParams& p, const EpiCtx& e, const ExtRow& xr, bool aligned, int cb, uint32_t (&ax)[16]) {
+  const bool vec = aligned && xr.row_valid && cb < e.bn && e.n0 + cb + 32 <= p.N;
+  if (vec) {
+    const uint4* ap = reinterpret_cast<const uint4*>(xr.aux_row + e.n0 + cb);
+#pragma unroll
+    for (int q4 = 0; q4 < 4; ++q4) { const uint4 t = __ldg(ap + q4); ax[4 * q4] = t.x; ax[4 * q4 + 1] = t.y; ax[4 * q4 + 2] = t.z; ax[4 * q4 + 3] = t.w; }
+  }
+  return vec;
+}
+
+template <bool MASK, bool CSUM, int kCta>
 __device__ __forceinline__ bool epi_tile_ext(const TcParams& p, const CUtensorMap* tma_d, const EpiCtx& e) {
   const int lane = e.lane;
   bool released = false;
@@ -412,48 +449,35 @@ __device__ __forceinline__ bool epi_tile_ext(const TcParams& p, const CUtensorMa
   xr.aux_row = p.aux != nullptr ? p.aux + row_off : nullptr;
   xr.csum = p.colsum == nullptr ? nullptr : (p.csum_smem ? e.csum_sh : p.colsum) + (int64_t)e.b0 * p.colsum_bs0;
   const bool aux_aligned = xr.aux_row != nullptr && ((reinterpret_cast<uintptr_t>(xr.aux_row) | (uintptr_t)(e.n0 * 2)) & 15) == 0;
+  // The aux loads (global memory, ~1 us) are software-pipelined one 32-column half ahead of their use: the epilogue of a wide
+  // K = 512 tile is exposed (one accumulator stage), un-hidden latency there showed up 1:1 in the launch time.
+  uint32_t ax0[16] = {}, ax1[16] = {};
+  bool v0 = ext_load_aux(p, e, xr, aux_aligned, e.part * 64, ax0), v1 = false;
   for (int c0 = e.part * 64; c0 < e.bn; c0 += 64 * e.parts) {
     if (e.n0 + c0 >= p.N) break;
     const bool second = c0 + 32 < e.bn;
+    const int c_next = c0 + 64 * e.parts;
     uint32_t r[32], pk[16];
-    uint32_t ax[16] = {};
     tc_ld32_issue(e.tbase + c0, r);
-    // ---- columns [c0, c0 + 32)
-    bool ax_vec = aux_aligned && xr.row_valid && e.n0 + c0 + 32 <= p.N;
-    if (ax_vec) {
-      const uint4* ap = reinterpret_cast<const uint4*>(xr.aux_row + e.n0 + c0);
-#pragma unroll
-      for (int q4 = 0; q4 < 4; ++q4) { const uint4 t = __ldg(ap + q4); ax[4 * q4] = t.x; ax[4 * q4 + 1] = t.y; ax[4 * q4 + 2] = t.z; ax[4 * q4 + 3] = t.w; }
-    }
+    if (second) v1 = ext_load_aux(p, e, xr, aux_aligned, c0 + 32, ax1);
     tc_wait_ld();
-    {
-      uint32_t r0[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) r0[j] = r[j];
-      if (second) tc_ld32_issue(e.tbase + c0 + 32, r);      // the second half's TMEM load is in flight under the math
-      ext_half<MASK>(p, e, xr, r0, ax, ax_vec, c0, pk);
-    }
+    // ---- columns [c0, c0 + 32)
+    uint32_t r2[32];
+    if (second) tc_ld32_issue(e.tbase + c0 + 32, r2);       // the second half's TMEM load is in flight under the math
+    ext_half<MASK, CSUM>(p, e, xr, r, ax0, v0, c0, pk);
+    if (c_next < e.bn && e.n0 + c_next < p.N) v0 = ext_load_aux(p, e, xr, aux_aligned, c_next, ax0);   // next chunk's first half
     if (lane == 0) bulk_wait_read0();       // previous TMA store has finished reading the staging tile
     __syncwarp();
 #pragma unroll
     for (int ch = 0; ch < 4; ++ch)
       st_shared_v4(e.row_smem + (((uint32_t)ch ^ e.sw) << 4), pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
-    // ---- columns [c0 + 32, c0 + 64)
-    if (second) {
-      ax_vec = aux_aligned && xr.row_valid && e.n0 + c0 + 64 <= p.N;
-      if (ax_vec) {
-        const uint4* ap = reinterpret_cast<const uint4*>(xr.aux_row + e.n0 + c0 + 32);
-#pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) { const uint4 t = __ldg(ap + q4); ax[4 * q4] = t.x; ax[4 * q4 + 1] = t.y; ax[4 * q4 + 2] = t.z; ax[4 * q4 + 3] = t.w; }
-      }
-      tc_wait_ld();
-    }
+    if (second) tc_wait_ld();
     // every TMEM read of this chunk has landed: hand the accumulator (half) back before the remaining math / staging / store
-    const int c_next = c0 + 64 * e.parts;
     if (e.tempty_mid != 0u && c0 < 256 && c_next >= 256) epi_release<kCta>(e.tempty_mid, lane);
     if (c_next >= e.bn || e.n0 + c_next >= p.N) { epi_release<kCta>(e.tempty, lane); released = true; }
+    // ---- columns [c0 + 32, c0 + 64)
     if (second) {
-      ext_half<MASK>(p, e, xr, r, ax, ax_vec, c0 + 32, pk);
+      ext_half<MASK, CSUM>(p, e, xr, r2, ax1, v1, c0 + 32, pk);
     } else {
 #pragma unroll
       for (int j = 0; j < 16; ++j) pk[j] = 0u;
@@ -476,9 +500,9 @@ __device__ __forceinline__ bool epi_tile_ext(const TcParams& p, const CUtensorMa
 // geometry, x = hi + lo (hi = bf16(x), lo = bf16(x - hi), 16 mantissa bits together).  A stage holds the four tiles
 // A_hi | A_lo and B_hi | B_lo, and every k-step issues THREE tcgen05.mma into the same fp32 TMEM accumulator:
 // A_hi B_hi + A_hi B_lo + A_lo B_hi  (the dropped lo x lo term is 2^-16 relative) -- the 1e-3 parity gate on tensor cores.
-// kExt: the extended backward epilogue (epi_tile_ext) -- its own instantiation so that the common kernels keep their register
-// allocation (127 registers, no spills; the extended epilogue needs ~170)
-template <int kCta, bool kMask, int kEpi, bool kX3, bool kExt>
+// kExt: the extended backward epilogue (epi_tile_ext): 0 = none, 1 = activation-gradient fold (epi_aux), 2 = fold and / or column
+// sums (d_colsum) -- own instantiations so that the common kernels keep their register allocation (122-128 registers, no spills)
+template <int kCta, bool kMask, int kEpi, bool kX3, int kExt>
 __global__ void __launch_bounds__(64 + 32 * kEpi, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a_hi, const __grid_constant__ CUtensorMap tma_b_hi,
                const __grid_constant__ CUtensorMap tma_d, const __grid_constant__ CUtensorMap tma_a_lo,
@@ -816,8 +840,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a_hi, const __grid_consta
       ec.prof = eprof;
 #endif
       bool released;
-      if constexpr (kExt) {
-        released = epi_tile_ext<kMask, kCta>(p, &tma_d, ec);
+      if constexpr (kExt != 0) {
+        released = epi_tile_ext<kMask, kExt == 2, kCta>(p, &tma_d, ec);
       } else {
         if (p.act == JMT_ACT_NONE) released = epi_tile<JMT_ACT_NONE, kMask, kCta>(p, &tma_d, ec);
         else if (p.act == JMT_ACT_RELU) released = epi_tile<JMT_ACT_RELU, kMask, kCta>(p, &tma_d, ec);
@@ -830,7 +854,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a_hi, const __grid_consta
       }
       if (ec.tempty_end2 != 0u) epi_release<kCta>(ec.tempty_end2, lane);
     }
-    if (kExt && p.csum_smem) {                     // flush the shared-memory column sums: one global atomic per entry and CTA
+    if (kExt == 2 && p.csum_smem) {                     // flush the shared-memory column sums: one global atomic per entry and CTA
       asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpi) : "memory");
       for (int i = et; i < p.csum_len; i += 32 * kEpi) {
         const float v = bias_ptr[i];
@@ -1070,12 +1094,14 @@ static int gemm_tc_launch(const jmt_gemm_desc* g, const void* a_lo, const void* 
   if (!attr_set[dev & 63].load(std::memory_order_acquire)) {
     cudaError_t e = cudaSuccess;
     auto set_smem = [&e](const void* fn) { if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); };
-    set_smem((const void*)gemm_tc_kernel<1, false, 8, false, false>); set_smem((const void*)gemm_tc_kernel<2, false, 8, false, false>);
-    set_smem((const void*)gemm_tc_kernel<1, true, 8, false, false>); set_smem((const void*)gemm_tc_kernel<2, true, 8, false, false>);
-    set_smem((const void*)gemm_tc_kernel<1, false, 8, true, false>); set_smem((const void*)gemm_tc_kernel<2, false, 8, true, false>);
-    set_smem((const void*)gemm_tc_kernel<1, true, 8, true, false>); set_smem((const void*)gemm_tc_kernel<2, true, 8, true, false>);
-    set_smem((const void*)gemm_tc_kernel<1, false, 8, false, true>); set_smem((const void*)gemm_tc_kernel<2, false, 8, false, true>);
-    set_smem((const void*)gemm_tc_kernel<1, true, 8, false, true>); set_smem((const void*)gemm_tc_kernel<2, true, 8, false, true>);
+    set_smem((const void*)gemm_tc_kernel<1, false, 8, false, 0>); set_smem((const void*)gemm_tc_kernel<2, false, 8, false, 0>);
+    set_smem((const void*)gemm_tc_kernel<1, true, 8, false, 0>); set_smem((const void*)gemm_tc_kernel<2, true, 8, false, 0>);
+    set_smem((const void*)gemm_tc_kernel<1, false, 8, true, 0>); set_smem((const void*)gemm_tc_kernel<2, false, 8, true, 0>);
+    set_smem((const void*)gemm_tc_kernel<1, true, 8, true, 0>); set_smem((const void*)gemm_tc_kernel<2, true, 8, true, 0>);
+    set_smem((const void*)gemm_tc_kernel<1, false, 8, false, 1>); set_smem((const void*)gemm_tc_kernel<2, false, 8, false, 1>);
+    set_smem((const void*)gemm_tc_kernel<1, true, 8, false, 1>); set_smem((const void*)gemm_tc_kernel<2, true, 8, false, 1>);
+    set_smem((const void*)gemm_tc_kernel<1, false, 8, false, 2>); set_smem((const void*)gemm_tc_kernel<2, false, 8, false, 2>);
+    set_smem((const void*)gemm_tc_kernel<1, true, 8, false, 2>); set_smem((const void*)gemm_tc_kernel<2, true, 8, false, 2>);
     if (e != cudaSuccess) { set_error("jmt_gemm_bf16: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); cudaGetLastError(); return JMT_ERR_CUDA; }
     attr_set[dev & 63].store(1, std::memory_order_release);
   }
@@ -1099,9 +1125,9 @@ static int gemm_tc_launch(const jmt_gemm_desc* g, const void* a_lo, const void* 
   cfg.numAttrs = pdl ? 2 : 1;
   cudaError_t le;
 #define JMT_TC_LAUNCH(CTA, MASK, X3, EXT) le = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<CTA, MASK, 8, X3, EXT>, map_a, map_b, map_d, map_a_lo, map_b_lo, p)
-#define JMT_TC_LAUNCH_X(CTA, MASK) do { if (x3) JMT_TC_LAUNCH(CTA, MASK, true, false); else if (ext) JMT_TC_LAUNCH(CTA, MASK, false, true); \
-                                        else JMT_TC_LAUNCH(CTA, MASK, false, false); } while (0)
-  const bool ext = p.aux != nullptr || p.colsum != nullptr;
+#define JMT_TC_LAUNCH_X(CTA, MASK) do { if (x3) JMT_TC_LAUNCH(CTA, MASK, true, 0); else if (ext == 2) JMT_TC_LAUNCH(CTA, MASK, false, 2); \
+                                        else if (ext == 1) JMT_TC_LAUNCH(CTA, MASK, false, 1); else JMT_TC_LAUNCH(CTA, MASK, false, 0); } while (0)
+  const int ext = p.colsum != nullptr ? 2 : (p.aux != nullptr ? 1 : 0);
   if (p.colmask) { if (p.cluster == 2) JMT_TC_LAUNCH_X(2, true); else JMT_TC_LAUNCH_X(1, true); }
   else { if (p.cluster == 2) JMT_TC_LAUNCH_X(2, false); else JMT_TC_LAUNCH_X(1, false); }
 #undef JMT_TC_LAUNCH_X
