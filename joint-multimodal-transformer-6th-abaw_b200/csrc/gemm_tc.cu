@@ -449,23 +449,25 @@ __device__ __forceinline__ bool epi_tile_ext(const TcParams& p, const CUtensorMa
   xr.aux_row = p.aux != nullptr ? p.aux + row_off : nullptr;
   xr.csum = p.colsum == nullptr ? nullptr : (p.csum_smem ? e.csum_sh : p.colsum) + (int64_t)e.b0 * p.colsum_bs0;
   const bool aux_aligned = xr.aux_row != nullptr && ((reinterpret_cast<uintptr_t>(xr.aux_row) | (uintptr_t)(e.n0 * 2)) & 15) == 0;
-  // The aux loads (global memory, ~1 us) are software-pipelined one 32-column half ahead of their use: the epilogue of a wide
-  // K = 512 tile is exposed (one accumulator stage), un-hidden latency there showed up 1:1 in the launch time.
+  // (Pipelining the aux loads one half ahead of their use was tried and measured SLOWER -- FFN2 dgrad 77 -> 94 us under ncu --:
+  //  the loads are issued right before the TMEM wait they overlap with.)
   uint32_t ax0[16] = {}, ax1[16] = {};
-  bool v0 = ext_load_aux(p, e, xr, aux_aligned, e.part * 64, ax0), v1 = false;
+  bool v0 = false, v1 = false;
   for (int c0 = e.part * 64; c0 < e.bn; c0 += 64 * e.parts) {
     if (e.n0 + c0 >= p.N) break;
     const bool second = c0 + 32 < e.bn;
     const int c_next = c0 + 64 * e.parts;
     uint32_t r[32], pk[16];
     tc_ld32_issue(e.tbase + c0, r);
-    if (second) v1 = ext_load_aux(p, e, xr, aux_aligned, c0 + 32, ax1);
+    v0 = ext_load_aux(p, e, xr, aux_aligned, c0, ax0);
     tc_wait_ld();
     // ---- columns [c0, c0 + 32)
     uint32_t r2[32];
-    if (second) tc_ld32_issue(e.tbase + c0 + 32, r2);       // the second half's TMEM load is in flight under the math
+    if (second) {
+      tc_ld32_issue(e.tbase + c0 + 32, r2);       // the second half's TMEM load and aux loads are in flight under the math
+      v1 = ext_load_aux(p, e, xr, aux_aligned, c0 + 32, ax1);
+    }
     ext_half<MASK, CSUM>(p, e, xr, r, ax0, v0, c0, pk);
-    if (c_next < e.bn && e.n0 + c_next < p.N) v0 = ext_load_aux(p, e, xr, aux_aligned, c_next, ax0);   // next chunk's first half
     if (lane == 0) bulk_wait_read0();       // previous TMA store has finished reading the staging tile
     __syncwarp();
 #pragma unroll
