@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.join(ROOT, "joint-multimodal-transformer-6th-abaw_b200")
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libjmt_b200.so")
-SOURCES = ["core.cu", "ccc.cu", "rowops.cu", "elementwise.cu", "heads.cu", "gemm_simt.cu", "gemm_tc.cu", "attn_tc.cu", "valpost.cu"]
+SOURCES = ["core.cu", "ccc.cu", "rowops.cu", "elementwise.cu", "heads.cu", "gemm_simt.cu", "gemm_tc.cu", "attn_tc.cu", "attn_bwd_tc.cu", "valpost.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC",
               "-cudart", "static"]

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define JMT_ABI_VERSION 8
+#define JMT_ABI_VERSION 9
 
 typedef enum {
   JMT_OK = 0,
@@ -196,6 +196,45 @@ int jmt_attn_merge(const void* o_chunk, int64_t ld, int64_t hs, int64_t bs, cons
                    void* out, int first, int NB, int heads, int rows, int dh, void* stream);
 /* Debug aid: per-CTA cycle counters of the TMA / MMA / row-warp roles (148*16 uint64 device buffer; NULL disables). */
 int jmt_attn_set_profile_buffer(void* dev_buf);
+
+/* ------------------------------------------------------------------------------------------ *
+ * Attention backward, the three GEMMs behind dS / P in ONE launch (bf16, tcgen05, CTA pairs):
+ *   part 0 (x_trans = 0):  dQ(q, c) (op)= alpha * sum_s dS(q, s) * K(s, c)
+ *   part 1 (x_trans = 1):  dK(s, c) (op)= alpha * sum_q dS(q, s) * Q(q, c)
+ *   part 2 (x_trans = 1):  dV(s, c) (op)= alpha * sum_q P(q, s)  * dO(q, c)
+ * i.e. every part is  d(n, c) (op)= alpha * sum_k X(n, k) * a(k, c)  with X(n, k) = x[n*x_ld + k] (x_trans = 0: n < Lq, k < S) or
+ * x[k*x_ld + n] (x_trans = 1: n < S, k < Lq); x = dS or P, (NB, heads, Lq, x_ld) contiguous bf16 as written by
+ * jmt_attn_chain_bf16; a / d element (r, c) of (head h, batch b) at ptr[b*bs + h*hs + r*ld + c], c < dh.
+ * A part with d == NULL is skipped.  store_mode: JMT_STORE / JMT_ACCUMULATE.  colsum (nullable, fp32, heads*dh entries,
+ * caller-zeroed or running): colsum[h*dh + c] += sum over (b, n) of the values this launch stores / adds to d(n, c) -- the bias
+ * gradient of the projection that produced Q / K / V.
+ * Computed transposed on the tensor cores (head dimension on the MMA's M axis, the sequence extent on N: see
+ * csrc/attn_bwd_tc.cu).  Supported: dh in {256, 512}, Lq, S <= 320, heads*dh <= 1024, x_ld % 8 == 0, 16-byte aligned a / d
+ * geometry; jmt_attn_bwd_dqkv_supported() says whether a geometry is (the caller otherwise issues three jmt_gemm_bf16).
+ * Replaces the two bmm backward pairs of torch's MHA math path at the nn.MultiheadAttention call sites
+ * mm_multi_transformers.py:62,142-167.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  const void* a;                  /* bf16 (k extent, dh) matrix contracted over its rows: K (dQ), Q (dK), dO (dV) */
+  int64_t a_ld, a_hs, a_bs;
+  const void* x;                  /* bf16 dS or P */
+  int32_t x_trans;
+  void* d;                        /* bf16 output (n extent, dh); NULL: part skipped */
+  int64_t d_ld, d_hs, d_bs;
+  int32_t store_mode;
+  float alpha;
+  float* colsum;
+} jmt_attn_bwd_part;
+typedef struct {
+  jmt_attn_bwd_part part[3];
+  int32_t Lq, S, dh, heads, NB;
+  int64_t x_ld;
+} jmt_attn_bwd_desc;
+int jmt_attn_bwd_dqkv_supported(const jmt_attn_bwd_desc* g);   /* 1 / 0, no launch */
+int jmt_attn_bwd_dqkv_bf16(const jmt_attn_bwd_desc* g, void* stream);
+/* Debug aid: per-CTA cycle counters (148*16 uint64 device buffer; NULL disables): [0] MMA wait-A [1] wait-X [2] wait-TMEM
+ * [3] MMA total [4] epilogue wait-accumulator [5] epilogue total */
+int jmt_attn_bwd_set_profile_buffer(void* dev_buf);
 
 /* ------------------------------------------------------------------------------------------ *
  * Memory-bound fused row kernels (one warp per row, warp-shuffle reductions, 16-byte accesses).

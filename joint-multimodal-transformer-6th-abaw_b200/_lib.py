@@ -51,6 +51,25 @@ class AttnDesc(C.Structure):
     ]
 
 
+class AttnBwdPart(C.Structure):
+    """Mirror of jmt_attn_bwd_part (include/jmt_b200.h)."""
+    _fields_ = [
+        ("a", C.c_void_p), ("a_ld", C.c_int64), ("a_hs", C.c_int64), ("a_bs", C.c_int64),
+        ("x", C.c_void_p), ("x_trans", C.c_int32),
+        ("d", C.c_void_p), ("d_ld", C.c_int64), ("d_hs", C.c_int64), ("d_bs", C.c_int64),
+        ("store_mode", C.c_int32), ("alpha", C.c_float), ("colsum", C.c_void_p),
+    ]
+
+
+class AttnBwdDesc(C.Structure):
+    """Mirror of jmt_attn_bwd_desc (include/jmt_b200.h)."""
+    _fields_ = [
+        ("part", AttnBwdPart * 3),
+        ("Lq", C.c_int32), ("S", C.c_int32), ("dh", C.c_int32), ("heads", C.c_int32), ("NB", C.c_int32),
+        ("x_ld", C.c_int64),
+    ]
+
+
 _P, _I, _L, _F, _D, _U64 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double, C.c_uint64
 
 # name -> argtypes (restype is always int unless listed in _RESTYPES)
@@ -66,6 +85,9 @@ SIGNATURES = {
     "jmt_attn_chain_supported": [C.POINTER(AttnDesc)],
     "jmt_attn_chain_bf16": [C.POINTER(AttnDesc), _P],
     "jmt_attn_set_profile_buffer": [_P],
+    "jmt_attn_bwd_dqkv_supported": [C.POINTER(AttnBwdDesc)],
+    "jmt_attn_bwd_dqkv_bf16": [C.POINTER(AttnBwdDesc), _P],
+    "jmt_attn_bwd_set_profile_buffer": [_P],
     "jmt_attn_merge": [_P, _L, _L, _L, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "jmt_rowdot_bf16": [_P, _P, _L, _L, _L, _I, _I, _I, _I, _P, _P],
     "jmt_l2norm_fwd": [_P, _I, _L, _P, _I, _L, _I, _F, _P, _P],
@@ -125,7 +147,7 @@ def lib():
             fn = getattr(h, name)           # AttributeError if a declared symbol is not exported
             fn.argtypes = argtypes
             fn.restype = _RESTYPES.get(name, C.c_int)
-        if h.jmt_abi_version() != 8:
+        if h.jmt_abi_version() != 9:
             raise RuntimeError("libjmt_b200.so ABI version mismatch")
         _lib = h
     return _lib

@@ -5,6 +5,8 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
 #include <atomic>
 
 #include "../../include/jmt_b200.h"
@@ -100,6 +102,37 @@ __device__ __forceinline__ float apply_act(float x, int act, float slope) {
     else if ((code) == JMT_BF16) { using T = __nv_bfloat16; __VA_ARGS__; }\
     else { jmt::set_error("bad dtype code %d", (int)(code)); return JMT_ERR_INVALID; } \
   } while (0)
+
+// Programmatic dependent launch (PDL).  A kernel launched through launch_pdl() with JMT_PDL_ALL=1 may be scheduled while its
+// predecessor in the stream is still draining: its CTAs become resident early and MUST call pdl_wait() before they touch global
+// memory -- it blocks until the predecessor grid has completed and its writes are visible (a no-op without the attribute).
+// Measured on B200 (round 2, profiles/ab_same_box_r2.txt, r2w): giving the memory-bound kernels the attribute -- even without
+// an early trigger of their own -- costs 1.3 % of the step (14.69 k vs 14.89 k windows/s): their early-resident CTAs take
+// issue slots and registers from the tail of the tensor-core kernel in front of them.  OFF by default; the tensor-core kernels
+// keep PDL among themselves (prologue under the predecessor's tail).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+inline bool pdl_all_enabled() {
+  static const bool on = []() {
+    const char* a = getenv("JMT_PDL"); const char* b = getenv("JMT_PDL_ALL");
+    return (a ? atoi(a) != 0 : true) && (b ? atoi(b) != 0 : false);
+  }();
+  return on;
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_all_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 inline int grid_for(int64_t work_items, int per_block, int max_blocks = kNumSMs * 16) {
   int64_t b = (work_items + per_block - 1) / per_block;

@@ -8,6 +8,7 @@ constexpr int kEwThreads = 256;
 template <typename T>
 __global__ void __launch_bounds__(kEwThreads)
 act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ y, T* __restrict__ dx, int64_t n8, int64_t n, float slope) {
+  pdl_wait();          // launched with the PDL attribute: the predecessor grid is complete from here on
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nt = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = tid; i < n8; i += nt) {
     Vec8<T> a, b; a.load(dy + i * 8); b.load(y + i * 8);
@@ -24,6 +25,7 @@ act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ y, T* __restrict_
 template <typename T>
 __global__ void __launch_bounds__(kEwThreads)
 add_act_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out, int64_t n8, int64_t n, int act, float slope) {
+  pdl_wait();          // launched with the PDL attribute: the predecessor grid is complete from here on
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nt = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = tid; i < n8; i += nt) {
     Vec8<T> x, y; x.load(a + i * 8); y.load(b + i * 8);
@@ -73,6 +75,7 @@ copy2d_kernel(const TI* __restrict__ in, int64_t in_ld, TO* __restrict__ out, in
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(kEwThreads)
 copy_rows3d_kernel(const TI* __restrict__ in, int64_t in_bs, TO* __restrict__ out, int64_t out_bs, int64_t per, int vec) {
+  pdl_wait();          // launched with the PDL attribute: the predecessor grid is complete from here on
   const TI* ib = in + (int64_t)blockIdx.y * in_bs;
   TO* ob = out + (int64_t)blockIdx.y * out_bs;
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nt = (int64_t)gridDim.x * blockDim.x;
@@ -136,6 +139,7 @@ transpose_kernel(const TI* __restrict__ in, TO* __restrict__ out, int R, int C, 
 template <typename T>
 __global__ void __launch_bounds__(256)
 colsum_kernel(const T* __restrict__ x, int64_t ld, int64_t rows, int cols, float* __restrict__ out, int vec) {
+  pdl_wait();          // launched with the PDL attribute: the predecessor grid is complete from here on
   __shared__ float sh[8][257];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   float acc[8];
@@ -186,6 +190,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 act_bwd_fused_kernel(const T* __restrict__ dy, const T* __restrict__ y, const uint8_t* __restrict__ mask, T* __restrict__ dx,
                      int64_t rows, int cols, int L, float scale, float slope, float* __restrict__ colsum) {
+  pdl_wait();          // launched with the PDL attribute: the predecessor grid is complete from here on
   __shared__ float sh[8][257];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   float acc[8];
@@ -532,7 +537,7 @@ extern "C" int jmt_act_bwd(const void* dy, const void* y, void* dx, int64_t n, f
   if (n == 0) return JMT_OK;
   const bool al = ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(dx)) & 31) == 0;
   const int64_t n8 = al ? n / 8 : 0;
-  JMT_DISPATCH_DTYPE(dtype, T, (act_bwd_kernel<T><<<grid_for(n, kEwThreads * 16), kEwThreads, 0, (cudaStream_t)stream>>>((const T*)dy, (const T*)y, (T*)dx, n8, n, slope)));
+  JMT_DISPATCH_DTYPE(dtype, T, (launch_pdl(act_bwd_kernel<T>, dim3(grid_for(n, kEwThreads * 16)), dim3(kEwThreads), 0, (cudaStream_t)stream, (const T*)dy, (const T*)y, (T*)dx, n8, n, slope)));
   return check_launch("act_bwd_kernel");
 }
 
@@ -541,7 +546,7 @@ extern "C" int jmt_add_act(const void* a, const void* b, void* out, int64_t n, i
   if (n == 0) return JMT_OK;
   const bool al = ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(out)) & 31) == 0;
   const int64_t n8 = al ? n / 8 : 0;
-  JMT_DISPATCH_DTYPE(dtype, T, (add_act_kernel<T><<<grid_for(n, kEwThreads * 16), kEwThreads, 0, (cudaStream_t)stream>>>((const T*)a, (const T*)b, (T*)out, n8, n, act, slope)));
+  JMT_DISPATCH_DTYPE(dtype, T, (launch_pdl(add_act_kernel<T>, dim3(grid_for(n, kEwThreads * 16)), dim3(kEwThreads), 0, (cudaStream_t)stream, (const T*)a, (const T*)b, (T*)out, n8, n, act, slope)));
   return check_launch("add_act_kernel");
 }
 
@@ -711,7 +716,7 @@ extern "C" int jmt_copy_rows3d(const void* in, int in_dtype, int64_t in_bs, void
   int gx = grid_for(per, kEwThreads * 8, kNumSMs * 8);
   dim3 grid(gx, (unsigned)nb);
   JMT_DISPATCH_DTYPE(in_dtype, TI, JMT_DISPATCH_DTYPE(out_dtype, TO,
-      (copy_rows3d_kernel<TI, TO><<<grid, kEwThreads, 0, st>>>((const TI*)in, in_bs, (TO*)out, out_bs, per, vec))));
+      (launch_pdl(copy_rows3d_kernel<TI, TO>, grid, dim3(kEwThreads), 0, st, (const TI*)in, in_bs, (TO*)out, out_bs, per, vec))));
   return check_launch("copy_rows3d_kernel");
 }
 
@@ -724,7 +729,7 @@ extern "C" int jmt_colsum(const void* x, int dtype, int64_t ld, int64_t rows, in
   if (gy > cap) gy = cap;
   if (gy < 1) gy = 1;
   const int vec = (cols % 8 == 0 && ld % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) ? 1 : 0;
-  JMT_DISPATCH_DTYPE(dtype, T, (colsum_kernel<T><<<dim3(gx, gy), 256, 0, (cudaStream_t)stream>>>((const T*)x, ld, rows, cols, out, vec)));
+  JMT_DISPATCH_DTYPE(dtype, T, (launch_pdl(colsum_kernel<T>, dim3(gx, gy), dim3(256), 0, (cudaStream_t)stream, (const T*)x, ld, rows, cols, out, vec)));
   return check_launch("colsum_kernel");
 }
 

@@ -560,8 +560,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a_hi, const __grid_consta
   pdl_wait();
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ================================ TMA producer (every CTA) ================================
+    {
+      // ================================ TMA producer (every CTA; whole warp, one elected lane issues) ================================
+      const uint32_t el = elect_one();
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_a_hi)) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_b_hi)) : "memory");
       if constexpr (kX3) {
@@ -592,8 +593,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a_hi, const __grid_consta
           mbar_wait(empty_bar + 8 * stage, phase ^ 1);
           if (p.prof) pr_wait += clock64() - tw;
           const int b_tx = c.tail ? p.b_tail_bytes : p.b_tx_bytes;
-          if constexpr (kCta == 1) mbar_expect_tx(full_bar + 8 * stage, kOps * (kAStageBytes + b_tx));
-          else mbar_expect_tx_cluster(full_leader + 8 * stage, kOps * (kAStageBytes + b_tx));
+          if constexpr (kCta == 1) mbar_expect_tx_el(el, full_bar + 8 * stage, kOps * (kAStageBytes + b_tx));
+          else mbar_expect_tx_cluster_el(el, full_leader + 8 * stage, kOps * (kAStageBytes + b_tx));
 #pragma unroll
           for (int part = 0; part < kOps; ++part) {          // kX3: part 0 = hi tiles, part 1 = lo tiles (same coordinates)
           const CUtensorMap& tma_a = part == 0 ? tma_a_hi : tma_a_lo;
@@ -603,52 +604,52 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a_hi, const __grid_consta
           if constexpr (kCta == 1) {
             const uint32_t fb = full_bar + 8 * stage;
             if (p.a_major == JMT_MAJOR_K) {
-              tma_load_4d(a_dst, &tma_a, fb, kb * kBlockK, c.m0 + ash, ab0, ab1);
+              tma_load_4d_el(el, a_dst, &tma_a, fb, kb * kBlockK, c.m0 + ash, ab0, ab1);
             } else if (p.a_mn5) {
-              tma_load_5d(a_dst, &tma_a, fb, 0, kb * kBlockK + ash, c.m0 >> 6, ab0, ab1);
+              tma_load_5d_el(el, a_dst, &tma_a, fb, 0, kb * kBlockK + ash, c.m0 >> 6, ab0, ab1);
             } else {
-              tma_load_4d(a_dst, &tma_a, fb, c.m0, kb * kBlockK + ash, ab0, ab1);
-              tma_load_4d(a_dst + 8192, &tma_a, fb, c.m0 + 64, kb * kBlockK + ash, ab0, ab1);
+              tma_load_4d_el(el, a_dst, &tma_a, fb, c.m0, kb * kBlockK + ash, ab0, ab1);
+              tma_load_4d_el(el, a_dst + 8192, &tma_a, fb, c.m0 + 64, kb * kBlockK + ash, ab0, ab1);
             }
             if (!kX3 && c.tail) {      // tail piece: the tail map's box holds exactly this piece (tma_b_lo slot, unused without kX3)
-              if (p.b_major == JMT_MAJOR_K) tma_load_4d(b_dst, &tma_b_lo, fb, tap * p.K + kb * kBlockK, c.n0, bb0, bb1);
-              else tma_load_5d(b_dst, &tma_b_lo, fb, 0, kb * kBlockK + bsh, c.n0 >> 6, bb0, bb1);
+              if (p.b_major == JMT_MAJOR_K) tma_load_4d_el(el, b_dst, &tma_b_lo, fb, tap * p.K + kb * kBlockK, c.n0, bb0, bb1);
+              else tma_load_5d_el(el, b_dst, &tma_b_lo, fb, 0, kb * kBlockK + bsh, c.n0 >> 6, bb0, bb1);
             } else if (p.b_major == JMT_MAJOR_K) {
-              tma_load_4d(b_dst, &tma_b, fb, tap * p.K + kb * kBlockK, c.n0, bb0, bb1);
+              tma_load_4d_el(el, b_dst, &tma_b, fb, tap * p.K + kb * kBlockK, c.n0, bb0, bb1);
             } else if (p.b_mn5) {
-              tma_load_5d(b_dst, &tma_b, fb, 0, kb * kBlockK + bsh, c.n0 >> 6, bb0, bb1);
+              tma_load_5d_el(el, b_dst, &tma_b, fb, 0, kb * kBlockK + bsh, c.n0 >> 6, bb0, bb1);
             } else {
               for (int ch = 0; ch < b_chunks; ++ch)
-                tma_load_4d(b_dst + ch * 8192, &tma_b, fb, c.n0 + ch * 64, kb * kBlockK + bsh, bb0, bb1);
+                tma_load_4d_el(el, b_dst + ch * 8192, &tma_b, fb, c.n0 + ch * 64, kb * kBlockK + bsh, bb0, bb1);
             }
           } else {
             const uint32_t fb = full_leader + 8 * stage;
             if (p.a_major == JMT_MAJOR_K) {
-              tma_load_4d_2sm(a_dst, &tma_a, fb, kb * kBlockK, c.m0 + ash, ab0, ab1);
+              tma_load_4d_2sm_el(el, a_dst, &tma_a, fb, kb * kBlockK, c.m0 + ash, ab0, ab1);
             } else if (p.a_mn5) {
-              tma_load_5d_2sm(a_dst, &tma_a, fb, 0, kb * kBlockK + ash, c.m0 >> 6, ab0, ab1);
+              tma_load_5d_2sm_el(el, a_dst, &tma_a, fb, 0, kb * kBlockK + ash, c.m0 >> 6, ab0, ab1);
             } else {
-              tma_load_4d_2sm(a_dst, &tma_a, fb, c.m0, kb * kBlockK + ash, ab0, ab1);
-              tma_load_4d_2sm(a_dst + 8192, &tma_a, fb, c.m0 + 64, kb * kBlockK + ash, ab0, ab1);
+              tma_load_4d_2sm_el(el, a_dst, &tma_a, fb, c.m0, kb * kBlockK + ash, ab0, ab1);
+              tma_load_4d_2sm_el(el, a_dst + 8192, &tma_a, fb, c.m0 + 64, kb * kBlockK + ash, ab0, ab1);
             }
             if (!kX3 && c.tail) {      // tail piece: this CTA's half of it through the tail map (tma_b_lo slot, unused without kX3)
               const int n_t = c.n0 + crank * (p.tail_bn / kCta);
-              if (p.b_major == JMT_MAJOR_K) tma_load_4d_2sm(b_dst, &tma_b_lo, fb, tap * p.K + kb * kBlockK, n_t, bb0, bb1);
-              else tma_load_5d_2sm(b_dst, &tma_b_lo, fb, 0, kb * kBlockK + bsh, n_t >> 6, bb0, bb1);
+              if (p.b_major == JMT_MAJOR_K) tma_load_4d_2sm_el(el, b_dst, &tma_b_lo, fb, tap * p.K + kb * kBlockK, n_t, bb0, bb1);
+              else tma_load_5d_2sm_el(el, b_dst, &tma_b_lo, fb, 0, kb * kBlockK + bsh, n_t >> 6, bb0, bb1);
             } else if (p.wide) {          // two 128-column pieces: this CTA's share of the B operand of each of the two MMAs
 #pragma unroll
               for (int h = 0; h < 2; ++h) {
                 const int n_h = c.n0 + h * 256 + crank * 128;
-                if (p.b_major == JMT_MAJOR_K) tma_load_4d_2sm(b_dst + h * 16384, &tma_b, fb, tap * p.K + kb * kBlockK, n_h, bb0, bb1);
-                else tma_load_5d_2sm(b_dst + h * 16384, &tma_b, fb, 0, kb * kBlockK + bsh, n_h >> 6, bb0, bb1);
+                if (p.b_major == JMT_MAJOR_K) tma_load_4d_2sm_el(el, b_dst + h * 16384, &tma_b, fb, tap * p.K + kb * kBlockK, n_h, bb0, bb1);
+                else tma_load_5d_2sm_el(el, b_dst + h * 16384, &tma_b, fb, 0, kb * kBlockK + bsh, n_h >> 6, bb0, bb1);
               }
             } else if (p.b_major == JMT_MAJOR_K) {
-              tma_load_4d_2sm(b_dst, &tma_b, fb, tap * p.K + kb * kBlockK, c.n0 + n_off, bb0, bb1);
+              tma_load_4d_2sm_el(el, b_dst, &tma_b, fb, tap * p.K + kb * kBlockK, c.n0 + n_off, bb0, bb1);
             } else if (p.b_mn5) {
-              tma_load_5d_2sm(b_dst, &tma_b, fb, 0, kb * kBlockK + bsh, (c.n0 + n_off) >> 6, bb0, bb1);
+              tma_load_5d_2sm_el(el, b_dst, &tma_b, fb, 0, kb * kBlockK + bsh, (c.n0 + n_off) >> 6, bb0, bb1);
             } else {
               for (int ch = 0; ch < b_chunks; ++ch)
-                tma_load_4d_2sm(b_dst + ch * 8192, &tma_b, fb, c.n0 + n_off + ch * 64, kb * kBlockK + bsh, bb0, bb1);
+                tma_load_4d_2sm_el(el, b_dst + ch * 8192, &tma_b, fb, c.n0 + n_off + ch * 64, kb * kBlockK + bsh, bb0, bb1);
             }
           }
           }
@@ -660,11 +661,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a_hi, const __grid_consta
           }
         }
       }
-      if (p.prof) { p.prof[blockIdx.x * 16 + 3] = pr_wait; p.prof[blockIdx.x * 16 + 4] = clock64() - pr_t0; }
+      if (p.prof && lane == 0) { p.prof[blockIdx.x * 16 + 3] = pr_wait; p.prof[blockIdx.x * 16 + 4] = clock64() - pr_t0; }
     }
   } else if (warp == 1) {
-    if (lane == 0 && crank == 0) {
-      // ================================ MMA issuer (leader CTA of a pair) ================================
+    if (crank == 0) {
+      // ================================ MMA issuer (leader CTA of a pair; whole warp, one elected lane issues) ================================
+      const uint32_t el = elect_one();
       int stage = 0; uint32_t phase = 0;
       int tile_iter = 0;
       long long mw_full = 0, mw_tempty = 0; const long long mw_t0 = p.prof ? clock64() : 0;
@@ -698,7 +700,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a_hi, const __grid_consta
               const uint64_t b_desc = make_smem_desc(sB + stage * b_stride, b_lbo, 1024);
 #pragma unroll
               for (int k = 0; k < kBlockK / kUmmaK; ++k)
-                tc_mma<kCta>(d_tmem, a_desc + (uint64_t)(k * a_kstep), b_desc + (uint64_t)(k * b_kstep), p.idesc, (it > c.it0 || k > 0) ? 1u : 0u);
+                tc_mma_elect<kCta>(el, d_tmem, a_desc + (uint64_t)(k * a_kstep), b_desc + (uint64_t)(k * b_kstep), p.idesc, (it > c.it0 || k > 0) ? 1u : 0u);
             }
             ++pend;
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -709,7 +711,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a_hi, const __grid_consta
                 if (p.prof) mw_tempty += clock64() - tw2;
                 h1_free = true;
               } else {
-                h1_free = mbar_test(tempty_bar + 8, acc_phase ^ 1);
+                h1_free = __shfl_sync(0xffffffffu, mbar_test(tempty_bar + 8, acc_phase ^ 1) ? 1 : 0, 0) != 0;
               }
               if (h1_free) tc_fence_after();
             }
@@ -719,14 +721,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a_hi, const __grid_consta
                 const uint64_t b_desc = make_smem_desc(sB + pend_stage * b_stride, b_lbo, 1024);
 #pragma unroll
                 for (int k = 0; k < kBlockK / kUmmaK; ++k)
-                  tc_mma<kCta>(d_tmem + 256, a_desc + (uint64_t)(k * a_kstep), b_desc + (uint64_t)(1024 + k * b_kstep), p.idesc,
+                  tc_mma_elect<kCta>(el, d_tmem + 256, a_desc + (uint64_t)(k * a_kstep), b_desc + (uint64_t)(1024 + k * b_kstep), p.idesc,
                                (pend_it > c.it0 || k > 0) ? 1u : 0u);
-                tc_commit<kCta>(empty_bar + 8 * pend_stage);
+                tc_commit_elect<kCta>(el, empty_bar + 8 * pend_stage);
                 if (++pend_stage == p.stages) pend_stage = 0;
               }
             }
           }
-          tc_commit<kCta>(tfull_bar);
+          tc_commit_elect<kCta>(el, tfull_bar);
           continue;
         }
         for (int it = c.it0; it < c.it1; ++it) {
@@ -738,22 +740,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a_hi, const __grid_consta
           const uint64_t b_desc = make_smem_desc(sB + stage * b_stride, b_lbo, 1024);
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-            tc_mma<kCta>(d_tmem, a_desc + (uint64_t)(k * a_kstep), b_desc + (uint64_t)(k * b_kstep), c.tail ? p.idesc_tail : p.idesc,
+            tc_mma_elect<kCta>(el, d_tmem, a_desc + (uint64_t)(k * a_kstep), b_desc + (uint64_t)(k * b_kstep), c.tail ? p.idesc_tail : p.idesc,
                          (it > c.it0 || k > 0) ? 1u : 0u);
             if constexpr (kX3) {   // + A_hi B_lo + A_lo B_hi (the lo tiles sit one tile behind the hi tiles; descriptor units of 16 B)
-              tc_mma<kCta>(d_tmem, a_desc + (uint64_t)(k * a_kstep), b_desc + (uint64_t)((p.b_stage_bytes >> 4) + k * b_kstep), p.idesc, 1u);
-              tc_mma<kCta>(d_tmem, a_desc + (uint64_t)((kAStageBytes >> 4) + k * a_kstep), b_desc + (uint64_t)(k * b_kstep), p.idesc, 1u);
+              tc_mma_elect<kCta>(el, d_tmem, a_desc + (uint64_t)(k * a_kstep), b_desc + (uint64_t)((p.b_stage_bytes >> 4) + k * b_kstep), p.idesc, 1u);
+              tc_mma_elect<kCta>(el, d_tmem, a_desc + (uint64_t)((kAStageBytes >> 4) + k * a_kstep), b_desc + (uint64_t)(k * b_kstep), p.idesc, 1u);
             }
             if (p.wide && !c.tail)      // columns 256..511 of the tile: same A, second B piece (16 KB further), TMEM columns 256..511
-              tc_mma<kCta>(d_tmem + 256, a_desc + (uint64_t)(k * a_kstep), b_desc + (uint64_t)(1024 + k * b_kstep), p.idesc,
+              tc_mma_elect<kCta>(el, d_tmem + 256, a_desc + (uint64_t)(k * a_kstep), b_desc + (uint64_t)(1024 + k * b_kstep), p.idesc,
                            (it > c.it0 || k > 0) ? 1u : 0u);
           }
-          tc_commit<kCta>(empty_bar + 8 * stage);  // frees the smem slot (in both CTAs) once these MMAs retire
+          tc_commit_elect<kCta>(el, empty_bar + 8 * stage);  // frees the smem slot (in both CTAs) once these MMAs retire
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
-        tc_commit<kCta>(tfull_bar + 8 * acc);      // accumulator ready for the epilogue warps (of both CTAs)
+        tc_commit_elect<kCta>(el, tfull_bar + 8 * acc);      // accumulator ready for the epilogue warps (of both CTAs)
       }
-      if (p.prof) { p.prof[blockIdx.x * 16 + 0] = mw_full; p.prof[blockIdx.x * 16 + 1] = mw_tempty; p.prof[blockIdx.x * 16 + 2] = clock64() - mw_t0; }
+      if (p.prof && lane == 0) { p.prof[blockIdx.x * 16 + 0] = mw_full; p.prof[blockIdx.x * 16 + 1] = mw_tempty; p.prof[blockIdx.x * 16 + 2] = clock64() - mw_t0; }
     }
   } else {
     // ================================ epilogue (warps 2 .. 2 + kEpi - 1) ================================

@@ -323,7 +323,7 @@ class Ctx:
     def colsum_target(self, v: Var, c0: int = 0, c1: Optional[int] = None) -> Optional[torch.Tensor]:
         """fp32 accumulator slice for the column sums of a gradient contribution to v[:, c0:c1] written by a capable GEMM
         (None: not tracked).  Callers must have obtained the gradient buffer with capable=True."""
-        if not (v.track_colsum and self.ext_on() and EPI_COLSUM):
+        if not (v.track_colsum and self.ext_on() and (EPI_COLSUM or v.colsum_direct is not None)):
             return None
         c1 = c1 if c1 is not None else v.data.shape[1]
         if v.colsum_direct is not None:
@@ -593,7 +593,8 @@ def linear(ctx: Ctx, x: Var, wname: str, bname: Optional[str], act=L.ACT_NONE, s
            out: Optional[torch.Tensor] = None, w_rows: Optional[Tuple[int, int]] = None,
            w_cols: Optional[Tuple[int, int]] = None, accumulate_into: Optional[Var] = None,
            grad_from: Optional[Tuple[Var, int, int]] = None, bias_grad_external: bool = False,
-           zero_rows: Tuple[int, int] = (0, 0), fold_act: bool = False, gemm_writers_only: bool = False) -> Var:
+           zero_rows: Tuple[int, int] = (0, 0), fold_act: bool = False, gemm_writers_only: bool = False,
+           writers_emit_colsum: bool = False) -> Var:
     """y = act(x W[r0:r1, c0:c1]^T + b[r0:r1])  (nn.Linear).  ``out`` may be a strided (rows, N) view
     (concat-free epilogue: a GEMM writes straight into its slice of a wider buffer);
     ``accumulate_into`` adds into an existing Var (Linear over a concatenation = sum of Linears over
@@ -603,7 +604,9 @@ def linear(ctx: Ctx, x: Var, wname: str, bname: Optional[str], act=L.ACT_NONE, s
     ``fold_act``: the caller guarantees that y's only consumer is another GEMM op (Linear / conv): that op's dgrad epilogue
     multiplies by act'(y) and emits the column sums, so neither the act-bwd nor the bias-gradient pass runs (bf16 mode).
     ``gemm_writers_only``: the caller guarantees that every writer of d(y) is a GEMM that emits column sums (the projections
-    consumed by attention_core): the bias gradient is accumulated in place by those GEMMs."""
+    consumed by attention_core): the bias gradient is accumulated in place by those GEMMs.
+    ``writers_emit_colsum`` (with gemm_writers_only): the writers are the attention-backward kernel (jmt_attn_bwd_dqkv_bf16), whose
+    transposed epilogue has the column sums for free: they go straight into the bias gradient even without JMT_EPI_EXT=2."""
     W = ctx.w(wname)
     if W.dim() == 3:                       # 1x1 Conv1d weight (cout, cin, 1)
         W = W.view(W.shape[0], W.shape[1])
@@ -628,7 +631,8 @@ def linear(ctx: Ctx, x: Var, wname: str, bname: Optional[str], act=L.ACT_NONE, s
             y.track_colsum = bool(bname) and not bias_grad_external and (act == L.ACT_NONE or fold_act)
             if fold_act and act != L.ACT_NONE and zero_rows == (0, 0):
                 y.fold = (slope, None, 1.0, 0)
-            if EPI_COLSUM and y.track_colsum and (y.fold is not None or (gemm_writers_only and act == L.ACT_NONE)):
+            if y.track_colsum and ((EPI_COLSUM and (y.fold is not None or (gemm_writers_only and act == L.ACT_NONE))) or
+                                   (writers_emit_colsum and gemm_writers_only and act == L.ACT_NONE)):
                 y.colsum_direct = lambda: ctx.pgrad(bname)[r0:r1]
     if ctx.record:
         def bwd():
@@ -798,6 +802,9 @@ ATTN_DELTA_IN_KERNEL = os.environ.get("JMT_ATTN_DELTA", "1") != "0"   # softmax-
 LONG_S_CHUNKED = True       # forward-only attention beyond the fused kernel's key limit: chunked fused kernel + log-sum-exp merge
 LONG_S_CHUNK_MIN_BYTES = 2 << 30   # ... once the fp32 score tensor of the composed path would exceed this (measured: NONE eval at
                                    # B = 1024, 1.26 GB of scores, 7.4 ms composed vs 9.1 ms chunked; B = 4096, 20 GB: chunked only)
+ATTN_BWD_DQKV = os.environ.get("JMT_ATTN_DQKV", "1") != "0"   # dQ / dK / dV of the "ds" backward by ONE launch of jmt_attn_bwd_dqkv_bf16
+                                                               # (transposed CTA-pair kernel, bias-gradient column sums included) instead of
+                                                               # three batched jmt_gemm_bf16 launches, when the geometry is supported
 FUSED_ATTENTION_BWD = "ds"   # "ds": dP GEMM + softmax backward fused (dS on chip, dQ/dK/dV plain GEMMs); "full": dP -> dS -> dQ in one
                              # kernel (correct, not faster than the composition yet); False: GEMM + softmax_bwd kernel
 
@@ -833,6 +840,36 @@ def _attn_chain(ctx: Ctx, mode: int, a1, a1_geo, b1, b1_geo, b2, b2_geo, p_in, x
         e1.record()
         prof.append(("attn_chain_kernel", (2.0 if d is None else 4.0) * NB * heads * Lq * S * dh, e0, e1, (Lq, S, dh, NB * heads, mode)))
     return True
+
+
+def dqkv_planned(ctx: Ctx, dh: int, Lq: int, S: int, heads: int) -> bool:
+    """Will attention_core's backward run jmt_attn_bwd_dqkv_bf16 for this geometry?  (Decided before the projections are built:
+    they then let that kernel add the bias-gradient column sums.  attention_core falls back to column-sum-emitting GEMMs should
+    the fused forward turn out to be unsupported.)"""
+    return (ctx.record and ctx.ext_on() and ATTN_BWD_DQKV and FUSED_ATTENTION is True and FUSED_ATTENTION_BWD == "ds" and
+            dh in (256, 512) and Lq <= 320 and S <= 320 and heads * dh <= 1024)
+
+
+def _attn_bwd_dqkv(ctx: Ctx, parts, Lq, S, dh, heads, NB, x_ld):
+    """One launch of jmt_attn_bwd_dqkv_bf16 (include/jmt_b200.h).  parts: up to three (a, a_geo, x, x_trans, d, d_geo, store, alpha,
+    colsum) tuples; *_geo = (ld, head stride, batch stride) in elements."""
+    g = L.AttnBwdDesc()
+    for i, (a, a_geo, x, x_trans, d, d_geo, store, alpha, colsum) in enumerate(parts):
+        pt = g.part[i]
+        pt.a, pt.x, pt.d = a.data_ptr(), x.data_ptr(), d.data_ptr()
+        pt.a_ld, pt.a_hs, pt.a_bs = a_geo
+        pt.d_ld, pt.d_hs, pt.d_bs = d_geo
+        pt.x_trans, pt.store_mode, pt.alpha = x_trans, store, alpha
+        pt.colsum = colsum.data_ptr() if colsum is not None else None
+    g.Lq, g.S, g.dh, g.heads, g.NB, g.x_ld = Lq, S, dh, heads, NB, x_ld
+    prof = PROFILE
+    if prof is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    L.check(ctx.lib.jmt_attn_bwd_dqkv_bf16(C.byref(g), _stream()), "jmt_attn_bwd_dqkv_bf16")
+    if prof is not None:
+        e1.record()
+        prof.append(("attn_bwd_dqkv_kernel", 2.0 * len(parts) * NB * heads * Lq * S * dh, e0, e1, (Lq, S, dh, NB * heads, len(parts))))
 
 
 def attention_core(ctx: Ctx, q: Var, qcol: int, k: Var, kcol: int, v: Var, vcol: int, E: int, heads: int,
@@ -929,6 +966,20 @@ def attention_core(ctx: Ctx, q: Var, qcol: int, k: Var, kcol: int, v: Var, vcol:
                                                     _stream()), "jmt_rowdot_bf16")
                 _attn_chain(ctx, 1, do, o_geo, vd, v_geo, None, None, probs, ds, None, None, Lq, S, dh, heads, NB, s_ld, scale,
                             L.STORE, delta_in=delta)
+                if ATTN_BWD_DQKV and dh in (256, 512) and Lq <= 320 and S <= 320 and heads * dh <= 1024:
+                    # dQ = dS K, dK = dS^T Q, dV = P^T dO (+ the projections' bias-gradient column sums) in ONE launch
+                    gv, v_mode = _proj_grad_slice(ctx, v, vcol, vcol + E, capable=True)
+                    gk_, k_mode = _proj_grad_slice(ctx, k, kcol, kcol + E, capable=True)
+                    cs = [ctx.colsum_target(t, c0, c0 + E) if t.track_colsum and ctx.ext_on() else None
+                          for t, c0 in ((q, qcol), (k, kcol), (v, vcol))]
+                    gk_ld, gv_ld = gk_.stride(0), gv.stride(0)
+                    _attn_bwd_dqkv(ctx, [
+                        (kd, k_geo, ds, 0, gq_s, dq_geo, q_mode, 1.0, cs[0]),
+                        (qd, q_geo, ds, 1, gk_, (gk.seq_stride * gk_ld, dh, gk.batch_stride * gk_ld), k_mode, 1.0, cs[1]),
+                        (do, o_geo, probs, 1, gv, (gk.seq_stride * gv_ld, dh, gk.batch_stride * gv_ld), v_mode, 1.0, cs[2]),
+                    ], Lq, S, dh, heads, NB, s_ld)
+                    ctx.release(out)
+                    return
                 gemm(ctx, ds, kd, gq_s, M=Lq, N=dh, K=S, a_rows=Lq, b_major=L.MAJOR_MN, b_rows=S,
                      a_ld=s_ld, b_ld=gk.seq_stride * kld, d_ld=gq.seq_stride * q_gld,
                      nb0=heads, nb1=NB, a_bs=sb, b_bs=(dh, gk.batch_stride * kld), d_bs=(dh, gq.batch_stride * q_gld),
@@ -1003,7 +1054,9 @@ def mha_self(ctx: Ctx, x: Var, prefix: str, heads: int, geom: Optional[AttnGeom]
              out_bias_grad_external: bool = False) -> Var:
     """nn.MultiheadAttention(x, x, x): packed QKV projection (one N=3E GEMM), attention, out-proj."""
     E = x.data.shape[1]
-    qkv = linear(ctx, x, prefix + "in_proj_weight", prefix + "in_proj_bias", gemm_writers_only=small is None and _attn_bwd_by_gemms())
+    wec = small is None and geom is not None and dqkv_planned(ctx, E // heads, geom.seq, geom.seq, heads)
+    qkv = linear(ctx, x, prefix + "in_proj_weight", prefix + "in_proj_bias", gemm_writers_only=small is None and _attn_bwd_by_gemms(),
+                 writers_emit_colsum=wec)
     if small is not None:
         o = attention_small(ctx, qkv, small[0], small[1], E, heads)
     else:
@@ -1016,12 +1069,15 @@ def mha_cross(ctx: Ctx, xq: Var, xkv: Var, prefix: str, heads: int, gq: AttnGeom
     """nn.MultiheadAttention(xq, xkv, xkv).  The Q projection of a module applied twice to the same
     query (cross_attention_{v,p,pv} in MultimodalTransformer_w_JR) is computed once."""
     E = xq.data.shape[1]
+    wec = dqkv_planned(ctx, E // heads, gq.seq, gk.seq, heads)
     key = (prefix, id(xq))
     q = ctx.qcache.get(key)
     if q is None:
-        q = linear(ctx, xq, prefix + "in_proj_weight", prefix + "in_proj_bias", w_rows=(0, E), gemm_writers_only=_attn_bwd_by_gemms())
+        q = linear(ctx, xq, prefix + "in_proj_weight", prefix + "in_proj_bias", w_rows=(0, E), gemm_writers_only=_attn_bwd_by_gemms(),
+                   writers_emit_colsum=wec)
         ctx.qcache[key] = q
-    kv = linear(ctx, xkv, prefix + "in_proj_weight", prefix + "in_proj_bias", w_rows=(E, 3 * E), gemm_writers_only=_attn_bwd_by_gemms())
+    kv = linear(ctx, xkv, prefix + "in_proj_weight", prefix + "in_proj_bias", w_rows=(E, 3 * E), gemm_writers_only=_attn_bwd_by_gemms(),
+                writers_emit_colsum=wec)
     o = attention_core(ctx, q, 0, kv, 0, kv, E, E, heads, gq, gk)
     return linear(ctx, o, prefix + "out_proj.weight", prefix + "out_proj.bias", out=out, grad_from=grad_from)
 

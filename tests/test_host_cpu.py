@@ -27,7 +27,7 @@ def test_library_builds_and_exports_header_symbols():
         assert hasattr(h, name), f"{name} declared in jmt_b200.h but not exported"
         assert name in _lib.SIGNATURES, f"{name} has no ctypes signature"
     assert set(_lib.SIGNATURES) == declared
-    assert h.jmt_abi_version() == 8
+    assert h.jmt_abi_version() == 9
     # argument validation works without a GPU and reports through jmt_last_error
     assert h.jmt_ccc_sums(None, None, 0, 1, 0, 0, 0.0, None, None) == -1
     assert b"jmt_ccc_sums" in h.jmt_last_error()

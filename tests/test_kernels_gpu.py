@@ -377,10 +377,14 @@ ATTN_CASES = [
     ("t130_s77_h8", 2, 8, 130, 77, 512, True, False),
     ("t260_h2_e256", 2, 2, 260, 260, 256, False, False),
     ("batchdim_h2", 5, 2, 37, 37, 512, False, True),
+    ("t300_s123_h1_x", 3, 1, 300, 123, 512, True, False),
+    ("t200_s300_h2_x", 2, 2, 200, 300, 512, True, False),
+    ("t300_h1_nb80", 80, 1, 300, 300, 512, False, False),      # 480 pair tiles of the dQ/dK/dV kernel: several per CTA pair, ring wrap-around
 ]
 
 
-@pytest.mark.parametrize("fused", [("full", "full"), ("full", "ds"), ("p", "ds"), (False, False)], ids=["full-full", "full-ds", "p-ds", "composed"])
+@pytest.mark.parametrize("fused", [("full", "full"), ("full", "ds"), ("full", "ds", "gemms"), ("p", "ds"), (False, False)],
+                         ids=["full-full", "full-ds", "full-ds-gemms", "p-ds", "composed"])
 @pytest.mark.parametrize("case", ATTN_CASES, ids=[c[0] for c in ATTN_CASES])
 def test_attention_core_bf16(case, fused):
     """softmax(QK^T/sqrt(dh))V forward + dQ/dK/dV through engine.attention_core in bf16 mode: the fused tcgen05
@@ -392,8 +396,11 @@ def test_attention_core_bf16(case, fused):
     dh = E_ // h
     ctx = _ctx("bf16")
     ctx.record = True
-    old = (E.FUSED_ATTENTION, E.FUSED_ATTENTION_BWD)
+    old = (E.FUSED_ATTENTION, E.FUSED_ATTENTION_BWD, E.ATTN_BWD_DQKV)
     E.FUSED_ATTENTION, E.FUSED_ATTENTION_BWD = (True if fused[0] == "full" else fused[0]), fused[1]
+    E.ATTN_BWD_DQKV = len(fused) < 3           # "gemms": dQ / dK / dV by three batched jmt_gemm_bf16 instead of jmt_attn_bwd_dqkv_bf16
+    if NB > 8 and fused[:2] != ("full", "ds"):
+        pytest.skip("large-batch case only for the default path")
     try:
         # projection matrices as the engine holds them: rows = batch*seq (or seq*batch for the batch-major geometry)
         qw = E_ if cross else 3 * E_          # a cross-attention Q projection is (rows, E); self-attention packs Q | K | V
@@ -444,7 +451,90 @@ def test_attention_core_bf16(case, fused):
         assert (gk_got - want_k).abs().max() < 3e-2 * want_k.abs().max(), "dK"
         assert (gv_got - want_v).abs().max() < 3e-2 * want_v.abs().max(), "dV"
     finally:
-        E.FUSED_ATTENTION, E.FUSED_ATTENTION_BWD = old
+        E.FUSED_ATTENTION, E.FUSED_ATTENTION_BWD, E.ATTN_BWD_DQKV = old
+
+
+DQKV_CASES = [
+    # name, NB, heads, Lq, S, dh
+    ("w300_dh512", 5, 1, 300, 300, 512),
+    ("w300_dh512_nb160", 160, 1, 300, 300, 512),
+    ("lq77_s290_dh256_h2", 3, 2, 77, 290, 256),
+    ("lq320_s17_dh512", 4, 1, 320, 17, 512),
+    ("lq1_s1_dh256", 2, 1, 1, 1, 256),
+    ("lq130_s129_dh256_h4", 2, 4, 130, 129, 256),
+]
+
+
+@pytest.mark.parametrize("case", DQKV_CASES, ids=[c[0] for c in DQKV_CASES])
+def test_attn_bwd_dqkv_kernel(case):
+    """jmt_attn_bwd_dqkv_bf16 (dQ = dS K, dK = dS^T Q, dV = P^T dO in one launch, transposed CTA-pair tiles) against fp64 einsums on
+    the same bf16 operands: STORE, then ACCUMULATE on top, bias-gradient column sums, strided (packed QKV) operand / output
+    geometry, padded x_ld with NaN in the pad columns (they must never be read)."""
+    name, NB, h, Lq, S, dh = case
+    torch.manual_seed(len(name) + NB)
+    dev = torch.device("cuda")
+    E_ = h * dh
+    ctx = _ctx("bf16")
+    x_ld = (S + 7) // 8 * 8
+    ds = torch.full((NB, h, Lq, x_ld), float("nan")).to(torch.bfloat16)
+    pr = torch.full((NB, h, Lq, x_ld), float("nan")).to(torch.bfloat16)
+    ds[..., :S] = (torch.randn(NB, h, Lq, S) * 0.3).to(torch.bfloat16)
+    pr[..., :S] = torch.rand(NB, h, Lq, S).to(torch.bfloat16)
+    qkv = (torch.randn(NB * max(Lq, S), 3 * E_) * 0.5).to(torch.bfloat16)      # packed projections: Q | K | V column slices, ld = 3E
+    do = (torch.randn(NB * Lq, E_) * 0.5).to(torch.bfloat16)
+    rows = max(Lq, S)
+    q4 = qkv.view(NB, rows, 3 * E_)[:, :Lq, :E_].double().reshape(NB, Lq, h, dh)
+    k4 = qkv.view(NB, rows, 3 * E_)[:, :S, E_:2 * E_].double().reshape(NB, S, h, dh)
+    do4 = do.view(NB, Lq, E_).double().reshape(NB, Lq, h, dh)
+    want_q = torch.einsum("bhqs,bshd->bqhd", ds[..., :S].double(), k4).reshape(NB, Lq, E_)
+    want_k = torch.einsum("bhqs,bqhd->bshd", ds[..., :S].double(), q4).reshape(NB, S, E_) * 0.5
+    want_v = torch.einsum("bhqs,bqhd->bshd", pr[..., :S].double(), do4).reshape(NB, S, E_)
+    dsd, prd, qkvd, dod = ds.to(dev), pr.to(dev), qkv.to(dev), do.to(dev)
+    g = torch.full((NB * rows, 3 * E_), float("nan"), dtype=torch.bfloat16, device=dev)     # gradient of the packed projection
+    cs = torch.zeros(3, E_, dtype=torch.float32, device=dev)
+    ld = 3 * E_
+    geo = (ld, dh, rows * ld)
+    o_geo = (E_, dh, Lq * E_)
+
+    def run(store):
+        E._attn_bwd_dqkv(ctx, [
+            (qkvd[:, E_:2 * E_], geo, dsd, 0, g[:, :E_], geo, store, 1.0, cs[0]),
+            (qkvd[:, :E_], geo, dsd, 1, g[:, E_:2 * E_], geo, store, 0.5, cs[1]),
+            (dod, o_geo, prd, 1, g[:, 2 * E_:], geo, store, 1.0, cs[2]),
+        ], Lq, S, dh, h, NB, x_ld)
+        torch.cuda.synchronize()
+
+    def check(mult):
+        g4 = g.cpu().double().view(NB, rows, 3 * E_)
+        for nm, got, want in (("dQ", g4[:, :Lq, :E_], want_q), ("dK", g4[:, :S, E_:2 * E_], want_k), ("dV", g4[:, :S, 2 * E_:], want_v)):
+            err = (got - mult * want).abs().max()
+            assert err < 1.2e-2 * mult * want.abs().max() + 1e-6, (nm, float(err), float(want.abs().max()))
+        # rows beyond the valid extent of a part are never written
+        if Lq < rows:
+            assert torch.isnan(g4[:, Lq:, :E_]).all()
+        if S < rows:
+            assert torch.isnan(g4[:, S:, E_:]).all()
+        for i, want in enumerate((want_q, want_k, want_v)):
+            wsum = mult * want.sum(dim=(0, 1))
+            err = (cs[i].cpu().double() - wsum).abs().max()
+            assert err < 2e-2 * mult * want.abs().sum(dim=(0, 1)).max() / math.sqrt(want.shape[0] * want.shape[1]) + 1e-3, ("colsum", i, float(err))
+
+    assert L.lib().jmt_attn_bwd_dqkv_supported is not None
+    run(L.STORE)
+    check(1.0)
+    run(L.ACCUMULATE)
+    check(2.0)
+
+
+def test_attn_bwd_dqkv_rejects_unsupported_geometry():
+    g = L.AttnBwdDesc()
+    g.Lq, g.S, g.dh, g.heads, g.NB, g.x_ld = 300, 300, 64, 8, 2, 304
+    assert L.lib().jmt_attn_bwd_dqkv_supported(C.byref(g)) == 0
+    assert L.lib().jmt_attn_bwd_dqkv_bf16(C.byref(g), None) == -3
+    g.dh, g.heads, g.S = 512, 1, 400
+    assert L.lib().jmt_attn_bwd_dqkv_supported(C.byref(g)) == 0
+    g.S = 300
+    assert L.lib().jmt_attn_bwd_dqkv_supported(C.byref(g)) == 1
 
 
 @pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
