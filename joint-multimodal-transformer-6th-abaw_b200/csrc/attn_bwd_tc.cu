@@ -8,33 +8,42 @@
 //
 // Here the problem is computed TRANSPOSED, out^T (dh x n) = A^T (dh x k) X(n, k)^T:
 //   * M axis = head dimension (256 or 512): whole CTA pairs (cta_group::2, M = 256), no ghost tiles; the pair's two CTAs each
-//     stage their own 128 rows of A and HALF of X (64 of a piece's 128 columns);
-//   * N axis = the 300-extent, cut into pieces of 128 columns (last piece narrowed to a multiple of 16); the A tile of an M tile
-//     (all of its <= 5 k-blocks, 80 KB) stays resident in shared memory for all pieces, only X is streamed through a ring;
-//   * every (M tile, piece) accumulates into one of FOUR 128-column TMEM slots, so the epilogue of piece i overlaps the MMAs of
-//     pieces i+1 .. i+3 -- also across tiles;
-//   * epilogue: thread = TMEM lane = head-dimension index; it writes its 64 columns as a COLUMN of a [64 n][32 m] bf16 staging
-//     tile (conflict-free 2-byte stores) that one TMA store / reduce-add writes into out[n][m] -- the transposition costs no
-//     shuffle and no extra pass; the per-thread row sum is the bias-gradient column sum of the projection (optional).
-// Roles: warp 0 = A producer (TMA), warp 1 = MMA issuer (leader CTA), warp 2 = X producer (TMA), warps 4..11 = epilogue.
+//     stage their own 128 rows of A and HALF of X's columns;
+//   * N axis = the whole 300-extent in ONE tile, as two MMAs per K = 16 step that share the A tile: a "big" piece of
+//     N1 = 512 - r32(max(Lq, S)) columns (192 for 300) and a "small" rest (108 -> 112);
+//   * TMEM: two big accumulator regions (alternating by tile) and one small one, N1 + N1 + rest <= 512 columns.  The epilogue
+//     drains the small piece first, so the next tile's MMAs (other big region + the small one) start after a quarter of the
+//     drain: epilogue and mainloop overlap although a tile's accumulators are 304 columns wide;
+//   * a plain k-block pipeline: stage = A k-block (16 KB) + the CTA's half of both X pieces (<= 24 KB), 4 stages in flight --
+//     the first versions kept a tile's A resident and streamed X piece by piece through a small ring: 79 us for the loads alone
+//     (too few bytes in flight for the round trip of a slot), MMAs and stores came on top (profiles/dqkv_r2_notes.txt);
+//   * bound: DRAM.  One launch at the C2 geometry reads K, Q, dO (236 MB) and dS / P (92 MB) and writes dQ, dK, dV (236 MB):
+//     564 MB = 87 us at the measured 6.5 TB/s; measured 95-97 us (the three batched GEMMs it replaces: 137 us);
+//   * epilogue: thread = TMEM lane = head-dimension index; it writes 32 columns as a COLUMN of a [32 n][128 m] bf16 staging
+//     tile (conflict-free 2-byte stores; the four lane-quarter warps of a column half fill one tile) that one TMA store /
+//     reduce-add writes into out[n][m] -- the transposition costs no shuffle and no extra pass (16 epilogue warps with a tile
+//     each measured the same: the epilogue is bound by its instruction count, ~5 per element); the per-thread row sum is the bias-gradient column sum of the projection (optional).
+// Roles: warp 0 = TMA producer, warp 1 = MMA issuer (leader CTA), warps 4..11 = epilogue; producer / issuer run their loops
+// warp-uniformly and one elected lane executes the TMA / MMA instructions (operands in uniform registers: under `if (lane == 0)`
+// ptxas wraps every tcgen05.mma in a ~25-instruction ELECT / R2UR loop, which alone made the first version 1.8x slower).
 // Replaces the bmm calls torch autograd issues for F.multi_head_attention_forward's two bmm's (SURVEY Q4;
 // mm_multi_transformers.py:62,142-167) in the backward pass.
 #include "tc_common.cuh"
 
 namespace jmt {
 
-constexpr int kBwThreads = 384;
+constexpr int kBwThreads = 384;      // warp 0 producer, warp 1 MMA issuer, warps 4..11 epilogue
 constexpr int kBwMaxKb = 5;          // k-blocks of 64 per tile: Lq, S <= 320
-constexpr int kBwRing = 8;           // X ring slots (8 KB each)
-constexpr int kBwAcc = 4;            // TMEM accumulator slots of 128 columns
-constexpr int kBwPiece = 128;
+constexpr int kBwMaxStages = 5;      // 4 by default (5 with single-buffered epilogue staging: JMT_DQKV_STAGES=5)
+constexpr int kBwStageSz = 16384 + 16384 + 8192;      // A k-block | X big piece (this CTA's half) | X small piece
 constexpr int kBwEpiWarps = 8;
-constexpr int kBwABytes = kBwMaxKb * 16384;
-constexpr int kBwStageBytes = kBwEpiWarps * 2 * 4096;
+constexpr int kBwStgTile = 8192;                      // [32 n][128 m x 2 B] staging tile, shared by the four warps of a column half
 constexpr int kBwCsumMax = 1024;     // heads * dh entries per part
 
 struct BwPart {
-  int Nn, Kk, nkb, np, trans, store_mode, last_k16, n_last;   // n_last: MMA N of the last piece (multiple of 16)
+  int Nn, Kk, nkb, np, trans, store_mode, last_k16;
+  int n0[2], nmma[2], units[2];      // per piece (0 = big, 1 = small): first column, MMA N (multiple of 16), 32-column epilogue units
+  uint32_t tx_bytes;                 // bytes one CTA lands per stage
   float alpha;
   float* colsum;
 };
@@ -42,9 +51,12 @@ struct BwPart {
 struct BwParams {
   BwPart part[3];
   int nparts, mtiles, heads, dh, total_tiles, csum_len;
+  int n1;                        // columns of a big accumulator region (regions at TMEM columns 0 and n1; the small one starts at 2 * n1)
   FastDiv fd_mt, fd_parts, fd_heads;
   uint32_t idesc_base;           // everything but N and the B major
   unsigned long long* prof;
+  int stages, sbufs, csum_stride; // pipeline stages (4 / 5), staging tiles per column half (2 / 1), floats per part in the column-sum area
+  int debug;                     // JMT_DQKV_DEBUG bit mask (diagnostics only): 1 = epilogue without staging / stores, 2 = issuer without MMAs
 };
 
 struct BwTile { int mtile, part, head, b; };
@@ -61,6 +73,24 @@ __device__ __forceinline__ void st_shared_u16(uint32_t addr, uint16_t v) {
   asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
 }
 
+// 32 accumulator columns of this thread's row -> [alpha *] -> row sum (valid columns only) -> bf16 -> a COLUMN of the staging tile
+// (row pitch 256 B).  Warp-uniform template switches keep the loop at one FADD, half a pack and one 2-byte store per element.
+template <bool SCALE, bool FULL>
+__device__ __forceinline__ void stage_unit(const uint32_t (&r)[32], float alpha, int nv, uint32_t col, float& rsum) {
+  float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+  for (int j = 0; j < 32; j += 2) {
+    float v0 = __uint_as_float(r[j]), v1 = __uint_as_float(r[j + 1]);
+    if (SCALE) { v0 *= alpha; v1 *= alpha; }
+    if (FULL) { s0 += v0; s1 += v1; }
+    else { if (j < nv) s0 += v0; if (j + 1 < nv) s1 += v1; }
+    const uint32_t pk = pack_bf16(v0, v1);
+    st_shared_u16(col + j * 256, (uint16_t)(pk & 0xFFFFu));
+    st_shared_u16(col + (j + 1) * 256, (uint16_t)(pk >> 16));
+  }
+  rsum += s0 + s1;
+}
+
 __global__ void __launch_bounds__(kBwThreads, 1)
 attn_bwd_dqkv_kernel(const __grid_constant__ CUtensorMap ma0, const __grid_constant__ CUtensorMap ma1, const __grid_constant__ CUtensorMap ma2,
                      const __grid_constant__ CUtensorMap mx0, const __grid_constant__ CUtensorMap mx1, const __grid_constant__ CUtensorMap mx2,
@@ -69,15 +99,15 @@ attn_bwd_dqkv_kernel(const __grid_constant__ CUtensorMap ma0, const __grid_const
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = smem_u32(smem_raw);
   if ((base & 1023u) != 0u) __trap();
-  const uint32_t sA = base;                              // kBwMaxKb x [2 chunks x 64 k x 128 B]
-  const uint32_t sX = sA + kBwABytes;                    // ring of [64 x 128 B] tiles
-  const uint32_t sStage = sX + kBwRing * 8192;           // 8 warps x 2 x [64 n x 64 B]
-  const uint32_t sCsum = sStage + kBwStageBytes;         // 3 x csum_len floats
-  const uint32_t bars = sCsum + 3 * kBwCsumMax * 4;
-  const uint32_t a_full = bars, a_empty = bars + 8 * kBwMaxKb;
-  const uint32_t x_full = a_empty + 8 * kBwMaxKb, x_empty = x_full + 8 * kBwRing;
-  const uint32_t t_full = x_empty + 8 * kBwRing, t_empty = t_full + 8 * kBwAcc;
-  const uint32_t tmem_slot = t_empty + 8 * kBwAcc;
+  const uint32_t sRing = base;                                   // stages x (A | X big | X small)
+  const uint32_t sStage = sRing + p.stages * kBwStageSz;         // 2 halves x sbufs x [32 n x 256 B]
+  const uint32_t sCsum = sStage + 2 * p.sbufs * kBwStgTile;      // 3 x csum_stride floats
+  const uint32_t bars = sCsum + 3 * p.csum_stride * 4;
+  const uint32_t full_bar = bars, empty_bar = bars + 8 * kBwMaxStages;
+  const uint32_t t_full = empty_bar + 8 * kBwMaxStages;          // [2]: tile parity
+  const uint32_t t_empty_big = t_full + 16;                      // [2]: big region
+  const uint32_t t_empty_small = t_empty_big + 16;
+  const uint32_t tmem_slot = t_empty_small + 8;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - base));
   float* csum_sh = reinterpret_cast<float*>(smem_raw + (sCsum - base));
 
@@ -86,9 +116,9 @@ attn_bwd_dqkv_kernel(const __grid_constant__ CUtensorMap ma0, const __grid_const
   const int first_tile = blockIdx.x >> 1, tile_stride = gridDim.x >> 1;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kBwMaxKb; ++s) { mbar_init(a_full + 8 * s, 2); mbar_init(a_empty + 8 * s, 1); }
-    for (int s = 0; s < kBwRing; ++s) { mbar_init(x_full + 8 * s, 2); mbar_init(x_empty + 8 * s, 1); }
-    for (int s = 0; s < kBwAcc; ++s) { mbar_init(t_full + 8 * s, 1); mbar_init(t_empty + 8 * s, kBwEpiWarps * 2); }
+    for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar + 8 * s, 2); mbar_init(empty_bar + 8 * s, 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(t_full + 8 * s, 1); mbar_init(t_empty_big + 8 * s, kBwEpiWarps * 2); }
+    mbar_init(t_empty_small, kBwEpiWarps * 2);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -96,7 +126,7 @@ attn_bwd_dqkv_kernel(const __grid_constant__ CUtensorMap ma0, const __grid_const
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < 3 * kBwCsumMax; i += kBwThreads) csum_sh[i] = 0.f;
+  for (int i = threadIdx.x; i < 3 * p.csum_stride; i += kBwThreads) csum_sh[i] = 0.f;
   tc_fence_before();
   __syncthreads();
   cluster_sync_relaxed();
@@ -106,167 +136,186 @@ attn_bwd_dqkv_kernel(const __grid_constant__ CUtensorMap ma0, const __grid_const
   pdl_wait();
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ================================ A producer: the (k x 128 m) tile of this CTA, one k-block per slot ================================
-      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&ma0)) : "memory");
-      if (p.nparts > 1) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&ma1)) : "memory");
-      if (p.nparts > 2) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&ma2)) : "memory");
-      uint32_t aph = 0;                                    // bit kb: phase of slot kb
-      const uint32_t full_leader = mapa_rank(a_full, 0);
-      for (int t = first_tile; t < p.total_tiles; t += tile_stride) {
-        const BwTile c = bw_decode(p, t);
-        const BwPart& P = p.part[c.part];
-        const CUtensorMap* ma = c.part == 0 ? &ma0 : (c.part == 1 ? &ma1 : &ma2);
-        const int mchunk = (c.mtile * 256 + crank * 128) >> 6;
-        for (int kb = 0; kb < P.nkb; ++kb) {
-          mbar_wait(a_empty + 8 * kb, ((aph >> kb) & 1u) ^ 1u);
-          aph ^= 1u << kb;
-          mbar_expect_tx_cluster(full_leader + 8 * kb, 16384);
-          tma_load_5d_2sm(sA + kb * 16384, ma, full_leader + 8 * kb, 0, kb * 64, mchunk, c.head, c.b);
+    // ================================ TMA producer (every CTA): A k-block + this CTA's half of both X pieces per stage ================================
+    const uint32_t el = elect_one();
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&ma0)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mx0)) : "memory");
+    if (p.nparts > 1) { asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&ma1)) : "memory");
+                        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mx1)) : "memory"); }
+    if (p.nparts > 2) { asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&ma2)) : "memory");
+                        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mx2)) : "memory"); }
+    int stage = 0; uint32_t phase = 0;
+    long long w_e = 0; const long long t0 = p.prof ? clock64() : 0;
+    const uint32_t full_leader = mapa_rank(full_bar, 0);
+    for (int t = first_tile; t < p.total_tiles; t += tile_stride) {
+      const BwTile c = bw_decode(p, t);
+      const BwPart& P = p.part[c.part];
+      const CUtensorMap* ma = c.part == 0 ? &ma0 : (c.part == 1 ? &ma1 : &ma2);
+      const CUtensorMap* mx = c.part == 0 ? &mx0 : (c.part == 1 ? &mx1 : &mx2);
+      const int nkb = P.nkb, np = P.np, trans = P.trans;
+      const uint32_t tx = P.tx_bytes;
+      const int mchunk = (c.mtile * 256 + crank * 128) >> 6;
+      // this CTA's share of the two pieces: columns [n0 + crank * nmma / 2, ...), nmma / 2 of them
+      const int hb = P.nmma[0] >> 1, hs = np > 1 ? P.nmma[1] >> 1 : 0;
+      const int nb0 = P.n0[0] + crank * hb, ns0 = np > 1 ? P.n0[1] + crank * hs : 0;
+      // MN-major (trans): 64-column chunks [64 k rows][128 B], 8 KB apart; K-major: 32-row boxes [32 n rows][64 k], 4 KB apart
+      const int ldb = trans ? (hb + 63) >> 6 : (hb + 31) >> 5, lds = trans ? (hs + 63) >> 6 : (hs + 31) >> 5;
+      for (int kb = 0; kb < nkb; ++kb) {
+        { const long long tw = p.prof ? clock64() : 0; mbar_wait(empty_bar + 8 * stage, phase ^ 1u); if (p.prof) w_e += clock64() - tw; }
+        const uint32_t fb = full_leader + 8 * stage;
+        const uint32_t dst = sRing + stage * kBwStageSz;
+        mbar_expect_tx_cluster_el(el, fb, tx);
+        tma_load_5d_2sm_el(el, dst, ma, fb, 0, kb * 64, mchunk, c.head, c.b);
+        if (trans) {
+          for (int j = 0; j < ldb; ++j) tma_load_4d_2sm_el(el, dst + 16384 + j * 8192, mx, fb, nb0 + j * 64, kb * 64, c.head, c.b);
+          for (int j = 0; j < lds; ++j) tma_load_4d_2sm_el(el, dst + 32768 + j * 8192, mx, fb, ns0 + j * 64, kb * 64, c.head, c.b);
+        } else {
+          for (int j = 0; j < ldb; ++j) tma_load_4d_2sm_el(el, dst + 16384 + j * 4096, mx, fb, kb * 64, nb0 + j * 32, c.head, c.b);
+          for (int j = 0; j < lds; ++j) tma_load_4d_2sm_el(el, dst + 32768 + j * 4096, mx, fb, kb * 64, ns0 + j * 32, c.head, c.b);
         }
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       }
     }
-  } else if (warp == 2) {
-    if (lane == 0) {
-      // ================================ X producer: this CTA's half of every piece, k-block by k-block ================================
-      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mx0)) : "memory");
-      if (p.nparts > 1) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mx1)) : "memory");
-      if (p.nparts > 2) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mx2)) : "memory");
-      int slot = 0; uint32_t phase = 0;
-      const uint32_t full_leader = mapa_rank(x_full, 0);
-      for (int t = first_tile; t < p.total_tiles; t += tile_stride) {
-        const BwTile c = bw_decode(p, t);
-        const BwPart& P = p.part[c.part];
-        const CUtensorMap* mx = c.part == 0 ? &mx0 : (c.part == 1 ? &mx1 : &mx2);
-        for (int pc = 0; pc < P.np; ++pc) {
-          const int npc = pc == P.np - 1 ? P.n_last : kBwPiece;       // MMA N of this piece; this CTA supplies columns [crank * npc / 2, ...)
-          const int n0 = pc * kBwPiece + crank * (npc >> 1);
-          for (int kb = 0; kb < P.nkb; ++kb) {
-            mbar_wait(x_empty + 8 * slot, phase ^ 1u);
-            const uint32_t fb = full_leader + 8 * slot;
-            mbar_expect_tx_cluster(fb, 8192);
-            if (P.trans) tma_load_4d_2sm(sX + slot * 8192, mx, fb, n0, kb * 64, c.head, c.b);     // [64 k rows][64 n]: MN-major
-            else tma_load_4d_2sm(sX + slot * 8192, mx, fb, kb * 64, n0, c.head, c.b);              // [64 n rows][64 k]: K-major
-            if (++slot == kBwRing) { slot = 0; phase ^= 1u; }
-          }
-        }
-      }
-    }
+    if (p.prof && lane == 0) { unsigned long long* o = p.prof + blockIdx.x * 16; o[6] = w_e; o[7] = clock64() - t0; }
   } else if (warp == 1) {
     if (crank == 0) {
       // ================================ MMA issuer (leader CTA; whole warp, one elected lane issues) ================================
       const uint32_t el = elect_one();
-      int slot = 0; uint32_t phase = 0, aph = 0;
-      uint32_t acc_it = 0;
-      long long w_a = 0, w_x = 0, w_t = 0; const long long t0 = p.prof ? clock64() : 0;
-      for (int t = first_tile; t < p.total_tiles; t += tile_stride) {
+      int stage = 0; uint32_t phase = 0;
+      uint32_t it = 0;                                // tiles done by this pair
+      long long w_x = 0, w_t = 0; const long long t0 = p.prof ? clock64() : 0;
+      for (int t = first_tile; t < p.total_tiles; t += tile_stride, ++it) {
         const BwTile c = bw_decode(p, t);
         const BwPart& P = p.part[c.part];
         const uint32_t x_lbo = P.trans ? 8192u : 16u;
         const uint32_t x_kstep = P.trans ? 128u : 2u;
-        const int nkb = P.nkb, np = P.np, last_k16 = P.last_k16, n_last = P.n_last;
+        const int nkb = P.nkb, last_k16 = P.last_k16;
+        const bool two = P.np > 1;
         const uint32_t idesc_t = p.idesc_base | ((uint32_t)P.trans << 16);
-        for (int pc = 0; pc < np; ++pc, ++acc_it) {
-          const uint32_t acc = acc_it & (kBwAcc - 1), acc_par = (acc_it >> 2) & 1u;
-          const int npc = pc == np - 1 ? n_last : kBwPiece;
-          const uint32_t idesc = idesc_t | ((uint32_t)(npc >> 3) << 17);
-          { const long long tw = p.prof ? clock64() : 0; mbar_wait(t_empty + 8 * acc, acc_par ^ 1u); if (p.prof) w_t += clock64() - tw; }
+        const uint32_t idesc_b = idesc_t | ((uint32_t)(P.nmma[0] >> 3) << 17);
+        const uint32_t idesc_s = idesc_t | ((uint32_t)(P.nmma[1] >> 3) << 17);
+        const uint32_t reg = it & 1u;
+        { const long long tw = p.prof ? clock64() : 0;
+          mbar_wait(t_empty_big + 8 * reg, ((it >> 1) & 1u) ^ 1u);       // this big region was drained (two tiles ago)
+          mbar_wait(t_empty_small, (it & 1u) ^ 1u);                      // the small region was drained (previous tile)
+          if (p.prof) w_t += clock64() - tw; }
+        tc_fence_after();
+        const uint32_t d_big = tmem_base + reg * p.n1, d_small = tmem_base + 2 * p.n1;
+        for (int kb = 0; kb < nkb; ++kb) {
+          { const long long tw = p.prof ? clock64() : 0; mbar_wait(full_bar + 8 * stage, phase); if (p.prof) w_x += clock64() - tw; }
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + acc * kBwPiece;
-          const bool last_piece = pc == np - 1;
-          for (int kb = 0; kb < nkb; ++kb) {
-            if (pc == 0) {
-              const long long tw = p.prof ? clock64() : 0;
-              mbar_wait(a_full + 8 * kb, (aph >> kb) & 1u);
-              if (p.prof) w_a += clock64() - tw;
-              aph ^= 1u << kb;
-            }
-            { const long long tw = p.prof ? clock64() : 0; mbar_wait(x_full + 8 * slot, phase); if (p.prof) w_x += clock64() - tw; }
-            tc_fence_after();
-            const uint64_t a_desc = make_smem_desc(sA + kb * 16384, 8192, 1024);
-            const uint64_t b_desc = make_smem_desc(sX + slot * 8192, x_lbo, 1024);
-            const int nk = kb == nkb - 1 ? last_k16 : 4;
+          const uint32_t st = sRing + stage * kBwStageSz;
+          const uint64_t a_desc = make_smem_desc(st, 8192, 1024);
+          const uint64_t b_desc = make_smem_desc(st + 16384, x_lbo, 1024);
+          const uint64_t s_desc = make_smem_desc(st + 32768, x_lbo, 1024);
+          const int nk = kb == nkb - 1 ? last_k16 : 4;
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              if (k < nk) tc_mma_elect<2>(el, d_tmem, a_desc + (uint64_t)(k * 128), b_desc + (uint64_t)(k * x_kstep), idesc, (kb > 0 || k > 0) ? 1u : 0u);
-            tc_commit_elect<2>(el, x_empty + 8 * slot);
-            if (last_piece) tc_commit_elect<2>(el, a_empty + 8 * kb);     // last piece: this k-block of A is free for the next tile
-            if (++slot == kBwRing) { slot = 0; phase ^= 1u; }
+          for (int k = 0; k < 4; ++k) {
+            if (k < nk && !(p.debug & 2)) {
+              tc_mma_elect<2>(el, d_big, a_desc + (uint64_t)(k * 128), b_desc + (uint64_t)(k * x_kstep), idesc_b, (kb > 0 || k > 0) ? 1u : 0u);
+              if (two) tc_mma_elect<2>(el, d_small, a_desc + (uint64_t)(k * 128), s_desc + (uint64_t)(k * x_kstep), idesc_s, (kb > 0 || k > 0) ? 1u : 0u);
+            }
           }
-          tc_commit_elect<2>(el, t_full + 8 * acc);
+          tc_commit_elect<2>(el, empty_bar + 8 * stage);
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
+        tc_commit_elect<2>(el, t_full + 8 * reg);
       }
-      if (p.prof && lane == 0) { unsigned long long* o = p.prof + blockIdx.x * 16; o[0] = w_a; o[1] = w_x; o[2] = w_t; o[3] = clock64() - t0; }
+      if (p.prof && lane == 0) { unsigned long long* o = p.prof + blockIdx.x * 16; o[1] = w_x; o[2] = w_t; o[3] = clock64() - t0; }
     }
   } else if (warp >= 4) {
     // ================================ epilogue (warps 4..11) ================================
     const int q = warp & 3;                          // TMEM lane quarter
     const int ew = warp - 4;
-    const int half = ew >> 2;                        // which 64 columns of a piece
-    const uint32_t stg0 = sStage + ew * 8192;
-    const uint32_t tempty_leader = mapa_rank(t_empty, 0);
-    uint32_t acc_it = 0;
+    const int half = ew >> 2;                        // this warp takes the 32-column units u = half, half + 2, ... of a piece
+    const uint32_t stg0 = sStage + half * p.sbufs * kBwStgTile;
     int sbuf = 0;
+    const uint32_t big_leader = mapa_rank(t_empty_big, 0), small_leader = mapa_rank(t_empty_small, 0);
+    uint32_t it = 0;
     long long w_f = 0; const long long t0 = p.prof ? clock64() : 0;
-    for (int t = first_tile; t < p.total_tiles; t += tile_stride) {
+    for (int t = first_tile; t < p.total_tiles; t += tile_stride, ++it) {
       const BwTile c = bw_decode(p, t);
       const BwPart& P = p.part[c.part];
       const CUtensorMap* md = c.part == 0 ? &md0 : (c.part == 1 ? &md1 : &md2);
-      const int m_loc = c.mtile * 256 + crank * 128 + q * 32;     // first head-dimension index of this warp
+      const int m_cta = c.mtile * 256 + crank * 128;              // first head-dimension index of this CTA's accumulator rows
+      const int m_loc = m_cta + q * 32;                           // ... and of this warp's
+      const float alpha = P.alpha;
+      const int Nn = P.Nn, np = P.np, store_mode = P.store_mode;
+      const uint32_t reg = it & 1u;
       float rsum = 0.f;
-      for (int pc = 0; pc < P.np; ++pc, ++acc_it) {
-        const uint32_t acc = acc_it & (kBwAcc - 1), acc_par = (acc_it >> 2) & 1u;
-        const int n_base = pc * kBwPiece + half * 64;
-        const bool active = n_base < P.Nn;             // warp-uniform
-        { const long long tw = p.prof ? clock64() : 0; mbar_wait(t_full + 8 * acc, acc_par); if (p.prof) w_f += clock64() - tw; }
-        tc_fence_after();
-        uint32_t r0[32], r1[32];
-        if (active) {
-          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kBwPiece + half * 64;
-          tc_ld32_issue(taddr, r0);
-          tc_ld32_issue(taddr + 32, r1);
+      { const long long tw = p.prof ? clock64() : 0; mbar_wait(t_full + 8 * reg, (it >> 1) & 1u); if (p.prof) w_f += clock64() - tw; }
+      tc_fence_after();
+      // the small piece first: its region is what the next tile's MMAs wait for
+      for (int pc = 1; pc >= 0; --pc) {
+        const uint32_t rel_bar = pc == 1 ? small_leader : big_leader + 8 * reg;
+        const int units = pc < np ? P.units[pc] : 0, n0 = pc < np ? P.n0[pc] : 0;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (pc == 1 ? 2 * p.n1 : reg * p.n1);
+        // this warp's units u = half, half + 2, ...: the TMEM load of the next unit is in flight while the current one is converted,
+        // staged and stored (two register buffers); the region is handed back as soon as the warp's last load has landed
+        uint32_t ra[32], rb[32];
+        auto release = [&]() {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(rel_bar);      // (both CTAs' warps arrive on the leader's barrier)
+        };
+        auto process = [&](const uint32_t (&r)[32], int u) {
+          if (p.debug & 1) { rsum += __uint_as_float(r[0]); return; }
+          const int n_base = n0 + u * 32;
+          // the four warps of this column half (one per TMEM lane quarter) fill ONE [32 n][128 m] staging tile: 256-byte rows for the
+          // TMA store instead of a 64-byte-row tile per warp
+          const uint32_t stg = stg0 + sbuf * kBwStgTile;
+          if (q == 0 && lane == 0 && !(p.debug & 64)) { if (p.sbufs == 2) bulk_wait_read1(); else bulk_wait_read0(); }   // the last store out of this buffer has read it
+          if (!(p.debug & 32)) asm volatile("bar.sync %0, 128;" ::"r"(2 + half) : "memory");
+          const uint32_t col = stg + q * 64 + lane * 2;
+          const int nv = Nn - n_base;                    // valid columns of this unit
+          if (nv >= 32) { if (alpha == 1.f) stage_unit<false, true>(r, alpha, nv, col, rsum); else stage_unit<true, true>(r, alpha, nv, col, rsum); }
+          else { if (alpha == 1.f) stage_unit<false, false>(r, alpha, nv, col, rsum); else stage_unit<true, false>(r, alpha, nv, col, rsum); }
+          fence_async_smem();
+          asm volatile("bar.sync %0, 128;" ::"r"(2 + half) : "memory");
+          if (q == 0 && lane == 0) {
+            if (store_mode == JMT_STORE) tma_store_4d(md, stg, m_cta, n_base, c.head, c.b);
+            else tma_reduce_add_4d(md, stg, m_cta, n_base, c.head, c.b);
+            bulk_commit();
+          }
+          if (p.sbufs == 2) sbuf ^= 1;
+        };
+        int u = half;
+        if (pc == 1) {
+          // small piece (<= 4 units, <= 2 per warp): all TMEM loads first, then the region goes back at once -- the next tile's MMAs
+          // wait for it (single small region), so nothing but the load latency may sit in front of the release
+          const bool h0 = u < units, h1 = u + 2 < units;
+          if (h0) tc_ld32_issue(taddr + u * 32, ra);
+          if (h1) tc_ld32_issue(taddr + (u + 2) * 32, rb);
+          if (h0) tc_wait_ld();
+          release();
+          if (h0) process(ra, u);
+          if (h1) process(rb, u + 2);
+          continue;
+        }
+        if (u < units) tc_ld32_issue(taddr + u * 32, ra);
+        else release();
+        while (u < units) {
           tc_wait_ld();
+          if (u + 2 < units) tc_ld32_issue(taddr + (u + 2) * 32, rb); else release();
+          process(ra, u);
+          u += 2;
+          if (u >= units) break;
+          tc_wait_ld();
+          if (u + 2 < units) tc_ld32_issue(taddr + (u + 2) * 32, ra); else release();
+          process(rb, u);
+          u += 2;
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(tempty_leader + 8 * acc);      // accumulator slot handed back (both CTAs' warps arrive)
-        if (!active) continue;
-        const uint32_t stg = stg0 + sbuf * 4096;
-        if (lane == 0) bulk_wait_read1();              // the store issued two pieces ago has finished reading this buffer
-        __syncwarp();
-        const uint32_t col = stg + lane * 2;
-        const int nv = P.Nn - n_base;                  // valid columns of this warp's 64
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float v = P.alpha * __uint_as_float(r0[j]);
-          if (j < nv) rsum += v;
-          st_shared_u16(col + j * 64, __bfloat16_as_ushort(__float2bfloat16_rn(v)));
-        }
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float v = P.alpha * __uint_as_float(r1[j]);
-          if (32 + j < nv) rsum += v;
-          st_shared_u16(col + (32 + j) * 64, __bfloat16_as_ushort(__float2bfloat16_rn(v)));
-        }
-        fence_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          if (P.store_mode == JMT_STORE) tma_store_4d(md, stg, m_loc, n_base, c.head, c.b);
-          else tma_reduce_add_4d(md, stg, m_loc, n_base, c.head, c.b);
-          bulk_commit();
-        }
-        sbuf ^= 1;
       }
-      if (P.colsum != nullptr) atomicAdd(csum_sh + c.part * kBwCsumMax + c.head * p.dh + m_loc + lane, rsum);
+      if (P.colsum != nullptr) atomicAdd(csum_sh + c.part * p.csum_stride + c.head * p.dh + m_loc + lane, rsum);
     }
-    if (lane == 0) bulk_wait0();
+    if (q == 0 && lane == 0) bulk_wait0();
     // flush the bias-gradient column sums: one global atomic per entry and CTA
     asm volatile("bar.sync 1, %0;" ::"n"(32 * kBwEpiWarps) : "memory");
     for (int pa = 0; pa < p.nparts; ++pa) {
       float* dst = p.part[pa].colsum;
       if (dst == nullptr) continue;
       for (int i = threadIdx.x - 128; i < p.csum_len; i += 32 * kBwEpiWarps) {
-        const float v = csum_sh[pa * kBwCsumMax + i];
+        const float v = csum_sh[pa * p.csum_stride + i];
         if (v != 0.f) atomicAdd(dst + i, v);
       }
     }
@@ -282,7 +331,7 @@ attn_bwd_dqkv_kernel(const __grid_constant__ CUtensorMap ma0, const __grid_const
   }
 }
 
-// transposed-output tensor map: out(n, m) of (head, batch) at ptr + b*bs + h*hs + n*ld + m; box {32 m, 64 n}, no swizzle
+// transposed-output tensor map: out(n, m) of (head, batch) at ptr + b*bs + h*hs + n*ld + m; box {128 m, 32 n}, no swizzle
 static int make_map_dt(CUtensorMap* map, const void* ptr, int64_t inner, int64_t rows, int64_t ld, int64_t nb0, int64_t bs0,
                        int64_t nb1, int64_t bs1, const char* who) {
   EncodeTiledFn enc = get_encode_fn();
@@ -292,7 +341,7 @@ static int make_map_dt(CUtensorMap* map, const void* ptr, int64_t inner, int64_t
   const cuuint64_t dims[4] = {(cuuint64_t)inner, (cuuint64_t)rows, (cuuint64_t)nb0, (cuuint64_t)nb1};
   const cuuint64_t row_bytes = (cuuint64_t)ld * 2;
   const cuuint64_t strides[3] = {row_bytes, nb0 > 1 ? (cuuint64_t)bs0 * 2 : row_bytes, nb1 > 1 ? (cuuint64_t)bs1 * 2 : row_bytes};
-  const cuuint32_t box[4] = {32, 64, 1, 1};
+  const cuuint32_t box[4] = {128, 32, 1, 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -335,7 +384,10 @@ extern "C" int jmt_attn_bwd_dqkv_bf16(const jmt_attn_bwd_desc* g, void* stream) 
   BwParams p;
   memset(&p, 0, sizeof(p));
   CUtensorMap ma[3], mx[3], md[3];
-  static const int narrow_env = []() { const char* e = getenv("JMT_DQKV_NARROW"); return e ? atoi(e) : 2; }();
+  // accumulator geometry common to all parts: big slots of n1 columns at TMEM columns 0 and n1, the small slot behind them
+  const int lmax = g->Lq > g->S ? g->Lq : g->S;
+  const int rmax = (lmax + 31) / 32 * 32;
+  p.n1 = rmax <= 256 ? 256 : 512 - rmax;
   int np_ = 0;
   for (int i = 0; i < 3; ++i) {
     const jmt_attn_bwd_part& s = g->part[i];
@@ -347,20 +399,27 @@ extern "C" int jmt_attn_bwd_dqkv_bf16(const jmt_attn_bwd_desc* g, void* stream) 
     P.Nn = P.trans ? g->S : g->Lq;
     P.Kk = P.trans ? g->Lq : g->S;
     P.nkb = (P.Kk + 63) / 64;
-    P.np = (P.Nn + kBwPiece - 1) / kBwPiece;
     P.last_k16 = (P.Kk - 64 * (P.nkb - 1) + 15) / 16;
-    P.n_last = kBwPiece;
+    // pieces: one big piece when the extent fits a big slot, else big + small; an MMA's N covers the valid columns rounded up to 16
+    P.np = P.Nn <= p.n1 ? 1 : 2;
+    for (int pc = 0; pc < P.np; ++pc) {
+      P.n0[pc] = pc * p.n1;
+      const int cols = (pc == P.np - 1 ? P.Nn : p.n1) - P.n0[pc];
+      P.nmma[pc] = (cols + 15) / 16 * 16;
+      P.units[pc] = (cols + 31) / 32;
+    }
     {
-      const int rem = (P.Nn - kBwPiece * (P.np - 1) + 15) / 16 * 16;      // columns the last piece needs (multiple of 16)
-      if (narrow_env >= 2 || (narrow_env == 1 && !P.trans)) P.n_last = rem;
+      const int hb = P.nmma[0] / 2, hs = P.np > 1 ? P.nmma[1] / 2 : 0;
+      P.tx_bytes = 16384u + (P.trans ? (uint32_t)(((hb + 63) / 64 + (hs + 63) / 64) * 8192) : (uint32_t)(((hb + 31) / 32 + (hs + 31) / 32) * 4096));
     }
     P.store_mode = s.store_mode;
     P.alpha = s.alpha;
     P.colsum = s.colsum;
     int rc = make_map_mn5(&ma[np_], s.a, g->dh, P.Kk, s.a_ld, g->heads, s.a_hs, g->NB, s.a_bs, 64, 2, "jmt_attn_bwd_dqkv_bf16(A)");
     if (rc != JMT_OK) return rc;
-    rc = make_map(&mx[np_], s.x, g->S, g->Lq, g->x_ld, g->heads, (int64_t)g->Lq * g->x_ld, g->NB, (int64_t)g->heads * g->Lq * g->x_ld, 64,
-                  "jmt_attn_bwd_dqkv_bf16(X)");
+    // X: MN-major parts fetch [64 k rows][64 columns] chunks, the K-major part [32 n rows][64 k] boxes
+    rc = make_map(&mx[np_], s.x, g->S, g->Lq, g->x_ld, g->heads, (int64_t)g->Lq * g->x_ld, g->NB, (int64_t)g->heads * g->Lq * g->x_ld,
+                  P.trans ? 64 : 32, "jmt_attn_bwd_dqkv_bf16(X)");
     if (rc != JMT_OK) return rc;
     rc = make_map_dt(&md[np_], s.d, g->dh, P.Nn, s.d_ld, g->heads, s.d_hs, g->NB, s.d_bs, "jmt_attn_bwd_dqkv_bf16(D)");
     if (rc != JMT_OK) return rc;
@@ -380,8 +439,18 @@ extern "C" int jmt_attn_bwd_dqkv_bf16(const jmt_attn_bwd_desc* g, void* stream) 
   // fp32 accumulate, bf16 A / B, A MN-major, M = 256 (cta_group::2); N and the B major are set per piece
   p.idesc_base = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | ((uint32_t)(256 >> 4) << 24);
   p.prof = g_bw_prof.load();
+  { static const int dbg = []() { const char* e = getenv("JMT_DQKV_DEBUG"); return e ? atoi(e) : 0; }(); p.debug = dbg; }
 
-  const int smem = kBwABytes + kBwRing * 8192 + kBwStageBytes + 3 * kBwCsumMax * 4 + 512;
+  // shared memory plan: 4 pipeline stages + two staging tiles per column half.  (JMT_DQKV_STAGES=5: 5 stages + one staging tile when
+  // the column-sum area is small -- measured slower, 102 vs 97 us: the single staging tile makes the epilogue the bottleneck.)
+  p.csum_stride = (p.csum_len + 63) / 64 * 64;
+  {
+    static const int st_env = []() { const char* e = getenv("JMT_DQKV_STAGES"); return e ? atoi(e) : 4; }();
+    const int budget = 227 * 1024 - 512 - 3 * p.csum_stride * 4;
+    p.stages = 4; p.sbufs = 2;
+    if (st_env == 5 && 5 * kBwStageSz + 2 * kBwStgTile <= budget) { p.stages = 5; p.sbufs = 1; }
+  }
+  const int smem = p.stages * kBwStageSz + 2 * p.sbufs * kBwStgTile + 3 * p.csum_stride * 4 + 512;
   static std::atomic<int> attr_set[64];
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); set_error("jmt_attn_bwd_dqkv_bf16: no CUDA device"); return JMT_ERR_CUDA; }

@@ -320,8 +320,9 @@ attn_chain_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ================================ TMA producer ================================
+    {
+      // ================================ TMA producer (whole warp, one elected lane issues) ================================
+      const uint32_t el = elect_one();
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a1)) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b1)) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b2)) : "memory");
@@ -339,12 +340,12 @@ attn_chain_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
             const uint32_t fb = full_bar + 8 * slot;
             const uint32_t dst = sRing + slot * p.slot_bytes;
             if (s == 0) {
-              mbar_expect_tx(fb, 16384 + p.b1_bytes);
-              tma_load_4d(dst, &map_a1, fb, kb * kBlockK, c.q0, c.head, c.b);
-              tma_load_4d(dst + 16384, &map_b1, fb, kb * kBlockK, 0, c.head, c.b);
+              mbar_expect_tx_el(el, fb, 16384 + p.b1_bytes);
+              tma_load_4d_el(el, dst, &map_a1, fb, kb * kBlockK, c.q0, c.head, c.b);
+              tma_load_4d_el(el, dst + 16384, &map_b1, fb, kb * kBlockK, 0, c.head, c.b);
             } else {
-              mbar_expect_tx(fb, p.b1_bytes);
-              tma_load_4d(dst, &map_b1, fb, kb * kBlockK, p.n1, c.head, c.b);
+              mbar_expect_tx_el(el, fb, p.b1_bytes);
+              tma_load_4d_el(el, dst, &map_b1, fb, kb * kBlockK, p.n1, c.head, c.b);
             }
             if (++slot == p.slots) { slot = 0; phase ^= 1; }
           }
@@ -356,16 +357,17 @@ attn_chain_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
             if (p.prof) pw += clock64() - tw;
             const uint32_t fb = full_bar + 8 * slot;
             const uint32_t dst = sRing + slot * p.slot_bytes;
-            mbar_expect_tx(fb, p.b2_bytes);
-            tma_load_5d(dst, &map_b2, fb, 0, kb * kBlockK, nh * b2_chunks, c.head, c.b);     // all n2 / 64 chunks in one instruction
+            mbar_expect_tx_el(el, fb, p.b2_bytes);
+            tma_load_5d_el(el, dst, &map_b2, fb, 0, kb * kBlockK, nh * b2_chunks, c.head, c.b);     // all n2 / 64 chunks in one instruction
             if (++slot == p.slots) { slot = 0; phase ^= 1; }
           }
       }
-      if (p.prof) { p.prof[blockIdx.x * 16 + 0] = pw; p.prof[blockIdx.x * 16 + 1] = clock64() - pt0; }
+      if (p.prof && lane == 0) { p.prof[blockIdx.x * 16 + 0] = pw; p.prof[blockIdx.x * 16 + 1] = clock64() - pt0; }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ================================ MMA issuer ================================
+    {
+      // ================================ MMA issuer (whole warp, one elected lane issues) ================================
+      const uint32_t el = elect_one();
       int slot = 0; uint32_t phase = 0;
       int tile_iter = 0;
       long long mw1 = 0, mw2 = 0, mwx = 0, mwe = 0; const long long mt0 = p.prof ? clock64() : 0;
@@ -383,7 +385,7 @@ attn_chain_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
           const uint64_t b_desc = make_smem_desc(st + 16384, 16, 1024);
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; ++k)
-            tc_mma<1>(tmem_base, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), p.idesc1, (kb > 0 || k > 0) ? 1u : 0u);
+            tc_mma_elect<1>(el, tmem_base, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), p.idesc1, (kb > 0 || k > 0) ? 1u : 0u);
           if (++slot == p.slots) { slot = 0; phase ^= 1; }
           if (p.nsplit1 == 2) {
             AT_TIMED_WAIT(mw1, full_bar + 8 * slot, phase);
@@ -391,15 +393,15 @@ attn_chain_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
             const uint64_t b2_desc = make_smem_desc(sRing + slot * p.slot_bytes, 16, 1024);
 #pragma unroll
             for (int k = 0; k < kBlockK / kUmmaK; ++k)
-              tc_mma<1>(tmem_base + p.n1, a_desc + (uint64_t)(k * 2), b2_desc + (uint64_t)(k * 2), p.idesc1, (kb > 0 || k > 0) ? 1u : 0u);
-            tc_commit<1>(empty_bar + 8 * slot_a);             // the A tile is shared by both groups: freed only now
-            tc_commit<1>(empty_bar + 8 * slot);
+              tc_mma_elect<1>(el, tmem_base + p.n1, a_desc + (uint64_t)(k * 2), b2_desc + (uint64_t)(k * 2), p.idesc1, (kb > 0 || k > 0) ? 1u : 0u);
+            tc_commit_elect<1>(el, empty_bar + 8 * slot_a);             // the A tile is shared by both groups: freed only now
+            tc_commit_elect<1>(el, empty_bar + 8 * slot);
             if (++slot == p.slots) { slot = 0; phase ^= 1; }
           } else {
-            tc_commit<1>(empty_bar + 8 * slot_a);
+            tc_commit_elect<1>(el, empty_bar + 8 * slot_a);
           }
         }
-        tc_commit<1>(t1_full);
+        tc_commit_elect<1>(el, t1_full);
         AT_TIMED_WAIT(mwx, x_ready, par);                     // X (P or dS) is in shared memory, T1 is dead
         tc_fence_after();
         if (p.skip2) continue;                                // T1 has been consumed (x_ready): next tile's GEMM1 may overwrite it
@@ -411,14 +413,14 @@ attn_chain_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
             const uint64_t b_desc = make_smem_desc(sRing + slot * p.slot_bytes, 8192, 1024);
 #pragma unroll
             for (int k = 0; k < kBlockK / kUmmaK; ++k)
-              tc_mma<1>(tmem_base + nh * p.n2, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 128), p.idesc2,
+              tc_mma_elect<1>(el, tmem_base + nh * p.n2, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 128), p.idesc2,
                         (kb > 0 || k > 0) ? 1u : 0u);
-            tc_commit<1>(empty_bar + 8 * slot);
+            tc_commit_elect<1>(el, empty_bar + 8 * slot);
             if (++slot == p.slots) { slot = 0; phase ^= 1; }
           }
-        tc_commit<1>(t2_full);
+        tc_commit_elect<1>(el, t2_full);
       }
-      if (p.prof) {
+      if (p.prof && lane == 0) {
         unsigned long long* o = p.prof + blockIdx.x * 16;
         o[2] = mw1; o[3] = mw2; o[4] = mwx; o[5] = mwe; o[6] = clock64() - mt0;
       }
