@@ -418,17 +418,20 @@ def main():
         att = [r for r in rec if r[0] == "attn_chain_kernel"]
         att_ms = sum(r[2].elapsed_time(r[3]) for r in att)
         att_fl = sum(r[1] for r in att)
+        dq = [r for r in rec if r[0] == "attn_bwd_dqkv_kernel"]        # dQ / dK / dV of the attention backward (DRAM-bound)
+        dq_ms = sum(r[2].elapsed_time(r[3]) for r in dq)
+        dq_fl = sum(r[1] for r in dq)
         # DRAM traffic of the dominant kernel's most frequent launch (76800x512x512 linear, 40 of 147 GEMM launches per step)
         # from the committed `ncu --set full` capture; algorithmic bytes of that launch = A + W + D = 157.8 MB
         traffic, traffic_src = None, None
-        tpath = os.path.join(ROOT, "profiles", "ncu_gemm_tc_r2p_linear_76800x512x512.csv")
+        tpath = os.path.join(ROOT, "profiles", "ncu_gemm_tc_r3e_linear_76800x512x512.csv")
         if kname == "gemm_tc_kernel" and os.path.exists(tpath):
             import csv
             rows = {r[0]: r for r in csv.reader(open(tpath)) if len(r) == 3}
             mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
             try:
                 traffic = sum(float(rows[k][2]) * mult[rows[k][1]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
-                traffic_src = "profiles/ncu_gemm_tc_r2p_linear_76800x512x512.csv (dram read+write of one 76800x512x512 launch; algorithmic 157.8e6 B)"
+                traffic_src = "profiles/ncu_gemm_tc_r3e_linear_76800x512x512.csv (dram read+write of one 76800x512x512 launch; algorithmic 157.8e6 B)"
             except (KeyError, ValueError):
                 traffic = None
         roof = {"bound": "tensor", "kernel": kname, "achieved": ach, "peak": peak, "unit": "TFLOP/s",
@@ -441,7 +444,12 @@ def main():
                 "attn_chain_kernel": {"launches_per_step": len(att) // nprof, "ms_per_step": att_ms / nprof,
                                       "gflop_per_step": att_fl / nprof / 1e9,
                                       "achieved_tflops": att_fl / (att_ms / 1e3) / 1e12 if att_ms > 0 else 0.0},
-                "tensor_kernels_tflops": (tot_fl + att_fl) / ((tot_ms + att_ms) / 1e3) / 1e12 if tot_ms + att_ms > 0 else 0.0}
+                "attn_bwd_dqkv_kernel": {"launches_per_step": len(dq) // nprof, "ms_per_step": dq_ms / nprof,
+                                         "gflop_per_step": dq_fl / nprof / 1e9,
+                                         "achieved_tflops": dq_fl / (dq_ms / 1e3) / 1e12 if dq_ms > 0 else 0.0,
+                                         "bound": "hbm", "dram_mb_per_launch_algorithmic": 564.0},
+                "tensor_kernels_tflops": ((tot_fl + att_fl + dq_fl) / ((tot_ms + att_ms + dq_ms) / 1e3) / 1e12
+                                          if tot_ms + att_ms + dq_ms > 0 else 0.0)}
         if args.gemm_table and rank == 0:
             agg = {}
             for r in rec:
