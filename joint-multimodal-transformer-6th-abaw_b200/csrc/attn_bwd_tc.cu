@@ -111,7 +111,7 @@ attn_bwd_dqkv_kernel(const __grid_constant__ CUtensorMap ma0, const __grid_const
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - base));
   float* csum_sh = reinterpret_cast<float*>(smem_raw + (sCsum - base));
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // (shfl: lets ptxas treat the warp index as warp-uniform)
   const int crank = (int)cluster_ctarank();
   const int first_tile = blockIdx.x >> 1, tile_stride = gridDim.x >> 1;
 

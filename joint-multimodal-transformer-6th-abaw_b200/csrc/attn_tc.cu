@@ -301,7 +301,7 @@ attn_chain_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_aligned + (tmem_slot - base));
   float* red = reinterpret_cast<float*>(smem_aligned + (sRed - base));     // [0..255] max / dot, [256..511] sum
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // (shfl: lets ptxas treat the warp index as warp-uniform)
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.slots; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }

@@ -179,6 +179,7 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int t, int c
 
 struct EpiCtx {
   uint32_t tbase, stage_smem, row_smem, sw;
+  uint32_t el;                // 1 in the warp's elected lane (issues / commits / waits for this warp's TMA stores), else 0
   const float* bias;          // this tile's bias slice in shared memory (zeros when there is none)
   const uint32_t* fwords;     // MASK: this thread's sample's keep-flag words (one bit per column of the tile, shared memory)
   uint32_t keep;              // 0 when this thread's output row must be written as zeros, else ~0
@@ -238,7 +239,7 @@ __device__ __forceinline__ bool epi_tile(const TcParams& p, const CUtensorMap* t
         epi_math_bf16<ACT, MASK>(r, e.bias + c0, MASK ? e.fwords[c0 >> 5] : 0u, p.colmask_scale, e.keep, p.alpha, p.slope, pk);
         if (second) tc_ld32_issue(e.tbase + c0 + 32, r);
         EPI_T(1);
-        if (lane == 0) bulk_wait_read0();       // previous TMA store has finished reading the staging tile
+        bulk_wait_read0_el(e.el);       // previous TMA store has finished reading the staging tile
         __syncwarp();
         EPI_T(2);
 #pragma unroll
@@ -263,10 +264,10 @@ __device__ __forceinline__ bool epi_tile(const TcParams& p, const CUtensorMap* t
         EPI_T(4);
         fence_async_smem();
         __syncwarp();
-        if (lane == 0 && warp_rows_valid) {
-          if (p.store_mode == JMT_STORE) tma_store_4d(tma_d, e.stage_smem, e.n0 + c0, e.m0w, e.b0, e.b1);
-          else tma_reduce_add_4d(tma_d, e.stage_smem, e.n0 + c0, e.m0w, e.b0, e.b1);
-          bulk_commit();
+        {
+          const uint32_t elv = warp_rows_valid ? e.el : 0u;
+          if (p.store_mode == JMT_STORE) tma_store_4d_el(elv, tma_d, e.stage_smem, e.n0 + c0, e.m0w, e.b0, e.b1);
+          else tma_reduce_add_4d_el(elv, tma_d, e.stage_smem, e.n0 + c0, e.m0w, e.b0, e.b1);
         }
         EPI_T(5);
       }
@@ -279,17 +280,17 @@ __device__ __forceinline__ bool epi_tile(const TcParams& p, const CUtensorMap* t
         if (e.tempty_mid != 0u && c0 < 256 && c_next >= 256) epi_release<kCta>(e.tempty_mid, lane);   // accumulator half 0 drained
         if (c_next >= e.bn || e.n0 + c_next >= p.N) { epi_release<kCta>(e.tempty, lane); released = true; }
         epi_math_f32<ACT, MASK>(r, e.bias + c0, MASK ? e.fwords[c0 >> 5] : 0u, p.colmask_scale, e.keep, p.alpha, p.slope);
-        if (lane == 0) bulk_wait_read0();
+        bulk_wait_read0_el(e.el);
         __syncwarp();
 #pragma unroll
         for (int ch = 0; ch < 8; ++ch)
           st_shared_v4(e.row_smem + ((ch ^ e.sw) << 4), r[4 * ch], r[4 * ch + 1], r[4 * ch + 2], r[4 * ch + 3]);
         fence_async_smem();
         __syncwarp();
-        if (lane == 0 && warp_rows_valid) {
-          if (p.store_mode == JMT_STORE) tma_store_4d(tma_d, e.stage_smem, e.n0 + c0, e.m0w, e.b0, e.b1);
-          else tma_reduce_add_4d(tma_d, e.stage_smem, e.n0 + c0, e.m0w, e.b0, e.b1);
-          bulk_commit();
+        {
+          const uint32_t elv = warp_rows_valid ? e.el : 0u;
+          if (p.store_mode == JMT_STORE) tma_store_4d_el(elv, tma_d, e.stage_smem, e.n0 + c0, e.m0w, e.b0, e.b1);
+          else tma_reduce_add_4d_el(elv, tma_d, e.stage_smem, e.n0 + c0, e.m0w, e.b0, e.b1);
         }
       }
     }
@@ -468,7 +469,7 @@ __device__ __forceinline__ bool epi_tile_ext(const TcParams& p, const CUtensorMa
       v1 = ext_load_aux(p, e, xr, aux_aligned, c0 + 32, ax1);
     }
     ext_half<MASK, CSUM>(p, e, xr, r, ax0, v0, c0, pk);
-    if (lane == 0) bulk_wait_read0();       // previous TMA store has finished reading the staging tile
+    bulk_wait_read0_el(e.el);       // previous TMA store has finished reading the staging tile
     __syncwarp();
 #pragma unroll
     for (int ch = 0; ch < 4; ++ch)
@@ -489,10 +490,10 @@ __device__ __forceinline__ bool epi_tile_ext(const TcParams& p, const CUtensorMa
       st_shared_v4(e.row_smem + (((uint32_t)(ch + 4) ^ e.sw) << 4), pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
     fence_async_smem();
     __syncwarp();
-    if (lane == 0 && warp_rows_valid) {
-      if (p.store_mode == JMT_STORE) tma_store_4d(tma_d, e.stage_smem, e.n0 + c0, e.m0w, e.b0, e.b1);
-      else tma_reduce_add_4d(tma_d, e.stage_smem, e.n0 + c0, e.m0w, e.b0, e.b1);
-      bulk_commit();
+    {
+      const uint32_t elv = warp_rows_valid ? e.el : 0u;
+      if (p.store_mode == JMT_STORE) tma_store_4d_el(elv, tma_d, e.stage_smem, e.n0 + c0, e.m0w, e.b0, e.b1);
+      else tma_reduce_add_4d_el(elv, tma_d, e.stage_smem, e.n0 + c0, e.m0w, e.b0, e.b1);
     }
   }
   return released;
@@ -527,7 +528,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a_hi, const __grid_consta
   uint8_t* smem_aligned = smem_raw + (smem_base - smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_aligned + (tmem_slot - smem_base));
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // (shfl: lets ptxas treat the warp index as warp-uniform)
   const int crank = kCta == 2 ? (int)cluster_ctarank() : 0;
   const int first_tile = blockIdx.x / kCta;          // tile (pair) index owned by this CTA's cluster
   const int tile_stride = gridDim.x / kCta;
@@ -765,6 +766,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a_hi, const __grid_consta
     const uint32_t stage_smem = sD + ew * kEpiStageBytes;
     float* bias_ptr = reinterpret_cast<float*>(smem_aligned + (sBias - smem_base));
     const int et = threadIdx.x - 64;              // index among the epilogue threads
+    const uint32_t epi_el = elect_one();          // the lane that issues, commits and waits for this warp's TMA stores
     const uint32_t row_smem = stage_smem + lane * 128;
     const uint32_t sw = lane & 7;                 // 128B-swizzle phase of this thread's staging row
     const uint32_t tempty_leader = kCta == 2 ? mapa_rank(tempty_bar, 0) : tempty_bar;
@@ -818,7 +820,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a_hi, const __grid_consta
       p.fd_nb0.divmod((uint32_t)c.batch, b1u, b0u);
       EpiCtx ec;
       ec.tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kAccStride);
-      ec.stage_smem = stage_smem; ec.row_smem = row_smem; ec.sw = sw; ec.bias = bias_tile;
+      ec.stage_smem = stage_smem; ec.row_smem = row_smem; ec.sw = sw; ec.bias = bias_tile; ec.el = epi_el;
       {
         const uint32_t m = (uint32_t)(c.m0 + q * 32 + lane);
         ec.keep = ~0u;
@@ -865,7 +867,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a_hi, const __grid_consta
         if (v != 0.f) atomicAdd(p.colsum + i, v);
       }
     }
-    if (lane == 0) bulk_wait0();                   // all TMA stores of this warp have completed
+    bulk_wait0_el(epi_el);                         // all TMA stores of this warp have completed
 #ifdef JMT_EPI_PROF
     if (blockIdx.x == 0 && threadIdx.x == 64) for (int i = 0; i < 6; ++i) g_epi_prof[i] = (unsigned long long)eprof[i];
 #endif

@@ -248,6 +248,28 @@ __device__ __forceinline__ void tma_load_5d_2sm_el(uint32_t el, uint32_t dst, co
       "@q cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];\n\t}"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(el) : "memory");
 }
+// elected-lane TMA stores (epilogue warps: the whole warp computes the warp-uniform coordinates, lane `el` issues, commits and waits)
+__device__ __forceinline__ void tma_store_4d_el(uint32_t el, const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %6, 0;\n\t"
+               "@q cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];\n\t"
+               "@q cp.async.bulk.commit_group;\n\t}"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(el) : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_4d_el(uint32_t el, const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %6, 0;\n\t"
+               "@q cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];\n\t"
+               "@q cp.async.bulk.commit_group;\n\t}"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(el) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_read0_el(uint32_t el) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %0, 0;\n\t@q cp.async.bulk.wait_group.read 0;\n\t}" ::"r"(el) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_read1_el(uint32_t el) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %0, 0;\n\t@q cp.async.bulk.wait_group.read 1;\n\t}" ::"r"(el) : "memory");
+}
+__device__ __forceinline__ void bulk_wait0_el(uint32_t el) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %0, 0;\n\t@q cp.async.bulk.wait_group 0;\n\t}" ::"r"(el) : "memory");
+}
 // 32 lanes x 32 columns of fp32 accumulators -> 32 registers per thread (thread = TMEM lane = output row).
 // Issue only; tc_wait_ld() must precede the first use of r[] (several loads can be in flight).
 __device__ __forceinline__ void tc_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
