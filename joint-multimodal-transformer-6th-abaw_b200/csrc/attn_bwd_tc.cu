@@ -231,6 +231,7 @@ attn_bwd_dqkv_kernel(const __grid_constant__ CUtensorMap ma0, const __grid_const
     const uint32_t stg0 = sStage + half * p.sbufs * kBwStgTile;
     int sbuf = 0;
     const uint32_t big_leader = mapa_rank(t_empty_big, 0), small_leader = mapa_rank(t_empty_small, 0);
+    const uint32_t el = q == 0 ? elect_one() : 0u;   // one lane of the quarter-0 warp issues / commits / waits for the column half's TMA stores
     uint32_t it = 0;
     long long w_f = 0; const long long t0 = p.prof ? clock64() : 0;
     for (int t = first_tile; t < p.total_tiles; t += tile_stride, ++it) {
@@ -264,19 +265,16 @@ attn_bwd_dqkv_kernel(const __grid_constant__ CUtensorMap ma0, const __grid_const
           // the four warps of this column half (one per TMEM lane quarter) fill ONE [32 n][128 m] staging tile: 256-byte rows for the
           // TMA store instead of a 64-byte-row tile per warp
           const uint32_t stg = stg0 + sbuf * kBwStgTile;
-          if (q == 0 && lane == 0 && !(p.debug & 64)) { if (p.sbufs == 2) bulk_wait_read1(); else bulk_wait_read0(); }   // the last store out of this buffer has read it
-          if (!(p.debug & 32)) asm volatile("bar.sync %0, 128;" ::"r"(2 + half) : "memory");
+          if (p.sbufs == 2) bulk_wait_read1_el(el); else bulk_wait_read0_el(el);      // the last store out of this buffer has read it
+          asm volatile("bar.sync %0, 128;" ::"r"(2 + half) : "memory");
           const uint32_t col = stg + q * 64 + lane * 2;
           const int nv = Nn - n_base;                    // valid columns of this unit
           if (nv >= 32) { if (alpha == 1.f) stage_unit<false, true>(r, alpha, nv, col, rsum); else stage_unit<true, true>(r, alpha, nv, col, rsum); }
           else { if (alpha == 1.f) stage_unit<false, false>(r, alpha, nv, col, rsum); else stage_unit<true, false>(r, alpha, nv, col, rsum); }
           fence_async_smem();
           asm volatile("bar.sync %0, 128;" ::"r"(2 + half) : "memory");
-          if (q == 0 && lane == 0) {
-            if (store_mode == JMT_STORE) tma_store_4d(md, stg, m_cta, n_base, c.head, c.b);
-            else tma_reduce_add_4d(md, stg, m_cta, n_base, c.head, c.b);
-            bulk_commit();
-          }
+          if (store_mode == JMT_STORE) tma_store_4d_el(el, md, stg, m_cta, n_base, c.head, c.b);
+          else tma_reduce_add_4d_el(el, md, stg, m_cta, n_base, c.head, c.b);
           if (p.sbufs == 2) sbuf ^= 1;
         };
         int u = half;
@@ -308,7 +306,7 @@ attn_bwd_dqkv_kernel(const __grid_constant__ CUtensorMap ma0, const __grid_const
       }
       if (P.colsum != nullptr) atomicAdd(csum_sh + c.part * p.csum_stride + c.head * p.dh + m_loc + lane, rsum);
     }
-    if (q == 0 && lane == 0) bulk_wait0();
+    bulk_wait0_el(el);
     // flush the bias-gradient column sums: one global atomic per entry and CTA
     asm volatile("bar.sync 1, %0;" ::"n"(32 * kBwEpiWarps) : "memory");
     for (int pa = 0; pa < p.nparts; ++pa) {
