@@ -144,6 +144,11 @@ int jmt_split_bf16x2(const float* x, void* hi, void* lo, int64_t n, void* stream
 /* Debug aid (no reference counterpart): when dev_buf != NULL (device buffer of 148*16 uint64) every later
  * jmt_gemm_bf16 launch overwrites per-CTA cycle counters of its TMA / MMA / epilogue roles; NULL disables. */
 int jmt_gemm_set_profile_buffer(void* dev_buf);
+/* B-stationary scheduling of jmt_gemm_bf16 for short-K linears (K <= 512, N % 256 == 0, one tap, no batch): every CTA pair keeps
+ * its 256-column slice of B resident in shared memory and streams only A (csrc/gemm_tc.cu, TcParams::bres).  Results are
+ * independent of the mode.  mode: -1 = environment (JMT_GEMM_BRES, default automatic), 0 = off, 1 = automatic (large M only),
+ * 2 = whenever the geometry allows (tests).  Returns the previous mode. */
+int jmt_gemm_set_bres_mode(int mode);
 
 /* ------------------------------------------------------------------------------------------ *
  * Fused attention core (bf16, tcgen05): two chained GEMMs with the row-wise softmax algebra between them.

@@ -82,6 +82,7 @@ SIGNATURES = {
     "jmt_gemm_bf16x3": [C.POINTER(GemmDesc), _P, _P, _P],
     "jmt_split_bf16x2": [_P, _P, _P, _L, _P],
     "jmt_gemm_set_profile_buffer": [_P],
+    "jmt_gemm_set_bres_mode": [_I],
     "jmt_attn_chain_supported": [C.POINTER(AttnDesc)],
     "jmt_attn_chain_bf16": [C.POINTER(AttnDesc), _P],
     "jmt_attn_set_profile_buffer": [_P],

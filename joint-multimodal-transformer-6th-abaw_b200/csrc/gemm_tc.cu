@@ -90,6 +90,12 @@ struct TcParams {
   FastDiv fd_tsplit;
   unsigned long long* prof;   // optional per-CTA cycle counters (16 per CTA), see jmt_gemm_set_profile_buffer
   int tma_store;      // epilogue through swizzled smem + TMA store / reduce-add (needs 16-byte aligned D geometry)
+  int l2_ahead, l2_mstep;   // bres: L2 prefetch distance in tiles of this pair, and the M distance of two consecutive tiles of a pair
+  int bres;           // B-stationary pairs (K <= 512, N % 256 == 0, no taps / batches): every CTA pair keeps ITS 256-column slice of B (all
+                      // k-blocks, <= 128 KB per CTA) resident in shared memory for the whole launch and streams only A.  The K = 512 linears are
+                      // bound by what an SM ingests from L2 (narrow tiles: 32 KB per 128x256x64 block, 60 % of the issuer's time waiting for
+                      // operands) or by the un-overlapped epilogue (wide tiles, one accumulator stage); with B resident a block costs 16 KB and the
+                      // two 256-column accumulator stages keep the epilogue under the next tile's mainloop
 };
 
 template <int ACT>
@@ -516,15 +522,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a_hi, const __grid_consta
   const uint32_t smem_base = smem_u32(smem_raw);
   if ((smem_base & 1023u) != 0u) __trap();
   constexpr int kOps = kX3 ? 2 : 1;                          // tiles per operand and stage (hi | lo)
-  const uint32_t a_stride = kOps * kAStageBytes, b_stride = kOps * p.b_stage_bytes;
+  const uint32_t a_stride = kOps * kAStageBytes, b_stride = p.bres ? 0u : kOps * p.b_stage_bytes;
   const uint32_t sA = smem_base;
-  const uint32_t sB = sA + p.stages * a_stride;
-  const uint32_t sD = sB + p.stages * b_stride;              // epilogue warps x 4 KiB staging (1024-aligned)
+  const uint32_t sB = sA + p.stages * a_stride;              // ring of B tiles, or (bres) this CTA's resident B slice: kblocks tiles
+  const uint32_t sD = sB + (p.bres ? p.kblocks * p.b_stage_bytes : p.stages * b_stride);   // epilogue warps x 4 KiB staging (1024-aligned)
   const uint32_t sBias = sD + kEpi * kEpiStageBytes;         // 256 floats: this tile's bias slice
   const uint32_t bars = sBias + kBiasFlagBytes;              // 8-byte aligned (behind the bias tile and the keep-flag words)
   const uint32_t full_bar = bars, empty_bar = bars + 8 * kMaxStages;
   const uint32_t tfull_bar = bars + 16 * kMaxStages, tempty_bar = tfull_bar + 16;
   const uint32_t tmem_slot = tempty_bar + 16;
+  const uint32_t bres_bar = tmem_slot + 8;                   // resident B slice has landed (bres)
   uint8_t* smem_aligned = smem_raw + (smem_base - smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_aligned + (tmem_slot - smem_base));
 
@@ -538,6 +545,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a_hi, const __grid_consta
     // (multicast to both CTAs); tempty: every epilogue warp of every CTA of the pair (on the leader's barrier)
     for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar + 8 * s, kCta); mbar_init(empty_bar + 8 * s, 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar + 8 * s, 1); mbar_init(tempty_bar + 8 * s, kEpi * kCta); }
+    mbar_init(bres_bar, kCta);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -575,6 +583,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a_hi, const __grid_consta
       const int b_chunks = p.b_chunks_cta;                    // 64-wide MN chunks staged by this CTA
       const int n_off = crank * (p.block_n / kCta);           // this CTA's half of the B tile (kCta == 2)
       const uint32_t full_leader = kCta == 2 ? mapa_rank(full_bar, 0) : full_bar;
+      if constexpr (kCta == 2 && !kX3) {
+        if (p.bres && first_tile < p.total_tiles) {
+          // B-stationary: this pair's N slice is the same for every tile it owns (grid = a multiple of n_tiles): load all its k-blocks once
+          const TileCoord c0 = decode_tile(p, first_tile, crank);
+          const uint32_t fb = mapa_rank(bres_bar, 0);
+          mbar_expect_tx_cluster_el(el, fb, (uint32_t)(p.kblocks * p.b_tx_bytes));
+          for (int kb = 0; kb < p.kblocks; ++kb) {
+            const uint32_t dst = sB + kb * p.b_stage_bytes;
+            if (p.b_major == JMT_MAJOR_K) tma_load_4d_2sm_el(el, dst, &tma_b_hi, fb, kb * kBlockK, c0.n0 + n_off, 0, 0);
+            else if (p.b_mn5) tma_load_5d_2sm_el(el, dst, &tma_b_hi, fb, 0, kb * kBlockK + p.b_shift0, (c0.n0 + n_off) >> 6, 0, 0);
+            else for (int ch = 0; ch < b_chunks; ++ch)
+              tma_load_4d_2sm_el(el, dst + ch * 8192, &tma_b_hi, fb, c0.n0 + n_off + ch * 64, kb * kBlockK + p.b_shift0, 0, 0);
+          }
+        }
+      }
       for (int t = first_tile; t < p.total_tiles; t += tile_stride) {
         const TileCoord c = decode_tile(p, t, crank);
         // (tap, rb, kb) of the first iteration; afterwards the counters advance incrementally (no divisions in the loop)
@@ -593,7 +616,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a_hi, const __grid_consta
           const long long tw = p.prof ? clock64() : 0;
           mbar_wait(empty_bar + 8 * stage, phase ^ 1);
           if (p.prof) pr_wait += clock64() - tw;
-          const int b_tx = c.tail ? p.b_tail_bytes : p.b_tx_bytes;
+          const int b_tx = p.bres ? 0 : (c.tail ? p.b_tail_bytes : p.b_tx_bytes);
           if constexpr (kCta == 1) mbar_expect_tx_el(el, full_bar + 8 * stage, kOps * (kAStageBytes + b_tx));
           else mbar_expect_tx_cluster_el(el, full_leader + 8 * stage, kOps * (kAStageBytes + b_tx));
 #pragma unroll
@@ -625,6 +648,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a_hi, const __grid_consta
             }
           } else {
             const uint32_t fb = full_leader + 8 * stage;
+            if (p.bres && p.l2_ahead > 0 && t + p.l2_ahead * tile_stride < p.total_tiles) {
+              // B-stationary: only A is streamed and its ring is short (B takes 128 KB): pull the same k-block of the tile this pair
+              // works on `l2_ahead` tiles from now into L2, so the later load is an L2 hit (~1/3 of the DRAM round trip)
+              const int m_next = c.m0 + p.l2_ahead * p.l2_mstep;
+              if (p.a_major == JMT_MAJOR_K) tma_prefetch_4d_el(el, &tma_a, kb * kBlockK, m_next, 0, 0);
+              else if (p.a_mn5) tma_prefetch_5d_el(el, &tma_a, 0, kb * kBlockK, m_next >> 6, 0, 0);
+            }
             if (p.a_major == JMT_MAJOR_K) {
               tma_load_4d_2sm_el(el, a_dst, &tma_a, fb, kb * kBlockK, c.m0 + ash, ab0, ab1);
             } else if (p.a_mn5) {
@@ -633,7 +663,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a_hi, const __grid_consta
               tma_load_4d_2sm_el(el, a_dst, &tma_a, fb, c.m0, kb * kBlockK + ash, ab0, ab1);
               tma_load_4d_2sm_el(el, a_dst + 8192, &tma_a, fb, c.m0 + 64, kb * kBlockK + ash, ab0, ab1);
             }
-            if (!kX3 && c.tail) {      // tail piece: this CTA's half of it through the tail map (tma_b_lo slot, unused without kX3)
+            if (p.bres) {               // (B is resident)
+            } else if (!kX3 && c.tail) {      // tail piece: this CTA's half of it through the tail map (tma_b_lo slot, unused without kX3)
               const int n_t = c.n0 + crank * (p.tail_bn / kCta);
               if (p.b_major == JMT_MAJOR_K) tma_load_4d_2sm_el(el, b_dst, &tma_b_lo, fb, tap * p.K + kb * kBlockK, n_t, bb0, bb1);
               else tma_load_5d_2sm_el(el, b_dst, &tma_b_lo, fb, 0, kb * kBlockK + bsh, n_t >> 6, bb0, bb1);
@@ -675,6 +706,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a_hi, const __grid_consta
       const uint32_t b_lbo = p.b_major == JMT_MAJOR_K ? 16u : 8192u;
       const uint32_t a_kstep = p.a_major == JMT_MAJOR_K ? (kUmmaK * 2) >> 4 : (kUmmaK * 128) >> 4;   // desc.lo units (16 B)
       const uint32_t b_kstep = p.b_major == JMT_MAJOR_K ? (kUmmaK * 2) >> 4 : (kUmmaK * 128) >> 4;
+      if (p.bres && first_tile < p.total_tiles) { mbar_wait(bres_bar, 0); tc_fence_after(); }     // the resident B slice has landed
       for (int t = first_tile; t < p.total_tiles; t += tile_stride, ++tile_iter) {
         const TileCoord c = decode_tile(p, t, crank);
         const int acc = p.wide ? 0 : (tile_iter & 1);
@@ -738,7 +770,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a_hi, const __grid_consta
           if (p.prof) mw_full += clock64() - tw1;
           tc_fence_after();
           const uint64_t a_desc = make_smem_desc(sA + stage * a_stride, a_lbo, 1024);
-          const uint64_t b_desc = make_smem_desc(sB + stage * b_stride, b_lbo, 1024);
+          const uint64_t b_desc = make_smem_desc(p.bres ? sB + it * p.b_stage_bytes : sB + stage * b_stride, b_lbo, 1024);   // (bres: it = k-block)
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; ++k) {
             tc_mma_elect<kCta>(el, d_tmem, a_desc + (uint64_t)(k * a_kstep), b_desc + (uint64_t)(k * b_kstep), c.tail ? p.idesc_tail : p.idesc,
@@ -906,6 +938,10 @@ static int pick_block_n(int N) {
 using namespace jmt;
 
 static std::atomic<unsigned long long*> g_prof_buf{nullptr};
+// B-stationary mode of the short-K linears: -1 = environment (JMT_GEMM_BRES, default 1 = automatic), 0 = off, 1 = automatic, 2 = forced
+// whenever the geometry allows it (tests: small M)
+static std::atomic<int> g_bres_mode{-1};
+extern "C" int jmt_gemm_set_bres_mode(int mode) { return g_bres_mode.exchange(mode); }
 // Debug aid: when set (device buffer of 16 x 148 uint64), every jmt_gemm_bf16 launch overwrites per-CTA cycle
 // counters: [0] MMA wait-full [1] MMA wait-tmem-empty [2] MMA total [3] TMA wait-empty [4] TMA total
 // [5] epilogue wait-tmem-full [6] epilogue bias barriers [7] epilogue wait-store-read [8] epilogue total
@@ -958,7 +994,15 @@ static int gemm_tc_launch(const jmt_gemm_desc* g, const void* a_lo, const void* 
   {
     static const int wide_env = []() { const char* e = getenv("JMT_GEMM_WIDE"); return e ? atoi(e) : 1; }();
     const int min_iters = wide_env > 1 ? wide_env : kWideMinIters;
-    p.wide = (wide_env != 0 && !x3 && p.cluster == 2 && !p.pair_batch && g->N % 512 == 0 &&
+    // B-stationary pairs for short-K linears (see TcParams::bres); JMT_GEMM_BRES=0 disables
+    static const int bres_env0 = []() { const char* e = getenv("JMT_GEMM_BRES"); return e ? atoi(e) : 1; }();
+    const int bres_set = g_bres_mode.load();
+    const int bres_env = bres_set >= 0 ? bres_set : bres_env0;
+    p.bres = (bres_env != 0 && !x3 && p.cluster == 2 && !p.pair_batch && g->ntaps == 1 && nb == 1 && p.split_k == 1 && g->N % 256 == 0 &&
+              p.kblocks <= 8 && g->N / 256 <= kNumSMs / 2 &&
+              (bres_env == 2 /* forced: tests */ || (p.kblocks >= 4 && p.m_tiles >= 8 * (kNumSMs / 2) / (g->N / 256)))) ? 1 : 0;
+    if (p.bres) { p.block_n = 256; p.n_tiles = g->N / 256; }
+    p.wide = (wide_env != 0 && !x3 && !p.bres && p.cluster == 2 && !p.pair_batch && g->N % 512 == 0 &&
               p.iters_total / p.split_k >= min_iters) ? 1 : 0;
     if (p.wide) { p.block_n = 512; p.n_tiles = g->N / 512; }
     // measured (round 2, profiles/gemm_roles_r2h_tp*.txt): the MMA issuer's wait for the accumulator halves (20.9 k -> 11.7 k of 62 k
@@ -986,12 +1030,13 @@ static int gemm_tc_launch(const jmt_gemm_desc* g, const void* a_lo, const void* 
   p.b_chunks_cta = (b_cols_cta + 63) / 64;
   p.b_stage_bytes = (g->b_major == JMT_MAJOR_K ? b_cols_cta * 128 : p.b_chunks_cta * 8192) * (p.wide ? 2 : 1);
   p.b_tx_bytes = p.b_stage_bytes;
-  const int stage_bytes = (kAStageBytes + p.b_stage_bytes) * (x3 ? 2 : 1);     // x3: hi and lo tile of each operand
+  const int stage_bytes = p.bres ? kAStageBytes : (kAStageBytes + p.b_stage_bytes) * (x3 ? 2 : 1);     // x3: hi and lo tile of each operand
+  const int bres_bytes = p.bres ? p.kblocks * p.b_stage_bytes : 0;
   // 8 epilogue warps, two per TMEM lane quarter (a 16-warp variant measured 3-10 % slower on every shape in round 1: the
   // epilogue waits on the stage hand-over, it is not short of warps; the instantiation was dropped)
   p.epi_warps = 8;
   const int budget = 227 * 1024 - 256 /*barriers*/ - epi_smem_bytes(p.epi_warps);      // the dynamic window is 1024-aligned (checked in the kernel)
-  p.stages = budget / stage_bytes;
+  p.stages = (budget - bres_bytes) / stage_bytes;
   if (p.stages > kMaxStages) p.stages = kMaxStages;
   JMT_REQUIRE(p.stages >= 2, "jmt_gemm_bf16: shared memory budget");
   p.prof = g_prof_buf.load();
@@ -1062,7 +1107,7 @@ static int gemm_tc_launch(const jmt_gemm_desc* g, const void* a_lo, const void* 
     const int rem = p.total_tiles % units;
     const int gran = g->b_major == JMT_MAJOR_K ? 64 : 64 * p.cluster;
     const bool b_ok = g->b_major == JMT_MAJOR_K || p.b_mn5;
-    if (tail_env && !x3 && p.split_k == 1 && !p.reduce_batch && b_ok && p.total_tiles > units && rem > 0 && 2 * rem <= units) {
+    if (tail_env && !x3 && !p.bres && p.split_k == 1 && !p.reduce_batch && b_ok && p.total_tiles > units && rem > 0 && 2 * rem <= units) {
       int sp = 1;
       while (sp < 8 && rem * sp * 2 <= units && p.block_n % (sp * 2) == 0 && (p.block_n / (sp * 2)) % gran == 0) sp *= 2;
       if (sp > 1 && p.block_n / sp <= 256) {
@@ -1093,7 +1138,7 @@ static int gemm_tc_launch(const jmt_gemm_desc* g, const void* a_lo, const void* 
     rc = make_map_d(&map_d, g->d, g->d_dtype, g->N, g->M, g->d_ld, dnb0, g->d_bs0, dnb1, g->d_bs1, "jmt_gemm_bf16(D)");
     if (rc != JMT_OK) return rc;
   }
-  const int smem = p.stages * stage_bytes + epi_smem_bytes(p.epi_warps) + 256;
+  const int smem = p.stages * stage_bytes + bres_bytes + epi_smem_bytes(p.epi_warps) + 256;
   static std::atomic<int> attr_set[64];     // per device (immutable once set)
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); set_error("jmt_gemm_bf16: no CUDA device"); return JMT_ERR_CUDA; }
@@ -1111,8 +1156,14 @@ static int gemm_tc_launch(const jmt_gemm_desc* g, const void* a_lo, const void* 
     if (e != cudaSuccess) { set_error("jmt_gemm_bf16: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); cudaGetLastError(); return JMT_ERR_CUDA; }
     attr_set[dev & 63].store(1, std::memory_order_release);
   }
-  const int max_groups = kNumSMs / p.cluster;
+  int max_groups = kNumSMs / p.cluster;
+  if (p.bres) max_groups -= max_groups % p.n_tiles;       // a pair's tiles t, t + groups, ... all have the same N slice (t % n_tiles)
   const int groups = p.total_tiles < max_groups ? p.total_tiles : max_groups;
+  {
+    static const int l2_env = []() { const char* e = getenv("JMT_GEMM_L2_AHEAD"); return e ? atoi(e) : 1; }();
+    p.l2_ahead = p.bres ? l2_env : 0;
+    p.l2_mstep = p.bres ? (groups / p.n_tiles) * kBlockM * p.cluster : 0;      // tiles t and t + groups of a pair are groups / n_tiles pair-rows apart
+  }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(groups * p.cluster);

@@ -270,6 +270,17 @@ __device__ __forceinline__ void bulk_wait_read1_el(uint32_t el) {
 __device__ __forceinline__ void bulk_wait0_el(uint32_t el) {
   asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %0, 0;\n\t@q cp.async.bulk.wait_group 0;\n\t}" ::"r"(el) : "memory");
 }
+// elected-lane L2 prefetch of a tensor-map box
+__device__ __forceinline__ void tma_prefetch_4d_el(uint32_t el, const CUtensorMap* map, int c0, int c1, int c2, int c3) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+               "@q cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];\n\t}"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(el) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_5d_el(uint32_t el, const CUtensorMap* map, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %6, 0;\n\t"
+               "@q cp.async.bulk.prefetch.tensor.5d.L2.global.tile [%0, {%1, %2, %3, %4, %5}];\n\t}"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(el) : "memory");
+}
 // 32 lanes x 32 columns of fp32 accumulators -> 32 registers per thread (thread = TMEM lane = output row).
 // Issue only; tc_wait_ld() must precede the first use of r[] (several loads can be in flight).
 __device__ __forceinline__ void tc_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {

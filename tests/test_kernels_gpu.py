@@ -165,6 +165,57 @@ def test_gemm(case, precision):
                              f"bad cols {sorted(set(i[2] for i in bad.nonzero().tolist()))[:16]} frac {bad.float().mean().item():.3f}")
 
 
+BRES_CASES = [
+    # name, M, N, K, b_major, act, bias, store, aux
+    ("lin_relu", 1100, 512, 512, 0, 1, True, 0, False),
+    ("dgrad_mn_acc", 1024, 1024, 448, 1, 0, False, 1, False),
+    ("k256_n256", 2048, 256, 256, 0, 0, True, 0, False),
+    ("n1536_ragged_m", 1333, 1536, 512, 0, 0, True, 0, False),
+    ("dgrad_fold", 1280, 512, 512, 1, 0, False, 0, True),
+]
+
+
+@pytest.mark.parametrize("case", BRES_CASES, ids=[c[0] for c in BRES_CASES])
+def test_gemm_b_stationary(case):
+    """B-stationary CTA pairs (TcParams::bres: the pair's 256-column slice of B resident in shared memory, A streamed) forced at
+    small M: against fp64 on the same bf16 operands, and bit-identical to the regular schedule."""
+    name, M, N, K, b_major, act, has_bias, store, aux = case
+    torch.manual_seed(len(name))
+    dev = torch.device("cuda")
+    ctx = _ctx("bf16")
+    a = (torch.randn(M, K) * 0.5).to(torch.bfloat16)
+    b = (torch.randn(N, K) * 0.5).to(torch.bfloat16) if b_major == 0 else (torch.randn(K, N) * 0.5).to(torch.bfloat16)
+    bias = torch.randn(N) if has_bias else None
+    y = (torch.randn(M, N)).to(torch.bfloat16) if aux else None
+    d0 = (torch.randn(M, N) * 0.5).to(torch.bfloat16)
+    bm = b.double() if b_major == 0 else b.double().t()
+    ref = a.double() @ bm.t()
+    if bias is not None:
+        ref = ref + bias.double()
+    if act == 1:
+        ref = torch.relu(ref)
+    if aux:
+        ref = ref * torch.where(y.double() > 0, 1.0, 0.25)
+    if store == 1:
+        ref = ref + d0.double()
+    outs = []
+    lib = L.lib()
+    for mode in (2, 0):
+        prev = lib.jmt_gemm_set_bres_mode(mode)
+        try:
+            d = d0.clone().to(dev)
+            E.gemm(ctx, a.to(dev), b.to(dev), d, M=M, N=N, K=K, b_major=b_major, b_rows=N if b_major == 0 else K,
+                   bias=bias.to(dev) if bias is not None else None, act=act, store=store,
+                   epi_aux=y.to(dev) if aux else None, aux_slope=0.25)
+            torch.cuda.synchronize()
+        finally:
+            lib.jmt_gemm_set_bres_mode(prev)
+        outs.append(d.cpu())
+    err = (outs[0].double() - ref).abs().max()
+    assert err < 1.5e-2 * ref.abs().max(), (name, float(err))
+    assert torch.equal(outs[0], outs[1]), name
+
+
 @pytest.mark.parametrize("precision", ["fp32", "bf16x3", "bf16"])
 @pytest.mark.parametrize("nb", [3, 4])
 def test_gemm_colmask(precision, nb):
