@@ -42,7 +42,9 @@ def _ptr(t: Optional[torch.Tensor]):
 
 
 def _stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    # raw handle of the current stream of the current device (torch.cuda.current_stream() builds a Stream object through several
+    # Python layers: ~15 us a call, 3 ms of an eagerly launched step)
+    return C.c_void_p(torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice()))
 
 
 def require_cuda(*ts):

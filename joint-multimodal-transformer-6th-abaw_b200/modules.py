@@ -91,7 +91,7 @@ class _TapeFn(torch.autograd.Function):
     @staticmethod
     def forward(actx, owner, runner, record, n_in, *tensors):
         inputs, params = tensors[:n_in], tensors[n_in:]
-        names = owner._live_names()
+        names = owner._live_names_fast()
         pd = {n: p for n, p in zip(names, params)}
         owner._calls = getattr(owner, "_calls", 0) + 1
         seed = (torch.initial_seed() * 1000003 + owner._calls) & ((1 << 62) - 1)
@@ -154,6 +154,37 @@ class _JmtModule(nn.Module):
         dead = self._dead_prefixes()
         return [p for n, p in self.named_parameters() if not any(n.startswith(d) for d in dead)]
 
+    def _live_params_fast(self) -> List[nn.Parameter]:
+        """The live parameters in `_live_names()` order without walking the module tree on every call: the walk (named_parameters
+        over ~60 sub-modules) is cached as (owner module, attribute) pairs and each call only re-reads the attributes, so a
+        parameter that was re-assigned is still picked up; adding / removing sub-modules or parameters invalidates the cache through
+        the module count."""
+        n_mod = sum(1 for _ in self.modules())
+        cache = self.__dict__.get("_live_slots")
+        if cache is None or cache[0] != n_mod:
+            dead = self._dead_prefixes()
+            slots, seen = [], set()
+            for mname, mod in self.named_modules():
+                for pname, par in mod._parameters.items():
+                    if par is None or id(par) in seen:
+                        continue
+                    seen.add(id(par))
+                    full = (mname + "." if mname else "") + pname
+                    if not any(full.startswith(d) for d in dead):
+                        slots.append((full, mod, pname))
+            order = {n: i for i, n in enumerate(self._live_names())}
+            slots.sort(key=lambda s: order[s[0]])
+            assert len(slots) == len(order), "live-parameter inventory mismatch"
+            cache = (n_mod, slots)
+            self.__dict__["_live_slots"] = cache
+        return [mod._parameters[pname] for _, mod, pname in cache[1]]
+
+    def _live_names_fast(self) -> List[str]:
+        """`_live_names()` from the same cache (the order `_live_params_fast` returns)."""
+        if self.__dict__.get("_live_slots") is None:
+            self._live_params_fast()
+        return [n for n, _, _ in self.__dict__["_live_slots"][1]]
+
     def set_grad_sync(self, fn):
         """fn(flat_fp32_bucket) is called at the end of backward (data-parallel all-reduce hook)."""
         self.__dict__["_grad_sync"] = fn
@@ -162,9 +193,7 @@ class _JmtModule(nn.Module):
         inputs = tuple(i.float() if i.dtype == torch.float16 else i for i in inputs)
         for i in inputs:
             E.require_cuda(i)
-        names = self._live_names()
-        sd = dict(self.named_parameters())
-        params = [sd[n] for n in names]
+        params = self._live_params_fast()
         E.require_cuda(*params)
         record = torch.is_grad_enabled() and any(t.requires_grad for t in (*inputs, *params))
         with torch.autocast("cuda", enabled=False):
