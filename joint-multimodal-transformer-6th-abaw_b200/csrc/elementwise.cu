@@ -134,6 +134,38 @@ transpose_kernel(const TI* __restrict__ in, TO* __restrict__ out, int R, int C, 
   }
 }
 
+// bf16 -> bf16 fast path of the transpose (the (B, 1024, T) -> channels-last input transpose of the TCN, 157 MB in + 157 MB out per step):
+// 8-byte global loads (16 lanes per 128-byte row segment), 16-byte global stores (8 lanes per 128-byte output row segment); the 64 x 64
+// tile sits UN-transposed in shared memory (pitch 33 words), the transposition is the 2-byte gather of the read-out (2-way bank
+// conflicts at most).  Needs C % 4 == 0, R % 8 == 0 and 8- / 16-byte aligned batch strides; the generic kernel above is the fallback.
+__global__ void __launch_bounds__(256)
+transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int R, int C, int64_t in_bs, int64_t out_bs) {
+  __shared__ __align__(16) uint16_t tile[64][66];
+  const int64_t b = blockIdx.z;
+  const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
+  const __nv_bfloat16* ib = in + b * in_bs;
+  __nv_bfloat16* ob = out + b * out_bs;
+  const int t = threadIdx.x;
+#pragma unroll
+  for (int pass = 0; pass < 4; ++pass) {
+    const int r = pass * 16 + (t >> 4), c = (t & 15) * 4;
+    uint2 v = make_uint2(0u, 0u);
+    if (r0 + r < R && c0 + c < C) v = *reinterpret_cast<const uint2*>(ib + (int64_t)(r0 + r) * C + c0 + c);     // (C % 4 == 0: whole or nothing)
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&tile[r][c]);
+    dst[0] = v.x; dst[1] = v.y;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    const int c = pass * 32 + (t >> 3), r8 = (t & 7) * 8;
+    if (c0 + c >= C || r0 + r8 >= R) continue;
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) w[i] = (uint32_t)tile[r8 + 2 * i][c] | ((uint32_t)tile[r8 + 2 * i + 1][c] << 16);
+    *reinterpret_cast<uint4*>(ob + (int64_t)(c0 + c) * R + r0 + r8) = make_uint4(w[0], w[1], w[2], w[3]);          // (R % 8 == 0)
+  }
+}
+
 // out[c] += sum_r x[r*ld + c].  Block = 32 column-groups (8 columns each, one 16-byte load) x 8 row lanes;
 // grid.y slabs of rows; per-block shared reduction then one fp32 atomic per column.
 template <typename T>
@@ -696,6 +728,11 @@ extern "C" int jmt_transpose_strided(const void* in, int in_dtype, int64_t in_bs
   if (out_bs == 0) out_bs = (int64_t)R * C;
   dim3 grid((C + 63) / 64, (R + 63) / 64, (unsigned)nb);
   cudaStream_t st = (cudaStream_t)stream;
+  if (in_dtype == JMT_BF16 && out_dtype == JMT_BF16 && C % 4 == 0 && R % 8 == 0 && in_bs % 4 == 0 && out_bs % 8 == 0 &&
+      (reinterpret_cast<uintptr_t>(in) & 7) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+    transpose_bf16_kernel<<<grid, 256, 0, st>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, R, C, in_bs, out_bs);
+    return check_launch("transpose_bf16_kernel");
+  }
   JMT_DISPATCH_DTYPE(in_dtype, TI, JMT_DISPATCH_DTYPE(out_dtype, TO,
       (transpose_kernel<TI, TO><<<grid, 256, 0, st>>>((const TI*)in, (TO*)out, R, C, in_bs, out_bs))));
   return check_launch("transpose_kernel");

@@ -848,8 +848,12 @@ def dqkv_planned(ctx: Ctx, dh: int, Lq: int, S: int, heads: int) -> bool:
     """Will attention_core's backward run jmt_attn_bwd_dqkv_bf16 for this geometry?  (Decided before the projections are built:
     they then let that kernel add the bias-gradient column sums.  attention_core falls back to column-sum-emitting GEMMs should
     the fused forward turn out to be unsupported.)"""
-    return (ctx.record and ctx.ext_on() and ATTN_BWD_DQKV and FUSED_ATTENTION is True and FUSED_ATTENTION_BWD == "ds" and
-            dh in (256, 512) and Lq <= 320 and S <= 320 and heads * dh <= 1024)
+    return (ctx.record and ctx.ext_on() and FUSED_ATTENTION is True and FUSED_ATTENTION_BWD == "ds" and dqkv_geometry_ok(dh, Lq, S, heads))
+
+
+def dqkv_geometry_ok(dh: int, Lq: int, S: int, heads: int) -> bool:
+    """Geometries jmt_attn_bwd_dqkv_bf16 supports (jmt_attn_bwd_dqkv_supported, csrc/attn_bwd_tc.cu) and the switch for it."""
+    return ATTN_BWD_DQKV and dh in (256, 512) and Lq <= 320 and S <= 320 and heads * dh <= 1024
 
 
 def _attn_bwd_dqkv(ctx: Ctx, parts, Lq, S, dh, heads, NB, x_ld):
@@ -968,7 +972,7 @@ def attention_core(ctx: Ctx, q: Var, qcol: int, k: Var, kcol: int, v: Var, vcol:
                                                     _stream()), "jmt_rowdot_bf16")
                 _attn_chain(ctx, 1, do, o_geo, vd, v_geo, None, None, probs, ds, None, None, Lq, S, dh, heads, NB, s_ld, scale,
                             L.STORE, delta_in=delta)
-                if ATTN_BWD_DQKV and dh in (256, 512) and Lq <= 320 and S <= 320 and heads * dh <= 1024:
+                if dqkv_geometry_ok(dh, Lq, S, heads):
                     # dQ = dS K, dK = dS^T Q, dV = P^T dO (+ the projections' bias-gradient column sums) in ONE launch
                     gv, v_mode = _proj_grad_slice(ctx, v, vcol, vcol + E, capable=True)
                     gk_, k_mode = _proj_grad_slice(ctx, k, kcol, kcol + E, capable=True)

@@ -36,6 +36,8 @@ geo = (3 * Eh, dh, T * 3 * Eh); ogeo = (Eh, dh, T * Eh)
 sc = 1 / math.sqrt(dh)
 run("fwd", lambda: E._attn_chain(ctx, 0, qd, geo, kd, geo, vd, geo, None, probs, o, ogeo, T, T, dh, h, NB, s_ld, sc, L.STORE))
 run("bwd", lambda: E._attn_chain(ctx, 1, do, ogeo, vd, geo, kd, geo, probs, ds, dq[:, :Eh], geo, T, T, dh, h, NB, s_ld, sc, L.ACCUMULATE, o_in=o))
+run("bwd dS-only (the mode of the step: delta = rowsum(P o dP) in kernel, no GEMM2)",
+    lambda: E._attn_chain(ctx, 1, do, ogeo, vd, geo, None, None, probs, ds, None, None, T, T, dh, h, NB, s_ld, sc, L.STORE))
 # E1: separate contiguous Q/K/V (row pitch 1024 B instead of 3072 B)
 qc, kc, vc = qd.contiguous(), kd.contiguous(), vd.contiguous()
 geo2 = (Eh, dh, T * Eh)

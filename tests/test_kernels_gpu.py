@@ -836,6 +836,16 @@ def test_small_kernels():
     x_d = x.to(dev)
     L.check(lib.jmt_transpose(E._ptr(x_d), L.F32, E._ptr(o), L.BF16, 3, 37, 70, st), "tr")
     assert torch.equal(o.cpu(), x.transpose(1, 2).to(torch.bfloat16))
+    # bf16 -> bf16 fast path (8-byte loads, 16-byte stores): the TCN input geometry (1024 channels x 300 frames) with a padded
+    # output batch stride, a ragged tile in both directions, and canaries around every output sequence
+    for (nb, R, Cc, pad) in ((3, 1024, 300, 32), (2, 72, 44, 0), (1, 8, 4, 5)):
+        xb = torch.randn(nb, R, Cc).to(torch.bfloat16)
+        ob = torch.full((nb, pad + Cc, R), 7.0, device=dev, dtype=torch.bfloat16)
+        xb_d = xb.to(dev)
+        L.check(lib.jmt_transpose_strided(E._ptr(xb_d), L.BF16, R * Cc, E._ptr(ob[:, pad:]), L.BF16, (pad + Cc) * R, nb, R, Cc, st), "trb")
+        torch.cuda.synchronize()
+        assert torch.equal(ob[:, pad:].cpu(), xb.transpose(1, 2)), (nb, R, Cc)
+        assert (ob[:, :pad].cpu() == 7.0).all()
     # colsum
     a = torch.randn(1000, 130).to(torch.bfloat16)
     out = torch.zeros(130, device=dev)
