@@ -1,8 +1,11 @@
 // jmt_gemm_bf16: persistent, warp-specialised tcgen05 GEMM for sm_100a.
 //
-//   warp 0 (1 elected thread) : TMA producer   -- cp.async.bulk.tensor.4d -> 128B-swizzled smem ring
-//   warp 1 (1 elected thread) : MMA issuer     -- tcgen05.mma.cta_group::{1,2}.kind::f16, fp32 accum in TMEM
-//   warps 2..9                : epilogue       -- tcgen05.ld 32x32b -> alpha/bias/activation -> swizzled smem -> TMA store
+//   warp 0 : TMA producer   -- cp.async.bulk.tensor.4d / 5d -> 128B-swizzled smem ring
+//   warp 1 : MMA issuer     -- tcgen05.mma.cta_group::{1,2}.kind::f16, fp32 accum in TMEM
+//   warps 2..9 : epilogue   -- tcgen05.ld 32x32b -> alpha/bias/activation -> swizzled smem -> TMA store
+// The producer and issuer warps run their loops with ALL lanes (warp-uniform control flow, operands in uniform registers) and ONE
+// elected lane executes the TMA / MMA / commit instructions (tc_common.cuh: *_el, tc_mma_elect): under `if (lane == 0)` ptxas wraps
+// every such instruction in an ELECT + R2UR.BROADCAST loop of ~25 single-thread instructions -- as long as an N = 256 MMA takes.
 //
 // Two TMEM accumulator stages (2 x 256 columns) let the epilogue of tile i overlap the mainloop of
 // tile i+1; an epilogue warp hands its stage back as soon as its last tcgen05.ld of the tile has landed.  One descriptor (jmt_gemm_desc) covers every dense contraction of the JMT path: Linear
