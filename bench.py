@@ -424,14 +424,14 @@ def main():
         # DRAM traffic of the dominant kernel's most frequent launch (76800x512x512 linear, 40 of 147 GEMM launches per step)
         # from the committed `ncu --set full` capture; algorithmic bytes of that launch = A + W + D = 157.8 MB
         traffic, traffic_src = None, None
-        tpath = os.path.join(ROOT, "profiles", "ncu_gemm_tc_r3e_linear_76800x512x512.csv")
+        tpath = os.path.join(ROOT, "profiles", "ncu_gemm_tc_r3p_linear_76800x512x512.csv")
         if kname == "gemm_tc_kernel" and os.path.exists(tpath):
             import csv
             rows = {r[0]: r for r in csv.reader(open(tpath)) if len(r) == 3}
             mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
             try:
                 traffic = sum(float(rows[k][2]) * mult[rows[k][1]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
-                traffic_src = "profiles/ncu_gemm_tc_r3e_linear_76800x512x512.csv (dram read+write of one 76800x512x512 launch; algorithmic 157.8e6 B)"
+                traffic_src = "profiles/ncu_gemm_tc_r3p_linear_76800x512x512.csv (dram read+write of one 76800x512x512 launch; algorithmic 157.8e6 B)"
             except (KeyError, ValueError):
                 traffic = None
         roof = {"bound": "tensor", "kernel": kname, "achieved": ach, "peak": peak, "unit": "TFLOP/s",
