@@ -252,6 +252,14 @@ int jmt_l2norm_fwd(const void* x, int in_dtype, int64_t in_ld, void* out, int ou
 /* dx = r*(dy - y*(y.dy)) (r = inv_norm; rows with ||x|| < eps: dx = r*dy).  y = saved output. */
 int jmt_l2norm_bwd(const void* dy, const void* y, int dtype, const float* inv_norm, float eps,
                    void* dx, int dx_dtype, int64_t rows, int D, void* stream);
+/* The same on the TCN's flat padded layout (I3DWSDDA.py:44 `temporal(x).transpose(1, 2)` followed by two_transformers.py:118): the
+ * input of the forward / the dx of the backward has seq_rows = row0 + seq_len physical rows per sequence, the first row0 of them
+ * padding; out / dy / y / inv_norm are compact (nseq*seq_len rows).  The backward writes the padding rows of dx as zeros.  Saves the
+ * un-padding copy and, in the backward, the zero fill + scatter copy of the padded gradient. */
+int jmt_l2norm_fwd_seq(const void* x, int in_dtype, int64_t in_ld, void* out, int out_dtype, int64_t nseq, int seq_len,
+                       int seq_rows, int row0, int D, float eps, float* inv_norm, void* stream);
+int jmt_l2norm_bwd_seq(const void* dy, const void* y, int dtype, const float* inv_norm, float eps, void* dx, int dx_dtype,
+                       int64_t nseq, int seq_len, int seq_rows, int row0, int D, void* stream);
 
 /* y = LayerNorm(x + res) * gamma + beta  (post-LN residual: mm_multi_transformers.py:62-69).
  * res nullable.  Saves mean/rstd (rows) fp32. */

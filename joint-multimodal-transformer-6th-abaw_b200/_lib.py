@@ -93,6 +93,8 @@ SIGNATURES = {
     "jmt_rowdot_bf16": [_P, _P, _L, _L, _L, _I, _I, _I, _I, _P, _P],
     "jmt_l2norm_fwd": [_P, _I, _L, _P, _I, _L, _I, _F, _P, _P],
     "jmt_l2norm_bwd": [_P, _P, _I, _P, _F, _P, _I, _L, _I, _P],
+    "jmt_l2norm_fwd_seq": [_P, _I, _L, _P, _I, _L, _I, _I, _I, _I, _F, _P, _P],
+    "jmt_l2norm_bwd_seq": [_P, _P, _I, _P, _F, _P, _I, _L, _I, _I, _I, _I, _P],
     "jmt_add_layernorm_fwd": [_P, _P, _P, _P, _F, _P, _P, _P, _L, _I, _I, _P],
     "jmt_add_layernorm_bwd": [_P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _L, _I, _I, _P],
     "jmt_softmax_fwd": [_P, _L, _P, _I, _L, _L, _I, _P],

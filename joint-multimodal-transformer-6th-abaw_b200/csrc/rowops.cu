@@ -13,12 +13,14 @@ constexpr int kWarpsPerBlock = kRowThreads / 32;
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(kRowThreads)
 l2norm_fwd_kernel(const TI* __restrict__ x, int64_t in_ld, TO* __restrict__ out, int64_t rows, int D, float eps,
-                  float* __restrict__ inv_norm) {
+                  float* __restrict__ inv_norm, int seq_len, int seq_rows, int row0) {
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
   for (int64_t r = warp0; r < rows; r += nwarps) {
-    const TI* xr = x + r * in_ld;
+    // seq_len > 0: compact row r = n * seq_len + t lives at physical row n * seq_rows + row0 + t of x (the TCN's flat padded layout)
+    const int64_t pr = seq_len > 0 ? (r / seq_len) * seq_rows + row0 + r % seq_len : r;
+    const TI* xr = x + pr * in_ld;
     float ss = 0.f;
     for (int c = lane * 8; c < D; c += 256) {
       Vec8<TI> v; v.load(xr + c);
@@ -42,11 +44,28 @@ l2norm_fwd_kernel(const TI* __restrict__ x, int64_t in_ld, TO* __restrict__ out,
 template <typename T, typename TO>
 __global__ void __launch_bounds__(kRowThreads)
 l2norm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ y, const float* __restrict__ inv_norm, float eps,
-                  TO* __restrict__ dx, int64_t rows, int D) {
+                  TO* __restrict__ dx, int64_t rows, int D, int seq_len, int seq_rows, int row0) {
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
-  for (int64_t r = warp0; r < rows; r += nwarps) {
+  // seq_len > 0: dx is the flat padded layout (seq_rows physical rows per sequence, the first row0 of them padding): the loop runs over
+  // PHYSICAL rows, padding rows are written as zeros (the TCN backward relies on them), the others take compact row n * seq_len + t
+  const int64_t prows = seq_len > 0 ? rows / seq_len * seq_rows : rows;
+  for (int64_t pr = warp0; pr < prows; pr += nwarps) {
+    int64_t r = pr;
+    if (seq_len > 0) {
+      const int64_t n = pr / seq_rows;
+      const int t = (int)(pr - n * seq_rows) - row0;
+      if (t < 0) {
+        TO* z = dx + pr * (int64_t)D;
+        Vec8<TO> o;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o.v[i] = 0.f;
+        for (int c = lane * 8; c < D; c += 256) o.store(z + c);
+        continue;
+      }
+      r = n * seq_len + t;
+    }
     const T* dyr = dy + r * (int64_t)D;
     const T* yr = y + r * (int64_t)D;
     const float inv = inv_norm[r];
@@ -59,7 +78,7 @@ l2norm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ y, const float
     dot = warp_sum(dot);
     // ||x|| clamped by eps: y = x/eps is linear in x, no projection term
     if (inv >= 1.f / eps) dot = 0.f;
-    TO* dxr = dx + r * (int64_t)D;
+    TO* dxr = dx + pr * (int64_t)D;
     for (int c = lane * 8; c < D; c += 256) {
       Vec8<T> a, b; a.load(dyr + c); b.load(yr + c);
       Vec8<TO> o;
@@ -250,7 +269,19 @@ extern "C" int jmt_l2norm_fwd(const void* x, int in_dtype, int64_t in_ld, void* 
   if (rows == 0) return JMT_OK;
   cudaStream_t st = (cudaStream_t)stream;
   JMT_DISPATCH_DTYPE(in_dtype, TI, JMT_DISPATCH_DTYPE(out_dtype, TO,
-      (l2norm_fwd_kernel<TI, TO><<<row_grid(rows), kRowThreads, 0, st>>>((const TI*)x, in_ld, (TO*)out, rows, D, eps, inv_norm))));
+      (l2norm_fwd_kernel<TI, TO><<<row_grid(rows), kRowThreads, 0, st>>>((const TI*)x, in_ld, (TO*)out, rows, D, eps, inv_norm, 0, 0, 0))));
+  return check_launch("l2norm_fwd_kernel");
+}
+
+extern "C" int jmt_l2norm_fwd_seq(const void* x, int in_dtype, int64_t in_ld, void* out, int out_dtype, int64_t nseq, int seq_len,
+                                  int seq_rows, int row0, int D, float eps, float* inv_norm, void* stream) {
+  JMT_REQUIRE(x && out && nseq >= 0 && seq_len > 0 && row0 >= 0 && seq_rows >= row0 + seq_len && D > 0 && D % 8 == 0 && in_ld % 8 == 0,
+              "jmt_l2norm_fwd_seq: bad arguments");
+  const int64_t rows = nseq * seq_len;
+  if (rows == 0) return JMT_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  JMT_DISPATCH_DTYPE(in_dtype, TI, JMT_DISPATCH_DTYPE(out_dtype, TO,
+      (l2norm_fwd_kernel<TI, TO><<<row_grid(rows), kRowThreads, 0, st>>>((const TI*)x, in_ld, (TO*)out, rows, D, eps, inv_norm, seq_len, seq_rows, row0))));
   return check_launch("l2norm_fwd_kernel");
 }
 
@@ -260,7 +291,21 @@ extern "C" int jmt_l2norm_bwd(const void* dy, const void* y, int dtype, const fl
   if (rows == 0) return JMT_OK;
   cudaStream_t st = (cudaStream_t)stream;
   JMT_DISPATCH_DTYPE(dtype, T, JMT_DISPATCH_DTYPE(dx_dtype, TO,
-      (l2norm_bwd_kernel<T, TO><<<row_grid(rows), kRowThreads, 0, st>>>((const T*)dy, (const T*)y, inv_norm, eps, (TO*)dx, rows, D))));
+      (l2norm_bwd_kernel<T, TO><<<row_grid(rows), kRowThreads, 0, st>>>((const T*)dy, (const T*)y, inv_norm, eps, (TO*)dx, rows, D, 0, 0, 0))));
+  return check_launch("l2norm_bwd_kernel");
+}
+
+extern "C" int jmt_l2norm_bwd_seq(const void* dy, const void* y, int dtype, const float* inv_norm, float eps, void* dx, int dx_dtype,
+                                  int64_t nseq, int seq_len, int seq_rows, int row0, int D, void* stream) {
+  JMT_REQUIRE(dy && y && inv_norm && dx && nseq >= 0 && seq_len > 0 && row0 >= 0 && seq_rows >= row0 + seq_len && D > 0 && D % 8 == 0,
+              "jmt_l2norm_bwd_seq: bad arguments");
+  JMT_REQUIRE(seq_rows == row0 + seq_len, "jmt_l2norm_bwd_seq: rows behind a sequence are not supported (they would stay unwritten)");
+  const int64_t rows = nseq * seq_len;
+  if (rows == 0) return JMT_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  JMT_DISPATCH_DTYPE(dtype, T, JMT_DISPATCH_DTYPE(dx_dtype, TO,
+      (l2norm_bwd_kernel<T, TO><<<row_grid(nseq * seq_rows), kRowThreads, 0, st>>>((const T*)dy, (const T*)y, inv_norm, eps, (TO*)dx, rows, D,
+                                                                                   seq_len, seq_rows, row0))));
   return check_launch("l2norm_bwd_kernel");
 }
 

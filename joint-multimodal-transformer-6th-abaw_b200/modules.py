@@ -719,8 +719,8 @@ class JMTPipeline(_JmtModule):
                 pad = E.tcn_pad(specs)
                 h, gv = E.transpose_in(ctx, vis, vis.requires_grad, pad)
                 h = _tcn_graph(ctx, h, "tcn.", specs, N, Ls, pad)
-                h = E.unpad_rows(ctx, h, N, Ls, pad)                              # (B*T, 512) == transpose(1,2)
-                video_n = _l2norm_var(ctx, h)
+                # (B*T, 512) == transpose(1, 2), normalised: read straight from / differentiated straight into the padded layout
+                video_n = _l2norm_var(ctx, h, seq=(N, Ls, pad)) if pad > 0 else _l2norm_var(ctx, h)
             else:
                 video_n, gv = E.l2norm(ctx, vis, vis.requires_grad)
             # Backward runs the tape in reverse: everything recorded after this point (the fusion) is done when this entry
@@ -733,21 +733,36 @@ class JMTPipeline(_JmtModule):
         return v, a
 
 
-def _l2norm_var(ctx, x):
-    """F.normalize on an activation Var (rows, D) staying in the activation dtype."""
-    rows, D = x.data.shape
+def _l2norm_var(ctx, x, seq=None):
+    """F.normalize on an activation Var (rows, D) staying in the activation dtype.  seq = (N, L, pad): x is the TCN's flat padded
+    layout (N * (pad + L) rows); the result is compact (N * L rows, row = n*L + t) -- `E.unpad_rows` fused in, forward and backward."""
+    D = x.data.shape[1]
+    if seq is not None:
+        N, Ls, pad = seq
+        rows = N * Ls
+        assert x.data.shape[0] == N * (Ls + pad) and x.data.is_contiguous()
+    else:
+        rows = x.data.shape[0]
     out = ctx.empty((rows, D))
     inv = ctx.empty((rows,), torch.float32) if ctx.record else None
-    L.check(ctx.lib.jmt_l2norm_fwd(E._ptr(x.data), ctx.acode, x.data.stride(0), E._ptr(out), ctx.acode, rows, D, 1e-12,
-                                   E._ptr(inv), E._stream()), "jmt_l2norm_fwd")
+    if seq is not None:
+        L.check(ctx.lib.jmt_l2norm_fwd_seq(E._ptr(x.data), ctx.acode, x.data.stride(0), E._ptr(out), ctx.acode, N, Ls, Ls + pad, pad, D,
+                                           1e-12, E._ptr(inv), E._stream()), "jmt_l2norm_fwd_seq")
+    else:
+        L.check(ctx.lib.jmt_l2norm_fwd(E._ptr(x.data), ctx.acode, x.data.stride(0), E._ptr(out), ctx.acode, rows, D, 1e-12,
+                                       E._ptr(inv), E._stream()), "jmt_l2norm_fwd")
     y = E.Var(out)
     if ctx.record:
         def bwd():
             if y.grad is None:
                 return
-            gb = E.GradBuf(ctx.empty((rows, D)))         # straight into the activation dtype (no fp32 round trip)
-            L.check(ctx.lib.jmt_l2norm_bwd(E._ptr(y.grad), E._ptr(out), ctx.acode, E._ptr(inv), 1e-12, E._ptr(gb.t), ctx.acode, rows, D,
-                                           E._stream()), "jmt_l2norm_bwd")
+            gb = E.GradBuf(ctx.empty(x.data.shape))      # straight into the activation dtype (no fp32 round trip)
+            if seq is not None:
+                L.check(ctx.lib.jmt_l2norm_bwd_seq(E._ptr(y.grad), E._ptr(out), ctx.acode, E._ptr(inv), 1e-12, E._ptr(gb.t), ctx.acode,
+                                                   N, Ls, Ls + pad, pad, D, E._stream()), "jmt_l2norm_bwd_seq")
+            else:
+                L.check(ctx.lib.jmt_l2norm_bwd(E._ptr(y.grad), E._ptr(out), ctx.acode, E._ptr(inv), 1e-12, E._ptr(gb.t), ctx.acode, rows, D,
+                                               E._stream()), "jmt_l2norm_bwd")
             ctx.add_grad(x, gb)
             gb.refs -= 1
             ctx.release(y)

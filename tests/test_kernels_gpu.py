@@ -588,6 +588,35 @@ def test_attn_bwd_dqkv_rejects_unsupported_geometry():
     assert L.lib().jmt_attn_bwd_dqkv_supported(C.byref(g)) == 1
 
 
+def test_l2norm_on_padded_tcn_layout():
+    """jmt_l2norm_fwd_seq / jmt_l2norm_bwd_seq (F.normalize reading from / differentiating into the TCN's flat padded layout) against
+    the compact kernels on the un-padded copy: bit-identical values, zero padding rows in dx, nothing written elsewhere."""
+    torch.manual_seed(3)
+    dev = torch.device("cuda")
+    lib = L.lib()
+    st = E._stream()
+    N, Ls, pad, D = 5, 37, 32, 512
+    Lp = Ls + pad
+    xp = torch.randn(N, Lp, D).to(torch.bfloat16)
+    xp[:, :pad] = 0
+    xc = xp[:, pad:].reshape(N * Ls, D).contiguous()
+    dy = torch.randn(N * Ls, D).to(torch.bfloat16)
+    xp_d, xc_d, dy_d = xp.to(dev), xc.to(dev), dy.to(dev)
+    out = [torch.empty(N * Ls, D, device=dev, dtype=torch.bfloat16) for _ in range(2)]
+    inv = [torch.empty(N * Ls, device=dev) for _ in range(2)]
+    L.check(lib.jmt_l2norm_fwd_seq(E._ptr(xp_d), L.BF16, D, E._ptr(out[0]), L.BF16, N, Ls, Lp, pad, D, 1e-12, E._ptr(inv[0]), st), "fwd_seq")
+    L.check(lib.jmt_l2norm_fwd(E._ptr(xc_d), L.BF16, D, E._ptr(out[1]), L.BF16, N * Ls, D, 1e-12, E._ptr(inv[1]), st), "fwd")
+    torch.cuda.synchronize()
+    assert torch.equal(out[0], out[1]) and torch.equal(inv[0], inv[1])
+    dxp = torch.full((N, Lp, D), 9.0, device=dev, dtype=torch.bfloat16)
+    dxc = torch.empty(N * Ls, D, device=dev, dtype=torch.bfloat16)
+    L.check(lib.jmt_l2norm_bwd_seq(E._ptr(dy_d), E._ptr(out[0]), L.BF16, E._ptr(inv[0]), 1e-12, E._ptr(dxp), L.BF16, N, Ls, Lp, pad, D, st), "bwd_seq")
+    L.check(lib.jmt_l2norm_bwd(E._ptr(dy_d), E._ptr(out[1]), L.BF16, E._ptr(inv[1]), 1e-12, E._ptr(dxc), L.BF16, N * Ls, D, st), "bwd")
+    torch.cuda.synchronize()
+    assert torch.equal(dxp[:, pad:].reshape(N * Ls, D), dxc)
+    assert (dxp[:, :pad] == 0).all()
+
+
 @pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
 def test_layernorm_l2norm_softmax(dt):
     torch.manual_seed(0)
