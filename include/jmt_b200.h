@@ -316,6 +316,13 @@ int jmt_colsum(const void* x, int dtype, int64_t ld, int64_t rows, int cols, flo
  * dy/y/dx contiguous (rows, cols), cols % 8 == 0; mask (rows / L, cols) uint8 nullable; colsum fp32 nullable. */
 int jmt_act_bwd_fused(const void* dy, const void* y, const uint8_t* mask, void* dx, int64_t rows, int cols, int L,
                       float scale, float slope, float* colsum, int dtype, void* stream);
+/* Backward of out = act(a + b) fused with the backward of a = act2(pre) [* channel keep-mask * scale] (the TemporalBlock residual
+ * LeakyReLU together with conv2's LeakyReLU + Dropout2d, temporal_convolutional_model.py:54-57, 35-36):
+ *   dz = dy * act'(out)  (gradient of both a and b);  dz2 = dz * [mask(r / L, c) ? scale : 0] * act2'(a);  colsum[c] += sum_r dz2(r, c).
+ * One pass instead of jmt_act_bwd + jmt_act_bwd_fused; results are bit-identical to that sequence.  cols % 8 == 0, 16-byte aligned. */
+int jmt_add_act_bwd_fused(const void* dy, const void* out, const void* a, const uint8_t* mask, void* dz, void* dz2,
+                          int64_t rows, int cols, int L, float scale, float slope, float slope2, float* colsum, int dtype,
+                          void* stream);
 /* out = cast(in) */
 int jmt_cast(const void* in, int in_dtype, void* out, int out_dtype, int64_t n, void* stream);
 /* dst[e][i] = bf16(src[e][i]), i < n[e], for `count` tensors in one launch (HOST arrays of device pointers, 16-byte aligned):

@@ -106,6 +106,7 @@ SIGNATURES = {
     "jmt_act_bwd": [_P, _P, _P, _L, _F, _I, _P],
     "jmt_colsum": [_P, _I, _L, _L, _I, _P, _P],
     "jmt_act_bwd_fused": [_P, _P, _P, _P, _L, _I, _I, _F, _F, _P, _I, _P],
+    "jmt_add_act_bwd_fused": [_P, _P, _P, _P, _P, _P, _L, _I, _I, _F, _F, _F, _P, _I, _P],
     "jmt_cast": [_P, _I, _P, _I, _L, _P],
     "jmt_axpy": [_P, _P, _F, _L, _I, _P],
     "jmt_cast_multi": [_I, _P, _P, _P, _P],

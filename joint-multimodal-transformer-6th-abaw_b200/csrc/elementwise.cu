@@ -272,6 +272,61 @@ act_bwd_fused_kernel(const T* __restrict__ dy, const T* __restrict__ y, const ui
   }
 }
 
+// Backward of out = act(a + b) fused with the backward of a = act2(pre) [* channel-dropout mask] (TemporalBlock: the residual LeakyReLU
+// and conv2's LeakyReLU + Dropout2d, temporal_convolutional_model.py:54-57, 35-36):
+//   dz  = dy * act'(out)                      -> gradient of b (the residual branch) and of a
+//   dz2 = dz * [mask * scale] * act2'(a)      -> gradient of conv2's pre-activation;  colsum += column sums of dz2 (conv2's bias gradient)
+// One pass (3 reads, 2 writes) instead of act_bwd (2 + 1) followed by act_bwd_fused (2 + 1).  Same block shape as act_bwd_fused_kernel.
+template <typename T>
+__global__ void __launch_bounds__(256)
+add_act_bwd_fused_kernel(const T* __restrict__ dy, const T* __restrict__ out, const T* __restrict__ a, const uint8_t* __restrict__ mask,
+                         T* __restrict__ dz, T* __restrict__ dz2, int64_t rows, int cols, int L, float scale, float slope, float slope2,
+                         float* __restrict__ colsum) {
+  __shared__ float sh[8][257];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  const int c0 = blockIdx.x * 256 + tx * 8;
+  if (c0 < cols) {
+    const int64_t rs = (int64_t)gridDim.y * 8;
+    for (int64_t r = (int64_t)blockIdx.y * 8 + ty; r < rows; r += rs) {
+      Vec8<T> g, o, y2;
+      g.load(dy + r * cols + c0); o.load(out + r * cols + c0); y2.load(a + r * cols + c0);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) g.v[k] = o.v[k] > 0.f ? g.v[k] : g.v[k] * slope;
+      g.store(dz + r * cols + c0);
+      // (dz2 continues from the ROUNDED dz, as the two-kernel path does: bit-identical results)
+      Vec8<T> h;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) h.v[k] = to_f32(from_f32<T>(g.v[k]));
+      if (mask) {
+        const uint2 mk = *reinterpret_cast<const uint2*>(mask + (r / L) * cols + c0);
+        const uint8_t* mb = reinterpret_cast<const uint8_t*>(&mk);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) h.v[k] = mb[k] ? h.v[k] * scale : 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        h.v[k] = y2.v[k] > 0.f ? h.v[k] : h.v[k] * slope2;
+        acc[k] += h.v[k];
+      }
+      h.store(dz2 + r * cols + c0);
+    }
+  }
+  if (colsum == nullptr) return;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sh[ty][tx * 8 + i] = acc[i];
+  __syncthreads();
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += sh[i][threadIdx.x];
+    atomicAdd(colsum + c, t);
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kEwThreads)
 apply_mask_kernel(const T* __restrict__ x, const uint8_t* __restrict__ mask, T* __restrict__ out, int64_t total, int L,
@@ -784,6 +839,24 @@ extern "C" int jmt_act_bwd_fused(const void* dy, const void* y, const uint8_t* m
   JMT_DISPATCH_DTYPE(dtype, T, (act_bwd_fused_kernel<T><<<dim3(gx, gy), 256, 0, (cudaStream_t)stream>>>(
       (const T*)dy, (const T*)y, mask, (T*)dx, rows, cols, L, scale, slope, colsum)));
   return check_launch("act_bwd_fused_kernel");
+}
+
+extern "C" int jmt_add_act_bwd_fused(const void* dy, const void* out, const void* a, const uint8_t* mask, void* dz, void* dz2,
+                                     int64_t rows, int cols, int L, float scale, float slope, float slope2, float* colsum, int dtype,
+                                     void* stream) {
+  JMT_REQUIRE(dy && out && a && dz && dz2 && rows >= 0 && cols > 0 && cols % 8 == 0 && L >= 1, "jmt_add_act_bwd_fused: bad arguments (cols %% 8)");
+  JMT_REQUIRE(((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(a) |
+                reinterpret_cast<uintptr_t>(dz) | reinterpret_cast<uintptr_t>(dz2)) & 15) == 0 && (reinterpret_cast<uintptr_t>(mask) & 7) == 0,
+              "jmt_add_act_bwd_fused: pointers must be 16-byte aligned");
+  if (rows == 0) return JMT_OK;
+  const int gx = (cols + 255) / 256;
+  int gy = (int)((rows + 63) / 64);
+  const int cap = (kNumSMs * 8 + gx - 1) / gx;
+  if (gy > cap) gy = cap;
+  if (gy < 1) gy = 1;
+  JMT_DISPATCH_DTYPE(dtype, T, (add_act_bwd_fused_kernel<T><<<dim3(gx, gy), 256, 0, (cudaStream_t)stream>>>(
+      (const T*)dy, (const T*)out, (const T*)a, mask, (T*)dz, (T*)dz2, rows, cols, L, scale, slope, slope2, colsum)));
+  return check_launch("add_act_bwd_fused_kernel");
 }
 
 extern "C" int jmt_apply_mask(const void* x, const uint8_t* mask, void* out, int64_t nb, int L, int C, int per_channel,

@@ -110,7 +110,8 @@ class Var:
       fold         : (slope, mask, mask_scale, mask_rows) when this Var is act(pre) [* channel-dropout mask] and its only
                      consumer is a GEMM: that GEMM's dgrad epilogue multiplies by act'(data) (and the mask), so the gradient
                      buffer holds d(pre) (``folded``) and no act-bwd pass runs."""
-    __slots__ = ("data", "gbuf", "needs_grad", "track_colsum", "colsum_tmp", "colsum_ok", "fold", "folded", "colsum_direct")
+    __slots__ = ("data", "gbuf", "needs_grad", "track_colsum", "colsum_tmp", "colsum_ok", "fold", "folded", "colsum_direct",
+                 "act_pending", "act_done")
 
     def __init__(self, data: torch.Tensor, needs_grad: bool = True):
         self.data = data
@@ -122,6 +123,10 @@ class Var:
         self.fold: Optional[tuple] = None
         self.folded = False
         self.colsum_direct: Optional[Callable[[], torch.Tensor]] = None   # getter of the bias-gradient slice the writers add into
+        # (slope, mask, mask_rows, mask_scale, bias-gradient getter) of a conv output whose activation / dropout backward may be taken
+        # over by its only consumer (add_act, a_exclusive): act_done is then set and the gradient buffer holds d(pre-activation)
+        self.act_pending: Optional[tuple] = None
+        self.act_done = False
 
     @property
     def grad(self) -> Optional[torch.Tensor]:
@@ -800,6 +805,7 @@ FUSED_ATTENTION = True      # bf16 mode: True = QK^T -> softmax -> PV in one ker
 _EPI_MODE = int(os.environ.get("JMT_EPI_EXT", "1"))
 EPI_EXT = _EPI_MODE >= 1
 EPI_COLSUM = _EPI_MODE >= 2
+ADD_ACT_FUSED_BWD = os.environ.get("JMT_ADD_ACT_FUSED", "1") != "0"     # TemporalBlock: residual-ReLU backward fused with conv2's activation backward
 ATTN_DELTA_IN_KERNEL = os.environ.get("JMT_ATTN_DELTA", "1") != "0"   # softmax-backward delta = rowsum(P o dP) inside the dS kernel
 LONG_S_CHUNKED = True       # forward-only attention beyond the fused kernel's key limit: chunked fused kernel + log-sum-exp merge
 LONG_S_CHUNK_MIN_BYTES = 2 << 30   # ... once the fp32 score tensor of the composed path would exceed this (measured: NONE eval at
@@ -1440,6 +1446,8 @@ def causal_conv(ctx: Ctx, x: Var, prefix: str, N: int, Ls: int, cin: int, cout: 
         out.track_colsum = True
         if EPI_COLSUM:
             out.colsum_direct = lambda: ctx.pgrad(prefix + "bias")
+    if ctx.record and out.fold is None and (act != L.ACT_NONE or mask is not None) and cout % 8 == 0 and (mask is None or fuse_mask):
+        out.act_pending = (LEAKY_SLOPE if act != L.ACT_NONE else 1.0, mask, Lp, mscale, lambda: ctx.pgrad(prefix + "bias"))
     if ctx.record:
         def bwd():
             dy = out.grad
@@ -1448,7 +1456,9 @@ def causal_conv(ctx: Ctx, x: Var, prefix: str, N: int, Ls: int, cin: int, cout: 
             assert dy.is_contiguous()
             # where a channel was dropped y = 0 and the masked dy is 0, so act'(y) of the post-dropout y is exact;
             # padding rows of dy are zero (every producer keeps them so) and stay zero
-            if out.folded:
+            if out.act_done:
+                pass        # dy is d(pre-activation) already and the bias gradient has been summed (add_act's fused backward)
+            elif out.folded:
                 # dy is d(pre-activation) already (consumer's dgrad epilogue); its column sums = the bias gradient
                 if out.colsum_direct is None:
                     L.check(ctx.lib.jmt_colsum(_ptr(dy), _DT[dy.dtype], cout, R, cout, _ptr(ctx.pgrad(prefix + "bias")), _stream()), "jmt_colsum")
@@ -1480,8 +1490,11 @@ def causal_conv(ctx: Ctx, x: Var, prefix: str, N: int, Ls: int, cin: int, cout: 
     return out
 
 
-def add_act(ctx: Ctx, a: Var, b: Var, act: int, slope: float) -> Var:
-    """act(a + b)  (TemporalBlock residual, temporal_convolutional_model.py:54-57)."""
+def add_act(ctx: Ctx, a: Var, b: Var, act: int, slope: float, a_exclusive: bool = False) -> Var:
+    """act(a + b)  (TemporalBlock residual, temporal_convolutional_model.py:54-57).
+    a_exclusive: the caller guarantees that this op is the ONLY consumer of `a`; when `a` is a conv output with a pending
+    activation / channel-dropout backward (Var.act_pending), one fused pass then produces d(b) and d(pre-activation of a) together
+    with that conv's bias gradient (jmt_add_act_bwd_fused) instead of jmt_act_bwd followed by jmt_act_bwd_fused."""
     assert a.data.is_contiguous() and b.data.is_contiguous()
     y = ctx.empty(a.data.shape)
     L.check(ctx.lib.jmt_add_act(_ptr(a.data), _ptr(b.data), _ptr(y), y.numel(), act, slope, ctx.acode, _stream()), "jmt_add_act")
@@ -1492,8 +1505,20 @@ def add_act(ctx: Ctx, a: Var, b: Var, act: int, slope: float) -> Var:
             if dy is None:
                 return
             dz = GradBuf(ctx.empty(y.shape))
-            L.check(ctx.lib.jmt_act_bwd(_ptr(dy), _ptr(y), _ptr(dz.t), y.numel(), slope, ctx.acode, _stream()), "jmt_act_bwd")
-            ctx.add_grad(a, dz)
+            pend = a.act_pending if (a_exclusive and a.gbuf is None and a.needs_grad and a is not b and act != L.ACT_NONE and
+                                     dy.is_contiguous() and ADD_ACT_FUSED_BWD) else None
+            if pend is not None:
+                slope2, mask, mrows, mscale, bias_grad = pend
+                dz2 = GradBuf(ctx.empty(y.shape))
+                rows, cols = y.shape
+                L.check(ctx.lib.jmt_add_act_bwd_fused(_ptr(dy), _ptr(y), _ptr(a.data), _ptr(mask), _ptr(dz.t), _ptr(dz2.t), rows, cols,
+                                                      mrows, mscale, slope, slope2, _ptr(bias_grad()), ctx.acode, _stream()),
+                        "jmt_add_act_bwd_fused")
+                a.gbuf = dz2                       # d(pre-activation) of the conv that produced a: its backward skips the activation pass
+                a.act_done = True
+            else:
+                L.check(ctx.lib.jmt_act_bwd(_ptr(dy), _ptr(y), _ptr(dz.t), y.numel(), slope, ctx.acode, _stream()), "jmt_act_bwd")
+                ctx.add_grad(a, dz)
             ctx.add_grad(b, dz)
             dz.refs -= 1
             ctx.release(out)

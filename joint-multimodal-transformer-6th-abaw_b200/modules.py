@@ -670,7 +670,7 @@ def _tcn_graph(ctx, h, prefix, specs, N, Ls, pad):
                           keep_mask=m1)
         y = E.causal_conv(ctx, y, pre + "conv2.", N, Ls, cout, cout, k, d, L.ACT_LEAKY, drop_p=p, pad=pad, weights=w2, keep_mask=m2)
         res = _conv1x1(ctx, h, pre + "downsample.", (Ls + pad, pad)) if has_ds else h
-        h = E.add_act(ctx, y, res, L.ACT_LEAKY, E.LEAKY_SLOPE)
+        h = E.add_act(ctx, y, res, L.ACT_LEAKY, E.LEAKY_SLOPE, a_exclusive=True)      # y (conv2's output) has no other consumer
     return h
 
 

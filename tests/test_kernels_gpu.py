@@ -588,6 +588,34 @@ def test_attn_bwd_dqkv_rejects_unsupported_geometry():
     assert L.lib().jmt_attn_bwd_dqkv_supported(C.byref(g)) == 1
 
 
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("with_mask", [False, True])
+def test_add_act_bwd_fused(dt, with_mask):
+    """jmt_add_act_bwd_fused (residual LeakyReLU backward + conv2's LeakyReLU / Dropout2d backward + bias gradient in one pass) is
+    bit-identical to jmt_act_bwd followed by jmt_act_bwd_fused."""
+    torch.manual_seed(11)
+    dev = torch.device("cuda")
+    lib = L.lib()
+    st = E._stream()
+    code = L.BF16 if dt == torch.bfloat16 else L.F32
+    N, Lp, C = 3, 45, 264
+    rows = N * Lp
+    dy = torch.randn(rows, C).to(dt).to(dev)
+    out = torch.randn(rows, C).to(dt).to(dev)
+    a = torch.randn(rows, C).to(dt).to(dev)
+    mask = (torch.rand(N, C) > 0.3).to(torch.uint8).to(dev) if with_mask else None
+    scale, slope, slope2 = 1.0 / 0.7, 0.01, 0.02
+    dz_ref = torch.empty_like(dy); dz2_ref = torch.empty_like(dy); cs_ref = torch.zeros(C, device=dev)
+    L.check(lib.jmt_act_bwd(E._ptr(dy), E._ptr(out), E._ptr(dz_ref), dy.numel(), slope, code, st), "act_bwd")
+    L.check(lib.jmt_act_bwd_fused(E._ptr(dz_ref), E._ptr(a), E._ptr(mask), E._ptr(dz2_ref), rows, C, Lp, scale, slope2, E._ptr(cs_ref), code, st), "fused")
+    dz = torch.empty_like(dy); dz2 = torch.empty_like(dy); cs = torch.zeros(C, device=dev)
+    L.check(lib.jmt_add_act_bwd_fused(E._ptr(dy), E._ptr(out), E._ptr(a), E._ptr(mask), E._ptr(dz), E._ptr(dz2), rows, C, Lp, scale, slope,
+                                      slope2, E._ptr(cs), code, st), "add_act_bwd_fused")
+    torch.cuda.synchronize()
+    assert torch.equal(dz, dz_ref) and torch.equal(dz2, dz2_ref)
+    assert (cs - cs_ref).abs().max() <= 1e-4 * (cs_ref.abs().max() + 1)          # (different summation order of the fp32 column sums)
+
+
 def test_l2norm_on_padded_tcn_layout():
     """jmt_l2norm_fwd_seq / jmt_l2norm_bwd_seq (F.normalize reading from / differentiating into the TCN's flat padded layout) against
     the compact kernels on the un-padded copy: bit-identical values, zero padding rows in dx, nothing written elsewhere."""
