@@ -154,13 +154,12 @@ class _JmtModule(nn.Module):
         dead = self._dead_prefixes()
         return [p for n, p in self.named_parameters() if not any(n.startswith(d) for d in dead)]
 
-    def _live_params_fast(self) -> List[nn.Parameter]:
-        """The live parameters in `_live_names()` order without walking the module tree on every call: the walk (named_parameters
-        over ~60 sub-modules) is cached as (owner module, attribute) pairs and each call only re-reads the attributes, so a
-        parameter that was re-assigned is still picked up; adding / removing sub-modules or parameters invalidates the cache through
-        the module count."""
+    def _live_slots(self):
+        """(name, owner module, attribute) of every live parameter in `_live_names()` order.  The walk over the module tree
+        (named_parameters over ~60 sub-modules, 1 ms per call) is cached; the module count invalidates the cache when sub-modules are
+        added or removed, and because the slots are re-read on every use a re-assigned Parameter is picked up without a re-walk."""
         n_mod = sum(1 for _ in self.modules())
-        cache = self.__dict__.get("_live_slots")
+        cache = self.__dict__.get("_live_slots_cache")
         if cache is None or cache[0] != n_mod:
             dead = self._dead_prefixes()
             slots, seen = [], set()
@@ -176,14 +175,14 @@ class _JmtModule(nn.Module):
             slots.sort(key=lambda s: order[s[0]])
             assert len(slots) == len(order), "live-parameter inventory mismatch"
             cache = (n_mod, slots)
-            self.__dict__["_live_slots"] = cache
-        return [mod._parameters[pname] for _, mod, pname in cache[1]]
+            self.__dict__["_live_slots_cache"] = cache
+        return cache[1]
+
+    def _live_params_fast(self) -> List[nn.Parameter]:
+        return [mod._parameters[pname] for _, mod, pname in self._live_slots()]
 
     def _live_names_fast(self) -> List[str]:
-        """`_live_names()` from the same cache (the order `_live_params_fast` returns)."""
-        if self.__dict__.get("_live_slots") is None:
-            self._live_params_fast()
-        return [n for n, _, _ in self.__dict__["_live_slots"][1]]
+        return [n for n, _, _ in self._live_slots()]
 
     def set_grad_sync(self, fn):
         """fn(flat_fp32_bucket) is called at the end of backward (data-parallel all-reduce hook)."""

@@ -286,3 +286,40 @@ def test_wgrad_split_fills_whole_waves():
         assert n / (units * ((n + units - 1) // units)) >= 0.94, (red, m_out, n_out, batch, sk)
     # short reductions are never split
     assert E.wgrad_split(500, 512, 512) == 1 and E.split_k_waves(64 * 15, 4) == 1
+
+
+def test_live_parameter_cache_follows_the_module():
+    """_JmtModule._live_params_fast (the per-call parameter lookup of the autograd bridge) returns the parameters in _live_names()
+    order, skips the constructed-but-dead ones, picks up a re-assigned Parameter without re-walking the module tree and
+    re-walks it when a sub-module is added."""
+    import torch
+    import jmt_b200
+    m = jmt_b200.Two_transformers(0.0, 0.0, 1, 1, "TRANSFORMER", "FC", 512, precision="fp32")
+    names = m._live_names()
+    sd = dict(m.named_parameters())
+    got = m._live_params_fast()
+    assert m._live_names_fast() == names and len(got) == len(names)
+    assert all(a is sd[n] for a, n in zip(got, names))
+    assert not any(n.startswith("mm_transformer.final_encoder.") for n in names)
+    # re-assigned parameter: same slot, new object
+    lin = m.mm_transformer.out_layer1
+    new_w = torch.nn.Parameter(lin.weight.detach().clone() * 2)
+    lin.weight = new_w
+    got2 = m._live_params_fast()
+    assert got2[names.index("mm_transformer.out_layer1.weight")] is new_w
+    # structural change: the cache is rebuilt
+    m.extra = torch.nn.Linear(4, 4)
+    names3 = m._live_names()
+    assert m._live_names_fast() == names3 and "extra.weight" in names3
+
+
+def test_dqkv_planning_predicate():
+    """engine.dqkv_geometry_ok mirrors jmt_attn_bwd_dqkv_supported (csrc/attn_bwd_tc.cu): the projections only promise bias-gradient
+    column sums from their writers where that kernel will run."""
+    import ctypes as C
+    from jmt_b200 import engine as E, _lib as L
+    lib = L.lib()
+    for dh, Lq, S, heads in ((512, 300, 300, 1), (256, 300, 123, 2), (512, 321, 300, 1), (64, 300, 300, 8), (256, 37, 37, 4), (256, 100, 100, 5)):
+        g = L.AttnBwdDesc()
+        g.Lq, g.S, g.dh, g.heads, g.NB, g.x_ld = Lq, S, dh, heads, 2, (S + 7) // 8 * 8
+        assert bool(lib.jmt_attn_bwd_dqkv_supported(C.byref(g))) == bool(E.dqkv_geometry_ok(dh, Lq, S, heads)), (dh, Lq, S, heads)
